@@ -1,0 +1,343 @@
+// extern "C" surface of libcarlb (declared in include/carlb.h).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "engine.h"
+
+namespace carlb {
+
+std::atomic<long long> g_launches{0};
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+Segment make_segment(const carlb_env* env, int act_dtype) {
+  Segment s{};
+  s.kind = env->kind;
+  s.n = env->n;
+  s.max_steps = env->max_steps;
+  s.autoreset = env->autoreset;
+  s.act_dtype = act_dtype;
+  s.global_offset = env->global_offset;
+  s.state = env->bufs.state;
+  s.ctx = env->bufs.ctx;
+  s.elapsed = env->bufs.elapsed;
+  s.sbt = env->bufs.sbt;
+  s.rng = env->bufs.rng;
+  s.obs = env->bufs.obs;
+  s.reward = env->bufs.reward;
+  s.terminated = env->bufs.terminated;
+  s.truncated = env->bufs.truncated;
+  s.final_obs = env->bufs.final_obs;
+  s.n_peers = env->n_peers;
+  for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
+  return s;
+}
+
+template <int KIND> static void fill_info(carlb_env_info_t* o) {
+  typedef Traits<KIND> Tr;
+  o->kind = KIND;
+  o->state_words = Tr::S;
+  o->obs_dim = Tr::D;
+  o->act_dim = Tr::A;
+  o->act_discrete = Tr::DISCRETE ? 1 : 0;
+  o->n_actions = Tr::N_ACTIONS;
+  o->n_param_rows = Tr::P;
+  o->n_step_rows = Tr::P_STEP;
+  o->default_max_steps = Tr::MAX_STEPS;
+  o->gym_reset_draws = Tr::GYM_DRAWS;
+  o->act_low = 0.0f;
+  o->act_high = (float)(Tr::N_ACTIONS - 1);
+  if (KIND == KIND_PENDULUM) { o->act_low = -2.0f; o->act_high = 2.0f; }
+  if (KIND == KIND_MOUNTAINCAR_CONT) { o->act_low = -1.0f; o->act_high = 1.0f; }
+}
+
+static bool is_classic(int kind) { return kind >= 0 && kind < KIND_CLASSIC_COUNT; }
+static bool is_brax(int kind) { return kind >= KIND_BRAX_ANT && kind <= KIND_BRAX_HOPPER; }
+
+static bool valid_act_dtype(const carlb_env* env, int act_dtype) {
+  carlb_env_info_t info;
+  if (carlb_query_env(env->kind, &info) != CARLB_OK) return false;
+  if (info.act_discrete) return act_dtype == CARLB_ACT_I32 || act_dtype == CARLB_ACT_I64 || act_dtype == CARLB_ACT_U8;
+  return act_dtype == CARLB_ACT_F32;
+}
+
+static int check_ready(const carlb_env* env, const char* what) {
+  if (env == nullptr) {
+    set_error("%s: null handle", what);
+    return CARLB_ERR_INVALID;
+  }
+  if (!env->bound) {
+    set_error("%s: carlb_env_bind() has not been called", what);
+    return CARLB_ERR_STATE;
+  }
+  return CARLB_OK;
+}
+
+}  // namespace carlb
+
+using namespace carlb;
+
+extern "C" {
+
+int carlb_abi_version(void) { return CARLB_ABI_VERSION; }
+const char* carlb_last_error(void) { return g_err; }
+int64_t carlb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int carlb_query_env(int kind, carlb_env_info_t* out) {
+  if (out == nullptr) {
+    set_error("carlb_query_env: null output");
+    return CARLB_ERR_INVALID;
+  }
+  memset(out, 0, sizeof(*out));
+  switch (kind) {
+    case KIND_CARTPOLE: fill_info<KIND_CARTPOLE>(out); return CARLB_OK;
+    case KIND_PENDULUM: fill_info<KIND_PENDULUM>(out); return CARLB_OK;
+    case KIND_ACROBOT: fill_info<KIND_ACROBOT>(out); return CARLB_OK;
+    case KIND_MOUNTAINCAR: fill_info<KIND_MOUNTAINCAR>(out); return CARLB_OK;
+    case KIND_MOUNTAINCAR_CONT: fill_info<KIND_MOUNTAINCAR_CONT>(out); return CARLB_OK;
+    default: break;
+  }
+  if (is_brax(kind)) return brax_query(kind, out);
+  set_error("carlb_query_env: unknown env kind %d", kind);
+  return CARLB_ERR_INVALID;
+}
+
+int carlb_env_create(int kind, int n_envs, int precision, int device, int64_t global_offset, carlb_env_t** out) {
+  if (out == nullptr) {
+    set_error("carlb_env_create: null output");
+    return CARLB_ERR_INVALID;
+  }
+  *out = nullptr;
+  carlb_env_info_t info;
+  if (carlb_query_env(kind, &info) != CARLB_OK) return CARLB_ERR_INVALID;
+  if (n_envs <= 0) {
+    set_error("carlb_env_create: n_envs must be positive, got %d", n_envs);
+    return CARLB_ERR_INVALID;
+  }
+  if (precision != CARLB_F32 && precision != CARLB_F64) {
+    set_error("carlb_env_create: unknown precision %d", precision);
+    return CARLB_ERR_INVALID;
+  }
+  if (is_brax(kind) && precision != CARLB_F32) {
+    set_error("carlb_env_create: Brax envs are float32 only (the reference's JAX pipeline is float32)");
+    return CARLB_ERR_INVALID;
+  }
+  int n_dev = 0;
+  CARLB_CUDA_CHECK(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    set_error("carlb_env_create: device %d out of range (%d visible)", device, n_dev);
+    return CARLB_ERR_INVALID;
+  }
+  carlb_env* env = new (std::nothrow) carlb_env();
+  if (env == nullptr) {
+    set_error("carlb_env_create: out of host memory");
+    return CARLB_ERR_STATE;
+  }
+  env->kind = kind;
+  env->n = n_envs;
+  env->precision = precision;
+  env->device = device;
+  env->max_steps = info.default_max_steps;
+  env->autoreset = is_brax(kind) ? CARLB_AUTORESET_SAME_STEP : CARLB_AUTORESET_NONE;
+  env->global_offset = (long long)global_offset;
+  if (is_brax(kind)) {
+    CARLB_CUDA_CHECK(cudaSetDevice(device));
+    const int rc = brax_create(env);
+    if (rc != CARLB_OK) {
+      delete env;
+      return rc;
+    }
+  }
+  *out = env;
+  return CARLB_OK;
+}
+
+int carlb_env_destroy(carlb_env_t* env) {
+  if (env == nullptr) return CARLB_OK;
+  if (is_brax(env->kind)) brax_destroy(env);
+  delete env;
+  return CARLB_OK;
+}
+
+int carlb_env_bind(carlb_env_t* env, const carlb_buffers_t* b) {
+  if (env == nullptr || b == nullptr) {
+    set_error("carlb_env_bind: null argument");
+    return CARLB_ERR_INVALID;
+  }
+  const bool need_sbt = env->kind == KIND_CARTPOLE;
+  if (!b->state || !b->ctx || !b->elapsed || !b->rng || !b->obs || !b->reward || !b->terminated || !b->truncated ||
+      (need_sbt && !b->sbt)) {
+    set_error("carlb_env_bind: a required buffer pointer is null");
+    return CARLB_ERR_INVALID;
+  }
+  if (is_brax(env->kind) && (!b->first_state || !b->first_obs)) {
+    set_error("carlb_env_bind: Brax handles need first_state / first_obs buffers");
+    return CARLB_ERR_INVALID;
+  }
+  if (((uintptr_t)b->state & 15u) || ((uintptr_t)b->obs & 15u) || ((uintptr_t)b->ctx & 7u) || ((uintptr_t)b->rng & 7u)) {
+    set_error("carlb_env_bind: state/obs must be 16-byte aligned, ctx/rng 8-byte aligned");
+    return CARLB_ERR_INVALID;
+  }
+  env->bufs = *b;
+  env->bound = true;
+  return CARLB_OK;
+}
+
+int carlb_env_configure(carlb_env_t* env, int max_episode_steps, int autoreset) {
+  if (env == nullptr) {
+    set_error("carlb_env_configure: null handle");
+    return CARLB_ERR_INVALID;
+  }
+  if (autoreset != CARLB_AUTORESET_NONE && autoreset != CARLB_AUTORESET_SAME_STEP) {
+    set_error("carlb_env_configure: unknown autoreset mode %d", autoreset);
+    return CARLB_ERR_INVALID;
+  }
+  if (max_episode_steps > 0) env->max_steps = max_episode_steps;
+  env->autoreset = autoreset;
+  return CARLB_OK;
+}
+
+int carlb_env_set_peers(carlb_env_t* env, int n_peers, float* const* peer_obs) {
+  if (env == nullptr || n_peers < 0 || n_peers > CARLB_MAX_PEERS || (n_peers > 0 && peer_obs == nullptr)) {
+    set_error("carlb_env_set_peers: bad arguments (n_peers=%d, max %d)", n_peers, CARLB_MAX_PEERS);
+    return CARLB_ERR_INVALID;
+  }
+  env->n_peers = n_peers;
+  for (int r = 0; r < n_peers; ++r) env->peer_obs[r] = peer_obs[r];
+  return CARLB_OK;
+}
+
+int carlb_env_seed(carlb_env_t* env, uint64_t seed, void* stream) {
+  int rc = check_ready(env, "carlb_env_seed");
+  if (rc != CARLB_OK) return rc;
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  if (is_brax(env->kind)) return brax_seed(env, seed, (cudaStream_t)stream);
+  return classic_seed(env, seed, (cudaStream_t)stream);
+}
+
+int carlb_env_reset(carlb_env_t* env, const uint8_t* mask, void* stream) {
+  int rc = check_ready(env, "carlb_env_reset");
+  if (rc != CARLB_OK) return rc;
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  if (is_brax(env->kind)) return brax_reset(env, mask, (cudaStream_t)stream);
+  return classic_reset(env, mask, (cudaStream_t)stream);
+}
+
+int carlb_env_step(carlb_env_t* env, const void* actions, int act_dtype, void* stream) {
+  int rc = check_ready(env, "carlb_env_step");
+  if (rc != CARLB_OK) return rc;
+  if (actions == nullptr || !valid_act_dtype(env, act_dtype)) {
+    set_error("carlb_env_step: null actions or action dtype %d not valid for env kind %d", act_dtype, env->kind);
+    return CARLB_ERR_INVALID;
+  }
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  if (is_brax(env->kind)) return brax_step(env, actions, act_dtype, (cudaStream_t)stream);
+  return classic_step(env, actions, act_dtype, (cudaStream_t)stream);
+}
+
+int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtype, float* obs_host, float* reward_host,
+                        uint8_t* terminated_host, uint8_t* truncated_host, void* stream) {
+  int rc = check_ready(env, "carlb_env_step_host");
+  if (rc != CARLB_OK) return rc;
+  if (actions_host == nullptr || !valid_act_dtype(env, act_dtype)) {
+    set_error("carlb_env_step_host: null actions or action dtype %d not valid for env kind %d", act_dtype, env->kind);
+    return CARLB_ERR_INVALID;
+  }
+  if (env->bufs.act_staging == nullptr) {
+    set_error("carlb_env_step_host: act_staging buffer was not bound");
+    return CARLB_ERR_STATE;
+  }
+  carlb_env_info_t info;
+  carlb_query_env(env->kind, &info);
+  cudaStream_t st = (cudaStream_t)stream;
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  const size_t esz = act_dtype == CARLB_ACT_I64 ? 8 : (act_dtype == CARLB_ACT_U8 ? 1 : 4);
+  const size_t n = (size_t)env->n;
+  CARLB_CUDA_CHECK(cudaMemcpyAsync(env->bufs.act_staging, actions_host, n * esz * (size_t)info.act_dim,
+                                   cudaMemcpyHostToDevice, st));
+  rc = is_brax(env->kind) ? brax_step(env, env->bufs.act_staging, act_dtype, st)
+                          : classic_step(env, env->bufs.act_staging, act_dtype, st);
+  if (rc != CARLB_OK) return rc;
+  if (obs_host)
+    CARLB_CUDA_CHECK(cudaMemcpyAsync(obs_host, env->bufs.obs, n * info.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (reward_host)
+    CARLB_CUDA_CHECK(cudaMemcpyAsync(reward_host, env->bufs.reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (terminated_host)
+    CARLB_CUDA_CHECK(cudaMemcpyAsync(terminated_host, env->bufs.terminated, n, cudaMemcpyDeviceToHost, st));
+  if (truncated_host)
+    CARLB_CUDA_CHECK(cudaMemcpyAsync(truncated_host, env->bufs.truncated, n, cudaMemcpyDeviceToHost, st));
+  CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return CARLB_OK;
+}
+
+int carlb_env_rollout(carlb_env_t* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                      int act_dtype, const carlb_traj_t* traj, void* stream) {
+  int rc = check_ready(env, "carlb_env_rollout");
+  if (rc != CARLB_OK) return rc;
+  if (n_steps < 0) {
+    set_error("carlb_env_rollout: negative n_steps");
+    return CARLB_ERR_INVALID;
+  }
+  if (actions != nullptr && !valid_act_dtype(env, act_dtype)) {
+    set_error("carlb_env_rollout: action dtype %d not valid for env kind %d", act_dtype, env->kind);
+    return CARLB_ERR_INVALID;
+  }
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  if (is_brax(env->kind))
+    return brax_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream);
+  return classic_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream);
+}
+
+int carlb_mixed_step(carlb_env_t* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,
+                     void* stream) {
+  if (envs == nullptr || actions == nullptr || act_dtypes == nullptr || n_handles <= 0 || n_handles > CARLB_MAX_MIXED) {
+    set_error("carlb_mixed_step: bad arguments (n_handles=%d, max %d)", n_handles, CARLB_MAX_MIXED);
+    return CARLB_ERR_INVALID;
+  }
+  for (int k = 0; k < n_handles; ++k) {
+    int rc = check_ready(envs[k], "carlb_mixed_step");
+    if (rc != CARLB_OK) return rc;
+    if (!is_classic(envs[k]->kind)) {
+      set_error("carlb_mixed_step: handle %d is not a classic-control shard", k);
+      return CARLB_ERR_INVALID;
+    }
+    if (envs[k]->device != envs[0]->device) {
+      set_error("carlb_mixed_step: all shards of one launch must live on one device");
+      return CARLB_ERR_INVALID;
+    }
+    if (actions[k] == nullptr || !valid_act_dtype(envs[k], act_dtypes[k])) {
+      set_error("carlb_mixed_step: bad actions for handle %d", k);
+      return CARLB_ERR_INVALID;
+    }
+  }
+  CARLB_CUDA_CHECK(cudaSetDevice(envs[0]->device));
+  return classic_mixed_step(envs, actions, act_dtypes, n_handles, (cudaStream_t)stream);
+}
+
+int carlb_brax_set_tunables(carlb_env_t* env, const float* values, int n_values) {
+  if (env == nullptr || values == nullptr || !is_brax(env->kind)) {
+    set_error("carlb_brax_set_tunables: needs a Brax handle and values");
+    return CARLB_ERR_INVALID;
+  }
+  return brax_set_tunables(env, values, n_values);
+}
+
+int carlb_brax_get_tunables(int kind, float* values, int max_values, int* n_values) {
+  if (!is_brax(kind) || n_values == nullptr) {
+    set_error("carlb_brax_get_tunables: needs a Brax kind");
+    return CARLB_ERR_INVALID;
+  }
+  return brax_get_tunables(kind, values, max_values, n_values);
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+// Classic-control kernels (sm_100a): one env instance per thread, state rows as 128-bit vector
+// loads, per-env context SoA rows (coalesced 32-/64-bit loads), everything else in registers.
+//
+// These kernels are HBM/L2-latency bound integer+fp32 work (a 4-float state and ~20-300 flops per
+// env-step): no tensor cores, no shared memory. Single-step launches implement the reference's
+// `CARLEnv.step` contract; the fused rollout keeps the state in registers across K steps and
+// streams the trajectory to HBM.
+#include <cuda_runtime.h>
+
+#include "engine.h"
+
+namespace carlb {
+
+constexpr int kBlock = 128;
+
+template <int D> __device__ __forceinline__ void store_obs(float* base, size_t row, const float* o) {
+  float* dst = base + row * D;
+  if (D == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+  } else if (D == 2) {
+    *reinterpret_cast<float2*>(dst) = make_float2(o[0], o[1]);
+  } else if (D == 6) {
+    float2* d2 = reinterpret_cast<float2*>(dst);
+    d2[0] = make_float2(o[0], o[1]); d2[1] = make_float2(o[2], o[3]); d2[2] = make_float2(o[4], o[5]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < D; ++k) dst[k] = o[k];
+  }
+}
+
+template <int KIND, typename T>
+__device__ __forceinline__ void load_rows(const Segment& seg, int i, int r0, int r1, T* p) {
+  const T* ctx = static_cast<const T*>(seg.ctx);
+#pragma unroll
+  for (int r = 0; r < Traits<KIND>::P; ++r)
+    if (r >= r0 && r < r1) p[r] = __ldg(ctx + (size_t)r * seg.n + i);
+}
+
+// ------------------------------------------------------------------------------ seed
+__global__ void __launch_bounds__(kBlock) seed_kernel(uint64_t* rng, int n, uint64_t seed, long long global_offset) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Pcg64 g;
+  pcg64_seed_from_int(g, seed + (uint64_t)global_offset + (uint64_t)i);
+  rng[i] = g.state_hi; rng[(size_t)n + i] = g.state_lo; rng[2 * (size_t)n + i] = g.inc_hi; rng[3 * (size_t)n + i] = g.inc_lo;
+}
+
+// ----------------------------------------------------------------------------- reset
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ Segment seg, const uint8_t* mask) {
+  typedef Traits<KIND> Tr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= seg.n) return;
+  if (mask != nullptr && mask[i] == 0) return;
+  T p[Tr::P];
+  load_rows<KIND, T>(seg, i, Tr::P_STEP, Tr::P, p);
+  Pcg64 g = load_rng(seg.rng, seg.n, i);
+#pragma unroll
+  for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_advance1(g);  // gymnasium's own (discarded) draws
+  T s[Tr::S];
+  float o[Tr::D];
+  env_reset<KIND, T>(s, p, g, o);
+  store_rng_state(seg.rng, seg.n, i, g);
+  StateIO<T, Tr::S>::store(seg.state, i, s);
+  store_obs<Tr::D>(seg.obs, (size_t)i, o);
+  for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+  seg.elapsed[i] = 0;
+  if (KIND == KIND_CARTPOLE) seg.sbt[i] = 0;
+  seg.reward[i] = 0.0f;
+  seg.terminated[i] = 0;
+  seg.truncated[i] = 0;
+}
+
+// ------------------------------------------------------------------------------ step
+template <int KIND, typename T>
+__device__ __forceinline__ void step_one(const Segment& seg, const void* actions, int i) {
+  typedef Traits<KIND> Tr;
+  T s[Tr::S];
+  StateIO<T, Tr::S>::load(seg.state, i, s);
+  T p[Tr::P];
+  load_rows<KIND, T>(seg, i, 0, Tr::P_STEP, p);
+  const Action a = load_action(actions, seg.act_dtype, (long long)i);
+  int el = seg.elapsed[i];
+  uint8_t sb = 0;
+  if (KIND == KIND_CARTPOLE) sb = seg.sbt[i];
+
+  Pcg64 g;
+  bool rng_live = false;
+  T noise = (T)0;
+  if (KIND == KIND_ACROBOT) {
+    if (p[AC_NOISE] > (T)0) {  // env RNG draw, as AcrobotEnv.step does
+      g = load_rng(seg.rng, seg.n, i);
+      rng_live = true;
+      noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
+    }
+  }
+  float o[Tr::D];
+  const StepOut so = env_step<KIND, T>(s, p, a, noise, sb, o);
+  el += 1;
+  const bool tr = seg.max_steps > 0 && el >= seg.max_steps;
+  if (seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr)) {
+    if (seg.final_obs != nullptr) store_obs<Tr::D>(seg.final_obs, (size_t)i, o);
+    load_rows<KIND, T>(seg, i, Tr::P_STEP, Tr::P, p);
+    if (!rng_live) g = load_rng(seg.rng, seg.n, i);
+    rng_live = true;
+#pragma unroll
+    for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_advance1(g);
+    env_reset<KIND, T>(s, p, g, o);
+    el = 0;
+    sb = 0;
+  }
+  if (rng_live) store_rng_state(seg.rng, seg.n, i, g);
+  StateIO<T, Tr::S>::store(seg.state, i, s);
+  store_obs<Tr::D>(seg.obs, (size_t)i, o);
+  for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+  seg.reward[i] = so.reward;
+  seg.terminated[i] = so.terminated ? 1 : 0;
+  seg.truncated[i] = tr ? 1 : 0;
+  seg.elapsed[i] = el;
+  if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
+}
+
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Segment seg, const void* actions) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= seg.n) return;
+  step_one<KIND, T>(seg, actions, i);
+}
+
+// ----------------------------------------------------------------------- mixed batch
+struct MixedParams {
+  int n_seg;
+  int block_start[CARLB_MAX_MIXED + 1];
+  int precision[CARLB_MAX_MIXED];
+  const void* actions[CARLB_MAX_MIXED];
+  Segment seg[CARLB_MAX_MIXED];
+};
+
+template <typename T>
+__device__ __forceinline__ void mixed_dispatch(const Segment& seg, const void* actions, int i) {
+  switch (seg.kind) {
+    case KIND_CARTPOLE: step_one<KIND_CARTPOLE, T>(seg, actions, i); break;
+    case KIND_PENDULUM: step_one<KIND_PENDULUM, T>(seg, actions, i); break;
+    case KIND_ACROBOT: step_one<KIND_ACROBOT, T>(seg, actions, i); break;
+    case KIND_MOUNTAINCAR: step_one<KIND_MOUNTAINCAR, T>(seg, actions, i); break;
+    default: step_one<KIND_MOUNTAINCAR_CONT, T>(seg, actions, i); break;
+  }
+}
+
+// One launch for several homogeneous shards: whole blocks belong to one shard, so the kind
+// switch is block-uniform (no divergence).
+__global__ void __launch_bounds__(kBlock) mixed_step_kernel(const __grid_constant__ MixedParams mp) {
+  int k = 0;
+  while (k + 1 < mp.n_seg && (int)blockIdx.x >= mp.block_start[k + 1]) ++k;
+  const Segment& seg = mp.seg[k];
+  const int i = ((int)blockIdx.x - mp.block_start[k]) * blockDim.x + threadIdx.x;
+  if (i >= seg.n) return;
+  if (mp.precision[k] == CARLB_F64) mixed_dispatch<double>(seg, mp.actions[k], i);
+  else mixed_dispatch<float>(seg, mp.actions[k], i);
+}
+
+// --------------------------------------------------------------------- fused rollout
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
+                                                         uint64_t policy_seed, uint32_t step_base, const void* actions,
+                                                         const carlb_traj_t traj) {
+  typedef Traits<KIND> Tr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = seg.n;
+  if (i >= n) return;
+  T s[Tr::S];
+  StateIO<T, Tr::S>::load(seg.state, i, s);
+  T p[Tr::P];
+  load_rows<KIND, T>(seg, i, 0, Tr::P, p);
+  Pcg64 g = load_rng(seg.rng, n, i);
+  int el = seg.elapsed[i];
+  uint8_t sb = 0;
+  if (KIND == KIND_CARTPOLE) sb = seg.sbt[i];
+  const uint64_t gid = (uint64_t)(seg.global_offset + i);
+  float o[Tr::D];
+  StepOut so;
+  so.reward = 0.0f;
+  so.terminated = false;
+  bool tr = false;
+#pragma unroll 1
+  for (int t = 0; t < n_steps; ++t) {
+    const size_t row = (size_t)t * n + i;
+    const Action a = (actions != nullptr) ? load_action(actions, seg.act_dtype, (long long)row)
+                                          : policy_action<KIND>(policy_seed, gid, step_base + (uint32_t)t);
+    T noise = (T)0;
+    if (KIND == KIND_ACROBOT) {
+      if (p[AC_NOISE] > (T)0) noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
+    }
+    so = env_step<KIND, T>(s, p, a, noise, sb, o);
+    el += 1;
+    tr = seg.max_steps > 0 && el >= seg.max_steps;
+    if (seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr)) {
+#pragma unroll
+      for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_advance1(g);
+      env_reset<KIND, T>(s, p, g, o);
+      el = 0;
+      sb = 0;
+    }
+    if (traj.obs != nullptr) store_obs<Tr::D>(traj.obs, row, o);
+    if (traj.actions != nullptr) {
+      if (Tr::DISCRETE) static_cast<int32_t*>(traj.actions)[row] = a.i;
+      else static_cast<float*>(traj.actions)[row] = a.f;
+    }
+    if (traj.reward != nullptr) traj.reward[row] = so.reward;
+    if (traj.done != nullptr) traj.done[row] = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0));
+  }
+  store_rng_state(seg.rng, n, i, g);
+  StateIO<T, Tr::S>::store(seg.state, i, s);
+  if (n_steps > 0) {
+    store_obs<Tr::D>(seg.obs, (size_t)i, o);
+    for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+    seg.reward[i] = so.reward;
+    seg.terminated[i] = so.terminated ? 1 : 0;
+    seg.truncated[i] = tr ? 1 : 0;
+  }
+  seg.elapsed[i] = el;
+  if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
+}
+
+// --------------------------------------------------------------------------- launchers
+#define CARLB_DISPATCH_KIND_T(KINDV, PREC, CALL)                                          \
+  switch ((KINDV) * 2 + ((PREC) == CARLB_F64 ? 1 : 0)) {                                  \
+    case KIND_CARTPOLE * 2: { constexpr int K_ = KIND_CARTPOLE; typedef float T_; CALL; } break;          \
+    case KIND_CARTPOLE * 2 + 1: { constexpr int K_ = KIND_CARTPOLE; typedef double T_; CALL; } break;     \
+    case KIND_PENDULUM * 2: { constexpr int K_ = KIND_PENDULUM; typedef float T_; CALL; } break;          \
+    case KIND_PENDULUM * 2 + 1: { constexpr int K_ = KIND_PENDULUM; typedef double T_; CALL; } break;     \
+    case KIND_ACROBOT * 2: { constexpr int K_ = KIND_ACROBOT; typedef float T_; CALL; } break;            \
+    case KIND_ACROBOT * 2 + 1: { constexpr int K_ = KIND_ACROBOT; typedef double T_; CALL; } break;       \
+    case KIND_MOUNTAINCAR * 2: { constexpr int K_ = KIND_MOUNTAINCAR; typedef float T_; CALL; } break;    \
+    case KIND_MOUNTAINCAR * 2 + 1: { constexpr int K_ = KIND_MOUNTAINCAR; typedef double T_; CALL; } break; \
+    case KIND_MOUNTAINCAR_CONT * 2: { constexpr int K_ = KIND_MOUNTAINCAR_CONT; typedef float T_; CALL; } break; \
+    case KIND_MOUNTAINCAR_CONT * 2 + 1: { constexpr int K_ = KIND_MOUNTAINCAR_CONT; typedef double T_; CALL; } break; \
+    default: set_error("unknown classic env kind %d", (int)(KINDV)); return CARLB_ERR_INVALID;           \
+  }
+
+static inline int grid_for(int n) { return (n + kBlock - 1) / kBlock; }
+
+int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
+  seed_kernel<<<grid_for(env->n), kBlock, 0, st>>>(env->bufs.rng, env->n, seed, env->global_offset);
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
+  const Segment seg = make_segment(env, CARLB_ACT_I32);
+  CARLB_DISPATCH_KIND_T(env->kind, env->precision, (reset_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, mask)));
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st) {
+  const Segment seg = make_segment(env, act_dtype);
+  CARLB_DISPATCH_KIND_T(env->kind, env->precision, (step_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, actions)));
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                    int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
+  const Segment seg = make_segment(env, act_dtype);
+  carlb_traj_t tj{};
+  if (traj != nullptr) tj = *traj;
+  // 64-thread blocks: at N = 65 536 that is 1024 blocks ~ 6.9 per SM (better tail balance over
+  // 148 SMs than 128-thread blocks for a long-running per-thread loop)
+  constexpr int kRolloutBlock = 64;
+  const int grid = (env->n + kRolloutBlock - 1) / kRolloutBlock;
+  CARLB_DISPATCH_KIND_T(env->kind, env->precision,
+                        (rollout_kernel<K_, T_><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
+                                                                                actions, tj)));
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int classic_mixed_step(carlb_env* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,
+                       cudaStream_t st) {
+  MixedParams mp{};
+  mp.n_seg = n_handles;
+  int blocks = 0;
+  for (int k = 0; k < n_handles; ++k) {
+    mp.block_start[k] = blocks;
+    mp.seg[k] = make_segment(envs[k], act_dtypes[k]);
+    mp.precision[k] = envs[k]->precision;
+    mp.actions[k] = actions[k];
+    blocks += grid_for(envs[k]->n);
+  }
+  mp.block_start[n_handles] = blocks;
+  mixed_step_kernel<<<blocks, kBlock, 0, st>>>(mp);
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+}  // namespace carlb

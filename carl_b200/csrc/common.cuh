@@ -1,0 +1,98 @@
+// Shared device-side declarations of libcarlb (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/carlb.h"
+#include "physics_classic.h"
+
+namespace carlb {
+
+// One homogeneous shard of env instances resident on this GPU. All pointers are device
+// pointers into caller-owned buffers (torch tensors); the library never allocates per step.
+struct Segment {
+  int kind;
+  int n;               // env instances in this shard
+  int max_steps;       // TimeLimit / EpisodeWrapper length (<=0: none)
+  int autoreset;       // 0: none (reference classic-control behaviour), 1: same-step auto-reset
+  int act_dtype;       // CARLB_ACT_*
+  long long global_offset;  // global env id of local env 0 (keys RNG streams; sharding-invariant)
+  void* state;         // T[n][S]
+  const void* ctx;     // T[P][n]
+  int32_t* elapsed;    // [n]
+  uint8_t* sbt;        // [n]  CartPole steps_beyond_terminated flag
+  uint64_t* rng;       // [4][n] PCG64 (state_hi, state_lo, inc_hi, inc_lo)
+  float* obs;          // [n][D]
+  float* reward;       // [n]
+  uint8_t* terminated; // [n]
+  uint8_t* truncated;  // [n]
+  float* final_obs;    // [n][D] or null
+  // fused cross-GPU observation gather: obs rows are additionally stored at
+  // peer_obs[r] + (global_offset + i) * D for every peer r (P2P-mapped symmetric buffers)
+  int n_peers;
+  float* peer_obs[CARLB_MAX_PEERS];
+};
+
+__device__ __forceinline__ Action load_action(const void* actions, int act_dtype, long long i) {
+  Action a;
+  a.i = 0;
+  a.f = 0.0f;
+  switch (act_dtype) {
+    case CARLB_ACT_I32: a.i = static_cast<const int32_t*>(actions)[i]; a.f = (float)a.i; break;
+    case CARLB_ACT_I64: a.i = (int)static_cast<const long long*>(actions)[i]; a.f = (float)a.i; break;
+    case CARLB_ACT_U8: a.i = (int)static_cast<const uint8_t*>(actions)[i]; a.f = (float)a.i; break;
+    default: a.f = static_cast<const float*>(actions)[i]; a.i = (int)a.f; break;
+  }
+  return a;
+}
+
+// 128-bit (or narrower) vector load / store of one env's S-word state row.
+template <typename T, int S> struct StateIO;
+template <> struct StateIO<float, 4> {
+  static __device__ __forceinline__ void load(const void* base, int i, float s[4]) {
+    const float4 v = static_cast<const float4*>(base)[i];
+    s[0] = v.x; s[1] = v.y; s[2] = v.z; s[3] = v.w;
+  }
+  static __device__ __forceinline__ void store(void* base, int i, const float s[4]) {
+    static_cast<float4*>(base)[i] = make_float4(s[0], s[1], s[2], s[3]);
+  }
+};
+template <> struct StateIO<float, 2> {
+  static __device__ __forceinline__ void load(const void* base, int i, float s[2]) {
+    const float2 v = static_cast<const float2*>(base)[i];
+    s[0] = v.x; s[1] = v.y;
+  }
+  static __device__ __forceinline__ void store(void* base, int i, const float s[2]) {
+    static_cast<float2*>(base)[i] = make_float2(s[0], s[1]);
+  }
+};
+template <> struct StateIO<double, 4> {
+  static __device__ __forceinline__ void load(const void* base, int i, double s[4]) {
+    const double2 a = static_cast<const double2*>(base)[2 * i], b = static_cast<const double2*>(base)[2 * i + 1];
+    s[0] = a.x; s[1] = a.y; s[2] = b.x; s[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(void* base, int i, const double s[4]) {
+    static_cast<double2*>(base)[2 * i] = make_double2(s[0], s[1]);
+    static_cast<double2*>(base)[2 * i + 1] = make_double2(s[2], s[3]);
+  }
+};
+template <> struct StateIO<double, 2> {
+  static __device__ __forceinline__ void load(const void* base, int i, double s[2]) {
+    const double2 a = static_cast<const double2*>(base)[i];
+    s[0] = a.x; s[1] = a.y;
+  }
+  static __device__ __forceinline__ void store(void* base, int i, const double s[2]) {
+    static_cast<double2*>(base)[i] = make_double2(s[0], s[1]);
+  }
+};
+
+__device__ __forceinline__ Pcg64 load_rng(const uint64_t* rng, int n, int i) {
+  Pcg64 g;
+  g.state_hi = rng[i]; g.state_lo = rng[(size_t)n + i]; g.inc_hi = rng[2 * (size_t)n + i]; g.inc_lo = rng[3 * (size_t)n + i];
+  return g;
+}
+__device__ __forceinline__ void store_rng_state(uint64_t* rng, int n, int i, const Pcg64& g) {
+  rng[i] = g.state_hi; rng[(size_t)n + i] = g.state_lo;  // the increment never changes
+}
+
+}  // namespace carlb

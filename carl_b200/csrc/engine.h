@@ -1,0 +1,62 @@
+// Internal host-side declarations shared by abi.cu / classic.cu / brax.cu.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+
+#include "common.cuh"
+
+struct carlb_env {
+  int kind = 0;
+  int n = 0;
+  int precision = CARLB_F32;
+  int device = 0;
+  int max_steps = 0;
+  int autoreset = CARLB_AUTORESET_NONE;
+  long long global_offset = 0;
+  bool bound = false;
+  carlb_buffers_t bufs{};
+  int n_peers = 0;
+  float* peer_obs[CARLB_MAX_PEERS] = {};
+  void* brax_sys = nullptr;  // device copy of the per-handle Brax system table
+  float brax_tunables[32] = {};
+  int brax_n_tunables = 0;
+};
+
+namespace carlb {
+
+extern std::atomic<long long> g_launches;
+void set_error(const char* fmt, ...);
+Segment make_segment(const carlb_env* env, int act_dtype);
+
+// classic.cu
+int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st);
+int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st);
+int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st);
+int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                    int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
+int classic_mixed_step(carlb_env* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,
+                       cudaStream_t st);
+
+// brax.cu
+int brax_query(int kind, carlb_env_info_t* out);
+int brax_create(carlb_env* env);
+void brax_destroy(carlb_env* env);
+int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st);
+int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st);
+int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st);
+int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                 int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
+int brax_set_tunables(carlb_env* env, const float* values, int n_values);
+int brax_get_tunables(int kind, float* values, int max_values, int* n_values);
+
+#define CARLB_CUDA_CHECK(expr)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      carlb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return CARLB_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+}  // namespace carlb

@@ -1,0 +1,167 @@
+// Random streams of the batched-step engine.
+//
+// * PCG64 + SeedSequence: the reference's classic-control resets draw from
+//   `np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))` (gymnasium
+//   `utils.seeding.np_random`, reached from carl/envs/carl_env.py:271 and consumed at
+//   carl/envs/gymnasium/classic_control/carl_cartpole.py:51-61 etc.). To make device-side
+//   (auto)resets bit-identical to that stream the same integer algorithms run per env:
+//   one 128-bit LCG state + increment per env instance.
+// * Philox4x32-10: counter-based stream for the synthetic random policy of the fused
+//   rollout kernels (keyed by seed, global env id, step) -- independent of sharding.
+//
+// Everything here is integer work and must be bit-exact; tests compare against numpy
+// itself (PCG64 / SeedSequence) and the Random123 known-answer vectors (Philox).
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CARLB_HD __host__ __device__ __forceinline__
+#else
+#define CARLB_HD static inline
+#endif
+
+namespace carlb {
+
+// ----------------------------------------------------------------------------- PCG64
+struct Pcg64 {
+  uint64_t state_hi, state_lo, inc_hi, inc_lo;
+};
+
+// 128-bit multiplier of PCG64 (PCG_DEFAULT_MULTIPLIER_128)
+#define CARLB_PCG_MULT_HI 0x2360ED051FC65DA4ULL
+#define CARLB_PCG_MULT_LO 0x4385DF649FCCF645ULL
+
+CARLB_HD uint64_t mulhi64(uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umul64hi(a, b);
+#else
+  return (uint64_t)(((unsigned __int128)a * (unsigned __int128)b) >> 64);
+#endif
+}
+
+// state = state * MULT + inc  (mod 2^128)
+CARLB_HD void pcg64_advance1(Pcg64& g) {
+  const uint64_t lo = g.state_lo * CARLB_PCG_MULT_LO;
+  uint64_t hi = mulhi64(g.state_lo, CARLB_PCG_MULT_LO) + g.state_hi * CARLB_PCG_MULT_LO +
+                g.state_lo * CARLB_PCG_MULT_HI;
+  const uint64_t nlo = lo + g.inc_lo;
+  hi += g.inc_hi + (nlo < lo ? 1ULL : 0ULL);
+  g.state_lo = nlo;
+  g.state_hi = hi;
+}
+
+// numpy pcg64_next64: step, then XSL-RR output of the new state
+CARLB_HD uint64_t pcg64_next64(Pcg64& g) {
+  pcg64_advance1(g);
+  const uint64_t x = g.state_hi ^ g.state_lo;
+  const unsigned rot = (unsigned)(g.state_hi >> 58);
+  return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+
+// numpy next_double: 53 random bits
+CARLB_HD double pcg64_next_double(Pcg64& g) {
+  return (double)(pcg64_next64(g) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// Generator.uniform(low, high) == low + (high - low) * next_double  (numpy random_uniform)
+CARLB_HD double pcg64_uniform(Pcg64& g, double low, double high) {
+  return low + (high - low) * pcg64_next_double(g);
+}
+
+// pcg_setseq_128_srandom_r(initstate, initseq)
+CARLB_HD void pcg64_srandom(Pcg64& g, uint64_t st_hi, uint64_t st_lo, uint64_t seq_hi, uint64_t seq_lo) {
+  g.state_hi = 0;
+  g.state_lo = 0;
+  g.inc_hi = (seq_hi << 1) | (seq_lo >> 63);
+  g.inc_lo = (seq_lo << 1) | 1ULL;
+  pcg64_advance1(g);
+  const uint64_t lo = g.state_lo + st_lo;
+  g.state_hi = g.state_hi + st_hi + (lo < g.state_lo ? 1ULL : 0ULL);
+  g.state_lo = lo;
+  pcg64_advance1(g);
+}
+
+// ----------------------------------------------------------------------- SeedSequence
+// numpy.random.SeedSequence(entropy=<non-negative int < 2^64>).generate_state(4, uint64)
+// followed by PCG64's seeding (initstate = words 0,1 ; initseq = words 2,3).
+CARLB_HD uint32_t ss_hashmix(uint32_t value, uint32_t& hash_const) {
+  value ^= hash_const;
+  hash_const *= 0x931e8875u;
+  value *= hash_const;
+  value ^= value >> 16;
+  return value;
+}
+CARLB_HD uint32_t ss_mix(uint32_t x, uint32_t y) {
+  uint32_t r = 0xca01f9ddu * x - 0x4973f715u * y;
+  r ^= r >> 16;
+  return r;
+}
+
+CARLB_HD void pcg64_seed_from_int(Pcg64& g, uint64_t entropy) {
+  uint32_t ent[2] = {(uint32_t)(entropy & 0xffffffffu), (uint32_t)(entropy >> 32)};
+  const int n_ent = ent[1] != 0u ? 2 : 1;
+  uint32_t pool[4];
+  uint32_t hc = 0x43b0d7e5u;
+  for (int i = 0; i < 4; ++i) pool[i] = ss_hashmix(i < n_ent ? ent[i] : 0u, hc);
+  for (int s = 0; s < 4; ++s)
+    for (int d = 0; d < 4; ++d)
+      if (s != d) pool[d] = ss_mix(pool[d], ss_hashmix(pool[s], hc));
+  // generate_state(8 x uint32)
+  uint32_t out[8];
+  uint32_t hb = 0x8b51f9ddu;
+  for (int i = 0; i < 8; ++i) {
+    uint32_t v = pool[i & 3];
+    v ^= hb;
+    hb *= 0x58f38dedu;
+    v *= hb;
+    v ^= v >> 16;
+    out[i] = v;
+  }
+  const uint64_t w0 = (uint64_t)out[0] | ((uint64_t)out[1] << 32);
+  const uint64_t w1 = (uint64_t)out[2] | ((uint64_t)out[3] << 32);
+  const uint64_t w2 = (uint64_t)out[4] | ((uint64_t)out[5] << 32);
+  const uint64_t w3 = (uint64_t)out[6] | ((uint64_t)out[7] << 32);
+  // numpy pcg64_set_seed(seed={w0,w1}, inc={w2,w3}): high word first
+  pcg64_srandom(g, w0, w1, w2, w3);
+}
+
+// ---------------------------------------------------------------------- Philox4x32-10
+struct Philox4 {
+  uint32_t v[4];
+};
+
+CARLB_HD uint32_t mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+CARLB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  Philox4 o;
+  o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+
+// uniform in [0,1) with 24 random bits (exactly representable in fp32)
+CARLB_HD float u32_to_unit_float(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// Synthetic-policy draw for (seed, global env id, step): 4 words
+CARLB_HD Philox4 policy_draw(uint64_t seed, uint64_t env_id, uint32_t step) {
+  return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), step, 0x43415242u /*"CARB"*/,
+                       (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+}  // namespace carlb

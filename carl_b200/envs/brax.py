@@ -1,0 +1,185 @@
+"""Contextual Brax-locomotion envs (batched, spring pipeline in CUDA).
+
+Feature tables are those of the reference classes: ``carl/envs/brax/carl_ant.py:20-49``,
+``carl_halfcheetah.py:20-67``, ``carl_hopper.py:20-58``; ``directions`` is
+``carl/envs/brax/brax_walker_goal_wrapper.py:33-50``.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from carl_b200.context.context_space import (
+    CategoricalContextFeature,
+    ContextFeature,
+    UniformFloatContextFeature,
+)
+from carl_b200.envs.carl_env import CARLEnv
+from carl_b200.utils.types import Context
+
+directions = [1, 3, 2, 4, 12, 32, 14, 34, 112, 332, 114, 334, 212, 232, 414, 434]
+
+DIRECTION_NAMES = {
+    1: "north", 3: "south", 2: "east", 4: "west", 12: "north east", 32: "south east", 14: "north west",
+    34: "south west", 112: "north north east", 332: "south south east", 114: "north north west",
+    334: "south south west", 212: "east north east", 232: "east south east", 414: "west north west",
+    434: "west south west",
+}
+
+# Context features CARLBraxEnv._update_context can apply (carl_brax_env.py:259-268) + every mass_<link>
+REGISTERED_CFS = ["friction", "ang_damping", "gravity", "viscosity", "elasticity", "target_distance",
+                  "target_direction", "target_radius"]
+
+
+def _uf(name, lower, upper, default):
+    return UniformFloatContextFeature(name, lower=lower, upper=upper, default_value=default)
+
+
+def _common_features() -> dict[str, ContextFeature]:
+    return {
+        "gravity": _uf("gravity", -1000, -1e-6, -9.8),
+        "friction": _uf("friction", 0, 100, 1),
+        "elasticity": _uf("elasticity", 0, 100, 0),
+        "ang_damping": _uf("ang_damping", -np.inf, np.inf, -0.05),
+    }
+
+
+def _goal_features() -> dict[str, ContextFeature]:
+    return {
+        "target_distance": _uf("target_distance", 0, np.inf, 100),
+        "target_direction": CategoricalContextFeature("target_direction", choices=directions, default_value=1),
+        "target_radius": _uf("target_radius", 0.1, np.inf, 5),
+    }
+
+
+def check_context(context: dict, registered_context_features: list[str]) -> None:
+    """``carl_brax_env.py:104-112``."""
+    for cfname in context.keys():
+        if cfname not in registered_context_features and not cfname.startswith("mass_"):
+            raise RuntimeError(
+                f"Context feature {cfname} can not be updated in the brax system. Only "
+                f"{registered_context_features} are possible."
+            )
+
+
+class CARLBraxEnv(CARLEnv):
+    """Family adapter (reference: ``carl/envs/brax/carl_brax_env.py:115-336``)."""
+
+    env_name: str
+    backend: str = "spring"
+    link_names: list[str] = []
+
+    def __init__(self, env=None, batch_size: int | None = None, contexts=None, obs_context_features=None,
+                 obs_context_as_dict: bool = True, context_selector=None, context_selector_kwargs=None,
+                 use_language_goals: bool = False, **kwargs):
+        """``carl_brax_env.py:119-236``. ``batch_size`` is the reference's name for the number of
+        batched env instances (``brax.envs.create(batch_size=...)``, :163-167); here every instance
+        may carry its own context."""
+        if batch_size is not None and batch_size != 1 and "num_envs" not in kwargs:
+            kwargs["num_envs"] = int(batch_size)
+        self.use_language_goals = use_language_goals
+        super().__init__(env=env, contexts=contexts, obs_context_features=obs_context_features,
+                         obs_context_as_dict=obs_context_as_dict, context_selector=context_selector,
+                         context_selector_kwargs=context_selector_kwargs, **kwargs)
+
+    def _default_autoreset(self) -> bool:
+        return True  # brax.envs.create(auto_reset=True) wraps the env in AutoResetWrapper
+
+    @classmethod
+    def get_default_context(cls) -> Context:
+        """``carl_brax_env.py:308-324``: default context without the goal features."""
+        default_context = cls.get_context_space().get_default_context()
+        for k in ("target_distance", "target_direction", "target_radius"):
+            default_context.pop(k, None)
+        return default_context
+
+    @classmethod
+    def get_default_goal_context(cls) -> Context:
+        """``carl_brax_env.py:326-336``."""
+        return cls.get_context_space().get_default_context()
+
+    @classmethod
+    def kernel_params(cls, table, names, context_mode="reference"):
+        """Batched ``CARLBraxEnv._update_context`` (``carl_brax_env.py:255-292``).
+
+        rows: gravity, friction, elasticity, ang_damping, mass_<link> for every link.
+        ``context_mode="reference"``: the reference assigns the modified ``sys`` to the gym shell,
+        whose jitted step never reads it -- the physics sees the *stock* system
+        (MJCF gravity/friction/masses) whatever the context says. ``"applied"``: the intended
+        semantics, including the `viscosity` -> `ang_damping` overwrite (:278-279)."""
+        from carl_b200.envs import brax_system as bs
+
+        sysd = bs.SYSTEMS[cls.env_name]
+        m = table.shape[0]
+        rows = np.empty((m, 4 + len(sysd["link_names"])), dtype=np.float64)
+        if context_mode == "reference":
+            rows[:, 0] = sysd["stock_gravity"]
+            rows[:, 1] = sysd["stock_friction"]
+            rows[:, 2] = sysd["stock_elasticity"]
+            rows[:, 3] = sysd["stock_ang_damping"]
+            rows[:, 4:] = np.asarray(sysd["stock_masses"])[None, :]
+            return rows
+        col = lambda k: table[:, names.index(k)]
+        check_context({n: 0 for n in names}, REGISTERED_CFS)
+        rows[:, 0] = col("gravity")
+        rows[:, 1] = col("friction")
+        rows[:, 2] = col("elasticity")
+        # "viscosity" in context overwrites ang_damping after "ang_damping" was applied (:276-279)
+        rows[:, 3] = col("viscosity") if "viscosity" in names else col("ang_damping")
+        for j, ln in enumerate(sysd["link_names"]):
+            key = f"mass_{ln}"
+            rows[:, 4 + j] = col(key) if key in names else sysd["stock_masses"][j]
+        return rows
+
+
+class CARLBraxAnt(CARLBraxEnv):
+    env_name: str = "ant"
+    kind = "brax_ant"
+    asset_path: str = "envs/assets/ant.xml"
+    metadata = {"render_modes": []}
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        f = _common_features()
+        f["mass_torso"] = _uf("mass_torso", 1e-6, np.inf, 10)
+        f["viscosity"] = _uf("viscosity", 0, np.inf, 0)
+        f.update(_goal_features())
+        return f
+
+
+class CARLBraxHalfcheetah(CARLBraxEnv):
+    env_name: str = "halfcheetah"
+    kind = "brax_halfcheetah"
+    asset_path: str = "envs/assets/half_cheetah.xml"
+    metadata = {"render_modes": []}
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        f = _common_features()
+        f["viscosity"] = _uf("viscosity", 0, np.inf, 0)
+        f["mass_torso"] = _uf("mass_torso", 1e-6, np.inf, 10)
+        f["mass_bthigh"] = _uf("mass_bthigh", 1e-6, np.inf, 1.5435146)
+        f["mass_bshin"] = _uf("mass_bshin", 1e-6, np.inf, 1.5874476)
+        f["mass_bfoot"] = _uf("mass_bfoot", 1e-6, np.inf, 1.0953975)
+        f["mass_fthigh"] = _uf("mass_fthigh", 1e-6, np.inf, 1.4380753)
+        f["mass_fshin"] = _uf("mass_fshin", 1e-6, np.inf, 1.2008368)
+        f["mass_ffoot"] = _uf("mass_ffoot", 1e-6, np.inf, 0.8845188)
+        f.update(_goal_features())
+        return f
+
+
+class CARLBraxHopper(CARLBraxEnv):
+    env_name: str = "hopper"
+    kind = "brax_hopper"
+    asset_path: str = "envs/assets/hopper.xml"
+    metadata = {"render_modes": []}
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        f = _common_features()
+        f["viscosity"] = _uf("viscosity", 0, np.inf, 0)
+        f["mass_torso"] = _uf("mass_torso", 1e-6, np.inf, 10)
+        f["mass_thigh"] = _uf("mass_thigh", 1e-6, np.inf, 4.0578904)
+        f["mass_leg"] = _uf("mass_leg", 1e-6, np.inf, 2.7813568)
+        f["mass_foot"] = _uf("mass_foot", 1e-6, np.inf, 5.3155746)
+        f.update(_goal_features())
+        return f

@@ -1,0 +1,619 @@
+"""Batched contextual env base class.
+
+``CARLEnv`` keeps the reference's gym-style surface (``carl/envs/carl_env.py:19-342``:
+``contexts`` / ``context`` / ``context_id`` / ``context_selector`` / ``obs_context_features`` /
+``obs_context_as_dict`` / ``observation_space`` / ``reset`` / ``step`` and the class-level
+``get_context_features`` / ``get_context_space`` / ``get_default_context``) but steps
+``num_envs`` independent context instances per call, gymnasium-``VectorEnv`` shaped like the
+reference's only batched precedent (``carl/envs/brax/wrappers.py:93-158``): ``reset() ->
+(obs, info)``, ``step(actions[N, ...]) -> (obs, reward[N], terminated[N], truncated[N], info)``.
+
+The physics runs in hand-written CUDA (libcarlb, ``include/carlb.h``) on caller-owned device
+buffers held here as torch tensors (device-buffer containers only). There is no CPU path.
+
+Differences from the reference that a user must know (all documented in DESIGN.md):
+
+* ``num_envs`` defaults to ``len(contexts)``; the context selector is *shared* by the batch and
+  queried once per env instance being reset, in env-index order (so a first ``reset()`` with the
+  default round-robin selector binds env i to context i).
+* returned tensors are views of persistent device buffers: they are overwritten by the next call.
+* numpy actions in -> numpy results out (pinned host buffers, copies inside the call);
+  torch CUDA actions in -> torch CUDA results out (no host traffic, stream-ordered).
+"""
+from __future__ import annotations
+
+import abc
+import ctypes
+import inspect
+from typing import Any
+
+import numpy as np
+import torch
+
+from carl_b200 import _native, spaces
+from carl_b200.context.context_space import ContextFeature, ContextSpace
+from carl_b200.context.selection import AbstractSelector, RoundRobinSelector
+from carl_b200.utils.types import Context, Contexts
+
+_TORCH_ACT = {
+    torch.int32: _native.ACT_I32, torch.int64: _native.ACT_I64, torch.uint8: _native.ACT_U8,
+    torch.float32: _native.ACT_F32,
+}
+_NP_ACT = {
+    np.dtype(np.int32): _native.ACT_I32, np.dtype(np.int64): _native.ACT_I64, np.dtype(np.uint8): _native.ACT_U8,
+    np.dtype(np.float32): _native.ACT_F32,
+}
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    return None if t is None else t.data_ptr()
+
+
+class ContextTable:
+    """Dense context set: ``float64[M, F]`` + feature names (+ the original keys).
+
+    The reference's ``Contexts`` is a dict of dicts (``carl/utils/types.py:5-6``); building 65 536
+    Python dicts is seconds of host work, so samplers can hand the batch env a table directly
+    (``ContextSampler.sample_context_table``). ``to_contexts()`` gives the dict view back."""
+
+    def __init__(self, names: list[str], values: np.ndarray, keys: list[Any] | None = None):
+        self.names = list(names)
+        self.values = np.ascontiguousarray(values, dtype=np.float64)
+        assert self.values.ndim == 2 and self.values.shape[1] == len(self.names)
+        self.keys = list(range(self.values.shape[0])) if keys is None else list(keys)
+        self._index = None
+
+    def index_of(self, key) -> int:
+        if self._index is None:
+            self._index = {k: i for i, k in enumerate(self.keys)}
+        return self._index[key]
+
+    def __len__(self) -> int:
+        return self.values.shape[0]
+
+    def to_contexts(self) -> Contexts:
+        return {k: {n: float(v) for n, v in zip(self.names, row)} for k, row in zip(self.keys, self.values)}
+
+    def keys_view(self):
+        return self.keys
+
+
+class CARLEnv(abc.ABC):
+    """Batched drop-in for ``carl.envs.carl_env.CARLEnv`` (reference ``carl_env.py:19``)."""
+
+    kind: str  # libcarlb env kind name (see _native.KIND)
+    metadata: dict = {"render_modes": []}
+
+    def __init__(
+        self,
+        env: Any = None,
+        contexts: Contexts | ContextTable | None = None,
+        obs_context_features: list[str] | None = None,
+        obs_context_as_dict: bool = True,
+        context_selector: AbstractSelector | type[AbstractSelector] | None = None,
+        context_selector_kwargs: dict | None = None,
+        *,
+        num_envs: int | None = None,
+        device: str | torch.device | int = "cuda",
+        dtype: str = "float32",
+        context_mode: str = "reference",
+        autoreset: bool | None = None,
+        max_episode_steps: int | None = None,
+        shard: tuple[int, int] | None = None,
+        **kwargs,
+    ):
+        """Parameters follow ``carl_env.py:20-74``; the keyword-only ones are new.
+
+        num_envs: env instances in the (global) batch; default ``len(contexts)``.
+        device: CUDA device of this shard.
+        dtype: ``"float32"`` (throughput) or ``"float64"`` (reference precision, classic control).
+        context_mode: ``"reference"`` reproduces what the reference's context injection actually
+            does, ``"applied"`` what it intends.
+        autoreset: same-step auto-reset inside the step kernel (default: off for classic control
+            as in the reference, on for Brax where ``brax.envs.create`` adds AutoResetWrapper).
+        shard: ``(rank, world_size)`` -- this object owns the contiguous slice of the global batch
+            that ``carl_b200.parallel.shard_range`` assigns to ``rank``.
+        """
+        if env is not None:
+            raise ValueError("carl_b200 envs own their physics; passing a gymnasium/brax `env` is not supported.")
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments {sorted(kwargs)}")
+        self._lib = _native.load()  # fails loudly when libcarlb is missing
+        self.obs_context_as_dict = obs_context_as_dict
+        if dtype not in ("float32", "float64"):
+            raise ValueError(f"dtype must be 'float32' or 'float64', got {dtype!r}")
+        if context_mode not in ("reference", "applied"):
+            raise ValueError(f"context_mode must be 'reference' or 'applied', got {context_mode!r}")
+        self.dtype = dtype
+        self.context_mode = context_mode
+        self._info = _native.query_env(_native.KIND[self.kind])
+
+        if contexts is None:
+            contexts = {0: self.get_default_context()}
+        self.contexts = contexts  # setter fills defaults and builds the dense table
+        self.context: Context | None = None
+        if obs_context_features is None:
+            obs_context_features = list(self._feature_names)
+        self.obs_context_features = obs_context_features
+
+        # Context selector (carl_env.py:90-108)
+        sel_contexts = _LazyContexts(self)
+        if context_selector is None:
+            self.context_selector = RoundRobinSelector(contexts=sel_contexts)
+        elif isinstance(context_selector, AbstractSelector):
+            self.context_selector = context_selector
+        elif inspect.isclass(context_selector) and issubclass(context_selector, AbstractSelector):
+            if context_selector_kwargs is None:
+                context_selector_kwargs = {}
+            _context_selector_kwargs = {"contexts": sel_contexts}
+            context_selector_kwargs.update(_context_selector_kwargs)
+            self.context_selector = context_selector(**context_selector_kwargs)
+        else:
+            raise ValueError(
+                f"Context selector must be None or an AbstractSelector class or instance. "
+                f"Got type {type(context_selector)}."
+            )
+
+        # batch geometry
+        self.global_num_envs = int(num_envs) if num_envs is not None else len(self._table)
+        if self.global_num_envs <= 0:
+            raise ValueError("num_envs must be positive")
+        if shard is None:
+            self.rank, self.world_size = 0, 1
+        else:
+            self.rank, self.world_size = int(shard[0]), int(shard[1])
+        from carl_b200.parallel import shard_range
+
+        self.env_lo, self.env_hi = shard_range(self.global_num_envs, self.rank, self.world_size)
+        self.num_envs = self.env_hi - self.env_lo
+        if self.num_envs <= 0:
+            raise ValueError(f"rank {self.rank} of {self.world_size} owns no env instances")
+
+        self.device = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if self.device.type != "cuda":
+            raise ValueError("carl_b200 runs on CUDA devices only (no CPU fallback)")
+        if not torch.cuda.is_available():
+            raise RuntimeError("carl_b200 needs a CUDA device: torch.cuda.is_available() is False")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+
+        # spaces (carl_env.py:77,110-112)
+        self.base_observation_space = self._single_observation_space()
+        self.single_action_space = self._single_action_space()
+        self.action_space = self._batched_action_space()
+        self.observation_space = self.get_observation_space(obs_context_feature_names=self.obs_context_features)
+
+        self._autoreset = self._default_autoreset() if autoreset is None else bool(autoreset)
+        self._max_episode_steps = int(max_episode_steps) if max_episode_steps else self._info.default_max_steps
+        self._alloc()
+        self._context_ids = np.full(self.num_envs, -1, dtype=np.int64)  # per-env current context id
+        self._ctx_obs_cache = None
+        self._seeded = False
+        self._host_io = None
+
+    # ------------------------------------------------------------------ contexts
+    @property
+    def contexts(self) -> Contexts:
+        if self._contexts_dict is None:
+            self._contexts_dict = self._table.to_contexts()
+        return self._contexts_dict
+
+    @contexts.setter
+    def contexts(self, contexts: Contexts | ContextTable) -> None:
+        """``carl_env.py:122-137``: every context is filled with the default values."""
+        context_space = self.get_context_space()
+        defaults = context_space.get_default_context()
+        names = list(defaults.keys())
+        self._feature_names = names
+        if isinstance(contexts, ContextTable):
+            unknown = [n for n in contexts.names if n not in defaults]
+            if unknown:
+                raise ValueError(f"Unknown context features {unknown}")
+            vals = np.empty((len(contexts), len(names)), dtype=np.float64)
+            for j, n in enumerate(names):
+                vals[:, j] = contexts.values[:, contexts.names.index(n)] if n in contexts.names else float(defaults[n])
+            self._table = ContextTable(names, vals, contexts.keys)
+            self._contexts_dict = None
+        else:
+            filled = {k: context_space.insert_defaults(v) for k, v in contexts.items()}
+            for k, c in filled.items():
+                unknown = [n for n in c if n not in defaults]
+                if unknown:
+                    raise ValueError(f"Unknown context features {unknown} in context {k!r}")
+            vals = np.array([[float(c[n]) for n in names] for c in filled.values()], dtype=np.float64)
+            self._table = ContextTable(names, vals.reshape(len(filled), len(names)), list(filled.keys()))
+            self._contexts_dict = filled
+        self._params_table = None  # rebuilt lazily by _update_context
+
+    @property
+    def context_table(self) -> ContextTable:
+        return self._table
+
+    @property
+    def context_id(self):
+        """Current context id: an int for a single env instance, else ``int64[num_envs]``."""
+        if getattr(self, "_context_ids", None) is None or (self._context_ids < 0).all():
+            return self.context_selector.context_id
+        if self.num_envs == 1:
+            return int(self._context_ids[0])
+        return self._context_ids.copy()
+
+    @context_id.setter
+    def context_id(self, new_id) -> None:
+        """``carl_env.py:139-157``: switch context immediately (an int applies to every env)."""
+        ids = np.broadcast_to(np.asarray(new_id, dtype=np.int64), (self.num_envs,)).copy()
+        valid = np.isin(ids, np.asarray(self.context_selector.context_ids))
+        assert valid.all(), "Unknown ID, this context does not exist in the context set."
+        self.context_selector.context_id = int(ids[-1])
+        self.context_selector.context = self.context_selector.contexts[
+            self.context_selector.contexts_keys[int(ids[-1])]
+        ]
+        self._context_ids = ids
+        self._refresh_context_view()
+        self._update_context()
+
+    def _refresh_context_view(self) -> None:
+        ids = self._context_ids
+        vals = self._table.values[ids]
+        if self.num_envs == 1:
+            self.context = {n: _pyval(v) for n, v in zip(self._feature_names, vals[0])}
+        else:
+            self.context = {n: vals[:, j].copy() for j, n in enumerate(self._feature_names)}
+        self._ctx_obs_cache = None
+
+    # -------------------------------------------------------------------- spaces
+    def get_observation_space(self, obs_context_feature_names: list[str] | None = None):
+        """``carl_env.py:159-188``: ``Dict{"obs": base, "context": ...}`` (single-env spaces)."""
+        context_space = self.get_context_space()
+        obs_space_context = context_space.to_gymnasium_space(
+            context_feature_names=obs_context_feature_names, as_dict=self.obs_context_as_dict
+        )
+        return spaces.Dict({"obs": self.base_observation_space, "context": obs_space_context})
+
+    def _single_observation_space(self):
+        hi = np.full(self._info.obs_dim, np.inf, dtype=np.float32)
+        return spaces.Box(-hi, hi, dtype=np.float32)
+
+    def _single_action_space(self):
+        if self._info.act_discrete:
+            return spaces.Discrete(self._info.n_actions)
+        lo = np.full(self._info.act_dim, self._info.act_low, dtype=np.float32)
+        hi = np.full(self._info.act_dim, self._info.act_high, dtype=np.float32)
+        return spaces.Box(lo, hi, dtype=np.float32)
+
+    def _batched_action_space(self):
+        if self._info.act_discrete:
+            return spaces.Box(
+                low=np.zeros(self.num_envs), high=np.full(self.num_envs, self._info.n_actions - 1), dtype=np.int64
+            )
+        return spaces.batch_box(self.single_action_space, self.num_envs)
+
+    @staticmethod
+    @abc.abstractmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        """``carl_env.py:190-202``."""
+        ...
+
+    @classmethod
+    def get_context_space(cls) -> ContextSpace:
+        """``carl_env.py:204-214``."""
+        return ContextSpace(cls.get_context_features())
+
+    @classmethod
+    def get_default_context(cls) -> Context:
+        """``carl_env.py:216-226``."""
+        return cls.get_context_space().get_default_context()
+
+    def _default_autoreset(self) -> bool:
+        return False
+
+    # ------------------------------------------------------------------- buffers
+    def _alloc(self) -> None:
+        n, info, dev = self.num_envs, self._info, self.device
+        tdt = torch.float32 if self.dtype == "float32" else torch.float64
+        self._precision = _native.F32 if self.dtype == "float32" else _native.F64
+        is_brax = self.kind.startswith("brax")
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
+        self._state = z(n, info.state_words, dtype=(torch.float32 if is_brax else tdt))
+        self._ctx = z(info.n_param_rows, n, dtype=(torch.float32 if is_brax else tdt))
+        self._elapsed = z(n, dtype=torch.int32)
+        self._sbt = z(n, dtype=torch.uint8)
+        self._rng = z(4, n, dtype=torch.int64)
+        self._obs = z(n, info.obs_dim, dtype=torch.float32)
+        self._reward = z(n, dtype=torch.float32)
+        self._terminated = z(n, dtype=torch.uint8)
+        self._truncated = z(n, dtype=torch.uint8)
+        self._final_obs = z(n, info.obs_dim, dtype=torch.float32)
+        self._first_state = z(n, info.state_words, dtype=torch.float32) if is_brax else None
+        self._first_obs = z(n, info.obs_dim, dtype=torch.float32) if is_brax else None
+        self._act_staging = z(n * max(1, info.act_dim), dtype=torch.int64)
+        self._handle = ctypes.c_void_p()
+        _native.check(self._lib.carlb_env_create(
+            _native.KIND[self.kind], n, self._precision, self.device.index, self.env_lo, ctypes.byref(self._handle)))
+        b = _native.Buffers(
+            state=_ptr(self._state), ctx=_ptr(self._ctx), elapsed=_ptr(self._elapsed), sbt=_ptr(self._sbt),
+            rng=_ptr(self._rng), obs=_ptr(self._obs), reward=_ptr(self._reward), terminated=_ptr(self._terminated),
+            truncated=_ptr(self._truncated), final_obs=_ptr(self._final_obs), first_state=_ptr(self._first_state),
+            first_obs=_ptr(self._first_obs), act_staging=_ptr(self._act_staging),
+        )
+        _native.check(self._lib.carlb_env_bind(self._handle, ctypes.byref(b)))
+        _native.check(self._lib.carlb_env_configure(
+            self._handle, self._max_episode_steps,
+            _native.AUTORESET_SAME_STEP if self._autoreset else _native.AUTORESET_NONE))
+
+    def close(self) -> None:
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            self._lib.carlb_env_destroy(h)
+            self._handle = ctypes.c_void_p()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    # ------------------------------------------------------- context -> kernel
+    @classmethod
+    @abc.abstractmethod
+    def kernel_params(cls, table: np.ndarray, names: list[str], context_mode: str = "reference") -> np.ndarray:
+        """Map the dense context table ``float64[M, F]`` onto the kernel-parameter columns
+        ``float64[M, P]`` (the batched form of ``_update_context``, ``carl_env.py:307-319``).
+        Pure host logic (testable without a GPU)."""
+        ...
+
+    def _update_context(self, mask: np.ndarray | None = None) -> None:
+        """Upload the kernel-parameter rows of the envs whose context id changed."""
+        if self._params_table is None:
+            self._params_table = np.ascontiguousarray(self.kernel_params(self._table.values, self._feature_names, self.context_mode))
+            assert self._params_table.shape == (len(self._table), self._info.n_param_rows)
+        ids = self._context_ids
+        np_dt = np.float32 if self._ctx.dtype == torch.float32 else np.float64
+        if mask is None or mask.all():
+            rows = np.ascontiguousarray(self._params_table[ids].T.astype(np_dt))
+            self._ctx.copy_(torch.from_numpy(rows), non_blocking=False)
+        else:
+            idx = np.nonzero(mask)[0]
+            rows = np.ascontiguousarray(self._params_table[ids[idx]].T.astype(np_dt))
+            self._ctx[:, torch.from_numpy(idx).to(self.device)] = torch.from_numpy(rows).to(self.device)
+
+    def _progress_instance(self, mask: np.ndarray | None = None) -> np.ndarray:
+        """``carl_env.py:228-243`` batched: one ``select()`` per env being reset, env order."""
+        n_sel = self.num_envs if mask is None else int(mask.sum())
+        # envs owned by other shards consume selector calls too, so ids do not depend on sharding
+        if mask is None and self.world_size > 1:
+            all_ids = self.context_selector.select_batch(self.global_num_envs)
+            new_ids = all_ids[self.env_lo:self.env_hi]
+        else:
+            new_ids = self.context_selector.select_batch(n_sel)
+        changed = np.zeros(self.num_envs, dtype=bool)
+        if mask is None:
+            changed = new_ids != self._context_ids
+            self._context_ids = np.asarray(new_ids, dtype=np.int64).copy()
+        else:
+            idx = np.nonzero(mask)[0]
+            changed[idx] = new_ids != self._context_ids[idx]
+            self._context_ids[idx] = new_ids
+        self._refresh_context_view()
+        return changed
+
+    # ------------------------------------------------------------- reset / step
+    def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None,
+              mask: np.ndarray | torch.Tensor | None = None):
+        """``carl_env.py:245-274``: select contexts, re-inject those that changed, reset, dict obs.
+
+        seed: env i of the *global* batch is seeded with ``seed + i`` (gymnasium vector-env
+        convention), reproducing ``np.random.Generator(PCG64(SeedSequence(seed + i)))`` on device.
+        mask: optional ``bool[num_envs]`` -- reset only those env instances."""
+        mask_np = None
+        if mask is not None:
+            mask_np = (mask.detach().cpu().numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)).astype(bool)
+            assert mask_np.shape == (self.num_envs,)
+        changed = self._progress_instance(mask_np)
+        if changed.any():
+            self._update_context(changed if not changed.all() else None)
+        st = self._stream()
+        if seed is not None:
+            _native.check(self._lib.carlb_env_seed(self._handle, int(seed), st))
+            self._seeded = True
+        elif not self._seeded:
+            # gymnasium seeds from OS entropy on the first unseeded reset
+            entropy = int(np.random.SeedSequence().generate_state(1, np.uint64)[0] >> 1)
+            _native.check(self._lib.carlb_env_seed(self._handle, entropy, st))
+            self._seeded = True
+        mask_t = None
+        if mask_np is not None:
+            mask_t = torch.from_numpy(mask_np.astype(np.uint8)).to(self.device)
+        _native.check(self._lib.carlb_env_reset(self._handle, _ptr(mask_t), st))
+        state = self._add_context_to_state(self._obs)
+        info = {"context_id": self.context_id}
+        return state, info
+
+    def _context_obs_tensors(self):
+        if self._ctx_obs_cache is None:
+            ids = self._context_ids
+            cols = [self._feature_names.index(k) for k in self.obs_context_features]
+            vals = self._table.values[ids][:, cols].astype(np.float32) if cols else np.zeros((self.num_envs, 0), np.float32)
+            t = torch.from_numpy(np.ascontiguousarray(vals)).to(self.device)
+            if self.obs_context_as_dict:
+                self._ctx_obs_cache = {k: t[:, j] for j, k in enumerate(self.obs_context_features)}
+            else:
+                self._ctx_obs_cache = t
+        return self._ctx_obs_cache
+
+    def _add_context_to_state(self, state: Any) -> dict[str, Any]:
+        """``carl_env.py:276-305``: ``{"obs": state, "context": dict | vector}`` (batched columns)."""
+        return {"obs": state, "context": self._context_obs_tensors()}
+
+    def _check_actions(self, n_expected: int, shape: tuple) -> None:
+        a = self._info.act_dim
+        ok = shape in ((n_expected,), (n_expected, a)) if a == 1 else shape == (n_expected, a)
+        assert ok, f"actions must have shape ({n_expected}, {a}), got {shape}"
+
+    def step(self, action: Any):
+        """``carl_env.py:321-342`` batched. torch CUDA actions -> device results;
+        numpy / list actions -> host (numpy) results through pinned buffers."""
+        if isinstance(action, torch.Tensor) and action.is_cuda:
+            self._check_actions(self.num_envs, tuple(action.shape))
+            if action.dtype not in _TORCH_ACT:
+                action = action.to(torch.int32 if self._info.act_discrete else torch.float32)
+            if not self._info.act_discrete and action.dtype != torch.float32:
+                action = action.to(torch.float32)
+            action = action.contiguous()
+            _native.check(self._lib.carlb_env_step(self._handle, action.data_ptr(), _TORCH_ACT[action.dtype], self._stream()))
+            obs, rew, term, trunc = self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool)
+            state = self._add_context_to_state(obs)
+            info = {"context_id": self.context_id}
+            if self._autoreset:
+                info["final_observation"] = self._final_obs
+            return state, rew, term, trunc, info
+        return self._step_host(action)
+
+    def _ensure_host_io(self):
+        if self._host_io is None:
+            n, info = self.num_envs, self._info
+            pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+            self._host_io = dict(
+                act=pin(n * max(1, info.act_dim), dtype=torch.int64),
+                obs=pin(n, info.obs_dim, dtype=torch.float32),
+                reward=pin(n, dtype=torch.float32),
+                term=pin(n, dtype=torch.uint8),
+                trunc=pin(n, dtype=torch.uint8),
+            )
+        return self._host_io
+
+    def _step_host(self, action: Any):
+        io = self._ensure_host_io()
+        a = np.asarray(action.cpu() if isinstance(action, torch.Tensor) else action)
+        self._check_actions(self.num_envs, tuple(a.shape))
+        if self._info.act_discrete:
+            if a.dtype not in _NP_ACT or a.dtype == np.float32:
+                a = a.astype(np.int64)
+        elif a.dtype != np.float32:
+            a = a.astype(np.float32)
+        nbytes = a.size * a.dtype.itemsize
+        staged = io["act"].numpy().view(np.uint8)[:nbytes].view(a.dtype)
+        staged[...] = a.reshape(-1)
+        _native.check(self._lib.carlb_env_step_host(
+            self._handle, io["act"].data_ptr(), _NP_ACT[a.dtype], io["obs"].data_ptr(), io["reward"].data_ptr(),
+            io["term"].data_ptr(), io["trunc"].data_ptr(), self._stream()))
+        obs = io["obs"].numpy()
+        state = {"obs": obs, "context": self._context_obs_host()}
+        info = {"context_id": self.context_id}
+        return state, io["reward"].numpy(), io["term"].numpy().view(np.bool_), io["trunc"].numpy().view(np.bool_), info
+
+    def _context_obs_host(self):
+        ids = self._context_ids
+        cols = [self._feature_names.index(k) for k in self.obs_context_features]
+        vals = self._table.values[ids][:, cols]
+        if self.obs_context_as_dict:
+            if self.num_envs == 1:
+                return {k: _pyval(vals[0, j]) for j, k in enumerate(self.obs_context_features)}
+            return {k: vals[:, j] for j, k in enumerate(self.obs_context_features)}
+        return vals.astype(np.float32)
+
+    # ----------------------------------------------------------- fused rollout
+    def rollout(self, n_steps: int, policy_seed: int = 0, step_base: int = 0, actions: torch.Tensor | None = None,
+                record: bool = False):
+        """Advance every env ``n_steps`` steps in ONE launch (state stays in registers).
+
+        actions=None: synthetic uniform random policy from Philox4x32-10 keyed by
+        ``(policy_seed, global env id, step_base + t)``. record=True returns the trajectory
+        ``{"obs": [K,N,D], "actions": [K,N(,A)], "reward": [K,N], "done": [K,N] (bit0 term, bit1 trunc)}``."""
+        n, info, dev = self.num_envs, self._info, self.device
+        traj_t = None
+        traj = None
+        if record:
+            adt = torch.int32 if info.act_discrete else torch.float32
+            ashape = (n_steps, n) if info.act_dim == 1 else (n_steps, n, info.act_dim)
+            traj_t = dict(
+                obs=torch.empty(n_steps, n, info.obs_dim, dtype=torch.float32, device=dev),
+                actions=torch.empty(*ashape, dtype=adt, device=dev),
+                reward=torch.empty(n_steps, n, dtype=torch.float32, device=dev),
+                done=torch.empty(n_steps, n, dtype=torch.uint8, device=dev),
+            )
+            traj = _native.Traj(obs=_ptr(traj_t["obs"]), actions=_ptr(traj_t["actions"]),
+                                reward=_ptr(traj_t["reward"]), done=_ptr(traj_t["done"]))
+        act_ptr, act_dt = None, _native.ACT_I32
+        if actions is not None:
+            assert actions.is_cuda and actions.shape[0] == n_steps and actions.shape[1] == n
+            actions = actions.contiguous()
+            act_ptr, act_dt = actions.data_ptr(), _TORCH_ACT[actions.dtype]
+        _native.check(self._lib.carlb_env_rollout(
+            self._handle, int(n_steps), int(policy_seed), int(step_base), act_ptr, act_dt,
+            ctypes.byref(traj) if traj is not None else None, self._stream()))
+        return traj_t
+
+    # ------------------------------------------------------------ checkpointing
+    def state_dict(self) -> dict[str, Any]:
+        """Everything needed to resume: env state, counters, RNG streams, context binding."""
+        return {
+            "state": self._state.clone(), "elapsed": self._elapsed.clone(), "sbt": self._sbt.clone(),
+            "rng": self._rng.clone(), "obs": self._obs.clone(), "context_ids": self._context_ids.copy(),
+            "first_state": None if self._first_state is None else self._first_state.clone(),
+            "first_obs": None if self._first_obs is None else self._first_obs.clone(),
+        }
+
+    def load_state_dict(self, sd: dict[str, Any]) -> None:
+        self._state.copy_(sd["state"]); self._elapsed.copy_(sd["elapsed"]); self._sbt.copy_(sd["sbt"])
+        self._rng.copy_(sd["rng"]); self._obs.copy_(sd["obs"])
+        if self._first_state is not None and sd.get("first_state") is not None:
+            self._first_state.copy_(sd["first_state"]); self._first_obs.copy_(sd["first_obs"])
+        self._context_ids = np.asarray(sd["context_ids"], dtype=np.int64).copy()
+        self._refresh_context_view()
+        self._update_context()
+        self._seeded = True
+
+    # raw views for tests / learners
+    @property
+    def state(self) -> torch.Tensor:
+        return self._state
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def render(self):
+        raise NotImplementedError("rendering is out of scope of the batched-step engine (DESIGN.md)")
+
+
+class _LazyContexts(dict):
+    """Dict view of the env's context table handed to selectors without materialising
+    ``len(contexts)`` Python dicts up front (they only need ``len``, ``keys`` and item access)."""
+
+    def __init__(self, env: CARLEnv):
+        super().__init__()
+        self._env = env
+
+    def __len__(self):
+        return len(self._env._table)
+
+    def keys(self):
+        return self._env._table.keys
+
+    def __iter__(self):
+        return iter(self._env._table.keys)
+
+    def __getitem__(self, k):
+        t = self._env._table
+        if self._env._contexts_dict is not None:
+            return self._env._contexts_dict[k]
+        row = t.values[t.index_of(k)]
+        return {n: _pyval(v) for n, v in zip(t.names, row)}
+
+    def __contains__(self, k):
+        return k in self._env._table.keys
+
+    def items(self):
+        return self._env.contexts.items()
+
+    def values(self):
+        return self._env.contexts.values()
+
+
+def _pyval(v):
+    f = float(v)
+    return f

@@ -1,0 +1,173 @@
+/*
+ * libcarlb -- C ABI of the B200-native batched-step engine for CARL's contextual
+ * classic-control and Brax-locomotion environments.
+ *
+ * The reference (automl/CARL) has no native boundary: its seam for this path is the gymnasium
+ * Env protocol that `CARLEnv` wraps (carl/envs/carl_env.py:245-342) plus the attribute pokes of
+ * its family adapters. Each entry point below names the reference interface it replaces.
+ * Plain pointers and sizes only; no torch types. Unless marked HOST, every pointer is a DEVICE
+ * pointer into caller-owned memory (the Python host layer passes `tensor.data_ptr()`); the
+ * library never allocates or frees per step and never synchronises the device except in the
+ * *_host entry points. Calls are stream-ordered on the `stream` argument (a cudaStream_t passed
+ * as void*; NULL = legacy default stream). A handle is not thread-safe; one handle per shard.
+ *
+ * All functions return CARLB_OK (0) or a negative error code; carlb_last_error() returns the
+ * thread-local message of the last failure.
+ */
+#ifndef CARLB_H_
+#define CARLB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CARLB_ABI_VERSION 1
+#define CARLB_MAX_PEERS 8
+#define CARLB_MAX_MIXED 8
+
+/* error codes */
+#define CARLB_OK 0
+#define CARLB_ERR_INVALID (-1)  /* bad argument (the host layer raises ValueError / AssertionError) */
+#define CARLB_ERR_STATE (-2)    /* call order: buffers not bound, not seeded, ... (RuntimeError) */
+#define CARLB_ERR_CUDA (-3)     /* a CUDA runtime call failed (RuntimeError) */
+
+/* env kinds: one per reference class on the hot path */
+#define CARLB_CARTPOLE 0          /* carl/envs/gymnasium/classic_control/carl_cartpole.py:11 */
+#define CARLB_PENDULUM 1          /* .../carl_pendulum.py:11 */
+#define CARLB_ACROBOT 2           /* .../carl_acrobot.py:11 */
+#define CARLB_MOUNTAINCAR 3       /* .../carl_mountaincar.py:11 */
+#define CARLB_MOUNTAINCAR_CONT 4  /* .../carl_mountaincarcontinuous.py:11 */
+#define CARLB_BRAX_ANT 16         /* carl/envs/brax/carl_ant.py:14 */
+#define CARLB_BRAX_HALFCHEETAH 17 /* carl/envs/brax/carl_halfcheetah.py:14 */
+#define CARLB_BRAX_HOPPER 18      /* carl/envs/brax/carl_hopper.py:14 */
+
+/* state / context precision of a handle */
+#define CARLB_F32 0 /* throughput mode: fp32 state and context in HBM */
+#define CARLB_F64 1 /* reference-precision mode (classic control only; the reference is float64) */
+
+/* action element types accepted by step / rollout */
+#define CARLB_ACT_I32 0
+#define CARLB_ACT_I64 1
+#define CARLB_ACT_U8 2
+#define CARLB_ACT_F32 3
+
+/* auto-reset modes */
+#define CARLB_AUTORESET_NONE 0 /* classic-control reference behaviour: the caller resets */
+#define CARLB_AUTORESET_SAME_STEP 1
+/* classic: done envs re-draw their state from their own PCG64 stream in the same launch
+ * (obs = first obs of the new episode, terminal obs goes to final_obs), context unchanged.
+ * Brax: brax AutoResetWrapper semantics -- state/obs replaced by the stored first state. */
+
+typedef struct carlb_env carlb_env_t;
+
+typedef struct carlb_env_info {
+  int kind;
+  int state_words;       /* per-env state elements (T for classic, float for Brax) */
+  int obs_dim;
+  int act_dim;
+  int act_discrete;      /* 1: Discrete(n_actions), 0: Box */
+  int n_actions;
+  int n_param_rows;      /* rows of the per-env kernel-parameter table ctx[P][n] */
+  int n_step_rows;       /* rows read by step (the rest are reset-only) */
+  int default_max_steps; /* gymnasium TimeLimit / brax EpisodeWrapper length */
+  int gym_reset_draws;   /* gymnasium's own reset draws that CARL's reset discards */
+  float act_low, act_high;
+} carlb_env_info_t;
+
+/* Caller-owned device buffers of one handle (n = n_envs, S = state_words, D = obs_dim,
+ * P = n_param_rows, T = float or double by precision). */
+typedef struct carlb_buffers {
+  void* state;         /* T[n][S]   env state rows (classic) / float[n][S] link state (Brax) */
+  void* ctx;           /* T[P][n]   per-env kernel parameters (context features, SoA) */
+  int32_t* elapsed;    /* [n]       TimeLimit counter */
+  uint8_t* sbt;        /* [n]       CartPole "steps_beyond_terminated is not None" flag */
+  uint64_t* rng;       /* [4][n]    per-env PCG64: state_hi, state_lo, inc_hi, inc_lo */
+  float* obs;          /* [n][D] */
+  float* reward;       /* [n] */
+  uint8_t* terminated; /* [n] */
+  uint8_t* truncated;  /* [n] */
+  float* final_obs;    /* [n][D] or NULL: terminal observation of auto-reset envs */
+  void* first_state;   /* Brax: float[n][S] state stored at reset (AutoResetWrapper), else NULL */
+  float* first_obs;    /* Brax: [n][D], else NULL */
+  void* act_staging;   /* [n] x 8 bytes device scratch for carlb_env_step_host */
+} carlb_buffers_t;
+
+/* Optional trajectory sinks of a fused rollout (any pointer may be NULL). K = n_steps. */
+typedef struct carlb_traj {
+  float* obs;      /* [K][n][D] observation returned by step t */
+  void* actions;   /* [K][n] int32 (discrete) or [K][n][A] float (continuous): action taken */
+  float* reward;   /* [K][n] */
+  uint8_t* done;   /* [K][n] bit0 = terminated, bit1 = truncated */
+} carlb_traj_t;
+
+int carlb_abi_version(void);
+const char* carlb_last_error(void);
+
+/* Static facts about an env kind (replaces reading gymnasium/brax spaces:
+ * carl/envs/carl_env.py:77, carl/envs/brax/wrappers.py:45-52). */
+int carlb_query_env(int kind, carlb_env_info_t* out);
+
+/* Replaces `gymnasium.make(env_name)` (carl/envs/gymnasium/carl_gymnasium_env.py:63-64) and
+ * `brax.envs.create(env_name, backend="spring", batch_size)` (carl/envs/brax/carl_brax_env.py:163-176)
+ * for a shard of n_envs instances on `device`; global_offset = global id of local env 0. */
+int carlb_env_create(int kind, int n_envs, int precision, int device, int64_t global_offset, carlb_env_t** out);
+int carlb_env_destroy(carlb_env_t* env);
+
+/* Hands the handle its buffers. Writing `ctx` is the batched `_update_context`
+ * (carl_gymnasium_env.py:75-77 setattr loop; carl_brax_env.py:255-292 sys.replace). */
+int carlb_env_bind(carlb_env_t* env, const carlb_buffers_t* bufs);
+
+/* max_episode_steps: TimeLimit of gymnasium.make / EpisodeWrapper of brax.envs.create
+ * (<= 0 keeps the kind's default); autoreset: CARLB_AUTORESET_*. */
+int carlb_env_configure(carlb_env_t* env, int max_episode_steps, int autoreset);
+
+/* `reset(seed=s)` seeding (carl/envs/carl_env.py:271 -> gymnasium np_random): env i gets
+ * PCG64(SeedSequence(seed + global_offset + i)), bit-identical to numpy. */
+int carlb_env_seed(carlb_env_t* env, uint64_t seed, void* stream);
+
+/* `CARL<Env>.reset` for the envs with mask[i] != 0 (mask NULL = all): gymnasium's own reset draws
+ * are consumed and discarded, then CARL's context-controlled draws produce the state
+ * (carl_cartpole.py:44-66, carl_pendulum.py:41-65, carl_acrobot.py:71-115,
+ * carl_mountaincar.py:53-85, carl_mountaincarcontinuous.py:50-82); Brax: `Ant.reset` etc. through
+ * carl/envs/brax/wrappers.py:54-59 (q = init_q + noise, forward kinematics). Writes obs. */
+int carlb_env_reset(carlb_env_t* env, const uint8_t* mask, void* stream);
+
+/* Batched `CARLEnv.step(action)` (carl/envs/carl_env.py:321-342 -> gymnasium step /
+ * carl/envs/brax/wrappers.py:62-67,74-78): one launch advances all n envs, writes
+ * obs, reward, terminated, truncated (and final_obs / auto-reset). */
+int carlb_env_step(carlb_env_t* env, const void* actions, int act_dtype, void* stream);
+
+/* Same call with HOST buffers (what a gymnasium user holds: numpy in, numpy out): copies the
+ * actions host->device, steps, copies obs/reward/terminated/truncated device->host and
+ * synchronises `stream`. Host pointers should be page-locked for full PCIe rate. Any output
+ * pointer may be NULL to skip that copy. */
+int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtype, float* obs_host,
+                        float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream);
+
+/* Fused K-step rollout (the `for t: env.step(policy(obs))` loop of a rollout worker in one
+ * launch; state stays in registers). actions == NULL: synthetic random policy from
+ * Philox4x32-10 keyed by (policy_seed, global env id, step_base + t); else actions[K][n]. */
+int carlb_env_rollout(carlb_env_t* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                      int act_dtype, const carlb_traj_t* traj, void* stream);
+
+/* Mixed-env batch: one launch steps several homogeneous shards (e.g. Pendulum + Acrobot). */
+int carlb_mixed_step(carlb_env_t* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,
+                     void* stream);
+
+/* Fused cross-GPU observation gather: every obs row is also stored to
+ * peer_obs[r] + (global_offset + i) * obs_dim (P2P-mapped gathered buffers of all ranks). */
+int carlb_env_set_peers(carlb_env_t* env, int n_peers, float* const* peer_obs);
+
+/* Brax: override entries of the named system-tunable table; values HOST. */
+int carlb_brax_set_tunables(carlb_env_t* env, const float* values, int n_values);
+int carlb_brax_get_tunables(int kind, float* values, int max_values, int* n_values);
+
+/* Counters of kernels launched through this library since load (bench `gpu_launches`). */
+int64_t carlb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CARLB_H_ */

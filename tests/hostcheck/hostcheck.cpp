@@ -1,0 +1,132 @@
+// TEST-ONLY shim: compiles the product's __host__ __device__ physics / RNG headers with g++ so
+// the no-GPU test suite can check the kernel *source logic* against the oracle and numpy before
+// GPU time is spent. Never loaded by the product (carl_b200 fails loudly without its CUDA lib).
+#include <stdint.h>
+#include <string.h>
+
+#include "../../carl_b200/csrc/physics_classic.h"
+
+using namespace carlb;
+
+extern "C" {
+
+void hc_pcg64_seed(uint64_t entropy, uint64_t out[4]) {
+  Pcg64 g;
+  pcg64_seed_from_int(g, entropy);
+  out[0] = g.state_hi; out[1] = g.state_lo; out[2] = g.inc_hi; out[3] = g.inc_lo;
+}
+
+void hc_pcg64_doubles(uint64_t st[4], int n, double* out) {
+  Pcg64 g{st[0], st[1], st[2], st[3]};
+  for (int i = 0; i < n; ++i) out[i] = pcg64_next_double(g);
+  st[0] = g.state_hi; st[1] = g.state_lo; st[2] = g.inc_hi; st[3] = g.inc_lo;
+}
+
+void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
+  Philox4 r = philox4x32_10(c[0], c[1], c[2], c[3], k[0], k[1]);
+  memcpy(out, r.v, sizeof(r.v));
+}
+
+void hc_policy_action(int kind, uint64_t seed, uint64_t env_id, uint32_t step, int* ai, float* af) {
+  Action a;
+  switch (kind) {
+    case KIND_CARTPOLE: a = policy_action<KIND_CARTPOLE>(seed, env_id, step); break;
+    case KIND_PENDULUM: a = policy_action<KIND_PENDULUM>(seed, env_id, step); break;
+    case KIND_ACROBOT: a = policy_action<KIND_ACROBOT>(seed, env_id, step); break;
+    case KIND_MOUNTAINCAR: a = policy_action<KIND_MOUNTAINCAR>(seed, env_id, step); break;
+    default: a = policy_action<KIND_MOUNTAINCAR_CONT>(seed, env_id, step); break;
+  }
+  *ai = a.i; *af = a.f;
+}
+
+}  // extern "C"
+
+// state: T[n][S] ; params: T[P][n] ; rng: u64[4][n]
+template <int KIND, typename T>
+static void step_all(int n, T* state, const T* params, const int* ai, const float* af, uint64_t* rng, uint8_t* sbt,
+                     int* elapsed, int max_steps, int autoreset, float* obs, float* reward, uint8_t* term,
+                     uint8_t* trunc, float* final_obs) {
+  typedef Traits<KIND> Tr;
+  for (int i = 0; i < n; ++i) {
+    T p[Tr::P];
+    for (int r = 0; r < Tr::P; ++r) p[r] = params[(size_t)r * n + i];
+    T* s = state + (size_t)i * Tr::S;
+    Pcg64 g{rng[0 * n + i], rng[1 * n + i], rng[2 * n + i], rng[3 * n + i]};
+    Action a{ai ? ai[i] : 0, af ? af[i] : 0.0f};
+    T noise = 0;
+    if (KIND == KIND_ACROBOT && p[AC_NOISE] > (T)0)
+      noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
+    float o[8];
+    StepOut so = env_step<KIND, T>(s, p, a, noise, sbt[i], o);
+    elapsed[i] += 1;
+    bool tr = max_steps > 0 && elapsed[i] >= max_steps;
+    if (autoreset && (so.terminated || tr)) {
+      if (final_obs) for (int k = 0; k < Tr::D; ++k) final_obs[(size_t)i * Tr::D + k] = o[k];
+      for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_next64(g);
+      env_reset<KIND, T>(s, p, g, o);
+      elapsed[i] = 0;
+      sbt[i] = 0;
+    }
+    for (int k = 0; k < Tr::D; ++k) obs[(size_t)i * Tr::D + k] = o[k];
+    reward[i] = so.reward; term[i] = so.terminated; trunc[i] = tr;
+    rng[0 * n + i] = g.state_hi; rng[1 * n + i] = g.state_lo; rng[2 * n + i] = g.inc_hi; rng[3 * n + i] = g.inc_lo;
+  }
+}
+
+template <int KIND, typename T>
+static void reset_all(int n, T* state, const T* params, uint64_t* rng, float* obs) {
+  typedef Traits<KIND> Tr;
+  for (int i = 0; i < n; ++i) {
+    T p[Tr::P];
+    for (int r = 0; r < Tr::P; ++r) p[r] = params[(size_t)r * n + i];
+    Pcg64 g{rng[0 * n + i], rng[1 * n + i], rng[2 * n + i], rng[3 * n + i]};
+    for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_next64(g);
+    float o[8];
+    env_reset<KIND, T>(state + (size_t)i * Tr::S, p, g, o);
+    for (int k = 0; k < Tr::D; ++k) obs[(size_t)i * Tr::D + k] = o[k];
+    rng[0 * n + i] = g.state_hi; rng[1 * n + i] = g.state_lo; rng[2 * n + i] = g.inc_hi; rng[3 * n + i] = g.inc_lo;
+  }
+}
+
+
+extern "C" {
+
+int hc_step(int kind, int f64, int n, void* state, const void* params, const int* ai, const float* af, uint64_t* rng,
+            uint8_t* sbt, int* elapsed, int max_steps, int autoreset, float* obs, float* reward, uint8_t* term,
+            uint8_t* trunc, float* final_obs) {
+#define ARGS_F (n, (float*)state, (const float*)params, ai, af, rng, sbt, elapsed, max_steps, autoreset, obs, reward, term, trunc, final_obs)
+#define ARGS_D (n, (double*)state, (const double*)params, ai, af, rng, sbt, elapsed, max_steps, autoreset, obs, reward, term, trunc, final_obs)
+  switch (kind * 2 + f64) {
+    case KIND_CARTPOLE * 2: step_all<KIND_CARTPOLE, float> ARGS_F; break;
+    case KIND_CARTPOLE * 2 + 1: step_all<KIND_CARTPOLE, double> ARGS_D; break;
+    case KIND_PENDULUM * 2: step_all<KIND_PENDULUM, float> ARGS_F; break;
+    case KIND_PENDULUM * 2 + 1: step_all<KIND_PENDULUM, double> ARGS_D; break;
+    case KIND_ACROBOT * 2: step_all<KIND_ACROBOT, float> ARGS_F; break;
+    case KIND_ACROBOT * 2 + 1: step_all<KIND_ACROBOT, double> ARGS_D; break;
+    case KIND_MOUNTAINCAR * 2: step_all<KIND_MOUNTAINCAR, float> ARGS_F; break;
+    case KIND_MOUNTAINCAR * 2 + 1: step_all<KIND_MOUNTAINCAR, double> ARGS_D; break;
+    case KIND_MOUNTAINCAR_CONT * 2: step_all<KIND_MOUNTAINCAR_CONT, float> ARGS_F; break;
+    case KIND_MOUNTAINCAR_CONT * 2 + 1: step_all<KIND_MOUNTAINCAR_CONT, double> ARGS_D; break;
+    default: return -1;
+  }
+  return 0;
+}
+
+int hc_reset(int kind, int f64, int n, void* state, const void* params, uint64_t* rng, float* obs) {
+  switch (kind * 2 + f64) {
+    case KIND_CARTPOLE * 2: reset_all<KIND_CARTPOLE, float>(n, (float*)state, (const float*)params, rng, obs); break;
+    case KIND_CARTPOLE * 2 + 1: reset_all<KIND_CARTPOLE, double>(n, (double*)state, (const double*)params, rng, obs); break;
+    case KIND_PENDULUM * 2: reset_all<KIND_PENDULUM, float>(n, (float*)state, (const float*)params, rng, obs); break;
+    case KIND_PENDULUM * 2 + 1: reset_all<KIND_PENDULUM, double>(n, (double*)state, (const double*)params, rng, obs); break;
+    case KIND_ACROBOT * 2: reset_all<KIND_ACROBOT, float>(n, (float*)state, (const float*)params, rng, obs); break;
+    case KIND_ACROBOT * 2 + 1: reset_all<KIND_ACROBOT, double>(n, (double*)state, (const double*)params, rng, obs); break;
+    case KIND_MOUNTAINCAR * 2: reset_all<KIND_MOUNTAINCAR, float>(n, (float*)state, (const float*)params, rng, obs); break;
+    case KIND_MOUNTAINCAR * 2 + 1: reset_all<KIND_MOUNTAINCAR, double>(n, (double*)state, (const double*)params, rng, obs); break;
+    case KIND_MOUNTAINCAR_CONT * 2: reset_all<KIND_MOUNTAINCAR_CONT, float>(n, (float*)state, (const float*)params, rng, obs); break;
+    case KIND_MOUNTAINCAR_CONT * 2 + 1: reset_all<KIND_MOUNTAINCAR_CONT, double>(n, (double*)state, (const double*)params, rng, obs); break;
+    default: return -1;
+  }
+  return 0;
+}
+
+}  // extern "C"
