@@ -1,0 +1,435 @@
+#!/usr/bin/env python
+"""Headline benchmark: env-steps/sec of the batched-step hot path.
+
+Workload (BASELINE.json configs[1]): CARLCartPole, 65 536 contexts per GPU sampled
+by ``ContextSampler(seed=0)`` with gravity~U(5,15), length~U(0.25,1.0), masscart~U(0.5,2.0);
+synthetic uniform random-policy actions; auto-reset on; TimeLimit 500. A bench "step" is ONE
+env-step of every env instance in the batch.
+
+Three measurements go into the one JSON line:
+
+* ``value``  -- device-resident whole-job throughput. The K timed steps run as K/T launches of the
+  fused T-step rollout kernel (``carlb_env_rollout``: state in registers, in-kernel Philox policy),
+  each launch streaming its full trajectory (obs, action, reward, done = 25 B per env-step) into a
+  ring of HBM buffers larger than L2, so every step's outputs really go to DRAM.
+* ``step_api`` -- the same workload through one ``carlb_env_step`` launch per step (the
+  reference's ``CARLEnv.step`` contract, 90 algorithmic bytes per env-step), device-resident
+  actions streamed from a ring larger than L2, launches replayed from a CUDA graph.
+* ``e2e`` -- the gym-style call a user makes, ``env.step(numpy_actions)``: HOST buffers in and out,
+  host->device and device->host copies inside the timed region (``carlb_env_step_host``).
+
+``--impl reference`` times the CPU oracle port of the reference's step (the reference itself is
+pure Python over gymnasium, which is not installable here) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_ENVS_PER_GPU = 65536
+METRIC = "env-steps/sec at N contexts"
+UNIT = "env-steps/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+L2_BYTES = 126 * 1024 * 1024
+
+# algorithmic bytes per env-step
+STEP_CONTRACT_BYTES = 90  # R: state16+ctx24+action4+elapsed4 ; W: state16+obs16+reward4+flags2+elapsed4
+TRAJ_BYTES = 16 + 4 + 4 + 1  # fused rollout: obs + action + reward + done written per env-step
+
+
+def make_context_table(n: int):
+    from carl_b200.context import ContextSampler, UniformFloatContextFeature
+    from carl_b200.envs import CARLCartPole
+
+    names = list(CARLCartPole.get_context_space().get_default_context().keys())
+    sampler = ContextSampler(
+        [UniformFloatContextFeature("gravity", 5, 15), UniformFloatContextFeature("length", 0.25, 1.0),
+         UniformFloatContextFeature("masscart", 0.5, 2.0)],
+        context_space=CARLCartPole.get_context_space(), seed=0)
+    return names, sampler.sample_context_table(n, names)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def cpu_baseline_leg(steps_per_call: int, target_seconds: float, n_envs: int = N_ENVS_PER_GPU):
+    """The oracle port of the reference's CartPole step, all host threads, bounded sample."""
+    import ctypes
+
+    import oracle
+    from oracle.classic import DEFAULTS
+
+    L = oracle.lib()
+    L.oracle_cartpole_rollout_baseline.restype = ctypes.c_longlong
+    L.oracle_cartpole_rollout_baseline.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+        ctypes.c_int, ctypes.c_void_p]
+    threads = int(L.oracle_max_threads())
+    _, table = make_context_table(n_envs)
+    table = np.ascontiguousarray(table)
+    state = np.random.default_rng(0).uniform(-0.1, 0.1, (n_envs, 4))
+
+    def run(steps):
+        ret = ctypes.c_double()
+        t0 = time.perf_counter()
+        done = L.oracle_cartpole_rollout_baseline(n_envs, steps, state.ctypes.data, table.ctypes.data, 500, 0, 0,
+                                                  threads, ctypes.byref(ret))
+        return done, time.perf_counter() - t0
+
+    run(2)  # warm
+    run(steps_per_call)
+    total, elapsed, reps = 0, 0.0, 0
+    while elapsed < target_seconds:
+        d, t = run(steps_per_call)
+        total += d
+        elapsed += t
+        reps += 1
+    return {"value": total / elapsed, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_envs} CARLCartPole contexts x {steps_per_call * reps} steps "
+                      f"({total:.3g} env-steps, {elapsed:.1f} s) -- C/OpenMP oracle port of the reference step",
+            "threads": threads}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import ctypes
+
+    import oracle
+
+    L = oracle.lib()
+    L.oracle_cartpole_rollout_baseline.restype = ctypes.c_longlong
+    L.oracle_cartpole_rollout_baseline.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+        ctypes.c_int, ctypes.c_void_p]
+    threads = int(L.oracle_max_threads())
+    n = N_ENVS_PER_GPU * args.gpus
+    _, table = make_context_table(n)
+    table = np.ascontiguousarray(table)
+    state = np.random.default_rng(0).uniform(-0.1, 0.1, (n, 4))
+    ret = ctypes.c_double()
+    call = lambda k: L.oracle_cartpole_rollout_baseline(n, k, state.ctypes.data, table.ctypes.data, 500, 0, 0, threads,
+                                                        ctypes.byref(ret))
+    call(args.warmup)
+    t0 = time.perf_counter()
+    done = call(args.steps)
+    dt = time.perf_counter() - t0
+    v = done / dt
+    from oracle.classic import scalar_python_cartpole_steps_per_s
+
+    out = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"CARLCartPole, {N_ENVS_PER_GPU} sampled contexts (gravity/length/masscart) per GPU",
+                   "n_envs": n, "policy": "uniform random (xorshift)", "autoreset": True, "time_limit": 500},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{n} contexts x {args.steps} steps, C/OpenMP oracle port (gymnasium/CARL not installable)"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "python_scalar_reference_shape": {
+            "value": scalar_python_cartpole_steps_per_s(100_000), "unit": UNIT, "cores": 1,
+            "note": "one env, scalar float64 Python + TimeLimit + dict obs per step: the reference's actual cost shape"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from carl_b200 import _native
+    from carl_b200.envs import CARLCartPole, ContextTable
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_local = N_ENVS_PER_GPU
+    n_global = n_local * world
+    names, table = make_context_table(n_global)
+    env = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world))
+    assert env.num_envs == n_local
+    env.reset(seed=0)
+    gather = None
+    if distributed:
+        from carl_b200.parallel import ObsGather
+
+        gather = ObsGather(env, mode="nccl")
+
+    K, W = args.steps, args.warmup
+    T = math.gcd(K, args.fuse)  # fused steps per launch; K/T launches time EXACTLY K steps
+    info = env._info
+    # trajectory ring: outputs larger than L2 so every launch's writes go to DRAM
+    slot_bytes = T * n_local * TRAJ_BYTES
+    n_slots = max(2, int(math.ceil(1.5 * L2_BYTES / slot_bytes)) + 1)
+    ring = [dict(obs=torch.empty(T, n_local, info.obs_dim, device=dev),
+                 actions=torch.empty(T, n_local, dtype=torch.int32, device=dev),
+                 reward=torch.empty(T, n_local, device=dev),
+                 done=torch.empty(T, n_local, dtype=torch.uint8, device=dev)) for _ in range(n_slots)]
+    trajs = [_native.Traj(obs=r["obs"].data_ptr(), actions=r["actions"].data_ptr(), reward=r["reward"].data_ptr(),
+                          done=r["done"].data_ptr()) for r in ring]
+    import ctypes
+
+    lib, handle = env._lib, env._handle
+    stream = torch.cuda.current_stream(dev)
+
+    def fused_launch(i, step_base):
+        _native.check(lib.carlb_env_rollout(handle, T, 12345, step_base, None, _native.ACT_I32,
+                                            ctypes.byref(trajs[i % n_slots]), stream.cuda_stream))
+        if gather is not None:
+            gather.gather()
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: fused rollout, device resident
+    for w in range(max(W // T, 3)):
+        fused_launch(w, w * T)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    launches0 = _native.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K // T)]
+    barrier()
+    ev0.record(stream)
+    for j in range(K // T):
+        kev[j][0].record(stream)
+        _native.check(lib.carlb_env_rollout(handle, T, 12345, 10_000 + j * T, None, _native.ACT_I32,
+                                            ctypes.byref(trajs[j % n_slots]), stream.cuda_stream))
+        kev[j][1].record(stream)
+        if gather is not None:
+            gather.gather()
+    ev1.record(stream)
+    barrier()
+    fused_ms = ev0.elapsed_time(ev1)
+    kernel_ms = [a.elapsed_time(b) for a, b in kev]
+    launches = _native.launch_count() - launches0
+    clock_info = clocks.stop() if rank == 0 else None
+    t_fused = torch.tensor([fused_ms], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t_fused, op=dist.ReduceOp.MAX)
+    fused_ms = float(t_fused.item())
+    value = n_global * K / (fused_ms * 1e-3)
+    k_avg_ms = float(np.mean(kernel_ms))
+
+    # ---------------- step_api: one launch per step, graph-replayed, actions ring > L2
+    K_api = min(K, 2000)
+    ring_steps = int(math.ceil(1.2 * L2_BYTES / (n_local * 4)))  # int32 actions: 256 KiB per step
+    G = min(K_api, ring_steps)
+    K_api -= K_api % G
+    act_ring = torch.randint(0, 2, (G, n_local), dtype=torch.int32, device=dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(stream)
+    with torch.cuda.stream(side):
+        for g_ in range(3):
+            _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, side.cuda_stream))
+    torch.cuda.synchronize(dev)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for g_ in range(G):
+            _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32,
+                                             torch.cuda.current_stream(dev).cuda_stream))
+    for _ in range(max(1, W // G)):
+        graph.replay()
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    for _ in range(K_api // G):
+        graph.replay()
+    a1.record(stream)
+    barrier()
+    api_ms = a0.elapsed_time(a1)
+    api_value = n_local * K_api / (api_ms * 1e-3)
+
+    # cold-L2 single launches: flush L2 (write a buffer larger than L2) between timed launches
+    flush = torch.empty(L2_BYTES * 2 // 4, dtype=torch.float32, device=dev)
+    cold = []
+    for g_ in range(20):
+        flush.fill_(float(g_))
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, stream.cuda_stream))
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        cold.append(c0.elapsed_time(c1))
+    cold_ms = float(np.median(cold[3:]))
+
+    # ---------------- e2e: env.step(numpy actions) -> numpy results (host buffers, copies timed)
+    K_e2e = min(K, 500)
+    host_actions = np.random.default_rng(1).integers(0, 2, size=(64, n_local), dtype=np.int32)
+    for w in range(5):
+        env.step(host_actions[w])
+    barrier()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for j in range(K_e2e):
+        obs, rew, term, trunc, _ = env.step(host_actions[j % 64])
+        acc += float(rew[0])  # the result is read on the host every step
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    t_e2e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if distributed:
+        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
+    e2e_value = n_global * K_e2e / float(t_e2e.item())
+    h2d = n_local * 4
+    d2h = n_local * (info.obs_dim * 4 + 4 + 1 + 1)
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = hbm_peak()
+    fused_bytes_per_launch = (TRAJ_BYTES * T + STEP_CONTRACT_BYTES) * n_local  # trajectory + one state/ctx round trip
+    achieved = fused_bytes_per_launch / (k_avg_ms * 1e-3) / 1e9
+    api_ms_per_launch = api_ms / K_api
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": fused_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": f"CARLCartPole, {N_ENVS_PER_GPU} sampled contexts (gravity/length/masscart) per GPU "
+                        f"(BASELINE configs[1]), uniform random policy, autoreset, TimeLimit 500",
+            "n_envs": n_global, "fused_steps_per_launch": T, "launches": K // T,
+            "l2": f"trajectory ring {n_slots} x {slot_bytes / 2**20:.0f} MiB > L2 (outputs go to DRAM); env state "
+                  f"({n_local * 90 / 2**20:.1f} MiB working set) is register/L2 resident by design",
+            "collective": "NCCL all-gather of the last obs per launch" if distributed else "none",
+        },
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": K_e2e, "api": "CARLCartPole.step(numpy int32 actions) -> numpy obs/reward/terminated/truncated "
+                                       "(carlb_env_step_host, pinned staging)", "ms_per_step": float(t_e2e.item()) / K_e2e * 1e3},
+        "roofline": {
+            "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "peak_source": peak_src, "traffic": None,
+            "algorithmic_bytes_per_launch": fused_bytes_per_launch,
+            "bytes_per_env_step": TRAJ_BYTES + STEP_CONTRACT_BYTES / T,
+            "kernel_ms_avg": k_avg_ms,
+            "frac_vs_step_contract_90B": (STEP_CONTRACT_BYTES * n_local * T / (k_avg_ms * 1e-3) / 1e9) / peak,
+        },
+        "step_api": {
+            "value": api_value * world, "unit": UNIT, "steps": K_api, "us_per_launch": api_ms_per_launch * 1e3,
+            "l2": f"actions ring of {G} steps x 256 KiB > L2; CUDA-graph replay of {G} launches",
+            "roofline": {"kernel": "step_kernel<CARTPOLE,float>", "bound": "hbm",
+                         "achieved": STEP_CONTRACT_BYTES * n_local / (api_ms_per_launch * 1e-3) / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": STEP_CONTRACT_BYTES * n_local / (api_ms_per_launch * 1e-3) / 1e9 / peak,
+                         "algorithmic_bytes_per_launch": STEP_CONTRACT_BYTES * n_local},
+            "cold_l2_us_per_launch": cold_ms * 1e3,
+            "cold_l2_frac": STEP_CONTRACT_BYTES * n_local / (cold_ms * 1e-3) / 1e9 / peak,
+        },
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline_leg(steps_per_call=200, target_seconds=args.cpu_seconds)
+    print(json.dumps(out))
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="carl_b200", choices=["carl_b200", "reference"])
+    ap.add_argument("--fuse", type=int, default=100, help="env-steps fused per rollout launch")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -27,7 +27,7 @@ EXPORTS = [
     "carlb_abi_version", "carlb_last_error", "carlb_query_env", "carlb_env_create", "carlb_env_destroy",
     "carlb_env_bind", "carlb_env_configure", "carlb_env_seed", "carlb_env_reset", "carlb_env_step",
     "carlb_env_step_host", "carlb_env_rollout", "carlb_mixed_step", "carlb_env_set_peers",
-    "carlb_brax_set_tunables", "carlb_brax_get_tunables", "carlb_launch_count",
+    "carlb_brax_set_system", "carlb_brax_reset_from_q", "carlb_launch_count",
 ]
 
 
@@ -89,8 +89,8 @@ def load() -> ctypes.CDLL:
     lib.carlb_env_rollout.argtypes = [c_void_p, c_int, c_uint64, c_uint32, c_void_p, c_int, POINTER(Traj), c_void_p]
     lib.carlb_mixed_step.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), c_int, c_void_p]
     lib.carlb_env_set_peers.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
-    lib.carlb_brax_set_tunables.argtypes = [c_void_p, POINTER(c_float), c_int]
-    lib.carlb_brax_get_tunables.argtypes = [c_int, POINTER(c_float), c_int, POINTER(c_int)]
+    lib.carlb_brax_set_system.argtypes = [c_void_p, c_void_p, c_int, c_int]
+    lib.carlb_brax_reset_from_q.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     if lib.carlb_abi_version() != 1:
         raise NativeLibraryError(f"libcarlb ABI version {lib.carlb_abi_version()} != 1")
     _lib = lib

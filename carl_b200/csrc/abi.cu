@@ -324,20 +324,23 @@ int carlb_mixed_step(carlb_env_t* const* envs, const void* const* actions, const
   return classic_mixed_step(envs, actions, act_dtypes, n_handles, (cudaStream_t)stream);
 }
 
-int carlb_brax_set_tunables(carlb_env_t* env, const float* values, int n_values) {
-  if (env == nullptr || values == nullptr || !is_brax(env->kind)) {
-    set_error("carlb_brax_set_tunables: needs a Brax handle and values");
+int carlb_brax_set_system(carlb_env_t* env, const float* table, int n_floats, int stock_contact) {
+  if (env == nullptr || table == nullptr || !is_brax(env->kind)) {
+    set_error("carlb_brax_set_system: needs a Brax handle and a table");
     return CARLB_ERR_INVALID;
   }
-  return brax_set_tunables(env, values, n_values);
+  return brax_set_system(env, table, n_floats, stock_contact);
 }
 
-int carlb_brax_get_tunables(int kind, float* values, int max_values, int* n_values) {
-  if (!is_brax(kind) || n_values == nullptr) {
-    set_error("carlb_brax_get_tunables: needs a Brax kind");
+int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* q, const float* qd, void* stream) {
+  int rc = check_ready(env, "carlb_brax_reset_from_q");
+  if (rc != CARLB_OK) return rc;
+  if (!is_brax(env->kind) || q == nullptr || qd == nullptr) {
+    set_error("carlb_brax_reset_from_q: needs a Brax handle and q / qd");
     return CARLB_ERR_INVALID;
   }
-  return brax_get_tunables(kind, values, max_values, n_values);
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  return brax_reset_from(env, mask, q, qd, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,13 +1,674 @@
-// placeholder until the spring pipeline lands (replaced below in this round)
+// Brax-locomotion kernels (sm_100a): ONE WARP PER ENV INSTANCE.
+//
+// Lanes 0..L-1 own the links of the body (13-float centre-of-mass state in registers), lanes
+// 0..P-1 own the ground-contact candidate points during the collision phase; the per-warp exchange
+// (parent/child states, joint reactions, contact impulses) goes through a 2 KB shared-memory
+// scratch guarded by __syncwarp. The system table (3.1 KB: link frames, inertias, joint limits,
+// contact points, tunables) is staged once per CTA into shared memory with a TMA bulk copy
+// (cp.async.bulk + mbarrier); each env's 13 context scalars (gravity, friction, elasticity,
+// ang_damping, link masses) are read with one coalesced load and broadcast with warp shuffles.
+//
+// This is FP32-issue / latency bound work (~6e4 flops per Ant env-step against ~1.1 kB of HBM
+// traffic): no tensor cores. One launch = n_frames spring substeps (+ env layer); the fused
+// rollout keeps the link state in registers across K env-steps.
+#include <cuda_runtime.h>
+#include <string.h>
+
 #include "engine.h"
+#include "physics_brax.h"
+
 namespace carlb {
-int brax_query(int, carlb_env_info_t*) { set_error("Brax kernels not built yet"); return CARLB_ERR_INVALID; }
-int brax_create(carlb_env*) { return CARLB_ERR_INVALID; }
-void brax_destroy(carlb_env*) {}
-int brax_seed(const carlb_env*, uint64_t, cudaStream_t) { return CARLB_ERR_INVALID; }
-int brax_reset(const carlb_env*, const uint8_t*, cudaStream_t) { return CARLB_ERR_INVALID; }
-int brax_step(const carlb_env*, const void*, int, cudaStream_t) { return CARLB_ERR_INVALID; }
-int brax_rollout(const carlb_env*, int, uint64_t, uint32_t, const void*, int, const carlb_traj_t*, cudaStream_t) { return CARLB_ERR_INVALID; }
-int brax_set_tunables(carlb_env*, const float*, int) { return CARLB_ERR_INVALID; }
-int brax_get_tunables(int, float*, int, int*) { return CARLB_ERR_INVALID; }
+using namespace brax;
+
+constexpr int kWarpsPerCta = 4;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr unsigned kFull = 0xffffffffu;
+
+struct BraxSys {        // device-resident per-handle system table (+ static facts)
+  float table[TABLE_FLOATS];
+};
+
+struct BraxSeg {
+  int n;
+  int max_steps;
+  int autoreset;
+  int state_words;   // padded 13*L
+  int obs_dim;
+  int n_ctx;         // 4 + L
+  int act_dim;
+  long long global_offset;
+  uint64_t seed;
+  const float* sys;  // BraxSys::table in global memory
+  float* state;      // [n][state_words]
+  const float* ctx;  // [n][n_ctx]  (AoS per env: one coalesced load + shuffle broadcast)
+  int32_t* elapsed;
+  uint64_t* episode; // [n] reset counter (rng buffer row 0)
+  float* obs;        // [n][D]
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  float* final_obs;
+  float* first_state;
+  float* first_obs;
+  int n_peers;
+  float* peer_obs[CARLB_MAX_PEERS];
+};
+
+struct WarpScratch {
+  float ls[MAX_LINKS * LINK_WORDS];  // link states (also the coalesced I/O staging of the state row)
+  float pw[MAX_LINKS * 6];           // reaction wrench of joint l on its parent
+  float co[MAX_POINTS * 7];          // contact outputs: impulse(3) angular impulse(3) active
+  float q[MAX_Q];
+  float qd[MAX_Q];
+  float act[16];
+  float obs[64];
+};
+
+// ---- TMA bulk copy + mbarrier (PTX) ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// Stage the system table into shared memory: one elected thread issues the bulk copy, everyone
+// waits on the mbarrier phase.
+__device__ __forceinline__ void stage_system(float* sys_s, const float* sys_g, uint64_t* bar) {
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, TABLE_FLOATS * sizeof(float));
+    bulk_g2s(sys_s, sys_g, TABLE_FLOATS * sizeof(float), bar);
+  }
+  mbar_wait(bar, 0);
+}
+
+// ---- state row I/O: coalesced through the warp scratch --------------------------------------------
+__device__ __forceinline__ LinkState read_link(const float* ls, int l) {
+  const float* p = ls + l * LINK_WORDS;
+  LinkState s;
+  s.pos = v3(p[0], p[1], p[2]);
+  s.rot = q4(p[3], p[4], p[5], p[6]);
+  s.vel = v3(p[7], p[8], p[9]);
+  s.ang = v3(p[10], p[11], p[12]);
+  return s;
+}
+__device__ __forceinline__ void write_link(float* ls, int l, const LinkState& s) {
+  float* p = ls + l * LINK_WORDS;
+  p[0] = s.pos.x; p[1] = s.pos.y; p[2] = s.pos.z;
+  p[3] = s.rot.w; p[4] = s.rot.x; p[5] = s.rot.y; p[6] = s.rot.z;
+  p[7] = s.vel.x; p[8] = s.vel.y; p[9] = s.vel.z;
+  p[10] = s.ang.x; p[11] = s.ang.y; p[12] = s.ang.z;
+}
+__device__ __forceinline__ void row_g2s(float* dst, const float* src, int words, int lane) {
+  for (int i = lane; i < words; i += 32) dst[i] = src[i];
+}
+__device__ __forceinline__ void row_s2g(float* dst, const float* src, int words, int lane) {
+  for (int i = lane; i < words; i += 32) dst[i] = src[i];
+}
+
+// ---- one env, one warp: per-lane constants ---------------------------------------------------------
+struct LaneCtx {
+  int L, P, n_frames, env_kind;
+  bool is_link, is_point;
+  const float* lt;   // my link row
+  const float* plt;  // parent's link row
+  int parent;
+  int type;
+  int act;           // actuator index or -1
+  const float* pt;   // my contact point row
+  int pt_link;
+  float mass;        // my link's (context) mass
+  float pt_mass;     // mass of my contact point's link
+  float gravity, friction_ctx, elasticity_ctx, ang_damping;
+  float pt_friction, pt_elasticity;
+};
+
+__device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const float* ctx_row, int n_ctx, int lane,
+                                                 bool stock_contact) {
+  LaneCtx c;
+  c.L = (int)sys[H_N_LINKS];
+  c.P = (int)sys[H_N_POINTS];
+  c.n_frames = (int)sys[H_N_FRAMES];
+  c.env_kind = (int)sys[H_ENV];
+  c.is_link = lane < c.L;
+  c.is_point = lane < c.P;
+  const int l = c.is_link ? lane : 0;
+  c.lt = link_tab(sys, l);
+  c.parent = (int)c.lt[L_PARENT];
+  c.plt = link_tab(sys, c.parent >= 0 ? c.parent : 0);
+  c.type = (int)c.lt[L_TYPE];
+  c.act = (int)c.lt[L_ACT];
+  const int p = c.is_point ? lane : 0;
+  c.pt = point_tab(sys, p);
+  c.pt_link = (int)c.pt[0];
+  // one coalesced load of the env's context scalars, then shuffle broadcast
+  const float cv = (lane < n_ctx) ? ctx_row[lane] : 0.0f;
+  c.gravity = __shfl_sync(kFull, cv, C_GRAVITY);
+  c.friction_ctx = __shfl_sync(kFull, cv, C_FRICTION);
+  c.elasticity_ctx = __shfl_sync(kFull, cv, C_ELASTICITY);
+  c.ang_damping = __shfl_sync(kFull, cv, C_ANG_DAMPING);
+  c.mass = __shfl_sync(kFull, cv, C_MASS0 + l);
+  c.pt_mass = __shfl_sync(kFull, cv, C_MASS0 + c.pt_link);
+  // friction / elasticity: a negative context value means "keep the stock per-geom value"
+  c.pt_friction = (c.friction_ctx < 0.0f || stock_contact) ? c.pt[5] : c.friction_ctx;
+  c.pt_elasticity = (c.elasticity_ctx < 0.0f || stock_contact) ? c.pt[6] : c.elasticity_ctx;
+  return c;
+}
+
+// n_frames spring substeps for the env held by this warp. `s` is this lane's link (valid for
+// lane < L), `tau` this lane's actuator torque.
+__device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, WarpScratch& w, LinkState& s, float tau,
+                                               int lane) {
+  const float dt = sys[H_DT];
+  for (int f = 0; f < c.n_frames; ++f) {
+    if (c.is_link) write_link(w.ls, lane, s);
+    __syncwarp();
+    // joints: lane l resolves the joint between link l and its parent
+    Wrench wr;
+    wr.f = v3(0, 0, 0); wr.t = v3(0, 0, 0);
+    if (c.is_link && c.type != TYPE_FREE) {
+      const bool world_parent = c.parent < 0;
+      const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
+      const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, tau);
+      wr = jo.child;
+      float* pw = w.pw + lane * 6;
+      pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
+      pw[3] = jo.parent.t.x; pw[4] = jo.parent.t.y; pw[5] = jo.parent.t.z;
+    }
+    __syncwarp();
+    if (c.is_link) {
+      // add the reactions of my children (fixed order: deterministic sums)
+      for (int k = lane + 1; k < c.L; ++k) {
+        if ((int)link_tab(sys, k)[L_PARENT] == lane) {
+          const float* pw = w.pw + k * 6;
+          wr.f = wr.f + v3(pw[0], pw[1], pw[2]);
+          wr.t = wr.t + v3(pw[3], pw[4], pw[5]);
+        }
+      }
+      integrate_xdd(s, wr, sys, c.lt, c.mass, c.gravity, c.ang_damping);
+      write_link(w.ls, lane, s);
+    }
+    __syncwarp();
+    // ground contacts: lane p resolves candidate point p against the plane
+    if (c.is_point) {
+      const LinkState ps = read_link(w.ls, c.pt_link);
+      const ContactOut co = contact_resolve(sys, c.pt, link_tab(sys, c.pt_link), ps, c.pt_mass, c.pt_friction,
+                                            c.pt_elasticity);
+      float* o = w.co + lane * 7;
+      o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
+    }
+    __syncwarp();
+    if (c.is_link) {
+      V3 ps = v3(0, 0, 0), ts = v3(0, 0, 0);
+      float na = 0.0f;
+      const int p0 = (int)c.lt[L_FIRST_PT], np = (int)c.lt[L_N_PT];
+      for (int k = p0; k < p0 + np; ++k) {
+        const float* o = w.co + k * 7;
+        ps = ps + v3(o[0], o[1], o[2]);
+        ts = ts + v3(o[3], o[4], o[5]);
+        na += o[6];
+      }
+      integrate_xdv(s, ps, ts, na, sys, c.lt, c.mass);
+      integrate_pose(s, dt);
+    }
+    __syncwarp();
+  }
+}
+
+// kinematics.inverse + env observation: fills w.obs[0..D) and returns (lane-uniform) root facts
+struct RootFacts {
+  float x, z, angle;
+  bool state_ok;  // Hopper: all |q[2:]|, |qd| < 100
+};
+
+__device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, WarpScratch& w, const LinkState& s,
+                                                 int lane) {
+  if (c.is_link) write_link(w.ls, lane, s);
+  __syncwarp();
+  const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
+  if (c.is_link) {
+    const int qi = (int)c.lt[L_QIDX], qdi = (int)c.lt[L_QDIDX];
+    if (c.type == TYPE_FREE) {
+      const V3 o = link_origin(s, c.lt), vo = origin_velocity(s, c.lt), al = inv_rotate(s.ang, s.rot);
+      w.q[qi + 0] = o.x; w.q[qi + 1] = o.y; w.q[qi + 2] = o.z;
+      w.q[qi + 3] = s.rot.w; w.q[qi + 4] = s.rot.x; w.q[qi + 5] = s.rot.y; w.q[qi + 6] = s.rot.z;
+      w.qd[qdi + 0] = vo.x; w.qd[qdi + 1] = vo.y; w.qd[qdi + 2] = vo.z;
+      w.qd[qdi + 3] = al.x; w.qd[qdi + 4] = al.y; w.qd[qdi + 5] = al.z;
+    } else {
+      const bool world_parent = c.parent < 0;
+      const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
+      const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, 0.0f);
+      const int nd = c.type == TYPE_PLANAR ? 3 : 1;
+      for (int k = 0; k < nd; ++k) {
+        w.q[qi + k] = jo.q[k];
+        w.qd[qdi + k] = jo.qd[k];
+      }
+    }
+  }
+  __syncwarp();
+  const int ex = (int)sys[H_EXCLUDE_POS];
+  const float clip = sys[H_QD_CLIP];
+  const int D = (nq - ex) + nqd;
+  for (int i = lane; i < D; i += 32) {
+    float v;
+    if (i < nq - ex) {
+      v = w.q[ex + i];
+    } else {
+      v = w.qd[i - (nq - ex)];
+      if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+    }
+    w.obs[i] = v;
+  }
+  // Hopper healthy_state: every entry of state_vec = q[2:] ++ qd inside (-100, 100)
+  bool ok = true;
+  for (int i = lane; i < (nq - 2) + nqd; i += 32) {
+    const float v = (i < nq - 2) ? w.q[2 + i] : w.qd[i - (nq - 2)];
+    ok = ok && (v > -100.0f) && (v < 100.0f);
+  }
+  RootFacts r;
+  r.state_ok = __all_sync(kFull, ok);
+  __syncwarp();
+  const float* lt0 = link_tab(sys, 0);
+  const LinkState s0 = read_link(w.ls, 0);
+  const V3 o0 = link_origin(s0, lt0);
+  r.x = o0.x;
+  r.z = o0.z;
+  r.angle = ((int)lt0[L_TYPE] == TYPE_PLANAR) ? w.q[2] : 0.0f;
+  return r;
+}
+
+// Env layer of brax.envs.{ant,half_cheetah,hopper}.step after the pipeline advanced.
+__device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& before, const RootFacts& after,
+                                            float act_sq_sum, float& reward, bool& done) {
+  const float dt_env = sys[H_DT] * sys[H_N_FRAMES];
+  const float x_velocity = (after.x - before.x) / dt_env;
+  const float forward_reward = sys[H_FORWARD_WEIGHT] * x_velocity;
+  const int kind = (int)sys[H_ENV];
+  bool healthy = true;
+  if (kind == ENV_ANT) {
+    healthy = !(after.z < sys[H_HEALTHY_Z_MIN]) && !(after.z > sys[H_HEALTHY_Z_MAX]);
+  } else if (kind == ENV_HOPPER) {
+    const bool hz = (sys[H_HEALTHY_Z_MIN] < after.z) && (after.z < sys[H_HEALTHY_Z_MAX]);
+    const bool ha = (sys[H_ANGLE_MIN] < after.angle) && (after.angle < sys[H_ANGLE_MAX]);
+    healthy = after.state_ok && hz && ha;
+  }
+  const float ctrl_cost = sys[H_CTRL_COST] * act_sq_sum;
+  reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
+  done = (sys[H_TERMINATE] > 0.0f) && !healthy;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// actuator.to_tau for this lane's link: gear * clip(action[act], ctrl_range)
+__device__ __forceinline__ float lane_tau(const LaneCtx& c, const WarpScratch& w) {
+  if (!c.is_link || c.act < 0) return 0.0f;
+  const float a = fminf(fmaxf(w.act[c.act], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
+  return c.lt[L_GEAR] * a;
+}
+
+struct SmemLayout {
+  float sys[TABLE_FLOATS];
+  WarpScratch warp[kWarpsPerCta];
+  uint64_t bar;
+};
+
+// ------------------------------------------------------------------------------- step
+// One env-step: [AutoReset zeroing] -> n_frames substeps -> obs/reward/done -> EpisodeWrapper
+// truncation -> AutoReset (state/obs replaced by the stored first ones where done).
+__global__ void __launch_bounds__(kThreads) brax_step_kernel(const __grid_constant__ BraxSeg seg, const float* actions,
+                                                             int n_steps, uint64_t policy_seed, uint32_t step_base,
+                                                             const carlb_traj_t traj, int stock_contact) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  stage_system(sm.sys, seg.sys, &sm.bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * kWarpsPerCta + warp;
+  if (env >= seg.n) return;
+  const float* sys = sm.sys;
+  WarpScratch& w = sm.warp[warp];
+  const LaneCtx c = make_lane_ctx(sys, seg.ctx + (size_t)env * seg.n_ctx, seg.n_ctx, lane, stock_contact != 0);
+  float* state_row = seg.state + (size_t)env * seg.state_words;
+  row_g2s(w.ls, state_row, seg.state_words, lane);
+  __syncwarp();
+  LinkState s = read_link(w.ls, c.is_link ? lane : 0);
+  __syncwarp();
+  int el = seg.elapsed[env];
+  const uint64_t gid = (uint64_t)(seg.global_offset + env);
+  const int A = seg.act_dim, D = seg.obs_dim;
+  float reward = 0.0f;
+  bool done = false;
+  RootFacts before = compute_obs(sys, c, w, s, lane);
+  for (int t = 0; t < n_steps; ++t) {
+    // actions of this step: given tensor [n][A] (single step) / [K][n][A] (rollout) or Philox policy
+    float a = 0.0f;
+    if (lane < A) {
+      if (actions != nullptr) {
+        a = actions[((size_t)t * seg.n + env) * A + lane];
+      } else {
+        const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step_base + (uint32_t)t,
+                                        0x42524158u + (uint32_t)lane, (uint32_t)policy_seed, (uint32_t)(policy_seed >> 32));
+        a = 2.0f * u32_to_unit_float(r.v[0]) - 1.0f;
+      }
+      w.act[lane] = a;
+    }
+    __syncwarp();
+    const float act_sq = warp_sum(lane < A ? a * a : 0.0f);
+    const float tau = lane_tau(c, w);
+    pipeline_steps(sys, c, w, s, tau, lane);
+    const RootFacts after = compute_obs(sys, c, w, s, lane);
+    env_outcome(sys, before, after, act_sq, reward, done);
+    // EpisodeWrapper: steps += 1; done = where(steps >= episode_length, 1, done)
+    el += 1;
+    if (seg.max_steps > 0 && el >= seg.max_steps) done = true;
+    before = after;
+    if (done && seg.autoreset != CARLB_AUTORESET_NONE) {
+      if (seg.final_obs != nullptr && n_steps == 1)
+        for (int i = lane; i < D; i += 32) seg.final_obs[(size_t)env * D + i] = w.obs[i];
+      // AutoResetWrapper: pipeline_state and obs <- the ones stored at reset
+      __syncwarp();
+      row_g2s(w.ls, seg.first_state + (size_t)env * seg.state_words, seg.state_words, lane);
+      for (int i = lane; i < D; i += 32) w.obs[i] = seg.first_obs[(size_t)env * D + i];
+      __syncwarp();
+      s = read_link(w.ls, c.is_link ? lane : 0);
+      __syncwarp();
+      before = compute_obs(sys, c, w, s, lane);
+      for (int i = lane; i < D; i += 32) w.obs[i] = seg.first_obs[(size_t)env * D + i];
+      __syncwarp();
+      el = 0;
+    }
+    if (n_steps > 1 || traj.obs != nullptr) {
+      const size_t row = (size_t)t * seg.n + env;
+      if (traj.obs != nullptr)
+        for (int i = lane; i < D; i += 32) traj.obs[row * D + i] = w.obs[i];
+      if (traj.actions != nullptr && lane < A) static_cast<float*>(traj.actions)[row * A + lane] = a;
+      if (lane == 0) {
+        if (traj.reward != nullptr) traj.reward[row] = reward;
+        if (traj.done != nullptr) traj.done[row] = done ? 1 : 0;
+      }
+    }
+    __syncwarp();
+  }
+  // write back: state row (coalesced through the scratch), obs, scalars
+  if (c.is_link) write_link(w.ls, lane, s);
+  __syncwarp();
+  row_s2g(state_row, w.ls, seg.state_words, lane);
+  for (int i = lane; i < D; i += 32) {
+    const float v = w.obs[i];
+    seg.obs[(size_t)env * D + i] = v;
+    for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
+  }
+  if (lane == 0) {
+    seg.reward[env] = reward;
+    seg.terminated[env] = done ? 1 : 0;  // CARL maps brax `done` (incl. the time limit) to terminated
+    seg.truncated[env] = 0;              // and truncated = False always (wrappers.py:75-78)
+    seg.elapsed[env] = el;
+  }
+}
+
+// ------------------------------------------------------------------------------ reset
+// Env.reset: q = init_q + U(+-noise), qd = noise * N(0,1) (Hopper: both uniform), forward
+// kinematics (pipeline_init), obs; stores the first state/obs for AutoResetWrapper.
+__global__ void __launch_bounds__(kThreads) brax_reset_kernel(const __grid_constant__ BraxSeg seg, const uint8_t* mask,
+                                                              const float* q_in, const float* qd_in) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  stage_system(sm.sys, seg.sys, &sm.bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * kWarpsPerCta + warp;
+  if (env >= seg.n) return;
+  if (mask != nullptr && mask[env] == 0) return;
+  const float* sys = sm.sys;
+  WarpScratch& w = sm.warp[warp];
+  const LaneCtx c = make_lane_ctx(sys, seg.ctx + (size_t)env * seg.n_ctx, seg.n_ctx, lane, true);
+  const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
+  const uint64_t gid = (uint64_t)(seg.global_offset + env);
+  const uint32_t episode = (uint32_t)seg.episode[env];
+  const float noise = sys[H_RESET_NOISE];
+  const bool hopper = (int)sys[H_ENV] == ENV_HOPPER;
+  if (lane < nq) {
+    w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
+                                  : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
+  }
+  if (lane < nqd) {
+    w.qd[lane] = (qd_in != nullptr) ? qd_in[(size_t)env * nqd + lane]
+                 : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -noise, noise)
+                                    : noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
+  }
+  __syncwarp();
+  // forward kinematics down the tree (parents have smaller indices)
+  LinkState s;
+  s.pos = v3(0, 0, 0); s.rot = q4(1, 0, 0, 0); s.vel = v3(0, 0, 0); s.ang = v3(0, 0, 0);
+  for (int l = 0; l < c.L; ++l) {
+    if (lane == l) {
+      const bool world_parent = c.parent < 0;
+      const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
+      s = forward_link(sys, c.lt, w.q, w.qd, world_parent, c.plt, ps);
+      write_link(w.ls, lane, s);
+    }
+    __syncwarp();
+  }
+  compute_obs(sys, c, w, s, lane);
+  const int D = seg.obs_dim;
+  for (int i = seg.state_words - 3 + lane; i < seg.state_words; i += 32)
+    if (i >= c.L * LINK_WORDS) w.ls[i] = 0.0f;  // padding words
+  __syncwarp();
+  row_s2g(seg.state + (size_t)env * seg.state_words, w.ls, seg.state_words, lane);
+  row_s2g(seg.first_state + (size_t)env * seg.state_words, w.ls, seg.state_words, lane);
+  for (int i = lane; i < D; i += 32) {
+    const float v = w.obs[i];
+    seg.obs[(size_t)env * D + i] = v;
+    seg.first_obs[(size_t)env * D + i] = v;
+    for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
+  }
+  if (lane == 0) {
+    seg.reward[env] = 0.0f;
+    seg.terminated[env] = 0;
+    seg.truncated[env] = 0;
+    seg.elapsed[env] = 0;
+    seg.episode[env] = (uint64_t)episode + 1ull;
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+struct BraxHandle {
+  BraxSys* dev_sys = nullptr;
+  float host_table[TABLE_FLOATS] = {};
+  bool have_table = false;
+  uint64_t seed = 0;
+  int stock_contact = 0;
+};
+
+static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
+  switch (kind) {
+    case KIND_BRAX_ANT: L = 9; nq = 15; nqd = 14; A = 8; break;
+    case KIND_BRAX_HALFCHEETAH: L = 7; nq = 9; nqd = 9; A = 6; break;
+    default: L = 4; nq = 6; nqd = 6; A = 3; break;
+  }
+}
+
+int brax_query(int kind, carlb_env_info_t* o) {
+  int L, nq, nqd, A;
+  static_facts(kind, L, nq, nqd, A);
+  const int ex = kind == KIND_BRAX_ANT ? 2 : 1;
+  o->kind = kind;
+  o->state_words = ((LINK_WORDS * L + 3) / 4) * 4;
+  o->obs_dim = (nq - ex) + nqd;
+  o->act_dim = A;
+  o->act_discrete = 0;
+  o->n_actions = 0;
+  o->n_param_rows = 4 + L;
+  o->n_step_rows = 4 + L;
+  o->default_max_steps = 1000;  // brax.envs.create(episode_length=1000)
+  o->gym_reset_draws = 0;
+  o->act_low = -1.0f;
+  o->act_high = 1.0f;
+  return CARLB_OK;
+}
+
+int brax_create(carlb_env* env) {
+  BraxHandle* h = new BraxHandle();
+  cudaError_t e = cudaMalloc(&h->dev_sys, sizeof(BraxSys));
+  if (e != cudaSuccess) {
+    delete h;
+    set_error("cudaMalloc of the Brax system table failed: %s", cudaGetErrorString(e));
+    return CARLB_ERR_CUDA;
+  }
+  env->brax_sys = h;
+  return CARLB_OK;
+}
+
+void brax_destroy(carlb_env* env) {
+  BraxHandle* h = static_cast<BraxHandle*>(env->brax_sys);
+  if (h == nullptr) return;
+  if (h->dev_sys) cudaFree(h->dev_sys);
+  delete h;
+  env->brax_sys = nullptr;
+}
+
+int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_contact) {
+  BraxHandle* h = static_cast<BraxHandle*>(env->brax_sys);
+  if (n_floats != TABLE_FLOATS) {
+    set_error("carlb_brax_set_system: table has %d floats, expected %d", n_floats, TABLE_FLOATS);
+    return CARLB_ERR_INVALID;
+  }
+  int L, nq, nqd, A;
+  static_facts(env->kind, L, nq, nqd, A);
+  if ((int)table[H_N_LINKS] != L || (int)table[H_N_Q] != nq || (int)table[H_N_QD] != nqd || (int)table[H_N_ACT] != A ||
+      (int)table[H_N_POINTS] > MAX_POINTS) {
+    set_error("carlb_brax_set_system: table does not describe env kind %d (links %d, q %d, qd %d, act %d)", env->kind,
+              (int)table[H_N_LINKS], (int)table[H_N_Q], (int)table[H_N_QD], (int)table[H_N_ACT]);
+    return CARLB_ERR_INVALID;
+  }
+  for (int l = 0; l < L; ++l) {
+    const int parent = (int)table[OFF_LINKS + LINK_STRIDE * l + L_PARENT];
+    if (parent >= l) {
+      set_error("carlb_brax_set_system: link %d has parent %d (parents must precede children)", l, parent);
+      return CARLB_ERR_INVALID;
+    }
+  }
+  memcpy(h->host_table, table, sizeof(h->host_table));
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  CARLB_CUDA_CHECK(cudaMemcpy(h->dev_sys->table, table, sizeof(h->host_table), cudaMemcpyHostToDevice));
+  h->have_table = true;
+  h->stock_contact = stock_contact;
+  return CARLB_OK;
+}
+
+static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what) {
+  const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
+  if (h == nullptr || !h->have_table) {
+    set_error("%s: carlb_brax_set_system() has not been called", what);
+    return CARLB_ERR_STATE;
+  }
+  carlb_env_info_t info;
+  brax_query(env->kind, &info);
+  s = BraxSeg{};
+  s.n = env->n;
+  s.max_steps = env->max_steps;
+  s.autoreset = env->autoreset;
+  s.state_words = info.state_words;
+  s.obs_dim = info.obs_dim;
+  s.n_ctx = info.n_param_rows;
+  s.act_dim = info.act_dim;
+  s.global_offset = env->global_offset;
+  s.seed = h->seed;
+  s.sys = h->dev_sys->table;
+  s.state = static_cast<float*>(env->bufs.state);
+  s.ctx = static_cast<const float*>(env->bufs.ctx);
+  s.elapsed = env->bufs.elapsed;
+  s.episode = env->bufs.rng;
+  s.obs = env->bufs.obs;
+  s.reward = env->bufs.reward;
+  s.terminated = env->bufs.terminated;
+  s.truncated = env->bufs.truncated;
+  s.final_obs = env->bufs.final_obs;
+  s.first_state = static_cast<float*>(env->bufs.first_state);
+  s.first_obs = env->bufs.first_obs;
+  s.n_peers = env->n_peers;
+  for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
+  return CARLB_OK;
+}
+
+static inline int brax_grid(int n) { return (n + kWarpsPerCta - 1) / kWarpsPerCta; }
+
+int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
+  BraxHandle* h = static_cast<BraxHandle*>(env->brax_sys);
+  h->seed = seed;
+  CARLB_CUDA_CHECK(cudaMemsetAsync(env->bufs.rng, 0, sizeof(uint64_t) * 4 * (size_t)env->n, st));
+  return CARLB_OK;
+}
+
+int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st) {
+  BraxSeg seg;
+  int rc = make_brax_seg(env, seg, "carlb_env_reset");
+  if (rc != CARLB_OK) return rc;
+  brax_reset_kernel<<<brax_grid(env->n), kThreads, sizeof(SmemLayout), st>>>(seg, mask, q, qd);
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
+  return brax_reset_from(env, mask, nullptr, nullptr, st);
+}
+
+int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st) {
+  (void)act_dtype;
+  BraxSeg seg;
+  int rc = make_brax_seg(env, seg, "carlb_env_step");
+  if (rc != CARLB_OK) return rc;
+  const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
+  carlb_traj_t tj{};
+  brax_step_kernel<<<brax_grid(env->n), kThreads, sizeof(SmemLayout), st>>>(seg, static_cast<const float*>(actions), 1, 0, 0,
+                                                                            tj, h->stock_contact);
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                 int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
+  (void)act_dtype;
+  BraxSeg seg;
+  int rc = make_brax_seg(env, seg, "carlb_env_rollout");
+  if (rc != CARLB_OK) return rc;
+  if (n_steps == 0) return CARLB_OK;
+  const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
+  carlb_traj_t tj{};
+  if (traj != nullptr) tj = *traj;
+  seg.final_obs = nullptr;
+  brax_step_kernel<<<brax_grid(env->n), kThreads, sizeof(SmemLayout), st>>>(seg, static_cast<const float*>(actions), n_steps,
+                                                                            policy_seed, step_base, tj, h->stock_contact);
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+}  // namespace carlb

@@ -18,9 +18,7 @@ struct carlb_env {
   carlb_buffers_t bufs{};
   int n_peers = 0;
   float* peer_obs[CARLB_MAX_PEERS] = {};
-  void* brax_sys = nullptr;  // device copy of the per-handle Brax system table
-  float brax_tunables[32] = {};
-  int brax_n_tunables = 0;
+  void* brax_sys = nullptr;  // BraxHandle: device copy of the per-handle Brax system table
 };
 
 namespace carlb {
@@ -47,8 +45,8 @@ int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st);
 int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st);
 int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                  int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
-int brax_set_tunables(carlb_env* env, const float* values, int n_values);
-int brax_get_tunables(int kind, float* values, int max_values, int* n_values);
+int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_contact);
+int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st);
 
 #define CARLB_CUDA_CHECK(expr)                                                            \
   do {                                                                                    \

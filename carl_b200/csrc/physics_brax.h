@@ -1,0 +1,354 @@
+// Brax spring-pipeline physics of the batched-step engine: per-link / per-joint / per-contact
+// building blocks shared by the warp-per-env CUDA kernels (brax.cu) and the g++-compiled test
+// shim (tests/hostcheck).
+//
+// What this restates: the path `CARLEnv.step` -> `BraxGymWrapper.step` (carl/envs/brax/
+// wrappers.py:62-67,74-78) -> brax.envs.{ant,half_cheetah,hopper}.step -> PipelineEnv.pipeline_step
+// = n_frames x brax.spring.pipeline.step (maximal coordinates: joint spring/damper forces ->
+// semi-implicit velocity update -> ground-contact impulses -> pose integration), plus
+// pipeline_init (forward kinematics) and kinematics.inverse (q, qd for the observation).
+// brax==0.12.1 (pyproject.toml:62-63) is NOT vendored in the reference tree: the algorithm is
+// restated from the published Brax v2 sources (DESIGN.md §brax lists every
+// assumption); all system constants come from the table built in carl_b200/envs/brax_system.py.
+//
+// Conventions: quaternions are (w, x, y, z); per-link state is kept in the centre-of-mass frame
+// (pos = world COM, rot = link-frame orientation, vel = COM linear velocity, ang = world angular
+// velocity), as Brax integrates `x_i, xd_i`. float32 throughout (the reference's JAX pipeline is
+// float32).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "rng.h"
+
+namespace carlb {
+namespace brax {
+
+// ---- packed system table layout (mirrors carl_b200/envs/brax_system.py) ---------------------
+constexpr int MAX_LINKS = 12;
+constexpr int MAX_POINTS = 32;
+constexpr int MAX_Q = 24;
+constexpr int HEADER = 32;
+constexpr int LINK_STRIDE = 40;
+constexpr int POINT_STRIDE = 8;
+constexpr int OFF_LINKS = HEADER;
+constexpr int OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS;
+constexpr int OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS;
+constexpr int TABLE_FLOATS = OFF_INIT_Q + MAX_Q;
+
+enum Hdr {
+  H_N_LINKS = 0, H_N_Q, H_N_QD, H_N_POINTS, H_N_FRAMES, H_DT, H_ENV, H_N_ACT,
+  H_STIFFNESS, H_VEL_DAMPING_C, H_LIMIT_STIFFNESS, H_ANG_DAMPING_C, H_BAUMGARTE, H_VEL_DAMPING, H_MASS_SCALE,
+  H_INERTIA_SCALE,
+  H_RESET_NOISE, H_CTRL_COST, H_HEALTHY_REWARD, H_HEALTHY_Z_MIN, H_HEALTHY_Z_MAX, H_FORWARD_WEIGHT, H_ANGLE_MIN,
+  H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS
+};
+enum LinkSlot {
+  L_PARENT = 0, L_TYPE, L_QIDX, L_QDIDX, L_TPOS = 4, L_TROT = 7, L_JPOS = 11, L_JROT = 14, L_LIM_LO = 18, L_LIM_HI = 19,
+  L_COM = 20, L_IROT = 23, L_IDIAG = 27, L_MASS = 30, L_GEAR = 31, L_ACT = 32, L_CTRL_LO = 33, L_CTRL_HI = 34,
+  L_FIRST_PT = 35, L_N_PT = 36
+};
+enum LinkType { TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_PLANAR = 3 };
+enum EnvId { ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2 };
+// per-env context rows: gravity, friction, elasticity, ang_damping, then one mass per link
+enum CtxRow { C_GRAVITY = 0, C_FRICTION, C_ELASTICITY, C_ANG_DAMPING, C_MASS0 };
+constexpr int LINK_WORDS = 13;  // pos3 rot4 vel3 ang3
+
+// ---- small vector algebra -------------------------------------------------------------------
+struct V3 { float x, y, z; };
+struct Q4 { float w, x, y, z; };
+CARLB_HD V3 v3(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+CARLB_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+CARLB_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+CARLB_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+CARLB_HD V3 operator*(float s, V3 a) { return v3(a.x * s, a.y * s, a.z * s); }
+CARLB_HD float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+CARLB_HD V3 cross(V3 a, V3 b) { return v3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+CARLB_HD float norm(V3 a) { return sqrtf(dot(a, a)); }
+CARLB_HD Q4 q4(float w, float x, float y, float z) { Q4 r; r.w = w; r.x = x; r.y = y; r.z = z; return r; }
+CARLB_HD Q4 qmul(Q4 a, Q4 b) {
+  return q4(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+            a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x, a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w);
+}
+CARLB_HD Q4 qconj(Q4 a) { return q4(a.w, -a.x, -a.y, -a.z); }
+CARLB_HD Q4 qnormalize(Q4 a) {
+  const float n = sqrtf(a.w * a.w + a.x * a.x + a.y * a.y + a.z * a.z);
+  const float inv = 1.0f / n;
+  return q4(a.w * inv, a.x * inv, a.y * inv, a.z * inv);
+}
+// brax.math.rotate: r = 2 (u.v) u + (s^2 - u.u) v + 2 s (u x v)
+CARLB_HD V3 rotate(V3 v, Q4 q) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const float s = q.w;
+  return 2.0f * dot(u, v) * u + (s * s - dot(u, u)) * v + 2.0f * s * cross(u, v);
+}
+CARLB_HD V3 inv_rotate(V3 v, Q4 q) { return rotate(v, qconj(q)); }
+CARLB_HD Q4 quat_axis_angle(V3 axis, float angle) {
+  const float h = 0.5f * angle;
+  const float s = sinf(h);
+  return q4(cosf(h), axis.x * s, axis.y * s, axis.z * s);
+}
+CARLB_HD V3 ld3(const float* p) { return v3(p[0], p[1], p[2]); }
+CARLB_HD Q4 ld4(const float* p) { return q4(p[0], p[1], p[2], p[3]); }
+
+struct LinkState {
+  V3 pos;  // world COM position
+  Q4 rot;  // link frame orientation
+  V3 vel;  // COM linear velocity (world)
+  V3 ang;  // angular velocity (world)
+};
+struct Wrench {
+  V3 f;  // force (world)
+  V3 t;  // torque about the link COM (world)
+};
+
+CARLB_HD const float* link_tab(const float* sys, int l) { return sys + OFF_LINKS + LINK_STRIDE * l; }
+CARLB_HD const float* point_tab(const float* sys, int p) { return sys + OFF_POINTS + POINT_STRIDE * p; }
+
+// link-frame origin in the world (Brax `x.pos`) from the COM state
+CARLB_HD V3 link_origin(const LinkState& s, const float* lt) { return s.pos - rotate(ld3(lt + L_COM), s.rot); }
+CARLB_HD V3 origin_velocity(const LinkState& s, const float* lt) {
+  return s.vel - cross(s.ang, rotate(ld3(lt + L_COM), s.rot));
+}
+
+// effective mass / inverse inertia of the spring backend: mass^(1 - spring_mass_scale),
+// diag(I)^(1 - spring_inertia_scale) in the principal frame (brax.spring com.inv_inertia)
+CARLB_HD float eff_mass(float mass, const float* sys) { return powf(mass, 1.0f - sys[H_MASS_SCALE]); }
+CARLB_HD V3 eff_inv_idiag(const float* lt, const float* sys) {
+  const float e = 1.0f - sys[H_INERTIA_SCALE];
+  return v3(1.0f / powf(lt[L_IDIAG + 0], e), 1.0f / powf(lt[L_IDIAG + 1], e), 1.0f / powf(lt[L_IDIAG + 2], e));
+}
+CARLB_HD V3 apply_inv_inertia(V3 v, Q4 rot, const float* lt, V3 inv_idiag) {
+  const Q4 r = qmul(rot, ld4(lt + L_IROT));
+  V3 w = inv_rotate(v, r);
+  w = v3(w.x * inv_idiag.x, w.y * inv_idiag.y, w.z * inv_idiag.z);
+  return rotate(w, r);
+}
+
+// ---- joints (brax.spring.joints.resolve, one joint) ------------------------------------------
+// Output of one joint: force/torque in the WORLD frame acting on the child at its anchor `a_c`
+// and the opposite reaction on the parent at its anchor `a_p`; plus the joint coordinate (q, qd)
+// of kinematics.inverse for the observation.
+struct JointOut {
+  Wrench child;   // wrench on the child about its COM
+  Wrench parent;  // wrench on the parent about its COM (zero for a world parent)
+  float q[3];
+  float qd[3];
+};
+
+// child `c` (table row lt), parent state `p` (ignored when world_parent), parent row plt
+CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
+                                const float* plt, const LinkState& p, float tau) {
+  JointOut o;
+  const int type = (int)lt[L_TYPE];
+  const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
+  const V3 t_pos = ld3(lt + L_TPOS), j_pos = ld3(lt + L_JPOS);
+  // anchors (kinematics.world_to_joint): a_c = x_c o joint ; a_p = x_p o link.transform o joint
+  const V3 xc_pos = link_origin(c, lt);
+  const V3 ac_pos = xc_pos + rotate(j_pos, c.rot);
+  const Q4 ac_rot = qmul(c.rot, j_rot);
+  V3 ap_pos, xp_pos = v3(0, 0, 0), vp = v3(0, 0, 0), wp = v3(0, 0, 0), pcom = v3(0, 0, 0);
+  Q4 xp_rot = q4(1, 0, 0, 0);
+  if (!world_parent) {
+    xp_pos = link_origin(p, plt);
+    xp_rot = p.rot;
+    wp = p.ang;
+    pcom = p.pos;
+  }
+  ap_pos = xp_pos + rotate(t_pos + rotate(j_pos, t_rot), xp_rot);
+  const Q4 ap_rot = qmul(qmul(xp_rot, t_rot), j_rot);
+  if (!world_parent) vp = p.vel + cross(p.ang, ap_pos - p.pos);
+  const V3 vc = c.vel + cross(c.ang, ac_pos - c.pos);
+  // joint-frame offsets and rates
+  const V3 jpos = inv_rotate(ac_pos - ap_pos, ap_rot);
+  const Q4 jrot = qmul(qconj(ap_rot), ac_rot);
+  const V3 jvel = inv_rotate(vc - vp, ap_rot);
+  const V3 jang = inv_rotate(c.ang - wp, ap_rot);
+  const float k = sys[H_STIFFNESS], cv = sys[H_VEL_DAMPING_C], kl = sys[H_LIMIT_STIFFNESS], ca = sys[H_ANG_DAMPING_C];
+  const V3 ex = v3(1, 0, 0);
+  // hinge angle about the joint x axis
+  const V3 yc = rotate(v3(0, 1, 0), jrot);
+  const float psi = atan2f(yc.z, yc.y);
+  V3 fv, fa;
+  // torque aligning the child's joint axis with the parent's
+  const V3 axis_c_x = rotate(ex, jrot);
+  fa = k * cross(axis_c_x, ex);
+  if (type == TYPE_PLANAR) {
+    // slide-x / slide-z / hinge-y root: only the off-plane offset and off-axis rotation are constrained
+    fv = v3(-k * jpos.x - cv * jvel.x, 0.0f, 0.0f);
+    fa = fa - ca * v3(0.0f, jang.y, jang.z);
+  } else {
+    fv = (-k) * jpos - cv * jvel;
+    const float lo = lt[L_LIM_LO], hi = lt[L_LIM_HI];
+    float dang = 0.0f;
+    if (psi < lo) dang = lo - psi;
+    if (psi > hi) dang = hi - psi;
+    fa = fa + (kl * dang) * ex;
+    fa = fa - ca * jang;
+    fa = fa + tau * ex;  // actuator torque about the hinge axis
+  }
+  const V3 F = rotate(fv, ap_rot), T = rotate(fa, ap_rot);
+  o.child.f = F;
+  o.child.t = T + cross(ac_pos - c.pos, F);
+  o.parent.f = v3(0, 0, 0) - F;
+  o.parent.t = (v3(0, 0, 0) - T) - cross(ap_pos - pcom, F);
+  // joint coordinates for the observation (kinematics.inverse)
+  o.q[0] = psi; o.q[1] = 0; o.q[2] = 0;
+  o.qd[0] = jang.x; o.qd[1] = 0; o.qd[2] = 0;
+  if (type == TYPE_PLANAR) {
+    const V3 vo = origin_velocity(c, lt);
+    o.q[0] = xc_pos.x - t_pos.x; o.q[1] = xc_pos.z - t_pos.z; o.q[2] = psi;
+    o.qd[0] = vo.x; o.qd[1] = vo.z; o.qd[2] = jang.x;
+  }
+  return o;
+}
+
+// ---- semi-implicit velocity update (brax.spring.integrator.integrate_xdd) ---------------------
+CARLB_HD void integrate_xdd(LinkState& s, const Wrench& w, const float* sys, const float* lt, float mass,
+                            float gravity, float ang_damping) {
+  const float dt = sys[H_DT];
+  const float m = eff_mass(mass, sys);
+  const V3 acc = v3(0, 0, gravity) + w.f * (1.0f / m);
+  const V3 alpha = apply_inv_inertia(w.t, s.rot, lt, eff_inv_idiag(lt, sys));
+  s.vel = s.vel + acc * dt;
+  s.ang = s.ang + alpha * dt;
+  s.vel = s.vel * expf(sys[H_VEL_DAMPING] * dt);
+  s.ang = s.ang * expf(ang_damping * dt);
+}
+
+// ---- ground contact of one candidate point (brax.spring.collisions._collide vs the plane z=0) --
+struct ContactOut {
+  V3 p;        // linear impulse on the link
+  V3 t;        // angular impulse about the link COM
+  float active;
+};
+
+CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const float* lt, const LinkState& s, float mass,
+                                    float friction, float elasticity) {
+  ContactOut o;
+  o.p = v3(0, 0, 0); o.t = v3(0, 0, 0); o.active = 0.0f;
+  const float radius = pt[4];
+  const V3 origin = link_origin(s, lt);
+  const V3 c = origin + rotate(v3(pt[1], pt[2], pt[3]), s.rot);  // sphere centre in the world
+  const float dist = c.z - radius;                               // signed distance to the plane
+  const float penetration = -dist;
+  if (!(penetration > 0.0f)) return o;
+  const V3 n = v3(0, 0, 1);
+  const V3 cpos = v3(c.x, c.y, 0.5f * dist);  // midway between the two surfaces
+  const V3 rel_pos = cpos - s.pos;
+  const V3 rel_vel = s.vel + cross(s.ang, rel_pos);
+  const float normal_vel = dot(n, rel_vel);
+  const float inv_m = 1.0f / eff_mass(mass, sys);
+  const V3 inv_i = eff_inv_idiag(lt, sys);
+  const V3 temp1 = apply_inv_inertia(cross(rel_pos, n), s.rot, lt, inv_i);
+  const float ang = dot(n, cross(temp1, rel_pos));
+  const float dt = sys[H_DT];
+  const float baumgarte_vel = sys[H_BAUMGARTE] * penetration / dt;
+  const float impulse = (-1.0f * (1.0f + elasticity) * normal_vel + baumgarte_vel) / (inv_m + ang);
+  const V3 impulse_vec = impulse * n;
+  // drag from friction, parallel to the surface
+  const V3 vel_d = rel_vel - normal_vel * n;
+  const float speed_d = norm(vel_d);
+  float impulse_d = speed_d / (inv_m + ang);
+  const V3 dir_d = vel_d * (1.0f / (1e-6f + speed_d));
+  impulse_d = fminf(impulse_d, friction * impulse);
+  const V3 impulse_d_vec = (-impulse_d) * dir_d;
+  const bool apply_n = (normal_vel < 0.0f) && (impulse > 0.0f);
+  const bool apply_d = apply_n && (speed_d > 0.01f);
+  if (!apply_n) return o;
+  V3 total = impulse_vec;
+  if (apply_d) total = total + impulse_d_vec;
+  o.p = total;
+  o.t = cross(rel_pos, total);
+  o.active = 1.0f;
+  return o;
+}
+
+// delta-velocity from the link's summed contact impulses, averaged over its active contacts
+CARLB_HD void integrate_xdv(LinkState& s, V3 p_sum, V3 t_sum, float n_active, const float* sys, const float* lt,
+                            float mass) {
+  if (!(n_active > 0.0f)) return;
+  const float inv_n = 1.0f / n_active;
+  s.vel = s.vel + p_sum * (inv_n / eff_mass(mass, sys));
+  s.ang = s.ang + apply_inv_inertia(t_sum * inv_n, s.rot, lt, eff_inv_idiag(lt, sys));
+}
+
+// ---- pose integration (brax.spring.integrator.integrate) --------------------------------------
+CARLB_HD void integrate_pose(LinkState& s, float dt) {
+  s.pos = s.pos + s.vel * dt;
+  const Q4 w = q4(0.0f, s.ang.x * 0.5f * dt, s.ang.y * 0.5f * dt, s.ang.z * 0.5f * dt);
+  const Q4 d = qmul(w, s.rot);
+  s.rot = qnormalize(q4(s.rot.w + d.w, s.rot.x + d.x, s.rot.y + d.y, s.rot.z + d.z));
+}
+
+// ---- forward kinematics of one link (kinematics.forward + com.from_world), parent first ------
+CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* q, const float* qd, bool world_parent,
+                                const float* plt, const LinkState& p) {
+  const int type = (int)lt[L_TYPE];
+  const float* ql = q + (int)lt[L_QIDX];
+  const float* qdl = qd + (int)lt[L_QDIDX];
+  V3 xpos, xvel, xang;
+  Q4 xrot;
+  if (type == TYPE_FREE) {
+    xpos = v3(ql[0], ql[1], ql[2]);
+    xrot = qnormalize(q4(ql[3], ql[4], ql[5], ql[6]));
+    xvel = v3(qdl[0], qdl[1], qdl[2]);
+    xang = rotate(v3(qdl[3], qdl[4], qdl[5]), xrot);
+  } else {
+    const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
+    const V3 t_pos = ld3(lt + L_TPOS), j_pos = ld3(lt + L_JPOS);
+    const V3 axis = rotate(v3(1, 0, 0), j_rot);  // hinge axis in the child link frame
+    V3 xp_pos = v3(0, 0, 0), vp = v3(0, 0, 0), wp = v3(0, 0, 0);
+    Q4 xp_rot = q4(1, 0, 0, 0);
+    if (!world_parent) {
+      xp_pos = link_origin(p, plt);
+      xp_rot = p.rot;
+      vp = origin_velocity(p, plt);
+      wp = p.ang;
+    }
+    float angle, rate;
+    V3 trans = v3(0, 0, 0), tvel = v3(0, 0, 0);
+    if (type == TYPE_PLANAR) {
+      trans = v3(ql[0], 0.0f, ql[1]);
+      tvel = v3(qdl[0], 0.0f, qdl[1]);
+      angle = ql[2];
+      rate = qdl[2];
+    } else {
+      angle = ql[0];
+      rate = qdl[0];
+    }
+    const Q4 jrot = qnormalize(quat_axis_angle(axis, angle));
+    const V3 jpos = trans + (j_pos - rotate(j_pos, jrot));  // the joint position is the rotation pivot
+    const V3 lpos = t_pos + rotate(jpos, t_rot);
+    const Q4 lrot = qmul(t_rot, jrot);
+    xpos = xp_pos + rotate(lpos, xp_rot);
+    xrot = qnormalize(qmul(xp_rot, lrot));
+    xvel = vp + cross(wp, xpos - xp_pos) + rotate(tvel, xp_rot);
+    xang = wp + rotate(axis * rate, xrot);
+  }
+  LinkState s;
+  const V3 rc = rotate(ld3(lt + L_COM), xrot);
+  s.pos = xpos + rc;
+  s.rot = xrot;
+  s.vel = xvel + cross(xang, rc);
+  s.ang = xang;
+  return s;
+}
+
+// Reset-noise draws (throughput-mode RNG; the reference's JAX threefry stream is not
+// reproducible without JAX): one Philox block per (seed, env, episode, index).
+CARLB_HD float reset_uniform(uint64_t seed, uint64_t env, uint32_t episode, uint32_t idx, float lo, float hi) {
+  const Philox4 r = philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), episode, 0x52535430u + idx, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  return lo + (hi - lo) * u32_to_unit_float(r.v[0]);
+}
+CARLB_HD float reset_normal(uint64_t seed, uint64_t env, uint32_t episode, uint32_t idx) {
+  const Philox4 r = philox4x32_10((uint32_t)env, (uint32_t)(env >> 32), episode, 0x4e524d30u + idx, (uint32_t)seed,
+                                  (uint32_t)(seed >> 32));
+  const float u1 = ((float)(r.v[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = u32_to_unit_float(r.v[1]);
+  return sqrtf(-2.0f * logf(u1)) * cosf(6.283185307179586f * u2);
+}
+
+}  // namespace brax
+}  // namespace carlb

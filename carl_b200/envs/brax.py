@@ -70,19 +70,58 @@ class CARLBraxEnv(CARLEnv):
 
     def __init__(self, env=None, batch_size: int | None = None, contexts=None, obs_context_features=None,
                  obs_context_as_dict: bool = True, context_selector=None, context_selector_kwargs=None,
-                 use_language_goals: bool = False, **kwargs):
+                 use_language_goals: bool = False, brax_tunables: dict | None = None, **kwargs):
         """``carl_brax_env.py:119-236``. ``batch_size`` is the reference's name for the number of
         batched env instances (``brax.envs.create(batch_size=...)``, :163-167); here every instance
         may carry its own context."""
         if batch_size is not None and batch_size != 1 and "num_envs" not in kwargs:
             kwargs["num_envs"] = int(batch_size)
         self.use_language_goals = use_language_goals
+        from carl_b200.envs import brax_system as bs
+
+        self._sysd = bs.build_system(bs.MODELS[self.env_name](), brax_tunables) if brax_tunables else bs.SYSTEMS[self.env_name]
+        self.link_names = list(self._sysd["link_names"])
         super().__init__(env=env, contexts=contexts, obs_context_features=obs_context_features,
                          obs_context_as_dict=obs_context_as_dict, context_selector=context_selector,
                          context_selector_kwargs=context_selector_kwargs, **kwargs)
 
     def _default_autoreset(self) -> bool:
         return True  # brax.envs.create(auto_reset=True) wraps the env in AutoResetWrapper
+
+    def _post_alloc(self) -> None:
+        """Batched stand-in for ``mjcf.load`` (carl_brax_env.py:271-272): upload the system table."""
+        import ctypes
+
+        import numpy as np
+
+        from carl_b200 import _native
+
+        t = np.ascontiguousarray(self._sysd["table"], dtype=np.float32)
+        self._sys_table_host = t
+        _native.check(self._lib.carlb_brax_set_system(
+            self._handle, t.ctypes.data_as(ctypes.c_void_p), int(t.size), 1 if self.context_mode == "reference" else 0))
+
+    def reset_from_q(self, q, qd, mask=None):
+        """Parity-mode reset: ``pipeline_init(q, qd)`` from caller-supplied generalized coordinates
+        (``float32[num_envs, n_q]`` / ``[num_envs, n_qd]``) instead of the noise draws of the
+        reference's ``Env.reset`` (its JAX PRNG stream cannot be reproduced without JAX)."""
+        import torch
+
+        from carl_b200 import _native
+
+        changed = self._progress_instance(None)
+        if changed.any():
+            self._update_context(changed if not changed.all() else None)
+        qt = torch.as_tensor(q, dtype=torch.float32, device=self.device).contiguous()
+        qdt = torch.as_tensor(qd, dtype=torch.float32, device=self.device).contiguous()
+        assert qt.shape == (self.num_envs, self._sysd["n_q"]) and qdt.shape == (self.num_envs, self._sysd["n_qd"])
+        mt = None if mask is None else torch.as_tensor(mask, dtype=torch.uint8, device=self.device)
+        if not self._seeded:
+            _native.check(self._lib.carlb_env_seed(self._handle, 0, self._stream()))
+            self._seeded = True
+        _native.check(self._lib.carlb_brax_reset_from_q(
+            self._handle, None if mt is None else mt.data_ptr(), qt.data_ptr(), qdt.data_ptr(), self._stream()))
+        return self._add_context_to_state(self._obs), {"context_id": self.context_id}
 
     @classmethod
     def get_default_context(cls) -> Context:

@@ -1,0 +1,341 @@
+"""Brax system tables for the spring pipeline (host-side model building).
+
+The reference rebuilds its ``brax.System`` from the MJCF assets inside the brax package on every
+context change (``mjcf.load(epath.resource_path("brax") / asset_path)``,
+``carl/envs/brax/carl_brax_env.py:271-272``). brax 0.12.1 and its assets are NOT in the reference
+tree, so the three in-scope bodies are restated here from the standard Gym/MuJoCo models that
+Brax ships: the geometry is *pinned* by CARL's own per-link mass defaults
+(``carl_halfcheetah.py:40-57``, ``carl_hopper.py:40-48``), which are the masses MuJoCo derives from
+exactly these geoms -- ``tests/test_brax_system.py`` checks every one of them to 7 digits.
+
+What is NOT pinned by anything in the reference (and is therefore exposed as named tunables that
+a golden dump from a real Brax install can overwrite, ``tools/gen_brax_golden.py``): the Brax
+``<custom>`` constants of the spring backend (constraint stiffness / damping, baumgarte_erp,
+spring_mass_scale, spring_inertia_scale, ang_damping).
+
+The packed ``float32`` table built here is uploaded once per handle (``carlb_brax_set_system``)
+and staged by every CTA into shared memory with one TMA bulk copy.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MAX_LINKS = 12
+MAX_POINTS = 32
+MAX_Q = 24
+HEADER = 32
+LINK_STRIDE = 40
+POINT_STRIDE = 8
+OFF_LINKS = HEADER
+OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS
+OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS
+TABLE_FLOATS = OFF_INIT_Q + MAX_Q  # 792 floats = 3168 B (a multiple of 16 B for the bulk copy)
+
+# header slots
+H_N_LINKS, H_N_Q, H_N_QD, H_N_POINTS, H_N_FRAMES, H_DT, H_ENV, H_N_ACT = range(8)
+(H_STIFFNESS, H_VEL_DAMPING_C, H_LIMIT_STIFFNESS, H_ANG_DAMPING_C, H_BAUMGARTE, H_VEL_DAMPING, H_MASS_SCALE,
+ H_INERTIA_SCALE) = range(8, 16)
+(H_RESET_NOISE, H_CTRL_COST, H_HEALTHY_REWARD, H_HEALTHY_Z_MIN, H_HEALTHY_Z_MAX, H_FORWARD_WEIGHT, H_ANGLE_MIN,
+ H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS) = range(16, 28)
+TUNABLE_NAMES = ["constraint_stiffness", "constraint_vel_damping", "constraint_limit_stiffness",
+                 "constraint_ang_damping", "baumgarte_erp", "vel_damping", "spring_mass_scale",
+                 "spring_inertia_scale"]
+
+# link slots
+(L_PARENT, L_TYPE, L_QIDX, L_QDIDX) = range(4)
+L_TPOS, L_TROT, L_JPOS, L_JROT, L_LIM_LO, L_LIM_HI = 4, 7, 11, 14, 18, 19
+L_COM, L_IROT, L_IDIAG, L_MASS, L_GEAR, L_ACT, L_CTRL_LO, L_CTRL_HI, L_FIRST_PT, L_N_PT = 20, 23, 27, 30, 31, 32, 33, 34, 35, 36
+TYPE_FREE, TYPE_HINGE, TYPE_PLANAR = 0, 1, 3
+ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER = 0, 1, 2
+
+
+# ----------------------------------------------------------------------------- math
+def quat_mul(a, b):
+    aw, ax, ay, az = a
+    bw, bx, by, bz = b
+    return np.array([aw * bw - ax * bx - ay * by - az * bz, aw * bx + ax * bw + ay * bz - az * by,
+                     aw * by - ax * bz + ay * bw + az * bx, aw * bz + ax * by - ay * bx + az * bw])
+
+
+def quat_axis_angle(axis, angle):
+    axis = np.asarray(axis, dtype=np.float64)
+    axis = axis / np.linalg.norm(axis)
+    return np.concatenate([[np.cos(angle / 2)], np.sin(angle / 2) * axis])
+
+
+def quat_to_mat(q):
+    w, x, y, z = q
+    return np.array([
+        [1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+        [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+        [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def mat_to_quat(m):
+    t = np.trace(m)
+    if t > 0:
+        s = np.sqrt(t + 1.0) * 2
+        q = np.array([0.25 * s, (m[2, 1] - m[1, 2]) / s, (m[0, 2] - m[2, 0]) / s, (m[1, 0] - m[0, 1]) / s])
+    elif m[0, 0] > m[1, 1] and m[0, 0] > m[2, 2]:
+        s = np.sqrt(1.0 + m[0, 0] - m[1, 1] - m[2, 2]) * 2
+        q = np.array([(m[2, 1] - m[1, 2]) / s, 0.25 * s, (m[0, 1] + m[1, 0]) / s, (m[0, 2] + m[2, 0]) / s])
+    elif m[1, 1] > m[2, 2]:
+        s = np.sqrt(1.0 + m[1, 1] - m[0, 0] - m[2, 2]) * 2
+        q = np.array([(m[0, 2] - m[2, 0]) / s, (m[0, 1] + m[1, 0]) / s, 0.25 * s, (m[1, 2] + m[2, 1]) / s])
+    else:
+        s = np.sqrt(1.0 + m[2, 2] - m[0, 0] - m[1, 1]) * 2
+        q = np.array([(m[1, 0] - m[0, 1]) / s, (m[0, 2] + m[2, 0]) / s, (m[1, 2] + m[2, 1]) / s, 0.25 * s])
+    return q / np.linalg.norm(q)
+
+
+def frame_with_x(axis):
+    """Rotation whose x column is ``axis`` (the joint frame: first dof axis -> x)."""
+    x = np.asarray(axis, dtype=np.float64)
+    x = x / np.linalg.norm(x)
+    helper = np.array([0.0, 0.0, 1.0]) if abs(x[2]) < 0.9 else np.array([0.0, 1.0, 0.0])
+    y = np.cross(helper, x)
+    y /= np.linalg.norm(y)
+    z = np.cross(x, y)
+    return mat_to_quat(np.stack([x, y, z], axis=1))
+
+
+# ------------------------------------------------------------------------- geometry
+def capsule(p0, p1, r):
+    p0, p1 = np.asarray(p0, float), np.asarray(p1, float)
+    return dict(type="capsule", p0=p0, p1=p1, r=float(r))
+
+
+def capsule_axis_angle(pos, axis, angle, r, half):
+    """MJCF capsule given by pos + axisangle + size (radius, half-length); local axis is z."""
+    d = quat_to_mat(quat_axis_angle(axis, angle)) @ np.array([0.0, 0.0, half])
+    pos = np.asarray(pos, float)
+    return capsule(pos - d, pos + d, r)
+
+
+def sphere(pos, r):
+    return dict(type="sphere", p0=np.asarray(pos, float), r=float(r))
+
+
+def geom_mass_inertia(g, density):
+    """MuJoCo ``inertiafromgeom``: mass, COM and inertia tensor (about the COM, link frame)."""
+    r = g["r"]
+    if g["type"] == "sphere":
+        m = density * 4.0 / 3.0 * np.pi * r**3
+        return m, g["p0"], np.eye(3) * (0.4 * m * r * r)
+    axis = g["p1"] - g["p0"]
+    h = np.linalg.norm(axis)
+    z = axis / h
+    m_c = density * np.pi * r * r * h
+    m_s = density * 4.0 / 3.0 * np.pi * r**3
+    i_ax = m_c * r * r / 2 + m_s * 0.4 * r * r
+    i_lat = m_c * (r * r / 4 + h * h / 12) + m_s * (0.4 * r * r + h * h / 4 + 3 * h * r / 8)
+    zz = np.outer(z, z)
+    inertia = i_lat * (np.eye(3) - zz) + i_ax * zz
+    return m_c + m_s, 0.5 * (g["p0"] + g["p1"]), inertia
+
+
+def body_inertia(geoms, density):
+    parts = [geom_mass_inertia(g, density) for g in geoms]
+    m = sum(p[0] for p in parts)
+    com = sum(p[0] * p[1] for p in parts) / m
+    inertia = np.zeros((3, 3))
+    for mi, ci, ii in parts:
+        d = ci - com
+        inertia += ii + mi * (np.dot(d, d) * np.eye(3) - np.outer(d, d))
+    w, v = np.linalg.eigh(inertia)
+    if np.linalg.det(v) < 0:
+        v[:, 2] = -v[:, 2]
+    if np.allclose(inertia, np.diag(np.diag(inertia)), atol=1e-12 * max(1.0, np.abs(inertia).max())):
+        w, v = np.diag(inertia).copy(), np.eye(3)  # already principal: keep the link axes
+    return m, com, mat_to_quat(v), w
+
+
+def contact_points(geoms):
+    pts = []
+    for g in geoms:
+        if g["type"] == "sphere":
+            pts.append((g["p0"], g["r"], g.get("friction")))
+        else:  # capsule vs plane: both end spheres are contact candidates
+            pts.append((g["p0"], g["r"], g.get("friction")))
+            pts.append((g["p1"], g["r"], g.get("friction")))
+    return pts
+
+
+# --------------------------------------------------------------------------- models
+def _link(name, parent, typ, pos, geoms, axis=None, joint_pos=(0, 0, 0), limit=(0, 0), gear=0.0, quat=(1, 0, 0, 0)):
+    return dict(name=name, parent=parent, type=typ, pos=np.asarray(pos, float), quat=np.asarray(quat, float),
+                geoms=geoms, axis=axis, joint_pos=np.asarray(joint_pos, float), limit=limit, gear=gear)
+
+
+def ant_model():
+    """Brax/Gym ``ant.xml``: torso sphere + 4 x (aux capsule fused into the torso link, hip link,
+    ankle link); hip hinge about z (+-30 deg), ankle hinge about (-+1, 1, 0) (30..70 deg, mirrored)."""
+    r = 0.08
+    deg = np.pi / 180
+    torso_geoms = [sphere((0, 0, 0), 0.25)] + [capsule((0, 0, 0), (sx * 0.2, sy * 0.2, 0), r)
+                                              for sx, sy in ((1, 1), (-1, 1), (-1, -1), (1, -1))]
+    links = [_link("torso", -1, TYPE_FREE, (0, 0, 0.75), torso_geoms)]
+    legs = [  # (sx, sy, ankle axis, ankle range)
+        (1, 1, (-1, 1, 0), (30, 70)), (-1, 1, (1, 1, 0), (-70, -30)),
+        (-1, -1, (-1, 1, 0), (-70, -30)), (1, -1, (1, 1, 0), (30, 70))]
+    for i, (sx, sy, aax, arange) in enumerate(legs, start=1):
+        hip = len(links)
+        links.append(_link(f"aux_{i}", 0, TYPE_HINGE, (sx * 0.2, sy * 0.2, 0), [capsule((0, 0, 0), (sx * 0.2, sy * 0.2, 0), r)],
+                           axis=(0, 0, 1), limit=(-30 * deg, 30 * deg), gear=150.0))
+        links.append(_link(f"ankle_{i}", hip, TYPE_HINGE, (sx * 0.2, sy * 0.2, 0), [capsule((0, 0, 0), (sx * 0.4, sy * 0.4, 0), r)],
+                           axis=aax, limit=(arange[0] * deg, arange[1] * deg), gear=150.0))
+    init_q = np.array([0, 0, 0.55, 1, 0, 0, 0, 0, 1, 0, -1, 0, -1, 0, 1], dtype=np.float64)
+    return dict(
+        name="ant", env=ENV_ANT, links=links, density=5.0, total_mass=None, friction=1.0, init_q=init_q,
+        dt=0.005, n_frames=10,
+        tunables=dict(constraint_stiffness=4000.0, constraint_vel_damping=20.0, constraint_limit_stiffness=1000.0,
+                      constraint_ang_damping=10.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=1.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.1, ctrl_cost=0.5, healthy_reward=1.0, z_min=0.2, z_max=1.0, forward_weight=1.0,
+                        angle_min=0.0, angle_max=0.0, exclude_pos=2, qd_clip=0.0, terminate=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0,
+        # actuator order of the MJCF <actuator> block: hip_4, ankle_4, hip_1, ankle_1, hip_2, ankle_2, hip_3, ankle_3
+        actuator_links=["aux_4", "ankle_4", "aux_1", "ankle_1", "aux_2", "ankle_2", "aux_3", "ankle_3"],
+    )
+
+
+def halfcheetah_model():
+    """Gym ``half_cheetah.xml`` (angles in radian, ``settotalmass=14``, friction 0.4)."""
+    r = 0.046
+    y = (0, 1, 0)
+    links = [
+        _link("torso", -1, TYPE_PLANAR, (0, 0, 0.7),
+              [capsule((-0.5, 0, 0), (0.5, 0, 0), r), capsule_axis_angle((0.6, 0, 0.1), y, 0.87, r, 0.15)], axis=y),
+        _link("bthigh", 0, TYPE_HINGE, (-0.5, 0, 0), [capsule_axis_angle((0.1, 0, -0.13), y, -3.8, r, 0.145)], axis=y,
+              limit=(-0.52, 1.05), gear=120.0),
+        _link("bshin", 1, TYPE_HINGE, (0.16, 0, -0.25), [capsule_axis_angle((-0.14, 0, -0.07), y, -2.03, r, 0.15)], axis=y,
+              limit=(-0.785, 0.785), gear=90.0),
+        _link("bfoot", 2, TYPE_HINGE, (-0.28, 0, -0.14), [capsule_axis_angle((0.03, 0, -0.097), y, -0.27, r, 0.094)], axis=y,
+              limit=(-0.4, 0.785), gear=60.0),
+        _link("fthigh", 0, TYPE_HINGE, (0.5, 0, 0), [capsule_axis_angle((-0.07, 0, -0.12), y, 0.52, r, 0.133)], axis=y,
+              limit=(-1.0, 0.7), gear=120.0),
+        _link("fshin", 4, TYPE_HINGE, (-0.14, 0, -0.24), [capsule_axis_angle((0.065, 0, -0.09), y, -0.6, r, 0.106)], axis=y,
+              limit=(-1.2, 0.87), gear=100.0),  # Brax spring/positional gear override [120,90,60,120,100,100]
+        _link("ffoot", 5, TYPE_HINGE, (0.13, 0, -0.18), [capsule_axis_angle((0.045, 0, -0.07), y, -0.6, r, 0.07)], axis=y,
+              limit=(-0.5, 0.5), gear=100.0),
+    ]
+    return dict(
+        name="halfcheetah", env=ENV_HALFCHEETAH, links=links, density=1000.0, total_mass=14.0, friction=0.4,
+        init_q=np.zeros(9), dt=0.003125, n_frames=16,
+        tunables=dict(constraint_stiffness=25000.0, constraint_vel_damping=80.0, constraint_limit_stiffness=2000.0,
+                      constraint_ang_damping=10.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.1, ctrl_cost=0.1, healthy_reward=0.0, z_min=-1e9, z_max=1e9, forward_weight=1.0,
+                        angle_min=0.0, angle_max=0.0, exclude_pos=1, qd_clip=0.0, terminate=0.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0,
+        actuator_links=["bthigh", "bshin", "bfoot", "fthigh", "fshin", "ffoot"],
+    )
+
+
+def hopper_model():
+    """Gym ``hopper.xml`` in local coordinates (density 1000; joints about (0,-1,0); gear 200)."""
+    ax = (0, -1, 0)
+    deg = np.pi / 180
+    foot = capsule((-0.13, 0, 0), (0.26, 0, 0), 0.06)
+    foot["friction"] = 2.0
+    links = [
+        _link("torso", -1, TYPE_PLANAR, (0, 0, 1.25), [capsule((0, 0, 0.2), (0, 0, -0.2), 0.05)], axis=(0, 1, 0)),
+        _link("thigh", 0, TYPE_HINGE, (0, 0, -0.2), [capsule((0, 0, 0), (0, 0, -0.45), 0.05)], axis=ax,
+              limit=(-150 * deg, 0.0), gear=200.0),
+        _link("leg", 1, TYPE_HINGE, (0, 0, -0.45), [capsule((0, 0, 0), (0, 0, -0.5), 0.04)], axis=ax,
+              limit=(-150 * deg, 0.0), gear=200.0),
+        _link("foot", 2, TYPE_HINGE, (0, 0, -0.5), [foot], axis=ax, limit=(-45 * deg, 45 * deg), gear=200.0),
+    ]
+    return dict(
+        name="hopper", env=ENV_HOPPER, links=links, density=1000.0, total_mass=None, friction=1.0,
+        init_q=np.zeros(6), dt=0.002, n_frames=4,
+        tunables=dict(constraint_stiffness=30000.0, constraint_vel_damping=100.0, constraint_limit_stiffness=2000.0,
+                      constraint_ang_damping=10.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=5e-3, ctrl_cost=1e-3, healthy_reward=1.0, z_min=0.7, z_max=1e9, forward_weight=1.0,
+                        angle_min=-0.2, angle_max=0.2, exclude_pos=1, qd_clip=10.0, terminate=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0,
+        actuator_links=["thigh", "leg", "foot"],
+    )
+
+
+def build_system(model: dict, tunables: dict | None = None) -> dict:
+    """Derive masses / inertias (MuJoCo inertiafromgeom) and pack the float32 system table."""
+    links = model["links"]
+    n = len(links)
+    assert n <= MAX_LINKS
+    density = model["density"]
+    props = [body_inertia(l["geoms"], density) for l in links]
+    if model["total_mass"]:  # <compiler settotalmass=...>: uniform rescale of masses and inertias
+        scale = model["total_mass"] / sum(p[0] for p in props)
+        props = [(m * scale, c, q, w * scale) for m, c, q, w in props]
+    tun = dict(model["tunables"])
+    if tunables:
+        unknown = set(tunables) - set(tun)
+        if unknown:
+            raise ValueError(f"unknown Brax tunables {sorted(unknown)}; known: {TUNABLE_NAMES}")
+        tun.update(tunables)
+    t = np.zeros(TABLE_FLOATS, dtype=np.float64)
+    names = [l["name"] for l in links]
+    # q / qd indexing in link order
+    q_idx, qd_idx, qi, qdi = [], [], 0, 0
+    for l in links:
+        q_idx.append(qi)
+        qd_idx.append(qdi)
+        nq, nqd = {TYPE_FREE: (7, 6), TYPE_HINGE: (1, 1), TYPE_PLANAR: (3, 3)}[l["type"]]
+        qi += nq
+        qdi += nqd
+    act_of = {name: i for i, name in enumerate(model["actuator_links"])}
+    pts_all = []
+    max_pts = 0
+    for i, (l, (m, com, irot, idiag)) in enumerate(zip(links, props)):
+        o = OFF_LINKS + LINK_STRIDE * i
+        t[o + L_PARENT] = l["parent"]
+        t[o + L_TYPE] = l["type"]
+        t[o + L_QIDX] = q_idx[i]
+        t[o + L_QDIDX] = qd_idx[i]
+        t[o + L_TPOS:o + L_TPOS + 3] = l["pos"]
+        t[o + L_TROT:o + L_TROT + 4] = l["quat"]
+        t[o + L_JPOS:o + L_JPOS + 3] = l["joint_pos"]
+        t[o + L_JROT:o + L_JROT + 4] = frame_with_x(l["axis"]) if l["axis"] is not None else (1, 0, 0, 0)
+        t[o + L_LIM_LO], t[o + L_LIM_HI] = l["limit"]
+        t[o + L_COM:o + L_COM + 3] = com
+        t[o + L_IROT:o + L_IROT + 4] = irot
+        t[o + L_IDIAG:o + L_IDIAG + 3] = idiag
+        t[o + L_MASS] = m
+        t[o + L_GEAR] = l["gear"]
+        t[o + L_ACT] = act_of.get(l["name"], -1)
+        t[o + L_CTRL_LO], t[o + L_CTRL_HI] = -1.0, 1.0
+        pts = contact_points(l["geoms"])
+        t[o + L_FIRST_PT] = len(pts_all)
+        t[o + L_N_PT] = len(pts)
+        max_pts = max(max_pts, len(pts))
+        for (p, r, fr) in pts:
+            pts_all.append((i, p, r, model["friction"] if fr is None else fr))
+    assert len(pts_all) <= MAX_POINTS
+    for k, (li, p, r, fr) in enumerate(pts_all):
+        o = OFF_POINTS + POINT_STRIDE * k
+        t[o:o + 7] = [li, p[0], p[1], p[2], r, fr, model["stock_elasticity"]]
+    ep = model["env_params"]
+    t[H_N_LINKS], t[H_N_Q], t[H_N_QD], t[H_N_POINTS] = n, qi, qdi, len(pts_all)
+    t[H_N_FRAMES], t[H_DT], t[H_ENV], t[H_N_ACT] = model["n_frames"], model["dt"], model["env"], len(model["actuator_links"])
+    for k, name in enumerate(TUNABLE_NAMES):
+        t[H_STIFFNESS + k] = tun[name]
+    t[H_RESET_NOISE], t[H_CTRL_COST], t[H_HEALTHY_REWARD] = ep["reset_noise"], ep["ctrl_cost"], ep["healthy_reward"]
+    t[H_HEALTHY_Z_MIN], t[H_HEALTHY_Z_MAX], t[H_FORWARD_WEIGHT] = ep["z_min"], ep["z_max"], ep["forward_weight"]
+    t[H_ANGLE_MIN], t[H_ANGLE_MAX], t[H_EXCLUDE_POS], t[H_QD_CLIP] = ep["angle_min"], ep["angle_max"], ep["exclude_pos"], ep["qd_clip"]
+    t[H_TERMINATE], t[H_MAX_CHILD_POINTS] = ep["terminate"], max_pts
+    t[OFF_INIT_Q:OFF_INIT_Q + qi] = model["init_q"]
+    stock_friction = float(np.max([p[3] for p in pts_all]))
+    return dict(
+        name=model["name"], table=t.astype(np.float32), link_names=names, n_links=n, n_q=qi, n_qd=qdi,
+        n_points=len(pts_all), n_act=len(model["actuator_links"]), stock_masses=[float(p[0]) for p in props],
+        stock_gravity=model["stock_gravity"], stock_friction=stock_friction,
+        stock_elasticity=model["stock_elasticity"], stock_ang_damping=model["stock_ang_damping"],
+        tunables=tun, obs_dim=(qi - int(ep["exclude_pos"])) + qdi, state_words=((13 * n + 3) // 4) * 4,
+        dt=model["dt"] * model["n_frames"],
+    )
+
+
+MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model}
+SYSTEMS = {k: build_system(f()) for k, f in MODELS.items()}

@@ -188,6 +188,8 @@ class CARLEnv(abc.ABC):
         self._alloc()
         self._context_ids = np.full(self.num_envs, -1, dtype=np.int64)  # per-env current context id
         self._ctx_obs_cache = None
+        self._ctx_obs_host_cache = None
+        self._ids_view = None
         self._seeded = False
         self._host_io = None
 
@@ -236,7 +238,10 @@ class CARLEnv(abc.ABC):
             return self.context_selector.context_id
         if self.num_envs == 1:
             return int(self._context_ids[0])
-        return self._context_ids.copy()
+        if self._ids_view is None:
+            self._ids_view = self._context_ids.copy()
+            self._ids_view.setflags(write=False)
+        return self._ids_view
 
     @context_id.setter
     def context_id(self, new_id) -> None:
@@ -260,6 +265,8 @@ class CARLEnv(abc.ABC):
         else:
             self.context = {n: vals[:, j].copy() for j, n in enumerate(self._feature_names)}
         self._ctx_obs_cache = None
+        self._ctx_obs_host_cache = None
+        self._ids_view = None
 
     # -------------------------------------------------------------------- spaces
     def get_observation_space(self, obs_context_feature_names: list[str] | None = None):
@@ -315,7 +322,11 @@ class CARLEnv(abc.ABC):
         is_brax = self.kind.startswith("brax")
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)
         self._state = z(n, info.state_words, dtype=(torch.float32 if is_brax else tdt))
-        self._ctx = z(info.n_param_rows, n, dtype=(torch.float32 if is_brax else tdt))
+        # classic: SoA rows ctx[P][n] (one thread per env); Brax: AoS ctx[n][P] (one warp per env reads
+        # its P scalars with one coalesced load and broadcasts them with shuffles)
+        ctx_shape = (n, info.n_param_rows) if is_brax else (info.n_param_rows, n)
+        self._ctx = z(*ctx_shape, dtype=(torch.float32 if is_brax else tdt))
+        self._ctx_aos = is_brax
         self._elapsed = z(n, dtype=torch.int32)
         self._sbt = z(n, dtype=torch.uint8)
         self._rng = z(4, n, dtype=torch.int64)
@@ -340,6 +351,10 @@ class CARLEnv(abc.ABC):
         _native.check(self._lib.carlb_env_configure(
             self._handle, self._max_episode_steps,
             _native.AUTORESET_SAME_STEP if self._autoreset else _native.AUTORESET_NONE))
+        self._post_alloc()
+
+    def _post_alloc(self) -> None:
+        """Family hook run once the native handle exists (Brax uploads its system table)."""
 
     def close(self) -> None:
         h = getattr(self, "_handle", None)
@@ -373,12 +388,17 @@ class CARLEnv(abc.ABC):
         ids = self._context_ids
         np_dt = np.float32 if self._ctx.dtype == torch.float32 else np.float64
         if mask is None or mask.all():
-            rows = np.ascontiguousarray(self._params_table[ids].T.astype(np_dt))
+            rows = self._params_table[ids].astype(np_dt)
+            rows = np.ascontiguousarray(rows if self._ctx_aos else rows.T)
             self._ctx.copy_(torch.from_numpy(rows), non_blocking=False)
         else:
             idx = np.nonzero(mask)[0]
-            rows = np.ascontiguousarray(self._params_table[ids[idx]].T.astype(np_dt))
-            self._ctx[:, torch.from_numpy(idx).to(self.device)] = torch.from_numpy(rows).to(self.device)
+            rows = self._params_table[ids[idx]].astype(np_dt)
+            idx_t = torch.from_numpy(idx).to(self.device)
+            if self._ctx_aos:
+                self._ctx[idx_t] = torch.from_numpy(np.ascontiguousarray(rows)).to(self.device)
+            else:
+                self._ctx[:, idx_t] = torch.from_numpy(np.ascontiguousarray(rows.T)).to(self.device)
 
     def _progress_instance(self, mask: np.ndarray | None = None) -> np.ndarray:
         """``carl_env.py:228-243`` batched: one ``select()`` per env being reset, env order."""
@@ -506,14 +526,18 @@ class CARLEnv(abc.ABC):
         return state, io["reward"].numpy(), io["term"].numpy().view(np.bool_), io["trunc"].numpy().view(np.bool_), info
 
     def _context_obs_host(self):
-        ids = self._context_ids
-        cols = [self._feature_names.index(k) for k in self.obs_context_features]
-        vals = self._table.values[ids][:, cols]
-        if self.obs_context_as_dict:
-            if self.num_envs == 1:
-                return {k: _pyval(vals[0, j]) for j, k in enumerate(self.obs_context_features)}
-            return {k: vals[:, j] for j, k in enumerate(self.obs_context_features)}
-        return vals.astype(np.float32)
+        if self._ctx_obs_host_cache is None:  # contexts only change at reset / context_id assignment
+            ids = self._context_ids
+            cols = [self._feature_names.index(k) for k in self.obs_context_features]
+            vals = self._table.values[ids][:, cols]
+            if self.obs_context_as_dict:
+                if self.num_envs == 1:
+                    self._ctx_obs_host_cache = {k: _pyval(vals[0, j]) for j, k in enumerate(self.obs_context_features)}
+                else:
+                    self._ctx_obs_host_cache = {k: np.ascontiguousarray(vals[:, j]) for j, k in enumerate(self.obs_context_features)}
+            else:
+                self._ctx_obs_host_cache = vals.astype(np.float32)
+        return self._ctx_obs_host_cache
 
     # ----------------------------------------------------------- fused rollout
     def rollout(self, n_steps: int, policy_seed: int = 0, step_base: int = 0, actions: torch.Tensor | None = None,

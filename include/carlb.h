@@ -160,9 +160,17 @@ int carlb_mixed_step(carlb_env_t* const* envs, const void* const* actions, const
  * peer_obs[r] + (global_offset + i) * obs_dim (P2P-mapped gathered buffers of all ranks). */
 int carlb_env_set_peers(carlb_env_t* env, int n_peers, float* const* peer_obs);
 
-/* Brax: override entries of the named system-tunable table; values HOST. */
-int carlb_brax_set_tunables(carlb_env_t* env, const float* values, int n_values);
-int carlb_brax_get_tunables(int kind, float* values, int max_values, int* n_values);
+/* Brax: upload the packed system table (HOST float[n_floats]) that the host layer builds from the
+ * body model -- the batched stand-in for `mjcf.load(asset)` + `sys.replace(...)`
+ * (carl/envs/brax/carl_brax_env.py:271-292). Layout: carl_b200/envs/brax_system.py /
+ * carl_b200/csrc/physics_brax.h. stock_contact != 0 keeps the per-geom stock friction/elasticity
+ * (context_mode="reference", where the reference's context never reaches the physics). */
+int carlb_brax_set_system(carlb_env_t* env, const float* table, int n_floats, int stock_contact);
+
+/* Brax parity-mode reset: `pipeline_init(q, qd)` (forward kinematics) from caller-supplied
+ * generalized coordinates q[n][n_q], qd[n][n_qd] (DEVICE) instead of the noise draws of
+ * `Ant.reset` etc. (the reference's JAX PRNG stream is not reproducible without JAX). */
+int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* q, const float* qd, void* stream);
 
 /* Counters of kernels launched through this library since load (bench `gpu_launches`). */
 int64_t carlb_launch_count(void);

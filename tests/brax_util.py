@@ -1,0 +1,67 @@
+"""Brax test helpers (test infrastructure)."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from carl_b200.envs import brax_system as bs
+
+
+def random_ctx(sysd, n, rng, applied=True):
+    """Per-env kernel context rows: gravity, friction, elasticity, ang_damping, link masses."""
+    L = sysd["n_links"]
+    ctx = np.zeros((n, 4 + L), dtype=np.float32)
+    if applied:
+        ctx[:, 0] = rng.uniform(-15, -5, n)
+        ctx[:, 1] = rng.uniform(0.5, 1.5, n)
+        ctx[:, 2] = rng.uniform(0.0, 0.3, n)
+        ctx[:, 3] = rng.uniform(-0.1, 0.0, n)
+        ctx[:, 4:] = np.asarray(sysd["stock_masses"])[None] * rng.uniform(0.5, 2.0, (n, L))
+    else:
+        ctx[:, 0] = sysd["stock_gravity"]
+        ctx[:, 1] = -1.0
+        ctx[:, 2] = -1.0
+        ctx[:, 3] = sysd["stock_ang_damping"]
+        ctx[:, 4:] = np.asarray(sysd["stock_masses"])[None]
+    return ctx
+
+
+def random_q(sysd, n, rng, scale=1.0):
+    nq, nqd = sysd["n_q"], sysd["n_qd"]
+    init_q = sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + nq].astype(np.float32)
+    q = init_q[None] + rng.uniform(-0.1 * scale, 0.1 * scale, (n, nq)).astype(np.float32)
+    qd = (0.1 * scale * rng.standard_normal((n, nqd))).astype(np.float32)
+    return q.astype(np.float32), qd
+
+
+class BraxHostCheck:
+    def __init__(self):
+        from tests.hostcheck.build_hostcheck import build
+
+        self.lib = ctypes.CDLL(build())
+
+    @staticmethod
+    def _p(a):
+        return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+    def init(self, sysd, q, qd):
+        n = q.shape[0]
+        state = np.zeros((n, sysd["state_words"]), dtype=np.float32)
+        obs = np.zeros((n, sysd["obs_dim"]), dtype=np.float32)
+        t = np.ascontiguousarray(sysd["table"], dtype=np.float32)
+        self.lib.hc_brax_init(self._p(t), n, self._p(np.ascontiguousarray(q)), self._p(np.ascontiguousarray(qd)),
+                              self._p(state), sysd["state_words"], self._p(obs), sysd["obs_dim"])
+        return state, obs
+
+    def step(self, sysd, state, ctx, actions, elapsed, max_steps, autoreset, first_state, first_obs, stock_contact=0):
+        n = state.shape[0]
+        obs = np.zeros((n, sysd["obs_dim"]), dtype=np.float32)
+        reward = np.zeros(n, dtype=np.float32)
+        done = np.zeros(n, dtype=np.uint8)
+        t = np.ascontiguousarray(sysd["table"], dtype=np.float32)
+        self.lib.hc_brax_step(self._p(t), n, self._p(state), sysd["state_words"], self._p(ctx), ctx.shape[1],
+                              self._p(np.ascontiguousarray(actions, dtype=np.float32)), self._p(elapsed), int(max_steps),
+                              int(autoreset), self._p(first_state), self._p(first_obs), self._p(obs), sysd["obs_dim"],
+                              self._p(reward), self._p(done), int(stock_contact))
+        return obs, reward, done.astype(bool)

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 
 
 def build(force: bool = False) -> str:
-    srcs = [os.path.join(HERE, "hostcheck.cpp")]
+    srcs = [os.path.join(HERE, "hostcheck.cpp"), os.path.join(HERE, "hostcheck_brax.cpp")]
     csrc = os.path.join(ROOT, "carl_b200", "csrc")
     deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):

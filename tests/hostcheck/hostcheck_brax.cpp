@@ -1,0 +1,147 @@
+// TEST-ONLY shim: the product's __host__ __device__ Brax physics (carl_b200/csrc/physics_brax.h)
+// driven by a serial loop that mirrors the phases of the warp-per-env kernel in brax.cu, compiled
+// by g++ so the no-GPU suite can compare it with the oracle. Never loaded by the product.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../carl_b200/csrc/physics_brax.h"
+
+using namespace carlb;
+using namespace carlb::brax;
+
+static LinkState rd(const float* p) {
+  LinkState s;
+  s.pos = v3(p[0], p[1], p[2]); s.rot = q4(p[3], p[4], p[5], p[6]); s.vel = v3(p[7], p[8], p[9]); s.ang = v3(p[10], p[11], p[12]);
+  return s;
+}
+static void wr(float* p, const LinkState& s) {
+  p[0] = s.pos.x; p[1] = s.pos.y; p[2] = s.pos.z; p[3] = s.rot.w; p[4] = s.rot.x; p[5] = s.rot.y; p[6] = s.rot.z;
+  p[7] = s.vel.x; p[8] = s.vel.y; p[9] = s.vel.z; p[10] = s.ang.x; p[11] = s.ang.y; p[12] = s.ang.z;
+}
+
+static void obs_of(const float* sys, const LinkState* st, float* obs, float* root /*x,z,angle,ok*/) {
+  const int L = (int)sys[H_N_LINKS], nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
+  float q[MAX_Q], qd[MAX_Q];
+  for (int l = 0; l < L; ++l) {
+    const float* lt = link_tab(sys, l);
+    const int qi = (int)lt[L_QIDX], qdi = (int)lt[L_QDIDX], type = (int)lt[L_TYPE], parent = (int)lt[L_PARENT];
+    if (type == TYPE_FREE) {
+      const V3 o = link_origin(st[l], lt), vo = origin_velocity(st[l], lt), al = inv_rotate(st[l].ang, st[l].rot);
+      q[qi] = o.x; q[qi + 1] = o.y; q[qi + 2] = o.z; q[qi + 3] = st[l].rot.w; q[qi + 4] = st[l].rot.x; q[qi + 5] = st[l].rot.y; q[qi + 6] = st[l].rot.z;
+      qd[qdi] = vo.x; qd[qdi + 1] = vo.y; qd[qdi + 2] = vo.z; qd[qdi + 3] = al.x; qd[qdi + 4] = al.y; qd[qdi + 5] = al.z;
+    } else {
+      const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], 0.0f);
+      const int nd = type == TYPE_PLANAR ? 3 : 1;
+      for (int k = 0; k < nd; ++k) { q[qi + k] = jo.q[k]; qd[qdi + k] = jo.qd[k]; }
+    }
+  }
+  const int ex = (int)sys[H_EXCLUDE_POS];
+  const float clip = sys[H_QD_CLIP];
+  int k = 0;
+  for (int i = ex; i < nq; ++i) obs[k++] = q[i];
+  for (int i = 0; i < nqd; ++i) { float v = qd[i]; if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip); obs[k++] = v; }
+  bool ok = true;
+  for (int i = 2; i < nq; ++i) ok = ok && q[i] > -100.0f && q[i] < 100.0f;
+  for (int i = 0; i < nqd; ++i) ok = ok && qd[i] > -100.0f && qd[i] < 100.0f;
+  const V3 o0 = link_origin(st[0], link_tab(sys, 0));
+  root[0] = o0.x; root[1] = o0.z; root[2] = ((int)link_tab(sys, 0)[L_TYPE] == TYPE_PLANAR) ? q[2] : 0.0f; root[3] = ok ? 1.0f : 0.0f;
+}
+
+extern "C" {
+
+void hc_brax_init(const float* sys, int n, const float* q_all, const float* qd_all, float* state, int words, float* obs, int D) {
+  const int L = (int)sys[H_N_LINKS], nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
+  for (int e = 0; e < n; ++e) {
+    LinkState st[MAX_LINKS];
+    for (int l = 0; l < L; ++l) {
+      const float* lt = link_tab(sys, l);
+      const int parent = (int)lt[L_PARENT];
+      st[l] = forward_link(sys, lt, q_all + (size_t)e * nq, qd_all + (size_t)e * nqd, parent < 0,
+                           link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent]);
+    }
+    float* rows = state + (size_t)e * words;
+    memset(rows, 0, sizeof(float) * words);
+    for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);
+    float root[4];
+    obs_of(sys, st, obs + (size_t)e * D, root);
+  }
+}
+
+void hc_brax_step(const float* sys, int n, float* state, int words, const float* ctx, int n_ctx, const float* actions,
+                  int* elapsed, int max_steps, int autoreset, const float* first_state, const float* first_obs, float* obs,
+                  int D, float* reward, uint8_t* done_out, int stock_contact) {
+  const int L = (int)sys[H_N_LINKS], P = (int)sys[H_N_POINTS], A = (int)sys[H_N_ACT], NF = (int)sys[H_N_FRAMES];
+  for (int e = 0; e < n; ++e) {
+    float* rows = state + (size_t)e * words;
+    const float* c = ctx + (size_t)e * n_ctx;
+    const float* act = actions + (size_t)e * A;
+    LinkState st[MAX_LINKS];
+    for (int l = 0; l < L; ++l) st[l] = rd(rows + l * LINK_WORDS);
+    float before[4], after[4], ob[64];
+    obs_of(sys, st, ob, before);
+    float act_sq = 0.0f;
+    for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
+    for (int f = 0; f < NF; ++f) {
+      Wrench w[MAX_LINKS], pw[MAX_LINKS];
+      for (int l = 0; l < L; ++l) {
+        w[l].f = v3(0, 0, 0); w[l].t = v3(0, 0, 0); pw[l] = w[l];
+        const float* lt = link_tab(sys, l);
+        if ((int)lt[L_TYPE] == TYPE_FREE) continue;
+        const int parent = (int)lt[L_PARENT], ai = (int)lt[L_ACT];
+        float tau = 0.0f;
+        if (ai >= 0) tau = lt[L_GEAR] * fminf(fmaxf(act[ai], lt[L_CTRL_LO]), lt[L_CTRL_HI]);
+        const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], tau);
+        w[l] = jo.child; pw[l] = jo.parent;
+      }
+      LinkState nx[MAX_LINKS];
+      for (int l = 0; l < L; ++l) {
+        Wrench tot = w[l];
+        for (int k = l + 1; k < L; ++k)
+          if ((int)link_tab(sys, k)[L_PARENT] == l) { tot.f = tot.f + pw[k].f; tot.t = tot.t + pw[k].t; }
+        nx[l] = st[l];
+        integrate_xdd(nx[l], tot, sys, link_tab(sys, l), c[C_MASS0 + l], c[C_GRAVITY], c[C_ANG_DAMPING]);
+      }
+      ContactOut co[MAX_POINTS];
+      for (int p = 0; p < P; ++p) {
+        const float* pt = point_tab(sys, p);
+        const int l = (int)pt[0];
+        const float fr = (c[C_FRICTION] < 0.0f || stock_contact) ? pt[5] : c[C_FRICTION];
+        const float el = (c[C_ELASTICITY] < 0.0f || stock_contact) ? pt[6] : c[C_ELASTICITY];
+        co[p] = contact_resolve(sys, pt, link_tab(sys, l), nx[l], c[C_MASS0 + l], fr, el);
+      }
+      for (int l = 0; l < L; ++l) {
+        const float* lt = link_tab(sys, l);
+        V3 ps = v3(0, 0, 0), ts = v3(0, 0, 0);
+        float na = 0.0f;
+        for (int k = (int)lt[L_FIRST_PT]; k < (int)lt[L_FIRST_PT] + (int)lt[L_N_PT]; ++k) { ps = ps + co[k].p; ts = ts + co[k].t; na += co[k].active; }
+        integrate_xdv(nx[l], ps, ts, na, sys, lt, c[C_MASS0 + l]);
+        integrate_pose(nx[l], sys[H_DT]);
+        st[l] = nx[l];
+      }
+    }
+    obs_of(sys, st, ob, after);
+    const float dt_env = sys[H_DT] * sys[H_N_FRAMES];
+    const float xvel = (after[0] - before[0]) / dt_env;
+    const int kind = (int)sys[H_ENV];
+    bool healthy = true;
+    if (kind == ENV_ANT) healthy = !(after[1] < sys[H_HEALTHY_Z_MIN]) && !(after[1] > sys[H_HEALTHY_Z_MAX]);
+    else if (kind == ENV_HOPPER)
+      healthy = after[3] > 0.5f && sys[H_HEALTHY_Z_MIN] < after[1] && after[1] < sys[H_HEALTHY_Z_MAX] &&
+                sys[H_ANGLE_MIN] < after[2] && after[2] < sys[H_ANGLE_MAX];
+    const float r = sys[H_FORWARD_WEIGHT] * xvel + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
+    bool done = sys[H_TERMINATE] > 0.0f && !healthy;
+    elapsed[e] += 1;
+    if (max_steps > 0 && elapsed[e] >= max_steps) done = true;
+    for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);
+    memcpy(obs + (size_t)e * D, ob, sizeof(float) * D);
+    if (done && autoreset) {
+      memcpy(rows, first_state + (size_t)e * words, sizeof(float) * words);
+      memcpy(obs + (size_t)e * D, first_obs + (size_t)e * D, sizeof(float) * D);
+      elapsed[e] = 0;
+    }
+    reward[e] = r;
+    done_out[e] = done ? 1 : 0;
+  }
+}
+
+}  // extern "C"

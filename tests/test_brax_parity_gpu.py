@@ -1,0 +1,191 @@
+"""Brax-locomotion parity tests proper: the warp-per-env CUDA kernels, through the C ABI, against
+the CPU oracle (float32 both; 1e-5 relative per env-step, done masks identical).
+PARITY UNPINNED against real Brax (not installable here) -- see tests/test_brax_golden.py."""
+import numpy as np
+import pytest
+import torch
+
+from carl_b200.envs import brax_system as bs
+from oracle.brax import OracleBraxEnv
+from tests.brax_util import random_q
+
+pytestmark = pytest.mark.gpu
+BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper"}
+
+
+def make_env(body, n, rng, mode="applied", **kw):
+    import carl_b200.envs as E
+    from carl_b200.envs import ContextTable
+
+    cls = getattr(E, BODIES[body])
+    names = list(cls.get_default_context().keys())
+    d = cls.get_default_context()
+    table = np.tile(np.array([float(d[k]) for k in names]), (n, 1))
+    table[:, names.index("gravity")] = rng.uniform(-15, -5, n)
+    table[:, names.index("friction")] = rng.uniform(0.5, 1.5, n)
+    table[:, names.index("elasticity")] = rng.uniform(0.0, 0.3, n)
+    table[:, names.index("viscosity")] = rng.uniform(-0.1, 0.0, n)  # overwrites ang_damping (reference quirk B2)
+    for k in names:
+        if k.startswith("mass_"):
+            table[:, names.index(k)] *= rng.uniform(0.5, 2.0, n)
+    return cls(contexts=ContextTable(names, table), device="cuda:0", context_mode=mode, **kw)
+
+
+def oracle_for(env, **kw):
+    return OracleBraxEnv(env._sysd, env._ctx.cpu().numpy(), **kw)
+
+
+@pytest.mark.parametrize("body", list(BODIES))
+def test_pipeline_init_matches(body):
+    rng = np.random.default_rng(0)
+    n = 300
+    env = make_env(body, n, rng)
+    q, qd = random_q(env._sysd, n, rng, scale=3.0)
+    obs, info = env.reset_from_q(q, qd)
+    ora = oracle_for(env)
+    o_ref = ora.init_from_q(q, qd)
+    np.testing.assert_allclose(env.state.cpu().numpy(), ora.state, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(obs["obs"].cpu().numpy(), o_ref, rtol=1e-5, atol=2e-6)
+    np.testing.assert_array_equal(env._first_state.cpu().numpy(), env.state.cpu().numpy())
+
+
+@pytest.mark.parametrize("body", list(BODIES))
+@pytest.mark.parametrize("mode", ["applied", "reference"])
+def test_single_env_step_matches(body, mode):
+    rng = np.random.default_rng(1)
+    n = 1024
+    env = make_env(body, n, rng, mode=mode, autoreset=False)
+    q, qd = random_q(env._sysd, n, rng, scale=2.0)
+    env.reset_from_q(q, qd)
+    ctx = env._ctx.cpu().numpy().copy()
+    if mode == "reference":  # stock per-geom friction / elasticity
+        ctx[:, 1] = -1.0
+        ctx[:, 2] = -1.0
+    ora = OracleBraxEnv(env._sysd, ctx, autoreset=False)
+    ora.init_from_q(q, qd)
+    a = rng.uniform(-1.2, 1.2, (n, env._sysd["n_act"])).astype(np.float32)
+    o_ref, r_ref, d_ref, _ = ora.step(a)
+    obs, r, te, tr, _ = env.step(torch.from_numpy(a).cuda())
+    np.testing.assert_allclose(obs["obs"].cpu().numpy(), o_ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(r.cpu().numpy(), r_ref, rtol=1e-4, atol=1e-4)
+    assert (te.cpu().numpy() == d_ref).all() and not tr.any()
+    np.testing.assert_allclose(env.state.cpu().numpy(), ora.state, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("body", list(BODIES))
+def test_rollout_with_autoreset_matches(body):
+    rng = np.random.default_rng(2)
+    n, T, max_steps = 64, 60, 25
+    env = make_env(body, n, rng, max_episode_steps=max_steps)
+    q, qd = random_q(env._sysd, n, rng)
+    env.reset_from_q(q, qd)
+    ora = oracle_for(env, max_steps=max_steps, autoreset=True)
+    ora.init_from_q(q, qd)
+    n_done = 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, env._sysd["n_act"])).astype(np.float32)
+        o_ref, r_ref, d_ref, fin_ref = ora.step(a)
+        obs, r, te, tr, info = env.step(torch.from_numpy(a).cuda())
+        d = te.cpu().numpy()
+        assert (d == d_ref).all(), f"done mismatch at step {t}"
+        k = (t % max_steps) + 1
+        np.testing.assert_allclose(obs["obs"].cpu().numpy(), o_ref, rtol=2e-5 * k, atol=2e-5 * k)
+        if d.any():
+            np.testing.assert_allclose(info["final_observation"].cpu().numpy()[d], fin_ref[d], rtol=1e-3, atol=1e-3)
+        n_done += int(d.sum())
+    assert n_done >= n
+
+
+@pytest.mark.parametrize("body", list(BODIES))
+def test_fused_rollout_equals_stepwise(body):
+    rng = np.random.default_rng(3)
+    n, K = 130, 40
+    a_env = make_env(body, n, np.random.default_rng(3), max_episode_steps=15)
+    b_env = make_env(body, n, np.random.default_rng(3), max_episode_steps=15)
+    q, qd = random_q(a_env._sysd, n, rng)
+    a_env.reset_from_q(q, qd)
+    b_env.reset_from_q(q, qd)
+    traj = a_env.rollout(K, policy_seed=11, record=True)
+    for t in range(K):
+        obs, r, te, tr, _ = b_env.step(traj["actions"][t])
+        assert torch.equal(obs["obs"], traj["obs"][t]), f"obs differ at step {t}"
+        assert torch.equal(r, traj["reward"][t]) and torch.equal(te.to(torch.uint8), traj["done"][t])
+    assert torch.equal(a_env.state, b_env.state)
+    assert int(traj["done"].sum()) > 0
+    assert traj["actions"].abs().max() <= 1.0
+
+
+def test_noise_reset_statistics_and_autoreset_to_first_state():
+    """Ant.reset: q = init_q + U(+-0.1), qd = 0.1 N(0,1); AutoReset restores the stored first state."""
+    from carl_b200.envs import CARLBraxAnt
+
+    env = CARLBraxAnt(num_envs=4096, max_episode_steps=3)
+    obs, info = env.reset(seed=0)
+    o = obs["obs"].cpu().numpy()
+    init_q = env._sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + 15]
+    dz = o[:, 0] - init_q[2]
+    assert np.abs(dz).max() <= 0.1 + 1e-6 and abs(dz.mean()) < 0.01 and 0.05 < dz.std() < 0.065
+    joints = o[:, 5:13] - init_q[7:15]
+    assert np.abs(joints).max() <= 0.1 + 1e-5
+    qd = o[:, 13:16]
+    assert abs(qd.mean()) < 0.01 and 0.09 < qd.std() < 0.11
+    first = obs["obs"].clone()
+    for t in range(3):
+        obs, r, te, tr, _ = env.step(torch.zeros(4096, 8, device="cuda"))
+    assert te.all()  # EpisodeWrapper(3): truncation surfaces as terminated (wrappers.py:75-78)
+    assert torch.equal(obs["obs"], first) and torch.equal(env.state, env._first_state)
+    obs2, _ = env.reset()  # a new reset draws new noise (the episode counter advanced)
+    assert not torch.equal(obs2["obs"], first)
+
+
+def test_reference_mode_context_does_not_reach_physics():
+    """in the reference the modified sys never reaches the jitted step."""
+    from carl_b200.envs import CARLBraxAnt
+
+    outs = {}
+    for mode in ("reference", "applied"):
+        res = []
+        for g in (-9.8, -3.0):
+            env = CARLBraxAnt(contexts={0: {"gravity": g}}, context_mode=mode, num_envs=1)
+            q = env._sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + 15][None].copy()
+            q[0, 2] = 1.0  # in the air: free fall shows gravity
+            env.reset_from_q(q, np.zeros((1, 14), np.float32))
+            obs, *_ = env.step(torch.zeros(1, 8, device="cuda"))
+            res.append(obs["obs"].cpu().numpy()[0, 0])
+            assert obs["context"]["gravity"].item() == pytest.approx(g)  # the context is still observed
+        outs[mode] = res
+    assert outs["reference"][0] == outs["reference"][1]
+    assert outs["applied"][0] < outs["applied"][1]  # weaker gravity -> higher after one step
+
+
+def test_brax_api_shapes_and_batch_size():
+    """test/test_brax_env.py + wrappers.py VectorGymWrapper shape contract."""
+    import carl_b200.envs as E
+
+    for name, D, A in (("CARLBraxAnt", 27, 8), ("CARLBraxHalfcheetah", 17, 6), ("CARLBraxHopper", 11, 3)):
+        cls = getattr(E, name)
+        env = cls(batch_size=5)
+        env._progress_instance()
+        env._update_context()
+        obs, info = env.reset()
+        assert obs["obs"].shape == (5, D) and env.action_space.shape == (5, A)
+        assert "target_distance" not in env.contexts[0]
+        a = np.stack([env.single_action_space.sample() for _ in range(5)])
+        obs, r, te, tr, info = env.step(a)  # numpy in -> numpy out
+        assert obs["obs"].shape == (5, D) and r.shape == (5,) and te.dtype == np.bool_ and not tr.any()
+    with pytest.raises(RuntimeError):
+        E.CARLBraxAnt(contexts={0: {"gravity": -9.8}}, context_mode="applied").kernel_params(
+            np.zeros((1, 1)), ["bogus"], "applied")
+
+
+def test_full_size_properties_config4():
+    """BASELINE config 4 size (CARLAnt, 8 192 contexts): determinism + finiteness + sane returns."""
+    rng = np.random.default_rng(4)
+    e1, e2 = make_env("ant", 8192, np.random.default_rng(4)), make_env("ant", 8192, np.random.default_rng(4))
+    e1.reset(seed=1); e2.reset(seed=1)
+    t1 = e1.rollout(50, policy_seed=2, record=True)
+    t2 = e2.rollout(50, policy_seed=2, record=True)
+    assert torch.equal(t1["obs"], t2["obs"]) and torch.equal(t1["reward"], t2["reward"])
+    assert torch.isfinite(t1["obs"]).all() and torch.isfinite(t1["reward"]).all()
+    z = t1["obs"][..., 0]
+    assert 0.15 < z.min().item() and z.max().item() < 1.5

@@ -1,0 +1,106 @@
+"""No-GPU check of the Brax kernel source logic (physics_brax.h through tests/hostcheck) against
+the CPU oracle (oracle/brax_oracle.c): forward kinematics, n_frames spring substeps, env layer,
+EpisodeWrapper truncation and AutoReset. float32 on both sides; 1e-5 relative per step (north
+star), done masks identical."""
+import numpy as np
+import pytest
+
+from carl_b200.envs import brax_system as bs
+from oracle.brax import OracleBraxEnv
+from tests.brax_util import BraxHostCheck, random_ctx, random_q
+
+BODIES = ["ant", "halfcheetah", "hopper"]
+
+
+@pytest.fixture(scope="module")
+def hc():
+    return BraxHostCheck()
+
+
+@pytest.mark.parametrize("body", BODIES)
+def test_pipeline_init_matches(hc, body):
+    sysd = bs.SYSTEMS[body]
+    rng = np.random.default_rng(0)
+    q, qd = random_q(sysd, 64, rng, scale=3.0)
+    ora = OracleBraxEnv(sysd, random_ctx(sysd, 64, rng))
+    o_ref = ora.init_from_q(q, qd)
+    st, o = hc.init(sysd, q, qd)
+    np.testing.assert_allclose(st, ora.state, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o, o_ref, rtol=1e-5, atol=2e-6)
+    # forward then inverse kinematics is the identity on (q[ex:], qd)
+    ex = int(sysd["table"][bs.H_EXCLUDE_POS])
+    want = np.concatenate([q[:, ex:], qd], axis=1)
+    if body == "ant":  # the free root's quaternion is normalised by forward()
+        want[:, 1:5] /= np.linalg.norm(want[:, 1:5], axis=1, keepdims=True)
+        want[:, 13 + 3:13 + 6] = o_ref[:, 13 + 3:13 + 6]  # angular velocity is reported in the local frame
+    clip = sysd["table"][bs.H_QD_CLIP]
+    if clip > 0:
+        want[:, -sysd["n_qd"]:] = np.clip(want[:, -sysd["n_qd"]:], -clip, clip)
+    np.testing.assert_allclose(o_ref, want, rtol=2e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("body", BODIES)
+@pytest.mark.parametrize("applied", [True, False])
+def test_single_env_step_matches(hc, body, applied):
+    """P1/P4: one env-step (n_frames substeps) from random states, contexts and actions."""
+    sysd = bs.SYSTEMS[body]
+    n = 256
+    rng = np.random.default_rng(1)
+    ctx = random_ctx(sysd, n, rng, applied=applied)
+    q, qd = random_q(sysd, n, rng, scale=2.0)
+    ora = OracleBraxEnv(sysd, ctx, autoreset=False)
+    ora.init_from_q(q, qd)
+    st, _ = hc.init(sysd, q, qd)
+    a = rng.uniform(-1.2, 1.2, (n, sysd["n_act"])).astype(np.float32)
+    o_ref, r_ref, d_ref, _ = ora.step(a)
+    el = np.zeros(n, dtype=np.int32)
+    o, r, d = hc.step(sysd, st, ctx, a, el, 1000, 0, st.copy(), o_ref.copy(), stock_contact=0 if applied else 1)
+    np.testing.assert_allclose(o, o_ref, rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(r, r_ref, rtol=1e-4, atol=1e-4)
+    assert (d == d_ref).all()
+    np.testing.assert_allclose(st, ora.state, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("body", BODIES)
+def test_rollout_with_autoreset_matches(hc, body):
+    """P2: 60 env-steps with shared random actions, short episodes (truncation -> done ->
+    AutoReset to the stored first state); done masks identical, drift bounded."""
+    sysd = bs.SYSTEMS[body]
+    n, T, max_steps = 32, 60, 25
+    rng = np.random.default_rng(2)
+    ctx = random_ctx(sysd, n, rng)
+    q, qd = random_q(sysd, n, rng)
+    ora = OracleBraxEnv(sysd, ctx, max_steps=max_steps, autoreset=True)
+    o0 = ora.init_from_q(q, qd)
+    st, o = hc.init(sysd, q, qd)
+    first_state, first_obs = st.copy(), o.copy()
+    el = np.zeros(n, dtype=np.int32)
+    n_done = 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (n, sysd["n_act"])).astype(np.float32)
+        o_ref, r_ref, d_ref, _ = ora.step(a)
+        o, r, d = hc.step(sysd, st, ctx, a, el, max_steps, 1, first_state, first_obs)
+        assert (d == d_ref).all(), f"done mismatch at step {t}"
+        k = (t % max_steps) + 1
+        np.testing.assert_allclose(o, o_ref, rtol=2e-5 * k, atol=2e-5 * k)
+        n_done += int(d.sum())
+        assert (el == ora.elapsed).all()
+    assert n_done >= n  # every env was truncated at least twice
+
+
+@pytest.mark.parametrize("body", BODIES)
+def test_physical_sanity(body):
+    """The restated pipeline is physically sane: from the initial pose under zero action the body
+    settles (no blow-up), contacts hold it above the ground, energy does not grow."""
+    sysd = bs.SYSTEMS[body]
+    ctx = random_ctx(sysd, 1, np.random.default_rng(0), applied=False)
+    env = OracleBraxEnv(sysd, ctx, autoreset=False)
+    q = sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + sysd["n_q"]][None].astype(np.float32)
+    env.init_from_q(q, np.zeros((1, sysd["n_qd"]), np.float32))
+    for t in range(100):
+        obs, r, d, _ = env.step(np.zeros((1, sysd["n_act"]), np.float32))
+    assert np.isfinite(obs).all() and np.abs(obs[0, -sysd["n_qd"]:]).max() < 0.5  # came to rest
+    rows = env.state[0, :13 * sysd["n_links"]].reshape(-1, 13)
+    assert rows[:, 2].min() > 0.0  # every link COM above the plane
+    if body == "ant":
+        assert 0.4 < obs[0, 0] < 0.6  # torso height ~0.55 (the reference notebook shows z = 0.559)

@@ -1,0 +1,103 @@
+"""Brax body models: the geometry restated from the standard MJCF models is pinned by the
+reference's own per-link mass defaults (carl_halfcheetah.py:40-57, carl_hopper.py:40-48), and the
+packed-table layout is identical in Python, the CUDA header and the oracle."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from carl_b200.envs import brax_system as bs
+from carl_b200.envs.brax import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_halfcheetah_masses_match_carl_defaults():
+    s = bs.SYSTEMS["halfcheetah"]
+    d = CARLBraxHalfcheetah.get_context_space().get_default_context()
+    for name, m in zip(s["link_names"][1:], s["stock_masses"][1:]):
+        assert m == pytest.approx(d[f"mass_{name}"], rel=2e-7), name
+    assert sum(s["stock_masses"]) == pytest.approx(14.0, rel=1e-12)  # settotalmass
+    assert s["stock_masses"][0] == pytest.approx(6.2502092, rel=2e-7)
+
+
+def test_hopper_masses_match_carl_defaults():
+    s = bs.SYSTEMS["hopper"]
+    d = CARLBraxHopper.get_context_space().get_default_context()
+    for name, m in zip(s["link_names"][1:], s["stock_masses"][1:]):
+        assert m == pytest.approx(d[f"mass_{name}"], rel=2e-7), name
+    assert s["stock_masses"][0] == pytest.approx(3.6651914, rel=2e-7)  # CARL overrides it with 10
+
+
+def test_shapes_match_reference_observation_sizes():
+    a, h, p = bs.SYSTEMS["ant"], bs.SYSTEMS["halfcheetah"], bs.SYSTEMS["hopper"]
+    assert (a["n_links"], a["n_q"], a["n_qd"], a["obs_dim"], a["n_act"]) == (9, 15, 14, 27, 8)  # obs f32[27]: notebook
+    assert (h["n_links"], h["n_q"], h["n_qd"], h["obs_dim"], h["n_act"]) == (7, 9, 9, 17, 6)
+    assert (p["n_links"], p["n_q"], p["n_qd"], p["obs_dim"], p["n_act"]) == (4, 6, 6, 11, 3)
+    assert a["dt"] == pytest.approx(0.05) and h["dt"] == pytest.approx(0.05) and p["dt"] == pytest.approx(0.008)
+
+
+def test_every_mass_feature_names_a_link():
+    for cls, key in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper")):
+        links = bs.SYSTEMS[key]["link_names"]
+        for f in cls.get_context_features():
+            if f.startswith("mass_"):
+                assert f[len("mass_"):] in links
+
+
+def test_inertia_from_geom_known_values():
+    m, com, rot, diag = bs.body_inertia([bs.sphere((0, 0, 0), 0.25)], 5.0)
+    assert m == pytest.approx(5 * 4 / 3 * np.pi * 0.25**3) and np.allclose(diag, 0.4 * m * 0.25**2)
+    m, com, rot, diag = bs.body_inertia([bs.capsule((0, 0, 0), (0, 0, -0.45), 0.05)], 1000.0)
+    assert m == pytest.approx(4.0578905, rel=2e-7) and np.allclose(com, (0, 0, -0.225))
+    assert diag[2] < diag[0] and diag[0] == pytest.approx(diag[1])
+
+
+def _enum_values(text, enum_name):
+    body = re.search(r"enum\s+" + enum_name + r"\s*\{(.*?)\};", text, flags=re.S).group(1)
+    vals, cur = {}, -1
+    for item in body.split(","):
+        item = item.strip()
+        if not item:
+            continue
+        if "=" in item:
+            k, v = [x.strip() for x in item.split("=")]
+            cur = int(v)
+        else:
+            k, cur = item, cur + 1
+        vals[k] = cur
+    return vals
+
+
+def test_table_layout_identical_in_python_and_cuda_header():
+    text = open(os.path.join(ROOT, "carl_b200", "csrc", "physics_brax.h")).read()
+    for name in ("MAX_LINKS", "MAX_POINTS", "MAX_Q", "HEADER", "LINK_STRIDE", "POINT_STRIDE"):
+        assert int(re.search(rf"constexpr int {name} = (\d+);", text).group(1)) == getattr(bs, name)
+    hdr = _enum_values(text, "Hdr")
+    for k, v in hdr.items():
+        assert getattr(bs, k) == v, k
+    ls = _enum_values(text, "LinkSlot")
+    for k, v in ls.items():
+        assert getattr(bs, k) == v, k
+    assert bs.TABLE_FLOATS * 4 % 16 == 0  # TMA bulk copies move multiples of 16 bytes
+
+
+def test_tables_are_trees_with_parents_first():
+    for s in bs.SYSTEMS.values():
+        t = s["table"]
+        for l in range(s["n_links"]):
+            parent = int(t[bs.OFF_LINKS + bs.LINK_STRIDE * l + bs.L_PARENT])
+            assert parent < l
+        pts = int(t[bs.H_N_POINTS])
+        assert pts <= bs.MAX_POINTS
+        firsts = [int(t[bs.OFF_LINKS + bs.LINK_STRIDE * l + bs.L_FIRST_PT]) for l in range(s["n_links"])]
+        counts = [int(t[bs.OFF_LINKS + bs.LINK_STRIDE * l + bs.L_N_PT]) for l in range(s["n_links"])]
+        assert firsts == list(np.cumsum([0] + counts[:-1])) and sum(counts) == pts
+
+
+def test_tunable_override_and_validation():
+    s = bs.build_system(bs.ant_model(), {"constraint_stiffness": 1234.0})
+    assert s["table"][bs.H_STIFFNESS] == 1234.0
+    with pytest.raises(ValueError):
+        bs.build_system(bs.ant_model(), {"nope": 1.0})

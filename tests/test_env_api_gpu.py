@@ -1,0 +1,138 @@
+"""API-shape tests ported from the reference's test/test_CARLEnv.py, test_context_selector.py,
+test_gymnasium_envs.py and the notebook behaviour (round-robin ids, context_id setter), run
+against the batched CUDA-backed classes."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _pendulum_contexts():
+    context = {"dt": 0.03, "gravity": 10.0, "m": 1.0, "l": 1.8}
+    return {k: dict(context) for k in "abc"}
+
+
+def test_observation_dict_and_context_lengths():
+    from carl_b200.envs import CARLPendulum
+
+    env = CARLPendulum()
+    context = CARLPendulum.get_default_context()
+    obs, info = env.reset()
+    assert type(obs) is dict and "obs" in obs and "context" in obs
+    assert len(obs["context"]) == len(context)
+    assert obs["obs"].shape == (1, 3)
+    env = CARLPendulum(obs_context_features=[])
+    state, info = env.reset()
+    assert len(state["context"]) == 0
+    keys = list(context.keys())[:3]
+    env = CARLPendulum(obs_context_features=keys)
+    state, info = env.reset()
+    assert len(state["context"]) == 3
+    env = CARLPendulum(obs_context_as_dict=False)
+    state, _ = env.reset()
+    assert state["context"].shape == (1, len(context))
+
+
+def test_selector_wiring():
+    from carl_b200.context import RandomSelector, RoundRobinSelector
+    from carl_b200.envs import CARLPendulum
+
+    contexts = _pendulum_contexts()
+    env = CARLPendulum(contexts=contexts, num_envs=1)
+    env.reset()
+    assert type(env.context_selector) is RoundRobinSelector and env.context_selector.n_calls == 1
+    env.reset()
+    assert env.context_selector.n_calls == 2
+    assert type(CARLPendulum(contexts=contexts, context_selector=RoundRobinSelector(contexts=contexts)).context_selector) is RoundRobinSelector
+    assert type(CARLPendulum(contexts=contexts, context_selector=RandomSelector(contexts=contexts)).context_selector) is RandomSelector
+    assert type(CARLPendulum(contexts=contexts, context_selector=RandomSelector).context_selector) is RandomSelector
+    with pytest.raises(ValueError):
+        CARLPendulum(contexts=contexts, context_selector="bork")
+
+
+def test_round_robin_ids_and_context_id_setter():
+    """sample_contexts_with_brax.ipynb cells 7-11: first reset -> id 0, second -> 1, setter -> 4."""
+    from carl_b200.envs import CARLCartPole
+
+    contexts = {i: {"gravity": 9.8 + i} for i in range(5)}
+    env = CARLCartPole(contexts=contexts, num_envs=1)
+    _, info = env.reset()
+    assert env.context_id == 0 and info["context_id"] == 0 and env.context["gravity"] == 9.8
+    env.reset()
+    assert env.context_id == 1 and env.context["gravity"] == 10.8
+    env.context_id = 4
+    assert env.context_id == 4 and env.context["gravity"] == 13.8
+    assert env._ctx[0, 0].item() == pytest.approx(13.8)  # re-injected at once
+    with pytest.raises(AssertionError):
+        env.context_id = 17
+    # contexts setter fills defaults (carl_env.py:135-137)
+    assert env.contexts[3]["masscart"] == 1.0 and len(env.contexts[3]) == 8
+
+
+def test_batch_binds_env_i_to_context_i_and_defaults():
+    from carl_b200.envs import CARLCartPole
+
+    contexts = {i: {"gravity": 5.0 + i} for i in range(6)}
+    env = CARLCartPole(contexts=contexts)
+    assert env.num_envs == 6
+    obs, info = env.reset(seed=0)
+    np.testing.assert_array_equal(info["context_id"], np.arange(6))
+    np.testing.assert_allclose(obs["context"]["gravity"].cpu().numpy(), 5.0 + np.arange(6))
+    np.testing.assert_allclose(env._ctx[0].cpu().numpy(), 5.0 + np.arange(6))
+    # more envs than contexts: round robin wraps
+    env = CARLCartPole(contexts=contexts, num_envs=8)
+    _, info = env.reset(seed=0)
+    np.testing.assert_array_equal(info["context_id"], np.arange(8) % 6)
+
+
+@pytest.mark.parametrize("name", ["CARLCartPole", "CARLPendulum", "CARLAcrobot", "CARLMountainCar", "CARLMountainCarContinuous"])
+def test_all_classic_envs_construct_reset_step(name):
+    """test/test_gymnasium_envs.py + test_all_envs.py: features, construct, progress, update, reset."""
+    import carl_b200.envs as E
+
+    cls = getattr(E, name)
+    cls.get_context_features()
+    env = cls()
+    env._progress_instance()
+    env._update_context()
+    obs, info = env.reset()
+    assert obs["obs"].shape == (1, env._info.obs_dim)
+    a = env.single_action_space.sample()
+    out = env.step(np.asarray([a]))
+    assert len(out) == 5 and out[0]["obs"].shape == (1, env._info.obs_dim)
+    assert "context_id" in out[4]
+    assert env.observation_space["obs"].shape == (env._info.obs_dim,)
+    env.close()
+
+
+def test_invalid_arguments_raise():
+    from carl_b200.envs import CARLCartPole
+
+    with pytest.raises(ValueError):
+        CARLCartPole(contexts={0: {"not_a_feature": 1.0}})
+    with pytest.raises(ValueError):
+        CARLCartPole(dtype="float16")
+    env = CARLCartPole(num_envs=4)
+    env.reset(seed=0)
+    with pytest.raises(AssertionError):
+        env.step(torch.zeros(5, dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        env._lib  # noqa: B018
+        from carl_b200 import _native
+        _native.check(env._lib.carlb_env_step(env._handle, torch.zeros(4, device="cuda").data_ptr(), _native.ACT_F32, None))
+
+
+def test_checkpoint_roundtrip():
+    from carl_b200.envs import CARLAcrobot
+
+    env = CARLAcrobot(num_envs=64, autoreset=True)
+    env.reset(seed=2)
+    env.rollout(50, policy_seed=1)
+    sd = env.state_dict()
+    t1 = env.rollout(30, policy_seed=2, record=True)
+    env2 = CARLAcrobot(num_envs=64, autoreset=True)
+    env2.reset(seed=99)
+    env2.load_state_dict(sd)
+    t2 = env2.rollout(30, policy_seed=2, record=True)
+    assert torch.equal(t1["obs"], t2["obs"]) and torch.equal(t1["done"], t2["done"])
