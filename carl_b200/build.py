@@ -20,10 +20,14 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE]
 # classic control mirrors float64/NumPy arithmetic, which never fuses a*b+c: no FMA contraction
 # there (-fmad=false); the Brax pipeline keeps FMA contraction (the reference's XLA kernels do too).
+# Brax: parity first -- without FMA contraction the float32 kernel reproduces the float32 restatement
+# of the reference arithmetic to ~1e-6 per env-step (with contraction the stiff joint springs amplify
+# the different rounding to a few 1e-5; tests/test_brax_parity_gpu.py measures both against a float64
+# yardstick). CARLB_BRAX_FMAD=1 builds the contracted variant for performance experiments.
 UNITS = [
     ("abi.cu", []),
     ("classic.cu", ["-fmad=false"]),
-    ("brax.cu", []),
+    ("brax.cu", [] if os.environ.get("CARLB_BRAX_FMAD") == "1" else ["-fmad=false"]),
 ]
 
 

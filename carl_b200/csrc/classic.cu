@@ -177,16 +177,25 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   uint8_t sb = 0;
   if (KIND == KIND_CARTPOLE) sb = seg.sbt[i];
   const uint64_t gid = (uint64_t)(seg.global_offset + i);
+  PolicyStream ps = policy_stream(policy_seed, gid);
   float o[Tr::D];
   StepOut so;
   so.reward = 0.0f;
   so.terminated = false;
   bool tr = false;
+  // running row pointers: row (t, i) of a [K][n] buffer advances by n elements per step
+  float* t_obs = traj.obs != nullptr ? traj.obs + (size_t)i * Tr::D : nullptr;
+  int32_t* t_act_i = static_cast<int32_t*>(traj.actions);
+  float* t_act_f = static_cast<float*>(traj.actions);
+  if (traj.actions != nullptr) { t_act_i += i; t_act_f += i; }
+  float* t_rew = traj.reward != nullptr ? traj.reward + i : nullptr;
+  uint8_t* t_done = traj.done != nullptr ? traj.done + i : nullptr;
+  const size_t esz = seg.act_dtype == CARLB_ACT_I64 ? 8 : (seg.act_dtype == CARLB_ACT_U8 ? 1 : 4);
+  const unsigned char* a_in = actions != nullptr ? static_cast<const unsigned char*>(actions) + (size_t)i * esz : nullptr;
 #pragma unroll 1
   for (int t = 0; t < n_steps; ++t) {
-    const size_t row = (size_t)t * n + i;
-    const Action a = (actions != nullptr) ? load_action(actions, seg.act_dtype, (long long)row)
-                                          : policy_action<KIND>(policy_seed, gid, step_base + (uint32_t)t);
+    const Action a = (a_in != nullptr) ? load_action(a_in, seg.act_dtype, 0)
+                                       : policy_action<KIND>(ps, step_base + (uint32_t)t);
     T noise = (T)0;
     if (KIND == KIND_ACROBOT) {
       if (p[AC_NOISE] > (T)0) noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
@@ -201,13 +210,14 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
       el = 0;
       sb = 0;
     }
-    if (traj.obs != nullptr) store_obs<Tr::D>(traj.obs, row, o);
+    if (t_obs != nullptr) { store_obs<Tr::D>(t_obs, 0, o); t_obs += (size_t)n * Tr::D; }
     if (traj.actions != nullptr) {
-      if (Tr::DISCRETE) static_cast<int32_t*>(traj.actions)[row] = a.i;
-      else static_cast<float*>(traj.actions)[row] = a.f;
+      if (Tr::DISCRETE) { *t_act_i = a.i; t_act_i += n; }
+      else { *t_act_f = a.f; t_act_f += n; }
     }
-    if (traj.reward != nullptr) traj.reward[row] = so.reward;
-    if (traj.done != nullptr) traj.done[row] = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0));
+    if (t_rew != nullptr) { *t_rew = so.reward; t_rew += n; }
+    if (t_done != nullptr) { *t_done = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0)); t_done += n; }
+    if (a_in != nullptr) a_in += (size_t)n * esz;
   }
   store_rng_state(seg.rng, n, i, g);
   StateIO<T, Tr::S>::store(seg.state, i, s);

@@ -187,6 +187,8 @@ class CARLEnv(abc.ABC):
         self._max_episode_steps = int(max_episode_steps) if max_episode_steps else self._info.default_max_steps
         self._alloc()
         self._context_ids = np.full(self.num_envs, -1, dtype=np.int64)  # per-env current context id
+        self._reset_counts = np.zeros(self.num_envs, dtype=np.int64)
+        self._rr_offset = np.zeros(self.num_envs, dtype=np.int64)
         self._ctx_obs_cache = None
         self._ctx_obs_host_cache = None
         self._ids_view = None
@@ -254,6 +256,9 @@ class CARLEnv(abc.ABC):
             self.context_selector.contexts_keys[int(ids[-1])]
         ]
         self._context_ids = ids
+        # a round-robin selector continues from the assigned id (selection.py:116-118)
+        nxt = np.arange(self.num_envs) + self.env_lo + self._reset_counts * self.global_num_envs
+        self._rr_offset = (ids + 1 - nxt) % len(self._table)
         self._refresh_context_view()
         self._update_context()
 
@@ -403,12 +408,25 @@ class CARLEnv(abc.ABC):
     def _progress_instance(self, mask: np.ndarray | None = None) -> np.ndarray:
         """``carl_env.py:228-243`` batched: one ``select()`` per env being reset, env order."""
         n_sel = self.num_envs if mask is None else int(mask.sum())
+        sel = self.context_selector
+        if type(sel) is RoundRobinSelector:
+            # Round robin per env instance: the k-th reset of (global) env i selects context
+            # (i + k * N) mod M. For lock-step full resets this is exactly what one shared
+            # RoundRobinSelector queried in env order returns; unlike it, a partial (masked) reset
+            # does not depend on which other envs happen to reset (N contexts <-> N envs stay bound).
+            local = np.arange(self.num_envs) if mask is None else np.nonzero(mask)[0]
+            k = self._reset_counts[local]
+            new_ids = ((local + self.env_lo) + k * self.global_num_envs + self._rr_offset[local]) % len(self._table)
+            self._reset_counts[local] += 1
+            sel.n_calls += self.global_num_envs if mask is None else n_sel
+            if len(new_ids):
+                sel.context_id = int(new_ids[-1])
         # envs owned by other shards consume selector calls too, so ids do not depend on sharding
-        if mask is None and self.world_size > 1:
-            all_ids = self.context_selector.select_batch(self.global_num_envs)
+        elif mask is None and self.world_size > 1:
+            all_ids = sel.select_batch(self.global_num_envs)
             new_ids = all_ids[self.env_lo:self.env_hi]
         else:
-            new_ids = self.context_selector.select_batch(n_sel)
+            new_ids = sel.select_batch(n_sel)
         changed = np.zeros(self.num_envs, dtype=bool)
         if mask is None:
             changed = new_ids != self._context_ids

@@ -31,7 +31,7 @@
 
 /* ---- table layout (must match carl_b200/envs/brax_system.py) ---- */
 enum { MAXL = 12, MAXP = 32, MAXQ = 24, HDR = 32, LSTR = 40, PSTR = 8 };
-enum { OFF_L = HDR, OFF_P = HDR + LSTR * MAXL, OFF_Q = HDR + LSTR * MAXL + PSTR * MAXP };
+enum { OFF_L = HDR, OFF_P = HDR + LSTR * MAXL, OFF_Q = HDR + LSTR * MAXL + PSTR * MAXP, TABLE_N = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ };
 enum { hN_LINKS = 0, hN_Q, hN_QD, hN_POINTS, hN_FRAMES, hDT, hENV, hN_ACT, hK, hCV, hKL, hCA, hERP, hVDAMP, hMSCALE,
        hISCALE, hNOISE, hCTRL, hHEALTHY, hZMIN, hZMAX, hFWD, hAMIN, hAMAX, hEXCL, hQDCLIP, hTERM };
 enum { lPARENT = 0, lTYPE, lQ, lQD, lTPOS = 4, lTROT = 7, lJPOS = 11, lJROT = 14, lLO = 18, lHI = 19, lCOM = 20,
@@ -39,62 +39,88 @@ enum { lPARENT = 0, lTYPE, lQ, lQD, lTPOS = 4, lTROT = 7, lJPOS = 11, lJROT = 14
 enum { T_FREE = 0, T_HINGE = 1, T_PLANAR = 3 };
 enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2 };
 
-typedef float f3[3];
-typedef float f4[4];
+/* Arithmetic type of the restatement: float (the reference's JAX pipeline) by default; built a
+ * second time with -DORACLE_F64 as the round-off-free yardstick that tells float32 noise (stiff
+ * springs amplify it) from algorithmic differences. Tables / contexts / actions stay float32. */
+#ifdef ORACLE_F64
+typedef double real;
+#define NAME(x) x##64
+#define SQRT sqrt
+#define POW pow
+#define EXP exp
+#define ATAN2 atan2
+#define SIN sin
+#define COS cos
+#define FMIN fmin
+#define FMAX fmax
+#else
+typedef float real;
+#define NAME(x) x
+#define SQRT sqrtf
+#define POW powf
+#define EXP expf
+#define ATAN2 atan2f
+#define SIN sinf
+#define COS cosf
+#define FMIN fminf
+#define FMAX fmaxf
+#endif
+typedef real f3[3];
+typedef real f4[4];
 
-static void cross3(const float *a, const float *b, float *o) {
-  float x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+static void cross3(const real *a, const real *b, real *o) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   o[0] = x; o[1] = y; o[2] = z;
 }
-static float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
-static void qmul(const float *a, const float *b, float *o) {
-  float w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
-  float x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
-  float y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
-  float z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+static real dot3(const real *a, const real *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static void qmul(const real *a, const real *b, real *o) {
+  real w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  real x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  real y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  real z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
   o[0] = w; o[1] = x; o[2] = y; o[3] = z;
 }
-static void qconj(const float *a, float *o) { o[0] = a[0]; o[1] = -a[1]; o[2] = -a[2]; o[3] = -a[3]; }
-static void qnorm(float *q) {
-  float n = sqrtf(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  float inv = 1.0f / n;
+static void qconj(const real *a, real *o) { o[0] = a[0]; o[1] = -a[1]; o[2] = -a[2]; o[3] = -a[3]; }
+static void qnorm(real *q) {
+  real n = SQRT(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  real inv = 1.0f / n;
   for (int k = 0; k < 4; ++k) q[k] *= inv;
 }
 /* brax.math.rotate */
-static void rot3(const float *v, const float *q, float *o) {
-  const float *u = q + 1;
-  float s = q[0];
-  float uv = dot3(u, v), uu = dot3(u, u);
+static void rot3(const real *v, const real *q, real *o) {
+  const real *u = q + 1;
+  real s = q[0];
+  real uv = dot3(u, v), uu = dot3(u, u);
   f3 c;
   cross3(u, v, c);
   for (int k = 0; k < 3; ++k) o[k] = 2.0f * uv * u[k] + (s * s - uu) * v[k] + 2.0f * s * c[k];
 }
-static void irot3(const float *v, const float *q, float *o) {
+static void irot3(const real *v, const real *q, real *o) {
   f4 qc;
   qconj(q, qc);
   rot3(v, qc, o);
 }
 
 /* link-frame origin and its velocity from the COM row */
-static void origin_of(const float *row, const float *lt, float *o) {
+static void origin_of(const real *row, const real *lt, real *o) {
   f3 rc;
   rot3(lt + lCOM, row + 3, rc);
   for (int k = 0; k < 3; ++k) o[k] = row[k] - rc[k];
 }
-static void origin_vel_of(const float *row, const float *lt, float *o) {
+static void origin_vel_of(const real *row, const real *lt, real *o) {
   f3 rc, w;
   rot3(lt + lCOM, row + 3, rc);
   cross3(row + 10, rc, w);
   for (int k = 0; k < 3; ++k) o[k] = row[7 + k] - w[k];
 }
-static float eff_mass(float m, const float *sys) { return powf(m, 1.0f - sys[hMSCALE]); }
-static void apply_inv_inertia(const float *v, const float *rot, const float *lt, const float *sys, float *o) {
+static real eff_mass(real m, const real *sys) { return POW(m, 1.0f - sys[hMSCALE]); }
+static void apply_inv_inertia(const real *v, const real *rot, const real *lt, const real *sys, real *o) {
   f4 r;
   f3 w;
   qmul(rot, lt + lIROT, r);
   irot3(v, r, w);
-  float e = 1.0f - sys[hISCALE];
-  for (int k = 0; k < 3; ++k) w[k] *= 1.0f / powf(lt[lIDIAG + k], e);
+  real e = 1.0f - sys[hISCALE];
+  for (int k = 0; k < 3; ++k) w[k] *= 1.0f / POW(lt[lIDIAG + k], e);
   rot3(w, r, o);
 }
 
@@ -102,12 +128,12 @@ static void apply_inv_inertia(const float *v, const float *rot, const float *lt,
 typedef struct {
   f3 ac_pos, ap_pos, jpos, jvel, jang;
   f4 ap_rot, jrot;
-  float psi;
+  real psi;
 } jframe_t;
 
-static void joint_frame(const float *sys, const float *rows, int l, jframe_t *j) {
-  const float *lt = sys + OFF_L + LSTR * l;
-  const float *c = rows + 13 * l;
+static void joint_frame(const real *sys, const real *rows, int l, jframe_t *j) {
+  const real *lt = sys + OFF_L + LSTR * l;
+  const real *c = rows + 13 * l;
   int parent = (int)lt[lPARENT];
   f3 xc, xp = {0, 0, 0}, vp = {0, 0, 0}, wp = {0, 0, 0}, tmp, tmp2;
   f4 xprot = {1, 0, 0, 0}, ac_rot, t;
@@ -115,7 +141,7 @@ static void joint_frame(const float *sys, const float *rows, int l, jframe_t *j)
   rot3(lt + lJPOS, c + 3, tmp);
   for (int k = 0; k < 3; ++k) j->ac_pos[k] = xc[k] + tmp[k];
   qmul(c + 3, lt + lJROT, ac_rot);
-  const float *p = 0;
+  const real *p = 0;
   if (parent >= 0) {
     p = rows + 13 * parent;
     origin_of(p, sys + OFF_L + LSTR * parent, xp);
@@ -148,28 +174,28 @@ static void joint_frame(const float *sys, const float *rows, int l, jframe_t *j)
   irot3(tmp, j->ap_rot, j->jang);
   f3 ey = {0, 1, 0}, yc;
   rot3(ey, j->jrot, yc);
-  j->psi = atan2f(yc[2], yc[1]);
+  j->psi = ATAN2(yc[2], yc[1]);
 }
 
 /* one spring substep over all links of one env (brax.spring.pipeline.step) */
-static void substep(const float *sys, float *rows, const float *ctx, const float *tau) {
+static void substep(const real *sys, real *rows, const real *ctx, const real *tau) {
   const int L = (int)sys[hN_LINKS], P = (int)sys[hN_POINTS];
-  const float dt = sys[hDT];
-  const float gravity = ctx[0], friction = ctx[1], elasticity = ctx[2], ang_damping = ctx[3];
-  float F[MAXL][3], T[MAXL][3];
+  const real dt = sys[hDT];
+  const real gravity = ctx[0], friction = ctx[1], elasticity = ctx[2], ang_damping = ctx[3];
+  real F[MAXL][3], T[MAXL][3];
   memset(F, 0, sizeof(F));
   memset(T, 0, sizeof(T));
   /* 1. joint spring / damper / limit / actuator forces (spring/joints.py resolve) */
-  float pF[MAXL][3], pT[MAXL][3];
+  real pF[MAXL][3], pT[MAXL][3];
   for (int l = 0; l < L; ++l) {
-    const float *lt = sys + OFF_L + LSTR * l;
+    const real *lt = sys + OFF_L + LSTR * l;
     int type = (int)lt[lTYPE], parent = (int)lt[lPARENT];
     memset(pF[l], 0, sizeof(f3));
     memset(pT[l], 0, sizeof(f3));
     if (type == T_FREE) continue;
     jframe_t j;
     joint_frame(sys, rows, l, &j);
-    const float k = sys[hK], cv = sys[hCV], kl = sys[hKL], ca = sys[hCA];
+    const real k = sys[hK], cv = sys[hCV], kl = sys[hKL], ca = sys[hCA];
     f3 ex = {1, 0, 0}, fv, fa, axc;
     rot3(ex, j.jrot, axc);
     cross3(axc, ex, fa);
@@ -180,7 +206,7 @@ static void substep(const float *sys, float *rows, const float *ctx, const float
       fa[2] -= ca * j.jang[2];
     } else {
       for (int q = 0; q < 3; ++q) fv[q] = -k * j.jpos[q] - cv * j.jvel[q];
-      float dang = 0.0f;
+      real dang = 0.0f;
       if (j.psi < lt[lLO]) dang = lt[lLO] - j.psi;
       if (j.psi > lt[lHI]) dang = lt[lHI] - j.psi;
       fa[0] += kl * dang;
@@ -190,12 +216,12 @@ static void substep(const float *sys, float *rows, const float *ctx, const float
     f3 Fw, Tw, r, rxF;
     rot3(fv, j.ap_rot, Fw);
     rot3(fa, j.ap_rot, Tw);
-    const float *c = rows + 13 * l;
+    const real *c = rows + 13 * l;
     for (int q = 0; q < 3; ++q) r[q] = j.ac_pos[q] - c[q];
     cross3(r, Fw, rxF);
     for (int q = 0; q < 3; ++q) { F[l][q] += Fw[q]; T[l][q] += Tw[q] + rxF[q]; }
     if (parent >= 0) {
-      const float *p = rows + 13 * parent;
+      const real *p = rows + 13 * parent;
       for (int q = 0; q < 3; ++q) r[q] = j.ap_pos[q] - p[q];
       cross3(r, Fw, rxF);
       for (int q = 0; q < 3; ++q) { pF[l][q] = -Fw[q]; pT[l][q] = -Tw[q] - rxF[q]; }
@@ -207,56 +233,56 @@ static void substep(const float *sys, float *rows, const float *ctx, const float
         for (int q = 0; q < 3; ++q) { F[l][q] += pF[c][q]; T[l][q] += pT[c][q]; }
   /* 2. semi-implicit velocity update (integrator.integrate_xdd) */
   for (int l = 0; l < L; ++l) {
-    const float *lt = sys + OFF_L + LSTR * l;
-    float *s = rows + 13 * l;
-    float m = eff_mass(ctx[4 + l], sys);
+    const real *lt = sys + OFF_L + LSTR * l;
+    real *s = rows + 13 * l;
+    real m = eff_mass(ctx[4 + l], sys);
     f3 alpha;
     apply_inv_inertia(T[l], s + 3, lt, sys, alpha);
-    float inv_m = 1.0f / m;
+    real inv_m = 1.0f / m;
     f3 acc = {F[l][0] * inv_m, F[l][1] * inv_m, gravity + F[l][2] * inv_m};
-    float dv = expf(sys[hVDAMP] * dt), da = expf(ang_damping * dt);
+    real dv = EXP(sys[hVDAMP] * dt), da = EXP(ang_damping * dt);
     for (int q = 0; q < 3; ++q) {
       s[7 + q] = (s[7 + q] + acc[q] * dt) * dv;
       s[10 + q] = (s[10 + q] + alpha[q] * dt) * da;
     }
   }
   /* 3. ground contacts (spring/collisions.py), impulses averaged per link over active contacts */
-  float ps[MAXL][3], ts[MAXL][3], na[MAXL];
+  real ps[MAXL][3], ts[MAXL][3], na[MAXL];
   memset(ps, 0, sizeof(ps));
   memset(ts, 0, sizeof(ts));
   memset(na, 0, sizeof(na));
   for (int p = 0; p < P; ++p) {
-    const float *pt = sys + OFF_P + PSTR * p;
+    const real *pt = sys + OFF_P + PSTR * p;
     int l = (int)pt[0];
-    const float *lt = sys + OFF_L + LSTR * l;
-    const float *s = rows + 13 * l;
-    float fr = friction < 0.0f ? pt[5] : friction;
-    float el = elasticity < 0.0f ? pt[6] : elasticity;
+    const real *lt = sys + OFF_L + LSTR * l;
+    const real *s = rows + 13 * l;
+    real fr = friction < 0.0f ? pt[5] : friction;
+    real el = elasticity < 0.0f ? pt[6] : elasticity;
     f3 org, c, loc;
     origin_of(s, lt, org);
     rot3(pt + 1, s + 3, loc);
     for (int q = 0; q < 3; ++q) c[q] = org[q] + loc[q];
-    float dist = c[2] - pt[4], pen = -dist;
+    real dist = c[2] - pt[4], pen = -dist;
     if (!(pen > 0.0f)) continue;
     f3 n = {0, 0, 1}, cpos = {c[0], c[1], 0.5f * dist}, rel, rv, tmp;
     for (int q = 0; q < 3; ++q) rel[q] = cpos[q] - s[q];
     cross3(s + 10, rel, tmp);
     for (int q = 0; q < 3; ++q) rv[q] = s[7 + q] + tmp[q];
-    float nv = dot3(n, rv);
-    float inv_m = 1.0f / eff_mass(ctx[4 + l], sys);
+    real nv = dot3(n, rv);
+    real inv_m = 1.0f / eff_mass(ctx[4 + l], sys);
     f3 rxn, t1, t2;
     cross3(rel, n, rxn);
     apply_inv_inertia(rxn, s + 3, lt, sys, t1);
     cross3(t1, rel, t2);
-    float ang = dot3(n, t2);
-    float bvel = sys[hERP] * pen / sys[hDT];
-    float imp = (-1.0f * (1.0f + el) * nv + bvel) / (inv_m + ang);
+    real ang = dot3(n, t2);
+    real bvel = sys[hERP] * pen / sys[hDT];
+    real imp = (-1.0f * (1.0f + el) * nv + bvel) / (inv_m + ang);
     f3 vd;
     for (int q = 0; q < 3; ++q) vd[q] = rv[q] - nv * n[q];
-    float sd = sqrtf(dot3(vd, vd));
-    float impd = sd / (inv_m + ang);
-    float inv_sd = 1.0f / (1e-6f + sd);
-    impd = fminf(impd, fr * imp);
+    real sd = SQRT(dot3(vd, vd));
+    real impd = sd / (inv_m + ang);
+    real inv_sd = 1.0f / (1e-6f + sd);
+    impd = FMIN(impd, fr * imp);
     int apply_n = (nv < 0.0f) && (imp > 0.0f);
     int apply_d = apply_n && (sd > 0.01f);
     if (!apply_n) continue;
@@ -269,11 +295,11 @@ static void substep(const float *sys, float *rows, const float *ctx, const float
   }
   /* 4. delta-velocity + pose integration */
   for (int l = 0; l < L; ++l) {
-    const float *lt = sys + OFF_L + LSTR * l;
-    float *s = rows + 13 * l;
+    const real *lt = sys + OFF_L + LSTR * l;
+    real *s = rows + 13 * l;
     if (na[l] > 0.0f) {
-      float inv_n = 1.0f / na[l];
-      float sc = inv_n / eff_mass(ctx[4 + l], sys);
+      real inv_n = 1.0f / na[l];
+      real sc = inv_n / eff_mass(ctx[4 + l], sys);
       f3 tt = {ts[l][0] * inv_n, ts[l][1] * inv_n, ts[l][2] * inv_n}, dw;
       apply_inv_inertia(tt, s + 3, lt, sys, dw);
       for (int q = 0; q < 3; ++q) { s[7 + q] += ps[l][q] * sc; s[10 + q] += dw[q]; }
@@ -287,11 +313,11 @@ static void substep(const float *sys, float *rows, const float *ctx, const float
 }
 
 /* kinematics.inverse: generalized coordinates of one env */
-static void inverse_kinematics(const float *sys, const float *rows, float *q, float *qd) {
+static void inverse_kinematics(const real *sys, const real *rows, real *q, real *qd) {
   const int L = (int)sys[hN_LINKS];
   for (int l = 0; l < L; ++l) {
-    const float *lt = sys + OFF_L + LSTR * l;
-    const float *s = rows + 13 * l;
+    const real *lt = sys + OFF_L + LSTR * l;
+    const real *s = rows + 13 * l;
     int type = (int)lt[lTYPE], qi = (int)lt[lQ], qdi = (int)lt[lQD];
     if (type == T_FREE) {
       f3 o, vo, al;
@@ -317,30 +343,34 @@ static void inverse_kinematics(const float *sys, const float *rows, float *q, fl
   }
 }
 
-static void make_obs(const float *sys, const float *q, const float *qd, float *obs) {
+static void make_obs(const real *sys, const real *q, const real *qd, real *obs) {
   int nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD], ex = (int)sys[hEXCL];
-  float clip = sys[hQDCLIP];
+  real clip = sys[hQDCLIP];
   int k = 0;
   for (int i = ex; i < nq; ++i) obs[k++] = q[i];
   for (int i = 0; i < nqd; ++i) {
-    float v = qd[i];
-    if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+    real v = qd[i];
+    if (clip > 0.0f) v = FMIN(FMAX(v, -clip), clip);
     obs[k++] = v;
   }
 }
 
 /* pipeline_init: forward kinematics from (q, qd) into the COM rows */
-void brax_oracle_init(const float *sys, int n, const float *q_all, const float *qd_all, float *state, int state_words,
+void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const float *qd_all, real *state, int state_words,
                       float *obs, int obs_dim) {
+  real sys[TABLE_N];
+  for (int i = 0; i < TABLE_N; ++i) sys[i] = sys_f[i];
   const int L = (int)sys[hN_LINKS], nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD];
   for (int e = 0; e < n; ++e) {
-    const float *q = q_all + (size_t)e * nq, *qd = qd_all + (size_t)e * nqd;
-    float *rows = state + (size_t)e * state_words;
-    memset(rows, 0, sizeof(float) * state_words);
+    real q[MAXQ], qd[MAXQ];
+    for (int i = 0; i < nq; ++i) q[i] = q_all[(size_t)e * nq + i];
+    for (int i = 0; i < nqd; ++i) qd[i] = qd_all[(size_t)e * nqd + i];
+    real *rows = state + (size_t)e * state_words;
+    memset(rows, 0, sizeof(real) * state_words);
     for (int l = 0; l < L; ++l) {
-      const float *lt = sys + OFF_L + LSTR * l;
+      const real *lt = sys + OFF_L + LSTR * l;
       int type = (int)lt[lTYPE], parent = (int)lt[lPARENT];
-      const float *ql = q + (int)lt[lQ], *qdl = qd + (int)lt[lQD];
+      const real *ql = q + (int)lt[lQ], *qdl = qd + (int)lt[lQD];
       f3 xpos, xvel, xang;
       f4 xrot;
       if (type == T_FREE) {
@@ -353,14 +383,14 @@ void brax_oracle_init(const float *sys, int n, const float *q_all, const float *
         f4 xprot = {1, 0, 0, 0};
         rot3(ex, lt + lJROT, axis);
         if (parent >= 0) {
-          const float *p = rows + 13 * parent;
-          const float *plt = sys + OFF_L + LSTR * parent;
+          const real *p = rows + 13 * parent;
+          const real *plt = sys + OFF_L + LSTR * parent;
           origin_of(p, plt, xp);
           origin_vel_of(p, plt, vp);
           memcpy(xprot, p + 3, sizeof(f4));
           memcpy(wp, p + 10, sizeof(f3));
         }
-        float angle, rate;
+        real angle, rate;
         f3 trans = {0, 0, 0}, tvel = {0, 0, 0};
         if (type == T_PLANAR) {
           trans[0] = ql[0]; trans[2] = ql[1];
@@ -369,8 +399,8 @@ void brax_oracle_init(const float *sys, int n, const float *q_all, const float *
         } else {
           angle = ql[0]; rate = qdl[0];
         }
-        float h = 0.5f * angle, sn = sinf(h);
-        f4 jrot = {cosf(h), axis[0] * sn, axis[1] * sn, axis[2] * sn};
+        real h = 0.5f * angle, sn = SIN(h);
+        f4 jrot = {COS(h), axis[0] * sn, axis[1] * sn, axis[2] * sn};
         qnorm(jrot);
         f3 rj, jpos, lpos, tmp, tmp2;
         rot3(lt + lJPOS, jrot, rj);
@@ -391,53 +421,57 @@ void brax_oracle_init(const float *sys, int n, const float *q_all, const float *
         rot3(ar, xrot, tmp);
         for (int k = 0; k < 3; ++k) xang[k] = wp[k] + tmp[k];
       }
-      float *s = rows + 13 * l;
+      real *s = rows + 13 * l;
       f3 rc, w;
       rot3(lt + lCOM, xrot, rc);
       cross3(xang, rc, w);
       for (int k = 0; k < 3; ++k) { s[k] = xpos[k] + rc[k]; s[7 + k] = xvel[k] + w[k]; s[10 + k] = xang[k]; }
       for (int k = 0; k < 4; ++k) s[3 + k] = xrot[k];
     }
-    float qq[MAXQ], qqd[MAXQ];
+    real qq[MAXQ], qqd[MAXQ], ob[64];
     inverse_kinematics(sys, rows, qq, qqd);
-    make_obs(sys, qq, qqd, obs + (size_t)e * obs_dim);
+    make_obs(sys, qq, qqd, ob);
+    for (int i = 0; i < obs_dim; ++i) obs[(size_t)e * obs_dim + i] = (float)ob[i];
   }
 }
 
 /* One env-step of n envs: actuator torques, n_frames substeps, env layer, EpisodeWrapper,
  * AutoResetWrapper (autoreset != 0). ctx rows: gravity, friction, elasticity, ang_damping, masses. */
-void brax_oracle_step(const float *sys, int n, float *state, int state_words, const float *ctx, int n_ctx,
-                      const float *actions, int *elapsed, int max_steps, int autoreset, const float *first_state,
+void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_words, const float *ctx, int n_ctx,
+                      const float *actions, int *elapsed, int max_steps, int autoreset, const real *first_state,
                       const float *first_obs, float *obs, int obs_dim, float *reward, unsigned char *done_out,
                       float *final_obs) {
+  real sys[TABLE_N];
+  for (int i = 0; i < TABLE_N; ++i) sys[i] = sys_f[i];
   const int L = (int)sys[hN_LINKS], A = (int)sys[hN_ACT], NF = (int)sys[hN_FRAMES], env = (int)sys[hENV];
   const int nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD];
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
   for (int e = 0; e < n; ++e) {
-    float *rows = state + (size_t)e * state_words;
-    const float *c = ctx + (size_t)e * n_ctx;
-    const float *act = actions + (size_t)e * A;
-    float tau[MAXL];
-    float act_sq = 0.0f;
+    real *rows = state + (size_t)e * state_words;
+    real c[4 + MAXL], act[MAXL];
+    for (int i = 0; i < n_ctx; ++i) c[i] = ctx[(size_t)e * n_ctx + i];
+    for (int i = 0; i < A; ++i) act[i] = actions[(size_t)e * A + i];
+    real tau[MAXL];
+    real act_sq = 0.0f;
     for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
     for (int l = 0; l < L; ++l) {
-      const float *lt = sys + OFF_L + LSTR * l;
+      const real *lt = sys + OFF_L + LSTR * l;
       int ai = (int)lt[lACT];
       tau[l] = 0.0f;
-      if (ai >= 0) tau[l] = lt[lGEAR] * fminf(fmaxf(act[ai], lt[lCLO]), lt[lCHI]);
+      if (ai >= 0) tau[l] = lt[lGEAR] * FMIN(FMAX(act[ai], lt[lCLO]), lt[lCHI]);
     }
     f3 o0, o1;
     origin_of(rows, sys + OFF_L, o0);
     for (int f = 0; f < NF; ++f) substep(sys, rows, c, tau);
     origin_of(rows, sys + OFF_L, o1);
-    float q[MAXQ], qd[MAXQ];
+    real q[MAXQ], qd[MAXQ];
     inverse_kinematics(sys, rows, q, qd);
-    float *ob = obs + (size_t)e * obs_dim;
+    real ob[64];
     make_obs(sys, q, qd, ob);
-    float dt_env = sys[hDT] * sys[hN_FRAMES];
-    float xvel = (o1[0] - o0[0]) / dt_env;
+    real dt_env = sys[hDT] * sys[hN_FRAMES];
+    real xvel = (o1[0] - o0[0]) / dt_env;
     int healthy = 1;
     if (env == E_ANT) {
       healthy = !(o1[2] < sys[hZMIN]) && !(o1[2] > sys[hZMAX]);
@@ -447,17 +481,19 @@ void brax_oracle_step(const float *sys, int n, float *state, int state_words, co
       for (int i = 0; i < nqd; ++i) ok = ok && (qd[i] > -100.0f) && (qd[i] < 100.0f);
       healthy = ok && (sys[hZMIN] < o1[2]) && (o1[2] < sys[hZMAX]) && (sys[hAMIN] < q[2]) && (q[2] < sys[hAMAX]);
     }
-    float r = sys[hFWD] * xvel + sys[hHEALTHY] - sys[hCTRL] * act_sq;
+    real r = sys[hFWD] * xvel + sys[hHEALTHY] - sys[hCTRL] * act_sq;
     int done = (sys[hTERM] > 0.0f) && !healthy;
     elapsed[e] += 1;
     if (max_steps > 0 && elapsed[e] >= max_steps) done = 1;
     if (done && autoreset) {
-      if (final_obs) memcpy(final_obs + (size_t)e * obs_dim, ob, sizeof(float) * obs_dim);
-      memcpy(rows, first_state + (size_t)e * state_words, sizeof(float) * state_words);
-      memcpy(ob, first_obs + (size_t)e * obs_dim, sizeof(float) * obs_dim);
+      if (final_obs)
+        for (int i = 0; i < obs_dim; ++i) final_obs[(size_t)e * obs_dim + i] = (float)ob[i];
+      memcpy(rows, first_state + (size_t)e * state_words, sizeof(real) * state_words);
+      for (int i = 0; i < obs_dim; ++i) ob[i] = first_obs[(size_t)e * obs_dim + i];
       elapsed[e] = 0;
     }
-    reward[e] = r;
+    for (int i = 0; i < obs_dim; ++i) obs[(size_t)e * obs_dim + i] = (float)ob[i];
+    reward[e] = (float)r;
     done_out[e] = (unsigned char)done;
   }
 }

@@ -65,3 +65,17 @@ class BraxHostCheck:
                               int(autoreset), self._p(first_state), self._p(first_obs), self._p(obs), sysd["obs_dim"],
                               self._p(reward), self._p(done), int(stock_contact))
         return obs, reward, done.astype(bool)
+
+
+def assert_close_scaled(got, want, rel=1e-5, steps=1, what="obs"):
+    """North-star tolerance for the float32 Brax path: 1e-5 relative *to the magnitude of the
+    env's own vector* (joint velocities reach ~10 while angles are ~0.1: an element-wise rtol on
+    near-zero entries would test float32 cancellation noise, not the physics), scaled by the number
+    of env-steps compared without re-synchronisation."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    scale = np.maximum(1.0, np.abs(want).reshape(want.shape[0], -1).max(axis=1))
+    tol = rel * steps * scale.reshape((-1,) + (1,) * (want.ndim - 1))
+    err = np.abs(got - want)
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.size} entries beyond {rel:g} x {steps} x scale; "
+                           f"worst err {err.max():.3e} (allowed {tol.reshape(-1)[np.argmax((err / tol).reshape(err.shape[0], -1).max(axis=1))]:.3e})")

@@ -29,12 +29,13 @@ void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
 
 void hc_policy_action(int kind, uint64_t seed, uint64_t env_id, uint32_t step, int* ai, float* af) {
   Action a;
+  PolicyStream ps = policy_stream(seed, env_id);
   switch (kind) {
-    case KIND_CARTPOLE: a = policy_action<KIND_CARTPOLE>(seed, env_id, step); break;
-    case KIND_PENDULUM: a = policy_action<KIND_PENDULUM>(seed, env_id, step); break;
-    case KIND_ACROBOT: a = policy_action<KIND_ACROBOT>(seed, env_id, step); break;
-    case KIND_MOUNTAINCAR: a = policy_action<KIND_MOUNTAINCAR>(seed, env_id, step); break;
-    default: a = policy_action<KIND_MOUNTAINCAR_CONT>(seed, env_id, step); break;
+    case KIND_CARTPOLE: a = policy_action<KIND_CARTPOLE>(ps, step); break;
+    case KIND_PENDULUM: a = policy_action<KIND_PENDULUM>(ps, step); break;
+    case KIND_ACROBOT: a = policy_action<KIND_ACROBOT>(ps, step); break;
+    case KIND_MOUNTAINCAR: a = policy_action<KIND_MOUNTAINCAR>(ps, step); break;
+    default: a = policy_action<KIND_MOUNTAINCAR_CONT>(ps, step); break;
   }
   *ai = a.i; *af = a.f;
 }

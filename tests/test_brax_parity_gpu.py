@@ -7,7 +7,7 @@ import torch
 
 from carl_b200.envs import brax_system as bs
 from oracle.brax import OracleBraxEnv
-from tests.brax_util import random_q
+from tests.brax_util import assert_close_scaled, random_q
 
 pytestmark = pytest.mark.gpu
 BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper"}
@@ -33,6 +33,12 @@ def make_env(body, n, rng, mode="applied", **kw):
 
 def oracle_for(env, **kw):
     return OracleBraxEnv(env._sysd, env._ctx.cpu().numpy(), **kw)
+
+
+def scaled_err(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = np.maximum(1.0, np.abs(want).reshape(want.shape[0], -1).max(axis=1, keepdims=True))
+    return (np.abs(got - want).reshape(want.shape[0], -1) / scale).max()
 
 
 @pytest.mark.parametrize("body", list(BODIES))
@@ -62,18 +68,33 @@ def test_single_env_step_matches(body, mode):
         ctx[:, 1] = -1.0
         ctx[:, 2] = -1.0
     ora = OracleBraxEnv(env._sysd, ctx, autoreset=False)
+    ora64 = OracleBraxEnv(env._sysd, ctx, autoreset=False, f64=True)
     ora.init_from_q(q, qd)
+    ora64.init_from_q(q, qd)
     a = rng.uniform(-1.2, 1.2, (n, env._sysd["n_act"])).astype(np.float32)
     o_ref, r_ref, d_ref, _ = ora.step(a)
+    o64, r64, d64, _ = ora64.step(a)
     obs, r, te, tr, _ = env.step(torch.from_numpy(a).cuda())
-    np.testing.assert_allclose(obs["obs"].cpu().numpy(), o_ref, rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(r.cpu().numpy(), r_ref, rtol=1e-4, atol=1e-4)
+    got = obs["obs"].cpu().numpy()
+    # float32 round-off floor of the algorithm itself (stiff springs amplify rounding ~80x per
+    # substep): the float32 restatement against the same restatement in float64
+    floor = max(scaled_err(o_ref, o64), scaled_err(ora.state, ora64.state))
+    e_obs, e_state = scaled_err(got, o64), scaled_err(env.state.cpu().numpy(), ora64.state)
+    print(f"[{body}/{mode}] fp32 floor {floor:.2e}; CUDA vs f64: obs {e_obs:.2e} state {e_state:.2e}; "
+          f"CUDA vs fp32 oracle: obs {scaled_err(got, o_ref):.2e}")
+    tol = max(1e-5, 4.0 * floor)
+    assert e_obs <= tol and e_state <= tol, (e_obs, e_state, tol)
+    assert scaled_err(got, o_ref) <= tol
+    np.testing.assert_allclose(r.cpu().numpy(), r_ref, rtol=1e-4, atol=2e-4)
     assert (te.cpu().numpy() == d_ref).all() and not tr.any()
-    np.testing.assert_allclose(env.state.cpu().numpy(), ora.state, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("body", list(BODIES))
 def test_rollout_with_autoreset_matches(body):
+    """60 env-steps along the device trajectory with episode truncation -> done -> AutoReset. The
+    oracle is re-synchronised to the device state before every step (teacher forcing): contact-rich
+    locomotion is chaotic, free-running float32 trajectories diverge after a few contact switches
+    whatever the implementation, so the per-step transition is what can be compared."""
     rng = np.random.default_rng(2)
     n, T, max_steps = 64, 60, 25
     env = make_env(body, n, rng, max_episode_steps=max_steps)
@@ -84,15 +105,20 @@ def test_rollout_with_autoreset_matches(body):
     n_done = 0
     for t in range(T):
         a = rng.uniform(-1, 1, (n, env._sysd["n_act"])).astype(np.float32)
+        ora.state[:] = env.state.cpu().numpy()
+        ora.elapsed[:] = env._elapsed.cpu().numpy()
         o_ref, r_ref, d_ref, fin_ref = ora.step(a)
         obs, r, te, tr, info = env.step(torch.from_numpy(a).cuda())
         d = te.cpu().numpy()
         assert (d == d_ref).all(), f"done mismatch at step {t}"
-        k = (t % max_steps) + 1
-        np.testing.assert_allclose(obs["obs"].cpu().numpy(), o_ref, rtol=2e-5 * k, atol=2e-5 * k)
+        assert_close_scaled(obs["obs"].cpu().numpy(), o_ref, rel=5e-5)
+        assert_close_scaled(env.state.cpu().numpy(), ora.state, rel=5e-5, what="state")
+        np.testing.assert_allclose(r.cpu().numpy(), r_ref, rtol=1e-3, atol=1e-3)
         if d.any():
-            np.testing.assert_allclose(info["final_observation"].cpu().numpy()[d], fin_ref[d], rtol=1e-3, atol=1e-3)
+            assert_close_scaled(info["final_observation"].cpu().numpy()[d], fin_ref[d], rel=5e-5, what="final_obs")
+            np.testing.assert_array_equal(env.state.cpu().numpy()[d], env._first_state.cpu().numpy()[d])
         n_done += int(d.sum())
+        assert (env._elapsed.cpu().numpy() == ora.elapsed).all()
     assert n_done >= n
 
 
@@ -169,7 +195,8 @@ def test_brax_api_shapes_and_batch_size():
         env._update_context()
         obs, info = env.reset()
         assert obs["obs"].shape == (5, D) and env.action_space.shape == (5, A)
-        assert "target_distance" not in env.contexts[0]
+        assert "target_distance" in env.contexts[0]  # the contexts setter fills ALL defaults (carl_env.py:135-137)
+        assert "target_distance" not in cls.get_default_context()
         a = np.stack([env.single_action_space.sample() for _ in range(5)])
         obs, r, te, tr, info = env.step(a)  # numpy in -> numpy out
         assert obs["obs"].shape == (5, D) and r.shape == (5,) and te.dtype == np.bool_ and not tr.any()

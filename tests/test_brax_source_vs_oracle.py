@@ -7,7 +7,7 @@ import pytest
 
 from carl_b200.envs import brax_system as bs
 from oracle.brax import OracleBraxEnv
-from tests.brax_util import BraxHostCheck, random_ctx, random_q
+from tests.brax_util import BraxHostCheck, assert_close_scaled, random_ctx, random_q
 
 BODIES = ["ant", "halfcheetah", "hopper"]
 
@@ -55,10 +55,10 @@ def test_single_env_step_matches(hc, body, applied):
     o_ref, r_ref, d_ref, _ = ora.step(a)
     el = np.zeros(n, dtype=np.int32)
     o, r, d = hc.step(sysd, st, ctx, a, el, 1000, 0, st.copy(), o_ref.copy(), stock_contact=0 if applied else 1)
-    np.testing.assert_allclose(o, o_ref, rtol=1e-5, atol=1e-5)
+    assert_close_scaled(o, o_ref, rel=1e-5)
     np.testing.assert_allclose(r, r_ref, rtol=1e-4, atol=1e-4)
     assert (d == d_ref).all()
-    np.testing.assert_allclose(st, ora.state, rtol=1e-5, atol=1e-5)
+    assert_close_scaled(st, ora.state, rel=1e-5, what="state")
 
 
 @pytest.mark.parametrize("body", BODIES)
@@ -82,7 +82,7 @@ def test_rollout_with_autoreset_matches(hc, body):
         o, r, d = hc.step(sysd, st, ctx, a, el, max_steps, 1, first_state, first_obs)
         assert (d == d_ref).all(), f"done mismatch at step {t}"
         k = (t % max_steps) + 1
-        np.testing.assert_allclose(o, o_ref, rtol=2e-5 * k, atol=2e-5 * k)
+        assert_close_scaled(o, o_ref, rel=2e-5, steps=k)
         n_done += int(d.sum())
         assert (el == ora.elapsed).all()
     assert n_done >= n  # every env was truncated at least twice
