@@ -235,7 +235,7 @@ def run_gpu_arm(args):
     if distributed:
         from carl_b200.parallel import ObsGather
 
-        gather = ObsGather(env, mode="nccl")
+        gather = ObsGather(env, mode=args.gather)
 
     K, W = args.steps, args.warmup
     T = math.gcd(K, args.fuse)  # fused steps per launch; K/T launches time EXACTLY K steps
@@ -310,18 +310,29 @@ def run_gpu_arm(args):
         for g_ in range(3):
             _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, side.cuda_stream))
     torch.cuda.synchronize(dev)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph, stream=side):
-        for g_ in range(G):
-            _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32,
-                                             torch.cuda.current_stream(dev).cuda_stream))
+    graph = None
+    if not distributed:  # the fused gather changes slot / flag value per launch: not graph-capturable
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for g_ in range(G):
+                _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32,
+                                                 torch.cuda.current_stream(dev).cuda_stream))
+
+    def replay():
+        if graph is not None:
+            graph.replay()
+        else:
+            for g_ in range(G):
+                _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, stream.cuda_stream))
+                gather.gather()
+
     for _ in range(max(1, W // G)):
-        graph.replay()
+        replay()
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record(stream)
     for _ in range(K_api // G):
-        graph.replay()
+        replay()
     a1.record(stream)
     barrier()
     api_ms = a0.elapsed_time(a1)
@@ -379,7 +390,7 @@ def run_gpu_arm(args):
             "n_envs": n_global, "fused_steps_per_launch": T, "launches": K // T,
             "l2": f"trajectory ring {n_slots} x {slot_bytes / 2**20:.0f} MiB > L2 (outputs go to DRAM); env state "
                   f"({n_local * 90 / 2**20:.1f} MiB working set) is register/L2 resident by design",
-            "collective": "NCCL all-gather of the last obs per launch" if distributed else "none",
+            "collective": (f"obs all-gather per launch: {args.gather}" + (" (in-kernel NVLink peer stores + flag wait)" if args.gather == "fused" else "")) if distributed else "none",
         },
         "gpu_launches": int(launches),
         "clocks": clock_info,
@@ -406,12 +417,79 @@ def run_gpu_arm(args):
             "cold_l2_frac": STEP_CONTRACT_BYTES * n_local / (cold_ms * 1e-3) / 1e9 / peak,
         },
     }
+    if world == 1 and not args.no_ant:
+        out["ant_8192"] = ant_leg(dev, peak, args)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg(steps_per_call=200, target_seconds=args.cpu_seconds)
     print(json.dumps(out))
     if distributed:
         dist.destroy_process_group()
     return 0
+
+
+def ant_leg(dev, peak, args):
+    """Secondary north-star workload (BASELINE configs[3] at one GPU): CARLBraxAnt, 8 192 contexts
+    (gravity / mass_torso / friction sampled, context_mode="applied"), uniform random policy."""
+    import ctypes
+
+    import torch
+
+    from carl_b200 import _native
+    from carl_b200.context import ContextSampler, UniformFloatContextFeature
+    from carl_b200.envs import CARLBraxAnt, ContextTable
+
+    n = 8192
+    names = list(CARLBraxAnt.get_context_space().get_default_context().keys())
+    sampler = ContextSampler(
+        [UniformFloatContextFeature("gravity", -15, -5), UniformFloatContextFeature("mass_torso", 5, 20),
+         UniformFloatContextFeature("friction", 0.5, 1.5)], context_space=CARLBraxAnt.get_context_space(), seed=0)
+    env = CARLBraxAnt(contexts=ContextTable(names, sampler.sample_context_table(n, names)), device=dev,
+                      context_mode="applied")
+    env.reset(seed=0)
+    info = env._info
+    T, K = 20, 200
+    traj_bytes = info.obs_dim * 4 + info.act_dim * 4 + 4 + 1
+    ring = [dict(obs=torch.empty(T, n, info.obs_dim, device=dev), actions=torch.empty(T, n, info.act_dim, device=dev),
+                 reward=torch.empty(T, n, device=dev), done=torch.empty(T, n, dtype=torch.uint8, device=dev))
+            for _ in range(8)]  # 8 x 23 MiB > L2
+    trajs = [_native.Traj(obs=r["obs"].data_ptr(), actions=r["actions"].data_ptr(), reward=r["reward"].data_ptr(),
+                          done=r["done"].data_ptr()) for r in ring]
+    stream = torch.cuda.current_stream(dev)
+    launch = lambda j: _native.check(env._lib.carlb_env_rollout(env._handle, T, 7, j * T, None, _native.ACT_F32,
+                                                                ctypes.byref(trajs[j % 8]), stream.cuda_stream))
+    for j in range(3):
+        launch(j)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for j in range(K // T):
+        launch(10 + j)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    fused = n * K / (ms * 1e-3)
+    # single-step API, device actions
+    acts = torch.rand(64, n, info.act_dim, device=dev) * 2 - 1
+    for j in range(5):
+        env.step(acts[j])
+    torch.cuda.synchronize(dev)
+    e0.record(stream)
+    for j in range(100):
+        _native.check(env._lib.carlb_env_step(env._handle, acts[j % 64].data_ptr(), _native.ACT_F32, stream.cuda_stream))
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    api_ms = e0.elapsed_time(e1) / 100
+    step_bytes = 1114  # SURVEY §8(d): R state 468 + ctx 24 + action 32 + 4 ; W state 468 + obs 108 + 4 + 2 + 4
+    return {
+        "workload": "CARLBraxAnt, 8192 sampled contexts (gravity/mass_torso/friction), context_mode=applied, "
+                    "uniform random policy, 10 spring substeps per env-step",
+        "value": fused, "unit": UNIT, "fused_steps_per_launch": T, "ms_per_env_step_batch": ms / K,
+        "roofline": {"bound": "fp32-issue (HBM shown for reference)", "bytes_per_env_step": traj_bytes + step_bytes / T,
+                     "achieved": (traj_bytes * T + step_bytes) * n / (ms / (K // T) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": (traj_bytes * T + step_bytes) * n / (ms / (K // T) * 1e-3) / 1e9 / peak},
+        "step_api": {"value": n / (api_ms * 1e-3), "us_per_launch": api_ms * 1e3,
+                     "hbm_frac_1114B": step_bytes * n / (api_ms * 1e-3) / 1e9 / peak},
+    }
 
 
 def main():
@@ -423,6 +501,8 @@ def main():
     ap.add_argument("--fuse", type=int, default=100, help="env-steps fused per rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ant", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU obs gather path")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -28,6 +28,7 @@ UNITS = [
     ("abi.cu", []),
     ("classic.cu", ["-fmad=false"]),
     ("brax.cu", [] if os.environ.get("CARLB_BRAX_FMAD") == "1" else ["-fmad=false"]),
+    ("gather.cu", []),
 ]
 
 

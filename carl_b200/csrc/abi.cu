@@ -40,6 +40,7 @@ Segment make_segment(const carlb_env* env, int act_dtype) {
   s.final_obs = env->bufs.final_obs;
   s.n_peers = env->n_peers;
   for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
+  s.block_counter = nullptr;
   return s;
 }
 

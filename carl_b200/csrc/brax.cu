@@ -52,6 +52,9 @@ struct BraxSeg {
   float* first_obs;
   int n_peers;
   float* peer_obs[CARLB_MAX_PEERS];
+  unsigned int* peer_flags[CARLB_MAX_PEERS];
+  unsigned int signal_value;
+  unsigned int* block_counter;
 };
 
 struct WarpScratch {
@@ -144,6 +147,8 @@ struct LaneCtx {
   float pt_mass;     // mass of my contact point's link
   float gravity, friction_ctx, elasticity_ctx, ang_damping;
   float pt_friction, pt_elasticity;
+  LinkConst lc;     // loop-invariant constants of my link
+  LinkConst pt_lc;  // ... and of my contact point's link
 };
 
 __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const float* ctx_row, int n_ctx, int lane,
@@ -175,6 +180,8 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const float* 
   // friction / elasticity: a negative context value means "keep the stock per-geom value"
   c.pt_friction = (c.friction_ctx < 0.0f || stock_contact) ? c.pt[5] : c.friction_ctx;
   c.pt_elasticity = (c.elasticity_ctx < 0.0f || stock_contact) ? c.pt[6] : c.elasticity_ctx;
+  c.lc = make_link_const(sys, c.lt, c.mass, c.ang_damping);
+  c.pt_lc = make_link_const(sys, link_tab(sys, c.pt_link), c.pt_mass, c.ang_damping);
   return c;
 }
 
@@ -208,14 +215,14 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
           wr.t = wr.t + v3(pw[3], pw[4], pw[5]);
         }
       }
-      integrate_xdd(s, wr, sys, c.lt, c.mass, c.gravity, c.ang_damping);
+      integrate_xdd(s, wr, sys, c.lt, c.lc, c.gravity);
       write_link(w.ls, lane, s);
     }
     __syncwarp();
     // ground contacts: lane p resolves candidate point p against the plane
     if (c.is_point) {
       const LinkState ps = read_link(w.ls, c.pt_link);
-      const ContactOut co = contact_resolve(sys, c.pt, link_tab(sys, c.pt_link), ps, c.pt_mass, c.pt_friction,
+      const ContactOut co = contact_resolve(sys, c.pt, link_tab(sys, c.pt_link), ps, c.pt_lc, c.pt_friction,
                                             c.pt_elasticity);
       float* o = w.co + lane * 7;
       o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
@@ -231,7 +238,7 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
         ts = ts + v3(o[3], o[4], o[5]);
         na += o[6];
       }
-      integrate_xdv(s, ps, ts, na, sys, c.lt, c.mass);
+      integrate_xdv(s, ps, ts, na, c.lt, c.lc);
       integrate_pose(s, dt);
     }
     __syncwarp();
@@ -342,15 +349,9 @@ struct SmemLayout {
 // ------------------------------------------------------------------------------- step
 // One env-step: [AutoReset zeroing] -> n_frames substeps -> obs/reward/done -> EpisodeWrapper
 // truncation -> AutoReset (state/obs replaced by the stored first ones where done).
-__global__ void __launch_bounds__(kThreads) brax_step_kernel(const __grid_constant__ BraxSeg seg, const float* actions,
-                                                             int n_steps, uint64_t policy_seed, uint32_t step_base,
-                                                             const carlb_traj_t traj, int stock_contact) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
-  stage_system(sm.sys, seg.sys, &sm.bar);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * kWarpsPerCta + warp;
-  if (env >= seg.n) return;
+__device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayout& sm, int env, int warp, int lane,
+                                               const float* actions, int n_steps, uint64_t policy_seed,
+                                               uint32_t step_base, const carlb_traj_t& traj, int stock_contact) {
   const float* sys = sm.sys;
   WarpScratch& w = sm.warp[warp];
   const LaneCtx c = make_lane_ctx(sys, seg.ctx + (size_t)env * seg.n_ctx, seg.n_ctx, lane, stock_contact != 0);
@@ -432,18 +433,30 @@ __global__ void __launch_bounds__(kThreads) brax_step_kernel(const __grid_consta
   }
 }
 
-// ------------------------------------------------------------------------------ reset
-// Env.reset: q = init_q + U(+-noise), qd = noise * N(0,1) (Hopper: both uniform), forward
-// kinematics (pipeline_init), obs; stores the first state/obs for AutoResetWrapper.
-__global__ void __launch_bounds__(kThreads) brax_reset_kernel(const __grid_constant__ BraxSeg seg, const uint8_t* mask,
-                                                              const float* q_in, const float* qd_in) {
+__global__ void __launch_bounds__(kThreads, 4) brax_step_kernel(const __grid_constant__ BraxSeg seg, const float* actions,
+                                                             int n_steps, uint64_t policy_seed, uint32_t step_base,
+                                                             const carlb_traj_t traj, int stock_contact) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * kWarpsPerCta + warp;
-  if (env >= seg.n) return;
-  if (mask != nullptr && mask[env] == 0) return;
+  if (env < seg.n) brax_step_body(seg, sm, env, warp, lane, actions, n_steps, policy_seed, step_base, traj, stock_contact);
+  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+}
+
+// ------------------------------------------------------------------------------ reset
+// Env.reset: q = init_q + U(+-noise), qd = noise * N(0,1) (Hopper: both uniform), forward
+// kinematics (pipeline_init), obs; stores the first state/obs for AutoResetWrapper.
+__device__ __forceinline__ void brax_reset_body(const BraxSeg& seg, SmemLayout& sm, int env, int warp, int lane,
+                                                const uint8_t* mask, const float* q_in, const float* qd_in) {
+  if (mask != nullptr && mask[env] == 0) {
+    // not reset: with a fused gather attached the current row still has to reach the new slot
+    for (int r = 0; r < seg.n_peers; ++r)
+      for (int i = lane; i < seg.obs_dim; i += 32)
+        seg.peer_obs[r][(size_t)(seg.global_offset + env) * seg.obs_dim + i] = seg.obs[(size_t)env * seg.obs_dim + i];
+    return;
+  }
   const float* sys = sm.sys;
   WarpScratch& w = sm.warp[warp];
   const LaneCtx c = make_lane_ctx(sys, seg.ctx + (size_t)env * seg.n_ctx, seg.n_ctx, lane, true);
@@ -494,6 +507,17 @@ __global__ void __launch_bounds__(kThreads) brax_reset_kernel(const __grid_const
     seg.elapsed[env] = 0;
     seg.episode[env] = (uint64_t)episode + 1ull;
   }
+}
+
+__global__ void __launch_bounds__(kThreads) brax_reset_kernel(const __grid_constant__ BraxSeg seg, const uint8_t* mask,
+                                                              const float* q_in, const float* qd_in) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
+  stage_system(sm.sys, seg.sys, &sm.bar);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int env = blockIdx.x * kWarpsPerCta + warp;
+  if (env < seg.n) brax_reset_body(seg, sm, env, warp, lane, mask, q_in, qd_in);
+  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -613,6 +637,9 @@ static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what) {
   s.first_obs = env->bufs.first_obs;
   s.n_peers = env->n_peers;
   for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
+  s.block_counter = nullptr;
+  if (env->gather != nullptr)
+    gather_fill(env->gather, &s.n_peers, s.peer_obs, s.peer_flags, &s.signal_value, &s.block_counter);
   return CARLB_OK;
 }
 

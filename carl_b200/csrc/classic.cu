@@ -47,16 +47,22 @@ __global__ void __launch_bounds__(kBlock) seed_kernel(uint64_t* rng, int n, uint
 
 // ----------------------------------------------------------------------------- reset
 template <int KIND, typename T>
-__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ Segment seg, const uint8_t* mask) {
+__device__ __forceinline__ void reset_one(const Segment& seg, const uint8_t* mask, int i) {
   typedef Traits<KIND> Tr;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= seg.n) return;
-  if (mask != nullptr && mask[i] == 0) return;
+  if (mask != nullptr && mask[i] == 0) {
+    // not reset: with a fused gather attached the current row still has to reach the new slot
+    if (seg.n_peers > 0) {
+      float o[Tr::D];
+#pragma unroll
+      for (int k = 0; k < Tr::D; ++k) o[k] = seg.obs[(size_t)i * Tr::D + k];
+      for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+    }
+    return;
+  }
   T p[Tr::P];
   load_rows<KIND, T>(seg, i, Tr::P_STEP, Tr::P, p);
   Pcg64 g = load_rng(seg.rng, seg.n, i);
-#pragma unroll
-  for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_advance1(g);  // gymnasium's own (discarded) draws
+  pcg64_skip<Tr::GYM_DRAWS>(g);  // gymnasium's own (discarded) draws
   T s[Tr::S];
   float o[Tr::D];
   env_reset<KIND, T>(s, p, g, o);
@@ -69,6 +75,13 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
   seg.reward[i] = 0.0f;
   seg.terminated[i] = 0;
   seg.truncated[i] = 0;
+}
+
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ Segment seg, const uint8_t* mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < seg.n) reset_one<KIND, T>(seg, mask, i);
+  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
 // ------------------------------------------------------------------------------ step
@@ -103,8 +116,7 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
     load_rows<KIND, T>(seg, i, Tr::P_STEP, Tr::P, p);
     if (!rng_live) g = load_rng(seg.rng, seg.n, i);
     rng_live = true;
-#pragma unroll
-    for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_advance1(g);
+    pcg64_skip<Tr::GYM_DRAWS>(g);
     env_reset<KIND, T>(s, p, g, o);
     el = 0;
     sb = 0;
@@ -123,8 +135,8 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
 template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Segment seg, const void* actions) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= seg.n) return;
-  step_one<KIND, T>(seg, actions, i);
+  if (i < seg.n) step_one<KIND, T>(seg, actions, i);
+  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
 // ----------------------------------------------------------------------- mixed batch
@@ -167,7 +179,10 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   typedef Traits<KIND> Tr;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = seg.n;
-  if (i >= n) return;
+  if (i >= n) {
+    peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+    return;
+  }
   T s[Tr::S];
   StateIO<T, Tr::S>::load(seg.state, i, s);
   T p[Tr::P];
@@ -192,6 +207,27 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   uint8_t* t_done = traj.done != nullptr ? traj.done + i : nullptr;
   const size_t esz = seg.act_dtype == CARLB_ACT_I64 ? 8 : (seg.act_dtype == CARLB_ACT_U8 ? 1 : 4);
   const unsigned char* a_in = actions != nullptr ? static_cast<const unsigned char*>(actions) + (size_t)i * esz : nullptr;
+  // Batched pre-generation of the next reset state. A reset costs ~300 integer instructions (two
+  // 128-bit jump-ahead multiplies + S PCG64 draws); under a random policy ~5% of the envs of a warp
+  // reset each step, i.e. ~80% of the warp-iterations would execute that divergent path for one or
+  // two lanes. Instead every lane keeps its NEXT reset state ready in registers; consuming it is a
+  // few moves, and the warp regenerates the missing ones together once kRefill lanes need one, so
+  // the expensive path runs ~5x less often at several times the lane utilisation. The per-env
+  // PCG64 stream is consumed in exactly the same order as a step-by-step run (the draw merely
+  // happens earlier); a pre-generated but unused reset is rolled back at kernel exit. Acrobot with
+  // torque noise interleaves per-step draws on the same stream, so it keeps the in-place path.
+  constexpr int kRefill = 8;
+  bool batch_resets = seg.autoreset != CARLB_AUTORESET_NONE;
+  if (KIND == KIND_ACROBOT) batch_resets = false;
+  const unsigned lanes = __activemask();
+  bool have_next = false;
+  T ns[Tr::S];
+  float no[Tr::D];
+  uint64_t sv_hi = g.state_hi, sv_lo = g.state_lo;
+#pragma unroll
+  for (int k = 0; k < Tr::S; ++k) ns[k] = (T)0;
+#pragma unroll
+  for (int k = 0; k < Tr::D; ++k) no[k] = 0.0f;
 #pragma unroll 1
   for (int t = 0; t < n_steps; ++t) {
     const Action a = (a_in != nullptr) ? load_action(a_in, seg.act_dtype, 0)
@@ -204,11 +240,27 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     el += 1;
     tr = seg.max_steps > 0 && el >= seg.max_steps;
     if (seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr)) {
+      if (!have_next) {  // in-place reset (rare once the batched refill is running)
+        pcg64_skip<Tr::GYM_DRAWS>(g);
+        env_reset<KIND, T>(s, p, g, o);
+      } else {
 #pragma unroll
-      for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_advance1(g);
-      env_reset<KIND, T>(s, p, g, o);
+        for (int k = 0; k < Tr::S; ++k) s[k] = ns[k];
+#pragma unroll
+        for (int k = 0; k < Tr::D; ++k) o[k] = no[k];
+        have_next = false;
+      }
       el = 0;
       sb = 0;
+    }
+    if (batch_resets) {
+      const unsigned need = __ballot_sync(lanes, !have_next);
+      if (__popc(need) >= kRefill && !have_next) {
+        sv_hi = g.state_hi; sv_lo = g.state_lo;
+        pcg64_skip<Tr::GYM_DRAWS>(g);
+        env_reset<KIND, T>(ns, p, g, no);
+        have_next = true;
+      }
     }
     if (t_obs != nullptr) { store_obs<Tr::D>(t_obs, 0, o); t_obs += (size_t)n * Tr::D; }
     if (traj.actions != nullptr) {
@@ -218,6 +270,9 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     if (t_rew != nullptr) { *t_rew = so.reward; t_rew += n; }
     if (t_done != nullptr) { *t_done = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0)); t_done += n; }
     if (a_in != nullptr) a_in += (size_t)n * esz;
+  }
+  if (have_next) {  // roll back the reset that was pre-generated but never used
+    g.state_hi = sv_hi; g.state_lo = sv_lo;
   }
   store_rng_state(seg.rng, n, i, g);
   StateIO<T, Tr::S>::store(seg.state, i, s);
@@ -230,6 +285,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   }
   seg.elapsed[i] = el;
   if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
+  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
 // --------------------------------------------------------------------------- launchers
@@ -257,8 +313,15 @@ int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
   return CARLB_OK;
 }
 
+// Fused cross-GPU gather: point this launch at the next slot of every rank's buffer.
+static void attach_gather(const carlb_env* env, Segment& seg) {
+  if (env->gather == nullptr) return;
+  gather_fill(env->gather, &seg.n_peers, seg.peer_obs, seg.peer_flags, &seg.signal_value, &seg.block_counter);
+}
+
 int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
-  const Segment seg = make_segment(env, CARLB_ACT_I32);
+  Segment seg = make_segment(env, CARLB_ACT_I32);
+  attach_gather(env, seg);
   CARLB_DISPATCH_KIND_T(env->kind, env->precision, (reset_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, mask)));
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
@@ -266,7 +329,8 @@ int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
 }
 
 int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st) {
-  const Segment seg = make_segment(env, act_dtype);
+  Segment seg = make_segment(env, act_dtype);
+  attach_gather(env, seg);
   CARLB_DISPATCH_KIND_T(env->kind, env->precision, (step_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, actions)));
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
@@ -275,7 +339,8 @@ int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaS
 
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
-  const Segment seg = make_segment(env, act_dtype);
+  Segment seg = make_segment(env, act_dtype);
+  attach_gather(env, seg);
   carlb_traj_t tj{};
   if (traj != nullptr) tj = *traj;
   // 64-thread blocks: at N = 65 536 that is 1024 blocks ~ 6.9 per SM (better tail balance over

@@ -31,7 +31,29 @@ struct Segment {
   // peer_obs[r] + (global_offset + i) * D for every peer r (P2P-mapped symmetric buffers)
   int n_peers;
   float* peer_obs[CARLB_MAX_PEERS];
+  unsigned int* peer_flags[CARLB_MAX_PEERS];  // fused gather: my completion word in every rank's buffer
+  unsigned int signal_value;                  // value published when this launch's rows are stored
+  unsigned int* block_counter;                // local CTA arrival counter (last CTA publishes)
 };
+
+// Fused-gather epilogue: every thread of every CTA calls this at the end of an obs-producing
+// kernel. Stores to peer memory are fenced at system scope, the last CTA to arrive publishes the
+// launch number into every rank's flag word.
+__device__ __forceinline__ void peer_signal_epilogue(int n_peers, unsigned int* const* peer_flags, unsigned int signal_value,
+                                                     unsigned int* block_counter) {
+  if (n_peers <= 0 || block_counter == nullptr) return;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(block_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *block_counter = 0;
+      __threadfence_system();
+      for (int r = 0; r < n_peers; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[r]), "r"(signal_value) : "memory");
+    }
+  }
+}
 
 __device__ __forceinline__ Action load_action(const void* actions, int act_dtype, long long i) {
   Action a;

@@ -6,6 +6,8 @@
 
 #include "common.cuh"
 
+struct carlb_gather;
+
 struct carlb_env {
   int kind = 0;
   int n = 0;
@@ -19,6 +21,7 @@ struct carlb_env {
   int n_peers = 0;
   float* peer_obs[CARLB_MAX_PEERS] = {};
   void* brax_sys = nullptr;  // BraxHandle: device copy of the per-handle Brax system table
+  carlb_gather* gather = nullptr;  // fused cross-GPU obs gather (gather.cu), or null
 };
 
 namespace carlb {
@@ -26,6 +29,10 @@ namespace carlb {
 extern std::atomic<long long> g_launches;
 void set_error(const char* fmt, ...);
 Segment make_segment(const carlb_env* env, int act_dtype);
+
+// gather.cu
+void gather_fill(carlb_gather* g, int* n_peers, float** peer_obs, unsigned int** peer_flags, unsigned int* signal_value,
+                 unsigned int** block_counter);
 
 // classic.cu
 int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st);

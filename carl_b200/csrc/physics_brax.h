@@ -118,6 +118,23 @@ CARLB_HD V3 eff_inv_idiag(const float* lt, const float* sys) {
   const float e = 1.0f - sys[H_INERTIA_SCALE];
   return v3(1.0f / powf(lt[L_IDIAG + 0], e), 1.0f / powf(lt[L_IDIAG + 1], e), 1.0f / powf(lt[L_IDIAG + 2], e));
 }
+// Loop-invariant per-link constants (hoisted out of the substep loop: powf/expf are ~100
+// instructions each and the spring step would otherwise evaluate a dozen of them per substep).
+struct LinkConst {
+  float inv_mass;   // 1 / mass^(1 - spring_mass_scale)
+  V3 inv_idiag;     // 1 / diag(I)^(1 - spring_inertia_scale)
+  float vel_decay;  // exp(vel_damping * dt)
+  float ang_decay;  // exp(ang_damping * dt)
+};
+CARLB_HD LinkConst make_link_const(const float* sys, const float* lt, float mass, float ang_damping) {
+  LinkConst c;
+  c.inv_mass = 1.0f / eff_mass(mass, sys);
+  c.inv_idiag = eff_inv_idiag(lt, sys);
+  c.vel_decay = expf(sys[H_VEL_DAMPING] * sys[H_DT]);
+  c.ang_decay = expf(ang_damping * sys[H_DT]);
+  return c;
+}
+
 CARLB_HD V3 apply_inv_inertia(V3 v, Q4 rot, const float* lt, V3 inv_idiag) {
   const Q4 r = qmul(rot, ld4(lt + L_IROT));
   V3 w = inv_rotate(v, r);
@@ -204,16 +221,15 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
 }
 
 // ---- semi-implicit velocity update (brax.spring.integrator.integrate_xdd) ---------------------
-CARLB_HD void integrate_xdd(LinkState& s, const Wrench& w, const float* sys, const float* lt, float mass,
-                            float gravity, float ang_damping) {
+CARLB_HD void integrate_xdd(LinkState& s, const Wrench& w, const float* sys, const float* lt, const LinkConst& lc,
+                            float gravity) {
   const float dt = sys[H_DT];
-  const float m = eff_mass(mass, sys);
-  const V3 acc = v3(0, 0, gravity) + w.f * (1.0f / m);
-  const V3 alpha = apply_inv_inertia(w.t, s.rot, lt, eff_inv_idiag(lt, sys));
+  const V3 acc = v3(0, 0, gravity) + w.f * lc.inv_mass;
+  const V3 alpha = apply_inv_inertia(w.t, s.rot, lt, lc.inv_idiag);
   s.vel = s.vel + acc * dt;
   s.ang = s.ang + alpha * dt;
-  s.vel = s.vel * expf(sys[H_VEL_DAMPING] * dt);
-  s.ang = s.ang * expf(ang_damping * dt);
+  s.vel = s.vel * lc.vel_decay;
+  s.ang = s.ang * lc.ang_decay;
 }
 
 // ---- ground contact of one candidate point (brax.spring.collisions._collide vs the plane z=0) --
@@ -223,8 +239,8 @@ struct ContactOut {
   float active;
 };
 
-CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const float* lt, const LinkState& s, float mass,
-                                    float friction, float elasticity) {
+CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const float* lt, const LinkState& s,
+                                    const LinkConst& lc, float friction, float elasticity) {
   ContactOut o;
   o.p = v3(0, 0, 0); o.t = v3(0, 0, 0); o.active = 0.0f;
   const float radius = pt[4];
@@ -238,9 +254,8 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
   const V3 rel_pos = cpos - s.pos;
   const V3 rel_vel = s.vel + cross(s.ang, rel_pos);
   const float normal_vel = dot(n, rel_vel);
-  const float inv_m = 1.0f / eff_mass(mass, sys);
-  const V3 inv_i = eff_inv_idiag(lt, sys);
-  const V3 temp1 = apply_inv_inertia(cross(rel_pos, n), s.rot, lt, inv_i);
+  const float inv_m = lc.inv_mass;
+  const V3 temp1 = apply_inv_inertia(cross(rel_pos, n), s.rot, lt, lc.inv_idiag);
   const float ang = dot(n, cross(temp1, rel_pos));
   const float dt = sys[H_DT];
   const float baumgarte_vel = sys[H_BAUMGARTE] * penetration / dt;
@@ -265,12 +280,11 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
 }
 
 // delta-velocity from the link's summed contact impulses, averaged over its active contacts
-CARLB_HD void integrate_xdv(LinkState& s, V3 p_sum, V3 t_sum, float n_active, const float* sys, const float* lt,
-                            float mass) {
+CARLB_HD void integrate_xdv(LinkState& s, V3 p_sum, V3 t_sum, float n_active, const float* lt, const LinkConst& lc) {
   if (!(n_active > 0.0f)) return;
   const float inv_n = 1.0f / n_active;
-  s.vel = s.vel + p_sum * (inv_n / eff_mass(mass, sys));
-  s.ang = s.ang + apply_inv_inertia(t_sum * inv_n, s.rot, lt, eff_inv_idiag(lt, sys));
+  s.vel = s.vel + p_sum * (inv_n * lc.inv_mass);
+  s.ang = s.ang + apply_inv_inertia(t_sum * inv_n, s.rot, lt, lc.inv_idiag);
 }
 
 // ---- pose integration (brax.spring.integrator.integrate) --------------------------------------

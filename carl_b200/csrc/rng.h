@@ -50,6 +50,34 @@ CARLB_HD void pcg64_advance1(Pcg64& g) {
   g.state_hi = hi;
 }
 
+// 128 x 128 -> low 128 bits
+CARLB_HD void mul128(uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint64_t& r_hi, uint64_t& r_lo) {
+  r_lo = a_lo * b_lo;
+  r_hi = mulhi64(a_lo, b_lo) + a_hi * b_lo + a_lo * b_hi;
+}
+
+// Jump ahead by k in {1, 2, 4} draws at once: state <- A_k * state + C_k * inc (mod 2^128), with
+// A_k = MULT^k and C_k = 1 + MULT + ... + MULT^(k-1). Used for gymnasium's own reset draws, which
+// CARL's reset consumes and discards (two 128-bit multiplies instead of k).
+template <int K>
+CARLB_HD void pcg64_skip(Pcg64& g) {
+  static_assert(K == 1 || K == 2 || K == 4, "supported skips");
+  if (K == 1) {
+    pcg64_advance1(g);
+    return;
+  }
+  const uint64_t a_hi = K == 2 ? 0x17bce35bdf69743cULL : 0xf4dd417327db7a9bULL;
+  const uint64_t a_lo = K == 2 ? 0x529ed9eb20e0ae99ULL : 0xd194dfbe42d45771ULL;
+  const uint64_t c_hi = K == 2 ? 0x2360ed051fc65da4ULL : 0x610e11a14b07e063ULL;
+  const uint64_t c_lo = K == 2 ? 0x4385df649fccf646ULL : 0x817fa187adefba1cULL;
+  uint64_t s_hi, s_lo, i_hi, i_lo;
+  mul128(g.state_hi, g.state_lo, a_hi, a_lo, s_hi, s_lo);
+  mul128(g.inc_hi, g.inc_lo, c_hi, c_lo, i_hi, i_lo);
+  const uint64_t lo = s_lo + i_lo;
+  g.state_hi = s_hi + i_hi + (lo < s_lo ? 1ULL : 0ULL);
+  g.state_lo = lo;
+}
+
 // numpy pcg64_next64: step, then XSL-RR output of the new state
 CARLB_HD uint64_t pcg64_next64(Pcg64& g) {
   pcg64_advance1(g);

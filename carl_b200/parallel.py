@@ -53,12 +53,23 @@ class ObsGather:
             raise ValueError(f"unknown gather mode {mode!r}")
 
     def gather(self, obs=None):
-        """NCCL path: collective on the current stream. Returns the ``[N_global, D]`` tensor."""
-        obs = self.env._obs if obs is None else obs
+        """Returns the ``[N_global, D]`` tensor of the latest observation-producing call.
+
+        nccl: collective on the current stream. fused: the rows were already stored into every
+        rank's buffer by the step/reset/rollout kernel itself; only a one-warp wait kernel is enqueued
+        (no NCCL call, no host sync)."""
         if self.mode == "fused":
-            # rows were already stored by the step kernel; only order the ranks
-            self.dist.barrier(group=self.group)
-            return self.gathered
+            import ctypes
+
+            import torch
+
+            from carl_b200 import _native
+
+            ptr = ctypes.c_void_p()
+            _native.check(self._lib.carlb_gather_wait(self._g, torch.cuda.current_stream(self.env.device).cuda_stream,
+                                                      ctypes.byref(ptr)))
+            return self._views[ptr.value]
+        obs = self.env._obs if obs is None else obs
         if self.equal:
             self.dist.all_gather_into_tensor(self.gathered, obs, group=self.group)
         else:
@@ -78,7 +89,70 @@ class ObsGather:
         return self.gathered
 
     def _setup_fused(self):
-        raise NotImplementedError("fused peer-store gather is enabled in carl_b200.fused_gather")
+        """Create this rank's symmetric buffer, exchange the CUDA IPC handles, map every peer's
+        buffer and attach the gather to the env handle (its kernels then store obs rows to all
+        ranks over NVLink and publish completion flags)."""
+        import ctypes
+
+        import torch
+
+        from carl_b200 import _native
+
+        env = self.env
+        self._lib = _native.load()
+        self._g = ctypes.c_void_p()
+        D = env._info.obs_dim
+        _native.check(self._lib.carlb_gather_create(env.device.index, env.rank, env.world_size, env.global_num_envs, D,
+                                                    ctypes.byref(self._g)))
+        handle = (ctypes.c_ubyte * 64)()
+        _native.check(self._lib.carlb_gather_export(self._g, handle))
+        mine = bytes(handle)
+        if env.world_size > 1:
+            handles = [None] * env.world_size
+            self.dist.all_gather_object(handles, mine, group=self.group)
+        else:
+            handles = [mine]
+        for r, h in enumerate(handles):
+            if r == env.rank:
+                continue
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _native.check(self._lib.carlb_gather_open(self._g, r, buf))
+        _native.check(self._lib.carlb_gather_attach(self._g, env._handle))
+        # tensor views of the two slots of the local buffer (CUDA array interface on raw pointers)
+        slot_floats = (env.global_num_envs * D + 63) // 64 * 64
+        torch.cuda.synchronize(env.device)
+        # slot addresses are only known through carlb_gather_wait; issue a probe after a dummy launch is
+        # not possible before any launch, so derive them from the first wait lazily
+        self._views = _SlotViews(env.device, env.global_num_envs, D, slot_floats)
+        if env.world_size > 1:
+            self.dist.barrier(group=self.group)
+
+    def close(self):
+        if self.mode == "fused" and getattr(self, "_g", None) is not None and self._g.value:
+            self._lib.carlb_gather_destroy(self._g)
+            import ctypes
+
+            self._g = ctypes.c_void_p()
+
+
+class _DevArray:
+    def __init__(self, ptr: int, shape: tuple):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class _SlotViews(dict):
+    """pointer -> torch view of a gathered slot (created on first use)."""
+
+    def __init__(self, device, n, d, slot_floats):
+        super().__init__()
+        self.device, self.n, self.d = device, n, d
+
+    def __missing__(self, ptr):
+        import torch
+
+        t = torch.as_tensor(_DevArray(ptr, (self.n, self.d)), device=self.device)
+        self[ptr] = t
+        return t
 
 
 def host_gather_reference(shards: list[np.ndarray]) -> np.ndarray:

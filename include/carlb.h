@@ -61,6 +61,7 @@ extern "C" {
  * Brax: brax AutoResetWrapper semantics -- state/obs replaced by the stored first state. */
 
 typedef struct carlb_env carlb_env_t;
+typedef struct carlb_gather carlb_gather_t;
 
 typedef struct carlb_env_info {
   int kind;
@@ -171,6 +172,22 @@ int carlb_brax_set_system(carlb_env_t* env, const float* table, int n_floats, in
  * generalized coordinates q[n][n_q], qd[n][n_qd] (DEVICE) instead of the noise draws of
  * `Ant.reset` etc. (the reference's JAX PRNG stream is not reproducible without JAX). */
 int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* q, const float* qd, void* stream);
+
+/* ---- fused cross-GPU observation gather (the path's one exchange step) ----------
+ * One symmetric buffer per rank, mapped into every other rank's process with CUDA IPC. Once a
+ * gather is attached, every observation-producing launch of the handle (reset / step / rollout)
+ * also stores each obs row into every rank's buffer over NVLink and publishes a completion flag;
+ * carlb_gather_wait enqueues a one-warp kernel that waits for all ranks' flags and returns the
+ * [n_global][obs_dim] gathered tensor of the latest launch. All ranks must issue the same sequence
+ * of observation-producing launches. Not capturable into CUDA graphs (slot / flag value change per
+ * launch). Replaces `VectorGymWrapper`'s batched obs return (carl/envs/brax/wrappers.py:136-146)
+ * for a batch sharded over GPUs. */
+int carlb_gather_create(int device, int rank, int world, int64_t n_global, int obs_dim, carlb_gather_t** out);
+int carlb_gather_export(carlb_gather_t* g, void* handle64 /* HOST, 64 bytes out */);
+int carlb_gather_open(carlb_gather_t* g, int peer_rank, const void* handle64 /* HOST, 64 bytes */);
+int carlb_gather_attach(carlb_gather_t* g, carlb_env_t* env);
+int carlb_gather_wait(carlb_gather_t* g, void* stream, float** gathered /* HOST out: DEVICE pointer */);
+int carlb_gather_destroy(carlb_gather_t* g);
 
 /* Counters of kernels launched through this library since load (bench `gpu_launches`). */
 int64_t carlb_launch_count(void);

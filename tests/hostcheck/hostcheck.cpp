@@ -63,7 +63,7 @@ static void step_all(int n, T* state, const T* params, const int* ai, const floa
     bool tr = max_steps > 0 && elapsed[i] >= max_steps;
     if (autoreset && (so.terminated || tr)) {
       if (final_obs) for (int k = 0; k < Tr::D; ++k) final_obs[(size_t)i * Tr::D + k] = o[k];
-      for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_next64(g);
+      pcg64_skip<Tr::GYM_DRAWS>(g);
       env_reset<KIND, T>(s, p, g, o);
       elapsed[i] = 0;
       sbt[i] = 0;
@@ -81,7 +81,7 @@ static void reset_all(int n, T* state, const T* params, uint64_t* rng, float* ob
     T p[Tr::P];
     for (int r = 0; r < Tr::P; ++r) p[r] = params[(size_t)r * n + i];
     Pcg64 g{rng[0 * n + i], rng[1 * n + i], rng[2 * n + i], rng[3 * n + i]};
-    for (int k = 0; k < Tr::GYM_DRAWS; ++k) pcg64_next64(g);
+    pcg64_skip<Tr::GYM_DRAWS>(g);
     float o[8];
     env_reset<KIND, T>(state + (size_t)i * Tr::S, p, g, o);
     for (int k = 0; k < Tr::D; ++k) obs[(size_t)i * Tr::D + k] = o[k];

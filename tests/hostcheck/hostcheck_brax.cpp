@@ -81,6 +81,8 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     obs_of(sys, st, ob, before);
     float act_sq = 0.0f;
     for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
+    LinkConst lcs[MAX_LINKS];
+    for (int l = 0; l < L; ++l) lcs[l] = make_link_const(sys, link_tab(sys, l), c[C_MASS0 + l], c[C_ANG_DAMPING]);
     for (int f = 0; f < NF; ++f) {
       Wrench w[MAX_LINKS], pw[MAX_LINKS];
       for (int l = 0; l < L; ++l) {
@@ -99,7 +101,7 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         for (int k = l + 1; k < L; ++k)
           if ((int)link_tab(sys, k)[L_PARENT] == l) { tot.f = tot.f + pw[k].f; tot.t = tot.t + pw[k].t; }
         nx[l] = st[l];
-        integrate_xdd(nx[l], tot, sys, link_tab(sys, l), c[C_MASS0 + l], c[C_GRAVITY], c[C_ANG_DAMPING]);
+        integrate_xdd(nx[l], tot, sys, link_tab(sys, l), lcs[l], c[C_GRAVITY]);
       }
       ContactOut co[MAX_POINTS];
       for (int p = 0; p < P; ++p) {
@@ -107,14 +109,14 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         const int l = (int)pt[0];
         const float fr = (c[C_FRICTION] < 0.0f || stock_contact) ? pt[5] : c[C_FRICTION];
         const float el = (c[C_ELASTICITY] < 0.0f || stock_contact) ? pt[6] : c[C_ELASTICITY];
-        co[p] = contact_resolve(sys, pt, link_tab(sys, l), nx[l], c[C_MASS0 + l], fr, el);
+        co[p] = contact_resolve(sys, pt, link_tab(sys, l), nx[l], lcs[l], fr, el);
       }
       for (int l = 0; l < L; ++l) {
         const float* lt = link_tab(sys, l);
         V3 ps = v3(0, 0, 0), ts = v3(0, 0, 0);
         float na = 0.0f;
         for (int k = (int)lt[L_FIRST_PT]; k < (int)lt[L_FIRST_PT] + (int)lt[L_N_PT]; ++k) { ps = ps + co[k].p; ts = ts + co[k].t; na += co[k].active; }
-        integrate_xdv(nx[l], ps, ts, na, sys, lt, c[C_MASS0 + l]);
+        integrate_xdv(nx[l], ps, ts, na, lt, lcs[l]);
         integrate_pose(nx[l], sys[H_DT]);
         st[l] = nx[l];
       }

@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== pytest -m gpu" 
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?"
 tail -15 gpurun_out/pytest_gpu.log
 echo "== smoke"
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/smoke.log
@@ -19,6 +19,9 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 echo "== ncu full: rollout kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 2 -c 2 -f -o gpurun_out/prof_rollout \
   python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_rollout.log 2>&1; echo "ncu rollout exit $?"
+echo "== ncu full: brax step kernel"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:brax_step_kernel -s 3 -c 2 -f -o gpurun_out/prof_brax \
+  python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_brax.log 2>&1; echo "ncu brax exit $?"
 echo "== ncu full: step kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 10 -c 2 -f -o gpurun_out/prof_step \
   python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1; echo "ncu step exit $?"
