@@ -71,6 +71,20 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(rep: str):
+    """DRAM bytes per launch of the dominant kernel from the newest committed ncu --set full
+    summary (profiles/<tag>_traffic.json, written by tools/summarize_ncu.py), or None."""
+    d = os.path.join(ROOT, "profiles")
+    try:
+        files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json"))
+        if not files:
+            return None, None
+        j = json.load(open(os.path.join(d, files[-1])))
+        return float(j[rep]["dram_bytes_per_launch"]), files[-1]
+    except Exception:
+        return None, None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -400,7 +414,8 @@ def run_gpu_arm(args):
         "roofline": {
             "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": None,
+            "peak_source": peak_src, "traffic": measured_traffic("prof_rollout")[0],
+            "traffic_source": f"profiles/{measured_traffic('prof_rollout')[1]} (ncu --set full, same command at --steps 200)",
             "algorithmic_bytes_per_launch": fused_bytes_per_launch,
             "bytes_per_env_step": TRAJ_BYTES + STEP_CONTRACT_BYTES / T,
             "kernel_ms_avg": k_avg_ms,

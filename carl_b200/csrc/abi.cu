@@ -269,14 +269,28 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
   rc = is_brax(env->kind) ? brax_step(env, env->bufs.act_staging, act_dtype, st)
                           : classic_step(env, env->bufs.act_staging, act_dtype, st);
   if (rc != CARLB_OK) return rc;
-  if (obs_host)
-    CARLB_CUDA_CHECK(cudaMemcpyAsync(obs_host, env->bufs.obs, n * info.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (reward_host)
-    CARLB_CUDA_CHECK(cudaMemcpyAsync(reward_host, env->bufs.reward, n * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (terminated_host)
-    CARLB_CUDA_CHECK(cudaMemcpyAsync(terminated_host, env->bufs.terminated, n, cudaMemcpyDeviceToHost, st));
-  if (truncated_host)
-    CARLB_CUDA_CHECK(cudaMemcpyAsync(truncated_host, env->bufs.truncated, n, cudaMemcpyDeviceToHost, st));
+  // One device->host copy when the caller laid obs | reward | terminated | truncated out back to
+  // back on both sides (the Python host layer does): 4 copies -> 1 (each costs ~8 us of latency).
+  const unsigned char* d0 = reinterpret_cast<const unsigned char*>(env->bufs.obs);
+  unsigned char* h0 = reinterpret_cast<unsigned char*>(obs_host);
+  const size_t ob = n * info.obs_dim * sizeof(float), rb = n * sizeof(float);
+  const bool packed = obs_host && reward_host && terminated_host && truncated_host &&
+                      reinterpret_cast<const unsigned char*>(env->bufs.reward) == d0 + ob &&
+                      env->bufs.terminated == d0 + ob + rb && env->bufs.truncated == d0 + ob + rb + n &&
+                      reinterpret_cast<unsigned char*>(reward_host) == h0 + ob && terminated_host == h0 + ob + rb &&
+                      truncated_host == h0 + ob + rb + n;
+  if (packed) {
+    CARLB_CUDA_CHECK(cudaMemcpyAsync(h0, d0, ob + rb + 2 * n, cudaMemcpyDeviceToHost, st));
+  } else {
+    if (obs_host)
+      CARLB_CUDA_CHECK(cudaMemcpyAsync(obs_host, env->bufs.obs, ob, cudaMemcpyDeviceToHost, st));
+    if (reward_host)
+      CARLB_CUDA_CHECK(cudaMemcpyAsync(reward_host, env->bufs.reward, rb, cudaMemcpyDeviceToHost, st));
+    if (terminated_host)
+      CARLB_CUDA_CHECK(cudaMemcpyAsync(terminated_host, env->bufs.terminated, n, cudaMemcpyDeviceToHost, st));
+    if (truncated_host)
+      CARLB_CUDA_CHECK(cudaMemcpyAsync(truncated_host, env->bufs.truncated, n, cudaMemcpyDeviceToHost, st));
+  }
   CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
   return CARLB_OK;
 }

@@ -335,10 +335,13 @@ class CARLEnv(abc.ABC):
         self._elapsed = z(n, dtype=torch.int32)
         self._sbt = z(n, dtype=torch.uint8)
         self._rng = z(4, n, dtype=torch.int64)
-        self._obs = z(n, info.obs_dim, dtype=torch.float32)
-        self._reward = z(n, dtype=torch.float32)
-        self._terminated = z(n, dtype=torch.uint8)
-        self._truncated = z(n, dtype=torch.uint8)
+        # obs | reward | terminated | truncated back to back: the host path moves them with ONE copy
+        ob, rb = n * info.obs_dim * 4, n * 4
+        self._out = z(ob + rb + 2 * n, dtype=torch.uint8)
+        self._obs = self._out[:ob].view(torch.float32).view(n, info.obs_dim)
+        self._reward = self._out[ob:ob + rb].view(torch.float32)
+        self._terminated = self._out[ob + rb:ob + rb + n]
+        self._truncated = self._out[ob + rb + n:ob + rb + 2 * n]
         self._final_obs = z(n, info.obs_dim, dtype=torch.float32)
         self._first_state = z(n, info.state_words, dtype=torch.float32) if is_brax else None
         self._first_obs = z(n, info.obs_dim, dtype=torch.float32) if is_brax else None
@@ -514,12 +517,15 @@ class CARLEnv(abc.ABC):
         if self._host_io is None:
             n, info = self.num_envs, self._info
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
+            ob, rb = n * info.obs_dim * 4, n * 4
+            out = pin(ob + rb + 2 * n, dtype=torch.uint8)  # same packing as the device side
             self._host_io = dict(
                 act=pin(n * max(1, info.act_dim), dtype=torch.int64),
-                obs=pin(n, info.obs_dim, dtype=torch.float32),
-                reward=pin(n, dtype=torch.float32),
-                term=pin(n, dtype=torch.uint8),
-                trunc=pin(n, dtype=torch.uint8),
+                out=out,
+                obs=out[:ob].view(torch.float32).view(n, info.obs_dim),
+                reward=out[ob:ob + rb].view(torch.float32),
+                term=out[ob + rb:ob + rb + n],
+                trunc=out[ob + rb + n:ob + rb + 2 * n],
             )
         return self._host_io
 

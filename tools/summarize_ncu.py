@@ -71,6 +71,19 @@ def full(tag, rep):
                     f.write(f"  {w:85s} {r[hdr.index(w)]:>18s} {units[hdr.index(w)]}\n")
             f.write("\n")
     print("wrote", rep)
+    # per-launch DRAM traffic of the captured kernel -> bench.py's roofline.traffic
+    import json
+    try:
+        rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        vals = [float(r[rd]) * unit[units[rd]] + float(r[wr]) * unit[units[wr]] for r in rows[2:]]
+        tp = os.path.join(PROF, f"{tag}_traffic.json")
+        d = json.load(open(tp)) if os.path.exists(tp) else {}
+        d[rep] = {"kernel": rows[2][hdr.index("Kernel Name")], "dram_bytes_per_launch": sum(vals) / len(vals),
+                  "launches_captured": len(vals)}
+        json.dump(d, open(tp, "w"), indent=1)
+    except Exception as e:  # pragma: no cover
+        print("traffic summary failed:", e)
 
 
 if __name__ == "__main__":
