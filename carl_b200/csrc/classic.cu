@@ -6,6 +6,7 @@
 // `CARLEnv.step` contract; the fused rollout keeps the state in registers across K steps and
 // streams the trajectory to HBM.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "engine.h"
 
@@ -186,16 +187,10 @@ __global__ void __launch_bounds__(kBlock) mixed_step_kernel(const __grid_constan
 
 // --------------------------------------------------------------------- fused rollout
 template <int KIND, typename T>
-__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
-                                                         uint64_t policy_seed, uint32_t step_base, const void* actions,
-                                                         const carlb_traj_t traj) {
+__device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
+                                             uint32_t step_base, const void* actions, const carlb_traj_t& traj) {
   typedef Traits<KIND> Tr;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = seg.n;
-  if (i >= n) {
-    peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
-    return;
-  }
   T s[Tr::S];
   StateIO<T, Tr::S>::load(seg.state, i, s);
   T p[Tr::P];
@@ -298,6 +293,16 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   }
   seg.elapsed[i] = el;
   if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
+}
+
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
+                                                         uint64_t policy_seed, uint32_t step_base, const void* actions,
+                                                         const carlb_traj_t traj) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < seg.n) rollout_body<KIND, T>(seg, i, n_steps, policy_seed, step_base, actions, traj);
+  // ONE call site reached by every thread of the CTA: the epilogue contains an aligned barrier,
+  // which must not be executed from divergent code (ragged tail warps)
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
@@ -341,8 +346,23 @@ int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
   return CARLB_OK;
 }
 
+// Programmatic dependent launch is OPT-IN (CARLB_PDL=1). Measured on B200 (profiles/README.md,
+// r01d A/B): inside a CUDA-graph replay of back-to-back 65 536-env step launches the programmatic
+// edges cost more than they hide (4.19 us vs 3.31 us per launch), so plain launches are the default.
+static bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CARLB_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 template <int KIND, typename T>
 static cudaError_t launch_step_pdl(const Segment& seg, const void* actions, int n, cudaStream_t st) {
+  if (!pdl_enabled()) {
+    step_kernel<KIND, T><<<grid_for(n), kBlock, 0, st>>>(seg, actions);
+    return cudaGetLastError();
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid_for(n));
   cfg.blockDim = dim3(kBlock);

@@ -16,6 +16,10 @@ from tests.util import sample_context_table
 from oracle.classic import FEATURES
 
 
+def say(rank, msg):
+    print(f"[rank {rank}] {msg}", flush=True)
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -25,13 +29,16 @@ def main():
     table = sample_context_table("cartpole", n, np.random.default_rng(0))
     ctxs = ContextTable(FEATURES["cartpole"], table)
     for mode in ("nccl", "fused"):
+        say(rank, f"mode {mode}: build")
         ref = CARLCartPole(contexts=ctxs, device=dev, autoreset=True)
         env = CARLCartPole(contexts=ctxs, device=dev, autoreset=True, shard=(rank, world))
         g = ObsGather(env, mode=mode)
         o_ref, _ = ref.reset(seed=0)
         env.reset(seed=0)
+        say(rank, f"mode {mode}: reset done, gathering")
         G = g.gather()
         assert torch.equal(G, o_ref["obs"]), f"{mode}: reset gather mismatch"
+        say(rank, f"mode {mode}: reset gather ok")
         gen = torch.Generator(device="cpu").manual_seed(1)
         for t in range(25):
             a = torch.randint(0, 2, (n,), generator=gen, dtype=torch.int32).to(dev)
@@ -40,16 +47,19 @@ def main():
             G = g.gather()
             assert torch.equal(G, o_ref["obs"]), f"{mode}: step {t} gather mismatch"
             assert torch.equal(r, r_ref[env.env_lo:env.env_hi])
+        say(rank, f"mode {mode}: steps ok")
         env.rollout(17, policy_seed=3)
         ref.rollout(17, policy_seed=3)
         G = g.gather()
         assert torch.equal(G, ref._obs), f"{mode}: rollout gather mismatch"
+        say(rank, f"mode {mode}: rollout ok")
         # masked reset: rows that are not reset must still reach the new slot
         mask_full = (np.arange(n) % 3 == 0)
         ref.reset(mask=mask_full)
         env.reset(mask=mask_full[env.env_lo:env.env_hi])
         G = g.gather()
         assert torch.equal(G, ref._obs), f"{mode}: masked reset gather mismatch"
+        say(rank, f"mode {mode}: masked reset ok")
         torch.cuda.synchronize()
         dist.barrier()
         if mode == "fused":
@@ -61,7 +71,9 @@ def main():
     gb = ObsGather(envb, mode="fused")
     o_ref, _ = refb.reset(seed=5)
     envb.reset(seed=5)
+    say(rank, "brax: reset done")
     assert torch.equal(gb.gather(), o_ref["obs"]), "brax reset gather mismatch"
+    say(rank, "brax: reset gather ok")
     for t in range(5):
         a = (torch.rand(nb, 8, generator=torch.Generator().manual_seed(t)) * 2 - 1).to(dev)
         o_ref, *_ = refb.step(a)

@@ -22,6 +22,6 @@ def test_two_rank_gather_equals_single_gpu():
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=int(os.environ.get('CARLB_MGPU_TIMEOUT', '300')), cwd=ROOT)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     assert p.stdout.count("MGPU_OK") == 2
