@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -41,7 +42,18 @@ Segment make_segment(const carlb_env* env, int act_dtype) {
   s.n_peers = env->n_peers;
   for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
   s.block_counter = nullptr;
+  s.host_obs = nullptr; s.host_reward = nullptr; s.host_terminated = nullptr; s.host_truncated = nullptr;
   return s;
+}
+
+// true when `p` is page-locked host memory the device can address directly (UVA)
+static bool is_mapped_host(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost && a.devicePointer != nullptr;
 }
 
 template <int KIND> static void fill_info(carlb_env_info_t* o) {
@@ -264,6 +276,19 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
   CARLB_CUDA_CHECK(cudaSetDevice(env->device));
   const size_t esz = act_dtype == CARLB_ACT_I64 ? 8 : (act_dtype == CARLB_ACT_U8 ? 1 : 4);
   const size_t n = (size_t)env->n;
+  // Zero-copy path (classic envs, all five host buffers page-locked): the kernel reads the actions
+  // from and writes the results to mapped host memory itself -- no staging copy, no four
+  // device->host copies, the PCIe traffic overlaps the compute; one stream sync ends the call.
+  static const bool zero_copy = [] { const char* e = getenv("CARLB_ZEROCOPY"); return !(e && e[0] == '0'); }();
+  if (zero_copy && is_classic(env->kind) && obs_host && reward_host && terminated_host && truncated_host &&
+      is_mapped_host(actions_host) && is_mapped_host(obs_host) && is_mapped_host(reward_host) &&
+      is_mapped_host(terminated_host) && is_mapped_host(truncated_host)) {
+    HostMirrors hm{obs_host, reward_host, terminated_host, truncated_host};
+    rc = classic_step(env, actions_host, act_dtype, st, &hm);
+    if (rc != CARLB_OK) return rc;
+    CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
+    return CARLB_OK;
+  }
   CARLB_CUDA_CHECK(cudaMemcpyAsync(env->bufs.act_staging, actions_host, n * esz * (size_t)info.act_dim,
                                    cudaMemcpyHostToDevice, st));
   rc = is_brax(env->kind) ? brax_step(env, env->bufs.act_staging, act_dtype, st)

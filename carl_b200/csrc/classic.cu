@@ -141,6 +141,12 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
   seg.truncated[i] = tr ? 1 : 0;
   seg.elapsed[i] = el;
   if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
+  if (seg.host_obs != nullptr) {  // zero-copy mirrors in mapped host memory
+    store_obs<Tr::D>(seg.host_obs, (size_t)i, o);
+    seg.host_reward[i] = so.reward;
+    seg.host_terminated[i] = so.terminated ? 1 : 0;
+    seg.host_truncated[i] = tr ? 1 : 0;
+  }
 }
 
 template <int KIND, typename T>
@@ -376,9 +382,13 @@ static cudaError_t launch_step_pdl(const Segment& seg, const void* actions, int 
   return cudaLaunchKernelEx(&cfg, step_kernel<KIND, T>, seg, actions);
 }
 
-int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st) {
+int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm) {
   Segment seg = make_segment(env, act_dtype);
   attach_gather(env, seg);
+  if (hm != nullptr) {
+    seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
+    seg.host_truncated = hm->truncated;
+  }
   cudaError_t le = cudaSuccess;
   CARLB_DISPATCH_KIND_T(env->kind, env->precision, (le = launch_step_pdl<K_, T_>(seg, actions, env->n, st)));
   g_launches++;

@@ -34,6 +34,13 @@ struct Segment {
   unsigned int* peer_flags[CARLB_MAX_PEERS];  // fused gather: my completion word in every rank's buffer
   unsigned int signal_value;                  // value published when this launch's rows are stored
   unsigned int* block_counter;                // local CTA arrival counter (last CTA publishes)
+  // zero-copy host mirrors (carlb_env_step_host with page-locked buffers): results are ALSO stored
+  // straight into mapped host memory by the kernel (posted PCIe writes overlap the compute) instead
+  // of four device->host copies after it; null otherwise
+  float* host_obs;
+  float* host_reward;
+  uint8_t* host_terminated;
+  uint8_t* host_truncated;
 };
 
 // Fused-gather epilogue: every thread of every CTA calls this at the end of an obs-producing

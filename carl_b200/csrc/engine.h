@@ -37,7 +37,10 @@ void gather_fill(carlb_gather* g, int* n_peers, float** peer_obs, unsigned int**
 // classic.cu
 int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st);
 int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st);
-int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st);
+struct HostMirrors {  // mapped (page-locked) host result buffers of one zero-copy step
+  float* obs; float* reward; uint8_t* terminated; uint8_t* truncated;
+};
+int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm = nullptr);
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
 int classic_mixed_step(carlb_env* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,
