@@ -49,9 +49,9 @@ struct Segment {
 __device__ __forceinline__ void peer_signal_epilogue(int n_peers, unsigned int* const* peer_flags, unsigned int signal_value,
                                                      unsigned int* block_counter) {
   if (n_peers <= 0 || block_counter == nullptr) return;
-  __threadfence_system();
-  __syncthreads();
+  __syncthreads();  // the CTA's peer stores happen-before thread 0's fence (cumulativity through the barrier)
   if (threadIdx.x == 0) {
+    __threadfence_system();
     const unsigned int prev = atomicAdd(block_counter, 1u);
     if (prev == gridDim.x - 1) {
       *block_counter = 0;

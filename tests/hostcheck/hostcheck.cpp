@@ -27,6 +27,20 @@ void hc_philox(const uint32_t c[4], const uint32_t k[2], uint32_t out[4]) {
   memcpy(out, r.v, sizeof(r.v));
 }
 
+// threshold predicate exactness: float fast path vs the double comparison it replaces
+int hc_above_below_exact(const float* xs, int n, double thr, int* n_checked) {
+  int bad = 0;
+  for (int i = 0; i < n; ++i) {
+    const float x = xs[i];
+    if (above(x, thr) != ((double)x > thr)) ++bad;
+    if (below(x, -thr) != ((double)x < -thr)) ++bad;
+    if (above(x, -thr) != ((double)x > -thr)) ++bad;
+    if (below(x, thr) != ((double)x < thr)) ++bad;
+  }
+  *n_checked = 4 * n;
+  return bad;
+}
+
 void hc_policy_action(int kind, uint64_t seed, uint64_t env_id, uint32_t step, int* ai, float* af) {
   Action a;
   PolicyStream ps = policy_stream(seed, env_id);

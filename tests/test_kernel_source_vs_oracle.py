@@ -149,3 +149,26 @@ def test_short_rollout_fp32(hc, kind):
         agree = te == t_ref
         alive &= agree & ~t_ref  # stop comparing an env after its episode ended
     assert alive.sum() > 0
+
+
+def test_float_threshold_predicates_are_exact(hc):
+    """CartPole's done predicate in fp32 mode uses float comparisons that must equal the
+    reference's float64 comparison for EVERY float (checked on the neighbourhoods of the thresholds
+    and on random floats): done masks stay bit-identical."""
+    import ctypes
+
+    rng = np.random.default_rng(0)
+    for thr in (2.4, 12 * 2 * np.pi / 360, 0.5, 1.0, 0.1, 3.0000001):
+        c = np.float32(thr)
+        near = [c]
+        for _ in range(50):
+            near.append(np.nextafter(near[-1], np.float32(np.inf), dtype=np.float32))
+        lo = c
+        for _ in range(50):
+            lo = np.nextafter(lo, np.float32(-np.inf), dtype=np.float32)
+            near.append(lo)
+        xs = np.concatenate([np.asarray(near, dtype=np.float32), -np.asarray(near, dtype=np.float32),
+                             rng.uniform(-4, 4, 5000).astype(np.float32)])
+        n_checked = ctypes.c_int()
+        bad = hc.lib.hc_above_below_exact(xs.ctypes.data_as(ctypes.c_void_p), len(xs), ctypes.c_double(thr), ctypes.byref(n_checked))
+        assert bad == 0 and n_checked.value == 4 * len(xs)
