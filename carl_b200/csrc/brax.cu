@@ -34,7 +34,7 @@ struct BraxSeg {
   int autoreset;
   int state_words;   // padded 13*L
   int obs_dim;
-  int n_ctx;         // 4 + L
+  int n_ctx;         // 5 + L
   int act_dim;
   long long global_offset;
   uint64_t seed;
@@ -145,7 +145,7 @@ struct LaneCtx {
   int pt_link;
   float mass;        // my link's (context) mass
   float pt_mass;     // mass of my contact point's link
-  float gravity, friction_ctx, elasticity_ctx, ang_damping;
+  float gravity, friction_ctx, elasticity_ctx, ang_damping, stiffness_scale;
   float pt_friction, pt_elasticity;
   LinkConst lc;     // loop-invariant constants of my link
   LinkConst pt_lc;  // ... and of my contact point's link
@@ -175,6 +175,7 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const float* 
   c.friction_ctx = __shfl_sync(kFull, cv, C_FRICTION);
   c.elasticity_ctx = __shfl_sync(kFull, cv, C_ELASTICITY);
   c.ang_damping = __shfl_sync(kFull, cv, C_ANG_DAMPING);
+  c.stiffness_scale = __shfl_sync(kFull, cv, C_STIFFNESS_SCALE);
   c.mass = __shfl_sync(kFull, cv, C_MASS0 + l);
   c.pt_mass = __shfl_sync(kFull, cv, C_MASS0 + c.pt_link);
   // friction / elasticity: a negative context value means "keep the stock per-geom value"
@@ -199,7 +200,7 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
     if (c.is_link && c.type != TYPE_FREE) {
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, tau);
+      const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale);
       wr = jo.child;
       float* pw = w.pw + lane * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
@@ -547,8 +548,8 @@ int brax_query(int kind, carlb_env_info_t* o) {
   o->act_dim = A;
   o->act_discrete = 0;
   o->n_actions = 0;
-  o->n_param_rows = 4 + L;
-  o->n_step_rows = 4 + L;
+  o->n_param_rows = 5 + L;
+  o->n_step_rows = 5 + L;
   o->default_max_steps = 1000;  // brax.envs.create(episode_length=1000)
   o->gym_reset_draws = 0;
   o->act_low = -1.0f;

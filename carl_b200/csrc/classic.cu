@@ -192,7 +192,10 @@ __global__ void __launch_bounds__(kBlock) mixed_step_kernel(const __grid_constan
 }
 
 // --------------------------------------------------------------------- fused rollout
-template <int KIND, typename T>
+// REC = true: the common fast path -- in-kernel policy, all four trajectory sinks present: no
+// per-iteration null checks, one running element offset for all four streams. REC = false: generic
+// (optional sinks, optional given actions).
+template <int KIND, typename T, bool REC>
 __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
                                              uint32_t step_base, const void* actions, const carlb_traj_t& traj) {
   typedef Traits<KIND> Tr;
@@ -220,7 +223,8 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   float* t_rew = traj.reward != nullptr ? traj.reward + i : nullptr;
   uint8_t* t_done = traj.done != nullptr ? traj.done + i : nullptr;
   const size_t esz = seg.act_dtype == CARLB_ACT_I64 ? 8 : (seg.act_dtype == CARLB_ACT_U8 ? 1 : 4);
-  const unsigned char* a_in = actions != nullptr ? static_cast<const unsigned char*>(actions) + (size_t)i * esz : nullptr;
+  const unsigned char* a_in = (!REC && actions != nullptr) ? static_cast<const unsigned char*>(actions) + (size_t)i * esz : nullptr;
+  size_t off = (size_t)i;  // REC: element offset of row (t, i) in the [K][n] trajectory streams
   // Batched pre-generation of the next reset state. A reset costs ~300 integer instructions (two
   // 128-bit jump-ahead multiplies + S PCG64 draws); under a random policy ~5% of the envs of a warp
   // reset each step, i.e. ~80% of the warp-iterations would execute that divergent path for one or
@@ -244,8 +248,9 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   for (int k = 0; k < Tr::D; ++k) no[k] = 0.0f;
 #pragma unroll 1
   for (int t = 0; t < n_steps; ++t) {
-    const Action a = (a_in != nullptr) ? load_action(a_in, seg.act_dtype, 0)
-                                       : policy_action<KIND>(ps, step_base + (uint32_t)t);
+    Action a;
+    if (REC) a = policy_action<KIND>(ps, step_base + (uint32_t)t);
+    else a = (a_in != nullptr) ? load_action(a_in, seg.act_dtype, 0) : policy_action<KIND>(ps, step_base + (uint32_t)t);
     T noise = (T)0;
     if (KIND == KIND_ACROBOT) {
       if (p[AC_NOISE] > (T)0) noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
@@ -276,14 +281,23 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
         have_next = true;
       }
     }
-    if (t_obs != nullptr) { store_obs<Tr::D>(t_obs, 0, o); t_obs += (size_t)n * Tr::D; }
-    if (traj.actions != nullptr) {
-      if (Tr::DISCRETE) { *t_act_i = a.i; t_act_i += n; }
-      else { *t_act_f = a.f; t_act_f += n; }
+    if (REC) {
+      store_obs<Tr::D>(traj.obs, off, o);
+      if (Tr::DISCRETE) static_cast<int32_t*>(traj.actions)[off] = a.i;
+      else static_cast<float*>(traj.actions)[off] = a.f;
+      traj.reward[off] = so.reward;
+      traj.done[off] = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0));
+      off += (size_t)n;
+    } else {
+      if (t_obs != nullptr) { store_obs<Tr::D>(t_obs, 0, o); t_obs += (size_t)n * Tr::D; }
+      if (traj.actions != nullptr) {
+        if (Tr::DISCRETE) { *t_act_i = a.i; t_act_i += n; }
+        else { *t_act_f = a.f; t_act_f += n; }
+      }
+      if (t_rew != nullptr) { *t_rew = so.reward; t_rew += n; }
+      if (t_done != nullptr) { *t_done = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0)); t_done += n; }
+      if (a_in != nullptr) a_in += (size_t)n * esz;
     }
-    if (t_rew != nullptr) { *t_rew = so.reward; t_rew += n; }
-    if (t_done != nullptr) { *t_done = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0)); t_done += n; }
-    if (a_in != nullptr) a_in += (size_t)n * esz;
   }
   if (have_next) {  // roll back the reset that was pre-generated but never used
     g.state_hi = sv_hi; g.state_lo = sv_lo;
@@ -301,12 +315,12 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
 }
 
-template <int KIND, typename T>
+template <int KIND, typename T, bool REC>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
                                                          uint64_t policy_seed, uint32_t step_base, const void* actions,
                                                          const carlb_traj_t traj) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) rollout_body<KIND, T>(seg, i, n_steps, policy_seed, step_base, actions, traj);
+  if (i < seg.n) rollout_body<KIND, T, REC>(seg, i, n_steps, policy_seed, step_base, actions, traj);
   // ONE call site reached by every thread of the CTA: the epilogue contains an aligned barrier,
   // which must not be executed from divergent code (ragged tail warps)
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
@@ -407,9 +421,16 @@ int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uin
   // 148 SMs than 128-thread blocks for a long-running per-thread loop)
   constexpr int kRolloutBlock = 64;
   const int grid = (env->n + kRolloutBlock - 1) / kRolloutBlock;
-  CARLB_DISPATCH_KIND_T(env->kind, env->precision,
-                        (rollout_kernel<K_, T_><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
-                                                                                actions, tj)));
+  const bool rec = actions == nullptr && tj.obs != nullptr && tj.actions != nullptr && tj.reward != nullptr && tj.done != nullptr;
+  if (rec) {
+    CARLB_DISPATCH_KIND_T(env->kind, env->precision,
+                          (rollout_kernel<K_, T_, true><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
+                                                                                        actions, tj)));
+  } else {
+    CARLB_DISPATCH_KIND_T(env->kind, env->precision,
+                          (rollout_kernel<K_, T_, false><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
+                                                                                         actions, tj)));
+  }
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;

@@ -50,8 +50,10 @@ enum LinkSlot {
 };
 enum LinkType { TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_PLANAR = 3 };
 enum EnvId { ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2 };
-// per-env context rows: gravity, friction, elasticity, ang_damping, then one mass per link
-enum CtxRow { C_GRAVITY = 0, C_FRICTION, C_ELASTICITY, C_ANG_DAMPING, C_MASS0 };
+// per-env context rows: gravity, friction, elasticity, ang_damping, joint-stiffness scale (the
+// legacy `joint_stiffness` feature of CARL's docs mapped onto the spring constraint stiffness,
+// 1 = stock), then one mass per link
+enum CtxRow { C_GRAVITY = 0, C_FRICTION, C_ELASTICITY, C_ANG_DAMPING, C_STIFFNESS_SCALE, C_MASS0 };
 constexpr int LINK_WORDS = 13;  // pos3 rot4 vel3 ang3
 
 // ---- small vector algebra -------------------------------------------------------------------
@@ -155,7 +157,7 @@ struct JointOut {
 
 // child `c` (table row lt), parent state `p` (ignored when world_parent), parent row plt
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
-                                const float* plt, const LinkState& p, float tau) {
+                                const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f) {
   JointOut o;
   const int type = (int)lt[L_TYPE];
   const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
@@ -181,7 +183,8 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
   const Q4 jrot = qmul(qconj(ap_rot), ac_rot);
   const V3 jvel = inv_rotate(vc - vp, ap_rot);
   const V3 jang = inv_rotate(c.ang - wp, ap_rot);
-  const float k = sys[H_STIFFNESS], cv = sys[H_VEL_DAMPING_C], kl = sys[H_LIMIT_STIFFNESS], ca = sys[H_ANG_DAMPING_C];
+  const float k = sys[H_STIFFNESS] * stiffness_scale, cv = sys[H_VEL_DAMPING_C], kl = sys[H_LIMIT_STIFFNESS],
+              ca = sys[H_ANG_DAMPING_C];
   const V3 ex = v3(1, 0, 0);
   // hinge angle about the joint x axis
   const V3 yc = rotate(v3(0, 1, 0), jrot);

@@ -67,6 +67,12 @@ class CARLBraxEnv(CARLEnv):
     env_name: str
     backend: str = "spring"
     link_names: list[str] = []
+    # `torso_mass` and `joint_stiffness` exist only in the reference's
+    # stale v0 docs (docs/source/environments/data/context_definitions/CARLAnt.csv) but are what
+    # BASELINE.json's configs name. `torso_mass` is an alias of `mass_torso`; `joint_stiffness` is an
+    # extension: a per-env scale (1 = stock) of the spring backend's joint constraint stiffness.
+    feature_aliases = {"torso_mass": "mass_torso"}
+    extension_features = {"joint_stiffness": 1.0}
 
     def __init__(self, env=None, batch_size: int | None = None, contexts=None, obs_context_features=None,
                  obs_context_as_dict: bool = True, context_selector=None, context_selector_kwargs=None,
@@ -81,6 +87,11 @@ class CARLBraxEnv(CARLEnv):
 
         self._sysd = bs.build_system(bs.MODELS[self.env_name](), brax_tunables) if brax_tunables else bs.SYSTEMS[self.env_name]
         self.link_names = list(self._sysd["link_names"])
+        from carl_b200.envs import brax_goals
+
+        # carl_brax_env.py:195-223: goal wrapper only when the context set varies the target
+        self._goal_active = brax_goals.goal_wrapper_active(contexts if isinstance(contexts, dict) else None)
+        self._goal_state = None
         super().__init__(env=env, contexts=contexts, obs_context_features=obs_context_features,
                          obs_context_as_dict=obs_context_as_dict, context_selector=context_selector,
                          context_selector_kwargs=context_selector_kwargs, **kwargs)
@@ -100,6 +111,69 @@ class CARLBraxEnv(CARLEnv):
         self._sys_table_host = t
         _native.check(self._lib.carlb_brax_set_system(
             self._handle, t.ctypes.data_as(ctypes.c_void_p), int(t.size), 1 if self.context_mode == "reference" else 0))
+
+    # ------------------------------------------------------------------ goal wrappers
+    def _goal_reset(self, device_like):
+        """``BraxWalkerGoalWrapper.reset`` (brax_walker_goal_wrapper.py:111-122), batched."""
+        import torch
+
+        from carl_b200.envs import brax_goals
+
+        ids = self._context_ids
+        names = self._feature_names
+        vals = self._table.values[ids]
+        goal = brax_goals.goal_positions(vals[:, names.index("target_direction")], vals[:, names.index("target_distance")])
+        radius = vals[:, names.index("target_radius")]
+        self._goal_state = dict(
+            position=torch.zeros(self.num_envs, 2, dtype=torch.float64, device=self.device),
+            goal=torch.from_numpy(goal).to(self.device),
+            radius=torch.from_numpy(np.ascontiguousarray(radius)).to(self.device),
+            dt=brax_goals.MJCF_TIMESTEP[self.env_name],
+            idx=brax_goals.STATE_INDICES[self.env_name],
+        )
+        self._goal_strings = None
+
+    def _goal_strings_list(self):
+        from carl_b200.envs import brax_goals
+
+        if self._goal_strings is None:
+            ctxs = self.contexts
+            keys = self._table.keys
+            self._goal_strings = [brax_goals.goal_description(ctxs[keys[int(i)]]) for i in self._context_ids]
+        return self._goal_strings
+
+    def reset(self, *, seed=None, options=None, mask=None):
+        state, info = super().reset(seed=seed, options=options, mask=mask)
+        if self._goal_active:
+            self._goal_reset(state["obs"])
+            info["success"] = np.zeros(self.num_envs, dtype=np.int64)
+            if self.use_language_goals:
+                state = {"obs": {"obs": state["obs"], "goal": self._goal_strings_list()}, "context": state["context"]}
+        return state, info
+
+    def step(self, action):
+        import torch
+
+        state, reward, te, tr, info = super().step(action)
+        if not self._goal_active:
+            return state, reward, te, tr, info
+        from carl_b200.envs import brax_goals
+
+        g = self._goal_state
+        host = isinstance(state["obs"], np.ndarray)
+        obs_t = self._obs  # device copy of the same observation
+        vel = obs_t[:, g["idx"]].to(torch.float64)
+        g["position"], r, reached = brax_goals.goal_step(g["position"], g["goal"], g["radius"], vel, g["dt"])
+        te_t = self._terminated.view(torch.bool) | reached
+        info["success"] = reached.to(torch.int64)
+        if host:
+            reward, te = r.cpu().numpy(), te_t.cpu().numpy()
+            info["success"] = info["success"].cpu().numpy()
+        else:
+            reward, te = r, te_t
+        if self.use_language_goals:
+            state = {"obs": {"obs": state["obs"], "goal": self._goal_strings_list()}, "context": state["context"]}
+        return state, reward, te, tr, info
 
     def reset_from_q(self, q, qd, mask=None):
         """Parity-mode reset: ``pipeline_init(q, qd)`` from caller-supplied generalized coordinates
@@ -140,7 +214,7 @@ class CARLBraxEnv(CARLEnv):
     def kernel_params(cls, table, names, context_mode="reference"):
         """Batched ``CARLBraxEnv._update_context`` (``carl_brax_env.py:255-292``).
 
-        rows: gravity, friction, elasticity, ang_damping, mass_<link> for every link.
+        rows: gravity, friction, elasticity, ang_damping, joint-stiffness scale, mass_<link> per link.
         ``context_mode="reference"``: the reference assigns the modified ``sys`` to the gym shell,
         whose jitted step never reads it -- the physics sees the *stock* system
         (MJCF gravity/friction/masses) whatever the context says. ``"applied"``: the intended
@@ -149,24 +223,26 @@ class CARLBraxEnv(CARLEnv):
 
         sysd = bs.SYSTEMS[cls.env_name]
         m = table.shape[0]
-        rows = np.empty((m, 4 + len(sysd["link_names"])), dtype=np.float64)
+        rows = np.empty((m, 5 + len(sysd["link_names"])), dtype=np.float64)
         if context_mode == "reference":
             rows[:, 0] = sysd["stock_gravity"]
             rows[:, 1] = sysd["stock_friction"]
             rows[:, 2] = sysd["stock_elasticity"]
             rows[:, 3] = sysd["stock_ang_damping"]
-            rows[:, 4:] = np.asarray(sysd["stock_masses"])[None, :]
+            rows[:, 4] = 1.0
+            rows[:, 5:] = np.asarray(sysd["stock_masses"])[None, :]
             return rows
         col = lambda k: table[:, names.index(k)]
-        check_context({n: 0 for n in names}, REGISTERED_CFS)
+        check_context({n: 0 for n in names if n not in cls.extension_features}, REGISTERED_CFS)
         rows[:, 0] = col("gravity")
         rows[:, 1] = col("friction")
         rows[:, 2] = col("elasticity")
         # "viscosity" in context overwrites ang_damping after "ang_damping" was applied (:276-279)
         rows[:, 3] = col("viscosity") if "viscosity" in names else col("ang_damping")
+        rows[:, 4] = col("joint_stiffness") if "joint_stiffness" in names else 1.0
         for j, ln in enumerate(sysd["link_names"]):
             key = f"mass_{ln}"
-            rows[:, 4 + j] = col(key) if key in names else sysd["stock_masses"][j]
+            rows[:, 5 + j] = col(key) if key in names else sysd["stock_masses"][j]
         return rows
 
 

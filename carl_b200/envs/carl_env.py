@@ -83,6 +83,11 @@ class CARLEnv(abc.ABC):
 
     kind: str  # libcarlb env kind name (see _native.KIND)
     metadata: dict = {"render_modes": []}
+    # Legacy names of CARL's v0 docs (docs/source/environments/data/context_definitions/*.csv) that
+    # the reference's code no longer has: aliases are renamed on entry, extension
+    # features are accepted in a context (with a default) without being part of the context space.
+    feature_aliases: dict = {}
+    extension_features: dict = {}
 
     def __init__(
         self,
@@ -133,7 +138,8 @@ class CARLEnv(abc.ABC):
         self.contexts = contexts  # setter fills defaults and builds the dense table
         self.context: Context | None = None
         if obs_context_features is None:
-            obs_context_features = list(self._feature_names)
+            # the reference takes the keys of the first (default-filled) context (carl_env.py:86-88)
+            obs_context_features = [n for n in self._feature_names if n not in self.extension_features]
         self.obs_context_features = obs_context_features
 
         # Context selector (carl_env.py:90-108)
@@ -206,25 +212,36 @@ class CARLEnv(abc.ABC):
     def contexts(self, contexts: Contexts | ContextTable) -> None:
         """``carl_env.py:122-137``: every context is filled with the default values."""
         context_space = self.get_context_space()
-        defaults = context_space.get_default_context()
+        space_defaults = context_space.get_default_context()
+        defaults = dict(space_defaults)
+        defaults.update(self.extension_features)
         names = list(defaults.keys())
         self._feature_names = names
+        alias = self.feature_aliases
         if isinstance(contexts, ContextTable):
-            unknown = [n for n in contexts.names if n not in defaults]
+            cnames = [alias.get(n, n) for n in contexts.names]
+            unknown = [n for n in cnames if n not in defaults]
             if unknown:
                 raise ValueError(f"Unknown context features {unknown}")
             vals = np.empty((len(contexts), len(names)), dtype=np.float64)
             for j, n in enumerate(names):
-                vals[:, j] = contexts.values[:, contexts.names.index(n)] if n in contexts.names else float(defaults[n])
+                vals[:, j] = contexts.values[:, cnames.index(n)] if n in cnames else float(defaults[n])
             self._table = ContextTable(names, vals, contexts.keys)
             self._contexts_dict = None
         else:
-            filled = {k: context_space.insert_defaults(v) for k, v in contexts.items()}
+            renamed = {k: {alias.get(n, n): v for n, v in c.items()} for k, c in contexts.items()}
+            filled = {}
+            for k, c in renamed.items():
+                f = context_space.insert_defaults({n: v for n, v in c.items() if n in space_defaults or n not in defaults})
+                for n, d in self.extension_features.items():
+                    if n in c:
+                        f[n] = c[n]
+                filled[k] = f
             for k, c in filled.items():
                 unknown = [n for n in c if n not in defaults]
                 if unknown:
                     raise ValueError(f"Unknown context features {unknown} in context {k!r}")
-            vals = np.array([[float(c[n]) for n in names] for c in filled.values()], dtype=np.float64)
+            vals = np.array([[float(c.get(n, defaults[n])) for n in names] for c in filled.values()], dtype=np.float64)
             self._table = ContextTable(names, vals.reshape(len(filled), len(names)), list(filled.keys()))
             self._contexts_dict = filled
         self._params_table = None  # rebuilt lazily by _update_context

@@ -195,7 +195,7 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
     if (type == T_FREE) continue;
     jframe_t j;
     joint_frame(sys, rows, l, &j);
-    const real k = sys[hK], cv = sys[hCV], kl = sys[hKL], ca = sys[hCA];
+    const real k = sys[hK] * ctx[4], cv = sys[hCV], kl = sys[hKL], ca = sys[hCA];
     f3 ex = {1, 0, 0}, fv, fa, axc;
     rot3(ex, j.jrot, axc);
     cross3(axc, ex, fa);
@@ -235,7 +235,7 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
   for (int l = 0; l < L; ++l) {
     const real *lt = sys + OFF_L + LSTR * l;
     real *s = rows + 13 * l;
-    real m = eff_mass(ctx[4 + l], sys);
+    real m = eff_mass(ctx[5 + l], sys);
     f3 alpha;
     apply_inv_inertia(T[l], s + 3, lt, sys, alpha);
     real inv_m = 1.0f / m;
@@ -269,7 +269,7 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
     cross3(s + 10, rel, tmp);
     for (int q = 0; q < 3; ++q) rv[q] = s[7 + q] + tmp[q];
     real nv = dot3(n, rv);
-    real inv_m = 1.0f / eff_mass(ctx[4 + l], sys);
+    real inv_m = 1.0f / eff_mass(ctx[5 + l], sys);
     f3 rxn, t1, t2;
     cross3(rel, n, rxn);
     apply_inv_inertia(rxn, s + 3, lt, sys, t1);
@@ -299,7 +299,7 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
     real *s = rows + 13 * l;
     if (na[l] > 0.0f) {
       real inv_n = 1.0f / na[l];
-      real sc = inv_n / eff_mass(ctx[4 + l], sys);
+      real sc = inv_n / eff_mass(ctx[5 + l], sys);
       f3 tt = {ts[l][0] * inv_n, ts[l][1] * inv_n, ts[l][2] * inv_n}, dw;
       apply_inv_inertia(tt, s + 3, lt, sys, dw);
       for (int q = 0; q < 3; ++q) { s[7 + q] += ps[l][q] * sc; s[10 + q] += dw[q]; }
@@ -436,7 +436,8 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
 }
 
 /* One env-step of n envs: actuator torques, n_frames substeps, env layer, EpisodeWrapper,
- * AutoResetWrapper (autoreset != 0). ctx rows: gravity, friction, elasticity, ang_damping, masses. */
+ * AutoResetWrapper (autoreset != 0). ctx rows: gravity, friction, elasticity, ang_damping,
+ * joint-stiffness scale (legacy `joint_stiffness` extension, 1 = stock), masses. */
 void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_words, const float *ctx, int n_ctx,
                       const float *actions, int *elapsed, int max_steps, int autoreset, const real *first_state,
                       const float *first_obs, float *obs, int obs_dim, float *reward, unsigned char *done_out,
@@ -450,7 +451,7 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
 #endif
   for (int e = 0; e < n; ++e) {
     real *rows = state + (size_t)e * state_words;
-    real c[4 + MAXL], act[MAXL];
+    real c[5 + MAXL], act[MAXL];
     for (int i = 0; i < n_ctx; ++i) c[i] = ctx[(size_t)e * n_ctx + i];
     for (int i = 0; i < A; ++i) act[i] = actions[(size_t)e * A + i];
     real tau[MAXL];

@@ -11,19 +11,21 @@ from carl_b200.envs import brax_system as bs
 def random_ctx(sysd, n, rng, applied=True):
     """Per-env kernel context rows: gravity, friction, elasticity, ang_damping, link masses."""
     L = sysd["n_links"]
-    ctx = np.zeros((n, 4 + L), dtype=np.float32)
+    ctx = np.zeros((n, 5 + L), dtype=np.float32)
     if applied:
         ctx[:, 0] = rng.uniform(-15, -5, n)
         ctx[:, 1] = rng.uniform(0.5, 1.5, n)
         ctx[:, 2] = rng.uniform(0.0, 0.3, n)
         ctx[:, 3] = rng.uniform(-0.1, 0.0, n)
-        ctx[:, 4:] = np.asarray(sysd["stock_masses"])[None] * rng.uniform(0.5, 2.0, (n, L))
+        ctx[:, 4] = rng.uniform(0.5, 1.5, n)  # joint-stiffness scale
+        ctx[:, 5:] = np.asarray(sysd["stock_masses"])[None] * rng.uniform(0.5, 2.0, (n, L))
     else:
         ctx[:, 0] = sysd["stock_gravity"]
         ctx[:, 1] = -1.0
         ctx[:, 2] = -1.0
         ctx[:, 3] = sysd["stock_ang_damping"]
-        ctx[:, 4:] = np.asarray(sysd["stock_masses"])[None]
+        ctx[:, 4] = 1.0
+        ctx[:, 5:] = np.asarray(sysd["stock_masses"])[None]
     return ctx
 
 

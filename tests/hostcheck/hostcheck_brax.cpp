@@ -92,7 +92,7 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         const int parent = (int)lt[L_PARENT], ai = (int)lt[L_ACT];
         float tau = 0.0f;
         if (ai >= 0) tau = lt[L_GEAR] * fminf(fmaxf(act[ai], lt[L_CTRL_LO]), lt[L_CTRL_HI]);
-        const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], tau);
+        const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], tau, c[C_STIFFNESS_SCALE]);
         w[l] = jo.child; pw[l] = jo.parent;
       }
       LinkState nx[MAX_LINKS];

@@ -127,3 +127,17 @@ def test_gather_world_size_2_gloo(tmp_path, n):
         out, _ = p.communicate(timeout=180)
         assert p.returncode == 0, out.decode()
     assert np.array_equal(host_gather_reference([np.ones((2, 3)), np.zeros((1, 3))]).shape, (3, 3))
+
+
+def test_legacy_aliases_and_extension_features():
+    """BASELINE's `torso_mass` / `joint_stiffness` (stale-docs names) map onto
+    `mass_torso` and a per-env joint-constraint-stiffness scale."""
+    names = list(CARLBraxAnt.get_context_space().get_default_context()) + ["joint_stiffness"]
+    d = dict(CARLBraxAnt.get_context_space().get_default_context(), joint_stiffness=1.0)
+    t = np.array([[float(d[n]) for n in names]])
+    t[0, names.index("joint_stiffness")] = 1.7
+    rows = CARLBraxAnt.kernel_params(t, names, "applied")
+    assert rows.shape[1] == 5 + 9 and rows[0, 4] == 1.7
+    assert CARLBraxAnt.kernel_params(t, names, "reference")[0, 4] == 1.0
+    assert CARLBraxAnt.feature_aliases["torso_mass"] == "mass_torso"
+    assert "joint_stiffness" not in CARLBraxAnt.get_context_features()  # the context space stays the reference's

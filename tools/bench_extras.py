@@ -1,0 +1,69 @@
+"""Secondary BASELINE configs on one GPU (numbers for DESIGN.md / profiles; not the headline line):
+config 3 -- CARLPendulum + CARLAcrobot, 32 768 contexts each, ONE mixed launch per step;
+config 5 (single-GPU share) -- CARLBraxHalfcheetah + CARLBraxHopper, 8 192 contexts each."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from carl_b200.context import ContextSampler, UniformFloatContextFeature
+from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLPendulum, ContextTable, MixedBatch)
+
+
+def table(cls, feats, n):
+    names = list(cls.get_context_space().get_default_context().keys())
+    s = ContextSampler([UniformFloatContextFeature(k, lo, hi) for k, (lo, hi) in feats.items()],
+                       context_space=cls.get_context_space(), seed=0)
+    return ContextTable(names, s.sample_context_table(n, names))
+
+
+def timed(fn, iters, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    out = {}
+    n = 32768
+    pen = CARLPendulum(contexts=table(CARLPendulum, {"g": (5, 15), "m": (0.5, 2), "l": (0.5, 2)}, n), autoreset=True)
+    acr = CARLAcrobot(contexts=table(CARLAcrobot, {"LINK_MASS_1": (0.5, 2), "LINK_MASS_2": (0.5, 2), "LINK_LENGTH_1": (0.5, 2)}, n),
+                      autoreset=True)
+    mixed = MixedBatch([pen, acr])
+    mixed.reset(seed=0)
+    ap = torch.rand(n, device="cuda") * 4 - 2
+    aa = torch.randint(0, 3, (n,), dtype=torch.int32, device="cuda")
+    ms = timed(lambda: mixed.step([ap, aa]), 500)
+    out["config3_mixed_step"] = {"workload": "CARLPendulum 32768 + CARLAcrobot 32768, one mixed launch per step",
+                                 "us_per_step": ms * 1e3, "env_steps_per_s": 2 * n / (ms * 1e-3),
+                                 "algorithmic_GBps": (62 + 110) * n / (ms * 1e-3) / 1e9}
+    for env, name in ((pen, "pendulum"), (acr, "acrobot")):
+        T = 100
+        ms = timed(lambda: env.rollout(T, policy_seed=1, record=False), 10, warm=2)
+        out[f"config3_{name}_fused"] = {"env_steps_per_s": n * T / (ms * 1e-3), "ms_per_100_steps": ms}
+    nb = 8192
+    for cls, feats, name in ((CARLBraxHalfcheetah, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "halfcheetah"),
+                             (CARLBraxHopper, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "hopper")):
+        env = cls(contexts=table(cls, feats, nb), context_mode="applied")
+        env.reset(seed=0)
+        T = 20
+        ms = timed(lambda: env.rollout(T, policy_seed=1, record=False), 10, warm=2)
+        a = torch.rand(nb, env._info.act_dim, device="cuda") * 2 - 1
+        ms1 = timed(lambda: env.step(a), 50)
+        out[f"config5_{name}"] = {"workload": f"{cls.__name__} {nb} contexts", "fused_env_steps_per_s": nb * T / (ms * 1e-3),
+                                  "step_api_env_steps_per_s": nb / (ms1 * 1e-3), "step_us": ms1 * 1e3}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
