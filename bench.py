@@ -246,10 +246,29 @@ def run_gpu_arm(args):
     assert env.num_envs == n_local
     env.reset(seed=0)
     gather = None
+    gather_mode = args.gather
     if distributed:
         from carl_b200.parallel import ObsGather
 
-        gather = ObsGather(env, mode=args.gather)
+        if gather_mode == "fused":
+            # every rank must succeed in mapping its peers (CUDA IPC / P2P); otherwise all fall back to NCCL
+            ok = 1
+            try:
+                gather = ObsGather(env, mode="fused")
+            except Exception as e:  # pragma: no cover - depends on the box
+                ok = 0
+                print(f"[rank {rank}] fused gather unavailable ({e}); falling back to NCCL", file=sys.stderr)
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                if gather is not None:
+                    gather.close()
+                gather, gather_mode = None, "nccl"
+                # a handle that had a gather attached is rebuilt without one
+                env = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world))
+                env.reset(seed=0)
+        if gather is None:
+            gather = ObsGather(env, mode="nccl")
 
     K, W = args.steps, args.warmup
     T = math.gcd(K, args.fuse)  # fused steps per launch; K/T launches time EXACTLY K steps
@@ -404,7 +423,7 @@ def run_gpu_arm(args):
             "n_envs": n_global, "fused_steps_per_launch": T, "launches": K // T,
             "l2": f"trajectory ring {n_slots} x {slot_bytes / 2**20:.0f} MiB > L2 (outputs go to DRAM); env state "
                   f"({n_local * 90 / 2**20:.1f} MiB working set) is register/L2 resident by design",
-            "collective": (f"obs all-gather per launch: {args.gather}" + (" (in-kernel NVLink peer stores + flag wait)" if args.gather == "fused" else "")) if distributed else "none",
+            "collective": (f"obs all-gather per launch: {gather_mode}" + (" (in-kernel NVLink peer stores + flag wait)" if gather_mode == "fused" else "")) if distributed else "none",
         },
         "gpu_launches": int(launches),
         "clocks": clock_info,

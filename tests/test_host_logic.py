@@ -141,3 +141,12 @@ def test_legacy_aliases_and_extension_features():
     assert CARLBraxAnt.kernel_params(t, names, "reference")[0, 4] == 1.0
     assert CARLBraxAnt.feature_aliases["torso_mass"] == "mass_torso"
     assert "joint_stiffness" not in CARLBraxAnt.get_context_features()  # the context space stays the reference's
+
+
+def test_registration_is_optional():
+    from carl_b200.registration import ENV_NAMES, register_envs
+    import carl_b200.envs as E
+
+    ids = register_envs()
+    assert ids == [] or len(ids) == len(ENV_NAMES)
+    assert all(hasattr(E, n) for n in ENV_NAMES)
