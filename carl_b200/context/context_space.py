@@ -140,89 +140,73 @@ class CategoricalContextFeature(ContextFeature):
         return np.asarray(self.choices, dtype=object)[idx]
 
 
-class ContextSpace(object):
-    """Reference: ``carl/context/context_space.py:31-229`` (same methods, same results)."""
+class ContextSpace:
+    """The set of context features of one env class: names, defaults, bounds, validation and the
+    observation-space view. Public surface of the reference's ``ContextSpace``
+    (``carl/context/context_space.py:31-229``), same results."""
 
     def __init__(self, context_space: dict[str, ContextFeature]) -> None:
         self.context_space = context_space
 
     @property
     def context_feature_names(self) -> list[str]:
-        return list(self.context_space.keys())
-
-    def insert_defaults(self, context: Context, context_keys: List[str] | None = None) -> Context:
-        """``context_space.py:54-80``: defaults (optionally only ``context_keys``) updated by ``context``."""
-        context_with_defaults = self.get_default_context()
-        if context_keys:
-            context_with_defaults = {key: context_with_defaults[key] for key in context_keys}
-        context_with_defaults.update(context)
-        return context_with_defaults
-
-    def verify_context(self, context: Context) -> bool:
-        """``context_space.py:82-114``: names known and numerical values in bounds."""
-        is_valid = True
-        cfs = self.context_feature_names
-        for cfname, v in context.items():
-            if cfname not in cfs:
-                is_valid = False
-                break
-            cf = self.context_space[cfname]
-            if isinstance(cf, NumericalContextFeature):
-                if not (cf.lower <= v <= cf.upper):
-                    is_valid = False
-                    break
-        return is_valid
+        return [*self.context_space]
 
     def get_default_context(self) -> Context:
-        """``context_space.py:116-125``."""
-        return {cf.name: cf.default_value for cf in self.context_space.values()}
+        return {f.name: f.default_value for f in self.context_space.values()}
+
+    def insert_defaults(self, context: Context, context_keys: List[str] | None = None) -> Context:
+        """Defaults (restricted to ``context_keys`` when given) overridden by ``context``."""
+        base = self.get_default_context()
+        if context_keys:
+            base = {k: base[k] for k in context_keys}
+        return {**base, **context}
+
+    def verify_context(self, context: Context) -> bool:
+        """True iff every name is a known feature and every numerical value lies in its bounds."""
+        for name, value in context.items():
+            feature = self.context_space.get(name)
+            if feature is None:
+                return False
+            if isinstance(feature, NumericalContextFeature) and not (feature.lower <= value <= feature.upper):
+                return False
+        return True
 
     def get_lower_and_upper_bound(self, context_feature_name: str) -> tuple[float, float]:
-        """``context_space.py:127-143``."""
-        cf = self.context_space[context_feature_name]
-        return (cf.lower, cf.upper)
+        f = self.context_space[context_feature_name]
+        return f.lower, f.upper
 
     def to_gymnasium_space(self, context_feature_names: List[str] | None = None, as_dict: bool = False):
-        """``context_space.py:145-188``. Uses gymnasium's spaces when importable, else the
-        API-compatible stand-ins in ``carl_b200.spaces``."""
-        if context_feature_names is None:
-            context_feature_names = self.context_feature_names
-        if as_dict:
-            context_space = {}
-            for cf_name in context_feature_names:
-                context_feature = self.context_space[cf_name]
-                if isinstance(context_feature, NumericalContextFeature):
-                    context_space[context_feature.name] = spaces.Box(
-                        low=context_feature.lower, high=context_feature.upper
-                    )
-                else:
-                    context_space[context_feature.name] = spaces.Discrete(len(context_feature.choices))
-            return spaces.Dict(context_space)
-        low = np.array([self.context_space[cf].lower for cf in context_feature_names])
-        high = np.array([self.context_space[cf].upper for cf in context_feature_names])
-        return spaces.Box(low=low, high=high, dtype=np.float32)
+        """Observation-space view of (a subset of) the features: a ``Dict`` of per-feature ``Box`` /
+        ``Discrete`` spaces, or one float32 ``Box`` over the bounds vector. gymnasium's classes are
+        used when importable, else the stand-ins of ``carl_b200.spaces``."""
+        names = self.context_feature_names if context_feature_names is None else context_feature_names
+        feats = [self.context_space[n] for n in names]
+        if not as_dict:
+            return spaces.Box(low=np.array([f.lower for f in feats]), high=np.array([f.upper for f in feats]),
+                              dtype=np.float32)
+        per_feature = {}
+        for f in feats:
+            numeric = isinstance(f, NumericalContextFeature)
+            per_feature[f.name] = spaces.Box(low=f.lower, high=f.upper) if numeric else spaces.Discrete(len(f.choices))
+        return spaces.Dict(per_feature)
 
     def sample_contexts(self, context_keys: List[str] | None = None, size: int = 1) -> Context | List[Contexts]:
-        """``context_space.py:190-229``: unseeded ``rvs`` per feature; features outside
-        ``context_keys`` are dropped *unless* sampled (reference behaviour: the sampled value of
-        every feature overrides the inserted defaults)."""
+        """Unseeded samples of every feature (``rvs``), merged over the defaults of ``context_keys``.
+        A feature whose distribution is unbounded keeps its default. ``size == 1`` returns the bare
+        context, otherwise a list."""
         if context_keys is None:
-            context_keys = self.context_space.keys()
-        else:
-            for key in context_keys:
-                if key not in self.context_space.keys():
-                    raise ValueError(f"Invalid context feature name: {key}")
-        contexts = []
-        for _ in range(size):
-            context = {}
-            for cf in self.context_space.values():
-                try:
-                    context[cf.name] = cf.rvs()
-                except ValueError:
-                    # unbounded uniform features cannot be sampled; keep the default
-                    context[cf.name] = cf.default_value
-            context = self.insert_defaults(context, list(context_keys))
-            contexts += [context]
-        if size == 1:
-            return contexts[0]
-        return contexts
+            context_keys = list(self.context_space)
+        bad = [k for k in context_keys if k not in self.context_space]
+        if bad:
+            raise ValueError(f"Invalid context feature name: {bad[0]}")
+
+        def draw(f: ContextFeature):
+            try:
+                return f.rvs()
+            except ValueError:
+                return f.default_value
+
+        drawn = [self.insert_defaults({f.name: draw(f) for f in self.context_space.values()}, list(context_keys))
+                 for _ in range(size)]
+        return drawn[0] if size == 1 else drawn

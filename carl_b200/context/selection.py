@@ -1,14 +1,14 @@
-"""Context selectors.
+"""Context selectors of the batched engine.
 
-Same classes, attributes and selection rules as the reference's
-``carl/context/selection.py:11-180``. Added for the batched engine:
-``select_batch(n)`` — the ids ``n`` consecutive ``select()`` calls would return,
-computed vectorised for the built-in selectors (the batched env resets ``n`` env
-instances "in env-index order" against one shared selector).
+Same public surface as the reference's ``carl/context/selection.py`` (``AbstractSelector`` with
+``contexts / context_ids / contexts_keys / n_calls / context_id / context_key / select()``, and the
+``RandomSelector``, ``RoundRobinSelector``, ``StaticSelector``, ``CustomSelector`` policies), built
+around one vectorised primitive: ``select_batch(n)`` returns the ids that ``n`` consecutive
+``select()`` calls produce. The batched env resets many env instances against one shared selector,
+so the scalar ``select()`` is just ``select_batch(1)`` here.
 """
 from __future__ import annotations
 
-from abc import abstractmethod
 from typing import Any, Callable, List, Optional, Tuple
 
 import numpy as np
@@ -16,102 +16,87 @@ import numpy as np
 from carl_b200.utils.types import Context, Contexts
 
 
-class AbstractSelector(object):
-    """Reference: ``selection.py:11-95``."""
+class AbstractSelector:
+    """Bookkeeping shared by all selection policies (reference: ``selection.py:11-95``)."""
 
     def __init__(self, contexts: Contexts):
         self.contexts: Contexts = contexts
-        self.context_ids: List[int] = list(np.arange(len(contexts)))
         self.contexts_keys: List[Any] = list(contexts.keys())
+        self.context_ids: List[int] = list(np.arange(len(self.contexts_keys)))
         self.n_calls: int = 0
-        self.context_id: Optional[int] = None
+        self.context_id: Optional[int] = None  # index into contexts_keys; None until the first select
 
-    @abstractmethod
-    def _select(self) -> Tuple[Context, int]:
-        ...
+    # -- policy hook ---------------------------------------------------------------------------
+    def _next_ids(self, n: int) -> np.ndarray:
+        """Ids of the next ``n`` selections (policy specific); may read/update ``context_id``."""
+        out = np.empty(n, dtype=np.int64)
+        for j in range(n):  # generic fallback: a policy that only implements the scalar `_select`
+            _, cid = self._select()
+            self.context_id = cid
+            out[j] = cid
+        return out
+
+    def _select(self) -> Tuple[Context, int]:  # scalar hook kept for subclasses written against the reference
+        raise NotImplementedError
+
+    # -- public API ----------------------------------------------------------------------------
+    def select_batch(self, n: int) -> np.ndarray:
+        ids = np.asarray(self._next_ids(int(n)), dtype=np.int64)
+        if ids.size:
+            self.context_id = int(ids[-1])
+        self.n_calls += int(n)
+        return ids
 
     def select(self) -> Context:
-        """``selection.py:64-76``."""
-        context, context_id = self._select()
-        self.context_id = context_id
-        self.n_calls += 1
-        return context
-
-    def select_batch(self, n: int) -> np.ndarray:
-        """Ids of ``n`` consecutive ``select()`` calls (generic fallback: the loop itself)."""
-        ids = np.empty(n, dtype=np.int64)
-        for i in range(n):
-            self.select()
-            ids[i] = self.context_id
-        return ids
+        cid = int(self.select_batch(1)[0])
+        return self.contexts[self.contexts_keys[cid]]
 
     @property
     def context_key(self) -> Any | None:
-        """``selection.py:78-95`` (returns None for id 0 as the reference does)."""
-        if self.context_id:
-            key = self.contexts_keys[self.context_id]
-        else:
-            key = None
-        return key
-
-
-class RandomSelector(AbstractSelector):
-    """``selection.py:98-107``: ``np.random.choice`` on the global legacy RNG."""
-
-    def _select(self) -> Tuple[Context, int]:
-        context_id = np.random.choice(self.context_ids)
-        context = self.contexts[self.contexts_keys[context_id]]
-        return context, context_id
+        # the reference tests truthiness of the id, so id 0 reports None as well (selection.py:91-95)
+        return self.contexts_keys[self.context_id] if self.context_id else None
 
 
 class RoundRobinSelector(AbstractSelector):
-    """``selection.py:110-122``."""
+    """Cycle through the context set in key order (reference: ``selection.py:110-122``)."""
 
-    def _select(self) -> Tuple[Context, int]:
-        if self.context_id is None:
-            self.context_id = -1
-        self.context_id = (self.context_id + 1) % len(self.contexts)
-        context = self.contexts[self.contexts_keys[self.context_id]]
-        return context, self.context_id
-
-    def select_batch(self, n: int) -> np.ndarray:
-        if n == 0:
-            return np.empty(0, dtype=np.int64)
+    def _next_ids(self, n: int) -> np.ndarray:
         start = -1 if self.context_id is None else int(self.context_id)
-        ids = (start + 1 + np.arange(n, dtype=np.int64)) % len(self.contexts)
-        self.context_id = int(ids[-1])
-        self.n_calls += n
-        return ids
+        return (start + 1 + np.arange(n, dtype=np.int64)) % len(self.contexts_keys)
 
 
 class StaticSelector(AbstractSelector):
-    """``selection.py:125-136``."""
+    """Never change the context (reference: ``selection.py:125-136``)."""
 
-    def _select(self) -> Tuple[Context, int]:
-        if self.context_id is None:
-            self.context_id = self.context_ids[0]
-        context = self.contexts[self.contexts_keys[self.context_id]]
-        return context, self.context_id
+    def _next_ids(self, n: int) -> np.ndarray:
+        cid = self.context_ids[0] if self.context_id is None else self.context_id
+        return np.full(n, int(cid), dtype=np.int64)
 
-    def select_batch(self, n: int) -> np.ndarray:
-        if self.context_id is None:
-            self.context_id = self.context_ids[0]
-        self.n_calls += n
-        return np.full(n, int(self.context_id), dtype=np.int64)
+
+class RandomSelector(AbstractSelector):
+    """Uniformly random context per selection, drawn one at a time from NumPy's global legacy
+    generator exactly as the reference does (``np.random.choice``, ``selection.py:98-107``)."""
+
+    def _next_ids(self, n: int) -> np.ndarray:
+        return np.fromiter((np.random.choice(self.context_ids) for _ in range(n)), dtype=np.int64, count=n)
 
 
 class CustomSelector(AbstractSelector):
-    """``selection.py:139-180``."""
+    """User policy: ``selector_function(selector) -> (context, context_id)``
+    (reference: ``selection.py:139-180``; e.g. ``lambda s: (s.contexts[s.contexts_keys[1]], 1)``)."""
 
-    def __init__(
-        self,
-        contexts: Contexts,
-        selector_function: Callable[[AbstractSelector], Tuple[Context, int]],
-    ):
+    def __init__(self, contexts: Contexts, selector_function: Callable[[AbstractSelector], Tuple[Context, int]]):
         super().__init__(contexts=contexts)
         self.selector_function = selector_function
 
-    def _select(self) -> Tuple[Context, int]:
-        context, context_id = self.selector_function(self)
-        self.context_id = context_id
-        return context, context_id
+    def _next_ids(self, n: int) -> np.ndarray:
+        out = np.empty(n, dtype=np.int64)
+        for j in range(n):
+            _, cid = self.selector_function(self)
+            self.context_id = cid
+            out[j] = cid
+            if j + 1 < n:
+                self.n_calls += 1  # the user function may key on n_calls (reference docstring example)
+        if n > 1:
+            self.n_calls -= n - 1  # select_batch adds n once
+        return out

@@ -1,17 +1,15 @@
-"""Reference: ``carl/context/utils.py:6-35``."""
-from typing import Any, Dict, List, Tuple, Type
+"""Bounds helper of the context plugin surface (reference counterpart: ``carl/context/utils.py``,
+``get_context_bounds``)."""
+from __future__ import annotations
+
+from typing import Any, Mapping, Sequence
 
 import numpy as np
 
 
-def get_context_bounds(
-    context_keys: List[str], context_bounds: Dict[str, Tuple[float, float, Type[Any]]]
-) -> Tuple[np.ndarray, np.ndarray]:
-    """Lower / upper bound arrays for ``context_keys`` from ``{name: (lower, upper, dtype)}``."""
-    lower_bounds = np.empty(shape=len(context_keys))
-    upper_bounds = np.empty(shape=len(context_keys))
-    for i, context_key in enumerate(context_keys):
-        lower, upper, _dtype = context_bounds[context_key]
-        lower_bounds[i] = lower
-        upper_bounds[i] = upper
-    return lower_bounds, upper_bounds
+def get_context_bounds(context_keys: Sequence[str], context_bounds: Mapping[str, tuple[float, float, Any]]):
+    """``(lower, upper)`` float arrays for ``context_keys`` out of ``{name: (lower, upper, dtype)}``."""
+    picked = [context_bounds[k] for k in context_keys]
+    lower = np.fromiter((b[0] for b in picked), dtype=np.float64, count=len(picked))
+    upper = np.fromiter((b[1] for b in picked), dtype=np.float64, count=len(picked))
+    return lower, upper
