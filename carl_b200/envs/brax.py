@@ -195,6 +195,7 @@ class CARLBraxEnv(CARLEnv):
             self._seeded = True
         _native.check(self._lib.carlb_brax_reset_from_q(
             self._handle, None if mt is None else mt.data_ptr(), qt.data_ptr(), qdt.data_ptr(), self._stream()))
+        self._has_reset = True
         return self._add_context_to_state(self._obs), {"context_id": self.context_id}
 
     @classmethod

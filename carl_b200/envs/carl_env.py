@@ -105,6 +105,7 @@ class CARLEnv(abc.ABC):
         autoreset: bool | None = None,
         max_episode_steps: int | None = None,
         shard: tuple[int, int] | None = None,
+        validate_actions: bool = True,
         **kwargs,
     ):
         """Parameters follow ``carl_env.py:20-74``; the keyword-only ones are new.
@@ -118,6 +119,8 @@ class CARLEnv(abc.ABC):
             as in the reference, on for Brax where ``brax.envs.create`` adds AutoResetWrapper).
         shard: ``(rank, world_size)`` -- this object owns the contiguous slice of the global batch
             that ``carl_b200.parallel.shard_range`` assigns to ``rank``.
+        validate_actions: host-buffer path only -- assert that discrete actions lie in the action
+            space, as gymnasium's envs do on every step; device tensors are never validated (no sync).
         """
         if env is not None:
             raise ValueError("carl_b200 envs own their physics; passing a gymnasium/brax `env` is not supported.")
@@ -199,6 +202,8 @@ class CARLEnv(abc.ABC):
         self._ctx_obs_host_cache = None
         self._ids_view = None
         self._seeded = False
+        self._has_reset = False
+        self._validate_actions = bool(validate_actions)
         self._host_io = None
 
     # ------------------------------------------------------------------ contexts
@@ -486,6 +491,7 @@ class CARLEnv(abc.ABC):
         if mask_np is not None:
             mask_t = torch.from_numpy(mask_np.astype(np.uint8)).to(self.device)
         _native.check(self._lib.carlb_env_reset(self._handle, _ptr(mask_t), st))
+        self._has_reset = True
         state = self._add_context_to_state(self._obs)
         info = {"context_id": self.context_id}
         return state, info
@@ -514,6 +520,8 @@ class CARLEnv(abc.ABC):
     def step(self, action: Any):
         """``carl_env.py:321-342`` batched. torch CUDA actions -> device results;
         numpy / list actions -> host (numpy) results through pinned buffers."""
+        if not self._has_reset:  # gymnasium's OrderEnforcing wrapper raises ResetNeeded here
+            raise RuntimeError("Cannot call env.step() before calling env.reset()")
         if isinstance(action, torch.Tensor) and action.is_cuda:
             self._check_actions(self.num_envs, tuple(action.shape))
             if action.dtype not in _TORCH_ACT:
@@ -555,6 +563,10 @@ class CARLEnv(abc.ABC):
                 a = a.astype(np.int64)
         elif a.dtype != np.float32:
             a = a.astype(np.float32)
+        if self._validate_actions and self._info.act_discrete:
+            # `assert self.action_space.contains(action)` of the gymnasium envs, batched
+            assert a.size == 0 or (int(a.min()) >= 0 and int(a.max()) < self._info.n_actions), (
+                f"invalid action: values must lie in [0, {self._info.n_actions})")
         nbytes = a.size * a.dtype.itemsize
         staged = io["act"].numpy().view(np.uint8)[:nbytes].view(a.dtype)
         staged[...] = a.reshape(-1)
@@ -588,6 +600,8 @@ class CARLEnv(abc.ABC):
         actions=None: synthetic uniform random policy from Philox4x32-10 keyed by
         ``(policy_seed, global env id, step_base + t)``. record=True returns the trajectory
         ``{"obs": [K,N,D], "actions": [K,N(,A)], "reward": [K,N], "done": [K,N] (bit0 term, bit1 trunc)}``."""
+        if not self._has_reset:
+            raise RuntimeError("Cannot call env.rollout() before calling env.reset()")
         n, info, dev = self.num_envs, self._info, self.device
         traj_t = None
         traj = None
@@ -631,6 +645,7 @@ class CARLEnv(abc.ABC):
         self._refresh_context_view()
         self._update_context()
         self._seeded = True
+        self._has_reset = True
 
     # raw views for tests / learners
     @property

@@ -32,6 +32,8 @@ class MixedBatch:
 
     def step(self, actions: list[torch.Tensor]):
         assert len(actions) == len(self.envs)
+        if not all(e._has_reset for e in self.envs):
+            raise RuntimeError("Cannot call step() before calling reset()")
         acts, dts = [], []
         for e, a in zip(self.envs, actions):
             assert a.is_cuda, "mixed step takes device actions"

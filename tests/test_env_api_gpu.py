@@ -123,6 +123,21 @@ def test_invalid_arguments_raise():
         _native.check(env._lib.carlb_env_step(env._handle, torch.zeros(4, device="cuda").data_ptr(), _native.ACT_F32, None))
 
 
+def test_order_enforcing_and_action_validation():
+    from carl_b200.envs import CARLAcrobot
+
+    env = CARLAcrobot(num_envs=3)
+    with pytest.raises(RuntimeError, match="before calling env.reset"):
+        env.step(np.zeros(3, dtype=np.int64))
+    env.reset(seed=0)
+    env.step(np.array([0, 1, 2]))
+    with pytest.raises(AssertionError, match="invalid action"):
+        env.step(np.array([0, 3, 1]))
+    with pytest.raises(AssertionError, match="invalid action"):
+        env.step(np.array([0, -1, 1]))
+    CARLAcrobot(num_envs=3, validate_actions=False)
+
+
 def test_checkpoint_roundtrip():
     from carl_b200.envs import CARLAcrobot
 
