@@ -1,17 +1,20 @@
-// Brax-locomotion kernels (sm_100a): ONE WARP PER ENV INSTANCE.
+// Brax-locomotion kernels (sm_100a): ONE WARP PER 1 OR 3 ENV INSTANCES.
 //
-// Lanes 0..L-1 own the links of the body (13-float centre-of-mass state in registers), lanes
-// 0..P-1 own the ground-contact candidate points during the collision phase; the per-warp exchange
-// (parent/child states, joint reactions, contact impulses) goes through a 2 KB shared-memory
-// scratch guarded by __syncwarp. The system table (3.1 KB: link frames, inertias, joint limits,
-// contact points, tunables) is staged once per CTA into shared memory with a TMA bulk copy
-// (cp.async.bulk + mbarrier); each env's 13 context scalars (gravity, friction, elasticity,
-// ang_damping, link masses) are read with one coalesced load and broadcast with warp shuffles.
+// Each env owns LPE = 32/E consecutive lanes of a warp (E = 3 for bodies of at most 10 links: Ant,
+// Halfcheetah, Hopper). Sub-lanes 0..L-1 own the links of the body (13-float centre-of-mass state in
+// registers) and, in ceil(P/LPE) passes, the ground-contact candidate points of the collision phase;
+// the exchange between the lanes of an env (parent/child states, joint reactions, contact
+// impulses, loop invariants) goes through a 2.7 KB shared-memory scratch guarded by __syncwarp.
+// The system table (3.1 KB: link frames, inertias, joint limits, contact points, tunables) is
+// staged once per CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); each
+// env's context scalars (gravity, friction, elasticity, ang_damping, stiffness scale, link masses)
+// are staged with one coalesced load and then read as shared-memory broadcasts.
 //
 // This is FP32-issue / latency bound work (~6e4 flops per Ant env-step against ~1.1 kB of HBM
 // traffic): no tensor cores. One launch = n_frames spring substeps (+ env layer); the fused
 // rollout keeps the link state in registers across K env-steps.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "engine.h"
@@ -20,9 +23,9 @@
 namespace carlb {
 using namespace brax;
 
-constexpr int kWarpsPerCta = 4;
-constexpr int kThreads = kWarpsPerCta * 32;
-constexpr unsigned kFull = 0xffffffffu;
+// Warps (= env instances) per CTA. 4 x 128-thread CTAs per SM is the default; for batches of several
+// thousand envs a 7-warp CTA (2 resident per SM = 14 warps) makes the grid an almost exact multiple
+// of the machine: 8 192 envs = 3.96 waves of 148 SMs x 14 warps instead of 3.46 waves of 16.
 
 struct BraxSys {        // device-resident per-handle system table (+ static facts)
   float table[TABLE_FLOATS];
@@ -57,14 +60,17 @@ struct BraxSeg {
   unsigned int* block_counter;
 };
 
-struct WarpScratch {
+// Per-env shared-memory scratch (2.7 KB): the exchange medium between the lanes of one env.
+struct EnvScratch {
   float ls[MAX_LINKS * LINK_WORDS];  // link states (also the coalesced I/O staging of the state row)
   float pw[MAX_LINKS * 6];           // reaction wrench of joint l on its parent
   float co[MAX_POINTS * 7];          // contact outputs: impulse(3) angular impulse(3) active
+  float lc[MAX_LINKS * 6];           // per-link loop invariants: inv_mass, inv_idiag(3), vel_decay, ang_decay
   float q[MAX_Q];
   float qd[MAX_Q];
   float act[16];
   float obs[64];
+  float ctx[24];                     // this env's context scalars (gravity, friction, ..., link masses)
 };
 
 // ---- TMA bulk copy + mbarrier (PTX) ------------------------------------------------------------
@@ -108,7 +114,6 @@ __device__ __forceinline__ void stage_system(float* sys_s, const float* sys_g, u
   mbar_wait(bar, 0);
 }
 
-// ---- state row I/O: coalesced through the warp scratch --------------------------------------------
 __device__ __forceinline__ LinkState read_link(const float* ls, int l) {
   const float* p = ls + l * LINK_WORDS;
   LinkState s;
@@ -125,76 +130,46 @@ __device__ __forceinline__ void write_link(float* ls, int l, const LinkState& s)
   p[7] = s.vel.x; p[8] = s.vel.y; p[9] = s.vel.z;
   p[10] = s.ang.x; p[11] = s.ang.y; p[12] = s.ang.z;
 }
-__device__ __forceinline__ void row_g2s(float* dst, const float* src, int words, int lane) {
-  for (int i = lane; i < words; i += 32) dst[i] = src[i];
-}
-__device__ __forceinline__ void row_s2g(float* dst, const float* src, int words, int lane) {
-  for (int i = lane; i < words; i += 32) dst[i] = src[i];
-}
-
-// ---- one env, one warp: per-lane constants ---------------------------------------------------------
-struct LaneCtx {
-  int L, P, n_frames, env_kind;
-  bool is_link, is_point;
-  const float* lt;   // my link row
-  const float* plt;  // parent's link row
-  int parent;
-  int type;
-  int act;           // actuator index or -1
-  const float* pt;   // my contact point row
-  int pt_link;
-  float mass;        // my link's (context) mass
-  float pt_mass;     // mass of my contact point's link
-  float gravity, friction_ctx, elasticity_ctx, ang_damping, stiffness_scale;
-  float pt_friction, pt_elasticity;
-  LinkConst lc;     // loop-invariant constants of my link
-  LinkConst pt_lc;  // ... and of my contact point's link
-};
-
-__device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const float* ctx_row, int n_ctx, int lane,
-                                                 bool stock_contact) {
-  LaneCtx c;
-  c.L = (int)sys[H_N_LINKS];
-  c.P = (int)sys[H_N_POINTS];
-  c.n_frames = (int)sys[H_N_FRAMES];
-  c.env_kind = (int)sys[H_ENV];
-  c.is_link = lane < c.L;
-  c.is_point = lane < c.P;
-  const int l = c.is_link ? lane : 0;
-  c.lt = link_tab(sys, l);
-  c.parent = (int)c.lt[L_PARENT];
-  c.plt = link_tab(sys, c.parent >= 0 ? c.parent : 0);
-  c.type = (int)c.lt[L_TYPE];
-  c.act = (int)c.lt[L_ACT];
-  const int p = c.is_point ? lane : 0;
-  c.pt = point_tab(sys, p);
-  c.pt_link = (int)c.pt[0];
-  // one coalesced load of the env's context scalars, then shuffle broadcast
-  const float cv = (lane < n_ctx) ? ctx_row[lane] : 0.0f;
-  c.gravity = __shfl_sync(kFull, cv, C_GRAVITY);
-  c.friction_ctx = __shfl_sync(kFull, cv, C_FRICTION);
-  c.elasticity_ctx = __shfl_sync(kFull, cv, C_ELASTICITY);
-  c.ang_damping = __shfl_sync(kFull, cv, C_ANG_DAMPING);
-  c.stiffness_scale = __shfl_sync(kFull, cv, C_STIFFNESS_SCALE);
-  c.mass = __shfl_sync(kFull, cv, C_MASS0 + l);
-  c.pt_mass = __shfl_sync(kFull, cv, C_MASS0 + c.pt_link);
-  // friction / elasticity: a negative context value means "keep the stock per-geom value"
-  c.pt_friction = (c.friction_ctx < 0.0f || stock_contact) ? c.pt[5] : c.friction_ctx;
-  c.pt_elasticity = (c.elasticity_ctx < 0.0f || stock_contact) ? c.pt[6] : c.elasticity_ctx;
-  c.lc = make_link_const(sys, c.lt, c.mass, c.ang_damping);
-  c.pt_lc = make_link_const(sys, link_tab(sys, c.pt_link), c.pt_mass, c.ang_damping);
+__device__ __forceinline__ LinkConst read_lc(const float* lc, int l) {
+  const float* p = lc + l * 6;
+  LinkConst c;
+  c.inv_mass = p[0]; c.inv_idiag = v3(p[1], p[2], p[3]); c.vel_decay = p[4]; c.ang_decay = p[5];
   return c;
 }
 
-// n_frames spring substeps for the env held by this warp. `s` is this lane's link (valid for
-// lane < L), `tau` this lane's actuator torque.
-__device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, WarpScratch& w, LinkState& s, float tau,
-                                               int lane) {
+// ---- lane mapping -----------------------------------------------------------------------------------
+// E env instances share one warp: sub-env `sub` owns the LPE = 32/E consecutive lanes
+// [sub*LPE, (sub+1)*LPE); within it sub-lane `sl` owns link `sl` (sl < L) and, in pass k of the
+// collision phase, contact point k*LPE + sl. A warp of an Ant batch (9 links, 25 points) would use
+// 9 of 32 lanes in the joint / integration phases with E = 1; E = 3 uses 27.
+template <int E>
+struct Lanes {
+  static constexpr int LPE = 32 / E;
+};
+
+struct LaneCtx {
+  int L, P, n_frames;
+  int sub, sl;       // sub-env of this lane and the lane's index inside it
+  bool active;       // this lane's sub-env maps onto a real env instance
+  bool is_link;
+  const float* lt;   // my link row
+  const float* plt;  // parent's link row
+  int parent, type, act;
+  float gravity, stiffness_scale;
+  bool stock_contact;
+  LinkConst lc;      // loop invariants of my link
+};
+
+// n_frames spring substeps for the sub-envs of this warp. `s` is this lane's link.
+template <int E>
+__device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, EnvScratch& w, LinkState& s, float tau) {
+  constexpr int LPE = Lanes<E>::LPE;
   const float dt = sys[H_DT];
+  const int n_pass = (c.P + LPE - 1) / LPE;
   for (int f = 0; f < c.n_frames; ++f) {
-    if (c.is_link) write_link(w.ls, lane, s);
+    if (c.is_link) write_link(w.ls, c.sl, s);
     __syncwarp();
-    // joints: lane l resolves the joint between link l and its parent
+    // joints: sub-lane l resolves the joint between link l and its parent
     Wrench wr;
     wr.f = v3(0, 0, 0); wr.t = v3(0, 0, 0);
     if (c.is_link && c.type != TYPE_FREE) {
@@ -202,31 +177,37 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
       const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale);
       wr = jo.child;
-      float* pw = w.pw + lane * 6;
+      float* pw = w.pw + c.sl * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
       pw[3] = jo.parent.t.x; pw[4] = jo.parent.t.y; pw[5] = jo.parent.t.z;
     }
     __syncwarp();
     if (c.is_link) {
       // add the reactions of my children (fixed order: deterministic sums)
-      for (int k = lane + 1; k < c.L; ++k) {
-        if ((int)link_tab(sys, k)[L_PARENT] == lane) {
+      for (int k = c.sl + 1; k < c.L; ++k) {
+        if ((int)link_tab(sys, k)[L_PARENT] == c.sl) {
           const float* pw = w.pw + k * 6;
           wr.f = wr.f + v3(pw[0], pw[1], pw[2]);
           wr.t = wr.t + v3(pw[3], pw[4], pw[5]);
         }
       }
       integrate_xdd(s, wr, sys, c.lt, c.lc, c.gravity);
-      write_link(w.ls, lane, s);
+      write_link(w.ls, c.sl, s);
     }
     __syncwarp();
-    // ground contacts: lane p resolves candidate point p against the plane
-    if (c.is_point) {
-      const LinkState ps = read_link(w.ls, c.pt_link);
-      const ContactOut co = contact_resolve(sys, c.pt, link_tab(sys, c.pt_link), ps, c.pt_lc, c.pt_friction,
-                                            c.pt_elasticity);
-      float* o = w.co + lane * 7;
-      o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
+    // ground contacts: in pass k sub-lane sl resolves candidate point k*LPE + sl against the plane
+    for (int pass = 0; pass < n_pass; ++pass) {
+      const int p = pass * LPE + c.sl;
+      if (c.active && c.sl < LPE && p < c.P) {
+        const float* pt = point_tab(sys, p);
+        const int pl = (int)pt[0];
+        const LinkState ps = read_link(w.ls, pl);
+        const float fr = (c.stock_contact || w.ctx[C_FRICTION] < 0.0f) ? pt[5] : w.ctx[C_FRICTION];
+        const float el = (c.stock_contact || w.ctx[C_ELASTICITY] < 0.0f) ? pt[6] : w.ctx[C_ELASTICITY];
+        const ContactOut co = contact_resolve(sys, pt, link_tab(sys, pl), ps, read_lc(w.lc, pl), fr, el);
+        float* o = w.co + p * 7;
+        o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
+      }
     }
     __syncwarp();
     if (c.is_link) {
@@ -246,15 +227,16 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
   }
 }
 
-// kinematics.inverse + env observation: fills w.obs[0..D) and returns (lane-uniform) root facts
+// kinematics.inverse + env observation: fills w.obs[0..D) and returns the root facts of the sub-env
 struct RootFacts {
   float x, z, angle;
   bool state_ok;  // Hopper: all |q[2:]|, |qd| < 100
 };
 
-__device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, WarpScratch& w, const LinkState& s,
-                                                 int lane) {
-  if (c.is_link) write_link(w.ls, lane, s);
+template <int E>
+__device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, EnvScratch& w, const LinkState& s) {
+  constexpr int LPE = Lanes<E>::LPE;
+  if (c.is_link) write_link(w.ls, c.sl, s);
   __syncwarp();
   const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
   if (c.is_link) {
@@ -280,25 +262,25 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   const int ex = (int)sys[H_EXCLUDE_POS];
   const float clip = sys[H_QD_CLIP];
   const int D = (nq - ex) + nqd;
-  for (int i = lane; i < D; i += 32) {
-    float v;
-    if (i < nq - ex) {
-      v = w.q[ex + i];
-    } else {
-      v = w.qd[i - (nq - ex)];
-      if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+  if (c.sl < LPE) {
+    for (int i = c.sl; i < D; i += LPE) {
+      float v;
+      if (i < nq - ex) {
+        v = w.q[ex + i];
+      } else {
+        v = w.qd[i - (nq - ex)];
+        if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+      }
+      w.obs[i] = v;
     }
-    w.obs[i] = v;
   }
-  // Hopper healthy_state: every entry of state_vec = q[2:] ++ qd inside (-100, 100)
-  bool ok = true;
-  for (int i = lane; i < (nq - 2) + nqd; i += 32) {
-    const float v = (i < nq - 2) ? w.q[2 + i] : w.qd[i - (nq - 2)];
-    ok = ok && (v > -100.0f) && (v < 100.0f);
-  }
-  RootFacts r;
-  r.state_ok = __all_sync(kFull, ok);
   __syncwarp();
+  // Hopper healthy_state: every entry of state_vec = q[2:] ++ qd inside (-100, 100) (read by all lanes)
+  bool ok = true;
+  for (int i = 2; i < nq; ++i) ok = ok && (w.q[i] > -100.0f) && (w.q[i] < 100.0f);
+  for (int i = 0; i < nqd; ++i) ok = ok && (w.qd[i] > -100.0f) && (w.qd[i] < 100.0f);
+  RootFacts r;
+  r.state_ok = ok;
   const float* lt0 = link_tab(sys, 0);
   const LinkState s0 = read_link(w.ls, 0);
   const V3 o0 = link_origin(s0, lt0);
@@ -328,89 +310,135 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   done = (sys[H_TERMINATE] > 0.0f) && !healthy;
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
-
-// actuator.to_tau for this lane's link: gear * clip(action[act], ctrl_range)
-__device__ __forceinline__ float lane_tau(const LaneCtx& c, const WarpScratch& w) {
-  if (!c.is_link || c.act < 0) return 0.0f;
-  const float a = fminf(fmaxf(w.act[c.act], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
-  return c.lt[L_GEAR] * a;
-}
-
-struct SmemLayout {
+template <int W, int E>
+struct SmemLayoutT {
   float sys[TABLE_FLOATS];
-  WarpScratch warp[kWarpsPerCta];
+  EnvScratch env[W * E];
   uint64_t bar;
 };
 
+// Per-lane setup shared by the step and reset kernels: lane mapping, context staging (one strided
+// coalesced load of the env's context row into its scratch, then shared-memory broadcast reads),
+// loop invariants.
+template <int E>
+__device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg& seg, EnvScratch& w, int env, bool active,
+                                                 int sub, int sl, bool stock_contact) {
+  constexpr int LPE = Lanes<E>::LPE;
+  LaneCtx c;
+  c.L = (int)sys[H_N_LINKS];
+  c.P = (int)sys[H_N_POINTS];
+  c.n_frames = (int)sys[H_N_FRAMES];
+  c.sub = sub;
+  c.sl = sl;
+  c.active = active;
+  c.is_link = active && sl < LPE && sl < c.L;
+  const int l = c.is_link ? sl : 0;
+  c.lt = link_tab(sys, l);
+  c.parent = (int)c.lt[L_PARENT];
+  c.plt = link_tab(sys, c.parent >= 0 ? c.parent : 0);
+  c.type = (int)c.lt[L_TYPE];
+  c.act = (int)c.lt[L_ACT];
+  c.stock_contact = stock_contact;
+  if (active && sl < LPE) {
+    const float* row = seg.ctx + (size_t)env * seg.n_ctx;
+    for (int i = sl; i < seg.n_ctx; i += LPE) w.ctx[i] = row[i];
+  }
+  __syncwarp();
+  c.gravity = w.ctx[C_GRAVITY];
+  c.stiffness_scale = w.ctx[C_STIFFNESS_SCALE];
+  c.lc = make_link_const(sys, c.lt, active ? w.ctx[C_MASS0 + l] : 1.0f, active ? w.ctx[C_ANG_DAMPING] : 0.0f);
+  if (c.is_link) {
+    float* p = w.lc + sl * 6;
+    p[0] = c.lc.inv_mass; p[1] = c.lc.inv_idiag.x; p[2] = c.lc.inv_idiag.y; p[3] = c.lc.inv_idiag.z;
+    p[4] = c.lc.vel_decay; p[5] = c.lc.ang_decay;
+  }
+  __syncwarp();
+  return c;
+}
+
 // ------------------------------------------------------------------------------- step
-// One env-step: [AutoReset zeroing] -> n_frames substeps -> obs/reward/done -> EpisodeWrapper
-// truncation -> AutoReset (state/obs replaced by the stored first ones where done).
-__device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayout& sm, int env, int warp, int lane,
-                                               const float* actions, int n_steps, uint64_t policy_seed,
-                                               uint32_t step_base, const carlb_traj_t& traj, int stock_contact) {
+// One env-step per sub-env: [AutoReset zeroing] -> n_frames substeps -> obs/reward/done ->
+// EpisodeWrapper truncation -> AutoReset (state/obs replaced by the stored first ones where done).
+// Every __syncwarp() is reached by all 32 lanes: per-env conditions only predicate memory traffic.
+template <int W, int E>
+__device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W, E>& sm, const float* actions, int n_steps,
+                                               uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& traj,
+                                               int stock_contact) {
+  constexpr int LPE = Lanes<E>::LPE;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = min(lane / LPE, E - 1), sl = lane - sub * LPE;  // lanes beyond E*LPE idle in the last sub-env
+  const bool lane_ok = lane < E * LPE;
+  const int env = (blockIdx.x * W + warp) * E + sub;
+  const bool active = lane_ok && env < seg.n;
   const float* sys = sm.sys;
-  WarpScratch& w = sm.warp[warp];
-  const LaneCtx c = make_lane_ctx(sys, seg.ctx + (size_t)env * seg.n_ctx, seg.n_ctx, lane, stock_contact != 0);
-  float* state_row = seg.state + (size_t)env * seg.state_words;
-  row_g2s(w.ls, state_row, seg.state_words, lane);
+  EnvScratch& w = sm.env[warp * E + sub];
+  const LaneCtx c = make_lane_ctx<E>(sys, seg, w, env, active, sub, lane_ok ? sl : LPE, stock_contact != 0);
+  const int words = seg.state_words, D = seg.obs_dim, A = seg.act_dim;
+  float* state_row = seg.state + (size_t)(active ? env : 0) * words;
+  if (active && c.sl < LPE)
+    for (int i = c.sl; i < words; i += LPE) w.ls[i] = state_row[i];
   __syncwarp();
-  LinkState s = read_link(w.ls, c.is_link ? lane : 0);
+  LinkState s = read_link(w.ls, c.is_link ? c.sl : 0);
   __syncwarp();
-  int el = seg.elapsed[env];
+  int el = active ? seg.elapsed[env] : 0;
   const uint64_t gid = (uint64_t)(seg.global_offset + env);
-  const int A = seg.act_dim, D = seg.obs_dim;
   float reward = 0.0f;
   bool done = false;
-  RootFacts before = compute_obs(sys, c, w, s, lane);
+  RootFacts before = compute_obs<E>(sys, c, w, s);
   for (int t = 0; t < n_steps; ++t) {
     // actions of this step: given tensor [n][A] (single step) / [K][n][A] (rollout) or Philox policy
     float a = 0.0f;
-    if (lane < A) {
+    if (active && c.sl < A) {
       if (actions != nullptr) {
-        a = actions[((size_t)t * seg.n + env) * A + lane];
+        a = actions[((size_t)t * seg.n + env) * A + c.sl];
       } else {
         const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step_base + (uint32_t)t,
-                                        0x42524158u + (uint32_t)lane, (uint32_t)policy_seed, (uint32_t)(policy_seed >> 32));
+                                        0x42524158u + (uint32_t)c.sl, (uint32_t)policy_seed, (uint32_t)(policy_seed >> 32));
         a = 2.0f * u32_to_unit_float(r.v[0]) - 1.0f;
       }
-      w.act[lane] = a;
+      w.act[c.sl] = a;
     }
     __syncwarp();
-    const float act_sq = warp_sum(lane < A ? a * a : 0.0f);
-    const float tau = lane_tau(c, w);
-    pipeline_steps(sys, c, w, s, tau, lane);
-    const RootFacts after = compute_obs(sys, c, w, s, lane);
+    float act_sq = 0.0f;
+    for (int k = 0; k < A; ++k) act_sq += w.act[k] * w.act[k];  // jp.sum(jp.square(action)), in order
+    float tau = 0.0f;
+    if (c.is_link && c.act >= 0) tau = c.lt[L_GEAR] * fminf(fmaxf(w.act[c.act], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
+    pipeline_steps<E>(sys, c, w, s, tau);
+    const RootFacts after = compute_obs<E>(sys, c, w, s);
     env_outcome(sys, before, after, act_sq, reward, done);
     // EpisodeWrapper: steps += 1; done = where(steps >= episode_length, 1, done)
     el += 1;
     if (seg.max_steps > 0 && el >= seg.max_steps) done = true;
     before = after;
-    if (done && seg.autoreset != CARLB_AUTORESET_NONE) {
-      if (seg.final_obs != nullptr && n_steps == 1)
-        for (int i = lane; i < D; i += 32) seg.final_obs[(size_t)env * D + i] = w.obs[i];
-      // AutoResetWrapper: pipeline_state and obs <- the ones stored at reset
+    const bool do_reset = active && done && seg.autoreset != CARLB_AUTORESET_NONE;
+    if (__any_sync(0xffffffffu, do_reset)) {  // warp-uniform: the barriers inside are reached by all lanes
+      if (do_reset && seg.final_obs != nullptr && n_steps == 1 && c.sl < LPE)
+        for (int i = c.sl; i < D; i += LPE) seg.final_obs[(size_t)env * D + i] = w.obs[i];
       __syncwarp();
-      row_g2s(w.ls, seg.first_state + (size_t)env * seg.state_words, seg.state_words, lane);
-      for (int i = lane; i < D; i += 32) w.obs[i] = seg.first_obs[(size_t)env * D + i];
+      // AutoResetWrapper: pipeline_state and obs <- the ones stored at reset (predicated per sub-env)
+      if (do_reset && c.sl < LPE) {
+        const float* fs = seg.first_state + (size_t)env * words;
+        for (int i = c.sl; i < words; i += LPE) w.ls[i] = fs[i];
+      }
       __syncwarp();
-      s = read_link(w.ls, c.is_link ? lane : 0);
+      if (do_reset) s = read_link(w.ls, c.is_link ? c.sl : 0);
       __syncwarp();
-      before = compute_obs(sys, c, w, s, lane);
-      for (int i = lane; i < D; i += 32) w.obs[i] = seg.first_obs[(size_t)env * D + i];
+      // root facts of the restored state (also recomputes the unchanged obs of the other sub-envs)
+      const RootFacts fresh = compute_obs<E>(sys, c, w, s);
+      if (do_reset) {
+        before = fresh;
+        el = 0;
+      }
+      if (do_reset && c.sl < LPE)
+        for (int i = c.sl; i < D; i += LPE) w.obs[i] = seg.first_obs[(size_t)env * D + i];
       __syncwarp();
-      el = 0;
     }
-    if (n_steps > 1 || traj.obs != nullptr) {
+    if (active && (n_steps > 1 || traj.obs != nullptr)) {
       const size_t row = (size_t)t * seg.n + env;
-      if (traj.obs != nullptr)
-        for (int i = lane; i < D; i += 32) traj.obs[row * D + i] = w.obs[i];
-      if (traj.actions != nullptr && lane < A) static_cast<float*>(traj.actions)[row * A + lane] = a;
-      if (lane == 0) {
+      if (traj.obs != nullptr && c.sl < LPE)
+        for (int i = c.sl; i < D; i += LPE) traj.obs[row * D + i] = w.obs[i];
+      if (traj.actions != nullptr && c.sl < A) static_cast<float*>(traj.actions)[row * A + c.sl] = a;
+      if (c.sl == 0) {
         if (traj.reward != nullptr) traj.reward[row] = reward;
         if (traj.done != nullptr) traj.done[row] = done ? 1 : 0;
       }
@@ -418,106 +446,110 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayout& s
     __syncwarp();
   }
   // write back: state row (coalesced through the scratch), obs, scalars
-  if (c.is_link) write_link(w.ls, lane, s);
+  if (c.is_link) write_link(w.ls, c.sl, s);
   __syncwarp();
-  row_s2g(state_row, w.ls, seg.state_words, lane);
-  for (int i = lane; i < D; i += 32) {
-    const float v = w.obs[i];
-    seg.obs[(size_t)env * D + i] = v;
-    for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
-  }
-  if (lane == 0) {
-    seg.reward[env] = reward;
-    seg.terminated[env] = done ? 1 : 0;  // CARL maps brax `done` (incl. the time limit) to terminated
-    seg.truncated[env] = 0;              // and truncated = False always (wrappers.py:75-78)
-    seg.elapsed[env] = el;
+  if (active && c.sl < LPE) {
+    for (int i = c.sl; i < words; i += LPE) state_row[i] = w.ls[i];
+    for (int i = c.sl; i < D; i += LPE) {
+      const float v = w.obs[i];
+      seg.obs[(size_t)env * D + i] = v;
+      for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
+    }
+    if (c.sl == 0) {
+      seg.reward[env] = reward;
+      seg.terminated[env] = done ? 1 : 0;  // CARL maps brax `done` (incl. the time limit) to terminated
+      seg.truncated[env] = 0;              // and truncated = False always (wrappers.py:75-78)
+      seg.elapsed[env] = el;
+    }
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 4) brax_step_kernel(const __grid_constant__ BraxSeg seg, const float* actions,
-                                                             int n_steps, uint64_t policy_seed, uint32_t step_base,
-                                                             const carlb_traj_t traj, int stock_contact) {
+template <int W, int E>
+__global__ void __launch_bounds__(W * 32, W == 4 ? 4 : 2) brax_step_kernel(const __grid_constant__ BraxSeg seg,
+                                                                          const float* actions, int n_steps,
+                                                                          uint64_t policy_seed, uint32_t step_base,
+                                                                          const carlb_traj_t traj, int stock_contact) {
+  typedef SmemLayoutT<W, E> SmemLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * kWarpsPerCta + warp;
-  if (env < seg.n) brax_step_body(seg, sm, env, warp, lane, actions, n_steps, policy_seed, step_base, traj, stock_contact);
+  const int warp = threadIdx.x >> 5;
+  if ((blockIdx.x * W + warp) * E < seg.n)  // warp-uniform: at least one sub-env of this warp is real
+    brax_step_body<W, E>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact);
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
 // ------------------------------------------------------------------------------ reset
 // Env.reset: q = init_q + U(+-noise), qd = noise * N(0,1) (Hopper: both uniform), forward
-// kinematics (pipeline_init), obs; stores the first state/obs for AutoResetWrapper.
-__device__ __forceinline__ void brax_reset_body(const BraxSeg& seg, SmemLayout& sm, int env, int warp, int lane,
-                                                const uint8_t* mask, const float* q_in, const float* qd_in) {
-  if (mask != nullptr && mask[env] == 0) {
-    // not reset: with a fused gather attached the current row still has to reach the new slot
-    for (int r = 0; r < seg.n_peers; ++r)
-      for (int i = lane; i < seg.obs_dim; i += 32)
-        seg.peer_obs[r][(size_t)(seg.global_offset + env) * seg.obs_dim + i] = seg.obs[(size_t)env * seg.obs_dim + i];
-    return;
-  }
-  const float* sys = sm.sys;
-  WarpScratch& w = sm.warp[warp];
-  const LaneCtx c = make_lane_ctx(sys, seg.ctx + (size_t)env * seg.n_ctx, seg.n_ctx, lane, true);
-  const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
-  const uint64_t gid = (uint64_t)(seg.global_offset + env);
-  const uint32_t episode = (uint32_t)seg.episode[env];
-  const float noise = sys[H_RESET_NOISE];
-  const bool hopper = (int)sys[H_ENV] == ENV_HOPPER;
-  if (lane < nq) {
-    w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
-                                  : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
-  }
-  if (lane < nqd) {
-    w.qd[lane] = (qd_in != nullptr) ? qd_in[(size_t)env * nqd + lane]
-                 : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -noise, noise)
-                                    : noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
-  }
-  __syncwarp();
-  // forward kinematics down the tree (parents have smaller indices)
-  LinkState s;
-  s.pos = v3(0, 0, 0); s.rot = q4(1, 0, 0, 0); s.vel = v3(0, 0, 0); s.ang = v3(0, 0, 0);
-  for (int l = 0; l < c.L; ++l) {
-    if (lane == l) {
-      const bool world_parent = c.parent < 0;
-      const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      s = forward_link(sys, c.lt, w.q, w.qd, world_parent, c.plt, ps);
-      write_link(w.ls, lane, s);
-    }
-    __syncwarp();
-  }
-  compute_obs(sys, c, w, s, lane);
-  const int D = seg.obs_dim;
-  for (int i = seg.state_words - 3 + lane; i < seg.state_words; i += 32)
-    if (i >= c.L * LINK_WORDS) w.ls[i] = 0.0f;  // padding words
-  __syncwarp();
-  row_s2g(seg.state + (size_t)env * seg.state_words, w.ls, seg.state_words, lane);
-  row_s2g(seg.first_state + (size_t)env * seg.state_words, w.ls, seg.state_words, lane);
-  for (int i = lane; i < D; i += 32) {
-    const float v = w.obs[i];
-    seg.obs[(size_t)env * D + i] = v;
-    seg.first_obs[(size_t)env * D + i] = v;
-    for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
-  }
-  if (lane == 0) {
-    seg.reward[env] = 0.0f;
-    seg.terminated[env] = 0;
-    seg.truncated[env] = 0;
-    seg.elapsed[env] = 0;
-    seg.episode[env] = (uint64_t)episode + 1ull;
-  }
-}
-
-__global__ void __launch_bounds__(kThreads) brax_reset_kernel(const __grid_constant__ BraxSeg seg, const uint8_t* mask,
-                                                              const float* q_in, const float* qd_in) {
+// kinematics (pipeline_init), obs; stores the first state/obs for AutoResetWrapper. One env per warp.
+__global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__ BraxSeg seg, const uint8_t* mask,
+                                                         const float* q_in, const float* qd_in) {
+  typedef SmemLayoutT<4, 1> SmemLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int env = blockIdx.x * kWarpsPerCta + warp;
-  if (env < seg.n) brax_reset_body(seg, sm, env, warp, lane, mask, q_in, qd_in);
+  const int env = blockIdx.x * 4 + warp;
+  if (env < seg.n) {
+    if (mask != nullptr && mask[env] == 0) {
+      // not reset: with a fused gather attached the current row still has to reach the new slot
+      for (int r = 0; r < seg.n_peers; ++r)
+        for (int i = lane; i < seg.obs_dim; i += 32)
+          seg.peer_obs[r][(size_t)(seg.global_offset + env) * seg.obs_dim + i] = seg.obs[(size_t)env * seg.obs_dim + i];
+    } else {
+      const float* sys = sm.sys;
+      EnvScratch& w = sm.env[warp];
+      const LaneCtx c = make_lane_ctx<1>(sys, seg, w, env, true, 0, lane, true);
+      const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
+      const uint64_t gid = (uint64_t)(seg.global_offset + env);
+      const uint32_t episode = (uint32_t)seg.episode[env];
+      const float noise = sys[H_RESET_NOISE];
+      const bool hopper = (int)sys[H_ENV] == ENV_HOPPER;
+      if (lane < nq) {
+        w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
+                                      : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
+      }
+      if (lane < nqd) {
+        w.qd[lane] = (qd_in != nullptr) ? qd_in[(size_t)env * nqd + lane]
+                     : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -noise, noise)
+                                        : noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
+      }
+      __syncwarp();
+      // forward kinematics down the tree (parents have smaller indices)
+      LinkState s;
+      s.pos = v3(0, 0, 0); s.rot = q4(1, 0, 0, 0); s.vel = v3(0, 0, 0); s.ang = v3(0, 0, 0);
+      for (int l = 0; l < c.L; ++l) {
+        if (lane == l) {
+          const bool world_parent = c.parent < 0;
+          const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
+          s = forward_link(sys, c.lt, w.q, w.qd, world_parent, c.plt, ps);
+          write_link(w.ls, lane, s);
+        }
+        __syncwarp();
+      }
+      compute_obs<1>(sys, c, w, s);
+      const int D = seg.obs_dim;
+      for (int i = c.L * LINK_WORDS + lane; i < seg.state_words; i += 32) w.ls[i] = 0.0f;  // padding words
+      __syncwarp();
+      for (int i = lane; i < seg.state_words; i += 32) {
+        seg.state[(size_t)env * seg.state_words + i] = w.ls[i];
+        seg.first_state[(size_t)env * seg.state_words + i] = w.ls[i];
+      }
+      for (int i = lane; i < D; i += 32) {
+        const float v = w.obs[i];
+        seg.obs[(size_t)env * D + i] = v;
+        seg.first_obs[(size_t)env * D + i] = v;
+        for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
+      }
+      if (lane == 0) {
+        seg.reward[env] = 0.0f;
+        seg.terminated[env] = 0;
+        seg.truncated[env] = 0;
+        seg.elapsed[env] = 0;
+        seg.episode[env] = (uint64_t)episode + 1ull;
+      }
+    }
+  }
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
@@ -644,7 +676,49 @@ static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what) {
   return CARLB_OK;
 }
 
-static inline int brax_grid(int n) { return (n + kWarpsPerCta - 1) / kWarpsPerCta; }
+static inline int brax_grid(int n, int envs_per_cta) { return (n + envs_per_cta - 1) / envs_per_cta; }
+
+// Envs packed per warp for the step / rollout kernels: 3 when the body has at most 10 links (Ant 9,
+// Halfcheetah 7, Hopper 4), else 1. CARLB_BRAX_PACK=1|3 overrides.
+static int brax_pack(const float* table) {
+  static const int forced = [] {
+    const char* e = getenv("CARLB_BRAX_PACK");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  const int L = (int)table[H_N_LINKS];
+  if (forced == 1) return 1;
+  return L <= Lanes<3>::LPE ? 3 : 1;
+}
+
+template <int W, int E>
+static cudaError_t launch_brax_step_we(const BraxSeg& seg, int n, const float* actions, int n_steps, uint64_t policy_seed,
+                                       uint32_t step_base, const carlb_traj_t& tj, int stock_contact, cudaStream_t st) {
+  typedef SmemLayoutT<W, E> Smem;
+  static bool configured = false;
+  if (!configured) {  // > 48 KB of dynamic shared memory needs the opt-in attribute
+    cudaError_t e = cudaFuncSetAttribute(brax_step_kernel<W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  brax_step_kernel<W, E><<<brax_grid(n, W * E), W * 32, sizeof(Smem), st>>>(seg, actions, n_steps, policy_seed, step_base, tj,
+                                                                          stock_contact);
+  return cudaGetLastError();
+}
+
+static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, const float* actions, int n_steps,
+                                    uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& tj, cudaStream_t st) {
+  const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
+  const int n = env->n;
+  const int E = brax_pack(h->host_table);
+  // 4 warps/CTA x 4 CTAs/SM by default; for large batches CTAs of 7 warps (2 per SM) keep the
+  // grid close to a whole number of waves of 148 SMs
+  if (E == 3) {
+    if (n >= 12288) return launch_brax_step_we<7, 3>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
+    return launch_brax_step_we<4, 3>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
+  }
+  if (n >= 4096) return launch_brax_step_we<7, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
+  return launch_brax_step_we<4, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
+}
 
 int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
   BraxHandle* h = static_cast<BraxHandle*>(env->brax_sys);
@@ -657,7 +731,7 @@ int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, c
   BraxSeg seg;
   int rc = make_brax_seg(env, seg, "carlb_env_reset");
   if (rc != CARLB_OK) return rc;
-  brax_reset_kernel<<<brax_grid(env->n), kThreads, sizeof(SmemLayout), st>>>(seg, mask, q, qd);
+  brax_reset_kernel<<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1>), st>>>(seg, mask, q, qd);
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;
@@ -672,12 +746,9 @@ int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStre
   BraxSeg seg;
   int rc = make_brax_seg(env, seg, "carlb_env_step");
   if (rc != CARLB_OK) return rc;
-  const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
   carlb_traj_t tj{};
-  brax_step_kernel<<<brax_grid(env->n), kThreads, sizeof(SmemLayout), st>>>(seg, static_cast<const float*>(actions), 1, 0, 0,
-                                                                            tj, h->stock_contact);
+  CARLB_CUDA_CHECK(launch_brax_step(env, seg, static_cast<const float*>(actions), 1, 0, 0, tj, st));
   g_launches++;
-  CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;
 }
 
@@ -688,14 +759,11 @@ int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32
   int rc = make_brax_seg(env, seg, "carlb_env_rollout");
   if (rc != CARLB_OK) return rc;
   if (n_steps == 0) return CARLB_OK;
-  const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
   carlb_traj_t tj{};
   if (traj != nullptr) tj = *traj;
   seg.final_obs = nullptr;
-  brax_step_kernel<<<brax_grid(env->n), kThreads, sizeof(SmemLayout), st>>>(seg, static_cast<const float*>(actions), n_steps,
-                                                                            policy_seed, step_base, tj, h->stock_contact);
+  CARLB_CUDA_CHECK(launch_brax_step(env, seg, static_cast<const float*>(actions), n_steps, policy_seed, step_base, tj, st));
   g_launches++;
-  CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;
 }
 

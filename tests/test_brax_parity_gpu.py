@@ -224,3 +224,43 @@ def test_full_size_properties_config4():
     assert torch.isfinite(t1["obs"]).all() and torch.isfinite(t1["reward"]).all()
     z = t1["obs"][..., 0]
     assert 0.15 < z.min().item() and z.max().item() < 1.5
+
+
+PACK_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r})
+from carl_b200.envs import CARLBraxAnt, CARLBraxHopper
+out = {{}}
+for cls, name in ((CARLBraxAnt, "ant"), (CARLBraxHopper, "hopper")):
+    env = cls(num_envs=301, max_episode_steps=7)   # ragged vs both 12- and 4-env CTAs, short episodes
+    env.reset(seed=3)
+    t = env.rollout(24, policy_seed=5, record=True)
+    acts = (torch.rand(301, env._info.act_dim, generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
+    o, r, te, tr, _ = env.step(acts)
+    out[name + "_obs"] = t["obs"].cpu().numpy(); out[name + "_rew"] = t["reward"].cpu().numpy()
+    out[name + "_done"] = t["done"].cpu().numpy(); out[name + "_step"] = o["obs"].cpu().numpy()
+    out[name + "_state"] = env.state.cpu().numpy()
+np.savez(sys.argv[1], **out)
+"""
+
+
+def test_packed_lanes_equal_one_env_per_warp(tmp_path):
+    """Three envs per warp (E = 3) must be BIT-identical to one env per warp (E = 1): the lane
+    mapping changes, the per-link arithmetic does not."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pack.py"
+    script.write_text(PACK_SCRIPT.format(root=root))
+    res = {}
+    for pack in ("1", "3"):
+        out = tmp_path / f"pack{pack}.npz"
+        env = dict(os.environ, CARLB_BRAX_PACK=pack)
+        p = subprocess.run([sys.executable, str(script), str(out)], env=env, capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-2000:]
+        res[pack] = np.load(out)
+    for k in res["1"].files:
+        np.testing.assert_array_equal(res["1"][k], res["3"][k], err_msg=k)
+    assert res["1"]["ant_done"].sum() > 0
