@@ -164,7 +164,7 @@ class CARLBraxEnv(CARLEnv):
         obs_t = self._obs  # device copy of the same observation
         vel = obs_t[:, g["idx"]].to(torch.float64)
         g["position"], r, reached = brax_goals.goal_step(g["position"], g["goal"], g["radius"], vel, g["dt"])
-        te_t = self._terminated.view(torch.bool) | reached
+        te_t = self._terminated_b | reached
         info["success"] = reached.to(torch.int64)
         if host:
             reward, te = r.cpu().numpy(), te_t.cpu().numpy()

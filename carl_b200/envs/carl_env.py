@@ -364,6 +364,8 @@ class CARLEnv(abc.ABC):
         self._reward = self._out[ob:ob + rb].view(torch.float32)
         self._terminated = self._out[ob + rb:ob + rb + n]
         self._truncated = self._out[ob + rb + n:ob + rb + 2 * n]
+        self._terminated_b = self._terminated.view(torch.bool)  # cached views: step() returns these
+        self._truncated_b = self._truncated.view(torch.bool)
         self._final_obs = z(n, info.obs_dim, dtype=torch.float32)
         self._first_state = z(n, info.state_words, dtype=torch.float32) if is_brax else None
         self._first_obs = z(n, info.obs_dim, dtype=torch.float32) if is_brax else None
@@ -530,7 +532,7 @@ class CARLEnv(abc.ABC):
                 action = action.to(torch.float32)
             action = action.contiguous()
             _native.check(self._lib.carlb_env_step(self._handle, action.data_ptr(), _TORCH_ACT[action.dtype], self._stream()))
-            obs, rew, term, trunc = self._obs, self._reward, self._terminated.view(torch.bool), self._truncated.view(torch.bool)
+            obs, rew, term, trunc = self._obs, self._reward, self._terminated_b, self._truncated_b
             state = self._add_context_to_state(obs)
             info = {"context_id": self.context_id}
             if self._autoreset:

@@ -51,6 +51,6 @@ class MixedBatch:
         outs = []
         for e in self.envs:
             state = e._add_context_to_state(e._obs)
-            outs.append((state, e._reward, e._terminated.view(torch.bool), e._truncated.view(torch.bool),
+            outs.append((state, e._reward, e._terminated_b, e._truncated_b,
                          {"context_id": e.context_id}))
         return outs
