@@ -465,7 +465,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
 }
 
 template <int W, int E>
-__global__ void __launch_bounds__(W * 32, W == 4 ? 4 : 2) brax_step_kernel(const __grid_constant__ BraxSeg seg,
+__global__ void __launch_bounds__(W * 32, W == 4 ? (E >= 3 ? 5 : 4) : 2) brax_step_kernel(const __grid_constant__ BraxSeg seg,
                                                                           const float* actions, int n_steps,
                                                                           uint64_t policy_seed, uint32_t step_base,
                                                                           const carlb_traj_t traj, int stock_contact) {
@@ -678,16 +678,19 @@ static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what) {
 
 static inline int brax_grid(int n, int envs_per_cta) { return (n + envs_per_cta - 1) / envs_per_cta; }
 
-// Envs packed per warp for the step / rollout kernels: 3 when the body has at most 10 links (Ant 9,
-// Halfcheetah 7, Hopper 4), else 1. CARLB_BRAX_PACK=1|3 overrides.
+// Envs packed per warp for the step / rollout kernels: the largest E in {4, 3, 1} whose 32/E lanes
+// hold the body's links and actuators (Halfcheetah 7 links / 6 actuators and Hopper 4 / 3 -> E = 4;
+// Ant 9 / 8 -> E = 3). CARLB_BRAX_PACK=1 forces one env per warp.
 static int brax_pack(const float* table) {
   static const int forced = [] {
     const char* e = getenv("CARLB_BRAX_PACK");
     return e != nullptr ? atoi(e) : 0;
   }();
-  const int L = (int)table[H_N_LINKS];
+  const int need = max((int)table[H_N_LINKS], (int)table[H_N_ACT]);
   if (forced == 1) return 1;
-  return L <= Lanes<3>::LPE ? 3 : 1;
+  if (need <= Lanes<4>::LPE && forced != 3) return 4;
+  if (need <= Lanes<3>::LPE) return 3;
+  return 1;
 }
 
 template <int W, int E>
@@ -708,16 +711,15 @@ static cudaError_t launch_brax_step_we(const BraxSeg& seg, int n, const float* a
 static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, const float* actions, int n_steps,
                                     uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& tj, cudaStream_t st) {
   const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
-  const int n = env->n;
-  const int E = brax_pack(h->host_table);
-  // 4 warps/CTA x 4 CTAs/SM by default; for large batches CTAs of 7 warps (2 per SM) keep the
-  // grid close to a whole number of waves of 148 SMs
-  if (E == 3) {
-    if (n >= 12288) return launch_brax_step_we<7, 3>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
-    return launch_brax_step_we<4, 3>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
+  const int n = env->n, sc = h->stock_contact;
+  switch (brax_pack(h->host_table)) {
+    case 4: return launch_brax_step_we<4, 4>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    case 3: return launch_brax_step_we<4, 3>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    default: break;
   }
-  if (n >= 4096) return launch_brax_step_we<7, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
-  return launch_brax_step_we<4, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, h->stock_contact, st);
+  // one env per warp: 7-warp CTAs (2 per SM) keep large grids close to whole waves of 148 SMs
+  if (n >= 4096) return launch_brax_step_we<7, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  return launch_brax_step_we<4, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
 }
 
 int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
