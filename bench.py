@@ -71,18 +71,23 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(rep: str):
-    """DRAM bytes per launch of the dominant kernel from the newest committed ncu --set full
-    summary (profiles/<tag>_traffic.json, written by tools/summarize_ncu.py), or None."""
+def measured_profile(rep: str):
+    """Counters of the dominant kernel from the newest committed ncu --set full summary
+    (profiles/<tag>_traffic.json, written by tools/summarize_ncu.py): (dict, file name) or ({}, None)."""
     d = os.path.join(ROOT, "profiles")
     try:
         files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json"))
         if not files:
-            return None, None
+            return {}, None
         j = json.load(open(os.path.join(d, files[-1])))
-        return float(j[rep]["dram_bytes_per_launch"]), files[-1]
+        return dict(j[rep]), files[-1]
     except Exception:
-        return None, None
+        return {}, None
+
+
+def measured_traffic(rep: str):
+    p, f = measured_profile(rep)
+    return (float(p["dram_bytes_per_launch"]) if "dram_bytes_per_launch" in p else None), f
 
 
 class ClockSampler:
@@ -439,6 +444,9 @@ def run_gpu_arm(args):
             "bytes_per_env_step": TRAJ_BYTES + STEP_CONTRACT_BYTES / T,
             "kernel_ms_avg": k_avg_ms,
             "frac_vs_step_contract_90B": (STEP_CONTRACT_BYTES * n_local * T / (k_avg_ms * 1e-3) / 1e9) / peak,
+            # the kernel is instruction-issue bound, not HBM bound, at this batch size (ncu, same command):
+            "issue_slot_utilisation_pct": measured_profile("prof_rollout")[0].get("issue_active_pct"),
+            "warps_active_pct": measured_profile("prof_rollout")[0].get("warps_active_pct"),
         },
         "step_api": {
             "value": api_value * world, "unit": UNIT, "steps": K_api, "us_per_launch": api_ms_per_launch * 1e3,

@@ -79,8 +79,18 @@ def full(tag, rep):
         vals = [float(r[rd]) * unit[units[rd]] + float(r[wr]) * unit[units[wr]] for r in rows[2:]]
         tp = os.path.join(PROF, f"{tag}_traffic.json")
         d = json.load(open(tp)) if os.path.exists(tp) else {}
+        def avg(name):
+            if name not in hdr:
+                return None
+            xs = [float(r[hdr.index(name)]) for r in rows[2:]]
+            return sum(xs) / len(xs)
+
         d[rep] = {"kernel": rows[2][hdr.index("Kernel Name")], "dram_bytes_per_launch": sum(vals) / len(vals),
-                  "launches_captured": len(vals)}
+                  "launches_captured": len(vals),
+                  "issue_active_pct": avg("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                  "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                  "warp_instructions_per_launch": avg("smsp__inst_executed.sum"),
+                  "duration_us_under_ncu": avg("gpu__time_duration.sum")}
         json.dump(d, open(tp, "w"), indent=1)
     except Exception as e:  # pragma: no cover
         print("traffic summary failed:", e)
