@@ -296,7 +296,7 @@ def run_gpu_arm(args):
         _native.check(lib.carlb_env_rollout(handle, T, 12345, step_base, None, _native.ACT_I32,
                                             ctypes.byref(trajs[i % n_slots]), stream.cuda_stream))
         if gather is not None:
-            gather.gather()
+            gather.gather(lag=1 if i > 0 else 0)
 
     def barrier():
         if distributed:
@@ -322,7 +322,7 @@ def run_gpu_arm(args):
                                             ctypes.byref(trajs[j % n_slots]), stream.cuda_stream))
         kev[j][1].record(stream)
         if gather is not None:
-            gather.gather()
+            gather.gather(lag=1)  # pipelined consumer: launch k+1 is enqueued before obs k is awaited
     ev1.record(stream)
     barrier()
     fused_ms = ev0.elapsed_time(ev1)
@@ -428,7 +428,7 @@ def run_gpu_arm(args):
             "n_envs": n_global, "fused_steps_per_launch": T, "launches": K // T,
             "l2": f"trajectory ring {n_slots} x {slot_bytes / 2**20:.0f} MiB > L2 (outputs go to DRAM); env state "
                   f"({n_local * 90 / 2**20:.1f} MiB working set) is register/L2 resident by design",
-            "collective": (f"obs all-gather per launch: {gather_mode}" + (" (in-kernel NVLink peer stores + flag wait)" if gather_mode == "fused" else "")) if distributed else "none",
+            "collective": (f"obs all-gather per launch: {gather_mode}" + (" (in-kernel NVLink peer stores + flag wait)" if gather_mode == "fused" else "") + ", consumed one launch behind (pipelined)") if distributed else "none",
         },
         "gpu_launches": int(launches),
         "clocks": clock_info,

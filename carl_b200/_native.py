@@ -97,7 +97,7 @@ def load() -> ctypes.CDLL:
     lib.carlb_gather_export.argtypes = [c_void_p, c_void_p]
     lib.carlb_gather_open.argtypes = [c_void_p, c_int, c_void_p]
     lib.carlb_gather_attach.argtypes = [c_void_p, c_void_p]
-    lib.carlb_gather_wait.argtypes = [c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.carlb_gather_wait.argtypes = [c_void_p, c_int, c_void_p, POINTER(c_void_p)]
     lib.carlb_gather_destroy.argtypes = [c_void_p]
     if lib.carlb_abi_version() != 1:
         raise NativeLibraryError(f"libcarlb ABI version {lib.carlb_abi_version()} != 1")

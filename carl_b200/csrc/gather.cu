@@ -134,17 +134,17 @@ int carlb_gather_attach(carlb_gather_t* g, carlb_env_t* env) {
   return CARLB_OK;
 }
 
-int carlb_gather_wait(carlb_gather_t* g, void* stream, float** gathered) {
-  if (g == nullptr || gathered == nullptr) {
-    set_error("carlb_gather_wait: null argument");
+int carlb_gather_wait(carlb_gather_t* g, int lag, void* stream, float** gathered) {
+  if (g == nullptr || gathered == nullptr || lag < 0 || lag > 1) {
+    set_error("carlb_gather_wait: null argument or lag not in {0, 1}");
     return CARLB_ERR_INVALID;
   }
-  if (g->launches == 0) {
-    set_error("carlb_gather_wait: no observation-producing launch has been issued yet");
+  if (g->launches <= (unsigned int)lag) {
+    set_error("carlb_gather_wait: only %u observation-producing launches issued, lag %d", g->launches, lag);
     return CARLB_ERR_STATE;
   }
   CARLB_CUDA_CHECK(cudaSetDevice(g->device));
-  const unsigned int k = g->launches - 1;
+  const unsigned int k = g->launches - 1 - (unsigned int)lag;
   const unsigned int* flags = reinterpret_cast<const unsigned int*>(g->base[g->rank] + flags_offset(g));
   gather_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(flags, g->world, k + 1);
   g_launches++;

@@ -47,13 +47,19 @@ class ObsGather:
         self.gathered = torch.zeros(env.global_num_envs, D, dtype=torch.float32, device=env.device)
         self._padded = None
         self._mine = None
+        self._pending = None
+        self._pending_buf = None
+        self._pending_src = None
+        self._alt = None
         if mode == "fused":
             self._setup_fused()
         elif mode != "nccl":
             raise ValueError(f"unknown gather mode {mode!r}")
 
-    def gather(self, obs=None):
-        """Returns the ``[N_global, D]`` tensor of the latest observation-producing call.
+    def gather(self, obs=None, lag: int = 0):
+        """Returns the ``[N_global, D]`` tensor of the latest observation-producing call (``lag=0``)
+        or of the one before it (``lag=1``: a pipelined consumer enqueues launch k+1 first and then
+        asks for launch k, so neither the fused wait nor the NCCL collective stalls the stream).
 
         nccl: collective on the current stream. fused: the rows were already stored into every
         rank's buffer by the step/reset/rollout kernel itself; only a one-warp wait kernel is enqueued
@@ -66,10 +72,27 @@ class ObsGather:
             from carl_b200 import _native
 
             ptr = ctypes.c_void_p()
-            _native.check(self._lib.carlb_gather_wait(self._g, torch.cuda.current_stream(self.env.device).cuda_stream,
+            _native.check(self._lib.carlb_gather_wait(self._g, int(lag), torch.cuda.current_stream(self.env.device).cuda_stream,
                                                       ctypes.byref(ptr)))
             return self._views[ptr.value]
         obs = self.env._obs if obs is None else obs
+        if lag == 1 and self.equal:
+            # pipelined NCCL: start this launch's collective asynchronously into the other buffer and
+            # hand back the previous one (completed meanwhile)
+            import torch
+
+            if self._pending is None:
+                self._alt = torch.zeros_like(self.gathered)
+            prev, prev_buf = self._pending, self._pending_buf
+            buf = self._alt if self._pending_buf is self.gathered else self.gathered
+            src = obs.clone()  # the env's obs buffer is overwritten by the next launch
+            self._pending = self.dist.all_gather_into_tensor(buf, src, group=self.group, async_op=True)
+            self._pending_buf, self._pending_src = buf, src
+            if prev is None:
+                self._pending.wait()
+                return buf
+            prev.wait()
+            return prev_buf
         if self.equal:
             self.dist.all_gather_into_tensor(self.gathered, obs, group=self.group)
         else:

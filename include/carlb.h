@@ -186,7 +186,10 @@ int carlb_gather_create(int device, int rank, int world, int64_t n_global, int o
 int carlb_gather_export(carlb_gather_t* g, void* handle64 /* HOST, 64 bytes out */);
 int carlb_gather_open(carlb_gather_t* g, int peer_rank, const void* handle64 /* HOST, 64 bytes */);
 int carlb_gather_attach(carlb_gather_t* g, carlb_env_t* env);
-int carlb_gather_wait(carlb_gather_t* g, void* stream, float** gathered /* HOST out: DEVICE pointer */);
+/* lag = 0: the gathered tensor of the latest observation-producing launch; lag = 1: of the one
+ * before it (its slot stays intact until the launch after next) -- a pipelined consumer can enqueue
+ * launch k+1 first and then wait for launch k, so the wait never stalls the stream. */
+int carlb_gather_wait(carlb_gather_t* g, int lag, void* stream, float** gathered /* HOST out: DEVICE pointer */);
 int carlb_gather_destroy(carlb_gather_t* g);
 
 /* Counters of kernels launched through this library since load (bench `gpu_launches`). */

@@ -52,6 +52,14 @@ def main():
         ref.rollout(17, policy_seed=3)
         G = g.gather()
         assert torch.equal(G, ref._obs), f"{mode}: rollout gather mismatch"
+        # pipelined consumer: enqueue the next launch, then ask for the previous one (lag = 1)
+        if mode == "fused" or (n % world == 0):
+            prev = ref._obs.clone()
+            env.rollout(5, policy_seed=4)
+            ref.rollout(5, policy_seed=4)
+            G1 = g.gather(lag=1)
+            assert torch.equal(G1, prev), f"{mode}: lag-1 gather mismatch"
+            assert torch.equal(g.gather(), ref._obs), f"{mode}: lag-0 after lag-1 mismatch"
         say(rank, f"mode {mode}: rollout ok")
         # masked reset: rows that are not reset must still reach the new slot
         mask_full = (np.arange(n) % 3 == 0)
