@@ -540,7 +540,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="carl_b200", choices=["carl_b200", "reference"])
-    ap.add_argument("--fuse", type=int, default=100, help="env-steps fused per rollout launch")
+    ap.add_argument("--fuse", type=int, default=500, help="env-steps fused per rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ant", action="store_true")
