@@ -177,6 +177,7 @@ int carlb_env_create(int kind, int n_envs, int precision, int device, int64_t gl
 
 int carlb_env_destroy(carlb_env_t* env) {
   if (env == nullptr) return CARLB_OK;
+  if (env->gather != nullptr) gather_forget_env(env->gather, env);
   if (is_brax(env->kind)) brax_destroy(env);
   delete env;
   return CARLB_OK;

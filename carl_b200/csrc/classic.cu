@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kBlock) mixed_step_kernel(const __grid_constan
 // (optional sinks, optional given actions).
 template <int KIND, typename T, bool REC>
 __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
-                                             uint32_t step_base, const void* actions, const carlb_traj_t& traj) {
+                                             uint32_t step_base, const void* actions, const carlb_traj_t& traj,
+                                             int refill_threshold) {
   typedef Traits<KIND> Tr;
   const int n = seg.n;
   T s[Tr::S];
@@ -234,7 +235,7 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   // PCG64 stream is consumed in exactly the same order as a step-by-step run (the draw merely
   // happens earlier); a pre-generated but unused reset is rolled back at kernel exit. Acrobot with
   // torque noise interleaves per-step draws on the same stream, so it keeps the in-place path.
-  constexpr int kRefill = 8;
+  const int kRefill = refill_threshold;
   bool batch_resets = seg.autoreset != CARLB_AUTORESET_NONE;
   if (KIND == KIND_ACROBOT) batch_resets = false;
   const unsigned lanes = __activemask();
@@ -318,9 +319,9 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
 template <int KIND, typename T, bool REC>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
                                                          uint64_t policy_seed, uint32_t step_base, const void* actions,
-                                                         const carlb_traj_t traj) {
+                                                         const carlb_traj_t traj, int refill_threshold) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) rollout_body<KIND, T, REC>(seg, i, n_steps, policy_seed, step_base, actions, traj);
+  if (i < seg.n) rollout_body<KIND, T, REC>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold);
   // ONE call site reached by every thread of the CTA: the epilogue contains an aligned barrier,
   // which must not be executed from divergent code (ragged tail warps)
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
@@ -419,17 +420,28 @@ int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uin
   if (traj != nullptr) tj = *traj;
   // 64-thread blocks: at N = 65 536 that is 1024 blocks ~ 6.9 per SM (better tail balance over
   // 148 SMs than 128-thread blocks for a long-running per-thread loop)
-  constexpr int kRolloutBlock = 64;
+  // (CARLB_ROLLOUT_BLOCK / CARLB_ROLLOUT_REFILL override the block size and the batched-reset refill
+  // threshold for A/B measurements)
+  static const int kRolloutBlock = [] {
+    const char* e = getenv("CARLB_ROLLOUT_BLOCK");
+    const int v = e != nullptr ? atoi(e) : 64;
+    return (v == 32 || v == 64 || v == 128) ? v : 64;
+  }();
+  static const int kRefillThreshold = [] {
+    const char* e = getenv("CARLB_ROLLOUT_REFILL");
+    const int v = e != nullptr ? atoi(e) : 8;
+    return (v >= 1 && v <= 32) ? v : 8;
+  }();
   const int grid = (env->n + kRolloutBlock - 1) / kRolloutBlock;
   const bool rec = actions == nullptr && tj.obs != nullptr && tj.actions != nullptr && tj.reward != nullptr && tj.done != nullptr;
   if (rec) {
     CARLB_DISPATCH_KIND_T(env->kind, env->precision,
                           (rollout_kernel<K_, T_, true><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
-                                                                                        actions, tj)));
+                                                                                        actions, tj, kRefillThreshold)));
   } else {
     CARLB_DISPATCH_KIND_T(env->kind, env->precision,
                           (rollout_kernel<K_, T_, false><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
-                                                                                         actions, tj)));
+                                                                                         actions, tj, kRefillThreshold)));
   }
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());

@@ -31,6 +31,7 @@ void set_error(const char* fmt, ...);
 Segment make_segment(const carlb_env* env, int act_dtype);
 
 // gather.cu
+void gather_forget_env(carlb_gather* g, carlb_env* env);
 void gather_fill(carlb_gather* g, int* n_peers, float** peer_obs, unsigned int** peer_flags, unsigned int* signal_value,
                  unsigned int** block_counter);
 

@@ -27,9 +27,17 @@ struct carlb_gather {
   unsigned char* base[CARLB_MAX_PEERS] = {};  // base[r]: rank r's allocation mapped in this process
   bool opened[CARLB_MAX_PEERS] = {};
   unsigned int launches = 0;  // obs-producing launches issued so far
+  carlb_env* attached[CARLB_MAX_MIXED] = {};  // handles whose kernels write into this gather
+  int n_attached = 0;
 };
 
 namespace carlb {
+
+// called by carlb_env_destroy: forget a handle that goes away before its gather
+void gather_forget_env(carlb_gather* g, carlb_env* env) {
+  for (int i = 0; i < g->n_attached; ++i)
+    if (g->attached[i] == env) g->attached[i] = nullptr;
+}
 
 static size_t flags_offset(const carlb_gather* g) { return 2 * g->slot_floats * sizeof(float); }
 static size_t total_bytes(const carlb_gather* g) {
@@ -130,6 +138,16 @@ int carlb_gather_attach(carlb_gather_t* g, carlb_env_t* env) {
     set_error("carlb_gather_attach: obs_dim / device mismatch");
     return CARLB_ERR_INVALID;
   }
+  if (env->gather == g) return CARLB_OK;
+  if (env->gather != nullptr) {
+    set_error("carlb_gather_attach: the handle already has a gather attached");
+    return CARLB_ERR_STATE;
+  }
+  if (g->n_attached >= CARLB_MAX_MIXED) {
+    set_error("carlb_gather_attach: too many handles attached");
+    return CARLB_ERR_STATE;
+  }
+  g->attached[g->n_attached++] = env;
   env->gather = g;
   return CARLB_OK;
 }
@@ -155,7 +173,10 @@ int carlb_gather_wait(carlb_gather_t* g, int lag, void* stream, float** gathered
 
 int carlb_gather_destroy(carlb_gather_t* g) {
   if (g == nullptr) return CARLB_OK;
+  for (int i = 0; i < g->n_attached; ++i)  // the handles must not keep pointing at freed buffers
+    if (g->attached[i] != nullptr && g->attached[i]->gather == g) g->attached[i]->gather = nullptr;
   cudaSetDevice(g->device);
+  cudaDeviceSynchronize();  // no kernel may still be storing into the buffers that are unmapped below
   for (int r = 0; r < g->world; ++r) {
     if (r == g->rank) continue;
     if (g->opened[r] && g->base[r]) cudaIpcCloseMemHandle(g->base[r]);
