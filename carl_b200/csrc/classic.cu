@@ -230,7 +230,7 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   // 128-bit jump-ahead multiplies + S PCG64 draws); under a random policy ~5% of the envs of a warp
   // reset each step, i.e. ~80% of the warp-iterations would execute that divergent path for one or
   // two lanes. Instead every lane keeps its NEXT reset state ready in registers; consuming it is a
-  // few moves, and the warp regenerates the missing ones together once kRefill lanes need one, so
+  // few moves, and the warp regenerates the missing ones together once `refill_threshold` (16) lanes need one, so
   // the expensive path runs ~5x less often at several times the lane utilisation. The per-env
   // PCG64 stream is consumed in exactly the same order as a step-by-step run (the draw merely
   // happens earlier); a pre-generated but unused reset is rolled back at kernel exit. Acrobot with
@@ -429,8 +429,8 @@ int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uin
   }();
   static const int kRefillThreshold = [] {
     const char* e = getenv("CARLB_ROLLOUT_REFILL");
-    const int v = e != nullptr ? atoi(e) : 8;
-    return (v >= 1 && v <= 32) ? v : 8;
+    const int v = e != nullptr ? atoi(e) : 16;  // sweep on B200 (profiles/r01j_sweep.txt): 4 -> 0.332, 8 -> 0.286, 16 -> 0.278 ms
+    return (v >= 1 && v <= 32) ? v : 16;
   }();
   const int grid = (env->n + kRolloutBlock - 1) / kRolloutBlock;
   const bool rec = actions == nullptr && tj.obs != nullptr && tj.actions != nullptr && tj.reward != nullptr && tj.done != nullptr;
