@@ -304,6 +304,9 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
     const bool hz = (sys[H_HEALTHY_Z_MIN] < after.z) && (after.z < sys[H_HEALTHY_Z_MAX]);
     const bool ha = (sys[H_ANGLE_MIN] < after.angle) && (after.angle < sys[H_ANGLE_MAX]);
     healthy = after.state_ok && hz && ha;
+  } else if (kind == ENV_WALKER2D) {
+    healthy = !(after.z < sys[H_HEALTHY_Z_MIN]) && !(after.z > sys[H_HEALTHY_Z_MAX]) &&
+              !(after.angle > sys[H_ANGLE_MAX]) && !(after.angle < sys[H_ANGLE_MIN]);
   }
   const float ctrl_cost = sys[H_CTRL_COST] * act_sq_sum;
   reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
@@ -504,7 +507,7 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
       const uint64_t gid = (uint64_t)(seg.global_offset + env);
       const uint32_t episode = (uint32_t)seg.episode[env];
       const float noise = sys[H_RESET_NOISE];
-      const bool hopper = (int)sys[H_ENV] == ENV_HOPPER;
+      const bool hopper = sys[H_QD_UNIFORM] > 0.0f;  // Hopper / Walker2d: qd ~ U(+-noise) instead of noise * N(0,1)
       if (lane < nq) {
         w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
                                       : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
@@ -566,6 +569,7 @@ static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
   switch (kind) {
     case KIND_BRAX_ANT: L = 9; nq = 15; nqd = 14; A = 8; break;
     case KIND_BRAX_HALFCHEETAH: L = 7; nq = 9; nqd = 9; A = 6; break;
+    case KIND_BRAX_WALKER2D: L = 7; nq = 9; nqd = 9; A = 6; break;
     default: L = 4; nq = 6; nqd = 6; A = 3; break;
   }
 }

@@ -41,7 +41,7 @@ enum Hdr {
   H_STIFFNESS, H_VEL_DAMPING_C, H_LIMIT_STIFFNESS, H_ANG_DAMPING_C, H_BAUMGARTE, H_VEL_DAMPING, H_MASS_SCALE,
   H_INERTIA_SCALE,
   H_RESET_NOISE, H_CTRL_COST, H_HEALTHY_REWARD, H_HEALTHY_Z_MIN, H_HEALTHY_Z_MAX, H_FORWARD_WEIGHT, H_ANGLE_MIN,
-  H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS
+  H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS, H_QD_UNIFORM
 };
 enum LinkSlot {
   L_PARENT = 0, L_TYPE, L_QIDX, L_QDIDX, L_TPOS = 4, L_TROT = 7, L_JPOS = 11, L_JROT = 14, L_LIM_LO = 18, L_LIM_HI = 19,
@@ -49,7 +49,7 @@ enum LinkSlot {
   L_FIRST_PT = 35, L_N_PT = 36
 };
 enum LinkType { TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_PLANAR = 3 };
-enum EnvId { ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2 };
+enum EnvId { ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2, ENV_WALKER2D = 3 };
 // per-env context rows: gravity, friction, elasticity, ang_damping, joint-stiffness scale (the
 // legacy `joint_stiffness` feature of CARL's docs mapped onto the spring constraint stiffness,
 // 1 = stock), then one mass per link

@@ -8,5 +8,11 @@ from carl_b200.envs.classic_control import (  # noqa: F401
     CARLMountainCarContinuous,
     CARLPendulum,
 )
-from carl_b200.envs.brax import CARLBraxAnt, CARLBraxEnv, CARLBraxHalfcheetah, CARLBraxHopper  # noqa: F401,E402
+from carl_b200.envs.brax import (  # noqa: F401,E402
+    CARLBraxAnt,
+    CARLBraxEnv,
+    CARLBraxHalfcheetah,
+    CARLBraxHopper,
+    CARLBraxWalker2d,
+)
 from carl_b200.envs.mixed import MixedBatch  # noqa: F401,E402

@@ -299,3 +299,26 @@ class CARLBraxHopper(CARLBraxEnv):
         f["mass_foot"] = _uf("mass_foot", 1e-6, np.inf, 5.3155746)
         f.update(_goal_features())
         return f
+
+
+class CARLBraxWalker2d(CARLBraxEnv):
+    """``carl/envs/brax/carl_walker2d.py:14-67`` (same kernels, a new system table)."""
+
+    env_name: str = "walker2d"
+    kind = "brax_walker2d"
+    asset_path: str = "envs/assets/walker2d.xml"
+    metadata = {"render_modes": []}
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        f = _common_features()
+        f["viscosity"] = _uf("viscosity", 0, np.inf, 0)
+        f["mass_torso"] = _uf("mass_torso", 1e-6, np.inf, 10)
+        f["mass_thigh"] = _uf("mass_thigh", 1e-6, np.inf, 4.0578904)
+        f["mass_leg"] = _uf("mass_leg", 1e-6, np.inf, 2.7813568)
+        f["mass_foot"] = _uf("mass_foot", 1e-6, np.inf, 3.1667254)
+        f["mass_thigh_left"] = _uf("mass_thigh_left", 1e-6, np.inf, 4.0578904)
+        f["mass_leg_left"] = _uf("mass_leg_left", 1e-6, np.inf, 2.7813568)
+        f["mass_foot_left"] = _uf("mass_foot_left", 1e-6, np.inf, 3.1667254)
+        f.update(_goal_features())
+        return f

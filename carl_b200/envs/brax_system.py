@@ -36,7 +36,7 @@ H_N_LINKS, H_N_Q, H_N_QD, H_N_POINTS, H_N_FRAMES, H_DT, H_ENV, H_N_ACT = range(8
 (H_STIFFNESS, H_VEL_DAMPING_C, H_LIMIT_STIFFNESS, H_ANG_DAMPING_C, H_BAUMGARTE, H_VEL_DAMPING, H_MASS_SCALE,
  H_INERTIA_SCALE) = range(8, 16)
 (H_RESET_NOISE, H_CTRL_COST, H_HEALTHY_REWARD, H_HEALTHY_Z_MIN, H_HEALTHY_Z_MAX, H_FORWARD_WEIGHT, H_ANGLE_MIN,
- H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS) = range(16, 28)
+ H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS, H_QD_UNIFORM) = range(16, 29)
 TUNABLE_NAMES = ["constraint_stiffness", "constraint_vel_damping", "constraint_limit_stiffness",
                  "constraint_ang_damping", "baumgarte_erp", "vel_damping", "spring_mass_scale",
                  "spring_inertia_scale"]
@@ -46,7 +46,7 @@ TUNABLE_NAMES = ["constraint_stiffness", "constraint_vel_damping", "constraint_l
 L_TPOS, L_TROT, L_JPOS, L_JROT, L_LIM_LO, L_LIM_HI = 4, 7, 11, 14, 18, 19
 L_COM, L_IROT, L_IDIAG, L_MASS, L_GEAR, L_ACT, L_CTRL_LO, L_CTRL_HI, L_FIRST_PT, L_N_PT = 20, 23, 27, 30, 31, 32, 33, 34, 35, 36
 TYPE_FREE, TYPE_HINGE, TYPE_PLANAR = 0, 1, 3
-ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER = 0, 1, 2
+ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER, ENV_WALKER2D = 0, 1, 2, 3
 
 
 # ----------------------------------------------------------------------------- math
@@ -253,9 +253,42 @@ def hopper_model():
                       constraint_ang_damping=10.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
                       spring_inertia_scale=1.0),
         env_params=dict(reset_noise=5e-3, ctrl_cost=1e-3, healthy_reward=1.0, z_min=0.7, z_max=1e9, forward_weight=1.0,
-                        angle_min=-0.2, angle_max=0.2, exclude_pos=1, qd_clip=10.0, terminate=1.0),
+                        angle_min=-0.2, angle_max=0.2, exclude_pos=1, qd_clip=10.0, terminate=1.0, qd_uniform=1.0),
         stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0,
         actuator_links=["thigh", "leg", "foot"],
+    )
+
+
+def walker2d_model():
+    """Gym ``walker2d.xml`` in local coordinates (density 1000; hinges about (0,-1,0); gear 100).
+    The geometry is pinned by CARL's mass defaults (``carl/envs/brax/carl_walker2d.py:37-57``)."""
+    ax = (0, -1, 0)
+    deg = np.pi / 180
+
+    def leg(suffix, parent_of_thigh, foot_friction):
+        foot = capsule((0, 0, 0), (0.2, 0, 0), 0.06)
+        foot["friction"] = foot_friction
+        base = 1 if suffix == "" else 4
+        return [
+            _link(f"thigh{suffix}", parent_of_thigh, TYPE_HINGE, (0, 0, -0.2), [capsule((0, 0, 0), (0, 0, -0.45), 0.05)], axis=ax,
+                  limit=(-150 * deg, 0.0), gear=100.0),
+            _link(f"leg{suffix}", base, TYPE_HINGE, (0, 0, -0.45), [capsule((0, 0, 0), (0, 0, -0.5), 0.04)], axis=ax,
+                  limit=(-150 * deg, 0.0), gear=100.0),
+            _link(f"foot{suffix}", base + 1, TYPE_HINGE, (0, 0, -0.5), [foot], axis=ax, limit=(-45 * deg, 45 * deg), gear=100.0),
+        ]
+
+    links = [_link("torso", -1, TYPE_PLANAR, (0, 0, 1.25), [capsule((0, 0, 0.2), (0, 0, -0.2), 0.05)], axis=(0, 1, 0))]
+    links += leg("", 0, 0.9) + leg("_left", 0, 1.9)
+    return dict(
+        name="walker2d", env=ENV_WALKER2D, links=links, density=1000.0, total_mass=None, friction=1.0,
+        init_q=np.zeros(9), dt=0.002, n_frames=4,
+        tunables=dict(constraint_stiffness=30000.0, constraint_vel_damping=100.0, constraint_limit_stiffness=2000.0,
+                      constraint_ang_damping=10.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=5e-3, ctrl_cost=1e-3, healthy_reward=1.0, z_min=0.8, z_max=2.0, forward_weight=1.0,
+                        angle_min=-1.0, angle_max=1.0, exclude_pos=1, qd_clip=10.0, terminate=1.0, qd_uniform=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0,
+        actuator_links=["thigh", "leg", "foot", "thigh_left", "leg_left", "foot_left"],
     )
 
 
@@ -325,6 +358,7 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     t[H_HEALTHY_Z_MIN], t[H_HEALTHY_Z_MAX], t[H_FORWARD_WEIGHT] = ep["z_min"], ep["z_max"], ep["forward_weight"]
     t[H_ANGLE_MIN], t[H_ANGLE_MAX], t[H_EXCLUDE_POS], t[H_QD_CLIP] = ep["angle_min"], ep["angle_max"], ep["exclude_pos"], ep["qd_clip"]
     t[H_TERMINATE], t[H_MAX_CHILD_POINTS] = ep["terminate"], max_pts
+    t[H_QD_UNIFORM] = ep.get("qd_uniform", 0.0)  # Hopper / Walker2d draw qd uniformly, the others N(0,1)
     t[OFF_INIT_Q:OFF_INIT_Q + qi] = model["init_q"]
     stock_friction = float(np.max([p[3] for p in pts_all]))
     return dict(
@@ -337,5 +371,5 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     )
 
 
-MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model}
+MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model, "walker2d": walker2d_model}
 SYSTEMS = {k: build_system(f()) for k, f in MODELS.items()}

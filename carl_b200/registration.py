@@ -3,7 +3,7 @@
 from __future__ import annotations
 
 ENV_NAMES = ["CARLCartPole", "CARLPendulum", "CARLAcrobot", "CARLMountainCar", "CARLMountainCarContinuous",
-             "CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper"]
+             "CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d"]
 
 
 def register_envs(namespace: str = "carl_b200") -> list[str]:

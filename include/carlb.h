@@ -42,6 +42,7 @@ extern "C" {
 #define CARLB_BRAX_ANT 16         /* carl/envs/brax/carl_ant.py:14 */
 #define CARLB_BRAX_HALFCHEETAH 17 /* carl/envs/brax/carl_halfcheetah.py:14 */
 #define CARLB_BRAX_HOPPER 18      /* carl/envs/brax/carl_hopper.py:14 */
+#define CARLB_BRAX_WALKER2D 19    /* carl/envs/brax/carl_walker2d.py:14 (same kernels, new table) */
 
 /* state / context precision of a handle */
 #define CARLB_F32 0 /* throughput mode: fp32 state and context in HBM */

@@ -37,7 +37,7 @@ enum { hN_LINKS = 0, hN_Q, hN_QD, hN_POINTS, hN_FRAMES, hDT, hENV, hN_ACT, hK, h
 enum { lPARENT = 0, lTYPE, lQ, lQD, lTPOS = 4, lTROT = 7, lJPOS = 11, lJROT = 14, lLO = 18, lHI = 19, lCOM = 20,
        lIROT = 23, lIDIAG = 27, lMASS = 30, lGEAR = 31, lACT = 32, lCLO = 33, lCHI = 34, lFIRSTP = 35, lNP = 36 };
 enum { T_FREE = 0, T_HINGE = 1, T_PLANAR = 3 };
-enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2 };
+enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2, E_WALKER2D = 3 };
 
 /* Arithmetic type of the restatement: float (the reference's JAX pipeline) by default; built a
  * second time with -DORACLE_F64 as the round-off-free yardstick that tells float32 noise (stiff
@@ -481,6 +481,8 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
       for (int i = 2; i < nq; ++i) ok = ok && (q[i] > -100.0f) && (q[i] < 100.0f);
       for (int i = 0; i < nqd; ++i) ok = ok && (qd[i] > -100.0f) && (qd[i] < 100.0f);
       healthy = ok && (sys[hZMIN] < o1[2]) && (o1[2] < sys[hZMAX]) && (sys[hAMIN] < q[2]) && (q[2] < sys[hAMAX]);
+    } else if (env == E_WALKER2D) { /* brax walker2d: z and torso angle ranges, no state-range check */
+      healthy = !(o1[2] < sys[hZMIN]) && !(o1[2] > sys[hZMAX]) && !(q[2] > sys[hAMAX]) && !(q[2] < sys[hAMIN]);
     }
     real r = sys[hFWD] * xvel + sys[hHEALTHY] - sys[hCTRL] * act_sq;
     int done = (sys[hTERM] > 0.0f) && !healthy;

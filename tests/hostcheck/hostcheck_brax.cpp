@@ -130,6 +130,9 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     else if (kind == ENV_HOPPER)
       healthy = after[3] > 0.5f && sys[H_HEALTHY_Z_MIN] < after[1] && after[1] < sys[H_HEALTHY_Z_MAX] &&
                 sys[H_ANGLE_MIN] < after[2] && after[2] < sys[H_ANGLE_MAX];
+    else if (kind == ENV_WALKER2D)
+      healthy = !(after[1] < sys[H_HEALTHY_Z_MIN]) && !(after[1] > sys[H_HEALTHY_Z_MAX]) && !(after[2] > sys[H_ANGLE_MAX]) &&
+                !(after[2] < sys[H_ANGLE_MIN]);
     const float r = sys[H_FORWARD_WEIGHT] * xvel + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
     bool done = sys[H_TERMINATE] > 0.0f && !healthy;
     elapsed[e] += 1;

@@ -10,7 +10,8 @@ from oracle.brax import OracleBraxEnv
 from tests.brax_util import assert_close_scaled, random_q
 
 pytestmark = pytest.mark.gpu
-BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper"}
+BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper",
+          "walker2d": "CARLBraxWalker2d"}
 
 
 def make_env(body, n, rng, mode="applied", **kw):
@@ -196,7 +197,8 @@ def test_brax_api_shapes_and_batch_size():
     """test/test_brax_env.py + wrappers.py VectorGymWrapper shape contract."""
     import carl_b200.envs as E
 
-    for name, D, A in (("CARLBraxAnt", 27, 8), ("CARLBraxHalfcheetah", 17, 6), ("CARLBraxHopper", 11, 3)):
+    for name, D, A in (("CARLBraxAnt", 27, 8), ("CARLBraxHalfcheetah", 17, 6), ("CARLBraxHopper", 11, 3),
+                       ("CARLBraxWalker2d", 17, 6)):
         cls = getattr(E, name)
         env = cls(batch_size=5)
         env._progress_instance()
@@ -229,9 +231,10 @@ def test_full_size_properties_config4():
 PACK_SCRIPT = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, {root!r})
-from carl_b200.envs import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper
+from carl_b200.envs import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d
 out = {{}}
-for cls, name in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper")):
+for cls, name in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
+                  (CARLBraxWalker2d, "walker2d")):
     env = cls(num_envs=301, max_episode_steps=7)   # ragged vs both 12- and 4-env CTAs, short episodes
     env.reset(seed=3)
     t = env.rollout(24, policy_seed=5, record=True)

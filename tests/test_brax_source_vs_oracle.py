@@ -9,7 +9,7 @@ from carl_b200.envs import brax_system as bs
 from oracle.brax import OracleBraxEnv
 from tests.brax_util import BraxHostCheck, assert_close_scaled, random_ctx, random_q
 
-BODIES = ["ant", "halfcheetah", "hopper"]
+BODIES = ["ant", "halfcheetah", "hopper", "walker2d"]
 
 
 @pytest.fixture(scope="module")

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from carl_b200.envs import brax_system as bs
-from carl_b200.envs.brax import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper
+from carl_b200.envs.brax import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -30,6 +30,17 @@ def test_hopper_masses_match_carl_defaults():
     assert s["stock_masses"][0] == pytest.approx(3.6651914, rel=2e-7)  # CARL overrides it with 10
 
 
+def test_walker2d_masses_match_carl_defaults():
+    """carl/envs/brax/carl_walker2d.py:37-57: six leg-link masses pin the capsule geometry."""
+    s = bs.SYSTEMS["walker2d"]
+    d = CARLBraxWalker2d.get_context_space().get_default_context()
+    for name, m in zip(s["link_names"][1:], s["stock_masses"][1:]):
+        assert m == pytest.approx(d[f"mass_{name}"], rel=2e-7), name
+    assert s["stock_masses"][0] == pytest.approx(3.6651914, rel=2e-7)  # CARL overrides it with 10
+    assert (s["n_links"], s["n_q"], s["n_qd"], s["obs_dim"], s["n_act"]) == (7, 9, 9, 17, 6)
+    assert s["dt"] == pytest.approx(0.008)
+
+
 def test_shapes_match_reference_observation_sizes():
     a, h, p = bs.SYSTEMS["ant"], bs.SYSTEMS["halfcheetah"], bs.SYSTEMS["hopper"]
     assert (a["n_links"], a["n_q"], a["n_qd"], a["obs_dim"], a["n_act"]) == (9, 15, 14, 27, 8)  # obs f32[27]: notebook
@@ -39,7 +50,8 @@ def test_shapes_match_reference_observation_sizes():
 
 
 def test_every_mass_feature_names_a_link():
-    for cls, key in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper")):
+    for cls, key in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
+                     (CARLBraxWalker2d, "walker2d")):
         links = bs.SYSTEMS[key]["link_names"]
         for f in cls.get_context_features():
             if f.startswith("mass_"):

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from carl_b200.context import ContextSampler, UniformFloatContextFeature
-from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLPendulum, ContextTable, MixedBatch)
+from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d, CARLPendulum, ContextTable, MixedBatch)
 
 
 def table(cls, feats, n):
@@ -53,7 +53,8 @@ def main():
         out[f"config3_{name}_fused"] = {"env_steps_per_s": n * T / (ms * 1e-3), "ms_per_100_steps": ms}
     nb = 8192
     for cls, feats, name in ((CARLBraxHalfcheetah, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "halfcheetah"),
-                             (CARLBraxHopper, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "hopper")):
+                             (CARLBraxHopper, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "hopper"),
+                             (CARLBraxWalker2d, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "walker2d")):
         env = cls(contexts=table(cls, feats, nb), context_mode="applied")
         env.reset(seed=0)
         T = 20
