@@ -1,5 +1,7 @@
 // extern "C" surface of libcarlb (declared in include/carlb.h).
 #include <cuda_runtime.h>
+#include <limits>
+#include <type_traits>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -99,6 +101,23 @@ static int check_ready(const carlb_env* env, const char* what) {
 }  // namespace carlb
 
 using namespace carlb;
+
+// Host-side staging of a caller's (pageable) action array into the page-locked block the step reads:
+// ONE pass that copies and, for discrete spaces, range-checks (`assert self.action_space.contains(action)`
+// of the gymnasium envs, e.g. cartpole.py step) -- replaces a min, a max and a copy on the Python side.
+template <typename A>
+static bool stage_checked(A* __restrict__ dst, const A* __restrict__ src, int64_t count, uint64_t n_actions) {
+  typedef typename std::make_unsigned<A>::type U;  // as unsigned, a negative value exceeds every valid action
+  const U limit = n_actions > (uint64_t)std::numeric_limits<U>::max() ? std::numeric_limits<U>::max() : (U)n_actions;
+  const bool unbounded = n_actions > (uint64_t)std::numeric_limits<U>::max();
+  U bad = 0;
+  for (int64_t i = 0; i < count; ++i) {
+    const A v = src[i];
+    dst[i] = v;
+    bad |= (U)((U)v >= limit);
+  }
+  return unbounded || bad == 0;
+}
 
 extern "C" {
 
@@ -280,12 +299,21 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
   // Zero-copy path (classic envs, all five host buffers page-locked): the kernel reads the actions
   // from and writes the results to mapped host memory itself -- no staging copy, no four
   // device->host copies, the PCIe traffic overlaps the compute; one stream sync ends the call.
-  static const bool zero_copy = [] { const char* e = getenv("CARLB_ZEROCOPY"); return !(e && e[0] == '0'); }();
-  if (zero_copy && is_classic(env->kind) && obs_host && reward_host && terminated_host && truncated_host &&
+  // CARLB_ZEROCOPY: 1 (default) as above; 2 = results zero-copy, actions by an async H2D copy into the
+  // staging buffer (PCIe reads issued by the copy engine instead of by the SMs); 0 = staged copies.
+  const char* zc_env = getenv("CARLB_ZEROCOPY");
+  const int zero_copy = zc_env ? (zc_env[0] - '0') : 1;
+  if (zero_copy > 0 && is_classic(env->kind) && obs_host && reward_host && terminated_host && truncated_host &&
       is_mapped_host(actions_host) && is_mapped_host(obs_host) && is_mapped_host(reward_host) &&
       is_mapped_host(terminated_host) && is_mapped_host(truncated_host)) {
     HostMirrors hm{obs_host, reward_host, terminated_host, truncated_host};
-    rc = classic_step(env, actions_host, act_dtype, st, &hm);
+    const void* act_src = actions_host;
+    if (zero_copy == 2) {
+      CARLB_CUDA_CHECK(cudaMemcpyAsync(env->bufs.act_staging, actions_host, n * esz * (size_t)info.act_dim,
+                                       cudaMemcpyHostToDevice, st));
+      act_src = env->bufs.act_staging;
+    }
+    rc = classic_step(env, act_src, act_dtype, st, &hm);
     if (rc != CARLB_OK) return rc;
     CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
     return CARLB_OK;
@@ -318,6 +346,26 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
       CARLB_CUDA_CHECK(cudaMemcpyAsync(truncated_host, env->bufs.truncated, n, cudaMemcpyDeviceToHost, st));
   }
   CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return CARLB_OK;
+}
+
+int carlb_stage_actions(void* dst_pinned, const void* src, int64_t count, int act_dtype, int n_actions) {
+  if (dst_pinned == nullptr || src == nullptr || count < 0) {
+    set_error("carlb_stage_actions: null pointer or negative count");
+    return CARLB_ERR_INVALID;
+  }
+  bool ok = true;
+  switch (act_dtype) {
+    case CARLB_ACT_I32: ok = stage_checked((int32_t*)dst_pinned, (const int32_t*)src, count, (uint64_t)n_actions); break;
+    case CARLB_ACT_I64: ok = stage_checked((int64_t*)dst_pinned, (const int64_t*)src, count, (uint64_t)n_actions); break;
+    case CARLB_ACT_U8: ok = stage_checked((uint8_t*)dst_pinned, (const uint8_t*)src, count, (uint64_t)n_actions); break;
+    case CARLB_ACT_F32: memcpy(dst_pinned, src, (size_t)count * sizeof(float)); break;
+    default: set_error("carlb_stage_actions: unknown action dtype %d", act_dtype); return CARLB_ERR_INVALID;
+  }
+  if (!ok && n_actions > 0) {
+    set_error("invalid action: values must lie in [0, %d)", n_actions);
+    return CARLB_ERR_INVALID;
+  }
   return CARLB_OK;
 }
 

@@ -43,6 +43,7 @@ _NP_ACT = {
     np.dtype(np.int32): _native.ACT_I32, np.dtype(np.int64): _native.ACT_I64, np.dtype(np.uint8): _native.ACT_U8,
     np.dtype(np.float32): _native.ACT_F32,
 }
+_UNSIGNED = {1: np.uint8, 4: np.uint32, 8: np.uint64}
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -546,13 +547,18 @@ class CARLEnv(abc.ABC):
             pin = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype).pin_memory()
             ob, rb = n * info.obs_dim * 4, n * 4
             out = pin(ob + rb + 2 * n, dtype=torch.uint8)  # same packing as the device side
+            act = pin(n * max(1, info.act_dim), dtype=torch.int64)
+            obs, reward = out[:ob].view(torch.float32).view(n, info.obs_dim), out[ob:ob + rb].view(torch.float32)
+            term, trunc = out[ob + rb:ob + rb + n], out[ob + rb + n:ob + rb + 2 * n]
+            act_bytes = act.numpy().view(np.uint8)
             self._host_io = dict(
-                act=pin(n * max(1, info.act_dim), dtype=torch.int64),
-                out=out,
-                obs=out[:ob].view(torch.float32).view(n, info.obs_dim),
-                reward=out[ob:ob + rb].view(torch.float32),
-                term=out[ob + rb:ob + rb + n],
-                trunc=out[ob + rb + n:ob + rb + 2 * n],
+                act=act, out=out, obs=obs, reward=reward, term=term, trunc=trunc,
+                # everything the per-step path touches is resolved once: raw pointers, numpy views of the
+                # pinned result block, one staging view per accepted action dtype
+                ptrs=(act.data_ptr(), obs.data_ptr(), reward.data_ptr(), term.data_ptr(), trunc.data_ptr()),
+                np_obs=obs.numpy(), np_reward=reward.numpy(), np_term=term.numpy().view(np.bool_),
+                np_trunc=trunc.numpy().view(np.bool_),
+                staged={dt: act_bytes[:n * max(1, info.act_dim) * np.dtype(dt).itemsize].view(dt) for dt in _NP_ACT},
             )
         return self._host_io
 
@@ -565,20 +571,17 @@ class CARLEnv(abc.ABC):
                 a = a.astype(np.int64)
         elif a.dtype != np.float32:
             a = a.astype(np.float32)
-        if self._validate_actions and self._info.act_discrete:
-            # `assert self.action_space.contains(action)` of the gymnasium envs, batched
-            assert a.size == 0 or (int(a.min()) >= 0 and int(a.max()) < self._info.n_actions), (
-                f"invalid action: values must lie in [0, {self._info.n_actions})")
-        nbytes = a.size * a.dtype.itemsize
-        staged = io["act"].numpy().view(np.uint8)[:nbytes].view(a.dtype)
-        staged[...] = a.reshape(-1)
-        _native.check(self._lib.carlb_env_step_host(
-            self._handle, io["act"].data_ptr(), _NP_ACT[a.dtype], io["obs"].data_ptr(), io["reward"].data_ptr(),
-            io["term"].data_ptr(), io["trunc"].data_ptr(), self._stream()))
-        obs = io["obs"].numpy()
-        state = {"obs": obs, "context": self._context_obs_host()}
-        info = {"context_id": self.context_id}
-        return state, io["reward"].numpy(), io["term"].numpy().view(np.bool_), io["trunc"].numpy().view(np.bool_), info
+        flat = np.ascontiguousarray(a).reshape(-1)
+        n_act = self._info.n_actions if (self._validate_actions and self._info.act_discrete) else 0
+        # one native pass: copy into the page-locked staging block + `action_space.contains` range check
+        if self._lib.carlb_stage_actions(io["ptrs"][0], flat.ctypes.data, flat.size, _NP_ACT[a.dtype], n_act) != 0:
+            # gymnasium raises AssertionError from `assert self.action_space.contains(action)`
+            raise AssertionError(_native.last_error())
+        p = io["ptrs"]
+        _native.check(self._lib.carlb_env_step_host(self._handle, p[0], _NP_ACT[a.dtype], p[1], p[2], p[3], p[4],
+                                                    self._stream()))
+        state = {"obs": io["np_obs"], "context": self._context_obs_host()}
+        return state, io["np_reward"], io["np_term"], io["np_trunc"], {"context_id": self.context_id}
 
     def _context_obs_host(self):
         if self._ctx_obs_host_cache is None:  # contexts only change at reset / context_id assignment

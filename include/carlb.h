@@ -148,6 +148,12 @@ int carlb_env_step(carlb_env_t* env, const void* actions, int act_dtype, void* s
 int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtype, float* obs_host,
                         float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream);
 
+/* Host helper for the call above: copy a caller's (pageable) action array into the page-locked staging
+ * block in one pass and, for discrete action dtypes with n_actions > 0, range-check it like the
+ * `assert self.action_space.contains(action)` of the gymnasium envs the reference steps
+ * (carl/envs/carl_env.py:339). CARLB_ERR_INVALID (message "invalid action ...") when a value is outside. */
+int carlb_stage_actions(void* dst_pinned, const void* src, int64_t count, int act_dtype, int n_actions);
+
 /* Fused K-step rollout (the `for t: env.step(policy(obs))` loop of a rollout worker in one
  * launch; state stays in registers). actions == NULL: synthetic random policy from
  * Philox4x32-10 keyed by (policy_seed, global env id, step_base + t); else actions[K][n]. */
