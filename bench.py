@@ -347,7 +347,7 @@ def run_gpu_arm(args):
     side.wait_stream(stream)
     with torch.cuda.stream(side):
         for g_ in range(3):
-            _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, side.cuda_stream))
+            _native.check(lib.carlb_env_step(handle, act_ring[g_ % G].data_ptr(), _native.ACT_I32, side.cuda_stream))
     torch.cuda.synchronize(dev)
     graph = None
     if not distributed:  # the fused gather changes slot / flag value per launch: not graph-capturable
@@ -384,7 +384,7 @@ def run_gpu_arm(args):
         flush.fill_(float(g_))
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record(stream)
-        _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, stream.cuda_stream))
+        _native.check(lib.carlb_env_step(handle, act_ring[g_ % G].data_ptr(), _native.ACT_I32, stream.cuda_stream))
         c1.record(stream)
         torch.cuda.synchronize(dev)
         cold.append(c0.elapsed_time(c1))

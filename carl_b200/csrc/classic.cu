@@ -259,8 +259,22 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
     so = env_step<KIND, T>(s, p, a, noise, sb, o);
     el += 1;
     tr = seg.max_steps > 0 && el >= seg.max_steps;
-    if (seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr)) {
-      if (!have_next) {  // in-place reset (rare once the batched refill is running)
+    const bool need_reset = seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr);
+    if (batch_resets) {
+      // refill when enough lanes have used theirs up -- or when ANY lane must reset right now without
+      // one in hand: the warp would execute the divergent in-place path for that single lane anyway,
+      // so every lane that lacks a pre-generated state makes one in the same pass
+      const unsigned lacking = __ballot_sync(lanes, !have_next);
+      const unsigned urgent = __ballot_sync(lanes, need_reset && !have_next);
+      if ((__popc(lacking) >= kRefill || urgent != 0u) && !have_next) {
+        sv_hi = g.state_hi; sv_lo = g.state_lo;
+        pcg64_skip<Tr::GYM_DRAWS>(g);
+        env_reset<KIND, T>(ns, p, g, no);
+        have_next = true;
+      }
+    }
+    if (need_reset) {
+      if (!have_next) {  // in-place reset: only without batching (no autoreset batching / Acrobot noise)
         pcg64_skip<Tr::GYM_DRAWS>(g);
         env_reset<KIND, T>(s, p, g, o);
       } else {
@@ -272,15 +286,6 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
       }
       el = 0;
       sb = 0;
-    }
-    if (batch_resets) {
-      const unsigned need = __ballot_sync(lanes, !have_next);
-      if (__popc(need) >= kRefill && !have_next) {
-        sv_hi = g.state_hi; sv_lo = g.state_lo;
-        pcg64_skip<Tr::GYM_DRAWS>(g);
-        env_reset<KIND, T>(ns, p, g, no);
-        have_next = true;
-      }
     }
     if (REC) {
       store_obs<Tr::D>(traj.obs, off, o);

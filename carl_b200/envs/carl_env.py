@@ -259,14 +259,13 @@ class CARLEnv(abc.ABC):
     @property
     def context_id(self):
         """Current context id: an int for a single env instance, else ``int64[num_envs]``."""
-        if getattr(self, "_context_ids", None) is None or (self._context_ids < 0).all():
-            return self.context_selector.context_id
-        if self.num_envs == 1:
-            return int(self._context_ids[0])
-        if self._ids_view is None:
-            self._ids_view = self._context_ids.copy()
-            self._ids_view.setflags(write=False)
-        return self._ids_view
+        view = getattr(self, "_ids_view", None)  # per-step fast path: dropped whenever the ids change
+        if view is None:
+            if getattr(self, "_context_ids", None) is None or (self._context_ids < 0).all():
+                return self.context_selector.context_id
+            view = self._ids_view = self._context_ids.copy()
+            view.setflags(write=False)
+        return int(view[0]) if self.num_envs == 1 else view
 
     @context_id.setter
     def context_id(self, new_id) -> None:

@@ -144,4 +144,11 @@ int hc_reset(int kind, int f64, int n, void* state, const void* params, uint64_t
   return 0;
 }
 
+// Binary-action policy through ONE stream object over an arbitrary list of steps (the fused rollout
+// walks consecutive steps; the shift-register fast path must agree with a fresh stream per step).
+void hc_policy_sequence(uint64_t seed, uint64_t env_id, const uint32_t* steps, int n, int* out) {
+  PolicyStream ps = policy_stream(seed, env_id);
+  for (int k = 0; k < n; ++k) out[k] = policy_action<KIND_CARTPOLE>(ps, steps[k]).i;
+}
+
 }  // extern "C"

@@ -273,3 +273,15 @@ def test_full_size_properties_config2():
     e3.reset(seed=1000)  # env i of the slice had global seed 0 + (1000 + i)
     ora.reset(seed=1000)
     np.testing.assert_array_equal(e3.state.cpu().numpy(), ora.state.astype(np.float32))
+
+
+def test_small_angle_sincos_is_bit_identical_to_sincosf():
+    """`m_sincos`'s short branch (|x| < 0.78: sincosf's polynomials without its argument reduction)
+    against CUDA's sincosf for EVERY float in [-1, 1] -- run on the device by tests/devcheck."""
+    import subprocess
+
+    from tests.devcheck import build_devcheck
+
+    p = subprocess.run([build_devcheck.build()], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert p.stdout.startswith("mismatches 0 checked 2130706434"), p.stdout

@@ -69,3 +69,23 @@ def test_policy_actions_in_range_and_uniform(hc):
     assert counts.min() > 850
     vals = np.asarray(vals)
     assert vals.min() >= -2.0 and vals.max() < 2.0 and abs(vals.mean()) < 0.1
+
+
+def test_binary_policy_shift_register_equals_fresh_stream(hc):
+    """CartPole's random policy spends one Philox bit per step and walks it with a shift register;
+    whatever the order of the steps asked for (consecutive runs, unaligned launch boundaries, jumps
+    backwards), the action of (seed, env, step) must be the bit a fresh stream returns."""
+    rng = np.random.default_rng(0)
+    runs = [np.arange(0, 300), np.arange(13, 13 + 200), np.arange(4294967290 - 40, 4294967290),
+            rng.integers(0, 5000, size=400), np.concatenate([np.arange(95, 140), np.arange(20, 70), np.arange(127, 131)])]
+    ai, af = ctypes.c_int(), ctypes.c_float()
+    for env_id, steps in enumerate(runs):
+        steps = np.ascontiguousarray(steps, dtype=np.uint32)
+        out = np.zeros(len(steps), dtype=np.int32)
+        hc.lib.hc_policy_sequence(ctypes.c_uint64(77), ctypes.c_uint64(env_id), steps.ctypes.data_as(ctypes.c_void_p),
+                                  len(steps), out.ctypes.data_as(ctypes.c_void_p))
+        for s_, got in zip(steps, out):
+            hc.lib.hc_policy_action(0, ctypes.c_uint64(77), ctypes.c_uint64(env_id), ctypes.c_uint32(int(s_)), ctypes.byref(ai),
+                                    ctypes.byref(af))
+            assert ai.value == got, (env_id, int(s_))
+        assert 0.3 < out.mean() < 0.7
