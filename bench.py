@@ -192,7 +192,8 @@ def run_reference_arm(args):
     L.oracle_cartpole_rollout_baseline.argtypes = [
         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
         ctypes.c_int, ctypes.c_void_p]
-    threads = int(L.oracle_max_threads())
+    # torchrun exports OMP_NUM_THREADS=1 to its workers when N > 1; the CPU arm must not inherit that
+    threads = max(int(L.oracle_max_threads()), len(os.sched_getaffinity(0)))
     n = N_ENVS_PER_GPU * args.gpus
     _, table = make_context_table(n)
     table = np.ascontiguousarray(table)

@@ -195,20 +195,28 @@ __global__ void __launch_bounds__(kBlock) mixed_step_kernel(const __grid_constan
 // REC = true: the common fast path -- in-kernel policy, all four trajectory sinks present: no
 // per-iteration null checks, one running element offset for all four streams. REC = false: generic
 // (optional sinks, optional given actions).
-template <int KIND, typename T, bool REC>
+// AR: every terminated / truncated env is reset in the same step AND no env enters with its
+// "steps beyond terminated" flag set, so that flag is identically 0 (CartPole's reward is the constant
+// 1) -- the compiler drops its bookkeeping from the loop.
+template <int KIND, typename T, bool REC, bool AR>
 __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
                                              uint32_t step_base, const void* actions, const carlb_traj_t& traj,
-                                             int refill_threshold) {
+                                             int refill_threshold, uint64_t* sv_slot) {
   typedef Traits<KIND> Tr;
   const int n = seg.n;
   T s[Tr::S];
   StateIO<T, Tr::S>::load(seg.state, i, s);
   T p[Tr::P];
   load_rows<KIND, T>(seg, i, 0, Tr::P, p);
-  Pcg64 g = load_rng(seg.rng, n, i);
+  // Batched resets touch the env's PCG64 stream only inside the (rare) refill pass, so the stream
+  // stays in HBM/L2 there instead of occupying eight loop-carried registers; the generic loop and
+  // Acrobot (per-step noise draws) keep it in registers.
+  constexpr bool batch_resets = AR && KIND != KIND_ACROBOT;
+  Pcg64 g{};
+  if (!batch_resets) g = load_rng(seg.rng, n, i);
   int el = seg.elapsed[i];
   uint8_t sb = 0;
-  if (KIND == KIND_CARTPOLE) sb = seg.sbt[i];
+  if (KIND == KIND_CARTPOLE && !AR) sb = seg.sbt[i];
   const uint64_t gid = (uint64_t)(seg.global_offset + i);
   PolicyStream ps = policy_stream(policy_seed, gid);
   float o[Tr::D];
@@ -236,13 +244,10 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   // happens earlier); a pre-generated but unused reset is rolled back at kernel exit. Acrobot with
   // torque noise interleaves per-step draws on the same stream, so it keeps the in-place path.
   const int kRefill = refill_threshold;
-  bool batch_resets = seg.autoreset != CARLB_AUTORESET_NONE;
-  if (KIND == KIND_ACROBOT) batch_resets = false;
   const unsigned lanes = __activemask();
   bool have_next = false;
   T ns[Tr::S];
   float no[Tr::D];
-  uint64_t sv_hi = g.state_hi, sv_lo = g.state_lo;
 #pragma unroll
   for (int k = 0; k < Tr::S; ++k) ns[k] = (T)0;
 #pragma unroll
@@ -256,10 +261,11 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
     if (KIND == KIND_ACROBOT) {
       if (p[AC_NOISE] > (T)0) noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
     }
+    if (AR) sb = 0;
     so = env_step<KIND, T>(s, p, a, noise, sb, o);
     el += 1;
     tr = seg.max_steps > 0 && el >= seg.max_steps;
-    const bool need_reset = seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr);
+    const bool need_reset = (AR || seg.autoreset != CARLB_AUTORESET_NONE) && (so.terminated || tr);
     if (batch_resets) {
       // refill when enough lanes have used theirs up -- or when ANY lane must reset right now without
       // one in hand: the warp would execute the divergent in-place path for that single lane anyway,
@@ -267,17 +273,19 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
       const unsigned lacking = __ballot_sync(lanes, !have_next);
       const unsigned urgent = __ballot_sync(lanes, need_reset && !have_next);
       if ((__popc(lacking) >= kRefill || urgent != 0u) && !have_next) {
-        sv_hi = g.state_hi; sv_lo = g.state_lo;
-        pcg64_skip<Tr::GYM_DRAWS>(g);
-        env_reset<KIND, T>(ns, p, g, no);
+        Pcg64 gr = load_rng(seg.rng, n, i);
+        sv_slot[0] = gr.state_hi; sv_slot[kBlock] = gr.state_lo;  // shared memory: the roll-back point
+        pcg64_skip<Tr::GYM_DRAWS>(gr);
+        env_reset<KIND, T>(ns, p, gr, no);
+        store_rng_state(seg.rng, n, i, gr);
         have_next = true;
       }
     }
     if (need_reset) {
-      if (!have_next) {  // in-place reset: only without batching (no autoreset batching / Acrobot noise)
+      if (!batch_resets) {  // in-place reset: without batching (generic loop / Acrobot's interleaved noise draws)
         pcg64_skip<Tr::GYM_DRAWS>(g);
         env_reset<KIND, T>(s, p, g, o);
-      } else {
+      } else {  // batching guarantees a pre-generated state here (the urgent refill above)
 #pragma unroll
         for (int k = 0; k < Tr::S; ++k) s[k] = ns[k];
 #pragma unroll
@@ -305,10 +313,13 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
       if (a_in != nullptr) a_in += (size_t)n * esz;
     }
   }
-  if (have_next) {  // roll back the reset that was pre-generated but never used
-    g.state_hi = sv_hi; g.state_lo = sv_lo;
+  if (batch_resets) {
+    if (have_next) {  // roll back the reset that was pre-generated but never used
+      seg.rng[i] = sv_slot[0]; seg.rng[(size_t)n + i] = sv_slot[kBlock];
+    }
+  } else {
+    store_rng_state(seg.rng, n, i, g);
   }
-  store_rng_state(seg.rng, n, i, g);
   StateIO<T, Tr::S>::store(seg.state, i, s);
   if (n_steps > 0) {
     store_obs<Tr::D>(seg.obs, (size_t)i, o);
@@ -325,8 +336,15 @@ template <int KIND, typename T, bool REC>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
                                                          uint64_t policy_seed, uint32_t step_base, const void* actions,
                                                          const carlb_traj_t traj, int refill_threshold) {
+  __shared__ uint64_t sv_sh[2 * kBlock];  // per-thread PCG64 state saved before a pre-generated reset
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) rollout_body<KIND, T, REC>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold);
+  if (i < seg.n) {
+    bool clean = seg.autoreset != CARLB_AUTORESET_NONE;  // warp-uniform choice of the specialised loop
+    if (KIND == KIND_CARTPOLE) clean = __all_sync(__activemask(), clean && seg.sbt[i] == 0);
+    uint64_t* sv_slot = &sv_sh[threadIdx.x];
+    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot);
+    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot);
+  }
   // ONE call site reached by every thread of the CTA: the epilogue contains an aligned barrier,
   // which must not be executed from divergent code (ragged tail warps)
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
