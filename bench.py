@@ -286,6 +286,8 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     distributed = world > 1
     if distributed:
+        # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/carlb_bench_nccl_%h_%p.log")
         dist.init_process_group("nccl", device_id=dev)
 
     n_local = N_ENVS_PER_GPU
@@ -460,6 +462,13 @@ def run_gpu_arm(args):
         return 0
 
     peak, peak_src = hbm_peak()
+    # DRAM bytes of ONE launch from the committed ncu --set full capture -- only quoted when that capture
+    # fused the same number of env-steps per launch as this run (per launch, like `achieved`)
+    prof, prof_file = measured_profile("prof_rollout")
+    prof_T = prof.get("fused_steps_per_launch", 100)
+    prof_traffic = float(prof["dram_bytes_per_launch"]) if ("dram_bytes_per_launch" in prof and prof_T == T) else None
+    prof_traffic_src = (f"profiles/{prof_file} (ncu --set full of the same bench command, {prof_T} env-steps per launch"
+                        + ("" if prof_T == T else f"; this run fuses {T}, so no per-launch figure is quoted") + ")") if prof_file else None
     fused_bytes_per_launch = (TRAJ_BYTES * T + STEP_CONTRACT_BYTES) * n_local  # trajectory + one state/ctx round trip
     achieved = fused_bytes_per_launch / (k_avg_ms * 1e-3) / 1e9
     api_ms_per_launch = api_ms / K_api
@@ -483,8 +492,8 @@ def run_gpu_arm(args):
         "roofline": {
             "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "peak_source": peak_src, "traffic": measured_traffic("prof_rollout")[0],
-            "traffic_source": f"profiles/{measured_traffic('prof_rollout')[1]} (ncu --set full, same command at --steps 200)",
+            "peak_source": peak_src, "traffic": prof_traffic,
+            "traffic_source": prof_traffic_src,
             "algorithmic_bytes_per_launch": fused_bytes_per_launch,
             "bytes_per_env_step": TRAJ_BYTES + STEP_CONTRACT_BYTES / T,
             "kernel_ms_avg": k_avg_ms,

@@ -48,7 +48,7 @@ def launch_list(tag):
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(PROF, f"{tag}_launch_list.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (cold-cache, serialised: compare SHARES)\n")
-        f.write("# command: python bench.py --steps 200 --warmup 100 --no-cpu-baseline   (see tools/gpu_round.sh)\n")
+        f.write("# command: python bench.py --steps 1000 --warmup 500 --no-cpu-baseline   (see tools/gpu_round.sh)\n")
         f.write(f"# total kernel time {tot / 1e3:.1f} us over {sum(v[0] for v in agg.values())} launches\n")
         for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{v[1] / 1e3:12.1f} us  {v[0]:6d} launches  {100 * v[1] / tot:6.2f}%  avg {v[1] / v[0] / 1e3:9.2f} us  {k}\n")
@@ -91,6 +91,15 @@ def full(tag, rep):
                   "warps_active_pct": avg("sm__warps_active.avg.pct_of_peak_sustained_active"),
                   "warp_instructions_per_launch": avg("smsp__inst_executed.sum"),
                   "duration_us_under_ncu": avg("gpu__time_duration.sum")}
+        # the bench line printed under the profiler tells how many env-steps one captured launch fused
+        logp = os.path.join(OUT, rep.replace("prof_", "ncu_") + ".log")
+        if os.path.exists(logp):
+            for line in open(logp):
+                if line.startswith("{") and "fused_steps_per_launch" in line:
+                    try:
+                        d[rep]["fused_steps_per_launch"] = json.loads(line)["config"]["fused_steps_per_launch"]
+                    except Exception:
+                        pass
         json.dump(d, open(tp, "w"), indent=1)
     except Exception as e:  # pragma: no cover
         print("traffic summary failed:", e)
