@@ -195,6 +195,23 @@ __global__ void __launch_bounds__(kBlock) mixed_step_kernel(const __grid_constan
 // REC = true: the common fast path -- in-kernel policy, all four trajectory sinks present: no
 // per-iteration null checks, one running element offset for all four streams. REC = false: generic
 // (optional sinks, optional given actions).
+// Loop-invariant kernel parameters live in the constant bank; left alone, the compiler re-reads them
+// with a uniform load (LDCU) in EVERY iteration and stalls the first consumer on it (ncu source page,
+// profiles/r01k: ~14 % of the rollout kernel's stall samples). An empty asm makes the value opaque,
+// which pins it in a register for the whole loop.
+// (ptxas rematerialises a plain parameter read, so the value is routed through a warp shuffle -- once,
+// before the loop -- which it has to treat as an ordinary per-thread register.)
+__device__ __forceinline__ uint32_t pin_reg(uint32_t v) { return __shfl_sync(__activemask(), v, 0); }
+__device__ __forceinline__ int pin_reg(int v) { return (int)pin_reg((uint32_t)v); }
+__device__ __forceinline__ size_t pin_reg(size_t v) {
+  return ((size_t)pin_reg((uint32_t)(v >> 32)) << 32) | (size_t)pin_reg((uint32_t)v);
+}
+template <typename P> __device__ __forceinline__ P* pin_reg(P* v) {
+  P* q = reinterpret_cast<P*>(pin_reg(reinterpret_cast<size_t>(v)));
+  __builtin_assume(__isGlobal(q));  // keep STG (not generic ST) for the trajectory stores
+  return q;
+}
+
 // AR: every terminated / truncated env is reset in the same step AND no env enters with its
 // "steps beyond terminated" flag set, so that flag is identically 0 (CartPole's reward is the constant
 // 1) -- the compiler drops its bookkeeping from the loop.
@@ -204,6 +221,14 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
                                              int refill_threshold, uint64_t* sv_slot) {
   typedef Traits<KIND> Tr;
   const int n = seg.n;
+  const int max_steps = pin_reg(seg.max_steps);
+  const size_t row_stride = pin_reg((size_t)n);
+  n_steps = pin_reg(n_steps);
+  step_base = pin_reg(step_base);
+  float* const tj_obs = pin_reg(traj.obs);
+  void* const tj_act = pin_reg(traj.actions);
+  float* const tj_rew = pin_reg(traj.reward);
+  uint8_t* const tj_done = pin_reg(traj.done);
   T s[Tr::S];
   StateIO<T, Tr::S>::load(seg.state, i, s);
   T p[Tr::P];
@@ -243,7 +268,7 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   // PCG64 stream is consumed in exactly the same order as a step-by-step run (the draw merely
   // happens earlier); a pre-generated but unused reset is rolled back at kernel exit. Acrobot with
   // torque noise interleaves per-step draws on the same stream, so it keeps the in-place path.
-  const int kRefill = refill_threshold;
+  const int kRefill = pin_reg(refill_threshold);
   const unsigned lanes = __activemask();
   bool have_next = false;
   T ns[Tr::S];
@@ -264,7 +289,7 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
     if (AR) sb = 0;
     so = env_step<KIND, T>(s, p, a, noise, sb, o);
     el += 1;
-    tr = seg.max_steps > 0 && el >= seg.max_steps;
+    tr = max_steps > 0 && el >= max_steps;
     const bool need_reset = (AR || seg.autoreset != CARLB_AUTORESET_NONE) && (so.terminated || tr);
     if (batch_resets) {
       // refill when enough lanes have used theirs up -- or when ANY lane must reset right now without
@@ -296,12 +321,12 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
       sb = 0;
     }
     if (REC) {
-      store_obs<Tr::D>(traj.obs, off, o);
-      if (Tr::DISCRETE) static_cast<int32_t*>(traj.actions)[off] = a.i;
-      else static_cast<float*>(traj.actions)[off] = a.f;
-      traj.reward[off] = so.reward;
-      traj.done[off] = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0));
-      off += (size_t)n;
+      store_obs<Tr::D>(tj_obs, off, o);
+      if (Tr::DISCRETE) static_cast<int32_t*>(tj_act)[off] = a.i;
+      else static_cast<float*>(tj_act)[off] = a.f;
+      tj_rew[off] = so.reward;
+      tj_done[off] = (uint8_t)((so.terminated ? 1 : 0) | (tr ? 2 : 0));
+      off += row_stride;
     } else {
       if (t_obs != nullptr) { store_obs<Tr::D>(t_obs, 0, o); t_obs += (size_t)n * Tr::D; }
       if (traj.actions != nullptr) {
