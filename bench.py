@@ -154,6 +154,9 @@ def cpu_baseline_leg(steps_per_call: int, target_seconds: float, n_envs: int = N
         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
         ctypes.c_int, ctypes.c_void_p]
     threads = int(L.oracle_max_threads())
+    quota = cgroup_cpu_quota()
+    if quota:  # more runnable threads than granted CPUs only get throttled (see run_reference_arm)
+        threads = max(1, min(threads, int(round(quota))))
     _, table = make_context_table(n_envs)
     table = np.ascontiguousarray(table)
     state = np.random.default_rng(0).uniform(-0.1, 0.1, (n_envs, 4))
@@ -438,7 +441,12 @@ def run_gpu_arm(args):
 
     # ---------------- e2e: env.step(numpy actions) -> numpy results (host buffers, copies timed)
     K_e2e = min(K, 500)
-    host_actions = np.random.default_rng(1).integers(0, 2, size=(64, n_local), dtype=np.int32)
+    # inputs start in page-locked host memory (carl_b200.hostmem): the step kernel reads each step's action
+    # row in place over PCIe and writes obs/reward/terminated/truncated straight into page-locked result arrays
+    from carl_b200 import hostmem
+
+    host_actions = hostmem.pinned_empty((64, n_local), np.int32)
+    host_actions[...] = np.random.default_rng(1).integers(0, 2, size=(64, n_local), dtype=np.int32)
     for w in range(5):
         env.step(host_actions[w])
     barrier()
@@ -487,8 +495,9 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": K_e2e, "api": "CARLCartPole.step(numpy int32 actions) -> numpy obs/reward/terminated/truncated "
-                                       "(carlb_env_step_host, pinned staging)", "ms_per_step": float(t_e2e.item()) / K_e2e * 1e3},
+                "steps": K_e2e, "api": "CARLCartPole.step(numpy int32 actions in page-locked memory) -> numpy obs/reward/terminated/"
+                                       "truncated (carlb_env_step_host: range check on the host, actions read and "
+                                       "results written over PCIe by the step kernel itself)", "ms_per_step": float(t_e2e.item()) / K_e2e * 1e3},
         "roofline": {
             "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -106,6 +106,34 @@ using namespace carlb;
 // ONE pass that copies and, for discrete spaces, range-checks (`assert self.action_space.contains(action)`
 // of the gymnasium envs, e.g. cartpole.py step) -- replaces a min, a max and a copy on the Python side.
 template <typename A>
+static bool all_below(const A* __restrict__ src, int64_t count, uint64_t n_actions) {
+  typedef typename std::make_unsigned<A>::type U;
+  if (n_actions > (uint64_t)std::numeric_limits<U>::max()) return true;
+  const U limit = (U)n_actions;
+  U bad = 0;
+  for (int64_t i = 0; i < count; ++i) bad |= (U)((U)src[i] >= limit);
+  return bad == 0;
+}
+
+// range check of an action array that is already page-locked (nothing to copy)
+static int check_only(const void* src, int64_t count, int act_dtype, int n_actions) {
+  bool ok = true;
+  if (n_actions > 0) {
+    switch (act_dtype) {
+      case CARLB_ACT_I32: ok = all_below((const int32_t*)src, count, (uint64_t)n_actions); break;
+      case CARLB_ACT_I64: ok = all_below((const int64_t*)src, count, (uint64_t)n_actions); break;
+      case CARLB_ACT_U8: ok = all_below((const uint8_t*)src, count, (uint64_t)n_actions); break;
+      default: break;
+    }
+  }
+  if (!ok) {
+    set_error("invalid action: values must lie in [0, %d)", n_actions);
+    return CARLB_ERR_INVALID;
+  }
+  return CARLB_OK;
+}
+
+template <typename A>
 static bool stage_checked(A* __restrict__ dst, const A* __restrict__ src, int64_t count, uint64_t n_actions) {
   typedef typename std::make_unsigned<A>::type U;  // as unsigned, a negative value exceeds every valid action
   const U limit = n_actions > (uint64_t)std::numeric_limits<U>::max() ? std::numeric_limits<U>::max() : (U)n_actions;
@@ -350,10 +378,11 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
 }
 
 int carlb_stage_actions(void* dst_pinned, const void* src, int64_t count, int act_dtype, int n_actions) {
-  if (dst_pinned == nullptr || src == nullptr || count < 0) {
-    set_error("carlb_stage_actions: null pointer or negative count");
+  if (src == nullptr || count < 0) {
+    set_error("carlb_stage_actions: null source or negative count");
     return CARLB_ERR_INVALID;
   }
+  if (dst_pinned == nullptr || dst_pinned == src) return check_only(src, count, act_dtype, n_actions);
   bool ok = true;
   switch (act_dtype) {
     case CARLB_ACT_I32: ok = stage_checked((int32_t*)dst_pinned, (const int32_t*)src, count, (uint64_t)n_actions); break;

@@ -30,7 +30,7 @@ from typing import Any
 import numpy as np
 import torch
 
-from carl_b200 import _native, spaces
+from carl_b200 import _native, hostmem, spaces
 from carl_b200.context.context_space import ContextFeature, ContextSpace
 from carl_b200.context.selection import AbstractSelector, RoundRobinSelector
 from carl_b200.utils.types import Context, Contexts
@@ -572,13 +572,16 @@ class CARLEnv(abc.ABC):
             a = a.astype(np.float32)
         flat = np.ascontiguousarray(a).reshape(-1)
         n_act = self._info.n_actions if (self._validate_actions and self._info.act_discrete) else 0
-        # one native pass: copy into the page-locked staging block + `action_space.contains` range check
-        if self._lib.carlb_stage_actions(io["ptrs"][0], flat.ctypes.data, flat.size, _NP_ACT[a.dtype], n_act) != 0:
+        p = io["ptrs"]
+        src = flat.ctypes.data
+        # an array from carl_b200.hostmem.pinned_empty is read in place by the step kernel (range check
+        # only); anything else takes one native pass: copy into the page-locked staging block + check
+        in_place = hostmem.is_pinned(src, flat.nbytes)
+        if self._lib.carlb_stage_actions(None if in_place else p[0], src, flat.size, _NP_ACT[a.dtype], n_act) != 0:
             # gymnasium raises AssertionError from `assert self.action_space.contains(action)`
             raise AssertionError(_native.last_error())
-        p = io["ptrs"]
-        _native.check(self._lib.carlb_env_step_host(self._handle, p[0], _NP_ACT[a.dtype], p[1], p[2], p[3], p[4],
-                                                    self._stream()))
+        _native.check(self._lib.carlb_env_step_host(self._handle, src if in_place else p[0], _NP_ACT[a.dtype], p[1], p[2],
+                                                    p[3], p[4], self._stream()))
         state = {"obs": io["np_obs"], "context": self._context_obs_host()}
         return state, io["np_reward"], io["np_term"], io["np_trunc"], {"context_id": self.context_id}
 

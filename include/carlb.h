@@ -151,7 +151,8 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
 /* Host helper for the call above: copy a caller's (pageable) action array into the page-locked staging
  * block in one pass and, for discrete action dtypes with n_actions > 0, range-check it like the
  * `assert self.action_space.contains(action)` of the gymnasium envs the reference steps
- * (carl/envs/carl_env.py:339). CARLB_ERR_INVALID (message "invalid action ...") when a value is outside. */
+ * (carl/envs/carl_env.py:339). CARLB_ERR_INVALID (message "invalid action ...") when a value is outside.
+ * dst_pinned == NULL (or == src): range check only -- for action arrays that already are page-locked. */
 int carlb_stage_actions(void* dst_pinned, const void* src, int64_t count, int act_dtype, int n_actions);
 
 /* Fused K-step rollout (the `for t: env.step(policy(obs))` loop of a rollout worker in one

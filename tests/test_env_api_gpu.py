@@ -151,3 +151,37 @@ def test_checkpoint_roundtrip():
     env2.load_state_dict(sd)
     t2 = env2.rollout(30, policy_seed=2, record=True)
     assert torch.equal(t1["obs"], t2["obs"]) and torch.equal(t1["done"], t2["done"])
+
+
+def test_page_locked_actions_are_read_in_place_and_match_staged_path():
+    """`step(numpy)` with an array from carl_b200.hostmem.pinned_empty (no staging copy, the kernel reads
+    it over PCIe) must give exactly what the same actions in an ordinary array give; the range check
+    still fires for them."""
+    from carl_b200 import hostmem
+    from carl_b200.envs import CARLCartPole
+
+    n = 3000
+    a_env, b_env = CARLCartPole(num_envs=n), CARLCartPole(num_envs=n)
+    a_env.reset(seed=11)
+    b_env.reset(seed=11)
+    rng = np.random.default_rng(0)
+    pinned = hostmem.pinned_empty((5, n), np.int32)
+    pinned[...] = rng.integers(0, 2, size=(5, n))
+    for k in range(5):
+        oa, ra, ta, tra, _ = a_env.step(pinned[k])
+        ob, rb, tb, trb, _ = b_env.step(np.array(pinned[k]))  # pageable copy -> staged
+        np.testing.assert_array_equal(oa["obs"], ob["obs"])
+        np.testing.assert_array_equal(ra, rb)
+        np.testing.assert_array_equal(ta, tb)
+        np.testing.assert_array_equal(tra, trb)
+    np.testing.assert_array_equal(a_env.state.cpu().numpy(), b_env.state.cpu().numpy())
+    pinned[2, 7] = 2
+    with pytest.raises(AssertionError, match="invalid action"):
+        a_env.step(pinned[2])
+    u8 = hostmem.pinned_empty((n,), np.uint8)
+    u8[...] = 1
+    oa, *_ = a_env.step(u8)
+    ob, *_ = b_env.step(np.ones(n, dtype=np.int64))
+    np.testing.assert_array_equal(oa["obs"], ob["obs"])
+    hostmem.release(pinned)
+    hostmem.release(u8)

@@ -150,3 +150,34 @@ def test_registration_is_optional():
     ids = register_envs()
     assert ids == [] or len(ids) == len(ENV_NAMES)
     assert all(hasattr(E, n) for n in ENV_NAMES)
+
+
+def test_pinned_registry_and_check_only_staging():
+    """hostmem's address registry (what lets `step` read an action array in place) and the range-check-only
+    mode of carlb_stage_actions; the page-locked allocation itself needs the driver, so a plain tensor
+    stands in for the block here."""
+    import ctypes
+
+    import torch
+
+    from carl_b200 import _native, hostmem
+
+    t = torch.zeros(4096, dtype=torch.uint8)
+    hostmem._register(t)
+    a = t.numpy().view(np.int32).reshape(4, 256)
+    assert hostmem.is_pinned(a[1].ctypes.data, a[1].nbytes)
+    assert not hostmem.is_pinned(a[3].ctypes.data, a[3].nbytes + 4)       # runs past the end of the block
+    assert not hostmem.is_pinned(np.zeros(8).ctypes.data, 64)
+    lib = _native.load()
+    a[:] = 1
+    assert lib.carlb_stage_actions(None, a[2].ctypes.data, 256, _native.ACT_I32, 2) == 0
+    a[2, 17] = -3
+    assert lib.carlb_stage_actions(None, a[2].ctypes.data, 256, _native.ACT_I32, 2) == _native.ERR_INVALID
+    assert "invalid action" in _native.last_error()
+    assert lib.carlb_stage_actions(None, a[2].ctypes.data, 256, _native.ACT_I32, 0) == 0   # validation off
+    dst = np.zeros(256, dtype=np.int32)
+    a[2, 17] = 0
+    assert lib.carlb_stage_actions(dst.ctypes.data, a[2].ctypes.data, 256, _native.ACT_I32, 2) == 0
+    assert (dst == a[2]).all()
+    hostmem.release(a)
+    assert not hostmem.is_pinned(a[1].ctypes.data, a[1].nbytes)
