@@ -445,15 +445,18 @@ def run_gpu_arm(args):
     # row in place over PCIe and writes obs/reward/terminated/truncated straight into page-locked result arrays
     from carl_b200 import hostmem
 
-    host_actions = hostmem.pinned_empty((64, n_local), np.int32)
-    host_actions[...] = np.random.default_rng(1).integers(0, 2, size=(64, n_local), dtype=np.int32)
+    # (a policy writes into the same few page-locked buffers every step -- 4 here; cycling through many MB of
+    # them only adds IOTLB misses on the GPU's PCIe reads: tools/e2e_probe.py, profiles/r01l_e2e_probe.json)
+    E2E_ROWS = 4
+    host_actions = hostmem.pinned_empty((E2E_ROWS, n_local), np.int32)
+    host_actions[...] = np.random.default_rng(1).integers(0, 2, size=(E2E_ROWS, n_local), dtype=np.int32)
     for w in range(5):
-        env.step(host_actions[w])
+        env.step(host_actions[w % E2E_ROWS])
     barrier()
     t0 = time.perf_counter()
     acc = 0.0
     for j in range(K_e2e):
-        obs, rew, term, trunc, _ = env.step(host_actions[j % 64])
+        obs, rew, term, trunc, _ = env.step(host_actions[j % E2E_ROWS])
         acc += float(rew[0])  # the result is read on the host every step
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0

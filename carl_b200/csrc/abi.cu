@@ -110,6 +110,11 @@ static bool all_below(const A* __restrict__ src, int64_t count, uint64_t n_actio
   typedef typename std::make_unsigned<A>::type U;
   if (n_actions > (uint64_t)std::numeric_limits<U>::max()) return true;
   const U limit = (U)n_actions;
+  if ((n_actions & (n_actions - 1)) == 0) {  // power of two: OR-reduce (plain SSE2), any stray bit shows
+    U acc = 0;
+    for (int64_t i = 0; i < count; ++i) acc |= (U)src[i];
+    return acc < limit;
+  }
   U bad = 0;
   for (int64_t i = 0; i < count; ++i) bad |= (U)((U)src[i] >= limit);
   return bad == 0;
@@ -138,6 +143,15 @@ static bool stage_checked(A* __restrict__ dst, const A* __restrict__ src, int64_
   typedef typename std::make_unsigned<A>::type U;  // as unsigned, a negative value exceeds every valid action
   const U limit = n_actions > (uint64_t)std::numeric_limits<U>::max() ? std::numeric_limits<U>::max() : (U)n_actions;
   const bool unbounded = n_actions > (uint64_t)std::numeric_limits<U>::max();
+  if (!unbounded && (n_actions & (n_actions - 1)) == 0) {  // power of two: copy + OR-reduce
+    U acc = 0;
+    for (int64_t i = 0; i < count; ++i) {
+      const A v = src[i];
+      dst[i] = v;
+      acc |= (U)v;
+    }
+    return acc < limit;
+  }
   U bad = 0;
   for (int64_t i = 0; i < count; ++i) {
     const A v = src[i];

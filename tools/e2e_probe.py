@@ -51,6 +51,22 @@ def main():
         return float(r[0])
 
     out["python_env_step_int32_us"] = loop(py_step)
+    from carl_b200 import hostmem
+    for rows in (64, 4, 1):
+        pa = hostmem.pinned_empty((rows, n), np.int32)
+        pa[...] = a32[:rows]
+        kk = [0]
+
+        def pinned_step():
+            kk[0] += 1
+            o, r, te, tr, _ = env.step(pa[kk[0] % rows])
+            return float(r[0])
+
+        out[f"python_env_step_pinned_inplace_{rows}rows_us"] = loop(pinned_step)
+        out[f"c_abi_step_host_pinned_inplace_{rows}rows_us"] = loop(
+            lambda: lib.carlb_env_step_host(h, pa[kk[0] % rows].ctypes.data, _native.ACT_I32, p[1], p[2], p[3], p[4], st))
+        out[f"check_only_{rows}rows_us"] = loop(lambda: lib.carlb_stage_actions(None, pa[0].ctypes.data, n, _native.ACT_I32, 2), n=2000)
+        hostmem.release(pa)
     out["python_env_step_uint8_us"] = loop(lambda: env.step(a8[0]))
     out["stage_actions_int32_us"] = loop(lambda: lib.carlb_stage_actions(p[0], a32[3].ctypes.data, n, _native.ACT_I32, 2), n=2000)
     out["stage_actions_uint8_us"] = loop(lambda: lib.carlb_stage_actions(p[0], a8[3].ctypes.data, n, _native.ACT_U8, 2), n=2000)
