@@ -386,6 +386,16 @@ def run_gpu_arm(args):
     value = n_global * K / (fused_ms * 1e-3)
     k_avg_ms = float(np.mean(kernel_ms[:K // T]))  # the full-length launches (the roofline's per-launch figure)
 
+    if args.fused_only:  # profiling runs (tools/gpu_round.sh): only the timed region's launches, then stop
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
+                              "ms_per_step": fused_ms / K, "fused_only": True, "gpu_launches": int(launches),
+                              "config": {"fused_steps_per_launch": T, "launches": len(plan), "n_envs": n_global},
+                              "kernel_ms_avg": k_avg_ms}))
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
     # ---------------- step_api: one launch per step, graph-replayed, actions ring > L2
     K_api = min(K, 2000)
     ring_steps = int(math.ceil(1.2 * L2_BYTES / (n_local * 4)))  # int32 actions: 256 KiB per step
@@ -610,6 +620,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ant", action="store_true")
+    ap.add_argument("--fused-only", action="store_true",
+                    help="profiling aid: run the warm-up and the timed fused-rollout region, print a short line, stop")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU obs gather path")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -15,15 +15,15 @@ cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "$1" != "noncu" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1; echo "ncu list exit $?"
+  python bench.py --steps 2000 --warmup 200 --fused-only > gpurun_out/ncu_launch.log 2>&1; echo "ncu list exit $?"
 echo "== ncu full: rollout kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 2 -c 2 -f -o gpurun_out/prof_rollout \
-  python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_rollout.log 2>&1; echo "ncu rollout exit $?"
+  python bench.py --steps 2000 --warmup 200 --fused-only > gpurun_out/ncu_rollout.log 2>&1; echo "ncu rollout exit $?"
 echo "== ncu full: brax step kernel"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:brax_step_kernel -s 3 -c 2 -f -o gpurun_out/prof_brax \
-  python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_brax.log 2>&1; echo "ncu brax exit $?"
+  python bench.py --steps 1000 --warmup 500 --no-cpu-baseline > gpurun_out/ncu_brax.log 2>&1; echo "ncu brax exit $?"
 echo "== ncu full: step kernel"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 10 -c 2 -f -o gpurun_out/prof_step \
-  python bench.py --steps 200 --warmup 100 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1; echo "ncu step exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:^step_kernel -s 10 -c 2 -f -o gpurun_out/prof_step \
+  python bench.py --steps 1000 --warmup 500 --no-cpu-baseline > gpurun_out/ncu_step.log 2>&1; echo "ncu step exit $?"
 fi
 ls -la gpurun_out
