@@ -285,3 +285,34 @@ def test_small_angle_sincos_is_bit_identical_to_sincosf():
     p = subprocess.run([build_devcheck.build()], capture_output=True, text=True, timeout=300)
     assert p.returncode == 0, p.stdout + p.stderr
     assert p.stdout.startswith("mismatches 0 checked 2130706434"), p.stdout
+
+
+def test_trajectory_offsets_beyond_32_bits():
+    """Maximum sizes: 4 Mi envs x 300 fused steps puts the last observation rows at element offsets
+    > 2^32 of the trajectory buffer (19 GiB). The row written for step t must be what a second
+    run, cut into two launches at an unaligned step, writes for the same global step."""
+    from carl_b200.envs import CARLCartPole
+
+    n, K, cut = 1 << 22, 300, 173
+    a = CARLCartPole(num_envs=n, autoreset=True)
+    a.reset(seed=7)
+    ta = a.rollout(K, policy_seed=9, record=True)
+    assert ta["obs"].numel() > (1 << 32)
+    last = ta["obs"][-1].clone()
+    mid = ta["obs"][cut - 1].clone()
+    acts_tail = ta["actions"][-1].clone()
+    done_sum = int((ta["done"] != 0).sum().item())
+    assert torch.equal(last, a._obs) and torch.isfinite(last).all()
+    del ta
+    torch.cuda.empty_cache()
+    b = CARLCartPole(num_envs=n, autoreset=True)
+    b.reset(seed=7)
+    t1 = b.rollout(cut, policy_seed=9, step_base=0, record=True)
+    assert torch.equal(t1["obs"][-1], mid)
+    d1 = int((t1["done"] != 0).sum().item())
+    del t1
+    torch.cuda.empty_cache()
+    t2 = b.rollout(K - cut, policy_seed=9, step_base=cut, record=True)
+    assert torch.equal(t2["obs"][-1], last) and torch.equal(t2["actions"][-1], acts_tail)
+    assert d1 + int((t2["done"] != 0).sum().item()) == done_sum
+    assert 0.02 < done_sum / (n * K) < 0.08   # random policy: one episode end every ~22 steps
