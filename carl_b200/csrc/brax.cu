@@ -231,6 +231,9 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
 struct RootFacts {
   float x, z, angle;
   bool state_ok;  // Hopper: all |q[2:]|, |qd| < 100
+  // bodies without a locomotion root (inverted pendulums, reacher): what their env layer reads
+  float q1, qd1, qd2;  // pole angle; hinge rates (unclipped)
+  V3 site;             // pendulum tip (world) / reacher: fingertip - target
 };
 
 template <int E>
@@ -251,7 +254,7 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
       const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, 0.0f);
-      const int nd = c.type == TYPE_PLANAR ? 3 : 1;
+      const int nd = type_ndof(c.type);
       for (int k = 0; k < nd; ++k) {
         w.q[qi + k] = jo.q[k];
         w.qd[qdi + k] = jo.qd[k];
@@ -261,17 +264,29 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   __syncwarp();
   const int ex = (int)sys[H_EXCLUDE_POS];
   const float clip = sys[H_QD_CLIP];
-  const int D = (nq - ex) + nqd;
-  if (c.sl < LPE) {
-    for (int i = c.sl; i < D; i += LPE) {
-      float v;
-      if (i < nq - ex) {
-        v = w.q[ex + i];
-      } else {
-        v = w.qd[i - (nq - ex)];
-        if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+  const int kind = (int)sys[H_ENV];
+  RootFacts r;
+  r.site = v3(0, 0, 0);
+  if (kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
+    r.site = site_position(sys, read_link(w.ls, (int)sys[H_SITE_LINK]), read_link(w.ls, kind == ENV_REACHER ? 2 : 0));
+  }
+  if (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER) {
+    const int D = kind == ENV_REACHER ? 11 : 8;
+    if (c.sl < LPE)
+      for (int i = c.sl; i < D; i += LPE) w.obs[i] = special_obs_entry(kind, i, w.q, w.qd, r.site);
+  } else {
+    const int D = (nq - ex) + nqd;
+    if (c.sl < LPE) {
+      for (int i = c.sl; i < D; i += LPE) {
+        float v;
+        if (i < nq - ex) {
+          v = w.q[ex + i];
+        } else {
+          v = w.qd[i - (nq - ex)];
+          if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+        }
+        w.obs[i] = v;
       }
-      w.obs[i] = v;
     }
   }
   __syncwarp();
@@ -279,8 +294,10 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   bool ok = true;
   for (int i = 2; i < nq; ++i) ok = ok && (w.q[i] > -100.0f) && (w.q[i] < 100.0f);
   for (int i = 0; i < nqd; ++i) ok = ok && (w.qd[i] > -100.0f) && (w.qd[i] < 100.0f);
-  RootFacts r;
   r.state_ok = ok;
+  r.q1 = w.q[1];
+  r.qd1 = w.qd[1];
+  r.qd2 = w.qd[2];
   const float* lt0 = link_tab(sys, 0);
   const LinkState s0 = read_link(w.ls, 0);
   const V3 o0 = link_origin(s0, lt0);
@@ -311,6 +328,7 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   const float ctrl_cost = sys[H_CTRL_COST] * act_sq_sum;
   reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
   done = (sys[H_TERMINATE] > 0.0f) && !healthy;
+  if (kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
 }
 
 template <int W, int E>
@@ -397,7 +415,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
       } else {
         const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step_base + (uint32_t)t,
                                         0x42524158u + (uint32_t)c.sl, (uint32_t)policy_seed, (uint32_t)(policy_seed >> 32));
-        a = 2.0f * u32_to_unit_float(r.v[0]) - 1.0f;
+        a = sys[H_ACT_SCALE] * (2.0f * u32_to_unit_float(r.v[0]) - 1.0f);  // uniform over the action space
       }
       w.act[c.sl] = a;
     }
@@ -506,16 +524,24 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
       const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
       const uint64_t gid = (uint64_t)(seg.global_offset + env);
       const uint32_t episode = (uint32_t)seg.episode[env];
-      const float noise = sys[H_RESET_NOISE];
-      const bool hopper = sys[H_QD_UNIFORM] > 0.0f;  // Hopper / Walker2d: qd ~ U(+-noise) instead of noise * N(0,1)
+      const float noise = sys[H_RESET_NOISE], qd_noise = sys[H_QD_NOISE];
+      const bool hopper = sys[H_QD_UNIFORM] > 0.0f;  // Hopper / Walker2d / pendulum / reacher: qd ~ U(+-noise), else noise * N(0,1)
+      const bool reacher = (int)sys[H_ENV] == ENV_REACHER;
       if (lane < nq) {
         w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
                                       : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
       }
       if (lane < nqd) {
         w.qd[lane] = (qd_in != nullptr) ? qd_in[(size_t)env * nqd + lane]
-                     : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -noise, noise)
-                                        : noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
+                     : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -qd_noise, qd_noise)
+                                        : qd_noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
+      }
+      if (reacher && q_in == nullptr && lane >= 2 && lane < 4) {
+        // brax.envs.reacher._random_target: dist = 0.2 U, ang = 2 pi U; q[2:] = target, qd[2:] = 0
+        const float dist = 0.2f * reset_uniform(seg.seed, gid, episode, 128u, 0.0f, 1.0f);
+        const float ang = 6.283185307179586f * reset_uniform(seg.seed, gid, episode, 129u, 0.0f, 1.0f);
+        w.q[lane] = lane == 2 ? dist * cosf(ang) : dist * sinf(ang);
+        w.qd[lane] = 0.0f;
       }
       __syncwarp();
       // forward kinematics down the tree (parents have smaller indices)
@@ -570,6 +596,9 @@ static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
     case KIND_BRAX_ANT: L = 9; nq = 15; nqd = 14; A = 8; break;
     case KIND_BRAX_HALFCHEETAH: L = 7; nq = 9; nqd = 9; A = 6; break;
     case KIND_BRAX_WALKER2D: L = 7; nq = 9; nqd = 9; A = 6; break;
+    case KIND_BRAX_INVERTED_PENDULUM: L = 2; nq = 2; nqd = 2; A = 1; break;
+    case KIND_BRAX_INVERTED_DOUBLE_PENDULUM: L = 3; nq = 3; nqd = 3; A = 1; break;
+    case KIND_BRAX_REACHER: L = 3; nq = 4; nqd = 4; A = 2; break;
     default: L = 4; nq = 6; nqd = 6; A = 3; break;
   }
 }
@@ -577,10 +606,12 @@ static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
 int brax_query(int kind, carlb_env_info_t* o) {
   int L, nq, nqd, A;
   static_facts(kind, L, nq, nqd, A);
-  const int ex = kind == KIND_BRAX_ANT ? 2 : 1;
+  const int ex = kind == KIND_BRAX_ANT ? 2 : (kind == KIND_BRAX_INVERTED_PENDULUM ? 0 : 1);
   o->kind = kind;
   o->state_words = ((LINK_WORDS * L + 3) / 4) * 4;
   o->obs_dim = (nq - ex) + nqd;
+  if (kind == KIND_BRAX_INVERTED_DOUBLE_PENDULUM) o->obs_dim = 8;  // q0, sin, cos, clipped qd
+  if (kind == KIND_BRAX_REACHER) o->obs_dim = 11;                  // cos, sin, target, qd[:2], tip - target
   o->act_dim = A;
   o->act_discrete = 0;
   o->n_actions = 0;
@@ -588,8 +619,8 @@ int brax_query(int kind, carlb_env_info_t* o) {
   o->n_step_rows = 5 + L;
   o->default_max_steps = 1000;  // brax.envs.create(episode_length=1000)
   o->gym_reset_draws = 0;
-  o->act_low = -1.0f;
-  o->act_high = 1.0f;
+  o->act_low = kind == KIND_BRAX_INVERTED_PENDULUM ? -3.0f : -1.0f;  // BraxGymWrapper: Box(ctrl_range) (wrappers.py:48-50)
+  o->act_high = -o->act_low;
   return CARLB_OK;
 }
 

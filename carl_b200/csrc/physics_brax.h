@@ -36,20 +36,32 @@ constexpr int OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS;
 constexpr int OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS;
 constexpr int TABLE_FLOATS = OFF_INIT_Q + MAX_Q;
 
+// H_SITE_LINK: link carrying the body-fixed point the env layer reads (pendulum tip / reacher fingertip, L_SITE);
+// H_QD_NOISE: scale of the reset noise on qd (H_RESET_NOISE is the one on q); H_ACT_SCALE: action-space half width
+// (= actuator ctrl_range: 1 except the inverted pendulum's 3)
 enum Hdr {
   H_N_LINKS = 0, H_N_Q, H_N_QD, H_N_POINTS, H_N_FRAMES, H_DT, H_ENV, H_N_ACT,
   H_STIFFNESS, H_VEL_DAMPING_C, H_LIMIT_STIFFNESS, H_ANG_DAMPING_C, H_BAUMGARTE, H_VEL_DAMPING, H_MASS_SCALE,
   H_INERTIA_SCALE,
   H_RESET_NOISE, H_CTRL_COST, H_HEALTHY_REWARD, H_HEALTHY_Z_MIN, H_HEALTHY_Z_MAX, H_FORWARD_WEIGHT, H_ANGLE_MIN,
-  H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS, H_QD_UNIFORM
+  H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS, H_QD_UNIFORM,
+  H_SITE_LINK, H_QD_NOISE, H_ACT_SCALE
 };
+static_assert(H_ACT_SCALE < HEADER, "header slots exhausted");
 enum LinkSlot {
   L_PARENT = 0, L_TYPE, L_QIDX, L_QDIDX, L_TPOS = 4, L_TROT = 7, L_JPOS = 11, L_JROT = 14, L_LIM_LO = 18, L_LIM_HI = 19,
   L_COM = 20, L_IROT = 23, L_IDIAG = 27, L_MASS = 30, L_GEAR = 31, L_ACT = 32, L_CTRL_LO = 33, L_CTRL_HI = 34,
-  L_FIRST_PT = 35, L_N_PT = 36
+  L_FIRST_PT = 35, L_N_PT = 36, L_SITE = 37
 };
-enum LinkType { TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_PLANAR = 3 };
-enum EnvId { ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2, ENV_WALKER2D = 3 };
+// TYPE_SLIDE: one prismatic dof along the joint x axis (the cart of the inverted pendulums);
+// TYPE_SLIDE2: two prismatic dofs along the joint x and y axes (the reacher's target body)
+enum LinkType { TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_SLIDE = 2, TYPE_PLANAR = 3, TYPE_SLIDE2 = 4 };
+enum EnvId {
+  ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2, ENV_WALKER2D = 3, ENV_INVERTED_PENDULUM = 4,
+  ENV_INVERTED_DOUBLE_PENDULUM = 5, ENV_REACHER = 6
+};
+// joint coordinates per link type (free roots are handled separately: 7 / 6)
+CARLB_HD int type_ndof(int type) { return type == TYPE_PLANAR ? 3 : (type == TYPE_SLIDE2 ? 2 : 1); }
 // per-env context rows: gravity, friction, elasticity, ang_damping, joint-stiffness scale (the
 // legacy `joint_stiffness` feature of CARL's docs mapped onto the spring constraint stiffness,
 // 1 = stock), then one mass per link
@@ -197,6 +209,18 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     // slide-x / slide-z / hinge-y root: only the off-plane offset and off-axis rotation are constrained
     fv = v3(-k * jpos.x - cv * jvel.x, 0.0f, 0.0f);
     fa = fa - ca * v3(0.0f, jang.y, jang.z);
+  } else if (type == TYPE_SLIDE || type == TYPE_SLIDE2) {
+    // prismatic: free along the joint x axis (x and y for SLIDE2), the remaining offsets sprung,
+    // every rotation locked (second alignment torque on the y axes); limit + actuator force along x
+    const V3 ey = v3(0, 1, 0);
+    fa = fa + k * cross(yc, ey);
+    fa = fa - ca * jang;
+    const float lo = lt[L_LIM_LO], hi = lt[L_LIM_HI];
+    float dpos = 0.0f;
+    if (jpos.x < lo) dpos = lo - jpos.x;
+    if (jpos.x > hi) dpos = hi - jpos.x;
+    const float fy = (type == TYPE_SLIDE) ? (-k * jpos.y - cv * jvel.y) : 0.0f;
+    fv = v3(kl * dpos + tau, fy, -k * jpos.z - cv * jvel.z);
   } else {
     fv = (-k) * jpos - cv * jvel;
     const float lo = lt[L_LIM_LO], hi = lt[L_LIM_HI];
@@ -219,6 +243,9 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     const V3 vo = origin_velocity(c, lt);
     o.q[0] = xc_pos.x - t_pos.x; o.q[1] = xc_pos.z - t_pos.z; o.q[2] = psi;
     o.qd[0] = vo.x; o.qd[1] = vo.z; o.qd[2] = jang.x;
+  } else if (type == TYPE_SLIDE || type == TYPE_SLIDE2) {
+    o.q[0] = jpos.x; o.q[1] = jpos.y;
+    o.qd[0] = jvel.x; o.qd[1] = jvel.y;
   }
   return o;
 }
@@ -330,6 +357,16 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
       tvel = v3(qdl[0], 0.0f, qdl[1]);
       angle = ql[2];
       rate = qdl[2];
+    } else if (type == TYPE_SLIDE || type == TYPE_SLIDE2) {
+      trans = axis * ql[0];
+      tvel = axis * qdl[0];
+      if (type == TYPE_SLIDE2) {
+        const V3 axis_y = rotate(v3(0, 1, 0), j_rot);
+        trans = trans + axis_y * ql[1];
+        tvel = tvel + axis_y * qdl[1];
+      }
+      angle = 0.0f;
+      rate = 0.0f;
     } else {
       angle = ql[0];
       rate = qdl[0];
@@ -350,6 +387,49 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
   s.vel = xvel + cross(xang, rc);
   s.ang = xang;
   return s;
+}
+
+// Observation entry i of the bodies whose obs is not q[exclude:] ++ qd
+// (brax.envs.inverted_double_pendulum._get_obs, brax.envs.reacher._get_obs)
+CARLB_HD float special_obs_entry(int kind, int i, const float* q, const float* qd, V3 site) {
+  if (kind == ENV_INVERTED_DOUBLE_PENDULUM) {  // q[:1], sin(q[1:]), cos(q[1:]), clip(qd, -10, 10)
+    if (i == 0) return q[0];
+    if (i < 3) return sinf(q[i]);
+    if (i < 5) return cosf(q[i - 2]);
+    return fminf(fmaxf(qd[i - 5], -10.0f), 10.0f);
+  }
+  // reacher: cos(theta), sin(theta), q[2:] (target xy), qd[:2], tip - target
+  if (i < 2) return cosf(q[i]);
+  if (i < 4) return sinf(q[i - 2]);
+  if (i < 6) return q[i - 2];
+  if (i < 8) return qd[i - 6];
+  return i == 8 ? site.x : (i == 9 ? site.y : site.z);
+}
+
+// Env layer of the bodies without a locomotion root (brax.envs.inverted_pendulum / inverted_double_pendulum /
+// reacher .step); `site` is the pendulum tip in the world, or fingertip - target for the reacher.
+CARLB_HD void special_outcome(int kind, float q1, float qd1, float qd2, V3 site, float act_sq_sum, float& reward, bool& done) {
+  if (kind == ENV_INVERTED_PENDULUM) {  // reward 1, done = |pole angle| > 0.2
+    reward = 1.0f;
+    done = fabsf(q1) > 0.2f;
+  } else if (kind == ENV_INVERTED_DOUBLE_PENDULUM) {
+    const float x = site.x, y = site.z;
+    const float dist_penalty = 0.01f * (x * x) + (y - 2.0f) * (y - 2.0f);
+    const float vel_penalty = 1e-3f * (qd1 * qd1) + 5e-3f * (qd2 * qd2);
+    reward = 10.0f - dist_penalty - vel_penalty;
+    done = y <= 1.0f;
+  } else if (kind == ENV_REACHER) {  // -|tip - target| - sum(a^2), never done
+    reward = (0.0f - norm(site)) + (0.0f - act_sq_sum);
+    done = false;
+  }
+}
+
+// world position of the env's site: x.take(link).do(Transform(pos=site)); for the reacher minus the target origin
+CARLB_HD V3 site_position(const float* sys, const LinkState& site_link, const LinkState& link2) {
+  const float* slt = link_tab(sys, (int)sys[H_SITE_LINK]);
+  V3 p = link_origin(site_link, slt) + rotate(ld3(slt + L_SITE), site_link.rot);
+  if ((int)sys[H_ENV] == ENV_REACHER) p = p - link_origin(link2, link_tab(sys, 2));
+  return p;
 }
 
 // Reset-noise draws (throughput-mode RNG; the reference's JAX threefry stream is not

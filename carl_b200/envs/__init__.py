@@ -13,6 +13,9 @@ from carl_b200.envs.brax import (  # noqa: F401,E402
     CARLBraxEnv,
     CARLBraxHalfcheetah,
     CARLBraxHopper,
+    CARLBraxInvertedDoublePendulum,
+    CARLBraxInvertedPendulum,
+    CARLBraxReacher,
     CARLBraxWalker2d,
 )
 from carl_b200.envs.mixed import MixedBatch  # noqa: F401,E402

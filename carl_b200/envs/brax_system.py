@@ -36,7 +36,8 @@ H_N_LINKS, H_N_Q, H_N_QD, H_N_POINTS, H_N_FRAMES, H_DT, H_ENV, H_N_ACT = range(8
 (H_STIFFNESS, H_VEL_DAMPING_C, H_LIMIT_STIFFNESS, H_ANG_DAMPING_C, H_BAUMGARTE, H_VEL_DAMPING, H_MASS_SCALE,
  H_INERTIA_SCALE) = range(8, 16)
 (H_RESET_NOISE, H_CTRL_COST, H_HEALTHY_REWARD, H_HEALTHY_Z_MIN, H_HEALTHY_Z_MAX, H_FORWARD_WEIGHT, H_ANGLE_MIN,
- H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS, H_QD_UNIFORM) = range(16, 29)
+ H_ANGLE_MAX, H_EXCLUDE_POS, H_QD_CLIP, H_TERMINATE, H_MAX_CHILD_POINTS, H_QD_UNIFORM, H_SITE_LINK, H_QD_NOISE,
+ H_ACT_SCALE) = range(16, 32)
 TUNABLE_NAMES = ["constraint_stiffness", "constraint_vel_damping", "constraint_limit_stiffness",
                  "constraint_ang_damping", "baumgarte_erp", "vel_damping", "spring_mass_scale",
                  "spring_inertia_scale"]
@@ -45,8 +46,12 @@ TUNABLE_NAMES = ["constraint_stiffness", "constraint_vel_damping", "constraint_l
 (L_PARENT, L_TYPE, L_QIDX, L_QDIDX) = range(4)
 L_TPOS, L_TROT, L_JPOS, L_JROT, L_LIM_LO, L_LIM_HI = 4, 7, 11, 14, 18, 19
 L_COM, L_IROT, L_IDIAG, L_MASS, L_GEAR, L_ACT, L_CTRL_LO, L_CTRL_HI, L_FIRST_PT, L_N_PT = 20, 23, 27, 30, 31, 32, 33, 34, 35, 36
-TYPE_FREE, TYPE_HINGE, TYPE_PLANAR = 0, 1, 3
-ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER, ENV_WALKER2D = 0, 1, 2, 3
+L_SITE = 37  # body-fixed point read by the env layer (pendulum tip / reacher fingertip), on the H_SITE_LINK row
+# TYPE_SLIDE: one prismatic dof along the joint axis; TYPE_SLIDE2: two (joint x and y axes: the reacher's target)
+TYPE_FREE, TYPE_HINGE, TYPE_SLIDE, TYPE_PLANAR, TYPE_SLIDE2 = 0, 1, 2, 3, 4
+ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER, ENV_WALKER2D, ENV_INVERTED_PENDULUM, ENV_INVERTED_DOUBLE_PENDULUM, ENV_REACHER = range(7)
+TYPE_DOFS = {TYPE_FREE: (7, 6), TYPE_HINGE: (1, 1), TYPE_SLIDE: (1, 1), TYPE_PLANAR: (3, 3), TYPE_SLIDE2: (2, 2)}
+UNLIMITED = 1e30  # joint range of an unlimited hinge
 
 
 # ----------------------------------------------------------------------------- math
@@ -162,9 +167,10 @@ def contact_points(geoms):
 
 
 # --------------------------------------------------------------------------- models
-def _link(name, parent, typ, pos, geoms, axis=None, joint_pos=(0, 0, 0), limit=(0, 0), gear=0.0, quat=(1, 0, 0, 0)):
+def _link(name, parent, typ, pos, geoms, axis=None, joint_pos=(0, 0, 0), limit=(0, 0), gear=0.0, quat=(1, 0, 0, 0),
+          ctrl_range=(-1.0, 1.0)):
     return dict(name=name, parent=parent, type=typ, pos=np.asarray(pos, float), quat=np.asarray(quat, float),
-                geoms=geoms, axis=axis, joint_pos=np.asarray(joint_pos, float), limit=limit, gear=gear)
+                geoms=geoms, axis=axis, joint_pos=np.asarray(joint_pos, float), limit=limit, gear=gear, ctrl_range=ctrl_range)
 
 
 def ant_model():
@@ -292,6 +298,81 @@ def walker2d_model():
     )
 
 
+def inverted_pendulum_model():
+    """Gym / Brax ``inverted_pendulum.xml``: a cart on a slide joint along x (range +-1) carrying a pole on a
+    hinge about y (+-90 deg); motor on the slider, gear 100, ctrlrange +-3; no collision geometry
+    (contype = conaffinity = 0). CARL's ``mass_cart`` / ``mass_pole`` defaults of 1 are placeholders, not the
+    MJCF-derived masses (``carl/envs/brax/carl_inverted_pendulum.py:27-32``)."""
+    deg = np.pi / 180
+    links = [
+        _link("cart", -1, TYPE_SLIDE, (0, 0, 0), [capsule((-0.1, 0, 0), (0.1, 0, 0), 0.1)], axis=(1, 0, 0), limit=(-1.0, 1.0),
+              gear=100.0, ctrl_range=(-3.0, 3.0)),
+        _link("pole", 0, TYPE_HINGE, (0, 0, 0), [capsule((0, 0, 0), (0.001, 0, 0.6), 0.049)], axis=(0, 1, 0),
+              limit=(-90 * deg, 90 * deg)),
+    ]
+    return dict(
+        name="inverted_pendulum", env=ENV_INVERTED_PENDULUM, links=links, density=1000.0, total_mass=None, friction=1.0,
+        init_q=np.zeros(2), dt=0.005, n_frames=4, contacts=False,
+        tunables=dict(constraint_stiffness=10000.0, constraint_vel_damping=50.0, constraint_limit_stiffness=10000.0,
+                      constraint_ang_damping=0.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.01, qd_noise=0.01, ctrl_cost=0.0, healthy_reward=1.0, z_min=-1e9, z_max=1e9,
+                        forward_weight=0.0, angle_min=-0.2, angle_max=0.2, exclude_pos=0, qd_clip=0.0, terminate=1.0,
+                        qd_uniform=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0, actuator_links=["cart"],
+    )
+
+
+def inverted_double_pendulum_model():
+    """Gym / Brax ``inverted_double_pendulum.xml``: cart (slide x, +-1) + two 0.6 m poles on unlimited hinges about y;
+    motor on the slider, gear 500, ctrlrange +-1; tip site at (0, 0, 0.6) of the second pole; no collisions."""
+    links = [
+        _link("cart", -1, TYPE_SLIDE, (0, 0, 0), [capsule((-0.1, 0, 0), (0.1, 0, 0), 0.1)], axis=(1, 0, 0), limit=(-1.0, 1.0),
+              gear=500.0),
+        _link("pole", 0, TYPE_HINGE, (0, 0, 0), [capsule((0, 0, 0), (0, 0, 0.6), 0.045)], axis=(0, 1, 0),
+              limit=(-UNLIMITED, UNLIMITED)),
+        _link("pole2", 1, TYPE_HINGE, (0, 0, 0.6), [capsule((0, 0, 0), (0, 0, 0.6), 0.045)], axis=(0, 1, 0),
+              limit=(-UNLIMITED, UNLIMITED)),
+    ]
+    return dict(
+        name="inverted_double_pendulum", env=ENV_INVERTED_DOUBLE_PENDULUM, links=links, density=1000.0, total_mass=None,
+        friction=1.0, init_q=np.zeros(3), dt=0.005, n_frames=4, contacts=False, site=("pole2", (0.0, 0.0, 0.6)), obs_dim=8,
+        tunables=dict(constraint_stiffness=10000.0, constraint_vel_damping=50.0, constraint_limit_stiffness=10000.0,
+                      constraint_ang_damping=0.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.01, qd_noise=0.1, ctrl_cost=0.0, healthy_reward=10.0, z_min=-1e9, z_max=1e9,
+                        forward_weight=0.0, angle_min=0.0, angle_max=0.0, exclude_pos=0, qd_clip=10.0, terminate=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0, actuator_links=["cart"],
+    )
+
+
+def reacher_model():
+    """Gym / Brax ``reacher.xml``: two 0.1 m capsule links on hinges about z (joint0 unlimited, joint1 +-3 rad), the
+    fingertip sphere fused into the second link, and a target sphere on two slide joints (x, y). Gears 25 (Brax's
+    spring / positional override of the MJCF's 200). The capsule geometry is pinned by CARL's ``mass_body0`` /
+    ``mass_body1`` defaults (``carl/envs/brax/carl_reacher.py:36-41``)."""
+    z = (0, 0, 1)
+    links = [
+        _link("body0", -1, TYPE_HINGE, (0, 0, 0.01), [capsule((0, 0, 0), (0.1, 0, 0), 0.01)], axis=z,
+              limit=(-UNLIMITED, UNLIMITED), gear=25.0),
+        _link("body1", 0, TYPE_HINGE, (0.1, 0, 0), [capsule((0, 0, 0), (0.1, 0, 0), 0.01), sphere((0.11, 0, 0), 0.01)], axis=z,
+              limit=(-3.0, 3.0), gear=25.0),
+        _link("target", -1, TYPE_SLIDE2, (0, 0, 0.01), [sphere((0, 0, 0), 0.009)], axis=(1, 0, 0), limit=(-0.27, 0.27)),
+    ]
+    return dict(
+        name="reacher", env=ENV_REACHER, links=links, density=1000.0, total_mass=None, friction=1.0,
+        init_q=np.zeros(4), dt=0.005, n_frames=4, contacts=False, site=("body1", (0.11, 0.0, 0.0)), obs_dim=11,
+        # unit effective masses / inertias (scale 1): the 36 g links would need a far smaller step otherwise
+        tunables=dict(constraint_stiffness=5000.0, constraint_vel_damping=50.0, constraint_limit_stiffness=1000.0,
+                      constraint_ang_damping=5.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=1.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.1, qd_noise=0.005, ctrl_cost=1.0, healthy_reward=0.0, z_min=-1e9, z_max=1e9,
+                        forward_weight=0.0, angle_min=0.0, angle_max=0.0, exclude_pos=0, qd_clip=0.0, terminate=0.0,
+                        qd_uniform=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0, actuator_links=["body0", "body1"],
+    )
+
+
 def build_system(model: dict, tunables: dict | None = None) -> dict:
     """Derive masses / inertias (MuJoCo inertiafromgeom) and pack the float32 system table."""
     links = model["links"]
@@ -315,7 +396,7 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     for l in links:
         q_idx.append(qi)
         qd_idx.append(qdi)
-        nq, nqd = {TYPE_FREE: (7, 6), TYPE_HINGE: (1, 1), TYPE_PLANAR: (3, 3)}[l["type"]]
+        nq, nqd = TYPE_DOFS[l["type"]]
         qi += nq
         qdi += nqd
     act_of = {name: i for i, name in enumerate(model["actuator_links"])}
@@ -338,8 +419,8 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
         t[o + L_MASS] = m
         t[o + L_GEAR] = l["gear"]
         t[o + L_ACT] = act_of.get(l["name"], -1)
-        t[o + L_CTRL_LO], t[o + L_CTRL_HI] = -1.0, 1.0
-        pts = contact_points(l["geoms"])
+        t[o + L_CTRL_LO], t[o + L_CTRL_HI] = l["ctrl_range"]
+        pts = contact_points(l["geoms"]) if model.get("contacts", True) else []
         t[o + L_FIRST_PT] = len(pts_all)
         t[o + L_N_PT] = len(pts)
         max_pts = max(max_pts, len(pts))
@@ -359,17 +440,29 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     t[H_ANGLE_MIN], t[H_ANGLE_MAX], t[H_EXCLUDE_POS], t[H_QD_CLIP] = ep["angle_min"], ep["angle_max"], ep["exclude_pos"], ep["qd_clip"]
     t[H_TERMINATE], t[H_MAX_CHILD_POINTS] = ep["terminate"], max_pts
     t[H_QD_UNIFORM] = ep.get("qd_uniform", 0.0)  # Hopper / Walker2d draw qd uniformly, the others N(0,1)
+    t[H_QD_NOISE] = ep.get("qd_noise", ep["reset_noise"])
+    ranges = {tuple(l["ctrl_range"]) for l in links if l["name"] in act_of}
+    assert len(ranges) == 1 and next(iter(ranges))[0] == -next(iter(ranges))[1], "one symmetric ctrl_range per body"
+    t[H_ACT_SCALE] = next(iter(ranges))[1]
+    if model.get("site"):
+        site_link, site_pos = model["site"]
+        t[H_SITE_LINK] = names.index(site_link)
+        o = OFF_LINKS + LINK_STRIDE * names.index(site_link)
+        t[o + L_SITE:o + L_SITE + 3] = site_pos
     t[OFF_INIT_Q:OFF_INIT_Q + qi] = model["init_q"]
-    stock_friction = float(np.max([p[3] for p in pts_all]))
+    stock_friction = float(np.max([p[3] for p in pts_all])) if pts_all else float(model["friction"])
     return dict(
         name=model["name"], table=t.astype(np.float32), link_names=names, n_links=n, n_q=qi, n_qd=qdi,
         n_points=len(pts_all), n_act=len(model["actuator_links"]), stock_masses=[float(p[0]) for p in props],
         stock_gravity=model["stock_gravity"], stock_friction=stock_friction,
         stock_elasticity=model["stock_elasticity"], stock_ang_damping=model["stock_ang_damping"],
-        tunables=tun, obs_dim=(qi - int(ep["exclude_pos"])) + qdi, state_words=((13 * n + 3) // 4) * 4,
+        tunables=tun, obs_dim=model.get("obs_dim", (qi - int(ep["exclude_pos"])) + qdi), state_words=((13 * n + 3) // 4) * 4,
+        act_scale=float(t[H_ACT_SCALE]),
         dt=model["dt"] * model["n_frames"],
     )
 
 
-MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model, "walker2d": walker2d_model}
+MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model, "walker2d": walker2d_model,
+          "inverted_pendulum": inverted_pendulum_model, "inverted_double_pendulum": inverted_double_pendulum_model,
+          "reacher": reacher_model}
 SYSTEMS = {k: build_system(f()) for k, f in MODELS.items()}

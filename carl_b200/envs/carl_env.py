@@ -220,6 +220,11 @@ class CARLEnv(abc.ABC):
         context_space = self.get_context_space()
         space_defaults = context_space.get_default_context()
         defaults = dict(space_defaults)
+        # features registered under a key that differs from their NAME (the reference's `mass_pole2`,
+        # carl_inverted_double_pendulum.py:33-35) are missing from the name-keyed defaults but still settable
+        for key, feat in self.get_context_features().items():
+            if key not in defaults:
+                defaults[key] = feat.default_value
         defaults.update(self.extension_features)
         names = list(defaults.keys())
         self._feature_names = names
@@ -239,6 +244,9 @@ class CARLEnv(abc.ABC):
             filled = {}
             for k, c in renamed.items():
                 f = context_space.insert_defaults({n: v for n, v in c.items() if n in space_defaults or n not in defaults})
+                for n in defaults:
+                    if n not in space_defaults and n not in self.extension_features:
+                        f[n] = c.get(n, defaults[n])
                 for n, d in self.extension_features.items():
                     if n in c:
                         f[n] = c[n]

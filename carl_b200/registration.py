@@ -3,7 +3,8 @@
 from __future__ import annotations
 
 ENV_NAMES = ["CARLCartPole", "CARLPendulum", "CARLAcrobot", "CARLMountainCar", "CARLMountainCarContinuous",
-             "CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d"]
+             "CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d",
+             "CARLBraxInvertedPendulum", "CARLBraxInvertedDoublePendulum", "CARLBraxReacher"]
 
 
 def register_envs(namespace: str = "carl_b200") -> list[str]:

@@ -43,6 +43,9 @@ extern "C" {
 #define CARLB_BRAX_HALFCHEETAH 17 /* carl/envs/brax/carl_halfcheetah.py:14 */
 #define CARLB_BRAX_HOPPER 18      /* carl/envs/brax/carl_hopper.py:14 */
 #define CARLB_BRAX_WALKER2D 19    /* carl/envs/brax/carl_walker2d.py:14 (same kernels, new table) */
+#define CARLB_BRAX_INVERTED_PENDULUM 20        /* carl/envs/brax/carl_inverted_pendulum.py:9 (slide joint + new table) */
+#define CARLB_BRAX_INVERTED_DOUBLE_PENDULUM 21 /* carl/envs/brax/carl_inverted_double_pendulum.py:9 */
+#define CARLB_BRAX_REACHER 22                  /* carl/envs/brax/carl_reacher.py:9 (two-slide target body) */
 
 /* state / context precision of a handle */
 #define CARLB_F32 0 /* throughput mode: fp32 state and context in HBM */

@@ -33,11 +33,14 @@
 enum { MAXL = 12, MAXP = 32, MAXQ = 24, HDR = 32, LSTR = 40, PSTR = 8 };
 enum { OFF_L = HDR, OFF_P = HDR + LSTR * MAXL, OFF_Q = HDR + LSTR * MAXL + PSTR * MAXP, TABLE_N = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ };
 enum { hN_LINKS = 0, hN_Q, hN_QD, hN_POINTS, hN_FRAMES, hDT, hENV, hN_ACT, hK, hCV, hKL, hCA, hERP, hVDAMP, hMSCALE,
-       hISCALE, hNOISE, hCTRL, hHEALTHY, hZMIN, hZMAX, hFWD, hAMIN, hAMAX, hEXCL, hQDCLIP, hTERM };
+       hISCALE, hNOISE, hCTRL, hHEALTHY, hZMIN, hZMAX, hFWD, hAMIN, hAMAX, hEXCL, hQDCLIP, hTERM, hMAXCP, hQDUNI,
+       hSITE_LINK, hQDNOISE, hACTSCALE };
 enum { lPARENT = 0, lTYPE, lQ, lQD, lTPOS = 4, lTROT = 7, lJPOS = 11, lJROT = 14, lLO = 18, lHI = 19, lCOM = 20,
-       lIROT = 23, lIDIAG = 27, lMASS = 30, lGEAR = 31, lACT = 32, lCLO = 33, lCHI = 34, lFIRSTP = 35, lNP = 36 };
-enum { T_FREE = 0, T_HINGE = 1, T_PLANAR = 3 };
-enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2, E_WALKER2D = 3 };
+       lIROT = 23, lIDIAG = 27, lMASS = 30, lGEAR = 31, lACT = 32, lCLO = 33, lCHI = 34, lFIRSTP = 35, lNP = 36, lSITE = 37 };
+/* T_SLIDE: prismatic joint along the joint x axis (carts of brax.envs.inverted_pendulum /
+ * inverted_double_pendulum); T_SLIDE2: two prismatic dofs, joint x and y (target of brax.envs.reacher) */
+enum { T_FREE = 0, T_HINGE = 1, T_SLIDE = 2, T_PLANAR = 3, T_SLIDE2 = 4 };
+enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2, E_WALKER2D = 3, E_IPENDULUM = 4, E_IDPENDULUM = 5, E_REACHER = 6 };
 
 /* Arithmetic type of the restatement: float (the reference's JAX pipeline) by default; built a
  * second time with -DORACLE_F64 as the round-off-free yardstick that tells float32 noise (stiff
@@ -204,6 +207,20 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
       fv[0] = -k * j.jpos[0] - cv * j.jvel[0]; fv[1] = 0; fv[2] = 0;
       fa[1] -= ca * j.jang[1];
       fa[2] -= ca * j.jang[2];
+    } else if (type == T_SLIDE || type == T_SLIDE2) {
+      /* prismatic: no relative rotation at all (a second alignment torque on the y axes), springs on the
+       * constrained offsets only, range limit and actuator force along the first sliding axis */
+      f3 ey = {0, 1, 0}, ayc, t2;
+      rot3(ey, j.jrot, ayc);
+      cross3(ayc, ey, t2);
+      for (int q = 0; q < 3; ++q) fa[q] += k * t2[q];
+      for (int q = 0; q < 3; ++q) fa[q] -= ca * j.jang[q];
+      real dpos = 0.0f;
+      if (j.jpos[0] < lt[lLO]) dpos = lt[lLO] - j.jpos[0];
+      if (j.jpos[0] > lt[lHI]) dpos = lt[lHI] - j.jpos[0];
+      fv[0] = kl * dpos + tau[l];
+      fv[1] = (type == T_SLIDE) ? (-k * j.jpos[1] - cv * j.jvel[1]) : 0.0f;
+      fv[2] = -k * j.jpos[2] - cv * j.jvel[2];
     } else {
       for (int q = 0; q < 3; ++q) fv[q] = -k * j.jpos[q] - cv * j.jvel[q];
       real dang = 0.0f;
@@ -335,6 +352,10 @@ static void inverse_kinematics(const real *sys, const real *rows, real *q, real 
         origin_vel_of(s, lt, vo);
         q[qi] = o[0] - lt[lTPOS]; q[qi + 1] = o[2] - lt[lTPOS + 2]; q[qi + 2] = j.psi;
         qd[qdi] = vo[0]; qd[qdi + 1] = vo[2]; qd[qdi + 2] = j.jang[0];
+      } else if (type == T_SLIDE || type == T_SLIDE2) {
+        q[qi] = j.jpos[0];
+        qd[qdi] = j.jvel[0];
+        if (type == T_SLIDE2) { q[qi + 1] = j.jpos[1]; qd[qdi + 1] = j.jvel[1]; }
       } else {
         q[qi] = j.psi;
         qd[qdi] = j.jang[0];
@@ -343,10 +364,38 @@ static void inverse_kinematics(const real *sys, const real *rows, real *q, real 
   }
 }
 
-static void make_obs(const real *sys, const real *q, const real *qd, real *obs) {
-  int nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD], ex = (int)sys[hEXCL];
+/* world position of the env's site (pendulum tip / reacher fingertip): x.take(link).do(Transform(pos=site)) */
+static void site_pos(const real *sys, const real *rows, real *o) {
+  int l = (int)sys[hSITE_LINK];
+  const real *lt = sys + OFF_L + LSTR * l;
+  f3 org, r;
+  origin_of(rows + 13 * l, lt, org);
+  rot3(lt + lSITE, rows + 13 * l + 3, r);
+  for (int k = 0; k < 3; ++k) o[k] = org[k] + r[k];
+}
+
+static void make_obs(const real *sys, const real *rows, const real *q, const real *qd, real *obs) {
+  int nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD], ex = (int)sys[hEXCL], env = (int)sys[hENV];
   real clip = sys[hQDCLIP];
   int k = 0;
+  if (env == E_IDPENDULUM) { /* brax.envs.inverted_double_pendulum._get_obs */
+    obs[k++] = q[0];
+    obs[k++] = SIN(q[1]); obs[k++] = SIN(q[2]);
+    obs[k++] = COS(q[1]); obs[k++] = COS(q[2]);
+    for (int i = 0; i < 3; ++i) obs[k++] = FMIN(FMAX(qd[i], -10.0f), 10.0f);
+    return;
+  }
+  if (env == E_REACHER) { /* brax.envs.reacher._get_obs: cos, sin, target q, arm qd, tip - target */
+    f3 tip, tgt;
+    site_pos(sys, rows, tip);
+    origin_of(rows + 13 * 2, sys + OFF_L + LSTR * 2, tgt);
+    obs[k++] = COS(q[0]); obs[k++] = COS(q[1]);
+    obs[k++] = SIN(q[0]); obs[k++] = SIN(q[1]);
+    obs[k++] = q[2]; obs[k++] = q[3];
+    obs[k++] = qd[0]; obs[k++] = qd[1];
+    for (int i = 0; i < 3; ++i) obs[k++] = tip[i] - tgt[i];
+    return;
+  }
   for (int i = ex; i < nq; ++i) obs[k++] = q[i];
   for (int i = 0; i < nqd; ++i) {
     real v = qd[i];
@@ -396,6 +445,14 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
           trans[0] = ql[0]; trans[2] = ql[1];
           tvel[0] = qdl[0]; tvel[2] = qdl[1];
           angle = ql[2]; rate = qdl[2];
+        } else if (type == T_SLIDE || type == T_SLIDE2) {
+          for (int k = 0; k < 3; ++k) { trans[k] = axis[k] * ql[0]; tvel[k] = axis[k] * qdl[0]; }
+          if (type == T_SLIDE2) {
+            f3 ey = {0, 1, 0}, axis_y;
+            rot3(ey, lt + lJROT, axis_y);
+            for (int k = 0; k < 3; ++k) { trans[k] += axis_y[k] * ql[1]; tvel[k] += axis_y[k] * qdl[1]; }
+          }
+          angle = 0.0f; rate = 0.0f;
         } else {
           angle = ql[0]; rate = qdl[0];
         }
@@ -430,7 +487,7 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
     }
     real qq[MAXQ], qqd[MAXQ], ob[64];
     inverse_kinematics(sys, rows, qq, qqd);
-    make_obs(sys, qq, qqd, ob);
+    make_obs(sys, rows, qq, qqd, ob);
     for (int i = 0; i < obs_dim; ++i) obs[(size_t)e * obs_dim + i] = (float)ob[i];
   }
 }
@@ -470,7 +527,7 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
     real q[MAXQ], qd[MAXQ];
     inverse_kinematics(sys, rows, q, qd);
     real ob[64];
-    make_obs(sys, q, qd, ob);
+    make_obs(sys, rows, q, qd, ob);
     real dt_env = sys[hDT] * sys[hN_FRAMES];
     real xvel = (o1[0] - o0[0]) / dt_env;
     int healthy = 1;
@@ -486,6 +543,21 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
     }
     real r = sys[hFWD] * xvel + sys[hHEALTHY] - sys[hCTRL] * act_sq;
     int done = (sys[hTERM] > 0.0f) && !healthy;
+    if (env == E_IPENDULUM) { /* brax.envs.inverted_pendulum.step: reward 1, done = |obs[1]| > 0.2 */
+      r = 1.0f;
+      done = (q[1] < 0.0f ? -q[1] : q[1]) > 0.2f;
+    } else if (env == E_IDPENDULUM) { /* tip = x.take(2) o (0,0,0.6); x, _, y = tip.pos */
+      f3 tip;
+      site_pos(sys, rows, tip);
+      real dist_penalty = 0.01f * (tip[0] * tip[0]) + (tip[2] - 2.0f) * (tip[2] - 2.0f);
+      real vel_penalty = 1e-3f * (qd[1] * qd[1]) + 5e-3f * (qd[2] * qd[2]);
+      r = 10.0f - dist_penalty - vel_penalty;
+      done = tip[2] <= 1.0f;
+    } else if (env == E_REACHER) { /* reward_dist + reward_ctrl = -|tip - target| - sum(a^2) */
+      real d2 = ob[8] * ob[8] + ob[9] * ob[9] + ob[10] * ob[10];
+      r = (0.0f - SQRT(d2)) + (0.0f - act_sq);
+      done = 0;
+    }
     elapsed[e] += 1;
     if (max_steps > 0 && elapsed[e] >= max_steps) done = 1;
     if (done && autoreset) {

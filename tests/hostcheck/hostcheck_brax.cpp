@@ -19,7 +19,7 @@ static void wr(float* p, const LinkState& s) {
   p[7] = s.vel.x; p[8] = s.vel.y; p[9] = s.vel.z; p[10] = s.ang.x; p[11] = s.ang.y; p[12] = s.ang.z;
 }
 
-static void obs_of(const float* sys, const LinkState* st, float* obs, float* root /*x,z,angle,ok*/) {
+static void obs_of(const float* sys, const LinkState* st, float* obs, float* root /*x,z,angle,ok,q1,qd1,qd2,site xyz*/) {
   const int L = (int)sys[H_N_LINKS], nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
   float q[MAX_Q], qd[MAX_Q];
   for (int l = 0; l < L; ++l) {
@@ -31,15 +31,24 @@ static void obs_of(const float* sys, const LinkState* st, float* obs, float* roo
       qd[qdi] = vo.x; qd[qdi + 1] = vo.y; qd[qdi + 2] = vo.z; qd[qdi + 3] = al.x; qd[qdi + 4] = al.y; qd[qdi + 5] = al.z;
     } else {
       const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], 0.0f);
-      const int nd = type == TYPE_PLANAR ? 3 : 1;
+      const int nd = type_ndof(type);
       for (int k = 0; k < nd; ++k) { q[qi + k] = jo.q[k]; qd[qdi + k] = jo.qd[k]; }
     }
   }
   const int ex = (int)sys[H_EXCLUDE_POS];
   const float clip = sys[H_QD_CLIP];
   int k = 0;
-  for (int i = ex; i < nq; ++i) obs[k++] = q[i];
-  for (int i = 0; i < nqd; ++i) { float v = qd[i]; if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip); obs[k++] = v; }
+  const int kind = (int)sys[H_ENV];
+  V3 site = v3(0, 0, 0);
+  if (kind >= ENV_INVERTED_PENDULUM) site = site_position(sys, st[(int)sys[H_SITE_LINK]], st[kind == ENV_REACHER ? 2 : 0]);
+  if (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER) {
+    const int D = kind == ENV_REACHER ? 11 : 8;
+    for (int i = 0; i < D; ++i) obs[i] = special_obs_entry(kind, i, q, qd, site);
+  } else {
+    for (int i = ex; i < nq; ++i) obs[k++] = q[i];
+    for (int i = 0; i < nqd; ++i) { float v = qd[i]; if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip); obs[k++] = v; }
+  }
+  root[4] = q[1]; root[5] = qd[1]; root[6] = nqd > 2 ? qd[2] : 0.0f; root[7] = site.x; root[8] = site.y; root[9] = site.z;
   bool ok = true;
   for (int i = 2; i < nq; ++i) ok = ok && q[i] > -100.0f && q[i] < 100.0f;
   for (int i = 0; i < nqd; ++i) ok = ok && qd[i] > -100.0f && qd[i] < 100.0f;
@@ -62,7 +71,7 @@ void hc_brax_init(const float* sys, int n, const float* q_all, const float* qd_a
     float* rows = state + (size_t)e * words;
     memset(rows, 0, sizeof(float) * words);
     for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);
-    float root[4];
+    float root[10];
     obs_of(sys, st, obs + (size_t)e * D, root);
   }
 }
@@ -77,7 +86,7 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     const float* act = actions + (size_t)e * A;
     LinkState st[MAX_LINKS];
     for (int l = 0; l < L; ++l) st[l] = rd(rows + l * LINK_WORDS);
-    float before[4], after[4], ob[64];
+    float before[10], after[10], ob[64];
     obs_of(sys, st, ob, before);
     float act_sq = 0.0f;
     for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
@@ -133,8 +142,9 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     else if (kind == ENV_WALKER2D)
       healthy = !(after[1] < sys[H_HEALTHY_Z_MIN]) && !(after[1] > sys[H_HEALTHY_Z_MAX]) && !(after[2] > sys[H_ANGLE_MAX]) &&
                 !(after[2] < sys[H_ANGLE_MIN]);
-    const float r = sys[H_FORWARD_WEIGHT] * xvel + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
+    float r = sys[H_FORWARD_WEIGHT] * xvel + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
     bool done = sys[H_TERMINATE] > 0.0f && !healthy;
+    if (kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after[4], after[5], after[6], v3(after[7], after[8], after[9]), act_sq, r, done);
     elapsed[e] += 1;
     if (max_steps > 0 && elapsed[e] >= max_steps) done = true;
     for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);

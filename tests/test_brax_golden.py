@@ -8,7 +8,8 @@ import pytest
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "brax")
 BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper",
-          "walker2d": "CARLBraxWalker2d"}
+          "walker2d": "CARLBraxWalker2d", "inverted_pendulum": "CARLBraxInvertedPendulum",
+          "inverted_double_pendulum": "CARLBraxInvertedDoublePendulum", "reacher": "CARLBraxReacher"}
 
 
 def _load(body):

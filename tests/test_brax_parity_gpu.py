@@ -11,7 +11,8 @@ from tests.brax_util import assert_close_scaled, random_q
 
 pytestmark = pytest.mark.gpu
 BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper",
-          "walker2d": "CARLBraxWalker2d"}
+          "walker2d": "CARLBraxWalker2d", "inverted_pendulum": "CARLBraxInvertedPendulum",
+          "inverted_double_pendulum": "CARLBraxInvertedDoublePendulum", "reacher": "CARLBraxReacher"}
 
 
 def make_env(body, n, rng, mode="applied", **kw):
@@ -147,7 +148,9 @@ def test_fused_rollout_equals_stepwise(body):
         assert torch.equal(r, traj["reward"][t]) and torch.equal(te.to(torch.uint8), traj["done"][t])
     assert torch.equal(a_env.state, b_env.state)
     assert int(traj["done"].sum()) > 0
-    assert traj["actions"].abs().max() <= 1.0
+    assert traj["actions"].abs().max() <= a_env._sysd["act_scale"]  # uniform over the action space (+-3 for the inverted pendulum)
+    if body == "inverted_pendulum":
+        assert traj["actions"].abs().max() > 1.0
 
 
 def test_noise_reset_statistics_and_autoreset_to_first_state():
@@ -213,6 +216,58 @@ def test_brax_api_shapes_and_batch_size():
     with pytest.raises(RuntimeError):
         E.CARLBraxAnt(contexts={0: {"gravity": -9.8}}, context_mode="applied").kernel_params(
             np.zeros((1, 1)), ["bogus"], "applied")
+
+
+def test_pendulum_and_reacher_api_and_reset():
+    """SURVEY 8(f) row 2 bodies: shapes, action spaces (Box(ctrl_range), wrappers.py:48-50), noise resets and
+    the env layers (inverted pendulum: reward 1, done = |angle| > 0.2; double pendulum: done = tip z <= 1;
+    reacher: target inside the 0.2 disc, never done, reward = -|tip - target| - |a|^2)."""
+    import carl_b200.envs as E
+
+    n = 2048
+    ip = E.CARLBraxInvertedPendulum(num_envs=n)
+    obs, _ = ip.reset(seed=0)
+    o = obs["obs"].cpu().numpy()
+    assert o.shape == (n, 4) and np.abs(o).max() <= 0.01 + 1e-6 and o.std() > 0.004
+    assert ip.single_action_space.low[0] == -3.0 and ip.single_action_space.high[0] == 3.0
+    obs, r, te, tr, _ = ip.step(torch.zeros(n, 1, device="cuda"))
+    assert (r == 1.0).all() and not te.any()
+    q = np.zeros((n, 2), np.float32); q[:, 1] = np.linspace(-0.4, 0.4, n)
+    ip.reset_from_q(q, np.zeros((n, 2), np.float32))
+    ip2 = E.CARLBraxInvertedPendulum(num_envs=n, autoreset=False)
+    ip2.reset_from_q(q, np.zeros((n, 2), np.float32))
+    obs, r, te, tr, _ = ip2.step(torch.zeros(n, 1, device="cuda"))
+    ang = obs["obs"][:, 1]
+    assert torch.equal(te, ang.abs() > 0.2) and te.any() and not te.all()
+
+    idp = E.CARLBraxInvertedDoublePendulum(num_envs=n, autoreset=False)
+    obs, _ = idp.reset(seed=0)
+    o = obs["obs"].cpu().numpy()
+    assert o.shape == (n, 8) and np.abs(o[:, 1:3]).max() <= 0.011 and (o[:, 3:5] > 0.9999).all()
+    assert 0.08 < o[:, 5:].std() < 0.12  # qd = 0.1 N(0, 1)
+    obs, r, te, tr, _ = idp.step(torch.zeros(n, 1, device="cuda"))
+    assert not te.any() and (r > 9.0).all()  # upright: tip z ~ 1.2 -> 10 - (1.2 - 2)^2 - ...
+    q = np.zeros((n, 3), np.float32); q[:, 1] = 1.5  # first pole nearly horizontal: tip below 1
+    idp.reset_from_q(q, np.zeros((n, 3), np.float32))
+    obs, r, te, tr, _ = idp.step(torch.zeros(n, 1, device="cuda"))
+    assert te.all()
+
+    re = E.CARLBraxReacher(num_envs=n)
+    obs, _ = re.reset(seed=0)
+    o = obs["obs"].cpu().numpy()
+    assert o.shape == (n, 11)
+    dist = np.hypot(o[:, 4], o[:, 5])
+    assert dist.max() <= 0.2 + 1e-6 and 0.08 < dist.mean() < 0.12  # dist = 0.2 U
+    np.testing.assert_allclose(o[:, 0:2] ** 2 + o[:, 2:4] ** 2, 1.0, atol=1e-5)
+    a = (torch.rand(n, 2, device="cuda") * 2 - 1)
+    obs, r, te, tr, _ = re.step(a)
+    o = obs["obs"]
+    want = -(o[:, 8:11].norm(dim=1)) - (a * a).sum(dim=1)
+    torch.testing.assert_close(r, want, rtol=1e-5, atol=1e-6)
+    assert not te.any() and not tr.any()
+    np.testing.assert_allclose(obs["obs"][:, 4:6].cpu().numpy(), obs["obs"][:, 4:6].cpu().numpy())
+    t = re.rollout(30, policy_seed=1, record=True)
+    assert torch.isfinite(t["obs"]).all() and int(t["done"].sum()) == 0
 
 
 def test_full_size_properties_config4():

@@ -9,7 +9,7 @@ from carl_b200.envs import brax_system as bs
 from oracle.brax import OracleBraxEnv
 from tests.brax_util import BraxHostCheck, assert_close_scaled, random_ctx, random_q
 
-BODIES = ["ant", "halfcheetah", "hopper", "walker2d"]
+BODIES = ["ant", "halfcheetah", "hopper", "walker2d", "inverted_pendulum", "inverted_double_pendulum", "reacher"]
 
 
 @pytest.fixture(scope="module")
@@ -30,6 +30,13 @@ def test_pipeline_init_matches(hc, body):
     # forward then inverse kinematics is the identity on (q[ex:], qd)
     ex = int(sysd["table"][bs.H_EXCLUDE_POS])
     want = np.concatenate([q[:, ex:], qd], axis=1)
+    if body == "inverted_double_pendulum":  # _get_obs: q[:1], sin(q[1:]), cos(q[1:]), clip(qd)
+        want = np.concatenate([q[:, :1], np.sin(q[:, 1:]), np.cos(q[:, 1:]), np.clip(qd, -10, 10)], axis=1)
+    if body == "reacher":  # cos(theta), sin(theta), target, arm qd, fingertip - target (planar 2-link arm)
+        th1, th12 = q[:, 0].astype(np.float64), (q[:, 0] + q[:, 1]).astype(np.float64)
+        tip = np.stack([0.1 * np.cos(th1) + 0.11 * np.cos(th12), 0.1 * np.sin(th1) + 0.11 * np.sin(th12), 0.01 + 0 * th1], axis=1)
+        tgt = np.concatenate([q[:, 2:4], np.full((q.shape[0], 1), 0.01)], axis=1)
+        want = np.concatenate([np.cos(q[:, :2]), np.sin(q[:, :2]), q[:, 2:4], qd[:, :2], tip - tgt], axis=1)
     if body == "ant":  # the free root's quaternion is normalised by forward()
         want[:, 1:5] /= np.linalg.norm(want[:, 1:5], axis=1, keepdims=True)
         want[:, 13 + 3:13 + 6] = o_ref[:, 13 + 3:13 + 6]  # angular velocity is reported in the local frame
@@ -99,8 +106,55 @@ def test_physical_sanity(body):
     env.init_from_q(q, np.zeros((1, sysd["n_qd"]), np.float32))
     for t in range(100):
         obs, r, d, _ = env.step(np.zeros((1, sysd["n_act"]), np.float32))
+    if body == "reacher":
+        assert np.isfinite(obs).all() and np.abs(obs[0, 6:8]).max() < 0.5
+        return
+    if body.startswith("inverted"):  # an unstable equilibrium: the pole may fall, the cart stays on its rail
+        assert np.isfinite(obs).all() and abs(obs[0, 0]) < 1.1
+        return
     assert np.isfinite(obs).all() and np.abs(obs[0, -sysd["n_qd"]:]).max() < 0.5  # came to rest
     rows = env.state[0, :13 * sysd["n_links"]].reshape(-1, 13)
-    assert rows[:, 2].min() > 0.0  # every link COM above the plane
+    if sysd["n_points"] > 0:
+        assert rows[:, 2].min() > 0.0  # every link COM above the plane
     if body == "ant":
         assert 0.4 < obs[0, 0] < 0.6  # torso height ~0.55 (the reference notebook shows z = 0.559)
+
+
+def test_cart_pendulum_small_oscillation_period_is_analytic(hc):
+    """Known answer for the restated joint physics: without joint limits the pole of the inverted-pendulum
+    body, released 0.05 rad from hanging DOWN on its freely sliding cart, must swing with the textbook period
+    of a compound pendulum on a cart, omega^2 = m g d (M + m) / (I_end (M + m) - m^2 d^2), where the inertia
+    about the COM is the spring backend's effective one (spring_inertia_scale = 1: unity).
+    Checked for the oracle and for the kernel source."""
+    sysd = bs.build_system(bs.MODELS["inverted_pendulum"](), {"constraint_limit_stiffness": 0.0})
+    assert sysd["tunables"]["spring_inertia_scale"] == 1.0 and sysd["tunables"]["spring_mass_scale"] == 0.0
+    ctx = random_ctx(sysd, 1, np.random.default_rng(0), applied=False)
+    ctx[:, 3] = 0.0  # no angular damping
+    t = sysd["table"]
+    o = bs.OFF_LINKS + bs.LINK_STRIDE
+    M, m = float(t[bs.OFF_LINKS + bs.L_MASS]), float(t[o + bs.L_MASS])
+    d = float(np.linalg.norm(t[o + bs.L_COM:o + bs.L_COM + 3]))
+    i_end = 1.0 + m * d * d  # effective COM inertia I^(1 - 1) = 1
+    omega = np.sqrt(m * 9.81 * d * (M + m) / (i_end * (M + m) - m * m * d * d))
+    q = np.array([[0.0, np.pi - 0.05]], np.float32)
+    qd = np.zeros((1, 2), np.float32)
+    n_steps, dt = 300, sysd["dt"]
+
+    def fitted_omega(angles):
+        a = np.unwrap(np.asarray(angles, np.float64)) - np.pi
+        tt = dt * np.arange(1, n_steps + 1)
+        grid = omega * np.linspace(0.7, 1.3, 601)
+        resid = [np.sum((a + 0.05 * np.cos(w * tt)) ** 2) for w in grid]
+        return grid[int(np.argmin(resid))]
+
+    ora = OracleBraxEnv(sysd, ctx, autoreset=False, max_steps=0)
+    ora.init_from_q(q, qd)
+    st, ob = hc.init(sysd, q, qd)
+    el = np.zeros(1, dtype=np.int32)
+    ang_o, ang_k = [], []
+    zero = np.zeros((1, 1), np.float32)
+    for _ in range(n_steps):
+        ang_o.append(ora.step(zero)[0][0, 1])
+        ang_k.append(hc.step(sysd, st, ctx, zero, el, 0, 0, st.copy(), ob.copy())[0][0, 1])
+    assert abs(fitted_omega(ang_o) / omega - 1.0) < 0.02
+    assert abs(fitted_omega(ang_k) / omega - 1.0) < 0.02

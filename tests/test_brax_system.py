@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from carl_b200.envs import brax_system as bs
-from carl_b200.envs.brax import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d
+from carl_b200.envs.brax import (CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxInvertedDoublePendulum,
+                                 CARLBraxInvertedPendulum, CARLBraxReacher, CARLBraxWalker2d)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -51,11 +52,35 @@ def test_shapes_match_reference_observation_sizes():
 
 def test_every_mass_feature_names_a_link():
     for cls, key in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
-                     (CARLBraxWalker2d, "walker2d")):
+                     (CARLBraxWalker2d, "walker2d"), (CARLBraxInvertedPendulum, "inverted_pendulum"),
+                     (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher")):
         links = bs.SYSTEMS[key]["link_names"]
         for f in cls.get_context_features():
             if f.startswith("mass_"):
                 assert f[len("mass_"):] in links
+
+
+def test_reacher_masses_match_carl_defaults():
+    """carl/envs/brax/carl_reacher.py:36-41: mass_body0 / mass_body1 pin the capsule + fingertip geometry."""
+    s = bs.SYSTEMS["reacher"]
+    d = CARLBraxReacher.get_context_space().get_default_context()
+    for name in ("body0", "body1"):
+        assert s["stock_masses"][s["link_names"].index(name)] == pytest.approx(d[f"mass_{name}"], rel=2e-7)
+
+
+def test_pendulum_and_reacher_shapes():
+    """brax.envs.inverted_pendulum (obs q ++ qd = 4), inverted_double_pendulum (8), reacher (11); the inverted
+    pendulum's action space is its ctrl_range +-3 (BraxGymWrapper, carl/envs/brax/wrappers.py:48-50)."""
+    ip, idp, r = (bs.SYSTEMS[k] for k in ("inverted_pendulum", "inverted_double_pendulum", "reacher"))
+    assert (ip["n_links"], ip["n_q"], ip["n_qd"], ip["obs_dim"], ip["n_act"], ip["n_points"]) == (2, 2, 2, 4, 1, 0)
+    assert (idp["n_links"], idp["n_q"], idp["n_qd"], idp["obs_dim"], idp["n_act"], idp["n_points"]) == (3, 3, 3, 8, 1, 0)
+    assert (r["n_links"], r["n_q"], r["n_qd"], r["obs_dim"], r["n_act"], r["n_points"]) == (3, 4, 4, 11, 2, 0)
+    assert ip["act_scale"] == 3.0 and idp["act_scale"] == 1.0 and r["act_scale"] == 1.0
+    # bug-compatible default context of the double pendulum: no `mass_pole2` key (feature NAME is `mass_pole`)
+    d = CARLBraxInvertedDoublePendulum.get_default_context()
+    assert "mass_pole2" not in d and "mass_pole" in d
+    assert list(CARLBraxInvertedPendulum.get_context_features()) == [
+        "gravity", "friction", "elasticity", "mass_cart", "mass_pole", "ang_damping", "viscosity"]
 
 
 def test_inertia_from_geom_known_values():

@@ -181,3 +181,29 @@ def test_pinned_registry_and_check_only_staging():
     assert (dst == a[2]).all()
     hostmem.release(a)
     assert not hostmem.is_pinned(a[1].ctypes.data, a[1].nbytes)
+
+
+def test_brax_param_rows_and_shapes_match_native_query(native_lib):
+    """Every Brax class (incl. the inverted pendulums and the reacher): host-side kernel_params rows, obs / action
+    dims and the action range agree with what the C ABI reports for the kind."""
+    import carl_b200.envs as E
+    from carl_b200 import _native
+    from carl_b200.envs import brax_system as bs
+
+    for name in ("CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d", "CARLBraxInvertedPendulum",
+                 "CARLBraxInvertedDoublePendulum", "CARLBraxReacher"):
+        cls = getattr(E, name)
+        info = _native.query_env(_native.KIND[cls.kind])
+        sysd = bs.SYSTEMS[cls.env_name]
+        d = cls.get_default_context()
+        names = list(d)
+        t = np.array([[float(d[n]) for n in names]])
+        for mode in ("reference", "applied"):
+            assert cls.kernel_params(t, names, mode).shape == (1, info.n_param_rows)
+        assert (info.obs_dim, info.act_dim, info.state_words) == (sysd["obs_dim"], sysd["n_act"], sysd["state_words"])
+        assert info.act_high == sysd["act_scale"] and info.act_low == -sysd["act_scale"]
+        applied = cls.kernel_params(t, names, "applied")
+        for j, ln in enumerate(sysd["link_names"]):
+            want = d.get(f"mass_{ln}", sysd["stock_masses"][j])
+            assert applied[0, 5 + j] == pytest.approx(want)
+    assert E.brax.UNSUPPORTED_BODIES == ("CARLBraxHumanoid", "CARLBraxHumanoidStandup", "CARLBraxPusher")

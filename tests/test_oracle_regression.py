@@ -27,7 +27,7 @@ def test_classic_oracle_replays_fixture(kind):
     np.testing.assert_allclose(env.state[0], fx["state"], rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("body", ["ant", "halfcheetah", "hopper", "walker2d"])
+@pytest.mark.parametrize("body", ["ant", "halfcheetah", "hopper", "walker2d", "inverted_pendulum", "inverted_double_pendulum", "reacher"])
 def test_brax_oracle_replays_fixture(body):
     fx = G["brax"][body]
     sysd = bs.SYSTEMS[body]

@@ -51,7 +51,7 @@ def brax(body):
 
 def main():
     g = {"note": "oracle self-regression fixtures (float64 restatements); NOT reference goldens",
-         "classic": {k: classic(k) for k in KINDS}, "brax": {b: brax(b) for b in ("ant", "halfcheetah", "hopper", "walker2d")}}
+         "classic": {k: classic(k) for k in KINDS}, "brax": {b: brax(b) for b in ("ant", "halfcheetah", "hopper", "walker2d", "inverted_pendulum", "inverted_double_pendulum", "reacher")}}
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1)
     print("wrote", os.path.abspath(OUT))
