@@ -28,7 +28,7 @@ EXPORTS = [
     "carlb_abi_version", "carlb_last_error", "carlb_query_env", "carlb_env_create", "carlb_env_destroy",
     "carlb_env_bind", "carlb_env_configure", "carlb_env_seed", "carlb_env_reset", "carlb_env_step",
     "carlb_env_step_host", "carlb_stage_actions", "carlb_env_rollout", "carlb_mixed_step", "carlb_env_set_peers",
-    "carlb_brax_set_system", "carlb_brax_reset_from_q", "carlb_launch_count",
+    "carlb_brax_set_system", "carlb_brax_reset_from_q", "carlb_brax_goal_step", "carlb_launch_count",
     "carlb_gather_create", "carlb_gather_export", "carlb_gather_open", "carlb_gather_attach", "carlb_gather_wait",
     "carlb_gather_destroy",
 ]
@@ -95,6 +95,8 @@ def load() -> ctypes.CDLL:
     lib.carlb_env_set_peers.argtypes = [c_void_p, c_int, POINTER(c_void_p)]
     lib.carlb_brax_set_system.argtypes = [c_void_p, c_void_p, c_int, c_int]
     lib.carlb_brax_reset_from_q.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.carlb_brax_goal_step.argtypes = [c_void_p, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_void_p, c_void_p]
     lib.carlb_gather_create.argtypes = [c_int, c_int, c_int, c_int64, c_int, POINTER(c_void_p)]
     lib.carlb_gather_export.argtypes = [c_void_p, c_void_p]
     lib.carlb_gather_open.argtypes = [c_void_p, c_int, c_void_p]

@@ -475,4 +475,23 @@ int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* 
   return brax_reset_from(env, mask, q, qd, (cudaStream_t)stream);
 }
 
+int carlb_brax_goal_step(carlb_env_t* env, int idx0, int idx1, double dt, double* position, const double* goal,
+                         const double* radius, double* reward, uint8_t* success, void* stream) {
+  int rc = check_ready(env, "carlb_brax_goal_step");
+  if (rc != CARLB_OK) return rc;
+  carlb_env_info_t info;
+  if (!is_brax(env->kind) || position == nullptr || goal == nullptr || radius == nullptr || reward == nullptr ||
+      success == nullptr) {
+    set_error("carlb_brax_goal_step: needs a Brax handle and position / goal / radius / reward / success buffers");
+    return CARLB_ERR_INVALID;
+  }
+  brax_query(env->kind, &info);
+  if (idx0 < 0 || idx1 < 0 || idx0 >= info.obs_dim || idx1 >= info.obs_dim) {
+    set_error("carlb_brax_goal_step: observation indices (%d, %d) outside [0, %d)", idx0, idx1, info.obs_dim);
+    return CARLB_ERR_INVALID;
+  }
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  return brax_goal_step(env, idx0, idx1, dt, position, goal, radius, reward, success, (cudaStream_t)stream);
+}
+
 }  // extern "C"

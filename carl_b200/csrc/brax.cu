@@ -757,6 +757,40 @@ static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, co
   return launch_brax_step_we<4, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
 }
 
+// ------------------------------------------------------------------------ goal epilogue
+// BraxWalkerGoalWrapper.step (brax_walker_goal_wrapper.py:124-140), one thread per env, float64 like the
+// reference's NumPy scalars: dead-reckoned xy position from two observation entries, progress reward,
+// radius termination. np.linalg.norm of a 2-vector = sqrt(x*x + y*y) (this unit is built with -fmad=false).
+__global__ void __launch_bounds__(128) brax_goal_kernel(int n, int obs_dim, const float* obs, int idx0, int idx1, double dt,
+                                                        double* position, const double* goal, const double* radius,
+                                                        double* reward, uint8_t* terminated, uint8_t* success) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double2 pos = reinterpret_cast<const double2*>(position)[i];
+  const double2 g = reinterpret_cast<const double2*>(goal)[i];
+  const float* o = obs + (size_t)i * obs_dim;
+  const double nx = pos.x + (double)o[idx0] * dt, ny = pos.y + (double)o[idx1] * dt;
+  const double cx = g.x - nx, cy = g.y - ny, px = g.x - pos.x, py = g.y - pos.y;
+  const double cur = sqrt(cx * cx + cy * cy), prev = sqrt(px * px + py * py);
+  const double d = prev - cur;
+  reward[i] = d > 0.0 ? d : 0.0;
+  reinterpret_cast<double2*>(position)[i] = make_double2(nx, ny);
+  const bool reached = fabs(cur) <= radius[i];
+  success[i] = reached ? 1 : 0;
+  if (reached) terminated[i] = 1;
+}
+
+int brax_goal_step(const carlb_env* env, int idx0, int idx1, double dt, double* position, const double* goal,
+                   const double* radius, double* reward, uint8_t* success, cudaStream_t st) {
+  carlb_env_info_t info;
+  brax_query(env->kind, &info);
+  brax_goal_kernel<<<(env->n + 127) / 128, 128, 0, st>>>(env->n, info.obs_dim, env->bufs.obs, idx0, idx1, dt, position, goal,
+                                                         radius, reward, env->bufs.terminated, success);
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
 int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
   BraxHandle* h = static_cast<BraxHandle*>(env->brax_sys);
   h->seed = seed;

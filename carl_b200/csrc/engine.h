@@ -58,6 +58,8 @@ int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32
                  int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
 int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_contact);
 int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st);
+int brax_goal_step(const carlb_env* env, int idx0, int idx1, double dt, double* position, const double* goal,
+                   const double* radius, double* reward, uint8_t* success, cudaStream_t st);
 
 #define CARLB_CUDA_CHECK(expr)                                                            \
   do {                                                                                    \

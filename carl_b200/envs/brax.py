@@ -126,8 +126,10 @@ class CARLBraxEnv(CARLEnv):
         radius = vals[:, names.index("target_radius")]
         self._goal_state = dict(
             position=torch.zeros(self.num_envs, 2, dtype=torch.float64, device=self.device),
-            goal=torch.from_numpy(goal).to(self.device),
-            radius=torch.from_numpy(np.ascontiguousarray(radius)).to(self.device),
+            goal=torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float64)).to(self.device).contiguous(),
+            radius=torch.from_numpy(np.ascontiguousarray(radius, dtype=np.float64)).to(self.device).contiguous(),
+            reward=torch.zeros(self.num_envs, dtype=torch.float64, device=self.device),
+            success=torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device),
             dt=brax_goals.MJCF_TIMESTEP[self.env_name],
             idx=brax_goals.STATE_INDICES[self.env_name],
         )
@@ -159,13 +161,17 @@ class CARLBraxEnv(CARLEnv):
             return state, reward, te, tr, info
         from carl_b200.envs import brax_goals
 
+        from carl_b200 import _native
+
         g = self._goal_state
         host = isinstance(state["obs"], np.ndarray)
-        obs_t = self._obs  # device copy of the same observation
-        vel = obs_t[:, g["idx"]].to(torch.float64)
-        g["position"], r, reached = brax_goals.goal_step(g["position"], g["goal"], g["radius"], vel, g["dt"])
-        te_t = self._terminated_b | reached
-        info["success"] = reached.to(torch.int64)
+        # one launch on the step's stream: dead reckoning, progress reward, radius termination (OR-ed into
+        # the handle's terminated flags), success -- float64 like the reference wrapper's NumPy scalars
+        _native.check(self._lib.carlb_brax_goal_step(
+            self._handle, int(g["idx"][0]), int(g["idx"][1]), float(g["dt"]), g["position"].data_ptr(), g["goal"].data_ptr(),
+            g["radius"].data_ptr(), g["reward"].data_ptr(), g["success"].data_ptr(), self._stream()))
+        r, te_t = g["reward"], self._terminated_b
+        info["success"] = g["success"].to(torch.int64)
         if host:
             reward, te = r.cpu().numpy(), te_t.cpu().numpy()
             info["success"] = info["success"].cpu().numpy()

@@ -184,6 +184,16 @@ int carlb_brax_set_system(carlb_env_t* env, const float* table, int n_floats, in
  * `Ant.reset` etc. (the reference's JAX PRNG stream is not reproducible without JAX). */
 int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* q, const float* qd, void* stream);
 
+/* Brax positional-goal epilogue: one `BraxWalkerGoalWrapper.step`
+ * (carl/envs/brax/brax_walker_goal_wrapper.py:124-140) for every env instance, run on the handle's
+ * current observation right after carlb_env_step, in float64 like the reference's NumPy:
+ *   new = position + (obs[idx0], obs[idx1]) * dt;  reward = max(0, |goal - position| - |goal - new|);
+ *   position = new;  reached = |goal - new| <= radius;  terminated |= reached;  success = reached.
+ * All pointers are DEVICE memory: position[n][2] (in/out), goal[n][2], radius[n], reward[n] (out,
+ * float64), success[n] (out, 0/1); `terminated` is the handle's bound flag buffer, OR-ed in place. */
+int carlb_brax_goal_step(carlb_env_t* env, int idx0, int idx1, double dt, double* position, const double* goal,
+                         const double* radius, double* reward, uint8_t* success, void* stream);
+
 /* ---- fused cross-GPU observation gather (the path's one exchange step) ----------
  * One symmetric buffer per rank, mapped into every other rank's process with CUDA IPC. Once a
  * gather is attached, every observation-producing launch of the handle (reset / step / rollout)

@@ -104,3 +104,67 @@ def test_goal_wrapper_on_device_rewards_nonnegative():
                 assert (reward >= 0).all() and "success" in info
     env = CARLBraxAnt()  # no varying target -> plain env reward
     assert not env._goal_active
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cls_name,body", [("CARLBraxAnt", "ant"), ("CARLBraxHopper", "hopper")])
+def test_goal_kernel_epilogue_matches_reference_wrapper(cls_name, body):
+    """carlb_brax_goal_step (one launch after the step, float64) against the reference wrapper's own per-env
+    statements driven by the SAME observations: reward to 1e-12, terminated / success identical; the goal
+    state survives Brax auto-resets (the wrapper sits outside AutoResetWrapper) and is zeroed by reset()."""
+    import torch
+
+    import carl_b200.envs as E
+
+    cls = getattr(E, cls_name)
+    rng = np.random.default_rng(0)
+    n, T = 64, 40
+    dirs = rng.choice(list(bg.DIRECTION_VALUES), n)
+    ctxs = {i: dict(cls.get_default_goal_context(), target_direction=int(dirs[i]), target_distance=float(0.02 + 0.02 * i),
+                    target_radius=0.1) for i in range(n)}
+    env = cls(contexts=ctxs, max_episode_steps=15)
+    assert env._goal_active
+    obs, info = env.reset(seed=0)
+    assert (info["success"] == 0).all()
+    idx, dt = bg.STATE_INDICES[body], bg.MJCF_TIMESTEP[body]
+    pos = [(0, 0)] * n
+    goal = [np.array(bg.DIRECTION_VALUES[int(dirs[i])]) * ctxs[i]["target_distance"] for i in range(n)]
+    n_reached = 0
+    for t in range(T):
+        a = torch.from_numpy(rng.uniform(-1, 1, (n, env._info.act_dim)).astype(np.float32)).cuda()
+        obs, r, te, tr, info = env.step(a)
+        o = obs["obs"].cpu().numpy()
+        brax_done = env._elapsed.cpu().numpy() == 0  # auto-reset this step (time limit / unhealthy)
+        r, te, succ = r.cpu().numpy(), te.cpu().numpy(), info["success"].cpu().numpy()
+        assert r.dtype == np.float64
+        for i in range(n):
+            new_position = np.array(list(pos[i])) + np.array([o[i, idx[0]], o[i, idx[1]]]) * dt
+            cur = np.linalg.norm(goal[i] - new_position)
+            prev = np.linalg.norm(goal[i] - pos[i])
+            pos[i] = new_position
+            assert r[i] == pytest.approx(max(0, prev - cur), abs=1e-12)
+            reached = abs(cur) <= 0.1
+            assert bool(succ[i]) == reached
+            assert bool(te[i]) == (reached or bool(brax_done[i]))
+            n_reached += int(reached)
+    assert n_reached > 0
+    np.testing.assert_allclose(env._goal_state["position"].cpu().numpy(), np.array(pos), atol=1e-12)
+    # numpy actions -> numpy results through the same kernel
+    obs, r, te, tr, info = env.step(rng.uniform(-1, 1, (n, env._info.act_dim)).astype(np.float32))
+    assert isinstance(r, np.ndarray) and r.dtype == np.float64 and isinstance(info["success"], np.ndarray)
+    env.reset()
+    assert float(env._goal_state["position"].abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+def test_language_goal_observation():
+    import carl_b200.envs as E
+
+    ctxs = {i: dict(E.CARLBraxAnt.get_default_goal_context(), target_direction=d, target_distance=10.0 + i)
+            for i, d in enumerate((1, 112, 4))}
+    env = E.CARLBraxAnt(contexts=ctxs, use_language_goals=True)
+    obs, info = env.reset(seed=0)
+    assert set(obs["obs"]) == {"obs", "goal"} and len(obs["obs"]["goal"]) == 3
+    assert obs["obs"]["goal"][1] == bg.goal_description(ctxs[1])
+    obs, r, te, tr, info = env.step(np.zeros((3, 8), np.float32))
+    assert obs["obs"]["goal"][2] == bg.goal_description(ctxs[2]) and r.shape == (3,)
