@@ -10,7 +10,8 @@ import numpy as np
 import torch
 
 from carl_b200.context import ContextSampler, UniformFloatContextFeature
-from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d, CARLPendulum, ContextTable, MixedBatch)
+from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxInvertedDoublePendulum,
+                            CARLBraxInvertedPendulum, CARLBraxReacher, CARLBraxWalker2d, CARLPendulum, ContextTable, MixedBatch)
 
 
 def table(cls, feats, n):
@@ -54,7 +55,11 @@ def main():
     nb = 8192
     for cls, feats, name in ((CARLBraxHalfcheetah, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "halfcheetah"),
                              (CARLBraxHopper, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "hopper"),
-                             (CARLBraxWalker2d, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "walker2d")):
+                             (CARLBraxWalker2d, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "walker2d"),
+                             (CARLBraxInvertedPendulum, {"gravity": (-15, -5), "mass_cart": (5, 20), "mass_pole": (2, 8)}, "inverted_pendulum"),
+                             (CARLBraxInvertedDoublePendulum, {"gravity": (-15, -5), "mass_cart": (5, 20), "mass_pole": (2, 8)},
+                              "inverted_double_pendulum"),
+                             (CARLBraxReacher, {"gravity": (-15, -5), "mass_body0": (0.02, 0.06), "mass_body1": (0.02, 0.06)}, "reacher")):
         env = cls(contexts=table(cls, feats, nb), context_mode="applied")
         env.reset(seed=0)
         T = 20
