@@ -161,7 +161,7 @@ struct LaneCtx {
 };
 
 // n_frames spring substeps for the sub-envs of this warp. `s` is this lane's link.
-template <int E>
+template <int E, bool SP>
 __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, EnvScratch& w, LinkState& s, float tau) {
   constexpr int LPE = Lanes<E>::LPE;
   const float dt = sys[H_DT];
@@ -175,7 +175,7 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
     if (c.is_link && c.type != TYPE_FREE) {
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale);
+      const JointOut jo = joint_resolve<SP>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale);
       wr = jo.child;
       float* pw = w.pw + c.sl * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
@@ -236,7 +236,8 @@ struct RootFacts {
   V3 site;             // pendulum tip (world) / reacher: fingertip - target
 };
 
-template <int E>
+// SP: the body may have slide joints / an env-specific observation or outcome (inverted pendulums, reacher)
+template <int E, bool SP>
 __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, EnvScratch& w, const LinkState& s) {
   constexpr int LPE = Lanes<E>::LPE;
   if (c.is_link) write_link(w.ls, c.sl, s);
@@ -253,8 +254,8 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
     } else {
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve(sys, c.lt, s, world_parent, c.plt, ps, 0.0f);
-      const int nd = type_ndof(c.type);
+      const JointOut jo = joint_resolve<SP>(sys, c.lt, s, world_parent, c.plt, ps, 0.0f);
+      const int nd = SP ? type_ndof(c.type) : (c.type == TYPE_PLANAR ? 3 : 1);
       for (int k = 0; k < nd; ++k) {
         w.q[qi + k] = jo.q[k];
         w.qd[qdi + k] = jo.qd[k];
@@ -267,10 +268,10 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   const int kind = (int)sys[H_ENV];
   RootFacts r;
   r.site = v3(0, 0, 0);
-  if (kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
+  if (SP && kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
     r.site = site_position(sys, read_link(w.ls, (int)sys[H_SITE_LINK]), read_link(w.ls, kind == ENV_REACHER ? 2 : 0));
   }
-  if (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER) {
+  if (SP && (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER)) {
     const int D = kind == ENV_REACHER ? 11 : 8;
     if (c.sl < LPE)
       for (int i = c.sl; i < D; i += LPE) w.obs[i] = special_obs_entry(kind, i, w.q, w.qd, r.site);
@@ -308,6 +309,7 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
 }
 
 // Env layer of brax.envs.{ant,half_cheetah,hopper}.step after the pipeline advanced.
+template <bool SP>
 __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& before, const RootFacts& after,
                                             float act_sq_sum, float& reward, bool& done) {
   const float dt_env = sys[H_DT] * sys[H_N_FRAMES];
@@ -328,7 +330,7 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   const float ctrl_cost = sys[H_CTRL_COST] * act_sq_sum;
   reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
   done = (sys[H_TERMINATE] > 0.0f) && !healthy;
-  if (kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
+  if (SP && kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
 }
 
 template <int W, int E>
@@ -381,7 +383,7 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
 // One env-step per sub-env: [AutoReset zeroing] -> n_frames substeps -> obs/reward/done ->
 // EpisodeWrapper truncation -> AutoReset (state/obs replaced by the stored first ones where done).
 // Every __syncwarp() is reached by all 32 lanes: per-env conditions only predicate memory traffic.
-template <int W, int E>
+template <int W, int E, bool SP>
 __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W, E>& sm, const float* actions, int n_steps,
                                                uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& traj,
                                                int stock_contact) {
@@ -405,7 +407,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
   const uint64_t gid = (uint64_t)(seg.global_offset + env);
   float reward = 0.0f;
   bool done = false;
-  RootFacts before = compute_obs<E>(sys, c, w, s);
+  RootFacts before = compute_obs<E, SP>(sys, c, w, s);
   for (int t = 0; t < n_steps; ++t) {
     // actions of this step: given tensor [n][A] (single step) / [K][n][A] (rollout) or Philox policy
     float a = 0.0f;
@@ -424,9 +426,9 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
     for (int k = 0; k < A; ++k) act_sq += w.act[k] * w.act[k];  // jp.sum(jp.square(action)), in order
     float tau = 0.0f;
     if (c.is_link && c.act >= 0) tau = c.lt[L_GEAR] * fminf(fmaxf(w.act[c.act], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
-    pipeline_steps<E>(sys, c, w, s, tau);
-    const RootFacts after = compute_obs<E>(sys, c, w, s);
-    env_outcome(sys, before, after, act_sq, reward, done);
+    pipeline_steps<E, SP>(sys, c, w, s, tau);
+    const RootFacts after = compute_obs<E, SP>(sys, c, w, s);
+    env_outcome<SP>(sys, before, after, act_sq, reward, done);
     // EpisodeWrapper: steps += 1; done = where(steps >= episode_length, 1, done)
     el += 1;
     if (seg.max_steps > 0 && el >= seg.max_steps) done = true;
@@ -445,7 +447,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
       if (do_reset) s = read_link(w.ls, c.is_link ? c.sl : 0);
       __syncwarp();
       // root facts of the restored state (also recomputes the unchanged obs of the other sub-envs)
-      const RootFacts fresh = compute_obs<E>(sys, c, w, s);
+      const RootFacts fresh = compute_obs<E, SP>(sys, c, w, s);
       if (do_reset) {
         before = fresh;
         el = 0;
@@ -485,7 +487,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
   }
 }
 
-template <int W, int E>
+template <int W, int E, bool SP>
 __global__ void __launch_bounds__(W * 32, W == 4 ? (E >= 3 ? 5 : 4) : 2) brax_step_kernel(const __grid_constant__ BraxSeg seg,
                                                                           const float* actions, int n_steps,
                                                                           uint64_t policy_seed, uint32_t step_base,
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? (E >= 3 ? 5 : 4) : 2) brax_st
   stage_system(sm.sys, seg.sys, &sm.bar);
   const int warp = threadIdx.x >> 5;
   if ((blockIdx.x * W + warp) * E < seg.n)  // warp-uniform: at least one sub-env of this warp is real
-    brax_step_body<W, E>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact);
+    brax_step_body<W, E, SP>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact);
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
 }
 
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
         }
         __syncwarp();
       }
-      compute_obs<1>(sys, c, w, s);
+      compute_obs<1, true>(sys, c, w, s);
       const int D = seg.obs_dim;
       for (int i = c.L * LINK_WORDS + lane; i < seg.state_words; i += 32) w.ls[i] = 0.0f;  // padding words
       __syncwarp();
@@ -728,17 +730,17 @@ static int brax_pack(const float* table) {
   return 1;
 }
 
-template <int W, int E>
+template <int W, int E, bool SP>
 static cudaError_t launch_brax_step_we(const BraxSeg& seg, int n, const float* actions, int n_steps, uint64_t policy_seed,
                                        uint32_t step_base, const carlb_traj_t& tj, int stock_contact, cudaStream_t st) {
   typedef SmemLayoutT<W, E> Smem;
   static bool configured = false;
   if (!configured) {  // > 48 KB of dynamic shared memory needs the opt-in attribute
-    cudaError_t e = cudaFuncSetAttribute(brax_step_kernel<W, E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(brax_step_kernel<W, E, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  brax_step_kernel<W, E><<<brax_grid(n, W * E), W * 32, sizeof(Smem), st>>>(seg, actions, n_steps, policy_seed, step_base, tj,
+  brax_step_kernel<W, E, SP><<<brax_grid(n, W * E), W * 32, sizeof(Smem), st>>>(seg, actions, n_steps, policy_seed, step_base, tj,
                                                                           stock_contact);
   return cudaGetLastError();
 }
@@ -747,14 +749,19 @@ static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, co
                                     uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& tj, cudaStream_t st) {
   const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
   const int n = env->n, sc = h->stock_contact;
+  if ((int)h->host_table[H_ENV] >= ENV_INVERTED_PENDULUM) {
+    // inverted pendulums / reacher (2-3 links): the instantiation with slide joints and their env layers
+    if (brax_pack(h->host_table) == 1) return launch_brax_step_we<4, 1, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    return launch_brax_step_we<4, 4, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  }
   switch (brax_pack(h->host_table)) {
-    case 4: return launch_brax_step_we<4, 4>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
-    case 3: return launch_brax_step_we<4, 3>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    case 4: return launch_brax_step_we<4, 4, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    case 3: return launch_brax_step_we<4, 3, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
     default: break;
   }
   // one env per warp: 7-warp CTAs (2 per SM) keep large grids close to whole waves of 148 SMs
-  if (n >= 4096) return launch_brax_step_we<7, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
-  return launch_brax_step_we<4, 1>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  if (n >= 4096) return launch_brax_step_we<7, 1, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  return launch_brax_step_we<4, 1, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
 }
 
 // ------------------------------------------------------------------------ goal epilogue
@@ -769,7 +776,10 @@ __global__ void __launch_bounds__(128) brax_goal_kernel(int n, int obs_dim, cons
   const double2 pos = reinterpret_cast<const double2*>(position)[i];
   const double2 g = reinterpret_cast<const double2*>(goal)[i];
   const float* o = obs + (size_t)i * obs_dim;
-  const double nx = pos.x + (double)o[idx0] * dt, ny = pos.y + (double)o[idx1] * dt;
+  // `np.array([state[i0], state[i1]]) * self.dt` is a float32 array times a scalar: the product is rounded
+  // to float32 BEFORE it is added to the float64 position (NumPy keeps the array's dtype)
+  const float dtf = (float)dt;
+  const double nx = pos.x + (double)(o[idx0] * dtf), ny = pos.y + (double)(o[idx1] * dtf);
   const double cx = g.x - nx, cy = g.y - ny, px = g.x - pos.x, py = g.y - pos.y;
   const double cur = sqrt(cx * cx + cy * cy), prev = sqrt(px * px + py * py);
   const double d = prev - cur;

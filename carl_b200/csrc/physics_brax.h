@@ -167,7 +167,10 @@ struct JointOut {
   float qd[3];
 };
 
-// child `c` (table row lt), parent state `p` (ignored when world_parent), parent row plt
+// child `c` (table row lt), parent state `p` (ignored when world_parent), parent row plt.
+// SLIDES = false compiles the prismatic branches out (the locomotion bodies have none: their kernels
+// keep the instruction footprint they had before the pendulum / reacher bodies were added).
+template <bool SLIDES = true>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
                                 const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f) {
   JointOut o;
@@ -209,7 +212,7 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     // slide-x / slide-z / hinge-y root: only the off-plane offset and off-axis rotation are constrained
     fv = v3(-k * jpos.x - cv * jvel.x, 0.0f, 0.0f);
     fa = fa - ca * v3(0.0f, jang.y, jang.z);
-  } else if (type == TYPE_SLIDE || type == TYPE_SLIDE2) {
+  } else if (SLIDES && (type == TYPE_SLIDE || type == TYPE_SLIDE2)) {
     // prismatic: free along the joint x axis (x and y for SLIDE2), the remaining offsets sprung,
     // every rotation locked (second alignment torque on the y axes); limit + actuator force along x
     const V3 ey = v3(0, 1, 0);
@@ -243,7 +246,7 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     const V3 vo = origin_velocity(c, lt);
     o.q[0] = xc_pos.x - t_pos.x; o.q[1] = xc_pos.z - t_pos.z; o.q[2] = psi;
     o.qd[0] = vo.x; o.qd[1] = vo.z; o.qd[2] = jang.x;
-  } else if (type == TYPE_SLIDE || type == TYPE_SLIDE2) {
+  } else if (SLIDES && (type == TYPE_SLIDE || type == TYPE_SLIDE2)) {
     o.q[0] = jpos.x; o.q[1] = jpos.y;
     o.qd[0] = jvel.x; o.qd[1] = jvel.y;
   }

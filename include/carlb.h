@@ -187,7 +187,7 @@ int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* 
 /* Brax positional-goal epilogue: one `BraxWalkerGoalWrapper.step`
  * (carl/envs/brax/brax_walker_goal_wrapper.py:124-140) for every env instance, run on the handle's
  * current observation right after carlb_env_step, in float64 like the reference's NumPy:
- *   new = position + (obs[idx0], obs[idx1]) * dt;  reward = max(0, |goal - position| - |goal - new|);
+ *   new = position + float32((obs[idx0], obs[idx1]) * dt);  reward = max(0, |goal - position| - |goal - new|);
  *   position = new;  reached = |goal - new| <= radius;  terminated |= reached;  success = reached.
  * All pointers are DEVICE memory: position[n][2] (in/out), goal[n][2], radius[n], reward[n] (out,
  * float64), success[n] (out, 0/1); `terminated` is the handle's bound flag buffer, OR-ed in place. */
