@@ -27,7 +27,7 @@ KIND = {
 EXPORTS = [
     "carlb_abi_version", "carlb_last_error", "carlb_query_env", "carlb_env_create", "carlb_env_destroy",
     "carlb_env_bind", "carlb_env_configure", "carlb_env_seed", "carlb_env_reset", "carlb_env_step",
-    "carlb_env_step_host", "carlb_stage_actions", "carlb_env_rollout", "carlb_mixed_step", "carlb_env_set_peers",
+    "carlb_env_step_host", "carlb_env_step_host_checked", "carlb_stage_actions", "carlb_env_rollout", "carlb_mixed_step", "carlb_env_set_peers",
     "carlb_brax_set_system", "carlb_brax_reset_from_q", "carlb_brax_goal_step", "carlb_launch_count",
     "carlb_gather_create", "carlb_gather_export", "carlb_gather_open", "carlb_gather_attach", "carlb_gather_wait",
     "carlb_gather_destroy",
@@ -89,6 +89,8 @@ def load() -> ctypes.CDLL:
     lib.carlb_env_reset.argtypes = [c_void_p, c_void_p, c_void_p]
     lib.carlb_env_step.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
     lib.carlb_env_step_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.carlb_env_step_host_checked.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_void_p]
     lib.carlb_stage_actions.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int]
     lib.carlb_env_rollout.argtypes = [c_void_p, c_int, c_uint64, c_uint32, c_void_p, c_int, POINTER(Traj), c_void_p]
     lib.carlb_mixed_step.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), c_int, c_void_p]

@@ -240,6 +240,8 @@ int carlb_env_destroy(carlb_env_t* env) {
   if (env == nullptr) return CARLB_OK;
   if (env->gather != nullptr) gather_forget_env(env->gather, env);
   if (is_brax(env->kind)) brax_destroy(env);
+  if (env->undo_block != nullptr) cudaFree(env->undo_block);
+  if (env->bad_action_host != nullptr) cudaFreeHost(env->bad_action_host);
   delete env;
   return CARLB_OK;
 }
@@ -388,6 +390,86 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
       CARLB_CUDA_CHECK(cudaMemcpyAsync(truncated_host, env->bufs.truncated, n, cudaMemcpyDeviceToHost, st));
   }
   CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  return CARLB_OK;
+}
+
+// Undo log + report word of the checked step, allocated once per handle on first use.
+static int ensure_step_check(carlb_env* env, int n_actions, StepCheck* chk) {
+  carlb_env_info_t info;
+  carlb_query_env(env->kind, &info);
+  const size_t n = (size_t)env->n;
+  const size_t word = env->precision == CARLB_F64 ? 8 : 4;
+  const size_t state_b = ((n * info.state_words * word + 15) / 16) * 16, el_b = ((n * 4 + 15) / 16) * 16,
+               flag_b = ((n + 15) / 16) * 16, rng_b = 2 * n * 8;
+  if (env->undo_block == nullptr) {
+    CARLB_CUDA_CHECK(cudaMalloc(&env->undo_block, state_b + el_b + 2 * flag_b + rng_b));
+    CARLB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&env->bad_action_host), sizeof(int), cudaHostAllocMapped));
+    *env->bad_action_host = 0;
+  }
+  unsigned char* p = static_cast<unsigned char*>(env->undo_block);
+  chk->n_actions = n_actions;
+  chk->bad_action = env->bad_action_host;
+  chk->undo_state = p;
+  chk->undo_rng = reinterpret_cast<uint64_t*>(p + state_b);
+  chk->undo_elapsed = reinterpret_cast<int32_t*>(p + state_b + rng_b);
+  chk->undo_sbt = p + state_b + rng_b + el_b;
+  chk->undo_rng_flag = p + state_b + rng_b + el_b + flag_b;
+  return CARLB_OK;
+}
+
+int carlb_env_step_host_checked(carlb_env_t* env, const void* actions_host, int act_dtype, int n_actions, float* obs_host,
+                                float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream) {
+  int rc = check_ready(env, "carlb_env_step_host_checked");
+  if (rc != CARLB_OK) return rc;
+  if (actions_host == nullptr || !valid_act_dtype(env, act_dtype)) {
+    set_error("carlb_env_step_host_checked: null actions or action dtype %d not valid for env kind %d", act_dtype, env->kind);
+    return CARLB_ERR_INVALID;
+  }
+  carlb_env_info_t info;
+  carlb_query_env(env->kind, &info);
+  static const bool zc_on = [] {
+    const char* e = getenv("CARLB_ZEROCOPY");
+    return e == nullptr || e[0] == '1';
+  }();
+  const bool discrete_check = n_actions > 0 && info.act_discrete != 0;
+  bool zero_copy = zc_on && discrete_check && is_classic(env->kind) && obs_host && reward_host && terminated_host &&
+                   truncated_host;
+  if (zero_copy) {
+    // the four result pointers are verified once (the host layer passes the same page-locked block every
+    // step); the action pointer -- which a caller may change freely -- every time
+    const void* res[4] = {obs_host, reward_host, terminated_host, truncated_host};
+    for (int k = 0; k < 4 && zero_copy; ++k) {
+      if (env->zc_verified[k] == res[k]) continue;
+      if (is_mapped_host(res[k])) env->zc_verified[k] = res[k];
+      else zero_copy = false;
+    }
+    zero_copy = zero_copy && is_mapped_host(actions_host);
+  }
+  if (!zero_copy) {  // staged path: range check on the host first, then the plain host-buffer step
+    if (discrete_check) {
+      rc = check_only(actions_host, (int64_t)env->n * info.act_dim, act_dtype, n_actions);
+      if (rc != CARLB_OK) return rc;
+    }
+    return carlb_env_step_host(env, actions_host, act_dtype, obs_host, reward_host, terminated_host, truncated_host, stream);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  StepCheck chk;
+  rc = ensure_step_check(env, n_actions, &chk);
+  if (rc != CARLB_OK) return rc;
+  HostMirrors hm{obs_host, reward_host, terminated_host, truncated_host};
+  rc = classic_step_checked(env, actions_host, act_dtype, st, &hm, chk);
+  if (rc != CARLB_OK) return rc;
+  CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int bad = *reinterpret_cast<volatile int*>(env->bad_action_host);
+  if (bad != 0) {  // roll every env back: the reference's env is untouched when `action_space.contains` fails
+    *env->bad_action_host = 0;
+    rc = classic_step_undo(env, st, chk);
+    if (rc != CARLB_OK) return rc;
+    CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
+    set_error("invalid action: values must lie in [0, %d) (env %d)", n_actions, bad - 1);
+    return CARLB_ERR_INVALID;
+  }
   return CARLB_OK;
 }
 

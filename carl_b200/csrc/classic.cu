@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int KIND, typename T>
-__device__ __forceinline__ void step_one(const Segment& seg, const void* actions, int i) {
+template <int KIND, typename T, bool CHK>
+__device__ __forceinline__ void step_one(const Segment& seg, const void* actions, int i, const StepCheck& chk) {
   typedef Traits<KIND> Tr;
   T p[Tr::P];
   load_rows<KIND, T>(seg, i, 0, Tr::P_STEP, p);
@@ -107,6 +107,17 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
   int el = seg.elapsed[i];
   uint8_t sb = 0;
   if (KIND == KIND_CARTPOLE) sb = seg.sbt[i];
+  uint64_t g0_hi = 0, g0_lo = 0;  // CHK: the PCG64 state before this step (when the step touches it)
+  if (CHK) {
+    StateIO<T, Tr::S>::store(chk.undo_state, i, s);
+    chk.undo_elapsed[i] = el;
+    if (KIND == KIND_CARTPOLE) chk.undo_sbt[i] = sb;
+    if (Tr::DISCRETE && (unsigned)a.i >= (unsigned)chk.n_actions) {
+      *reinterpret_cast<volatile int*>(chk.bad_action) = i + 1;  // any one offender is enough
+      chk.undo_rng_flag[i] = 0;
+      return;  // this env does not step; the host rolls the others back after the sync
+    }
+  }
 
   Pcg64 g;
   bool rng_live = false;
@@ -114,6 +125,7 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
   if (KIND == KIND_ACROBOT) {
     if (p[AC_NOISE] > (T)0) {  // env RNG draw, as AcrobotEnv.step does
       g = load_rng(seg.rng, seg.n, i);
+      if (CHK) { g0_hi = g.state_hi; g0_lo = g.state_lo; }
       rng_live = true;
       noise = (T)pcg64_uniform(g, -(double)p[AC_NOISE], (double)p[AC_NOISE]);
     }
@@ -125,12 +137,19 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
   if (seg.autoreset != CARLB_AUTORESET_NONE && (so.terminated || tr)) {
     if (seg.final_obs != nullptr) store_obs<Tr::D>(seg.final_obs, (size_t)i, o);
     load_rows<KIND, T>(seg, i, Tr::P_STEP, Tr::P, p);
-    if (!rng_live) g = load_rng(seg.rng, seg.n, i);
+    if (!rng_live) {
+      g = load_rng(seg.rng, seg.n, i);
+      if (CHK) { g0_hi = g.state_hi; g0_lo = g.state_lo; }
+    }
     rng_live = true;
     pcg64_skip<Tr::GYM_DRAWS>(g);
     env_reset<KIND, T>(s, p, g, o);
     el = 0;
     sb = 0;
+  }
+  if (CHK) {
+    chk.undo_rng_flag[i] = rng_live ? 1 : 0;
+    if (rng_live) { chk.undo_rng[i] = g0_hi; chk.undo_rng[(size_t)seg.n + i] = g0_lo; }
   }
   if (rng_live) store_rng_state(seg.rng, seg.n, i, g);
   StateIO<T, Tr::S>::store(seg.state, i, s);
@@ -153,9 +172,36 @@ template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Segment seg, const void* actions) {
   pdl_launch_dependents();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) step_one<KIND, T>(seg, actions, i);
+  if (i < seg.n) step_one<KIND, T, false>(seg, actions, i, StepCheck{});
   else pdl_wait();
   peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+}
+
+// The host-buffer step with in-kernel action validation and an undo log (StepCheck).
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) step_checked_kernel(const __grid_constant__ Segment seg, const void* actions,
+                                                              const __grid_constant__ StepCheck chk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < seg.n) step_one<KIND, T, true>(seg, actions, i, chk);
+  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+}
+
+// Roll a checked step back: state / elapsed / steps-beyond flag of every env, PCG64 state where it moved.
+template <int KIND, typename T>
+__global__ void __launch_bounds__(kBlock) step_undo_kernel(const __grid_constant__ Segment seg,
+                                                           const __grid_constant__ StepCheck chk) {
+  typedef Traits<KIND> Tr;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= seg.n) return;
+  T s[Tr::S];
+  StateIO<T, Tr::S>::load(chk.undo_state, i, s);
+  StateIO<T, Tr::S>::store(seg.state, i, s);
+  seg.elapsed[i] = chk.undo_elapsed[i];
+  if (KIND == KIND_CARTPOLE) seg.sbt[i] = chk.undo_sbt[i];
+  if (chk.undo_rng_flag[i] != 0) {
+    seg.rng[i] = chk.undo_rng[i];
+    seg.rng[(size_t)seg.n + i] = chk.undo_rng[(size_t)seg.n + i];
+  }
 }
 
 // ----------------------------------------------------------------------- mixed batch
@@ -170,11 +216,11 @@ struct MixedParams {
 template <typename T>
 __device__ __forceinline__ void mixed_dispatch(const Segment& seg, const void* actions, int i) {
   switch (seg.kind) {
-    case KIND_CARTPOLE: step_one<KIND_CARTPOLE, T>(seg, actions, i); break;
-    case KIND_PENDULUM: step_one<KIND_PENDULUM, T>(seg, actions, i); break;
-    case KIND_ACROBOT: step_one<KIND_ACROBOT, T>(seg, actions, i); break;
-    case KIND_MOUNTAINCAR: step_one<KIND_MOUNTAINCAR, T>(seg, actions, i); break;
-    default: step_one<KIND_MOUNTAINCAR_CONT, T>(seg, actions, i); break;
+    case KIND_CARTPOLE: step_one<KIND_CARTPOLE, T, false>(seg, actions, i, StepCheck{}); break;
+    case KIND_PENDULUM: step_one<KIND_PENDULUM, T, false>(seg, actions, i, StepCheck{}); break;
+    case KIND_ACROBOT: step_one<KIND_ACROBOT, T, false>(seg, actions, i, StepCheck{}); break;
+    case KIND_MOUNTAINCAR: step_one<KIND_MOUNTAINCAR, T, false>(seg, actions, i, StepCheck{}); break;
+    default: step_one<KIND_MOUNTAINCAR_CONT, T, false>(seg, actions, i, StepCheck{}); break;
   }
 }
 
@@ -456,6 +502,29 @@ int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaS
   CARLB_DISPATCH_KIND_T(env->kind, env->precision, (le = launch_step_pdl<K_, T_>(seg, actions, env->n, st)));
   g_launches++;
   CARLB_CUDA_CHECK(le);
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int classic_step_checked(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm,
+                         const StepCheck& chk) {
+  Segment seg = make_segment(env, act_dtype);
+  attach_gather(env, seg);
+  if (hm != nullptr) {
+    seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
+    seg.host_truncated = hm->truncated;
+  }
+  CARLB_DISPATCH_KIND_T(env->kind, env->precision,
+                        (step_checked_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, actions, chk)));
+  g_launches++;
+  CARLB_CUDA_CHECK(cudaGetLastError());
+  return CARLB_OK;
+}
+
+int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk) {
+  Segment seg = make_segment(env, CARLB_ACT_I32);
+  CARLB_DISPATCH_KIND_T(env->kind, env->precision, (step_undo_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, chk)));
+  g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;
 }

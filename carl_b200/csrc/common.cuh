@@ -43,6 +43,21 @@ struct Segment {
   uint8_t* host_truncated;
 };
 
+// In-kernel action validation + undo log of the host-buffer step (carlb_env_step_host_checked): the
+// step kernel itself checks every discrete action against [0, n_actions) -- the `action_space.contains`
+// assert of the gymnasium envs -- instead of a host pass over the action array before the launch, and
+// logs what it overwrites so that a step with an invalid action can be rolled back (the reference's
+// env is untouched when the assert fires).
+struct StepCheck {
+  int n_actions;           // valid discrete actions are [0, n_actions)
+  int* bad_action;         // mapped host word: 1 + index of an env whose action is invalid (0: none)
+  void* undo_state;        // T[n][S] state before this step
+  int32_t* undo_elapsed;   // [n]
+  uint8_t* undo_sbt;       // [n]
+  uint64_t* undo_rng;      // [2][n] PCG64 state words before this step (valid where undo_rng_flag)
+  uint8_t* undo_rng_flag;  // [n]
+};
+
 // Fused-gather epilogue: every thread of every CTA calls this at the end of an obs-producing
 // kernel. Stores to peer memory are fenced at system scope, the last CTA to arrive publishes the
 // launch number into every rank's flag word.

@@ -22,6 +22,11 @@ struct carlb_env {
   float* peer_obs[CARLB_MAX_PEERS] = {};
   void* brax_sys = nullptr;  // BraxHandle: device copy of the per-handle Brax system table
   carlb_gather* gather = nullptr;  // fused cross-GPU obs gather (gather.cu), or null
+  // host-buffer step with in-kernel action validation (carlb_env_step_host_checked): undo log (one device
+  // block, allocated on first use -- never per step) and the mapped host word the kernel reports into
+  void* undo_block = nullptr;
+  int* bad_action_host = nullptr;
+  const void* zc_verified[4] = {};  // result pointers already verified as mapped page-locked memory
 };
 
 namespace carlb {
@@ -42,6 +47,9 @@ struct HostMirrors {  // mapped (page-locked) host result buffers of one zero-co
   float* obs; float* reward; uint8_t* terminated; uint8_t* truncated;
 };
 int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm = nullptr);
+int classic_step_checked(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm,
+                         const StepCheck& chk);
+int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk);
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
 int classic_mixed_step(carlb_env* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,

@@ -584,12 +584,21 @@ class CARLEnv(abc.ABC):
         src = flat.ctypes.data
         # an array from carl_b200.hostmem.pinned_empty is read in place by the step kernel (range check
         # only); anything else takes one native pass: copy into the page-locked staging block + check
-        in_place = hostmem.is_pinned(src, flat.nbytes)
-        if self._lib.carlb_stage_actions(None if in_place else p[0], src, flat.size, _NP_ACT[a.dtype], n_act) != 0:
-            # gymnasium raises AssertionError from `assert self.action_space.contains(action)`
-            raise AssertionError(_native.last_error())
-        _native.check(self._lib.carlb_env_step_host(self._handle, src if in_place else p[0], _NP_ACT[a.dtype], p[1], p[2],
-                                                    p[3], p[4], self._stream()))
+        if hostmem.is_pinned(src, flat.nbytes):
+            # one call: the step kernel validates the actions while it reads them and rolls the step back
+            # if one is out of range (carlb_env_step_host_checked) -- no host pass over the array
+            rc = self._lib.carlb_env_step_host_checked(self._handle, src, _NP_ACT[a.dtype], n_act, p[1], p[2], p[3], p[4],
+                                                       self._stream())
+            if rc != 0:
+                msg = _native.last_error()
+                if msg.startswith("invalid action"):
+                    raise AssertionError(msg)  # gymnasium: `assert self.action_space.contains(action)`
+                _native.check(rc)
+        else:
+            if self._lib.carlb_stage_actions(p[0], src, flat.size, _NP_ACT[a.dtype], n_act) != 0:
+                raise AssertionError(_native.last_error())
+            _native.check(self._lib.carlb_env_step_host(self._handle, p[0], _NP_ACT[a.dtype], p[1], p[2], p[3], p[4],
+                                                        self._stream()))
         state = {"obs": io["np_obs"], "context": self._context_obs_host()}
         return state, io["np_reward"], io["np_term"], io["np_trunc"], {"context_id": self.context_id}
 

@@ -151,6 +151,16 @@ int carlb_env_step(carlb_env_t* env, const void* actions, int act_dtype, void* s
 int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtype, float* obs_host,
                         float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream);
 
+/* carlb_env_step_host plus the `assert self.action_space.contains(action)` of the gymnasium envs
+ * (carl/envs/carl_env.py:339 -> gymnasium `step`): every discrete action must lie in [0, n_actions)
+ * (n_actions <= 0: no check). With page-locked buffers the step kernel validates the actions itself while
+ * it reads them (no host pass over the action array) and logs what it overwrites; if any action is
+ * invalid the step is rolled back on the device -- the env is untouched, as in the reference -- and the
+ * call returns CARLB_ERR_INVALID with the message "invalid action ...". Otherwise the check is a host
+ * pass before the staged step. */
+int carlb_env_step_host_checked(carlb_env_t* env, const void* actions_host, int act_dtype, int n_actions, float* obs_host,
+                                float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream);
+
 /* Host helper for the call above: copy a caller's (pageable) action array into the page-locked staging
  * block in one pass and, for discrete action dtypes with n_actions > 0, range-check it like the
  * `assert self.action_space.contains(action)` of the gymnasium envs the reference steps

@@ -185,3 +185,41 @@ def test_page_locked_actions_are_read_in_place_and_match_staged_path():
     np.testing.assert_array_equal(oa["obs"], ob["obs"])
     hostmem.release(pinned)
     hostmem.release(u8)
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "acrobot", "mountaincar"])
+def test_in_kernel_action_check_rolls_the_step_back(kind):
+    """carlb_env_step_host_checked: with page-locked actions the step kernel validates them itself; one
+    invalid action anywhere -> AssertionError and EVERY env is exactly where it was (state, step counters,
+    PCG64 streams -- also for the envs that had already auto-reset inside the rejected step), as the
+    reference's env is when gymnasium's `action_space.contains` assert fires."""
+    import carl_b200.envs as E
+    from carl_b200 import hostmem
+
+    cls = {"cartpole": E.CARLCartPole, "acrobot": E.CARLAcrobot, "mountaincar": E.CARLMountainCar}[kind]
+    n, n_act = 2048, {"cartpole": 2, "acrobot": 3, "mountaincar": 3}[kind]
+    a_env = cls(num_envs=n, autoreset=True, max_episode_steps=7)   # short episodes: resets inside the rejected step
+    b_env = cls(num_envs=n, autoreset=True, max_episode_steps=7)
+    a_env.reset(seed=5)
+    b_env.reset(seed=5)
+    rng = np.random.default_rng(3)
+    pinned = hostmem.pinned_empty((n,), np.int64)
+    for t in range(20):
+        acts = rng.integers(0, n_act, size=n)
+        if t in (6, 13):  # the truncation step (every env resets) and an ordinary one
+            before = (a_env.state.clone(), a_env._elapsed.clone(), a_env._rng.clone(), a_env._sbt.clone())
+            pinned[...] = acts
+            pinned[n // 2] = n_act if t == 6 else -1
+            with pytest.raises(AssertionError, match="invalid action"):
+                a_env.step(pinned)
+            after = (a_env.state, a_env._elapsed, a_env._rng, a_env._sbt)
+            for x, y in zip(before, after):
+                assert torch.equal(x, y)
+        pinned[...] = acts
+        oa, ra, ta, tra, _ = a_env.step(pinned)
+        ob, rb, tb, trb, _ = b_env.step(acts)  # pageable -> host check + staged copy
+        np.testing.assert_array_equal(oa["obs"], ob["obs"])
+        np.testing.assert_array_equal(ta, tb)
+        np.testing.assert_array_equal(tra, trb)
+    assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env._rng, b_env._rng)
+    hostmem.release(pinned)

@@ -65,6 +65,8 @@ def main():
         out[f"python_env_step_pinned_inplace_{rows}rows_us"] = loop(pinned_step)
         out[f"c_abi_step_host_pinned_inplace_{rows}rows_us"] = loop(
             lambda: lib.carlb_env_step_host(h, pa[kk[0] % rows].ctypes.data, _native.ACT_I32, p[1], p[2], p[3], p[4], st))
+        out[f"c_abi_step_host_checked_pinned_inplace_{rows}rows_us"] = loop(
+            lambda: lib.carlb_env_step_host_checked(h, pa[kk[0] % rows].ctypes.data, _native.ACT_I32, 2, p[1], p[2], p[3], p[4], st))
         out[f"check_only_{rows}rows_us"] = loop(lambda: lib.carlb_stage_actions(None, pa[0].ctypes.data, n, _native.ACT_I32, 2), n=2000)
         hostmem.release(pa)
     out["python_env_step_uint8_us"] = loop(lambda: env.step(a8[0]))
