@@ -509,8 +509,8 @@ def run_gpu_arm(args):
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": K_e2e, "api": "CARLCartPole.step(numpy int32 actions in page-locked memory) -> numpy obs/reward/terminated/"
-                                       "truncated (carlb_env_step_host: range check on the host, actions read and "
-                                       "results written over PCIe by the step kernel itself)", "ms_per_step": float(t_e2e.item()) / K_e2e * 1e3},
+                                       "truncated (carlb_env_step_host_checked: the step kernel reads the actions over PCIe, range-checks them "
+                                       "itself -- undo log, rolled back if one is invalid -- and writes the results over PCIe)", "ms_per_step": float(t_e2e.item()) / K_e2e * 1e3},
         "roofline": {
             "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
