@@ -28,6 +28,9 @@ WANT = [
     "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    # host-path (zero-copy) kernels: bytes the L2 moved to / from system memory over PCIe
+    "lts__t_sectors_aperture_sysmem_op_write.sum", "lts__t_sectors_aperture_sysmem_op_read.sum",
+    "pcie__write_bytes.sum", "pcie__read_bytes.sum",
 ]
 
 
