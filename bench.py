@@ -598,6 +598,23 @@ def ant_leg(dev, peak, args):
     torch.cuda.synchronize(dev)
     api_ms = e0.elapsed_time(e1) / 100
     step_bytes = 1114  # R state 468 + ctx 24 + action 32 + 4 ; W state 468 + obs 108 + 4 + 2 + 4
+    # host buffers in / out: env.step(numpy float32 actions in page-locked memory) -> numpy results
+    import time
+
+    from carl_b200 import hostmem
+
+    host_acts = hostmem.pinned_empty((4, n, info.act_dim), np.float32)
+    host_acts[...] = np.random.default_rng(2).uniform(-1, 1, size=host_acts.shape).astype(np.float32)
+    for j in range(5):
+        env.step(host_acts[j % 4])
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    acc = 0.0
+    for j in range(100):
+        o_h, r_h, te_h, tr_h, _ = env.step(host_acts[j % 4])
+        acc += float(r_h[0])
+    torch.cuda.synchronize(dev)
+    e2e_ms = (time.perf_counter() - t0) / 100 * 1e3
     return {
         "workload": "CARLBraxAnt, 8192 sampled contexts (gravity/mass_torso/friction), context_mode=applied, "
                     "uniform random policy, 10 spring substeps per env-step",
@@ -607,6 +624,10 @@ def ant_leg(dev, peak, args):
                      "frac": (traj_bytes * T + step_bytes) * n / (ms / (K // T) * 1e-3) / 1e9 / peak},
         "step_api": {"value": n / (api_ms * 1e-3), "us_per_launch": api_ms * 1e3,
                      "hbm_frac_1114B": step_bytes * n / (api_ms * 1e-3) / 1e9 / peak},
+        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "us_per_step": e2e_ms * 1e3,
+                "h2d_bytes_per_step": n * info.act_dim * 4, "d2h_bytes_per_step": n * (info.obs_dim * 4 + 4 + 1 + 1),
+                "api": "CARLBraxAnt.step(numpy float32 actions in page-locked memory) -> numpy obs/reward/terminated/truncated "
+                       "(the step kernel reads the actions and writes the results over PCIe itself)"},
     }
 
 

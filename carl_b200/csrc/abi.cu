@@ -347,7 +347,7 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
   // staging buffer (PCIe reads issued by the copy engine instead of by the SMs); 0 = staged copies.
   const char* zc_env = getenv("CARLB_ZEROCOPY");
   const int zero_copy = zc_env ? (zc_env[0] - '0') : 1;
-  if (zero_copy > 0 && is_classic(env->kind) && obs_host && reward_host && terminated_host && truncated_host &&
+  if (zero_copy > 0 && obs_host && reward_host && terminated_host && truncated_host &&
       is_mapped_host(actions_host) && is_mapped_host(obs_host) && is_mapped_host(reward_host) &&
       is_mapped_host(terminated_host) && is_mapped_host(truncated_host)) {
     HostMirrors hm{obs_host, reward_host, terminated_host, truncated_host};
@@ -357,7 +357,7 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
                                        cudaMemcpyHostToDevice, st));
       act_src = env->bufs.act_staging;
     }
-    rc = classic_step(env, act_src, act_dtype, st, &hm);
+    rc = is_brax(env->kind) ? brax_step(env, act_src, act_dtype, st, &hm) : classic_step(env, act_src, act_dtype, st, &hm);
     if (rc != CARLB_OK) return rc;
     CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
     return CARLB_OK;

@@ -58,6 +58,12 @@ struct BraxSeg {
   unsigned int* peer_flags[CARLB_MAX_PEERS];
   unsigned int signal_value;
   unsigned int* block_counter;
+  // zero-copy host mirrors (carlb_env_step_host with page-locked buffers): the single-step kernel also
+  // stores obs / reward / flags straight into mapped host memory (posted PCIe writes behind the physics)
+  float* host_obs;
+  float* host_reward;
+  uint8_t* host_terminated;
+  uint8_t* host_truncated;
 };
 
 // Per-env shared-memory scratch (2.7 KB): the exchange medium between the lanes of one env.
@@ -476,6 +482,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
     for (int i = c.sl; i < D; i += LPE) {
       const float v = w.obs[i];
       seg.obs[(size_t)env * D + i] = v;
+      if (seg.host_obs != nullptr) seg.host_obs[(size_t)env * D + i] = v;
       for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
     }
     if (c.sl == 0) {
@@ -483,6 +490,11 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
       seg.terminated[env] = done ? 1 : 0;  // CARL maps brax `done` (incl. the time limit) to terminated
       seg.truncated[env] = 0;              // and truncated = False always (wrappers.py:75-78)
       seg.elapsed[env] = el;
+      if (seg.host_obs != nullptr) {
+        seg.host_reward[env] = reward;
+        seg.host_terminated[env] = done ? 1 : 0;
+        seg.host_truncated[env] = 0;
+      }
     }
   }
 }
@@ -822,11 +834,15 @@ int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
   return brax_reset_from(env, mask, nullptr, nullptr, st);
 }
 
-int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st) {
+int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm) {
   (void)act_dtype;
   BraxSeg seg;
   int rc = make_brax_seg(env, seg, "carlb_env_step");
   if (rc != CARLB_OK) return rc;
+  if (hm != nullptr) {
+    seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
+    seg.host_truncated = hm->truncated;
+  }
   carlb_traj_t tj{};
   CARLB_CUDA_CHECK(launch_brax_step(env, seg, static_cast<const float*>(actions), 1, 0, 0, tj, st));
   g_launches++;

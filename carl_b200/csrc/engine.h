@@ -61,7 +61,7 @@ int brax_create(carlb_env* env);
 void brax_destroy(carlb_env* env);
 int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st);
 int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st);
-int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st);
+int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm = nullptr);
 int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                  int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
 int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_contact);

@@ -321,3 +321,33 @@ def test_packed_lanes_equal_one_env_per_warp(tmp_path):
     for k in res["1"].files:
         np.testing.assert_array_equal(res["1"][k], res["0"][k], err_msg=k)
     assert res["1"]["ant_done"].sum() > 0
+
+
+@pytest.mark.parametrize("body", ["ant", "hopper", "reacher"])
+def test_host_buffer_step_equals_device_step(body):
+    """`step(numpy)` -- page-locked array read in place (zero copy: the kernel reads the actions from and writes
+    the results to mapped host memory) and a pageable array (staged) -- must equal `step(cuda tensor)` bit for bit."""
+    import carl_b200.envs as E
+    from carl_b200 import hostmem
+
+    cls = getattr(E, BODIES[body])
+    n = 777
+    envs = [cls(num_envs=n, max_episode_steps=9) for _ in range(3)]
+    for e in envs:
+        e.reset(seed=4)
+    A = envs[0]._info.act_dim
+    pinned = hostmem.pinned_empty((n, A), np.float32)
+    rng = np.random.default_rng(0)
+    for t in range(12):
+        a = rng.uniform(-1, 1, (n, A)).astype(np.float32)
+        pinned[...] = a
+        o0, r0, te0, tr0, _ = envs[0].step(torch.from_numpy(a).cuda())
+        o1, r1, te1, tr1, _ = envs[1].step(pinned)
+        o2, r2, te2, tr2, _ = envs[2].step(a.copy())
+        for o, r, te in ((o1, r1, te1), (o2, r2, te2)):
+            assert isinstance(o["obs"], np.ndarray)
+            np.testing.assert_array_equal(o["obs"], o0["obs"].cpu().numpy())
+            np.testing.assert_array_equal(r, r0.cpu().numpy())
+            np.testing.assert_array_equal(te, te0.cpu().numpy())
+    assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].state, envs[2].state)
+    hostmem.release(pinned)
