@@ -482,7 +482,6 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
     for (int i = c.sl; i < D; i += LPE) {
       const float v = w.obs[i];
       seg.obs[(size_t)env * D + i] = v;
-      if (seg.host_obs != nullptr) seg.host_obs[(size_t)env * D + i] = v;
       for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
     }
     if (c.sl == 0) {
@@ -496,6 +495,16 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
         seg.host_truncated[env] = 0;
       }
     }
+  }
+  if (seg.host_obs != nullptr) {
+    // zero-copy obs mirror: the E envs of this warp are consecutive, so their E * D floats are ONE contiguous run in
+    // the host array -- the 32 lanes store it 128 B at a time (PCIe likes full-size posted writes; per-env sub-lane
+    // stores would go out as 40-byte fragments)
+    __syncwarp();
+    const int env0 = (blockIdx.x * W + warp) * E;
+    const int n_run = min(E, seg.n - env0) * D;
+    float* dst = seg.host_obs + (size_t)env0 * D;
+    for (int j = lane; j < n_run; j += 32) dst[j] = sm.env[warp * E + j / D].obs[j % D];
   }
 }
 
