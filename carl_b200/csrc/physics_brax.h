@@ -97,6 +97,19 @@ CARLB_HD V3 rotate(V3 v, Q4 q) {
   return 2.0f * dot(u, v) * u + (s * s - dot(u, u)) * v + 2.0f * s * cross(u, v);
 }
 CARLB_HD V3 inv_rotate(V3 v, Q4 q) { return rotate(v, qconj(q)); }
+// rotate((1,0,0), q) and rotate((0,1,0), q) with the multiplications by the literal 0 / 1 components carried out
+// by hand (IEEE arithmetic cannot fold x * 0 or x + 0 for the compiler): every surviving term is the one the general
+// formula produces, so the results are identical up to the sign of an exact zero.
+CARLB_HD V3 rotate_ex(Q4 q) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const float s = q.w, c = s * s - dot(u, u), d = 2.0f * q.x, t = 2.0f * s;
+  return v3(d * u.x + c, d * u.y + t * u.z, d * u.z + t * (0.0f - u.y));
+}
+CARLB_HD V3 rotate_ey(Q4 q) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const float s = q.w, c = s * s - dot(u, u), d = 2.0f * q.y, t = 2.0f * s;
+  return v3(d * u.x + t * (0.0f - u.z), d * u.y + c, d * u.z + t * u.x);
+}
 CARLB_HD Q4 quat_axis_angle(V3 axis, float angle) {
   const float h = 0.5f * angle;
   const float s = sinf(h);
@@ -170,9 +183,12 @@ struct JointOut {
 // child `c` (table row lt), parent state `p` (ignored when world_parent), parent row plt.
 // SLIDES = false compiles the prismatic branches out (the locomotion bodies have none: their kernels
 // keep the instruction footprint they had before the pendulum / reacher bodies were added).
+// anchor of the joint in the parent link frame: link.transform o joint position (table-only, loop invariant)
+CARLB_HD V3 parent_anchor(const float* lt) { return ld3(lt + L_TPOS) + rotate(ld3(lt + L_JPOS), ld4(lt + L_TROT)); }
+
 template <bool SLIDES = true>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
-                                const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f) {
+                                const float* plt, const LinkState& p, float tau, float stiffness_scale, V3 anchor_p) {
   JointOut o;
   const int type = (int)lt[L_TYPE];
   const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
@@ -189,7 +205,7 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     wp = p.ang;
     pcom = p.pos;
   }
-  ap_pos = xp_pos + rotate(t_pos + rotate(j_pos, t_rot), xp_rot);
+  ap_pos = xp_pos + rotate(anchor_p, xp_rot);
   const Q4 ap_rot = qmul(qmul(xp_rot, t_rot), j_rot);
   if (!world_parent) vp = p.vel + cross(p.ang, ap_pos - p.pos);
   const V3 vc = c.vel + cross(c.ang, ac_pos - c.pos);
@@ -202,11 +218,11 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
               ca = sys[H_ANG_DAMPING_C];
   const V3 ex = v3(1, 0, 0);
   // hinge angle about the joint x axis
-  const V3 yc = rotate(v3(0, 1, 0), jrot);
+  const V3 yc = rotate_ey(jrot);
   const float psi = atan2f(yc.z, yc.y);
   V3 fv, fa;
   // torque aligning the child's joint axis with the parent's
-  const V3 axis_c_x = rotate(ex, jrot);
+  const V3 axis_c_x = rotate_ex(jrot);
   fa = k * cross(axis_c_x, ex);
   if (type == TYPE_PLANAR) {
     // slide-x / slide-z / hinge-y root: only the off-plane offset and off-axis rotation are constrained
@@ -251,6 +267,12 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     o.qd[0] = jvel.x; o.qd[1] = jvel.y;
   }
   return o;
+}
+
+template <bool SLIDES = true>
+CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
+                                const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f) {
+  return joint_resolve<SLIDES>(sys, lt, c, world_parent, plt, p, tau, stiffness_scale, parent_anchor(lt));
 }
 
 // ---- semi-implicit velocity update (brax.spring.integrator.integrate_xdd) ---------------------
@@ -323,8 +345,11 @@ CARLB_HD void integrate_xdv(LinkState& s, V3 p_sum, V3 t_sum, float n_active, co
 // ---- pose integration (brax.spring.integrator.integrate) --------------------------------------
 CARLB_HD void integrate_pose(LinkState& s, float dt) {
   s.pos = s.pos + s.vel * dt;
-  const Q4 w = q4(0.0f, s.ang.x * 0.5f * dt, s.ang.y * 0.5f * dt, s.ang.z * 0.5f * dt);
-  const Q4 d = qmul(w, s.rot);
+  // d = qmul((0, w), rot) with the products by the zero scalar part written out (0*x - t == -t, 0*x + t == t)
+  const float wx = s.ang.x * 0.5f * dt, wy = s.ang.y * 0.5f * dt, wz = s.ang.z * 0.5f * dt;
+  const Q4 r = s.rot;
+  const Q4 d = q4((0.0f - wx * r.x) - wy * r.y - wz * r.z, wx * r.w + wy * r.z - wz * r.y, (wy * r.w - wx * r.z) + wz * r.x,
+                  wx * r.y - wy * r.x + wz * r.w);
   s.rot = qnormalize(q4(s.rot.w + d.w, s.rot.x + d.x, s.rot.y + d.y, s.rot.z + d.z));
 }
 
