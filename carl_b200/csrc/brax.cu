@@ -165,6 +165,7 @@ struct LaneCtx {
   bool stock_contact;
   LinkConst lc;      // loop invariants of my link
   V3 anchor_p;       // my joint's anchor in the parent link frame (table-only)
+  int jflags;        // JointFlags of my joint (table-only)
 };
 
 // n_frames spring substeps for the sub-envs of this warp. `s` is this lane's link.
@@ -182,7 +183,7 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
     if (c.is_link && c.type != TYPE_FREE) {
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve<SP>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p);
+      const JointOut jo = joint_resolve<SP>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags);
       wr = jo.child;
       float* pw = w.pw + c.sl * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
@@ -370,6 +371,7 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
   c.act = (int)c.lt[L_ACT];
   c.stock_contact = stock_contact;
   c.anchor_p = parent_anchor(c.lt);
+  c.jflags = joint_flags(c.lt);
   if (active && sl < LPE) {
     const float* row = seg.ctx + (size_t)env * seg.n_ctx;
     for (int i = sl; i < seg.n_ctx; i += LPE) w.ctx[i] = row[i];

@@ -186,16 +186,29 @@ struct JointOut {
 // anchor of the joint in the parent link frame: link.transform o joint position (table-only, loop invariant)
 CARLB_HD V3 parent_anchor(const float* lt) { return ld3(lt + L_TPOS) + rotate(ld3(lt + L_JPOS), ld4(lt + L_TROT)); }
 
+// Table-only facts of a joint that let joint_resolve skip work whose result is known exactly: bit 0 -- the link
+// transform has no rotation (q * (1,0,0,0) == q), bit 1 -- the joint sits at the link origin (rotate(0, q) == 0).
+// Both hold for every body built so far; the general path stays for tables that differ.
+enum JointFlags { JF_TROT_IDENTITY = 1, JF_JPOS_ZERO = 2 };
+CARLB_HD int joint_flags(const float* lt) {
+  int f = 0;
+  if (lt[L_TROT] == 1.0f && lt[L_TROT + 1] == 0.0f && lt[L_TROT + 2] == 0.0f && lt[L_TROT + 3] == 0.0f) f |= JF_TROT_IDENTITY;
+  if (lt[L_JPOS] == 0.0f && lt[L_JPOS + 1] == 0.0f && lt[L_JPOS + 2] == 0.0f) f |= JF_JPOS_ZERO;
+  return f;
+}
+
 template <bool SLIDES = true>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
-                                const float* plt, const LinkState& p, float tau, float stiffness_scale, V3 anchor_p) {
+                                const float* plt, const LinkState& p, float tau, float stiffness_scale, V3 anchor_p,
+                                int flags) {
   JointOut o;
   const int type = (int)lt[L_TYPE];
   const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
   const V3 t_pos = ld3(lt + L_TPOS), j_pos = ld3(lt + L_JPOS);
   // anchors (kinematics.world_to_joint): a_c = x_c o joint ; a_p = x_p o link.transform o joint
   const V3 xc_pos = link_origin(c, lt);
-  const V3 ac_pos = xc_pos + rotate(j_pos, c.rot);
+  V3 ac_pos = xc_pos;
+  if (!(flags & JF_JPOS_ZERO)) ac_pos = xc_pos + rotate(j_pos, c.rot);
   const Q4 ac_rot = qmul(c.rot, j_rot);
   V3 ap_pos, xp_pos = v3(0, 0, 0), vp = v3(0, 0, 0), wp = v3(0, 0, 0), pcom = v3(0, 0, 0);
   Q4 xp_rot = q4(1, 0, 0, 0);
@@ -206,7 +219,9 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     pcom = p.pos;
   }
   ap_pos = xp_pos + rotate(anchor_p, xp_rot);
-  const Q4 ap_rot = qmul(qmul(xp_rot, t_rot), j_rot);
+  Q4 xpt_rot = xp_rot;
+  if (!(flags & JF_TROT_IDENTITY)) xpt_rot = qmul(xp_rot, t_rot);
+  const Q4 ap_rot = qmul(xpt_rot, j_rot);
   if (!world_parent) vp = p.vel + cross(p.ang, ap_pos - p.pos);
   const V3 vc = c.vel + cross(c.ang, ac_pos - c.pos);
   // joint-frame offsets and rates
@@ -272,7 +287,7 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
 template <bool SLIDES = true>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
                                 const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f) {
-  return joint_resolve<SLIDES>(sys, lt, c, world_parent, plt, p, tau, stiffness_scale, parent_anchor(lt));
+  return joint_resolve<SLIDES>(sys, lt, c, world_parent, plt, p, tau, stiffness_scale, parent_anchor(lt), joint_flags(lt));
 }
 
 // ---- semi-implicit velocity update (brax.spring.integrator.integrate_xdd) ---------------------
