@@ -319,20 +319,23 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
   const float dist = c.z - radius;                               // signed distance to the plane
   const float penetration = -dist;
   if (!(penetration > 0.0f)) return o;
-  const V3 n = v3(0, 0, 1);
+  // The contact normal of the ground plane is n = (0, 0, 1). Brax's formulas below are written with the
+  // products by n's literal 0 / 1 components carried out by hand (the compiler may not fold x * 0 or x + 0 under
+  // IEEE rules): dot(n, v) = v.z, cross(r, n) = (r.y, -r.x, 0), s * n = (0, 0, s) -- the same values up to the
+  // sign of an exact zero.
   const V3 cpos = v3(c.x, c.y, 0.5f * dist);  // midway between the two surfaces
   const V3 rel_pos = cpos - s.pos;
   const V3 rel_vel = s.vel + cross(s.ang, rel_pos);
-  const float normal_vel = dot(n, rel_vel);
+  const float normal_vel = rel_vel.z;                                       // dot(n, rel_vel)
   const float inv_m = lc.inv_mass;
-  const V3 temp1 = apply_inv_inertia(cross(rel_pos, n), s.rot, lt, lc.inv_idiag);
-  const float ang = dot(n, cross(temp1, rel_pos));
+  const V3 temp1 = apply_inv_inertia(v3(rel_pos.y, 0.0f - rel_pos.x, 0.0f), s.rot, lt, lc.inv_idiag);  // cross(rel_pos, n)
+  const float ang = temp1.x * rel_pos.y - temp1.y * rel_pos.x;              // dot(n, cross(temp1, rel_pos))
   const float dt = sys[H_DT];
   const float baumgarte_vel = sys[H_BAUMGARTE] * penetration / dt;
   const float impulse = (-1.0f * (1.0f + elasticity) * normal_vel + baumgarte_vel) / (inv_m + ang);
-  const V3 impulse_vec = impulse * n;
+  const V3 impulse_vec = v3(0.0f, 0.0f, impulse);                           // impulse * n
   // drag from friction, parallel to the surface
-  const V3 vel_d = rel_vel - normal_vel * n;
+  const V3 vel_d = v3(rel_vel.x, rel_vel.y, rel_vel.z - normal_vel);        // rel_vel - normal_vel * n
   const float speed_d = norm(vel_d);
   float impulse_d = speed_d / (inv_m + ang);
   const V3 dir_d = vel_d * (1.0f / (1e-6f + speed_d));
