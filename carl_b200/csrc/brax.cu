@@ -70,6 +70,7 @@ struct BraxSeg {
 struct EnvScratch {
   float ls[MAX_LINKS * LINK_WORDS];  // link states (also the coalesced I/O staging of the state row)
   float pw[MAX_LINKS * 6];           // reaction wrench of joint l on its parent
+  float org[MAX_LINKS * 3];          // link-frame origins of this substep (joint phase -> contact phase)
   float co[MAX_POINTS * 7];          // contact outputs: impulse(3) angular impulse(3) active
   float lc[MAX_LINKS * 6];           // per-link loop invariants: inv_mass, inv_idiag(3), vel_decay, ang_decay
   float q[MAX_Q];
@@ -188,6 +189,12 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
       float* pw = w.pw + c.sl * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
       pw[3] = jo.parent.t.x; pw[4] = jo.parent.t.y; pw[5] = jo.parent.t.z;
+      float* og = w.org + c.sl * 3;
+      og[0] = jo.origin.x; og[1] = jo.origin.y; og[2] = jo.origin.z;
+    } else if (c.is_link && c.P > 0) {  // free root: no joint, but its contact points need the origin too
+      const V3 o0 = link_origin(s, c.lt);
+      float* og = w.org + c.sl * 3;
+      og[0] = o0.x; og[1] = o0.y; og[2] = o0.z;
     }
     __syncwarp();
     if (c.is_link) {
@@ -212,7 +219,7 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
         const LinkState ps = read_link(w.ls, pl);
         const float fr = (c.stock_contact || w.ctx[C_FRICTION] < 0.0f) ? pt[5] : w.ctx[C_FRICTION];
         const float el = (c.stock_contact || w.ctx[C_ELASTICITY] < 0.0f) ? pt[6] : w.ctx[C_ELASTICITY];
-        const ContactOut co = contact_resolve(sys, pt, link_tab(sys, pl), ps, read_lc(w.lc, pl), fr, el);
+        const ContactOut co = contact_resolve(sys, pt, link_tab(sys, pl), ps, read_lc(w.lc, pl), fr, el, ld3(w.org + pl * 3));
         float* o = w.co + p * 7;
         o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
       }

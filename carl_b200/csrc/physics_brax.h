@@ -178,6 +178,7 @@ struct JointOut {
   Wrench parent;  // wrench on the parent about its COM (zero for a world parent)
   float q[3];
   float qd[3];
+  V3 origin;      // the child's link-frame origin (x.pos), reused by the contact phase of the same substep
 };
 
 // child `c` (table row lt), parent state `p` (ignored when world_parent), parent row plt.
@@ -207,6 +208,7 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
   const V3 t_pos = ld3(lt + L_TPOS), j_pos = ld3(lt + L_JPOS);
   // anchors (kinematics.world_to_joint): a_c = x_c o joint ; a_p = x_p o link.transform o joint
   const V3 xc_pos = link_origin(c, lt);
+  o.origin = xc_pos;
   V3 ac_pos = xc_pos;
   if (!(flags & JF_JPOS_ZERO)) ac_pos = xc_pos + rotate(j_pos, c.rot);
   const Q4 ac_rot = qmul(c.rot, j_rot);
@@ -309,12 +311,13 @@ struct ContactOut {
   float active;
 };
 
+// `origin` is link_origin(s, lt): pose integration is the last phase of a substep, so the value the joint phase
+// computed for the link is still exact here and is passed in instead of being recomputed per contact point.
 CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const float* lt, const LinkState& s,
-                                    const LinkConst& lc, float friction, float elasticity) {
+                                    const LinkConst& lc, float friction, float elasticity, V3 origin) {
   ContactOut o;
   o.p = v3(0, 0, 0); o.t = v3(0, 0, 0); o.active = 0.0f;
   const float radius = pt[4];
-  const V3 origin = link_origin(s, lt);
   const V3 c = origin + rotate(v3(pt[1], pt[2], pt[3]), s.rot);  // sphere centre in the world
   const float dist = c.z - radius;                               // signed distance to the plane
   const float penetration = -dist;

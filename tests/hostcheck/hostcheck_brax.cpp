@@ -118,7 +118,7 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         const int l = (int)pt[0];
         const float fr = (c[C_FRICTION] < 0.0f || stock_contact) ? pt[5] : c[C_FRICTION];
         const float el = (c[C_ELASTICITY] < 0.0f || stock_contact) ? pt[6] : c[C_ELASTICITY];
-        co[p] = contact_resolve(sys, pt, link_tab(sys, l), nx[l], lcs[l], fr, el);
+        co[p] = contact_resolve(sys, pt, link_tab(sys, l), nx[l], lcs[l], fr, el, link_origin(nx[l], link_tab(sys, l)));
       }
       for (int l = 0; l < L; ++l) {
         const float* lt = link_tab(sys, l);

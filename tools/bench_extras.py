@@ -45,9 +45,20 @@ def main():
     ap = torch.rand(n, device="cuda") * 4 - 2
     aa = torch.randint(0, 3, (n,), dtype=torch.int32, device="cuda")
     ms = timed(lambda: mixed.step([ap, aa]), 500)
-    out["config3_mixed_step"] = {"workload": "CARLPendulum 32768 + CARLAcrobot 32768, one mixed launch per step",
+    out["config3_mixed_step"] = {"workload": "CARLPendulum 32768 + CARLAcrobot 32768, one mixed launch per step (Python API call)",
                                  "us_per_step": ms * 1e3, "env_steps_per_s": 2 * n / (ms * 1e-3),
                                  "algorithmic_GBps": (62 + 110) * n / (ms * 1e-3) / 1e9}
+    # the same launch through the bare C ABI (argument arrays built once): the Python call above is host bound
+    import ctypes
+
+    from carl_b200 import _native
+
+    ptrs = (ctypes.c_void_p * 2)(ap.data_ptr(), aa.data_ptr())
+    dts = (ctypes.c_int * 2)(_native.ACT_F32, _native.ACT_I32)
+    st = torch.cuda.current_stream().cuda_stream
+    ms = timed(lambda: mixed._lib.carlb_mixed_step(mixed._handles, ptrs, dts, 2, st), 2000)
+    out["config3_mixed_step_c_abi"] = {"us_per_step": ms * 1e3, "env_steps_per_s": 2 * n / (ms * 1e-3),
+                                       "algorithmic_GBps": (62 + 110) * n / (ms * 1e-3) / 1e9}
     for env, name in ((pen, "pendulum"), (acr, "acrobot")):
         T = 100
         ms = timed(lambda: env.rollout(T, policy_seed=1, record=False), 10, warm=2)
