@@ -78,3 +78,17 @@ def test_env_construction_fails_loudly_without_gpu():
         CARLCartPole()
     with pytest.raises(ValueError, match="no CPU fallback"):
         CARLCartPole(device="cpu")
+
+
+def test_new_entry_points_reject_null_handles_without_touching_the_gpu(native_lib):
+    """carlb_env_step_host_checked / carlb_brax_goal_step validate their arguments before any CUDA call:
+    a null handle is CARLB_ERR_INVALID / CARLB_ERR_STATE with a message, never a crash (no compute here)."""
+    from carl_b200 import _native
+
+    rc = native_lib.carlb_env_step_host_checked(None, None, _native.ACT_I32, 2, None, None, None, None, None)
+    assert rc in (_native.ERR_INVALID, _native.ERR_STATE) and native_lib.carlb_last_error()
+    rc = native_lib.carlb_brax_goal_step(None, 0, 1, ctypes.c_double(0.01), None, None, None, None, None, None)
+    assert rc in (_native.ERR_INVALID, _native.ERR_STATE) and native_lib.carlb_last_error()
+    for kind, (D, A) in {"brax_inverted_pendulum": (4, 1), "brax_inverted_double_pendulum": (8, 1), "brax_reacher": (11, 2)}.items():
+        q = _native.query_env(_native.KIND[kind])
+        assert (q.obs_dim, q.act_dim, q.default_max_steps) == (D, A, 1000)
