@@ -212,8 +212,11 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
     __syncwarp();
     // ground contacts: in pass k sub-lane sl resolves candidate point k*LPE + sl against the plane
     for (int pass = 0; pass < n_pass; ++pass) {
-      const int p = pass * LPE + c.sl;
-      if (c.active && c.sl < LPE && p < c.P) {
+      const int slot = pass * LPE + c.sl;
+      if (c.active && c.sl < LPE && slot < c.P) {
+        // contact schedule: candidates near the ground come first, so the later passes mostly return at the
+        // penetration test for every lane of the warp (same impulses, stored per candidate as before)
+        const int p = (int)point_tab(sys, slot)[P_SCHED];
         const float* pt = point_tab(sys, p);
         const int pl = (int)pt[0];
         const LinkState ps = read_link(w.ls, pl);

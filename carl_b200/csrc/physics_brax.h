@@ -31,6 +31,7 @@ constexpr int MAX_Q = 24;
 constexpr int HEADER = 32;
 constexpr int LINK_STRIDE = 40;
 constexpr int POINT_STRIDE = 8;
+constexpr int P_SCHED = 7;  // point row slot 7: contact schedule (candidate handled in this slot of the contact passes)
 constexpr int OFF_LINKS = HEADER;
 constexpr int OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS;
 constexpr int OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS;

@@ -26,6 +26,7 @@ MAX_Q = 24
 HEADER = 32
 LINK_STRIDE = 40
 POINT_STRIDE = 8
+P_SCHED = 7  # point row slot 7: contact schedule (the candidate handled in this slot of the contact passes)
 OFF_LINKS = HEADER
 OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS
 OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS
@@ -373,6 +374,32 @@ def reacher_model():
     )
 
 
+def _initial_point_clearance(links, init_q, pts_all, q_idx):
+    """Height above the ground (sphere centre z - radius) of every contact candidate in the initial pose:
+    a plain forward-kinematics pass (joints at the link origin, as in every model here). Only used to ORDER
+    the candidates for the kernel's contact passes, never for physics."""
+    world = []
+    for i, l in enumerate(links):
+        q = init_q[q_idx[i]:]
+        if l["type"] == TYPE_FREE:
+            pos, rot = np.asarray(q[:3], float), np.asarray(q[3:7], float) / np.linalg.norm(q[3:7])
+        else:
+            ppos, prot = (np.zeros(3), np.array([1.0, 0, 0, 0])) if l["parent"] < 0 else world[l["parent"]]
+            trans, angle = np.zeros(3), 0.0
+            if l["type"] == TYPE_PLANAR:
+                trans, angle = np.array([q[0], 0.0, q[1]]), q[2]
+            elif l["type"] == TYPE_HINGE:
+                angle = q[0]
+            elif l["type"] in (TYPE_SLIDE, TYPE_SLIDE2):
+                trans = np.asarray(l["axis"], float) * q[0]
+            jrot = quat_axis_angle(l["axis"], angle) if l["axis"] is not None else np.array([1.0, 0, 0, 0])
+            lrot = quat_mul(l["quat"], jrot)
+            pos = ppos + quat_to_mat(prot) @ (l["pos"] + quat_to_mat(l["quat"]) @ trans)
+            rot = quat_mul(prot, lrot)
+        world.append((pos, rot))
+    return [float((world[li][0] + quat_to_mat(world[li][1]) @ p)[2] - r) for (li, p, r, _fr) in pts_all]
+
+
 def build_system(model: dict, tunables: dict | None = None) -> dict:
     """Derive masses / inertias (MuJoCo inertiafromgeom) and pack the float32 system table."""
     links = model["links"]
@@ -430,6 +457,15 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     for k, (li, p, r, fr) in enumerate(pts_all):
         o = OFF_POINTS + POINT_STRIDE * k
         t[o:o + 7] = [li, p[0], p[1], p[2], r, fr, model["stock_elasticity"]]
+    # Contact schedule (slot 7 of the point rows): the kernel's contact pass k handles the candidates
+    # schedule[k * lanes ...]; candidates closest to the ground in the initial pose (feet) come first, so that the
+    # later passes hold the ones that rarely touch and a warp skips their impulse arithmetic altogether. Pure
+    # scheduling: impulses are still stored and summed per link in candidate order.
+    if pts_all:
+        clearance = _initial_point_clearance(links, np.asarray(model["init_q"], float), pts_all, q_idx)
+        order = sorted(range(len(pts_all)), key=lambda k: (round(clearance[k], 6), k))
+        for slot, k in enumerate(order):
+            t[OFF_POINTS + POINT_STRIDE * slot + P_SCHED] = k
     ep = model["env_params"]
     t[H_N_LINKS], t[H_N_Q], t[H_N_QD], t[H_N_POINTS] = n, qi, qdi, len(pts_all)
     t[H_N_FRAMES], t[H_DT], t[H_ENV], t[H_N_ACT] = model["n_frames"], model["dt"], model["env"], len(model["actuator_links"])

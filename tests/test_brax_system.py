@@ -138,3 +138,20 @@ def test_tunable_override_and_validation():
     assert s["table"][bs.H_STIFFNESS] == 1234.0
     with pytest.raises(ValueError):
         bs.build_system(bs.ant_model(), {"nope": 1.0})
+
+
+def test_contact_schedule_is_a_permutation_with_the_feet_first():
+    """Slot 7 of the point rows: the order in which the kernel's contact passes visit the candidates (pure
+    scheduling -- impulses are stored and summed per link in candidate order)."""
+    for name, s in bs.SYSTEMS.items():
+        t, P = s["table"], s["n_points"]
+        sched = [int(t[bs.OFF_POINTS + bs.POINT_STRIDE * k + bs.P_SCHED]) for k in range(P)]
+        assert sorted(sched) == list(range(P)), name
+    a = bs.SYSTEMS["ant"]
+    t = a["table"]
+    first = [a["link_names"][int(t[bs.OFF_POINTS + bs.POINT_STRIDE * int(t[bs.OFF_POINTS + bs.POINT_STRIDE * k + bs.P_SCHED])])]
+             for k in range(4)]
+    assert sorted(first) == ["ankle_1", "ankle_2", "ankle_3", "ankle_4"]  # the four feet lead pass 0
+    h = bs.SYSTEMS["hopper"]
+    t = h["table"]
+    assert h["link_names"][int(t[bs.OFF_POINTS + bs.POINT_STRIDE * int(t[bs.OFF_POINTS + bs.P_SCHED])])] == "foot"
