@@ -752,14 +752,20 @@ static inline int brax_grid(int n, int envs_per_cta) { return (n + envs_per_cta 
 
 // Envs packed per warp for the step / rollout kernels: the largest E in {4, 3, 1} whose 32/E lanes
 // hold the body's links and actuators (Halfcheetah 7 links / 6 actuators and Hopper 4 / 3 -> E = 4;
-// Ant 9 / 8 -> E = 3). CARLB_BRAX_PACK=1 forces one env per warp.
-static int brax_pack(const float* table) {
+// Ant 9 / 8 -> E = 3). CARLB_BRAX_PACK=1 forces one env per warp, 4 (or 3) forces packing whatever the batch size;
+// unset / 0 is the automatic choice below.
+static int brax_pack(const float* table, int n) {
   static const int forced = [] {
     const char* e = getenv("CARLB_BRAX_PACK");
     return e != nullptr ? atoi(e) : 0;
   }();
   const int need = max((int)table[H_N_LINKS], (int)table[H_N_ACT]);
   if (forced == 1) return 1;
+  // Small batches of the larger bodies are latency bound (one warp walks its substeps in ~40 us whatever the
+  // grid): one env per warp spreads the contact candidates over all 32 lanes (one pass instead of three) and
+  // quadruples the resident warps -- measured 10-25 % faster at <= 1 024 envs (profiles/r01m_brax_pack_sweep_*),
+  // bit-identical to the packed mapping (test_packed_lanes_equal_one_env_per_warp).
+  if (forced == 0 && n <= 1024 && (int)table[H_N_LINKS] >= 7) return 1;
   if (need <= Lanes<4>::LPE && forced != 3) return 4;
   if (need <= Lanes<3>::LPE) return 3;
   return 1;
@@ -786,10 +792,10 @@ static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, co
   const int n = env->n, sc = h->stock_contact;
   if ((int)h->host_table[H_ENV] >= ENV_INVERTED_PENDULUM) {
     // inverted pendulums / reacher (2-3 links): the instantiation with slide joints and their env layers
-    if (brax_pack(h->host_table) == 1) return launch_brax_step_we<4, 1, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
     return launch_brax_step_we<4, 4, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
   }
-  switch (brax_pack(h->host_table)) {
+  switch (brax_pack(h->host_table, n)) {
     case 4: return launch_brax_step_we<4, 4, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
     case 3: return launch_brax_step_we<4, 3, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
     default: break;

@@ -312,13 +312,16 @@ def test_packed_lanes_equal_one_env_per_warp(tmp_path):
     script = tmp_path / "pack.py"
     script.write_text(PACK_SCRIPT.format(root=root))
     res = {}
-    for pack in ("1", "0"):
+    # "1": one env per warp; "4": packed whatever the batch size (the largest E that fits the body); "0": the
+    # default dispatch, which picks one env per warp for small batches of the larger bodies
+    for pack in ("1", "4", "0"):
         out = tmp_path / f"pack{pack}.npz"
         env = dict(os.environ, CARLB_BRAX_PACK=pack)
         p = subprocess.run([sys.executable, str(script), str(out)], env=env, capture_output=True, text=True, timeout=300)
         assert p.returncode == 0, p.stderr[-2000:]
         res[pack] = np.load(out)
     for k in res["1"].files:
+        np.testing.assert_array_equal(res["1"][k], res["4"][k], err_msg=k)
         np.testing.assert_array_equal(res["1"][k], res["0"][k], err_msg=k)
     assert res["1"]["ant_done"].sum() > 0
 

@@ -16,3 +16,4 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 rm -f gpurun_out/prof_*.ncu-rep gpurun_out/launches.csv
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:brax_step_kernel -s 3 -c 2 -f -o gpurun_out/prof_brax \
   python bench.py --steps 1000 --warmup 500 --no-cpu-baseline > gpurun_out/ncu_brax.log 2>&1; echo "ncu brax exit $?"
+timeout 120 python tools/brax_pack_sweep.py > gpurun_out/pack_sweep_auto.json 2>/dev/null; echo "sweep exit $?"; cat gpurun_out/pack_sweep_auto.json
