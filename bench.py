@@ -146,7 +146,6 @@ def cpu_baseline_leg(steps_per_call: int, target_seconds: float, n_envs: int = N
     import ctypes
 
     import oracle
-    from oracle.classic import DEFAULTS
 
     L = oracle.lib()
     L.oracle_cartpole_rollout_baseline.restype = ctypes.c_longlong

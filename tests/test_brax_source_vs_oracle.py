@@ -158,3 +158,50 @@ def test_cart_pendulum_small_oscillation_period_is_analytic(hc):
         ang_k.append(hc.step(sysd, st, ctx, zero, el, 0, 0, st.copy(), ob.copy())[0][0, 1])
     assert abs(fitted_omega(ang_o) / omega - 1.0) < 0.02
     assert abs(fitted_omega(ang_k) / omega - 1.0) < 0.02
+
+
+def _crooked_hopper():
+    """A table no shipped body has: rotated link transforms (L_TROT != identity) and joints away from the link
+    origin (L_JPOS != 0) -- the general branches of joint_resolve / forward_link that the table-derived
+    JointFlags fast path skips for every real model."""
+    m = bs.hopper_model()
+    m = dict(m, name="crooked_hopper")
+    links = [dict(l) for l in m["links"]]
+    links[1]["quat"] = bs.quat_axis_angle((0, 1, 0), 0.3)
+    links[1]["joint_pos"] = np.array([0.02, 0.0, -0.05])
+    links[2]["quat"] = bs.quat_axis_angle((1, 2, 0.5), -0.2)
+    links[2]["joint_pos"] = np.array([0.0, 0.01, 0.03])
+    links[3]["joint_pos"] = np.array([0.05, 0.0, 0.0])
+    m["links"] = links
+    return bs.build_system(m)
+
+
+def test_general_joint_frames_match(hc):
+    """hostcheck (kernel source) vs oracle on a body with rotated link transforms and offset joints: pipeline_init,
+    one env-step, and the JointFlags really are off for these links (so the general path is what ran)."""
+    sysd = _crooked_hopper()
+    t = sysd["table"]
+    for l in (1, 2):
+        o = bs.OFF_LINKS + bs.LINK_STRIDE * l
+        assert not (t[o + bs.L_TROT] == 1.0) and np.abs(t[o + bs.L_JPOS:o + bs.L_JPOS + 3]).max() > 0
+    n = 128
+    rng = np.random.default_rng(5)
+    ctx = random_ctx(sysd, n, rng)
+    q, qd = random_q(sysd, n, rng, scale=2.0)
+    ora = OracleBraxEnv(sysd, ctx, autoreset=False)
+    o_ref = ora.init_from_q(q, qd)
+    st, o = hc.init(sysd, q, qd)
+    np.testing.assert_allclose(st, ora.state, rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(o, o_ref, rtol=1e-5, atol=2e-6)
+    # forward then inverse kinematics is the identity on (q[1:], qd) for offset joints too
+    want = np.concatenate([q[:, 1:], np.clip(qd, -10, 10)], axis=1)
+    np.testing.assert_allclose(o_ref, want, rtol=2e-5, atol=2e-5)
+    for _ in range(3):
+        a = rng.uniform(-1, 1, (n, sysd["n_act"])).astype(np.float32)
+        o_ref, r_ref, d_ref, _ = ora.step(a)
+        el = np.zeros(n, dtype=np.int32)
+        o, r, d = hc.step(sysd, st, ctx, a, el, 1000, 0, st.copy(), o_ref.copy())
+        assert_close_scaled(o, o_ref, rel=2e-5)
+        assert (d == d_ref).all()
+        assert_close_scaled(st, ora.state, rel=2e-5, what="state")
+        st[:] = ora.state  # teacher forcing
