@@ -205,3 +205,57 @@ def test_general_joint_frames_match(hc):
         assert (d == d_ref).all()
         assert_close_scaled(st, ora.state, rel=2e-5, what="state")
         st[:] = ora.state  # teacher forcing
+
+
+@pytest.mark.parametrize("body", ["ant", "reacher"])
+def test_free_flight_conserves_momentum(hc, body):
+    """Size-independent physical invariant of the restated spring pipeline: joint spring / limit / actuator
+    wrenches are internal (equal and opposite on child and parent), so for a body out of contact one env-step
+    changes the total linear momentum by exactly sum(m) g t -- whatever the actions -- and, with the joint DAMPERS
+    off (a damper force acts at two anchors that a stretched spring holds apart, so it alone carries a small net
+    torque), leaves the angular momentum about the vertical axis untouched. Checked with the effective masses of
+    the backend (Ant / Reacher: unit masses and isotropic unit inertias, so the spin part is simply the angular
+    velocity) on the float64 oracle (2e-5, see below), the float32 oracle and the kernel source (float32 round-off).
+    A wrong lever arm or a missing reaction term in joint_resolve breaks this at once."""
+    base = bs.MODELS[body]()
+    if body == "reacher":  # cut the arm loose: a world-anchored hinge exchanges momentum with the world
+        links = [dict(l) for l in base["links"]]
+        links[0]["type"], links[0]["axis"] = bs.TYPE_FREE, None
+        base = dict(base, links=links[:2], init_q=np.array([0, 0, 0, 1, 0, 0, 0, 0.0]), site=None,
+                    actuator_links=["body1"], env=bs.ENV_ANT)
+        base.pop("obs_dim")
+    sysd = bs.build_system(base, {"constraint_vel_damping": 0.0, "constraint_ang_damping": 0.0})
+    assert sysd["tunables"]["spring_mass_scale"] == 1.0 and sysd["tunables"]["spring_inertia_scale"] == 1.0
+    n, L = 16, sysd["n_links"]
+    rng = np.random.default_rng(9)
+    ctx = random_ctx(sysd, n, rng)
+    ctx[:, 3] = 0.0  # no global angular damping either: it is an external (dissipative) torque
+    q, qd = random_q(sysd, n, rng, scale=3.0)
+    q[:, 2] += 50.0  # far above the ground for the whole step
+    qd += rng.normal(0, 1.0, qd.shape).astype(np.float32)
+    a = rng.uniform(-1, 1, (n, sysd["n_act"])).astype(np.float32)
+    dt, nf = float(sysd["table"][bs.H_DT]), int(sysd["table"][bs.H_N_FRAMES])
+    g = ctx[:, 0].astype(np.float64)
+    want_dp = np.stack([0 * g, 0 * g, L * g * np.float32(dt) * nf], axis=1)
+
+    def momenta(state):
+        rows = np.asarray(state, np.float64)[:, :13 * L].reshape(n, L, 13)
+        pos, vel, ang = rows[..., 0:3], rows[..., 7:10], rows[..., 10:13]
+        return vel.sum(1), (np.cross(pos, vel) + ang).sum(1)  # unit effective masses / inertias
+
+    # float64 arithmetic on the float32 TABLE: its frame quaternions are unit only to 1e-7, so a torque pair reaches
+    # child and parent scaled by (1 +- 1e-7) -- the residual is ~1e-6 with 150 N m actuators, 1e-8 without actions
+    for f64, tol in ((True, 2e-5), (False, 3e-3)):
+        ora = OracleBraxEnv(sysd, ctx, autoreset=False, f64=f64)
+        ora.init_from_q(q, qd)
+        p0, l0 = momenta(ora.state)
+        ora.step(a)
+        p1, l1 = momenta(ora.state)
+        np.testing.assert_allclose(p1 - p0, want_dp, rtol=0, atol=tol)
+        np.testing.assert_allclose((l1 - l0)[:, 2], 0.0, atol=tol)
+    st, ob = hc.init(sysd, q, qd)
+    p0, l0 = momenta(st)
+    hc.step(sysd, st, ctx, a, np.zeros(n, np.int32), 0, 0, st.copy(), ob.copy())
+    p1, l1 = momenta(st)
+    np.testing.assert_allclose(p1 - p0, want_dp, rtol=0, atol=3e-3)
+    np.testing.assert_allclose((l1 - l0)[:, 2], 0.0, atol=3e-3)
