@@ -207,3 +207,6 @@ def test_brax_param_rows_and_shapes_match_native_query(native_lib):
             want = d.get(f"mass_{ln}", sysd["stock_masses"][j])
             assert applied[0, 5 + j] == pytest.approx(want)
     assert E.brax.UNSUPPORTED_BODIES == ("CARLBraxHumanoid", "CARLBraxHumanoidStandup", "CARLBraxPusher")
+    for name in E.brax.UNSUPPORTED_BODIES:  # asking for them fails loudly, nothing is substituted
+        with pytest.raises(NotImplementedError, match="not built"):
+            getattr(E, name)
