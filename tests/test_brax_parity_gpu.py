@@ -285,10 +285,12 @@ def test_full_size_properties_config4():
 PACK_SCRIPT = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, {root!r})
-from carl_b200.envs import CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d
+from carl_b200.envs import (CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d, CARLBraxInvertedPendulum,
+                            CARLBraxInvertedDoublePendulum, CARLBraxReacher)
 out = {{}}
 for cls, name in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
-                  (CARLBraxWalker2d, "walker2d")):
+                  (CARLBraxWalker2d, "walker2d"), (CARLBraxInvertedPendulum, "inverted_pendulum"),
+                  (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher")):
     env = cls(num_envs=301, max_episode_steps=7)   # ragged vs both 12- and 4-env CTAs, short episodes
     env.reset(seed=3)
     t = env.rollout(24, policy_seed=5, record=True)
