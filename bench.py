@@ -181,6 +181,48 @@ def cpu_baseline_leg(steps_per_call: int, target_seconds: float, n_envs: int = N
             "threads": threads}
 
 
+def brax_cpu_baseline(sysd, ctx, target_seconds: float = 3.0, threads: int | None = None):
+    """The Brax oracle port (plain C, OpenMP over the env instances) stepping the same batch with a uniform random
+    policy on the host cores: the CPU number next to `ant_8192` (bounded sample)."""
+    import ctypes
+
+    import oracle
+    from carl_b200.envs import brax_system as bs
+    from oracle.brax import OracleBraxEnv
+
+    L = oracle.lib()
+    if threads is None:
+        threads = int(L.oracle_max_threads())
+        quota = cgroup_cpu_quota()
+        if quota:
+            threads = max(1, min(threads, int(round(quota))))
+    # the OpenMP thread count is process-wide: set it through the classic baseline entry point (0 steps)
+    L.oracle_cartpole_rollout_baseline.restype = ctypes.c_longlong
+    L.oracle_cartpole_rollout_baseline.argtypes = [
+        ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_uint64,
+        ctypes.c_int, ctypes.c_void_p]
+    ret = ctypes.c_double()
+    dummy_state, dummy_table = np.zeros((1, 4)), np.ascontiguousarray(make_context_table(1)[1])
+    L.oracle_cartpole_rollout_baseline(1, 0, dummy_state.ctypes.data, dummy_table.ctypes.data, 500, 0, 0, threads, ctypes.byref(ret))
+    n = ctx.shape[0]
+    rng = np.random.default_rng(3)
+    env = OracleBraxEnv(sysd, ctx, autoreset=True)
+    init_q = sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + sysd["n_q"]]
+    q = (init_q[None] + rng.uniform(-0.1, 0.1, (n, sysd["n_q"]))).astype(np.float32)
+    qd = (0.1 * rng.standard_normal((n, sysd["n_qd"]))).astype(np.float32)
+    env.init_from_q(q, qd)
+    acts = rng.uniform(-1, 1, (8, n, sysd["n_act"])).astype(np.float32)
+    env.step(acts[0])  # warm
+    steps, elapsed = 0, 0.0
+    while elapsed < target_seconds:
+        t0 = time.perf_counter()
+        env.step(acts[steps % 8])
+        elapsed += time.perf_counter() - t0
+        steps += 1
+    return {"value": n * steps / elapsed, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n} envs x {steps} env-steps ({elapsed:.1f} s) -- C/OpenMP oracle port of the Brax spring step"}
+
+
 def cgroup_cpu_quota():
     """CPUs granted by the container's CFS quota (cgroup v2 `cpu.max`), or None."""
     try:
@@ -614,7 +656,14 @@ def ant_leg(dev, peak, args):
         acc += float(r_h[0])
     torch.cuda.synchronize(dev)
     e2e_ms = (time.perf_counter() - t0) / 100 * 1e3
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:  # reported next to the GPU number; never allowed to break the bench line
+            cpu = brax_cpu_baseline(env._sysd, env._ctx.cpu().numpy(), target_seconds=3.0)
+        except Exception as e:  # pragma: no cover
+            cpu = {"error": repr(e)}
     return {
+        "cpu_baseline": cpu,
         "workload": "CARLBraxAnt, 8192 sampled contexts (gravity/mass_torso/friction), context_mode=applied, "
                     "uniform random policy, 10 spring substeps per env-step",
         "value": fused, "unit": UNIT, "fused_steps_per_launch": T, "ms_per_env_step_batch": ms / K,
