@@ -374,6 +374,25 @@ def reacher_model():
     )
 
 
+def humanoid_geometry():
+    """Groundwork for ``CARLBraxHumanoid`` (NOT a buildable model yet: its 2- and 3-dof revolute joints and Brax's
+    cinert / cvel observation are not implemented). The collision geometry of Gym / Brax
+    ``humanoid.xml`` per link, pinned by CARL's own mass defaults (``carl/envs/brax/carl_humanoid.py:37-75``):
+    ``tests/test_brax_system.py::test_humanoid_geometry_matches_carl_masses`` reproduces all ten to 7 digits."""
+    arm_up = lambda sy: [capsule((0, 0, 0), (0.16, sy * 0.16, -0.16), 0.04)]
+    arm_lo = lambda sy: [capsule((0.01, sy * 0.01, 0.01), (0.17, sy * 0.17, 0.17), 0.031), sphere((0.18, sy * 0.18, 0.18), 0.04)]
+    thigh = lambda sy: [capsule((0, 0, 0), (0, sy * 0.01, -0.34), 0.06)]
+    shin = [capsule((0, 0, 0), (0, 0, -0.3), 0.049), sphere((0, 0, -0.35), 0.075)]
+    return {
+        "torso": [capsule((0, -0.07, 0), (0, 0.07, 0), 0.07), sphere((0, 0, 0.19), 0.09),
+                  capsule((-0.01, -0.06, -0.12), (-0.01, 0.06, -0.12), 0.06)],
+        "lwaist": [capsule((0, -0.06, 0), (0, 0.06, 0), 0.06)],
+        "pelvis": [capsule((-0.02, -0.07, 0), (-0.02, 0.07, 0), 0.09)],
+        "right_thigh": thigh(1), "right_shin": shin, "left_thigh": thigh(-1), "left_shin": shin,
+        "right_upper_arm": arm_up(-1), "right_lower_arm": arm_lo(1), "left_upper_arm": arm_up(1), "left_lower_arm": arm_lo(-1),
+    }
+
+
 def _initial_point_clearance(links, init_q, pts_all, q_idx):
     """Height above the ground (sphere centre z - radius) of every contact candidate in the initial pose:
     a plain forward-kinematics pass (joints at the link origin, as in every model here). Only used to ORDER

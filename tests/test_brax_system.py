@@ -155,3 +155,16 @@ def test_contact_schedule_is_a_permutation_with_the_feet_first():
     h = bs.SYSTEMS["hopper"]
     t = h["table"]
     assert h["link_names"][int(t[bs.OFF_POINTS + bs.POINT_STRIDE * int(t[bs.OFF_POINTS + bs.P_SCHED])])] == "foot"
+
+
+def test_humanoid_geometry_matches_carl_masses():
+    """Groundwork for the humanoid (not buildable yet): the per-link geoms reproduce every MJCF-derived mass default of
+    carl/envs/brax/carl_humanoid.py:41-75 to 7 digits (``mass_torso = 10`` there is a placeholder, like the Ant's)."""
+    want = {"lwaist": 2.2619467, "pelvis": 6.6161942, "right_thigh": 4.751751, "right_shin": 4.522842,
+            "left_thigh": 4.751751, "left_shin": 4.522842, "right_upper_arm": 1.6610805, "right_lower_arm": 1.2295402,
+            "left_upper_arm": 1.6610805, "left_lower_arm": 1.2295402}
+    geo = bs.humanoid_geometry()
+    assert list(geo) == ["torso"] + list(want)
+    for name, m in want.items():
+        assert bs.body_inertia(geo[name], 1000.0)[0] == pytest.approx(m, rel=2e-7), name
+    assert bs.body_inertia(geo["torso"], 1000.0)[0] == pytest.approx(8.907463, rel=1e-6)  # the MJCF's own torso mass
