@@ -71,18 +71,20 @@ def hbm_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def measured_profile(rep: str):
+def measured_profile(rep: str, fused_steps: int | None = None):
     """Counters of the dominant kernel from the newest committed ncu --set full summary
-    (profiles/<tag>_traffic.json, written by tools/summarize_ncu.py): (dict, file name) or ({}, None)."""
+    (profiles/<tag>_traffic.json, written by tools/summarize_ncu.py) -- of a capture that fused `fused_steps`
+    env-steps per launch when given: (dict, file name) or ({}, None)."""
     d = os.path.join(ROOT, "profiles")
     try:
-        files = sorted(f for f in os.listdir(d) if f.endswith("_traffic.json"))
-        if not files:
-            return {}, None
-        j = json.load(open(os.path.join(d, files[-1])))
-        return dict(j[rep]), files[-1]
+        files = sorted((f for f in os.listdir(d) if f.endswith("_traffic.json")), reverse=True)
+        for f in files:
+            j = json.load(open(os.path.join(d, f)))
+            if rep in j and (fused_steps is None or j[rep].get("fused_steps_per_launch") == fused_steps):
+                return dict(j[rep]), f
     except Exception:
-        return {}, None
+        pass
+    return {}, None
 
 
 def measured_traffic(rep: str):
@@ -314,11 +316,61 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
-def run_gpu_arm(args):
+def timed_train(replay, n_per_replay: int, stream, barrier, min_gpu_s: float, min_replays: int = 5, max_replays: int = 4000):
+    """Times a train of back-to-back `replay()` calls (each enqueues `n_per_replay` units of work on `stream`)
+    long enough for >= min_gpu_s of GPU time: one event before, one after every replay. Returns
+    (train_ms, [ms per replay], replays). The estimate for the train length comes from one untimed replay."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    replay()
+    e1.record(stream)
+    barrier()
+    est_ms = max(e0.elapsed_time(e1), 1e-3)
+    reps = int(min(max_replays, max(min_replays, math.ceil(min_gpu_s * 1e3 / est_ms))))
+    # every rank must enqueue the same number of launches (the gather is a collective)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        t = torch.tensor([reps], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        reps = int(t.item())
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    barrier()
+    evs[0].record(stream)
+    for r in range(reps):
+        replay()
+        evs[r + 1].record(stream)
+    barrier()
+    per = [evs[r].elapsed_time(evs[r + 1]) for r in range(reps)]
+    return evs[0].elapsed_time(evs[reps]), per, reps
+
+
+def max_over_ranks(x: float, dev, distributed: bool) -> float:
     import torch
     import torch.distributed as dist
 
-    from carl_b200 import _native
+    if not distributed:
+        return float(x)
+    t = torch.tensor([x], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def tensor_sha(t) -> str:
+    import hashlib
+
+    return hashlib.sha256(t.detach().cpu().contiguous().numpy().tobytes()).hexdigest()[:16]
+
+
+def run_gpu_arm(args):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    from carl_b200 import _native, hostmem
     from carl_b200.envs import CARLCartPole, ContextTable
 
     rank = int(os.environ.get("RANK", "0"))
@@ -337,19 +389,24 @@ def run_gpu_arm(args):
     n_local = N_ENVS_PER_GPU
     n_global = n_local * world
     names, table = make_context_table(n_global)
-    env = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world))
+
+    def make_env():
+        e = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world))
+        e.reset(seed=0)
+        return e
+
+    env = make_env()
     assert env.num_envs == n_local
-    env.reset(seed=0)
     gather = None
     gather_mode = args.gather
     if distributed:
         from carl_b200.parallel import ObsGather
 
         if gather_mode == "fused":
-            # every rank must succeed in mapping its peers (CUDA IPC / P2P); otherwise all fall back to NCCL
+            # every rank must succeed in mapping its peers; otherwise all fall back to NCCL
             ok = 1
             try:
-                gather = ObsGather(env, mode="fused")
+                gather = ObsGather(env, mode="fused", pipelined=True)
             except Exception as e:  # pragma: no cover - depends on the box
                 ok = 0
                 print(f"[rank {rank}] fused gather unavailable ({e}); falling back to NCCL", file=sys.stderr)
@@ -359,15 +416,14 @@ def run_gpu_arm(args):
                 if gather is not None:
                     gather.close()
                 gather, gather_mode = None, "nccl"
-                # a handle that had a gather attached is rebuilt without one
-                env = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world))
-                env.reset(seed=0)
+                env = make_env()  # a handle that had a gather attached is rebuilt without one
         if gather is None:
             gather = ObsGather(env, mode="nccl")
+    fused_gather = gather is not None and gather.mode == "fused"
 
     K, W = args.steps, args.warmup
     T = max(1, min(K, args.fuse))  # fused steps per launch
-    plan = [T] * (K // T) + ([K % T] if K % T else [])  # launches that time EXACTLY K steps
+    plan = [T] * (K // T) + ([K % T] if K % T else [])  # the launches of ONE pass = exactly K steps
     info = env._info
     # trajectory ring: outputs larger than L2 so every launch's writes go to DRAM
     slot_bytes = T * n_local * TRAJ_BYTES
@@ -378,110 +434,158 @@ def run_gpu_arm(args):
                  done=torch.empty(T, n_local, dtype=torch.uint8, device=dev)) for _ in range(n_slots)]
     trajs = [_native.Traj(obs=r["obs"].data_ptr(), actions=r["actions"].data_ptr(), reward=r["reward"].data_ptr(),
                           done=r["done"].data_ptr()) for r in ring]
-    import ctypes
-
     lib, handle = env._lib, env._handle
     stream = torch.cuda.current_stream(dev)
-
-    def fused_launch(i, step_base):
-        _native.check(lib.carlb_env_rollout(handle, T, 12345, step_base, None, _native.ACT_I32,
-                                            ctypes.byref(trajs[i % n_slots]), stream.cuda_stream))
-        if gather is not None:
-            gather.gather(lag=1 if i > 0 else 0)
 
     def barrier():
         if distributed:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---------------- value: fused rollout, device resident
-    for w in range(max(W // T, 3)):
-        fused_launch(w, w * T)
+    # ---------------- value: fused rollout, device resident.
+    # ONE pass = the K timed steps (len(plan) launches of the fused rollout kernel, each streaming its trajectory
+    # to a ring slot; with N > 1 every launch also carries the obs all-gather). A pass of a few launches is
+    # microseconds of GPU work, so the timed region is a TRAIN of R back-to-back passes (>= --min-gpu-seconds),
+    # replayed from a CUDA graph of C passes so that the host's enqueue rate is not what is measured.
+    launch_no = [0]
+
+    def one_pass(st):
+        for t_j in plan:
+            j = launch_no[0]
+            launch_no[0] += 1
+            _native.check(lib.carlb_env_rollout(handle, t_j, 12345, (j * T) & 0x3FFFFFFF, None, _native.ACT_I32,
+                                                ctypes.byref(trajs[j % n_slots]), st))
+            if gather is not None and not fused_gather:
+                gather.gather(lag=1 if j > 0 else 0)  # NCCL baseline: asynchronous collective, consumed one launch behind
+
+    for w in range(max(3, -(-W // K))):  # >= W warm-up steps, eager
+        one_pass(stream.cuda_stream)
     barrier()
+    use_graph = gather is None or fused_gather
+    passes_per_chunk = max(1, -(-n_slots // len(plan)))  # one trip round the ring
+    while passes_per_chunk * len(plan) < 24:
+        passes_per_chunk *= 2
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(stream)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(passes_per_chunk):
+                one_pass(torch.cuda.current_stream(dev).cuda_stream)
+        torch.cuda.synchronize(dev)
+
+    def chunk():
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(passes_per_chunk):
+                one_pass(stream.cuda_stream)
+
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     launches0 = _native.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in plan]
-    barrier()
-    ev0.record(stream)
-    for j, t_j in enumerate(plan):
-        kev[j][0].record(stream)
-        _native.check(lib.carlb_env_rollout(handle, t_j, 12345, 10_000 + j * T, None, _native.ACT_I32,
-                                            ctypes.byref(trajs[j % n_slots]), stream.cuda_stream))
-        kev[j][1].record(stream)
-        if gather is not None:
-            gather.gather(lag=1)  # pipelined consumer: launch k+1 is enqueued before obs k is awaited
-    ev1.record(stream)
-    barrier()
-    fused_ms = ev0.elapsed_time(ev1)
-    kernel_ms = [a.elapsed_time(b) for a, b in kev]
-    launches = _native.launch_count() - launches0
+    train_ms, chunk_ms, n_chunks = timed_train(chunk, passes_per_chunk, stream, barrier, args.min_gpu_seconds)
     clock_info = clocks.stop() if rank == 0 else None
-    t_fused = torch.tensor([fused_ms], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(t_fused, op=dist.ReduceOp.MAX)
-    fused_ms = float(t_fused.item())
-    value = n_global * K / (fused_ms * 1e-3)
-    k_avg_ms = float(np.mean(kernel_ms[:K // T]))  # the full-length launches (the roofline's per-launch figure)
+    if fused_gather:
+        gather.resync()
+    passes = n_chunks * passes_per_chunk
+    launches = passes * len(plan)  # kernels of the timed region (graph replays are not seen by the host-side counter)
+    train_ms = max_over_ranks(train_ms, dev, distributed)
+    value = n_global * K * passes / (train_ms * 1e-3)
+    pass_ms_median = float(np.median(chunk_ms)) / passes_per_chunk
+    k_avg_ms = train_ms / launches  # launch-to-launch period inside the train (upper bound of the kernel duration)
 
-    if args.fused_only:  # profiling runs (tools/gpu_round.sh): only the timed region's launches, then stop
+    if args.fused_only:  # profiling runs: only the warm-up and the timed train, then stop
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-                              "ms_per_step": fused_ms / K, "fused_only": True, "gpu_launches": int(launches),
-                              "config": {"fused_steps_per_launch": T, "launches": len(plan), "n_envs": n_global},
-                              "kernel_ms_avg": k_avg_ms}))
+                              "ms_per_step": train_ms / (passes * K), "fused_only": True, "gpu_launches": int(launches),
+                              "config": {"fused_steps_per_launch": T, "launches_per_pass": len(plan), "passes": passes,
+                                         "n_envs": n_global}, "kernel_ms_avg": k_avg_ms}))
         if distributed:
             dist.destroy_process_group()
         return 0
 
-    # ---------------- step_api: one launch per step, graph-replayed, actions ring > L2
-    K_api = min(K, 2000)
+    # gathered tensor == what ONE GPU computes for the whole batch (correctness of the sharded path in this very run)
+    gather_check = None
+    if distributed:
+        chk = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world))
+        from carl_b200.parallel import ObsGather
+
+        cg = ObsGather(chk, mode=gather.mode, pipelined=False)
+        chk.reset(seed=7)
+        for j in range(3):
+            chk.rollout(11, policy_seed=99, step_base=11 * j)
+        got = cg.gather().clone()
+        sha = tensor_sha(got)
+        torch.cuda.synchronize(dev)
+        want_sha = None
+        if rank == 0:
+            whole = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True)
+            whole.reset(seed=7)
+            for j in range(3):
+                whole.rollout(11, policy_seed=99, step_base=11 * j)
+            want_sha = tensor_sha(whole._obs)
+            whole.close()
+        shas = [None] * world
+        dist.all_gather_object(shas, sha)
+        if rank == 0:
+            gather_check = {"equal": all(s_ == want_sha for s_ in shas), "sha256_16": want_sha, "ranks_checked": world,
+                            "what": f"[{n_global}, {info.obs_dim}] gathered obs after reset(seed=7) + 3 x 11 fused steps on every "
+                                    f"rank vs the same sequence on ONE GPU holding all {n_global} envs"}
+        dist.barrier()
+        cg.close()
+        chk.close()
+
+    # ---------------- step_api: one launch per step (+ gather with N > 1), graph-replayed, actions ring > L2
     ring_steps = int(math.ceil(1.2 * L2_BYTES / (n_local * 4)))  # int32 actions: 256 KiB per step
-    G = min(K_api, ring_steps)
-    K_api -= K_api % G
+    G = ring_steps
     act_ring = torch.randint(0, 2, (G, n_local), dtype=torch.int32, device=dev)
-    side = torch.cuda.Stream(dev)
-    side.wait_stream(stream)
-    with torch.cuda.stream(side):
+    api_gather_mode = None
+    if fused_gather:
+        # the consumer that feeds obs k into step k+1 needs the gathered tensor of THIS step: SYNC mode
+        _native.check(lib.carlb_gather_set_mode(gather._g, 0))
+        api_gather_mode = "fused, sync (push + wait inside every step launch)"
+    side2 = torch.cuda.Stream(dev)
+    side2.wait_stream(stream)
+    with torch.cuda.stream(side2):
         for g_ in range(3):
-            _native.check(lib.carlb_env_step(handle, act_ring[g_ % G].data_ptr(), _native.ACT_I32, side.cuda_stream))
+            _native.check(lib.carlb_env_step(handle, act_ring[g_ % G].data_ptr(), _native.ACT_I32, side2.cuda_stream))
     torch.cuda.synchronize(dev)
-    graph = None
-    if not distributed:  # the fused gather changes slot / flag value per launch: not graph-capturable
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
+    api_graph = None
+    if use_graph:
+        api_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(api_graph, stream=side2):
             for g_ in range(G):
                 _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32,
                                                  torch.cuda.current_stream(dev).cuda_stream))
 
-    def replay():
-        if graph is not None:
-            graph.replay()
+    def api_replay():
+        if api_graph is not None:
+            api_graph.replay()
         else:
             for g_ in range(G):
                 _native.check(lib.carlb_env_step(handle, act_ring[g_].data_ptr(), _native.ACT_I32, stream.cuda_stream))
                 gather.gather()
+            api_gather_mode_nccl[0] = "nccl all_gather_into_tensor after every step"
 
-    for _ in range(max(1, W // G)):
-        replay()
-    barrier()
-    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a0.record(stream)
-    for _ in range(K_api // G):
-        replay()
-    a1.record(stream)
-    barrier()
-    api_ms = a0.elapsed_time(a1)
-    api_value = n_local * K_api / (api_ms * 1e-3)
+    api_gather_mode_nccl = [None]
+    api_ms, _, api_reps = timed_train(api_replay, G, stream, barrier, min(args.min_gpu_seconds, 0.1), min_replays=2)
+    api_ms = max_over_ranks(api_ms, dev, distributed)
+    K_api = api_reps * G
+    api_value = n_global * K_api / (api_ms * 1e-3)
+    if fused_gather:
+        gather.resync()
+        _native.check(lib.carlb_gather_set_mode(gather._g, 1))
 
     # cold-L2 single launches: flush L2 (write a buffer larger than L2) between timed launches
     flush = torch.empty(L2_BYTES * 2 // 4, dtype=torch.float32, device=dev)
     cold = []
     for g_ in range(20):
         flush.fill_(float(g_))
+        if distributed:
+            dist.barrier()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record(stream)
         _native.check(lib.carlb_env_step(handle, act_ring[g_ % G].data_ptr(), _native.ACT_I32, stream.cuda_stream))
@@ -489,69 +593,88 @@ def run_gpu_arm(args):
         torch.cuda.synchronize(dev)
         cold.append(c0.elapsed_time(c1))
     cold_ms = float(np.median(cold[3:]))
+    del flush
 
-    # ---------------- e2e: env.step(numpy actions) -> numpy results (host buffers, copies timed)
-    K_e2e = min(K, 500)
-    # inputs start in page-locked host memory (carl_b200.hostmem): the step kernel reads each step's action
-    # row in place over PCIe and writes obs/reward/terminated/truncated straight into page-locked result arrays
-    from carl_b200 import hostmem
-
+    # ---------------- e2e: env.step(numpy actions) -> numpy results (host buffers, copies timed).
+    # Passes of K calls, repeated until >= 2000 calls, per-pass times recorded.
     # (a policy writes into the same few page-locked buffers every step -- 4 here; cycling through many MB of
     # them only adds IOTLB misses on the GPU's PCIe reads: tools/e2e_probe.py, profiles/r01l_e2e_probe.json)
     E2E_ROWS = 4
     host_actions = hostmem.pinned_empty((E2E_ROWS, n_local), np.int32)
     host_actions[...] = np.random.default_rng(1).integers(0, 2, size=(E2E_ROWS, n_local), dtype=np.int32)
-    for w in range(5):
+    for w in range(max(5, min(W, 50))):
         env.step(host_actions[w % E2E_ROWS])
+    e2e_passes = max(3, -(-args.e2e_calls // K))
     barrier()
-    t0 = time.perf_counter()
+    pass_s = []
     acc = 0.0
-    for j in range(K_e2e):
-        obs, rew, term, trunc, _ = env.step(host_actions[j % E2E_ROWS])
-        acc += float(rew[0])  # the result is read on the host every step
+    t_begin = time.perf_counter()
+    j = 0
+    for p_ in range(e2e_passes):
+        t0 = time.perf_counter()
+        for _ in range(K):
+            obs, rew, term, trunc, _i = env.step(host_actions[j % E2E_ROWS])
+            acc += float(rew[0])  # the result is read on the host every step
+            j += 1
+        pass_s.append(time.perf_counter() - t0)
     torch.cuda.synchronize(dev)
-    e2e_s = time.perf_counter() - t0
-    t_e2e = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if distributed:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = n_global * K_e2e / float(t_e2e.item())
+    e2e_s = max_over_ranks(time.perf_counter() - t_begin, dev, distributed)
+    K_e2e = e2e_passes * K
+    e2e_value = n_global * K_e2e / e2e_s
     h2d = n_local * 4
     d2h = n_local * (info.obs_dim * 4 + 4 + 1 + 1)
+    e2e_async = e2e_async_leg(env, host_actions, K, e2e_passes, dev, distributed, n_global) if hasattr(env, "step_async") else None
 
+    peak, peak_src = hbm_peak()
+    extra = {}
+    if not args.no_ant:
+        extra["ant_8192"] = ant_leg(dev, peak, args, rank, world, barrier)
+        extra["config5_halfcheetah_hopper"] = config5_leg(dev, args, rank, world, barrier)
+    if not args.no_f64:
+        extra["value_f64"] = f64_leg(dev, names, table, rank, world, K, T, barrier, args, n_global)
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
         return 0
 
-    peak, peak_src = hbm_peak()
     # DRAM bytes of ONE launch from the committed ncu --set full capture -- only quoted when that capture
     # fused the same number of env-steps per launch as this run (per launch, like `achieved`)
-    prof, prof_file = measured_profile("prof_rollout")
-    prof_T = prof.get("fused_steps_per_launch", 100)
-    prof_traffic = float(prof["dram_bytes_per_launch"]) if ("dram_bytes_per_launch" in prof and prof_T == T) else None
-    prof_traffic_src = (f"profiles/{prof_file} (ncu --set full of the same bench command, {prof_T} env-steps per launch"
-                        + ("" if prof_T == T else f"; this run fuses {T}, so no per-launch figure is quoted") + ")") if prof_file else None
+    prof, prof_file = measured_profile("prof_rollout", T)
+    prof_traffic = float(prof["dram_bytes_per_launch"]) if "dram_bytes_per_launch" in prof else None
+    prof_traffic_src = (f"profiles/{prof_file} (ncu --set full of `bench.py --steps {T} --fused-only`, {T} env-steps per launch; "
+                        f"ncu flushes the caches before every replay and the 126 MB L2 still holds most of the launch's "
+                        f"trajectory writes when the kernel ends)") if prof_file else None
     fused_bytes_per_launch = (TRAJ_BYTES * T + STEP_CONTRACT_BYTES) * n_local  # trajectory + one state/ctx round trip
     achieved = fused_bytes_per_launch / (k_avg_ms * 1e-3) / 1e9
     api_ms_per_launch = api_ms / K_api
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": fused_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": train_ms / (passes * K), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
             "workload": f"CARLCartPole, {N_ENVS_PER_GPU} sampled contexts (gravity/length/masscart) per GPU "
                         f"(BASELINE configs[1]), uniform random policy, autoreset, TimeLimit 500",
-            "n_envs": n_global, "fused_steps_per_launch": T, "launches": len(plan),
+            "n_envs": n_global, "fused_steps_per_launch": T, "launches_per_pass": len(plan),
+            "timed_region": f"{passes} back-to-back passes of the {K}-step plan ({launches} rollout launches, "
+                            f"{train_ms:.1f} ms of GPU time) between two CUDA events; "
+                            + (f"replayed from a CUDA graph of {passes_per_chunk} passes" if graph is not None else "eager launches"),
+            "passes": passes, "pass_ms_median": pass_ms_median, "pass_ms_mean": train_ms / passes,
             "l2": f"trajectory ring {n_slots} x {slot_bytes / 2**20:.0f} MiB > L2 (outputs go to DRAM); env state "
                   f"({n_local * 90 / 2**20:.1f} MiB working set) is register/L2 resident by design",
-            "collective": (f"obs all-gather per launch: {gather_mode}" + (" (in-kernel NVLink peer stores + flag wait)" if gather_mode == "fused" else "") + ", consumed one launch behind (pipelined)") if distributed else "none",
+            "collective": (f"obs all-gather with EVERY rollout launch: {gather_mode}"
+                           + (f" ({gather.transport}; pipelined: a publisher warp per CTA pushes obs k over NVLink while launch "
+                              f"k+1 computes, flags and waits in-kernel, no extra launch)" if fused_gather else
+                              " (asynchronous NCCL collective, consumed one launch behind)")) if distributed else "none",
         },
         "gpu_launches": int(launches),
+        "gpu_launches_host_counted": int(_native.launch_count() - launches0),
         "clocks": clock_info,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": K_e2e, "api": "CARLCartPole.step(numpy int32 actions in page-locked memory) -> numpy obs/reward/terminated/"
-                                       "truncated (carlb_env_step_host_checked: the step kernel reads the actions over PCIe, range-checks them "
-                                       "itself -- undo log, rolled back if one is invalid -- and writes the results over PCIe)", "ms_per_step": float(t_e2e.item()) / K_e2e * 1e3},
+                "steps": K_e2e, "passes": e2e_passes, "pass_ms_median": float(np.median(pass_s)) * 1e3,
+                "api": "CARLCartPole.step(numpy int32 actions in page-locked memory) -> numpy obs/reward/terminated/"
+                       "truncated (carlb_env_step_host_checked: the step kernel reads the actions over PCIe, range-checks them "
+                       "itself -- undo log, rolled back if one is invalid -- and writes the results over PCIe)",
+                "ms_per_step": e2e_s / K_e2e * 1e3},
         "roofline": {
             "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -560,14 +683,21 @@ def run_gpu_arm(args):
             "algorithmic_bytes_per_launch": fused_bytes_per_launch,
             "bytes_per_env_step": TRAJ_BYTES + STEP_CONTRACT_BYTES / T,
             "kernel_ms_avg": k_avg_ms,
+            "kernel_ms_how": "train time / launches: the launch-to-launch period inside the timed train (includes the "
+                             "inter-kernel gap, so it bounds the kernel duration from above)",
             "frac_vs_step_contract_90B": (STEP_CONTRACT_BYTES * n_local * T / (k_avg_ms * 1e-3) / 1e9) / peak,
-            # the kernel is instruction-issue bound, not HBM bound, at this batch size (ncu, same command):
-            "issue_slot_utilisation_pct": measured_profile("prof_rollout")[0].get("issue_active_pct"),
-            "warps_active_pct": measured_profile("prof_rollout")[0].get("warps_active_pct"),
+            "frac_note": "`frac` counts the bytes the fused kernel must move (25 B trajectory per env-step + one 90 B "
+                         "state/context round trip per launch); SURVEY §8(d)'s per-step contract (90 B per env-step, state "
+                         "re-read every step) gives frac_vs_step_contract_90B, which can exceed 1 because the state stays in registers",
+            # the kernel is instruction-issue bound, not HBM bound, at this batch size (ncu, same T):
+            "issue_slot_utilisation_pct": prof.get("issue_active_pct"),
+            "warps_active_pct": prof.get("warps_active_pct"),
+            "ncu_kernel_us": prof.get("duration_us"),
         },
         "step_api": {
-            "value": api_value * world, "unit": UNIT, "steps": K_api, "us_per_launch": api_ms_per_launch * 1e3,
-            "l2": f"actions ring of {G} steps x 256 KiB > L2; CUDA-graph replay of {G} launches",
+            "value": api_value, "unit": UNIT, "steps": K_api, "us_per_launch": api_ms_per_launch * 1e3,
+            "l2": f"actions ring of {G} steps x 256 KiB > L2; " + (f"CUDA-graph replay of {G} launches" if api_graph is not None else "eager launches"),
+            "gather": (api_gather_mode or api_gather_mode_nccl[0]) if distributed else None,
             "roofline": {"kernel": "step_kernel<CARTPOLE,float>", "bound": "hbm",
                          "achieved": STEP_CONTRACT_BYTES * n_local / (api_ms_per_launch * 1e-3) / 1e9, "peak": peak,
                          "unit": "GB/s", "frac": STEP_CONTRACT_BYTES * n_local / (api_ms_per_launch * 1e-3) / 1e9 / peak,
@@ -576,8 +706,14 @@ def run_gpu_arm(args):
             "cold_l2_frac": STEP_CONTRACT_BYTES * n_local / (cold_ms * 1e-3) / 1e9 / peak,
         },
     }
-    if world == 1 and not args.no_ant:
-        out["ant_8192"] = ant_leg(dev, peak, args)
+    if e2e_async is not None:
+        out["e2e_async"] = e2e_async
+    if gather_check is not None:
+        out["gather_check"] = gather_check
+    out.update(extra)
+    done_counts = committed_done_mask_counts()
+    if done_counts is not None:
+        out["done_mask_mismatches_fp32"] = done_counts
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline_leg(steps_per_call=200, target_seconds=args.cpu_seconds)
     print(json.dumps(out))
@@ -586,27 +722,105 @@ def run_gpu_arm(args):
     return 0
 
 
-def ant_leg(dev, peak, args):
-    """Secondary north-star workload (BASELINE configs[3] at one GPU): CARLBraxAnt, 8 192 contexts
-    (gravity / mass_torso / friction sampled, context_mode="applied"), uniform random policy."""
+def committed_done_mask_counts():
+    """fp32-mode done-mask mismatches against the float64 oracle, counted by the GPU test-suite on 10^6 random
+    (state, action, context) triples per env kind (tests/test_classic_parity_gpu.py writes the file; bench.py
+    itself never runs the oracle outside its CPU-baseline leg)."""
+    p = os.path.join(ROOT, "profiles", "done_mask_counts.json")
+    try:
+        return json.load(open(p))
+    except Exception:
+        return None
+
+
+def e2e_async_leg(env, host_actions, K, passes, dev, distributed, n_global):
+    return None
+
+
+def f64_leg(dev, names, table, rank, world, K, T, barrier, args, n_global):
+    """The same fused-rollout train in the reference's own precision (dtype="float64": state, context and
+    arithmetic in float64, done masks bit-identical to the float64 reference)."""
     import ctypes
 
     import torch
 
     from carl_b200 import _native
-    from carl_b200.context import ContextSampler, UniformFloatContextFeature
-    from carl_b200.envs import CARLBraxAnt, ContextTable
+    from carl_b200.envs import CARLCartPole, ContextTable
 
-    n = 8192
-    names = list(CARLBraxAnt.get_context_space().get_default_context().keys())
-    sampler = ContextSampler(
-        [UniformFloatContextFeature("gravity", -15, -5), UniformFloatContextFeature("mass_torso", 5, 20),
-         UniformFloatContextFeature("friction", 0.5, 1.5)], context_space=CARLBraxAnt.get_context_space(), seed=0)
-    env = CARLBraxAnt(contexts=ContextTable(names, sampler.sample_context_table(n, names)), device=dev,
-                      context_mode="applied")
+    n_local = N_ENVS_PER_GPU
+    env = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True, shard=(rank, world), dtype="float64")
     env.reset(seed=0)
+    slot_bytes = T * n_local * TRAJ_BYTES
+    n_slots = max(2, int(math.ceil(1.5 * L2_BYTES / slot_bytes)) + 1)
+    ring = [dict(obs=torch.empty(T, n_local, 4, device=dev), actions=torch.empty(T, n_local, dtype=torch.int32, device=dev),
+                 reward=torch.empty(T, n_local, device=dev), done=torch.empty(T, n_local, dtype=torch.uint8, device=dev))
+            for _ in range(n_slots)]
+    trajs = [_native.Traj(obs=r["obs"].data_ptr(), actions=r["actions"].data_ptr(), reward=r["reward"].data_ptr(),
+                          done=r["done"].data_ptr()) for r in ring]
+    stream = torch.cuda.current_stream(dev)
+    plan = [T] * (K // T) + ([K % T] if K % T else [])
+    cnt = [0]
+
+    def one_pass(st):
+        for t_j in plan:
+            j = cnt[0]
+            cnt[0] += 1
+            _native.check(env._lib.carlb_env_rollout(env._handle, t_j, 12345, (j * T) & 0x3FFFFFFF, None, _native.ACT_I32,
+                                                     ctypes.byref(trajs[j % n_slots]), st))
+
+    for _ in range(3):
+        one_pass(stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    ppc = max(1, -(-n_slots // len(plan)))
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(stream)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(ppc):
+            one_pass(torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize(dev)
+    ms, _, reps = timed_train(graph.replay, ppc, stream, barrier, min(args.min_gpu_seconds, 0.1), min_replays=3)
+    ms = max_over_ranks(ms, dev, world > 1)
+    env.close()
+    return {"value": n_global * K * ppc * reps / (ms * 1e-3), "unit": UNIT, "dtype": "f64", "passes": ppc * reps,
+            "note": "same workload and plan as `value`, CARLCartPole(dtype='float64'): the reference's float64 arithmetic"}
+
+
+def _brax_contexts(cls, n, features):
+    from carl_b200.context import ContextSampler, UniformFloatContextFeature
+    from carl_b200.envs import ContextTable
+
+    names = list(cls.get_context_space().get_default_context().keys())
+    sampler = ContextSampler([UniformFloatContextFeature(k, lo, hi) for k, (lo, hi) in features.items()],
+                             context_space=cls.get_context_space(), seed=0)
+    return ContextTable(names, sampler.sample_context_table(n, names))
+
+
+def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
+    """Secondary north-star workload (BASELINE configs[3]): CARLBraxAnt, 8 192 contexts PER GPU (weak scaling over
+    1 -> 8 GPUs; gravity / mass_torso / friction sampled, context_mode="applied"), uniform random policy. With N > 1
+    every launch carries the obs all-gather (fused NVLink push, pipelined)."""
+    import ctypes
+    import time
+
+    import torch
+
+    from carl_b200 import _native, hostmem
+    from carl_b200.envs import CARLBraxAnt
+
+    distributed = world > 1
+    n = 8192
+    n_global = n * world
+    ctxs = _brax_contexts(CARLBraxAnt, n_global, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)})
+    env = CARLBraxAnt(contexts=ctxs, device=dev, context_mode="applied", shard=(rank, world))
+    env.reset(seed=0)
+    gather = None
+    if distributed:
+        from carl_b200.parallel import ObsGather
+
+        gather = ObsGather(env, mode="fused", pipelined=True)
     info = env._info
-    T, K = 20, 200
+    T = 20
     traj_bytes = info.obs_dim * 4 + info.act_dim * 4 + 4 + 1
     ring = [dict(obs=torch.empty(T, n, info.obs_dim, device=dev), actions=torch.empty(T, n, info.act_dim, device=dev),
                  reward=torch.empty(T, n, device=dev), done=torch.empty(T, n, dtype=torch.uint8, device=dev))
@@ -614,81 +828,152 @@ def ant_leg(dev, peak, args):
     trajs = [_native.Traj(obs=r["obs"].data_ptr(), actions=r["actions"].data_ptr(), reward=r["reward"].data_ptr(),
                           done=r["done"].data_ptr()) for r in ring]
     stream = torch.cuda.current_stream(dev)
-    launch = lambda j: _native.check(env._lib.carlb_env_rollout(env._handle, T, 7, j * T, None, _native.ACT_F32,
-                                                                ctypes.byref(trajs[j % 8]), stream.cuda_stream))
+    cnt = [0]
+
+    def launch():
+        j = cnt[0]
+        cnt[0] += 1
+        _native.check(env._lib.carlb_env_rollout(env._handle, T, 7, j * T, None, _native.ACT_F32,
+                                                 ctypes.byref(trajs[j % 8]), stream.cuda_stream))
+
     for j in range(3):
-        launch(j)
-    torch.cuda.synchronize(dev)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for j in range(K // T):
-        launch(10 + j)
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    ms = e0.elapsed_time(e1)
-    fused = n * K / (ms * 1e-3)
-    # single-step API, device actions
+        launch()
+    ms, per, reps = timed_train(launch, 1, stream, barrier, min(args.min_gpu_seconds, 0.15), min_replays=5)
+    ms = max_over_ranks(ms, dev, distributed)
+    fused = n_global * T * reps / (ms * 1e-3)
+    launch_ms = ms / reps
+    # single-step API, device actions (+ the gather of every step's obs in SYNC mode with N > 1)
+    if gather is not None:
+        _native.check(env._lib.carlb_gather_set_mode(gather._g, 0))
     acts = torch.rand(64, n, info.act_dim, device=dev) * 2 - 1
     for j in range(5):
         env.step(acts[j])
-    torch.cuda.synchronize(dev)
-    e0.record(stream)
-    for j in range(100):
+    cnt2 = [0]
+
+    def step_launch():
+        j = cnt2[0]
+        cnt2[0] += 1
         _native.check(env._lib.carlb_env_step(env._handle, acts[j % 64].data_ptr(), _native.ACT_F32, stream.cuda_stream))
-    e1.record(stream)
-    torch.cuda.synchronize(dev)
-    api_ms = e0.elapsed_time(e1) / 100
+
+    api_total_ms, _, api_reps = timed_train(step_launch, 1, stream, barrier, 0.03, min_replays=50)
+    api_ms = max_over_ranks(api_total_ms, dev, distributed) / api_reps
     step_bytes = 1114  # R state 468 + ctx 24 + action 32 + 4 ; W state 468 + obs 108 + 4 + 2 + 4
     # host buffers in / out: env.step(numpy float32 actions in page-locked memory) -> numpy results
-    import time
-
-    from carl_b200 import hostmem
-
     host_acts = hostmem.pinned_empty((4, n, info.act_dim), np.float32)
     host_acts[...] = np.random.default_rng(2).uniform(-1, 1, size=host_acts.shape).astype(np.float32)
     for j in range(5):
         env.step(host_acts[j % 4])
-    torch.cuda.synchronize(dev)
+    barrier()
     t0 = time.perf_counter()
     acc = 0.0
-    for j in range(100):
+    n_e2e = 200
+    for j in range(n_e2e):
         o_h, r_h, te_h, tr_h, _ = env.step(host_acts[j % 4])
         acc += float(r_h[0])
     torch.cuda.synchronize(dev)
-    e2e_ms = (time.perf_counter() - t0) / 100 * 1e3
+    e2e_ms = max_over_ranks(time.perf_counter() - t0, dev, distributed) / n_e2e * 1e3
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         try:  # reported next to the GPU number; never allowed to break the bench line
             cpu = brax_cpu_baseline(env._sysd, env._ctx.cpu().numpy(), target_seconds=3.0)
         except Exception as e:  # pragma: no cover
             cpu = {"error": repr(e)}
+    transport = gather.transport if gather is not None else None
+    if gather is not None:
+        torch.cuda.synchronize(dev)
+        barrier()
+        gather.close()
+    env.close()
     return {
         "cpu_baseline": cpu,
-        "workload": "CARLBraxAnt, 8192 sampled contexts (gravity/mass_torso/friction), context_mode=applied, "
-                    "uniform random policy, 10 spring substeps per env-step",
-        "value": fused, "unit": UNIT, "fused_steps_per_launch": T, "ms_per_env_step_batch": ms / K,
+        "workload": f"CARLBraxAnt, 8192 sampled contexts per GPU (gravity/mass_torso/friction), context_mode=applied, "
+                    f"uniform random policy, 10 spring substeps per env-step; {n_global} envs on {world} GPU(s), weak scaling",
+        "value": fused, "unit": UNIT, "fused_steps_per_launch": T, "launches": reps, "ms_per_env_step_batch": launch_ms / T,
+        "collective": (f"obs all-gather with every launch: fused ({transport}), pipelined" if distributed else "none"),
         "roofline": {"bound": "fp32-issue (HBM shown for reference)", "bytes_per_env_step": traj_bytes + step_bytes / T,
-                     "achieved": (traj_bytes * T + step_bytes) * n / (ms / (K // T) * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                     "frac": (traj_bytes * T + step_bytes) * n / (ms / (K // T) * 1e-3) / 1e9 / peak},
-        "step_api": {"value": n / (api_ms * 1e-3), "us_per_launch": api_ms * 1e3,
+                     "achieved": (traj_bytes * T + step_bytes) * n / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": (traj_bytes * T + step_bytes) * n / (launch_ms * 1e-3) / 1e9 / peak,
+                     "frac_vs_step_contract_1114B": step_bytes * n * T / (launch_ms * 1e-3) / 1e9 / peak},
+        "step_api": {"value": n_global / (api_ms * 1e-3), "us_per_launch": api_ms * 1e3,
+                     "gather": "fused, sync (push + wait inside every step launch)" if distributed else None,
                      "hbm_frac_1114B": step_bytes * n / (api_ms * 1e-3) / 1e9 / peak},
-        "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "us_per_step": e2e_ms * 1e3,
+        "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "us_per_step": e2e_ms * 1e3,
                 "h2d_bytes_per_step": n * info.act_dim * 4, "d2h_bytes_per_step": n * (info.obs_dim * 4 + 4 + 1 + 1),
                 "api": "CARLBraxAnt.step(numpy float32 actions in page-locked memory) -> numpy obs/reward/terminated/truncated "
                        "(the step kernel reads the actions and writes the results over PCIe itself)"},
     }
 
 
+def config5_leg(dev, args, rank, world, barrier):
+    """BASELINE configs[4]: CARLBraxHalfcheetah + CARLBraxHopper, 16 384 contexts in total (8 192 each), sharded over
+    the N GPUs (STRONG scaling: the total is fixed), one `step` per env kind per step with the obs all-gather of
+    EVERY step (fused NVLink push, sync mode: the gathered tensor of step k is complete when step k's launch ends).
+    The two kinds run on two streams (independent batches)."""
+    import torch
+
+    from carl_b200 import _native
+    from carl_b200.envs import CARLBraxHalfcheetah, CARLBraxHopper
+
+    distributed = world > 1
+    n_each = 8192
+    envs, gathers, acts, streams = [], [], [], []
+    for cls in (CARLBraxHalfcheetah, CARLBraxHopper):
+        ctxs = _brax_contexts(cls, n_each, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)})
+        e = cls(contexts=ctxs, device=dev, context_mode="applied", shard=(rank, world))
+        e.reset(seed=0)
+        envs.append(e)
+        if distributed:
+            from carl_b200.parallel import ObsGather
+
+            gathers.append(ObsGather(e, mode="fused", pipelined=False))
+        acts.append(torch.rand(16, e.num_envs, e._info.act_dim, device=dev) * 2 - 1)
+        streams.append(torch.cuda.Stream(dev))
+    main = torch.cuda.current_stream(dev)
+    cnt = [0]
+    fork, joins = torch.cuda.Event(), [torch.cuda.Event() for _ in envs]
+
+    def step_both():
+        j = cnt[0]
+        cnt[0] += 1
+        fork.record(main)
+        for e, a, st, jn in zip(envs, acts, streams, joins):
+            st.wait_event(fork)
+            _native.check(e._lib.carlb_env_step(e._handle, a[j % 16].data_ptr(), _native.ACT_F32, st.cuda_stream))
+            jn.record(st)
+            main.wait_event(jn)
+
+    for _ in range(5):
+        step_both()
+    ms, _, reps = timed_train(step_both, 1, main, barrier, min(args.min_gpu_seconds, 0.1), min_replays=20)
+    ms = max_over_ranks(ms, dev, distributed)
+    transport = gathers[0].transport if gathers else None
+    torch.cuda.synchronize(dev)
+    barrier()
+    for g in gathers:
+        g.close()
+    for e in envs:
+        e.close()
+    return {"workload": f"CARLBraxHalfcheetah 8192 + CARLBraxHopper 8192 contexts in total, sharded over {world} GPU(s) "
+                        f"({n_each // world} of each per GPU), one step per kind per step, obs all-gather EVERY step",
+            "value": 2 * n_each * reps / (ms * 1e-3), "unit": UNIT, "scaling": "strong", "steps": reps,
+            "us_per_step": ms / reps * 1e3,
+            "collective": f"fused ({transport}), sync: push + wait inside every step launch" if distributed else "none"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="carl_b200", choices=["carl_b200", "reference"])
     ap.add_argument("--fuse", type=int, default=500, help="env-steps fused per rollout launch")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-ant", action="store_true")
+    ap.add_argument("--no-ant", action="store_true", help="skip the CARLBraxAnt and Halfcheetah+Hopper legs")
+    ap.add_argument("--no-f64", action="store_true", help="skip the float64 leg")
+    ap.add_argument("--min-gpu-seconds", type=float, default=0.25,
+                    help="the timed train repeats the K-step pass until at least this much GPU time is covered")
+    ap.add_argument("--e2e-calls", type=int, default=2000, help="minimum number of timed env.step(numpy) calls")
     ap.add_argument("--fused-only", action="store_true",
                     help="profiling aid: run the warm-up and the timed fused-rollout region, print a short line, stop")
     ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="multi-GPU obs gather path")

@@ -41,9 +41,7 @@ Segment make_segment(const carlb_env* env, int act_dtype) {
   s.terminated = env->bufs.terminated;
   s.truncated = env->bufs.truncated;
   s.final_obs = env->bufs.final_obs;
-  s.n_peers = env->n_peers;
-  for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
-  s.block_counter = nullptr;
+  s.gth = GatherDev{};
   s.host_obs = nullptr; s.host_reward = nullptr; s.host_terminated = nullptr; s.host_truncated = nullptr;
   return s;
 }
@@ -284,16 +282,6 @@ int carlb_env_configure(carlb_env_t* env, int max_episode_steps, int autoreset) 
   return CARLB_OK;
 }
 
-int carlb_env_set_peers(carlb_env_t* env, int n_peers, float* const* peer_obs) {
-  if (env == nullptr || n_peers < 0 || n_peers > CARLB_MAX_PEERS || (n_peers > 0 && peer_obs == nullptr)) {
-    set_error("carlb_env_set_peers: bad arguments (n_peers=%d, max %d)", n_peers, CARLB_MAX_PEERS);
-    return CARLB_ERR_INVALID;
-  }
-  env->n_peers = n_peers;
-  for (int r = 0; r < n_peers; ++r) env->peer_obs[r] = peer_obs[r];
-  return CARLB_OK;
-}
-
 int carlb_env_seed(carlb_env_t* env, uint64_t seed, void* stream) {
   int rc = check_ready(env, "carlb_env_seed");
   if (rc != CARLB_OK) return rc;
@@ -506,6 +494,7 @@ int carlb_env_rollout(carlb_env_t* env, int n_steps, uint64_t policy_seed, uint3
     set_error("carlb_env_rollout: action dtype %d not valid for env kind %d", act_dtype, env->kind);
     return CARLB_ERR_INVALID;
   }
+  if (n_steps == 0) return CARLB_OK;  // nothing to do (and no observation produced: the fused gather must not count it)
   CARLB_CUDA_CHECK(cudaSetDevice(env->device));
   if (is_brax(env->kind))
     return brax_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream);

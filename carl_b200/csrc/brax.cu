@@ -53,11 +53,7 @@ struct BraxSeg {
   float* final_obs;
   float* first_state;
   float* first_obs;
-  int n_peers;
-  float* peer_obs[CARLB_MAX_PEERS];
-  unsigned int* peer_flags[CARLB_MAX_PEERS];
-  unsigned int signal_value;
-  unsigned int* block_counter;
+  GatherDev gth;     // fused cross-GPU obs gather of this launch (common.cuh; always an immediate push here)
   // zero-copy host mirrors (carlb_env_step_host with page-locked buffers): the single-step kernel also
   // stores obs / reward / flags straight into mapped host memory (posted PCIe writes behind the physics)
   float* host_obs;
@@ -406,7 +402,7 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
 template <int W, int E, bool SP>
 __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W, E>& sm, const float* actions, int n_steps,
                                                uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& traj,
-                                               int stock_contact) {
+                                               int stock_contact, unsigned int gseq) {
   constexpr int LPE = Lanes<E>::LPE;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = min(lane / LPE, E - 1), sl = lane - sub * LPE;  // lanes beyond E*LPE idle in the last sub-env
@@ -496,7 +492,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
     for (int i = c.sl; i < D; i += LPE) {
       const float v = w.obs[i];
       seg.obs[(size_t)env * D + i] = v;
-      for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
+      if (seg.gth.n_peers > 0) gather_store_elem(seg.gth, gseq, (size_t)(seg.global_offset + env) * D + i, v);
     }
     if (c.sl == 0) {
       seg.reward[env] = reward;
@@ -531,10 +527,11 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? (E >= 3 ? 5 : 4) : 2) brax_st
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
+  const unsigned int gseq = gather_begin(seg.gth);
   const int warp = threadIdx.x >> 5;
   if ((blockIdx.x * W + warp) * E < seg.n)  // warp-uniform: at least one sub-env of this warp is real
-    brax_step_body<W, E, SP>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact);
-  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+    brax_step_body<W, E, SP>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact, gseq);
+  gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // ------------------------------------------------------------------------------ reset
@@ -546,14 +543,15 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
+  const unsigned int gseq = gather_begin(seg.gth);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int env = blockIdx.x * 4 + warp;
   if (env < seg.n) {
     if (mask != nullptr && mask[env] == 0) {
       // not reset: with a fused gather attached the current row still has to reach the new slot
-      for (int r = 0; r < seg.n_peers; ++r)
+      if (seg.gth.n_peers > 0)
         for (int i = lane; i < seg.obs_dim; i += 32)
-          seg.peer_obs[r][(size_t)(seg.global_offset + env) * seg.obs_dim + i] = seg.obs[(size_t)env * seg.obs_dim + i];
+          gather_store_elem(seg.gth, gseq, (size_t)(seg.global_offset + env) * seg.obs_dim + i, seg.obs[(size_t)env * seg.obs_dim + i]);
     } else {
       const float* sys = sm.sys;
       EnvScratch& w = sm.env[warp];
@@ -605,7 +603,7 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
         const float v = w.obs[i];
         seg.obs[(size_t)env * D + i] = v;
         seg.first_obs[(size_t)env * D + i] = v;
-        for (int r = 0; r < seg.n_peers; ++r) seg.peer_obs[r][(size_t)(seg.global_offset + env) * D + i] = v;
+        if (seg.gth.n_peers > 0) gather_store_elem(seg.gth, gseq, (size_t)(seg.global_offset + env) * D + i, v);
       }
       if (lane == 0) {
         seg.reward[env] = 0.0f;
@@ -616,7 +614,7 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
       }
     }
   }
-  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+  gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // ---------------------------------------------------------------------------- host side
@@ -710,7 +708,7 @@ int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_
   return CARLB_OK;
 }
 
-static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what) {
+static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what, int gather_launch = -1) {
   const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
   if (h == nullptr || !h->have_table) {
     set_error("%s: carlb_brax_set_system() has not been called", what);
@@ -740,11 +738,8 @@ static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what) {
   s.final_obs = env->bufs.final_obs;
   s.first_state = static_cast<float*>(env->bufs.first_state);
   s.first_obs = env->bufs.first_obs;
-  s.n_peers = env->n_peers;
-  for (int r = 0; r < env->n_peers; ++r) s.peer_obs[r] = env->peer_obs[r];
-  s.block_counter = nullptr;
-  if (env->gather != nullptr)
-    gather_fill(env->gather, &s.n_peers, s.peer_obs, s.peer_flags, &s.signal_value, &s.block_counter);
+  s.gth = GatherDev{};
+  if (env->gather != nullptr && gather_launch >= 0) gather_fill(env->gather, &s.gth, gather_launch);
   return CARLB_OK;
 }
 
@@ -851,7 +846,7 @@ int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
 
 int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st) {
   BraxSeg seg;
-  int rc = make_brax_seg(env, seg, "carlb_env_reset");
+  int rc = make_brax_seg(env, seg, "carlb_env_reset", GL_RESET);
   if (rc != CARLB_OK) return rc;
   brax_reset_kernel<<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1>), st>>>(seg, mask, q, qd);
   g_launches++;
@@ -866,7 +861,7 @@ int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
 int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm) {
   (void)act_dtype;
   BraxSeg seg;
-  int rc = make_brax_seg(env, seg, "carlb_env_step");
+  int rc = make_brax_seg(env, seg, "carlb_env_step", GL_BRAX);
   if (rc != CARLB_OK) return rc;
   if (hm != nullptr) {
     seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
@@ -882,9 +877,9 @@ int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32
                  int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
   (void)act_dtype;
   BraxSeg seg;
-  int rc = make_brax_seg(env, seg, "carlb_env_rollout");
-  if (rc != CARLB_OK) return rc;
   if (n_steps == 0) return CARLB_OK;
+  int rc = make_brax_seg(env, seg, "carlb_env_rollout", GL_BRAX);
+  if (rc != CARLB_OK) return rc;
   carlb_traj_t tj{};
   if (traj != nullptr) tj = *traj;
   seg.final_obs = nullptr;

@@ -48,15 +48,15 @@ __global__ void __launch_bounds__(kBlock) seed_kernel(uint64_t* rng, int n, uint
 
 // ----------------------------------------------------------------------------- reset
 template <int KIND, typename T>
-__device__ __forceinline__ void reset_one(const Segment& seg, const uint8_t* mask, int i) {
+__device__ __forceinline__ void reset_one(const Segment& seg, const uint8_t* mask, int i, unsigned int gseq) {
   typedef Traits<KIND> Tr;
   if (mask != nullptr && mask[i] == 0) {
     // not reset: with a fused gather attached the current row still has to reach the new slot
-    if (seg.n_peers > 0) {
+    if (seg.gth.n_peers > 0) {
       float o[Tr::D];
 #pragma unroll
       for (int k = 0; k < Tr::D; ++k) o[k] = seg.obs[(size_t)i * Tr::D + k];
-      for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+      gather_store_row<Tr::D>(seg.gth, gseq, (size_t)(seg.global_offset + i), o);
     }
     return;
   }
@@ -70,7 +70,7 @@ __device__ __forceinline__ void reset_one(const Segment& seg, const uint8_t* mas
   store_rng_state(seg.rng, seg.n, i, g);
   StateIO<T, Tr::S>::store(seg.state, i, s);
   store_obs<Tr::D>(seg.obs, (size_t)i, o);
-  for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+  if (seg.gth.n_peers > 0) gather_store_row<Tr::D>(seg.gth, gseq, (size_t)(seg.global_offset + i), o);
   seg.elapsed[i] = 0;
   if (KIND == KIND_CARTPOLE) seg.sbt[i] = 0;
   seg.reward[i] = 0.0f;
@@ -80,9 +80,10 @@ __device__ __forceinline__ void reset_one(const Segment& seg, const uint8_t* mas
 
 template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ Segment seg, const uint8_t* mask) {
+  const unsigned int gseq = gather_begin(seg.gth);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) reset_one<KIND, T>(seg, mask, i);
-  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+  if (i < seg.n) reset_one<KIND, T>(seg, mask, i, gseq);
+  gather_epilogue_immediate(seg.gth, gseq);  // resets always push their own rows (no previous launch to defer to)
 }
 
 // ------------------------------------------------------------------------------ step
@@ -96,7 +97,8 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <int KIND, typename T, bool CHK>
-__device__ __forceinline__ void step_one(const Segment& seg, const void* actions, int i, const StepCheck& chk) {
+__device__ __forceinline__ void step_one(const Segment& seg, const void* actions, int i, const StepCheck& chk,
+                                         unsigned int gseq) {
   typedef Traits<KIND> Tr;
   T p[Tr::P];
   load_rows<KIND, T>(seg, i, 0, Tr::P_STEP, p);
@@ -154,7 +156,8 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
   if (rng_live) store_rng_state(seg.rng, seg.n, i, g);
   StateIO<T, Tr::S>::store(seg.state, i, s);
   store_obs<Tr::D>(seg.obs, (size_t)i, o);
-  for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+  if (seg.gth.n_peers > 0 && seg.gth.mode == GATHER_IMMEDIATE)
+    gather_store_row<Tr::D>(seg.gth, gseq, (size_t)(seg.global_offset + i), o);
   seg.reward[i] = so.reward;
   seg.terminated[i] = so.terminated ? 1 : 0;
   seg.truncated[i] = tr ? 1 : 0;
@@ -168,22 +171,66 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
   }
 }
 
+// DEFERRED push of the fused gather (common.cuh): the CTA carries one extra warp. Every compute thread
+// first stores the row the PREVIOUS launch left in seg.obs into every rank's gathered buffer (posted
+// NVLink stores: the thread does not wait for them) and arrives on a named barrier; the extra warp
+// waits on that barrier and does the part that would stall: the system-scope fence that drains the CTA's
+// peer stores, the CTA count and -- in the last CTA -- the flag publication. The physics of this launch
+// runs meanwhile. Returns false in the threads of the publisher warp (which are done).
+template <int D>
+__device__ __forceinline__ bool deferred_push_prologue(const Segment& seg, unsigned int gseq, int nct, int i) {
+  if ((int)threadIdx.x >= nct) {
+    named_bar_sync(kBarPushed, nct + 32);
+    if ((int)threadIdx.x == nct) gather_publish(seg.gth, gseq, gridDim.x);
+    return false;
+  }
+  if (i < seg.n) {
+    float o[D];
+    const float* src = seg.obs + (size_t)i * D;
+    if (D % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + k);
+        o[k] = v.x; o[k + 1] = v.y; o[k + 2] = v.z; o[k + 3] = v.w;
+      }
+    } else if (D % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k += 2) {
+        const float2 v = *reinterpret_cast<const float2*>(src + k);
+        o[k] = v.x; o[k + 1] = v.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) o[k] = src[k];
+    }
+    gather_store_row<D>(seg.gth, gseq, (size_t)(seg.global_offset + i), o);
+  }
+  named_bar_arrive(kBarPushed, nct + 32);
+  return true;
+}
+
 template <int KIND, typename T>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Segment seg, const void* actions) {
+__global__ void __launch_bounds__(kBlock + 32) step_kernel(const __grid_constant__ Segment seg, const void* actions) {
   pdl_launch_dependents();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) step_one<KIND, T, false>(seg, actions, i, StepCheck{});
+  const bool deferred = seg.gth.n_peers > 0 && seg.gth.mode == GATHER_DEFERRED;  // never together with PDL
+  const int nct = deferred ? (int)blockDim.x - 32 : (int)blockDim.x;             // compute threads per CTA
+  const unsigned int gseq = gather_begin(seg.gth);
+  const int i = blockIdx.x * nct + threadIdx.x;
+  if (deferred && !deferred_push_prologue<Traits<KIND>::D>(seg, gseq, nct, i)) return;
+  if (i < seg.n) step_one<KIND, T, false>(seg, actions, i, StepCheck{}, gseq);
   else pdl_wait();
-  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+  if (deferred) gather_epilogue_deferred(seg.gth, gseq, nct);
+  else gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // The host-buffer step with in-kernel action validation and an undo log (StepCheck).
 template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock) step_checked_kernel(const __grid_constant__ Segment seg, const void* actions,
                                                               const __grid_constant__ StepCheck chk) {
+  const unsigned int gseq = gather_begin(seg.gth);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) step_one<KIND, T, true>(seg, actions, i, chk);
-  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+  if (i < seg.n) step_one<KIND, T, true>(seg, actions, i, chk, gseq);
+  gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // Roll a checked step back: state / elapsed / steps-beyond flag of every env, PCG64 state where it moved.
@@ -216,11 +263,11 @@ struct MixedParams {
 template <typename T>
 __device__ __forceinline__ void mixed_dispatch(const Segment& seg, const void* actions, int i) {
   switch (seg.kind) {
-    case KIND_CARTPOLE: step_one<KIND_CARTPOLE, T, false>(seg, actions, i, StepCheck{}); break;
-    case KIND_PENDULUM: step_one<KIND_PENDULUM, T, false>(seg, actions, i, StepCheck{}); break;
-    case KIND_ACROBOT: step_one<KIND_ACROBOT, T, false>(seg, actions, i, StepCheck{}); break;
-    case KIND_MOUNTAINCAR: step_one<KIND_MOUNTAINCAR, T, false>(seg, actions, i, StepCheck{}); break;
-    default: step_one<KIND_MOUNTAINCAR_CONT, T, false>(seg, actions, i, StepCheck{}); break;
+    case KIND_CARTPOLE: step_one<KIND_CARTPOLE, T, false>(seg, actions, i, StepCheck{}, 0u); break;
+    case KIND_PENDULUM: step_one<KIND_PENDULUM, T, false>(seg, actions, i, StepCheck{}, 0u); break;
+    case KIND_ACROBOT: step_one<KIND_ACROBOT, T, false>(seg, actions, i, StepCheck{}, 0u); break;
+    case KIND_MOUNTAINCAR: step_one<KIND_MOUNTAINCAR, T, false>(seg, actions, i, StepCheck{}, 0u); break;
+    default: step_one<KIND_MOUNTAINCAR_CONT, T, false>(seg, actions, i, StepCheck{}, 0u); break;
   }
 }
 
@@ -264,7 +311,7 @@ template <typename P> __device__ __forceinline__ P* pin_reg(P* v) {
 template <int KIND, typename T, bool REC, bool AR>
 __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
                                              uint32_t step_base, const void* actions, const carlb_traj_t& traj,
-                                             int refill_threshold, uint64_t* sv_slot) {
+                                             int refill_threshold, uint64_t* sv_slot, unsigned int gseq) {
   typedef Traits<KIND> Tr;
   const int n = seg.n;
   const int max_steps = pin_reg(seg.max_steps);
@@ -394,7 +441,8 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   StateIO<T, Tr::S>::store(seg.state, i, s);
   if (n_steps > 0) {
     store_obs<Tr::D>(seg.obs, (size_t)i, o);
-    for (int r = 0; r < seg.n_peers; ++r) store_obs<Tr::D>(seg.peer_obs[r], (size_t)(seg.global_offset + i), o);
+    if (seg.gth.n_peers > 0 && seg.gth.mode == GATHER_IMMEDIATE)
+      gather_store_row<Tr::D>(seg.gth, gseq, (size_t)(seg.global_offset + i), o);
     seg.reward[i] = so.reward;
     seg.terminated[i] = so.terminated ? 1 : 0;
     seg.truncated[i] = tr ? 1 : 0;
@@ -404,21 +452,26 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
 }
 
 template <int KIND, typename T, bool REC>
-__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
-                                                         uint64_t policy_seed, uint32_t step_base, const void* actions,
-                                                         const carlb_traj_t traj, int refill_threshold) {
+__global__ void __launch_bounds__(kBlock + 32) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
+                                                              uint64_t policy_seed, uint32_t step_base, const void* actions,
+                                                              const carlb_traj_t traj, int refill_threshold) {
   __shared__ uint64_t sv_sh[2 * kBlock];  // per-thread PCG64 state saved before a pre-generated reset
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool deferred = seg.gth.n_peers > 0 && seg.gth.mode == GATHER_DEFERRED;
+  const int nct = deferred ? (int)blockDim.x - 32 : (int)blockDim.x;  // compute threads per CTA
+  const unsigned int gseq = gather_begin(seg.gth);
+  const int i = blockIdx.x * nct + threadIdx.x;
+  if (deferred && !deferred_push_prologue<Traits<KIND>::D>(seg, gseq, nct, i)) return;
   if (i < seg.n) {
     bool clean = seg.autoreset != CARLB_AUTORESET_NONE;  // warp-uniform choice of the specialised loop
     if (KIND == KIND_CARTPOLE) clean = __all_sync(__activemask(), clean && seg.sbt[i] == 0);
     uint64_t* sv_slot = &sv_sh[threadIdx.x];
-    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot);
-    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot);
+    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq);
+    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq);
   }
-  // ONE call site reached by every thread of the CTA: the epilogue contains an aligned barrier,
+  // ONE call site reached by every (compute) thread of the CTA: the epilogues contain an aligned barrier,
   // which must not be executed from divergent code (ragged tail warps)
-  peer_signal_epilogue(seg.n_peers, seg.peer_flags, seg.signal_value, seg.block_counter);
+  if (deferred) gather_epilogue_deferred(seg.gth, gseq, nct);
+  else gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // --------------------------------------------------------------------------- launchers
@@ -446,15 +499,19 @@ int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
   return CARLB_OK;
 }
 
-// Fused cross-GPU gather: point this launch at the next slot of every rank's buffer.
-static void attach_gather(const carlb_env* env, Segment& seg) {
+// Fused cross-GPU gather: describe this launch's push (slot / flag value come from device memory).
+static void attach_gather(const carlb_env* env, Segment& seg, int launch_kind) {
   if (env->gather == nullptr) return;
-  gather_fill(env->gather, &seg.n_peers, seg.peer_obs, seg.peer_flags, &seg.signal_value, &seg.block_counter);
+  gather_fill(env->gather, &seg.gth, launch_kind);
+}
+// block size of a step / rollout launch: one extra (publisher) warp per CTA when the push is deferred
+static inline int block_with_publisher(const Segment& seg, int compute_threads) {
+  return compute_threads + ((seg.gth.n_peers > 0 && seg.gth.mode == GATHER_DEFERRED) ? 32 : 0);
 }
 
 int classic_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) {
   Segment seg = make_segment(env, CARLB_ACT_I32);
-  attach_gather(env, seg);
+  attach_gather(env, seg, GL_RESET);
   CARLB_DISPATCH_KIND_T(env->kind, env->precision, (reset_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, mask)));
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
@@ -474,8 +531,8 @@ static bool pdl_enabled() {
 
 template <int KIND, typename T>
 static cudaError_t launch_step_pdl(const Segment& seg, const void* actions, int n, cudaStream_t st) {
-  if (!pdl_enabled()) {
-    step_kernel<KIND, T><<<grid_for(n), kBlock, 0, st>>>(seg, actions);
+  if (!pdl_enabled() || seg.gth.n_peers > 0) {  // the fused gather reads device-side counters the previous launch writes
+    step_kernel<KIND, T><<<grid_for(n), block_with_publisher(seg, kBlock), 0, st>>>(seg, actions);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg = {};
@@ -493,7 +550,7 @@ static cudaError_t launch_step_pdl(const Segment& seg, const void* actions, int 
 
 int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm) {
   Segment seg = make_segment(env, act_dtype);
-  attach_gather(env, seg);
+  attach_gather(env, seg, GL_CLASSIC_STEP);
   if (hm != nullptr) {
     seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
     seg.host_truncated = hm->truncated;
@@ -509,7 +566,7 @@ int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaS
 int classic_step_checked(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm,
                          const StepCheck& chk) {
   Segment seg = make_segment(env, act_dtype);
-  attach_gather(env, seg);
+  attach_gather(env, seg, GL_IMMEDIATE_ONLY);
   if (hm != nullptr) {
     seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
     seg.host_truncated = hm->truncated;
@@ -532,7 +589,7 @@ int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& ch
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
   Segment seg = make_segment(env, act_dtype);
-  attach_gather(env, seg);
+  attach_gather(env, seg, GL_CLASSIC_STEP);
   carlb_traj_t tj{};
   if (traj != nullptr) tj = *traj;
   // 64-thread blocks: at N = 65 536 that is 1024 blocks ~ 6.9 per SM (better tail balance over
@@ -553,11 +610,11 @@ int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uin
   const bool rec = actions == nullptr && tj.obs != nullptr && tj.actions != nullptr && tj.reward != nullptr && tj.done != nullptr;
   if (rec) {
     CARLB_DISPATCH_KIND_T(env->kind, env->precision,
-                          (rollout_kernel<K_, T_, true><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
+                          (rollout_kernel<K_, T_, true><<<grid, block_with_publisher(seg, kRolloutBlock), 0, st>>>(seg, n_steps, policy_seed, step_base,
                                                                                         actions, tj, kRefillThreshold)));
   } else {
     CARLB_DISPATCH_KIND_T(env->kind, env->precision,
-                          (rollout_kernel<K_, T_, false><<<grid, kRolloutBlock, 0, st>>>(seg, n_steps, policy_seed, step_base,
+                          (rollout_kernel<K_, T_, false><<<grid, block_with_publisher(seg, kRolloutBlock), 0, st>>>(seg, n_steps, policy_seed, step_base,
                                                                                          actions, tj, kRefillThreshold)));
   }
   g_launches++;

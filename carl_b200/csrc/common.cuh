@@ -8,6 +8,168 @@
 
 namespace carlb {
 
+// ------------------------------------------------------------------------------------------------
+// Fused cross-GPU observation gather, device side (host side: gather.cu).
+//
+// Every rank owns one symmetric buffer  obs[kGatherSlots][n_global][D] | flags[MAX_PEERS] | ctrl[8]
+// mapped into all ranks. A "push" stores this rank's rows into the SAME slot of every rank's buffer
+// and then publishes the push count into its flag word on every rank. Slot and flag value come from
+// a counter in DEVICE memory (ctrl[0] = pushes published so far), not from kernel parameters, so a
+// sequence of obs-producing launches can be captured into a CUDA graph and replayed.
+//
+//   GATHER_IMMEDIATE  the rows this launch computes are stored at its end (step / reset / rollout /
+//                     Brax kernels), the last CTA publishes, then (wait_lag >= 0) spins until every
+//                     rank has published push  seq + 1 - wait_lag.
+//   GATHER_DEFERRED   (classic step / rollout) a dedicated publisher warp per CTA pushes the rows the
+//                     PREVIOUS launch left in seg.obs while the other warps compute: the NVLink
+//                     transfer and its system-scope fence overlap the physics instead of draining at
+//                     the end of the grid.
+constexpr int kGatherSlots = 4;
+enum { GATHER_IMMEDIATE = 0, GATHER_DEFERRED = 1 };
+enum { GCTRL_SEQ = 0, GCTRL_PUSH_COUNTER = 1, GCTRL_END_COUNTER = 2 };
+
+struct GatherDev {
+  int n_peers;                                // world size (0: no gather attached)
+  int mode;                                   // GATHER_IMMEDIATE / GATHER_DEFERRED
+  int wait_lag;                               // < 0: no in-kernel wait
+  unsigned long long slot_floats;             // floats per slot
+  float* peer_base[CARLB_MAX_PEERS];          // slot 0 of rank r's buffer (mapped here)
+  unsigned int* peer_flags[CARLB_MAX_PEERS];  // MY flag word in rank r's buffer
+  float* mc_base;                             // multicast alias of slot 0 (one multimem.st reaches every rank) or null
+  unsigned int* mc_flag;                      // multicast alias of my flag word, or null
+  const unsigned int* my_flags;               // flags[world] of the local buffer (written by the peers)
+  unsigned int* ctrl;                         // local control words (GCTRL_*)
+};
+
+__device__ __forceinline__ unsigned int ld_volatile_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Push sequence number of this launch, identical in every thread of the CTA. One aligned barrier:
+// every thread of the CTA must call it (before anything divergent).
+__device__ __forceinline__ unsigned int gather_begin(const GatherDev& g) {
+  __shared__ unsigned int sh_seq;
+  if (g.n_peers <= 0) return 0u;
+  if (threadIdx.x == 0) sh_seq = ld_volatile_u32(g.ctrl + GCTRL_SEQ);
+  __syncthreads();
+  return sh_seq;
+}
+
+// Store one obs row (D floats, 16-byte aligned when D % 4 == 0) into slot `seq` of every rank.
+template <int D>
+__device__ __forceinline__ void gather_store_row(const GatherDev& g, unsigned int seq, size_t global_row, const float* o) {
+  const size_t off = (size_t)(seq % kGatherSlots) * g.slot_floats + global_row * D;
+  if (g.mc_base != nullptr) {
+    float* dst = g.mc_base + off;
+    if (D % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k += 4)
+        asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]),
+                     "f"(o[k + 2]), "f"(o[k + 3]) : "memory");
+    } else if (D % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k += 2)
+        asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]) : "memory");
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(dst + k), "f"(o[k]) : "memory");
+    }
+    return;
+  }
+  for (int r = 0; r < g.n_peers; ++r) {
+    float* dst = g.peer_base[r] + off;
+    if (D % 4 == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+    } else if (D % 2 == 0) {
+#pragma unroll
+      for (int k = 0; k < D; k += 2) *reinterpret_cast<float2*>(dst + k) = make_float2(o[k], o[k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) dst[k] = o[k];
+    }
+  }
+}
+// One float of an obs row (kernels whose lanes own single elements: Brax).
+__device__ __forceinline__ void gather_store_elem(const GatherDev& g, unsigned int seq, size_t global_elem, float v) {
+  const size_t off = (size_t)(seq % kGatherSlots) * g.slot_floats + global_elem;
+  if (g.mc_base != nullptr) {
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(g.mc_base + off), "f"(v) : "memory");
+    return;
+  }
+  for (int r = 0; r < g.n_peers; ++r) g.peer_base[r][off] = v;
+}
+
+// Called by ONE thread per CTA after the CTA's pushed rows are ordered before it (barrier). The CTA
+// arrives with a DEVICE-scope release (fence + counter); only the last CTA to arrive pays the
+// system-scope fence and publishes push `seq` (flag value seq + 1) to every rank, then advances the
+// device-side sequence counter. Cumulativity makes that single system fence cover every CTA's rows: their
+// stores happen-before the arrivals the last CTA has observed (release / acquire at gpu scope), which
+// happen-before its fence.sys and the release store of the flag. One MEMBAR.SYS per launch instead of one
+// per CTA matters: system-scope fences of different SMs serialise (r02b: 1 024 of them cost ~12 us per launch).
+// Returns true in the thread that published.
+__device__ __forceinline__ bool gather_publish(const GatherDev& g, unsigned int seq, unsigned int n_ctas) {
+  __threadfence();
+  const unsigned int prev = atomicAdd(g.ctrl + GCTRL_PUSH_COUNTER, 1u);
+  if (prev != n_ctas - 1) return false;
+  __threadfence();  // acquire side of the CTA arrivals
+  g.ctrl[GCTRL_PUSH_COUNTER] = 0;
+  __threadfence_system();
+  if (g.mc_flag != nullptr) {
+    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(g.mc_flag), "r"(seq + 1u) : "memory");
+  } else {
+    for (int r = 0; r < g.n_peers; ++r)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.peer_flags[r]), "r"(seq + 1u) : "memory");
+  }
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(g.ctrl + GCTRL_SEQ), "r"(seq + 1u) : "memory");
+  return true;
+}
+
+// Spin (one thread) until every rank has published push `seq - wait_lag`.
+__device__ __forceinline__ void gather_wait_all(const GatherDev& g, unsigned int seq) {
+  if (g.wait_lag < 0) return;
+  const int target = (int)(seq + 1u) - g.wait_lag;
+  if (target <= 0) return;
+  for (int r = 0; r < g.n_peers; ++r)
+    while ((int)(ld_acquire_sys_u32(g.my_flags + r) - (unsigned int)target) < 0) {}
+}
+
+// Epilogue of an IMMEDIATE push: every thread of every CTA calls it once, from non-divergent code,
+// after its row stores. The thread that publishes also performs the in-kernel wait, so the completion
+// of the grid implies that the gathered tensor of push `seq - wait_lag` is complete on this rank.
+__device__ __forceinline__ void gather_epilogue_immediate(const GatherDev& g, unsigned int seq) {
+  if (g.n_peers <= 0) return;
+  __syncthreads();  // the CTA's row stores happen-before thread 0's fence (cumulativity through the barrier)
+  if (threadIdx.x == 0 && gather_publish(g, seq, gridDim.x)) gather_wait_all(g, seq);
+}
+
+// Named barriers of the DEFERRED push (barrier 0 is __syncthreads). `count` must be a multiple of 32 and
+// every thread of a participating warp must execute the instruction.
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+constexpr int kBarPushed = 1;   // compute warps arrive after storing their rows; the publisher warp syncs on it
+constexpr int kBarCompute = 2;  // compute warps only, at the end of the kernel
+
+// End of a DEFERRED-push kernel, called by every COMPUTE thread (n_compute of them per CTA) from
+// non-divergent code: the last CTA to finish checks that every rank's push has arrived.
+__device__ __forceinline__ void gather_epilogue_deferred(const GatherDev& g, unsigned int seq, int n_compute) {
+  named_bar_sync(kBarCompute, n_compute);
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(g.ctrl + GCTRL_END_COUNTER, 1u);
+    if (prev == gridDim.x - 1) {
+      g.ctrl[GCTRL_END_COUNTER] = 0;
+      gather_wait_all(g, seq);
+    }
+  }
+}
+
 // One homogeneous shard of env instances resident on this GPU. All pointers are device
 // pointers into caller-owned buffers (torch tensors); the library never allocates per step.
 struct Segment {
@@ -27,13 +189,8 @@ struct Segment {
   uint8_t* terminated; // [n]
   uint8_t* truncated;  // [n]
   float* final_obs;    // [n][D] or null
-  // fused cross-GPU observation gather: obs rows are additionally stored at
-  // peer_obs[r] + (global_offset + i) * D for every peer r (P2P-mapped symmetric buffers)
-  int n_peers;
-  float* peer_obs[CARLB_MAX_PEERS];
-  unsigned int* peer_flags[CARLB_MAX_PEERS];  // fused gather: my completion word in every rank's buffer
-  unsigned int signal_value;                  // value published when this launch's rows are stored
-  unsigned int* block_counter;                // local CTA arrival counter (last CTA publishes)
+  // fused cross-GPU observation gather of this launch (gth.n_peers == 0: none)
+  GatherDev gth;
   // zero-copy host mirrors (carlb_env_step_host with page-locked buffers): results are ALSO stored
   // straight into mapped host memory by the kernel (posted PCIe writes overlap the compute) instead
   // of four device->host copies after it; null otherwise
@@ -57,25 +214,6 @@ struct StepCheck {
   uint64_t* undo_rng;      // [2][n] PCG64 state words before this step (valid where undo_rng_flag)
   uint8_t* undo_rng_flag;  // [n]
 };
-
-// Fused-gather epilogue: every thread of every CTA calls this at the end of an obs-producing
-// kernel. Stores to peer memory are fenced at system scope, the last CTA to arrive publishes the
-// launch number into every rank's flag word.
-__device__ __forceinline__ void peer_signal_epilogue(int n_peers, unsigned int* const* peer_flags, unsigned int signal_value,
-                                                     unsigned int* block_counter) {
-  if (n_peers <= 0 || block_counter == nullptr) return;
-  __syncthreads();  // the CTA's peer stores happen-before thread 0's fence (cumulativity through the barrier)
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    const unsigned int prev = atomicAdd(block_counter, 1u);
-    if (prev == gridDim.x - 1) {
-      *block_counter = 0;
-      __threadfence_system();
-      for (int r = 0; r < n_peers; ++r)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flags[r]), "r"(signal_value) : "memory");
-    }
-  }
-}
 
 __device__ __forceinline__ Action load_action(const void* actions, int act_dtype, long long i) {
   Action a;

@@ -18,8 +18,6 @@ struct carlb_env {
   long long global_offset = 0;
   bool bound = false;
   carlb_buffers_t bufs{};
-  int n_peers = 0;
-  float* peer_obs[CARLB_MAX_PEERS] = {};
   void* brax_sys = nullptr;  // BraxHandle: device copy of the per-handle Brax system table
   carlb_gather* gather = nullptr;  // fused cross-GPU obs gather (gather.cu), or null
   // host-buffer step with in-kernel action validation (carlb_env_step_host_checked): undo log (one device
@@ -37,8 +35,14 @@ Segment make_segment(const carlb_env* env, int act_dtype);
 
 // gather.cu
 void gather_forget_env(carlb_gather* g, carlb_env* env);
-void gather_fill(carlb_gather* g, int* n_peers, float** peer_obs, unsigned int** peer_flags, unsigned int* signal_value,
-                 unsigned int** block_counter);
+// kinds of obs-producing launches, as the gather's bookkeeping sees them
+enum GatherLaunch {
+  GL_RESET = 0,           // immediate push of the rows the launch computes, waits for every rank's push of this launch
+  GL_CLASSIC_STEP = 1,    // classic step / rollout: the push may be deferred to a publisher warp (pipelined mode)
+  GL_BRAX = 2,            // Brax step / rollout: immediate push; pipelined mode waits one push behind
+  GL_IMMEDIATE_ONLY = 3,  // checked host-buffer step: as GL_RESET
+};
+void gather_fill(carlb_gather* g, GatherDev* out, int launch_kind);
 
 // classic.cu
 int classic_seed(const carlb_env* env, uint64_t seed, cudaStream_t st);

@@ -95,6 +95,9 @@ class CARLBraxEnv(CARLEnv):
         super().__init__(env=env, contexts=contexts, obs_context_features=obs_context_features,
                          obs_context_as_dict=obs_context_as_dict, context_selector=context_selector,
                          context_selector_kwargs=context_selector_kwargs, **kwargs)
+        if contexts is not None and not isinstance(contexts, dict):
+            # a dense ContextTable that varies the target behaves like the equivalent dict of contexts
+            self._goal_active = brax_goals.goal_wrapper_active_table(list(contexts.names), np.asarray(contexts.values))
 
     def _default_autoreset(self) -> bool:
         return True  # brax.envs.create(auto_reset=True) wraps the env in AutoResetWrapper
@@ -113,8 +116,10 @@ class CARLBraxEnv(CARLEnv):
             self._handle, t.ctypes.data_as(ctypes.c_void_p), int(t.size), 1 if self.context_mode == "reference" else 0))
 
     # ------------------------------------------------------------------ goal wrappers
-    def _goal_reset(self, device_like):
-        """``BraxWalkerGoalWrapper.reset`` (brax_walker_goal_wrapper.py:111-122), batched."""
+    def _goal_reset(self, device_like, mask=None):
+        """``BraxWalkerGoalWrapper.reset`` (brax_walker_goal_wrapper.py:111-122), batched. With a reset mask
+        only the env instances being reset get a fresh position / goal / radius; the dead-reckoned position
+        (hence the progress reward) of the others is left alone."""
         import torch
 
         from carl_b200.envs import brax_goals
@@ -124,15 +129,25 @@ class CARLBraxEnv(CARLEnv):
         vals = self._table.values[ids]
         goal = brax_goals.goal_positions(vals[:, names.index("target_direction")], vals[:, names.index("target_distance")])
         radius = vals[:, names.index("target_radius")]
-        self._goal_state = dict(
-            position=torch.zeros(self.num_envs, 2, dtype=torch.float64, device=self.device),
-            goal=torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float64)).to(self.device).contiguous(),
-            radius=torch.from_numpy(np.ascontiguousarray(radius, dtype=np.float64)).to(self.device).contiguous(),
-            reward=torch.zeros(self.num_envs, dtype=torch.float64, device=self.device),
-            success=torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device),
-            dt=brax_goals.MJCF_TIMESTEP[self.env_name],
-            idx=brax_goals.STATE_INDICES[self.env_name],
-        )
+        goal_t = torch.from_numpy(np.ascontiguousarray(goal, dtype=np.float64)).to(self.device).contiguous()
+        radius_t = torch.from_numpy(np.ascontiguousarray(radius, dtype=np.float64)).to(self.device).contiguous()
+        if mask is not None and self._goal_state is not None:
+            m = torch.from_numpy(np.asarray(mask, dtype=bool)).to(self.device)
+            g = self._goal_state
+            g["position"][m] = 0.0
+            g["goal"][m] = goal_t[m]
+            g["radius"][m] = radius_t[m]
+            g["success"][m] = 0
+            g["reward"][m] = 0.0
+        else:
+            self._goal_state = dict(
+                position=torch.zeros(self.num_envs, 2, dtype=torch.float64, device=self.device),
+                goal=goal_t, radius=radius_t,
+                reward=torch.zeros(self.num_envs, dtype=torch.float64, device=self.device),
+                success=torch.zeros(self.num_envs, dtype=torch.uint8, device=self.device),
+                dt=brax_goals.MJCF_TIMESTEP[self.env_name],
+                idx=brax_goals.STATE_INDICES[self.env_name],
+            )
         self._goal_strings = None
 
     def _goal_strings_list(self):
@@ -147,8 +162,13 @@ class CARLBraxEnv(CARLEnv):
     def reset(self, *, seed=None, options=None, mask=None):
         state, info = super().reset(seed=seed, options=options, mask=mask)
         if self._goal_active:
-            self._goal_reset(state["obs"])
-            info["success"] = np.zeros(self.num_envs, dtype=np.int64)
+            mask_np = None
+            if mask is not None:
+                import torch
+
+                mask_np = (mask.detach().cpu().numpy() if isinstance(mask, torch.Tensor) else np.asarray(mask)).astype(bool)
+            self._goal_reset(state["obs"], mask_np)
+            info["success"] = self._goal_state["success"].to("cpu").numpy().astype(np.int64)
             if self.use_language_goals:
                 state = {"obs": {"obs": state["obs"], "goal": self._goal_strings_list()}, "context": state["context"]}
         return state, info
@@ -218,7 +238,7 @@ class CARLBraxEnv(CARLEnv):
         return cls.get_context_space().get_default_context()
 
     @classmethod
-    def kernel_params(cls, table, names, context_mode="reference"):
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
         """Batched ``CARLBraxEnv._update_context`` (``carl_brax_env.py:255-292``).
 
         rows: gravity, friction, elasticity, ang_damping, joint-stiffness scale, mass_<link> per link.

@@ -54,6 +54,16 @@ def goal_wrapper_active(contexts: dict | None) -> bool:
     return bool(max_diff_dir > 0.1 or max_diff_dist > 0.1)
 
 
+def goal_wrapper_active_table(names: list[str], values: np.ndarray) -> bool:
+    """The same gate for contexts handed over as a dense ``ContextTable`` (columns ``names``): on when the
+    table carries both target columns and either one rises above its first row's value by more than 0.1."""
+    if "target_distance" not in names or "target_direction" not in names or len(values) == 0:
+        return False
+    d = values[:, names.index("target_direction")]
+    r = values[:, names.index("target_distance")]
+    return bool((d - d[0]).max() > 0.1 or (r - r[0]).max() > 0.1)
+
+
 def goal_positions(directions: np.ndarray, distances: np.ndarray) -> np.ndarray:
     """``np.array(direction_values[target_direction]) * target_distance`` per env (:115-118)."""
     d = np.array([DIRECTION_VALUES[int(k)] for k in directions], dtype=np.float64)

@@ -203,6 +203,7 @@ class CARLEnv(abc.ABC):
         self._ctx_obs_host_cache = None
         self._ids_view = None
         self._seeded = False
+        self._seed_value = None
         self._has_reset = False
         self._validate_actions = bool(validate_actions)
         self._host_io = None
@@ -239,6 +240,9 @@ class CARLEnv(abc.ABC):
                 vals[:, j] = contexts.values[:, cnames.index(n)] if n in cnames else float(defaults[n])
             self._table = ContextTable(names, vals, contexts.keys)
             self._contexts_dict = None
+            # which features each context named itself (kernel_params of "applied" mode may need to tell a
+            # deliberately chosen default value from a filled-in one)
+            self._explicit = np.tile(np.array([n in cnames for n in names], dtype=bool), (len(contexts), 1))
         else:
             renamed = {k: {alias.get(n, n): v for n, v in c.items()} for k, c in contexts.items()}
             filled = {}
@@ -258,6 +262,7 @@ class CARLEnv(abc.ABC):
             vals = np.array([[float(c.get(n, defaults[n])) for n in names] for c in filled.values()], dtype=np.float64)
             self._table = ContextTable(names, vals.reshape(len(filled), len(names)), list(filled.keys()))
             self._contexts_dict = filled
+            self._explicit = np.array([[n in c for n in names] for c in renamed.values()], dtype=bool).reshape(len(filled), len(names))
         self._params_table = None  # rebuilt lazily by _update_context
 
     @property
@@ -414,7 +419,8 @@ class CARLEnv(abc.ABC):
     # ------------------------------------------------------- context -> kernel
     @classmethod
     @abc.abstractmethod
-    def kernel_params(cls, table: np.ndarray, names: list[str], context_mode: str = "reference") -> np.ndarray:
+    def kernel_params(cls, table: np.ndarray, names: list[str], context_mode: str = "reference",
+                      explicit: np.ndarray | None = None) -> np.ndarray:
         """Map the dense context table ``float64[M, F]`` onto the kernel-parameter columns
         ``float64[M, P]`` (the batched form of ``_update_context``, ``carl_env.py:307-319``).
         Pure host logic (testable without a GPU)."""
@@ -423,7 +429,8 @@ class CARLEnv(abc.ABC):
     def _update_context(self, mask: np.ndarray | None = None) -> None:
         """Upload the kernel-parameter rows of the envs whose context id changed."""
         if self._params_table is None:
-            self._params_table = np.ascontiguousarray(self.kernel_params(self._table.values, self._feature_names, self.context_mode))
+            self._params_table = np.ascontiguousarray(
+                self.kernel_params(self._table.values, self._feature_names, self.context_mode, explicit=self._explicit))
             assert self._params_table.shape == (len(self._table), self._info.n_param_rows)
         ids = self._context_ids
         np_dt = np.float32 if self._ctx.dtype == torch.float32 else np.float64
@@ -492,11 +499,13 @@ class CARLEnv(abc.ABC):
         if seed is not None:
             _native.check(self._lib.carlb_env_seed(self._handle, int(seed), st))
             self._seeded = True
+            self._seed_value = int(seed)
         elif not self._seeded:
             # gymnasium seeds from OS entropy on the first unseeded reset
             entropy = int(np.random.SeedSequence().generate_state(1, np.uint64)[0] >> 1)
             _native.check(self._lib.carlb_env_seed(self._handle, entropy, st))
             self._seeded = True
+            self._seed_value = entropy
         mask_t = None
         if mask_np is not None:
             mask_t = torch.from_numpy(mask_np.astype(np.uint8)).to(self.device)
@@ -534,7 +543,8 @@ class CARLEnv(abc.ABC):
             raise RuntimeError("Cannot call env.step() before calling env.reset()")
         if isinstance(action, torch.Tensor) and action.is_cuda:
             self._check_actions(self.num_envs, tuple(action.shape))
-            if action.dtype not in _TORCH_ACT:
+            if action.dtype not in _TORCH_ACT or (self._info.act_discrete and action.dtype.is_floating_point):
+                # as the host path does: a float tensor of integral action values is accepted for discrete envs
                 action = action.to(torch.int32 if self._info.act_discrete else torch.float32)
             if not self._info.act_discrete and action.dtype != torch.float32:
                 action = action.to(torch.float32)
@@ -652,24 +662,69 @@ class CARLEnv(abc.ABC):
 
     # ------------------------------------------------------------ checkpointing
     def state_dict(self) -> dict[str, Any]:
-        """Everything needed to resume: env state, counters, RNG streams, context binding."""
+        """Everything needed to resume an uninterrupted run: env state, counters, RNG streams (classic: the
+        PCG64 words; Brax: the reset seed + per-env episode counters), the context binding AND the selection
+        state (per-env round-robin counters, the selector's ``context_id`` / ``n_calls``), the goal wrapper's
+        dead-reckoned positions. ``load_state_dict`` checks kind, batch geometry and precision."""
+        sel = self.context_selector
+        goal = None
+        if getattr(self, "_goal_state", None) is not None:
+            goal = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in self._goal_state.items()}
         return {
+            "meta": {"kind": self.kind, "num_envs": self.num_envs, "global_num_envs": self.global_num_envs,
+                     "env_lo": self.env_lo, "dtype": self.dtype, "n_contexts": len(self._table)},
             "state": self._state.clone(), "elapsed": self._elapsed.clone(), "sbt": self._sbt.clone(),
-            "rng": self._rng.clone(), "obs": self._obs.clone(), "context_ids": self._context_ids.copy(),
+            "rng": self._rng.clone(), "obs": self._obs.clone(), "reward": self._reward.clone(),
+            "terminated": self._terminated.clone(), "truncated": self._truncated.clone(),
+            "context_ids": self._context_ids.copy(), "reset_counts": self._reset_counts.copy(),
+            "rr_offset": self._rr_offset.copy(),
+            "selector": {"context_id": getattr(sel, "context_id", None), "n_calls": getattr(sel, "n_calls", None)},
+            "seed": self._seed_value, "seeded": self._seeded, "has_reset": self._has_reset,
             "first_state": None if self._first_state is None else self._first_state.clone(),
             "first_obs": None if self._first_obs is None else self._first_obs.clone(),
+            "goal_state": goal,
         }
 
     def load_state_dict(self, sd: dict[str, Any]) -> None:
+        meta = sd.get("meta")
+        if meta is not None:
+            mine = {"kind": self.kind, "num_envs": self.num_envs, "global_num_envs": self.global_num_envs,
+                    "env_lo": self.env_lo, "dtype": self.dtype, "n_contexts": len(self._table)}
+            for k, v in mine.items():
+                assert meta.get(k) == v, f"state dict was saved from a different env ({k}: {meta.get(k)!r} != {v!r})"
+        for name, buf in (("state", self._state), ("elapsed", self._elapsed), ("sbt", self._sbt), ("rng", self._rng),
+                          ("obs", self._obs)):
+            t = sd[name]
+            assert tuple(t.shape) == tuple(buf.shape) and t.dtype == buf.dtype, \
+                f"state dict entry {name!r}: {tuple(t.shape)} {t.dtype}, expected {tuple(buf.shape)} {buf.dtype}"
+        if self._first_state is not None and sd.get("seed") is not None:
+            # Brax: the reset noise is keyed by (seed, global env id, episode counter). Re-key the handle FIRST
+            # (seeding zeroes the counters), then restore the counters with the rng buffer below.
+            _native.check(self._lib.carlb_env_seed(self._handle, int(sd["seed"]), self._stream()))
         self._state.copy_(sd["state"]); self._elapsed.copy_(sd["elapsed"]); self._sbt.copy_(sd["sbt"])
         self._rng.copy_(sd["rng"]); self._obs.copy_(sd["obs"])
+        for name, buf in (("reward", self._reward), ("terminated", self._terminated), ("truncated", self._truncated)):
+            if sd.get(name) is not None:
+                buf.copy_(sd[name])
         if self._first_state is not None and sd.get("first_state") is not None:
             self._first_state.copy_(sd["first_state"]); self._first_obs.copy_(sd["first_obs"])
         self._context_ids = np.asarray(sd["context_ids"], dtype=np.int64).copy()
+        if sd.get("reset_counts") is not None:
+            self._reset_counts = np.asarray(sd["reset_counts"], dtype=np.int64).copy()
+            self._rr_offset = np.asarray(sd["rr_offset"], dtype=np.int64).copy()
+        sel_sd = sd.get("selector") or {}
+        for k in ("context_id", "n_calls"):
+            if sel_sd.get(k) is not None and hasattr(self.context_selector, k):
+                setattr(self.context_selector, k, sel_sd[k])
+        if sd.get("goal_state") is not None:
+            self._goal_state = {k: (v.clone().to(self.device) if isinstance(v, torch.Tensor) else v)
+                                for k, v in sd["goal_state"].items()}
+            self._goal_strings = None
         self._refresh_context_view()
         self._update_context()
-        self._seeded = True
-        self._has_reset = True
+        self._seed_value = sd.get("seed", self._seed_value)
+        self._seeded = bool(sd.get("seeded", True))
+        self._has_reset = bool(sd.get("has_reset", True))
 
     # raw views for tests / learners
     @property

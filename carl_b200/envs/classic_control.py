@@ -50,7 +50,7 @@ class CARLCartPole(CARLGymnasiumEnv):
         }
 
     @classmethod
-    def kernel_params(cls, table, names, context_mode="reference"):
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
         # rows: gravity, masspole, length, force_mag, tau, total_mass, polemass_length, lo, hi
         g, mc, mp, ln, fm, tau, lo, hi = (table[:, names.index(k)] for k in (
             "gravity", "masscart", "masspole", "length", "force_mag", "tau", "initial_state_lower", "initial_state_upper"))
@@ -83,13 +83,17 @@ class CARLPendulum(CARLGymnasiumEnv):
         }
 
     @classmethod
-    def kernel_params(cls, table, names, context_mode="reference"):
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
         # `gravity` is a dead attribute on PendulumEnv (the live one is `g`): carl_pendulum.py:18-26
         g = table[:, names.index("g")]
         if context_mode == "applied":
-            # intended semantics: a context that varies `gravity` changes the physics
-            grav = table[:, names.index("gravity")]
-            g = np.where(grav != 8.0, grav, g)
+            # intended semantics: a context that SETS `gravity` changes the physics. `explicit[i, j]` says
+            # whether context i named feature j itself (a deliberate gravity=8.0 counts); without that
+            # information (bare tables) a value other than the default 8.0 is taken as set.
+            j = names.index("gravity")
+            grav = table[:, j]
+            chosen = explicit[:, j] if explicit is not None else grav != 8.0
+            g = np.where(chosen, grav, g)
         rest = cls._cols(table, names, ["m", "l", "dt", "initial_angle_max", "initial_velocity_max"])
         return np.concatenate([g[:, None], rest], axis=1)
 
@@ -119,7 +123,7 @@ class CARLAcrobot(CARLGymnasiumEnv):
         }
 
     @classmethod
-    def kernel_params(cls, table, names, context_mode="reference"):
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
         # LINK_LENGTH_2 is render-only in AcrobotEnv._dsdt
         return cls._cols(table, names, [
             "LINK_MASS_1", "LINK_MASS_2", "LINK_LENGTH_1", "LINK_COM_POS_1", "LINK_COM_POS_2", "LINK_MOI",
@@ -149,7 +153,7 @@ class CARLMountainCar(CARLGymnasiumEnv):
         }
 
     @classmethod
-    def kernel_params(cls, table, names, context_mode="reference"):
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
         return cls._cols(table, names, [
             "min_position", "max_position", "max_speed", "goal_position", "goal_velocity", "force", "gravity",
             "min_position_start", "max_position_start", "min_velocity_start", "max_velocity_start"])
@@ -176,7 +180,7 @@ class CARLMountainCarContinuous(CARLGymnasiumEnv):
         }
 
     @classmethod
-    def kernel_params(cls, table, names, context_mode="reference"):
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
         return cls._cols(table, names, [
             "min_position", "max_position", "max_speed", "goal_position", "goal_velocity", "power",
             "min_position_start", "max_position_start", "min_velocity_start", "max_velocity_start"])

@@ -4,9 +4,14 @@ The env instances are independent, so the path shards with no data-path collecti
 one the north star names: the gathered observation tensor. Two implementations:
 
 * ``ObsGather(mode="nccl")`` -- ``torch.distributed.all_gather_into_tensor`` (baseline).
-* ``ObsGather(mode="fused")`` -- the step kernel stores each obs row straight into every rank's
-  gathered buffer through P2P-mapped memory (CUDA IPC handles exchanged once); a step then only
-  needs a cross-rank barrier, not a separate collective launch.
+* ``ObsGather(mode="fused")`` -- the step / reset / rollout kernels store each obs row straight into
+  every rank's gathered buffer over NVLink (peer-mapped or NVLS-multicast symmetric memory) and
+  exchange per-rank push counts; no collective launch, no host synchronisation, CUDA-graph
+  capturable. ``pipelined=False``: when a launch has completed, the gathered tensor of ITS
+  observation is complete (the consumer that feeds obs k into step k+1). ``pipelined=True``: the
+  gathered tensor of the PREVIOUS launch's observation is complete -- the transfer of obs k
+  overlaps the physics of launch k+1 (``gather(lag=1)`` is then free, ``gather(lag=0)`` appends a
+  flush launch).
 """
 from __future__ import annotations
 
@@ -32,7 +37,8 @@ def shard_sizes(n_global: int, world_size: int) -> list[int]:
 class ObsGather:
     """All-gather of the per-rank observation shards into ``[N_global, D]`` on every rank."""
 
-    def __init__(self, env: Any, mode: str = "nccl", group: Any = None):
+    def __init__(self, env: Any, mode: str = "nccl", group: Any = None, pipelined: bool = False,
+                 symmetric: str = "auto"):
         import torch
         import torch.distributed as dist
 
@@ -51,8 +57,10 @@ class ObsGather:
         self._pending_buf = None
         self._pending_src = None
         self._alt = None
+        self.pipelined = bool(pipelined)
+        self.transport = "nccl"
         if mode == "fused":
-            self._setup_fused()
+            self._setup_fused(symmetric)
         elif mode != "nccl":
             raise ValueError(f"unknown gather mode {mode!r}")
 
@@ -111,11 +119,16 @@ class ObsGather:
                 off += sz
         return self.gathered
 
-    def _setup_fused(self):
-        """Create this rank's symmetric buffer, exchange the CUDA IPC handles, map every peer's
-        buffer and attach the gather to the env handle (its kernels then store obs rows to all
-        ranks over NVLink and publish completion flags)."""
+    def _setup_fused(self, symmetric: str = "auto"):
+        """Create this rank's symmetric buffer, map every peer's buffer and attach the gather to the env
+        handle (its kernels then push obs rows to all ranks over NVLink and publish push counts).
+
+        ``symmetric``: "torch" -- the block comes from ``torch.distributed._symmetric_memory`` (plumbing:
+        allocation + rendezvous), which also yields the NVLS multicast alias, so one ``multimem.st`` per
+        row reaches every rank; "ipc" -- a cudaMalloc block shared through CUDA IPC handles (one store
+        per rank and row); "auto" -- torch symmetric memory when every rank gets it, else IPC."""
         import ctypes
+        import os
 
         import torch
 
@@ -124,31 +137,76 @@ class ObsGather:
         env = self.env
         self._lib = _native.load()
         self._g = ctypes.c_void_p()
+        self._symm = None
         D = env._info.obs_dim
-        _native.check(self._lib.carlb_gather_create(env.device.index, env.rank, env.world_size, env.global_num_envs, D,
-                                                    ctypes.byref(self._g)))
-        handle = (ctypes.c_ubyte * 64)()
-        _native.check(self._lib.carlb_gather_export(self._g, handle))
-        mine = bytes(handle)
-        if env.world_size > 1:
-            handles = [None] * env.world_size
-            self.dist.all_gather_object(handles, mine, group=self.group)
-        else:
-            handles = [mine]
-        for r, h in enumerate(handles):
-            if r == env.rank:
-                continue
-            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-            _native.check(self._lib.carlb_gather_open(self._g, r, buf))
+        world = env.world_size
+        symmetric = os.environ.get("CARLB_GATHER_SYMMETRIC", symmetric)
+        use_symm = symmetric in ("auto", "torch") and world > 1
+        if use_symm:
+            ok, err = 1, None
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+
+                nbytes = int(self._lib.carlb_gather_bytes(env.global_num_envs, D))
+                block = symm_mem.empty(nbytes, dtype=torch.uint8, device=env.device)
+                block.zero_()
+                torch.cuda.synchronize(env.device)
+                hdl = symm_mem.rendezvous(block, self.group if self.group is not None else self.dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                mc = int(hdl.multicast_ptr)  # 0 when the fabric has no NVLS multicast
+                if os.environ.get("CARLB_GATHER_MULTICAST", "1") == "0":
+                    mc = 0
+                if len(ptrs) != world or any(p == 0 for p in ptrs):
+                    raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+            except Exception as e:  # pragma: no cover - depends on the box / driver
+                ok, err = 0, e
+            flag = torch.tensor([ok], device=env.device, dtype=torch.int32)
+            self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 1:
+                arr = (ctypes.c_void_p * world)(*ptrs)
+                _native.check(self._lib.carlb_gather_create_symmetric(env.device.index, env.rank, world, env.global_num_envs,
+                                                                      D, arr, ctypes.c_void_p(mc or None), ctypes.byref(self._g)))
+                self._symm = (block, hdl)  # keep the mapping alive
+                self.transport = "symmetric-memory multicast (multimem.st)" if mc else "symmetric-memory peer stores"
+            else:
+                if symmetric == "torch":
+                    raise RuntimeError(f"torch symmetric memory unavailable on some rank ({err})")
+                use_symm = False
+        if not use_symm:
+            _native.check(self._lib.carlb_gather_create(env.device.index, env.rank, world, env.global_num_envs, D,
+                                                        ctypes.byref(self._g)))
+            handle = (ctypes.c_ubyte * 64)()
+            _native.check(self._lib.carlb_gather_export(self._g, handle))
+            mine = bytes(handle)
+            if world > 1:
+                handles = [None] * world
+                self.dist.all_gather_object(handles, mine, group=self.group)
+            else:
+                handles = [mine]
+            for r, h in enumerate(handles):
+                if r == env.rank:
+                    continue
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                _native.check(self._lib.carlb_gather_open(self._g, r, buf))
+            self.transport = "cuda-ipc peer stores"
         _native.check(self._lib.carlb_gather_attach(self._g, env._handle))
-        # tensor views of the two slots of the local buffer (CUDA array interface on raw pointers)
+        _native.check(self._lib.carlb_gather_set_mode(self._g, 1 if self.pipelined else 0))
         slot_floats = (env.global_num_envs * D + 63) // 64 * 64
         torch.cuda.synchronize(env.device)
-        # slot addresses are only known through carlb_gather_wait; issue a probe after a dummy launch is
-        # not possible before any launch, so derive them from the first wait lazily
+        # tensor views of the slots of the local buffer, created lazily from the pointers carlb_gather_wait returns
         self._views = _SlotViews(env.device, env.global_num_envs, D, slot_floats)
-        if env.world_size > 1:
+        if world > 1:
             self.dist.barrier(group=self.group)
+
+    def resync(self):
+        """After replaying CUDA graphs that contain obs-producing launches: re-read the device-side push
+        counter (synchronises the current stream) so that ``gather()`` returns the right slot again."""
+        if self.mode == "fused":
+            import torch
+
+            from carl_b200 import _native
+
+            _native.check(self._lib.carlb_gather_resync(self._g, torch.cuda.current_stream(self.env.device).cuda_stream))
 
     def close(self):
         if self.mode == "fused" and getattr(self, "_g", None) is not None and self._g.value:
@@ -156,6 +214,7 @@ class ObsGather:
             import ctypes
 
             self._g = ctypes.c_void_p()
+            self._symm = None
 
 
 class _DevArray:

@@ -178,10 +178,6 @@ int carlb_env_rollout(carlb_env_t* env, int n_steps, uint64_t policy_seed, uint3
 int carlb_mixed_step(carlb_env_t* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,
                      void* stream);
 
-/* Fused cross-GPU observation gather: every obs row is also stored to
- * peer_obs[r] + (global_offset + i) * obs_dim (P2P-mapped gathered buffers of all ranks). */
-int carlb_env_set_peers(carlb_env_t* env, int n_peers, float* const* peer_obs);
-
 /* Brax: upload the packed system table (HOST float[n_floats]) that the host layer builds from the
  * body model -- the batched stand-in for `mjcf.load(asset)` + `sys.replace(...)`
  * (carl/envs/brax/carl_brax_env.py:271-292). Layout: carl_b200/envs/brax_system.py /
@@ -205,22 +201,43 @@ int carlb_brax_goal_step(carlb_env_t* env, int idx0, int idx1, double dt, double
                          const double* radius, double* reward, uint8_t* success, void* stream);
 
 /* ---- fused cross-GPU observation gather (the path's one exchange step) ----------
- * One symmetric buffer per rank, mapped into every other rank's process with CUDA IPC. Once a
- * gather is attached, every observation-producing launch of the handle (reset / step / rollout)
- * also stores each obs row into every rank's buffer over NVLink and publishes a completion flag;
- * carlb_gather_wait enqueues a one-warp kernel that waits for all ranks' flags and returns the
- * [n_global][obs_dim] gathered tensor of the latest launch. All ranks must issue the same sequence
- * of observation-producing launches. Not capturable into CUDA graphs (slot / flag value change per
- * launch). Replaces `VectorGymWrapper`'s batched obs return (carl/envs/brax/wrappers.py:136-146)
- * for a batch sharded over GPUs. */
+ * One symmetric buffer per rank -- four slots of [n_global][obs_dim] floats, a flag word per rank and a few
+ * control words -- mapped into every other rank's process (CUDA IPC, or symmetric memory the caller
+ * provides). Once a gather is attached, every observation-producing launch of the handle (reset / step /
+ * rollout) also stores ("pushes") its obs rows into every rank's buffer over NVLink and publishes its
+ * push count; slot and flag value come from a counter in DEVICE memory, so the launches can be captured
+ * into a CUDA graph and replayed. All ranks must issue the same sequence of observation-producing
+ * launches. Replaces `VectorGymWrapper`'s batched obs return (carl/envs/brax/wrappers.py:136-146) for a
+ * batch sharded over GPUs.
+ *
+ * CARLB_GATHER_SYNC (default): a launch pushes the rows it computes and its last CTA waits for every rank's
+ *   push of the same launch -- when launch k has completed, the gathered tensor of observation k is complete.
+ * CARLB_GATHER_PIPELINED: when launch k has completed, the gathered tensor of observation k-1 is complete;
+ *   classic step / rollout launches push the previous launch's rows from a dedicated warp per CTA while
+ *   they compute (the NVLink transfer, its fence and the flags overlap the physics), Brax launches push at
+ *   their end and wait one push behind. */
+#define CARLB_GATHER_SYNC 0
+#define CARLB_GATHER_PIPELINED 1
+int64_t carlb_gather_bytes(int64_t n_global, int obs_dim); /* size of one rank's symmetric block */
 int carlb_gather_create(int device, int rank, int world, int64_t n_global, int obs_dim, carlb_gather_t** out);
+/* Same, over memory the caller made symmetric (every block zeroed, carlb_gather_bytes() long, 16-byte
+ * aligned): bases[r] = rank r's block as mapped in THIS process (HOST array of DEVICE pointers);
+ * multicast_base = NVLS multicast alias of the blocks or NULL -- with it one `multimem.st` per row reaches
+ * every rank instead of one store per rank. */
+int carlb_gather_create_symmetric(int device, int rank, int world, int64_t n_global, int obs_dim, void* const* bases,
+                                  void* multicast_base, carlb_gather_t** out);
 int carlb_gather_export(carlb_gather_t* g, void* handle64 /* HOST, 64 bytes out */);
 int carlb_gather_open(carlb_gather_t* g, int peer_rank, const void* handle64 /* HOST, 64 bytes */);
-int carlb_gather_attach(carlb_gather_t* g, carlb_env_t* env);
-/* lag = 0: the gathered tensor of the latest observation-producing launch; lag = 1: of the one
- * before it (its slot stays intact until the launch after next) -- a pipelined consumer can enqueue
- * launch k+1 first and then wait for launch k, so the wait never stalls the stream. */
+int carlb_gather_attach(carlb_gather_t* g, carlb_env_t* env); /* one handle per gather */
+int carlb_gather_set_mode(carlb_gather_t* g, int mode);        /* CARLB_GATHER_*; between launches */
+/* The gathered tensor of the handle's latest observation (lag = 0) or of the one before it (lag = 1), valid
+ * for work enqueued on `stream` after this call. Whenever the mode already guarantees completeness nothing
+ * is launched; PIPELINED with lag = 0 appends a flush launch (push of the current observation + wait). A
+ * slot is overwritten by the fourth push after it. */
 int carlb_gather_wait(carlb_gather_t* g, int lag, void* stream, float** gathered /* HOST out: DEVICE pointer */);
+/* After replaying CUDA graphs that contain observation-producing launches: synchronises `stream` and
+ * re-reads the device-side push counter so that carlb_gather_wait returns the right slot again. */
+int carlb_gather_resync(carlb_gather_t* g, void* stream);
 int carlb_gather_destroy(carlb_gather_t* g);
 
 /* Counters of kernels launched through this library since load (bench `gpu_launches`). */

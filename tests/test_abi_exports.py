@@ -19,7 +19,7 @@ def declared_functions():
 def test_header_declares_expected_entry_points():
     names = declared_functions()
     for must in ("carlb_env_create", "carlb_env_bind", "carlb_env_seed", "carlb_env_reset", "carlb_env_step",
-                 "carlb_env_step_host", "carlb_env_rollout", "carlb_mixed_step", "carlb_env_set_peers",
+                 "carlb_env_step_host", "carlb_env_rollout", "carlb_mixed_step", "carlb_gather_create_symmetric",
                  "carlb_last_error", "carlb_query_env"):
         assert must in names
 
