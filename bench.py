@@ -240,6 +240,51 @@ def cgroup_cpu_quota():
         return None
 
 
+def try_real_reference(seconds: float = 2.0):
+    """B0: the REAL reference -- `carl.envs.CARLCartPole().step` over gymnasium -- if it can be
+    imported on this box (it cannot in this image: profiles/r02a_pip_install_attempt.txt). Returns a dict or the
+    import error."""
+    try:
+        import gymnasium  # noqa: F401
+        sys.path.insert(0, "/root/reference")
+        from carl.envs import CARLCartPole as RefCartPole
+    except Exception as e:  # the expected outcome here
+        return {"available": False, "why": f"{type(e).__name__}: {e}"}
+    env = RefCartPole()
+    env.reset(seed=0)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        _, _, te, tr, _ = env.step(env.action_space.sample())
+        if te or tr:
+            env.reset()
+        n += 1
+    return {"available": True, "value": n / (time.perf_counter() - t0), "unit": UNIT, "cores": 1}
+
+
+def _b2_worker(n_steps):
+    from oracle.classic import scalar_python_cartpole_steps_per_s
+
+    return scalar_python_cartpole_steps_per_s(n_steps)
+
+
+def python_scalar_all_cores(n_steps: int = 60_000):
+    """B2: the scalar-Python restatement of the reference's per-step cost shape (one env object,
+    math.sin/cos, TimeLimit, a fresh {"obs","context"} dict per step) in one process per host core."""
+    import multiprocessing as mp
+
+    procs = max(1, len(os.sched_getaffinity(0)))
+    quota = cgroup_cpu_quota()
+    if quota:
+        procs = max(1, min(procs, int(round(quota))))
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        rates = pool.map(_b2_worker, [n_steps] * procs)
+    wall = time.perf_counter() - t0
+    return {"value": float(sum(rates)), "unit": UNIT, "cores": procs, "per_core": float(np.mean(rates)),
+            "note": f"sum of the per-process rates of {procs} processes x {n_steps} steps (pool wall time {wall:.1f} s incl. spawn)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -308,9 +353,14 @@ def run_reference_arm(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "python_scalar_reference_shape": {
             "value": scalar_python_cartpole_steps_per_s(100_000), "unit": UNIT, "cores": 1,
-            "note": "one env, scalar float64 Python + TimeLimit + dict obs per step: the reference's actual cost shape"},
+            "note": "B1: one env, scalar float64 Python + TimeLimit + dict obs per step: the reference's actual cost shape"},
+        "real_reference_B0": try_real_reference(),
         "gpu_launches": 0,
     }
+    try:
+        out["python_scalar_all_cores_B2"] = python_scalar_all_cores()
+    except Exception as e:  # pragma: no cover - never allowed to break the line
+        out["python_scalar_all_cores_B2"] = {"error": repr(e)}
     print(json.dumps(out))
     return 0
 
@@ -602,8 +652,10 @@ def run_gpu_arm(args):
     E2E_ROWS = 4
     host_actions = hostmem.pinned_empty((E2E_ROWS, n_local), np.int32)
     host_actions[...] = np.random.default_rng(1).integers(0, 2, size=(E2E_ROWS, n_local), dtype=np.int32)
+    # the host-facing API hands every rank's results to its own process: no cross-GPU gather on this path
+    env_h = make_env() if distributed else env
     for w in range(max(5, min(W, 50))):
-        env.step(host_actions[w % E2E_ROWS])
+        env_h.step(host_actions[w % E2E_ROWS])
     e2e_passes = max(3, -(-args.e2e_calls // K))
     barrier()
     pass_s = []
@@ -613,7 +665,7 @@ def run_gpu_arm(args):
     for p_ in range(e2e_passes):
         t0 = time.perf_counter()
         for _ in range(K):
-            obs, rew, term, trunc, _i = env.step(host_actions[j % E2E_ROWS])
+            obs, rew, term, trunc, _i = env_h.step(host_actions[j % E2E_ROWS])
             acc += float(rew[0])  # the result is read on the host every step
             j += 1
         pass_s.append(time.perf_counter() - t0)
@@ -623,7 +675,7 @@ def run_gpu_arm(args):
     e2e_value = n_global * K_e2e / e2e_s
     h2d = n_local * 4
     d2h = n_local * (info.obs_dim * 4 + 4 + 1 + 1)
-    e2e_async = e2e_async_leg(env, host_actions, K, e2e_passes, dev, distributed, n_global) if hasattr(env, "step_async") else None
+    e2e_async = e2e_async_leg(env_h, host_actions, K, e2e_passes, dev, distributed, n_global)
 
     peak, peak_src = hbm_peak()
     extra = {}
@@ -669,12 +721,14 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "gpu_launches_host_counted": int(_native.launch_count() - launches0),
         "clocks": clock_info,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": K_e2e, "passes": e2e_passes, "pass_ms_median": float(np.median(pass_s)) * 1e3,
-                "api": "CARLCartPole.step(numpy int32 actions in page-locked memory) -> numpy obs/reward/terminated/"
-                       "truncated (carlb_env_step_host_checked: the step kernel reads the actions over PCIe, range-checks them "
-                       "itself -- undo log, rolled back if one is invalid -- and writes the results over PCIe)",
-                "ms_per_step": e2e_s / K_e2e * 1e3},
+        "e2e": None,
+        "e2e_sync": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                     "steps": K_e2e, "passes": e2e_passes, "pass_ms_median": float(np.median(pass_s)) * 1e3,
+                     "api": "CARLCartPole.step(numpy int32 actions in page-locked memory) -> numpy obs/reward/terminated/"
+                            "truncated, one synchronous call per step (carlb_env_step_host_checked: the step kernel reads the "
+                            "actions over PCIe, range-checks them itself -- undo log, rolled back if one is invalid -- writes the "
+                            "results over PCIe and stores a completion word the call polls)",
+                     "ms_per_step": e2e_s / K_e2e * 1e3},
         "roofline": {
             "kernel": "rollout_kernel<CARTPOLE,float> (fused T-step rollout, trajectory to HBM)",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -707,7 +761,15 @@ def run_gpu_arm(args):
         },
     }
     if e2e_async is not None:
-        out["e2e_async"] = e2e_async
+        # the headline end-to-end number: the same 65 536 envs per GPU stepped through the split-batch host API
+        out["e2e"] = dict(e2e_async, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                          api="CARLCartPole.step_async(numpy int32 actions of one half of the batch, page-locked) / "
+                              "step_wait(part) -> numpy obs/reward/terminated/truncated of that half, the two halves alternating "
+                              "(EnvPool-style split-batch stepping; carlb_env_step_host_begin / _end: in-kernel action check with "
+                              "undo log, results written over PCIe by the kernel, completion word polled by the host). Every step "
+                              "all envs advance once, all actions cross PCIe host->device and all results device->host")
+    else:
+        out["e2e"] = out["e2e_sync"]
     if gather_check is not None:
         out["gather_check"] = gather_check
     out.update(extra)
@@ -733,8 +795,45 @@ def committed_done_mask_counts():
         return None
 
 
-def e2e_async_leg(env, host_actions, K, passes, dev, distributed, n_global):
-    return None
+def e2e_async_leg(env, host_actions, K, passes, dev, distributed, n_global, parts=2):
+    """The split-batch host-buffer API (EnvPool send / recv, SB3 step_async / step_wait): the batch is stepped as
+    `parts` contiguous parts on their own streams; while the host reads part p's results and hands in its next
+    actions, the other part's results are crossing PCIe. One "step" = every part stepped once."""
+    import torch
+
+    env.async_parts = parts
+    rows = host_actions.shape[0]
+    bounds = [env.part_range(p) for p in range(parts)]
+    for w in range(10):
+        env.step_async(host_actions[w % rows])
+        env.step_wait()
+    if distributed:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    for p, (lo, hi) in enumerate(bounds):
+        env.step_async(host_actions[0, lo:hi], part=p)
+    acc = 0.0
+    pass_s = []
+    j = 0
+    t_begin = time.perf_counter()
+    for _ in range(passes):
+        t0 = time.perf_counter()
+        for _k in range(K):
+            row = host_actions[(j + 1) % rows]
+            for p, (lo, hi) in enumerate(bounds):
+                st, rew, term, trunc, _i = env.step_wait(part=p)
+                acc += float(rew[0])  # the part's result is read on the host every step
+                env.step_async(row[lo:hi], part=p)
+            j += 1
+        pass_s.append(time.perf_counter() - t0)
+    e2e_s = max_over_ranks(time.perf_counter() - t_begin, dev, distributed)
+    for p in range(parts):
+        env.step_wait(part=p)
+    steps = passes * K
+    return {"value": n_global * steps / e2e_s, "unit": UNIT, "steps": steps, "passes": passes, "parts": parts,
+            "ms_per_step": e2e_s / steps * 1e3, "pass_ms_median": float(np.median(pass_s)) * 1e3}
 
 
 def f64_leg(dev, names, table, rank, world, K, T, barrier, args, n_global):
@@ -842,6 +941,13 @@ def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
     ms = max_over_ranks(ms, dev, distributed)
     fused = n_global * T * reps / (ms * 1e-3)
     launch_ms = ms / reps
+    # the same train with the FMA-contracted build of the kernels (arithmetic="fma", carlb_brax_set_arithmetic)
+    _native.check(env._lib.carlb_brax_set_arithmetic(env._handle, 1))
+    for j in range(2):
+        launch()
+    ms_f, _, reps_f = timed_train(launch, 1, stream, barrier, min(args.min_gpu_seconds, 0.1), min_replays=5)
+    fused_fma = n_global * T * reps_f / (max_over_ranks(ms_f, dev, distributed) * 1e-3)
+    _native.check(env._lib.carlb_brax_set_arithmetic(env._handle, 0))
     # single-step API, device actions (+ the gather of every step's obs in SYNC mode with N > 1)
     if gather is not None:
         _native.check(env._lib.carlb_gather_set_mode(gather._g, 0))
@@ -889,6 +995,9 @@ def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
         "workload": f"CARLBraxAnt, 8192 sampled contexts per GPU (gravity/mass_torso/friction), context_mode=applied, "
                     f"uniform random policy, 10 spring substeps per env-step; {n_global} envs on {world} GPU(s), weak scaling",
         "value": fused, "unit": UNIT, "fused_steps_per_launch": T, "launches": reps, "ms_per_env_step_batch": launch_ms / T,
+        "value_fma": fused_fma,
+        "arithmetic": "value: strict (products and sums rounded separately; the parity mode); value_fma: FMA-contracted build "
+                      "(arithmetic='fma'; held to the float64 yardstick by tests/test_brax_parity_gpu.py)",
         "collective": (f"obs all-gather with every launch: fused ({transport}), pipelined" if distributed else "none"),
         "roofline": {"bound": "fp32-issue (HBM shown for reference)", "bytes_per_env_step": traj_bytes + step_bytes / T,
                      "achieved": (traj_bytes * T + step_bytes) * n / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",

@@ -27,8 +27,8 @@ KIND = {
 EXPORTS = [
     "carlb_abi_version", "carlb_last_error", "carlb_query_env", "carlb_env_create", "carlb_env_destroy",
     "carlb_env_bind", "carlb_env_configure", "carlb_env_seed", "carlb_env_reset", "carlb_env_step",
-    "carlb_env_step_host", "carlb_env_step_host_checked", "carlb_stage_actions", "carlb_env_rollout", "carlb_mixed_step",
-    "carlb_brax_set_system", "carlb_brax_reset_from_q", "carlb_brax_goal_step", "carlb_launch_count",
+    "carlb_env_step_host", "carlb_env_step_host_checked", "carlb_env_step_host_begin", "carlb_env_step_host_end", "carlb_stage_actions", "carlb_env_rollout", "carlb_mixed_step",
+    "carlb_brax_set_system", "carlb_brax_set_arithmetic", "carlb_brax_set_reset_rng", "carlb_brax_reset_from_q", "carlb_brax_goal_step", "carlb_launch_count",
     "carlb_gather_create", "carlb_gather_export", "carlb_gather_open", "carlb_gather_attach", "carlb_gather_wait",
     "carlb_gather_destroy", "carlb_gather_bytes", "carlb_gather_create_symmetric", "carlb_gather_set_mode", "carlb_gather_resync",
 ]
@@ -91,10 +91,15 @@ def load() -> ctypes.CDLL:
     lib.carlb_env_step_host.argtypes = [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.carlb_env_step_host_checked.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                                 c_void_p]
+    lib.carlb_env_step_host_begin.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                              c_void_p, c_void_p]
+    lib.carlb_env_step_host_end.argtypes = [c_void_p, c_int]
     lib.carlb_stage_actions.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_int]
     lib.carlb_env_rollout.argtypes = [c_void_p, c_int, c_uint64, c_uint32, c_void_p, c_int, POINTER(Traj), c_void_p]
     lib.carlb_mixed_step.argtypes = [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int), c_int, c_void_p]
     lib.carlb_brax_set_system.argtypes = [c_void_p, c_void_p, c_int, c_int]
+    lib.carlb_brax_set_arithmetic.argtypes = [c_void_p, c_int]
+    lib.carlb_brax_set_reset_rng.argtypes = [c_void_p, c_int, c_int64]
     lib.carlb_brax_reset_from_q.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.carlb_brax_goal_step.argtypes = [c_void_p, c_int, c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_void_p, c_void_p]

@@ -27,7 +27,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 UNITS = [
     ("abi.cu", []),
     ("classic.cu", ["-fmad=false"]),
-    ("brax.cu", [] if os.environ.get("CARLB_BRAX_FMAD") == "1" else ["-fmad=false"]),
+    ("brax.cu", ["-fmad=false"]),   # strict variant (parity mode)
+    ("brax_fma.cu", []),            # the same source with FMA contraction (carlb_brax_set_arithmetic)
     ("gather.cu", []),
 ]
 

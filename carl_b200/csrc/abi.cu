@@ -240,6 +240,7 @@ int carlb_env_destroy(carlb_env_t* env) {
   if (is_brax(env->kind)) brax_destroy(env);
   if (env->undo_block != nullptr) cudaFree(env->undo_block);
   if (env->bad_action_host != nullptr) cudaFreeHost(env->bad_action_host);
+  if (env->part_counters != nullptr) cudaFree(env->part_counters);
   delete env;
   return CARLB_OK;
 }
@@ -306,7 +307,9 @@ int carlb_env_step(carlb_env_t* env, const void* actions, int act_dtype, void* s
     return CARLB_ERR_INVALID;
   }
   CARLB_CUDA_CHECK(cudaSetDevice(env->device));
-  if (is_brax(env->kind)) return brax_step(env, actions, act_dtype, (cudaStream_t)stream);
+  if (is_brax(env->kind))
+    return env->brax_arithmetic == CARLB_BRAX_FMA ? brax_step_fma(env, actions, act_dtype, (cudaStream_t)stream)
+                                                  : brax_step(env, actions, act_dtype, (cudaStream_t)stream);
   return classic_step(env, actions, act_dtype, (cudaStream_t)stream);
 }
 
@@ -345,15 +348,18 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
                                        cudaMemcpyHostToDevice, st));
       act_src = env->bufs.act_staging;
     }
-    rc = is_brax(env->kind) ? brax_step(env, act_src, act_dtype, st, &hm) : classic_step(env, act_src, act_dtype, st, &hm);
+    rc = !is_brax(env->kind) ? classic_step(env, act_src, act_dtype, st, &hm)
+         : env->brax_arithmetic == CARLB_BRAX_FMA ? brax_step_fma(env, act_src, act_dtype, st, &hm)
+                                                  : brax_step(env, act_src, act_dtype, st, &hm);
     if (rc != CARLB_OK) return rc;
     CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
     return CARLB_OK;
   }
   CARLB_CUDA_CHECK(cudaMemcpyAsync(env->bufs.act_staging, actions_host, n * esz * (size_t)info.act_dim,
                                    cudaMemcpyHostToDevice, st));
-  rc = is_brax(env->kind) ? brax_step(env, env->bufs.act_staging, act_dtype, st)
-                          : classic_step(env, env->bufs.act_staging, act_dtype, st);
+  rc = !is_brax(env->kind) ? classic_step(env, env->bufs.act_staging, act_dtype, st)
+       : env->brax_arithmetic == CARLB_BRAX_FMA ? brax_step_fma(env, env->bufs.act_staging, act_dtype, st)
+                                                : brax_step(env, env->bufs.act_staging, act_dtype, st);
   if (rc != CARLB_OK) return rc;
   // One device->host copy when the caller laid obs | reward | terminated | truncated out back to
   // back on both sides (the Python host layer does): 4 copies -> 1 (each costs ~8 us of latency).
@@ -391,10 +397,18 @@ static int ensure_step_check(carlb_env* env, int n_actions, StepCheck* chk) {
                flag_b = ((n + 15) / 16) * 16, rng_b = 2 * n * 8;
   if (env->undo_block == nullptr) {
     CARLB_CUDA_CHECK(cudaMalloc(&env->undo_block, state_b + el_b + 2 * flag_b + rng_b));
-    CARLB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&env->bad_action_host), sizeof(int), cudaHostAllocMapped));
-    *env->bad_action_host = 0;
+    CARLB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&env->bad_action_host), 2 * CARLB_MAX_PARTS * sizeof(int),
+                                   cudaHostAllocMapped));
+    memset(env->bad_action_host, 0, 2 * CARLB_MAX_PARTS * sizeof(int));
+    CARLB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&env->part_counters), CARLB_MAX_PARTS * sizeof(unsigned int)));
+    CARLB_CUDA_CHECK(cudaMemset(env->part_counters, 0, CARLB_MAX_PARTS * sizeof(unsigned int)));
   }
   unsigned char* p = static_cast<unsigned char*>(env->undo_block);
+  chk->first = 0;
+  chk->count = env->n;
+  chk->done_word = nullptr;
+  chk->done_ticket = 0;
+  chk->part_counter = env->part_counters;
   chk->n_actions = n_actions;
   chk->bad_action = env->bad_action_host;
   chk->undo_state = p;
@@ -440,6 +454,18 @@ int carlb_env_step_host_checked(carlb_env_t* env, const void* actions_host, int 
     }
     return carlb_env_step_host(env, actions_host, act_dtype, obs_host, reward_host, terminated_host, truncated_host, stream);
   }
+  // No gather attached: the kernel stores a completion word into mapped host memory and the call polls it
+  // instead of synchronising the stream (CARLB_HOST_POLL=0 restores cudaStreamSynchronize for A/B runs).
+  static const bool poll = [] {
+    const char* e = getenv("CARLB_HOST_POLL");
+    return e == nullptr || e[0] != '0';
+  }();
+  if (poll && env->gather == nullptr && !env->part_pending[0]) {
+    rc = carlb_env_step_host_begin(env, 0, 1, actions_host, act_dtype, n_actions, obs_host, reward_host, terminated_host,
+                                   truncated_host, stream);
+    if (rc != CARLB_OK) return rc;
+    return carlb_env_step_host_end(env, 0);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   CARLB_CUDA_CHECK(cudaSetDevice(env->device));
   StepCheck chk;
@@ -456,6 +482,118 @@ int carlb_env_step_host_checked(carlb_env_t* env, const void* actions_host, int 
     if (rc != CARLB_OK) return rc;
     CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
     set_error("invalid action: values must lie in [0, %d) (env %d)", n_actions, bad - 1);
+    return CARLB_ERR_INVALID;
+  }
+  return CARLB_OK;
+}
+
+
+// ---- split-batch host step: begin (enqueue one part, no sync) / end (poll the completion word)
+static inline void part_range(int n, int part, int n_parts, int* first, int* count) {
+  const long long lo = (long long)n * part / n_parts, hi = (long long)n * (part + 1) / n_parts;
+  *first = (int)lo;
+  *count = (int)(hi - lo);
+}
+
+int carlb_env_step_host_begin(carlb_env_t* env, int part, int n_parts, const void* actions_host, int act_dtype, int n_actions,
+                              float* obs_host, float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                              void* stream) {
+  int rc = check_ready(env, "carlb_env_step_host_begin");
+  if (rc != CARLB_OK) return rc;
+  if (n_parts < 1 || n_parts > CARLB_MAX_PARTS || part < 0 || part >= n_parts || n_parts > env->n) {
+    set_error("carlb_env_step_host_begin: part %d of %d (at most %d parts, each at least one env)", part, n_parts, CARLB_MAX_PARTS);
+    return CARLB_ERR_INVALID;
+  }
+  if (!is_classic(env->kind) || env->gather != nullptr) {
+    set_error("carlb_env_step_host_begin: classic-control handles without a fused gather only");
+    return CARLB_ERR_INVALID;
+  }
+  if (actions_host == nullptr || !valid_act_dtype(env, act_dtype) || !obs_host || !reward_host || !terminated_host ||
+      !truncated_host) {
+    set_error("carlb_env_step_host_begin: null buffer or action dtype %d not valid for env kind %d", act_dtype, env->kind);
+    return CARLB_ERR_INVALID;
+  }
+  if (env->part_pending[part]) {
+    set_error("carlb_env_step_host_begin: part %d already has a step in flight (call carlb_env_step_host_end first)", part);
+    return CARLB_ERR_STATE;
+  }
+  const void* res[4] = {obs_host, reward_host, terminated_host, truncated_host};
+  for (int k = 0; k < 4; ++k) {
+    if (env->zc_verified[k] == res[k]) continue;
+    if (!is_mapped_host(res[k])) {
+      set_error("carlb_env_step_host_begin: result buffers must be page-locked (mapped) host memory");
+      return CARLB_ERR_INVALID;
+    }
+    env->zc_verified[k] = res[k];
+  }
+  if (!is_mapped_host(actions_host)) {
+    set_error("carlb_env_step_host_begin: the action array must be page-locked (mapped) host memory");
+    return CARLB_ERR_INVALID;
+  }
+  carlb_env_info_t info;
+  carlb_query_env(env->kind, &info);
+  cudaStream_t st = (cudaStream_t)stream;
+  CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+  StepCheck chk;
+  rc = ensure_step_check(env, info.act_discrete ? n_actions : 0, &chk);
+  if (rc != CARLB_OK) return rc;
+  part_range(env->n, part, n_parts, &chk.first, &chk.count);
+  chk.bad_action = env->bad_action_host + part;
+  chk.done_word = reinterpret_cast<unsigned int*>(env->bad_action_host) + CARLB_MAX_PARTS + part;
+  chk.done_ticket = ++env->part_ticket[part];
+  if (chk.done_ticket == 0) chk.done_ticket = ++env->part_ticket[part];  // 0 is the initial value of the word
+  chk.part_counter = env->part_counters + part;
+  HostMirrors hm{obs_host, reward_host, terminated_host, truncated_host};
+  // the kernel indexes the action array with the env's index in the handle: shift the part's pointer back by
+  // `first` elements (only the part's own rows are ever dereferenced)
+  const size_t esz = act_dtype == CARLB_ACT_I64 ? 8 : (act_dtype == CARLB_ACT_U8 ? 1 : 4);
+  const unsigned char* act_base = static_cast<const unsigned char*>(actions_host) - (size_t)chk.first * esz * (size_t)info.act_dim;
+  rc = classic_step_checked(env, act_base, act_dtype, st, &hm, chk);
+  if (rc != CARLB_OK) return rc;
+  env->part_pending[part] = true;
+  env->part_first[part] = chk.first;
+  env->part_count[part] = chk.count;
+  env->part_n_actions[part] = chk.n_actions;
+  env->part_stream[part] = st;
+  return CARLB_OK;
+}
+
+int carlb_env_step_host_end(carlb_env_t* env, int part) {
+  int rc = check_ready(env, "carlb_env_step_host_end");
+  if (rc != CARLB_OK) return rc;
+  if (part < 0 || part >= CARLB_MAX_PARTS || !env->part_pending[part]) {
+    set_error("carlb_env_step_host_end: part %d has no step in flight", part);
+    return CARLB_ERR_STATE;
+  }
+  volatile unsigned int* word = reinterpret_cast<volatile unsigned int*>(env->bad_action_host) + CARLB_MAX_PARTS + part;
+  const unsigned int ticket = env->part_ticket[part];
+  unsigned long long spins = 0;
+  while (*word != ticket) {
+    __builtin_ia32_pause();
+    if ((++spins & 0xFFFFFull) == 0) {  // every ~1M polls: has the stream failed?
+      const cudaError_t q = cudaStreamQuery(env->part_stream[part]);
+      if (q != cudaSuccess && q != cudaErrorNotReady) {
+        env->part_pending[part] = false;
+        set_error("carlb_env_step_host_end: the step of part %d failed: %s", part, cudaGetErrorString(q));
+        return CARLB_ERR_CUDA;
+      }
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  env->part_pending[part] = false;
+  const int bad = *reinterpret_cast<volatile int*>(env->bad_action_host + part);
+  if (bad != 0) {  // roll the part back: the reference's env is untouched when `action_space.contains` fails
+    env->bad_action_host[part] = 0;
+    StepCheck chk;
+    rc = ensure_step_check(env, env->part_n_actions[part], &chk);
+    if (rc != CARLB_OK) return rc;
+    chk.first = env->part_first[part];
+    chk.count = env->part_count[part];
+    CARLB_CUDA_CHECK(cudaSetDevice(env->device));
+    rc = classic_step_undo(env, env->part_stream[part], chk);
+    if (rc != CARLB_OK) return rc;
+    CARLB_CUDA_CHECK(cudaStreamSynchronize(env->part_stream[part]));
+    set_error("invalid action: values must lie in [0, %d) (env %d)", env->part_n_actions[part], bad - 1);
     return CARLB_ERR_INVALID;
   }
   return CARLB_OK;
@@ -497,7 +635,9 @@ int carlb_env_rollout(carlb_env_t* env, int n_steps, uint64_t policy_seed, uint3
   if (n_steps == 0) return CARLB_OK;  // nothing to do (and no observation produced: the fused gather must not count it)
   CARLB_CUDA_CHECK(cudaSetDevice(env->device));
   if (is_brax(env->kind))
-    return brax_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream);
+    return env->brax_arithmetic == CARLB_BRAX_FMA
+               ? brax_rollout_fma(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream)
+               : brax_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream);
   return classic_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, (cudaStream_t)stream);
 }
 
@@ -533,6 +673,23 @@ int carlb_brax_set_system(carlb_env_t* env, const float* table, int n_floats, in
     return CARLB_ERR_INVALID;
   }
   return brax_set_system(env, table, n_floats, stock_contact);
+}
+
+int carlb_brax_set_arithmetic(carlb_env_t* env, int arithmetic) {
+  if (env == nullptr || !is_brax(env->kind) || (arithmetic != CARLB_BRAX_STRICT && arithmetic != CARLB_BRAX_FMA)) {
+    set_error("carlb_brax_set_arithmetic: needs a Brax handle and CARLB_BRAX_STRICT / CARLB_BRAX_FMA");
+    return CARLB_ERR_INVALID;
+  }
+  env->brax_arithmetic = arithmetic;
+  return CARLB_OK;
+}
+
+int carlb_brax_set_reset_rng(carlb_env_t* env, int mode, int64_t n_global) {
+  if (env == nullptr || !is_brax(env->kind) || (mode != CARLB_RESET_PHILOX && mode != CARLB_RESET_JAX) || n_global < 1) {
+    set_error("carlb_brax_set_reset_rng: needs a Brax handle, CARLB_RESET_PHILOX / CARLB_RESET_JAX and n_global >= 1");
+    return CARLB_ERR_INVALID;
+  }
+  return brax_set_reset_rng(env, mode, (long long)n_global);
 }
 
 int carlb_brax_reset_from_q(carlb_env_t* env, const uint8_t* mask, const float* q, const float* qd, void* stream) {

@@ -20,7 +20,20 @@
 #include "engine.h"
 #include "physics_brax.h"
 
+// Two builds of this file go into libcarlb.so (carl_b200/build.py): the STRICT variant (-fmad=false: every
+// product and sum rounded separately, which is what reproduces the float32 restatement of the reference
+// arithmetic to ~1e-6 per env-step) and, through brax_fma.cu, the FMA variant (ptxas contracts a*b+c into FFMA,
+// as XLA does for the reference's own kernels: ~25 % fewer issued instructions, results at the float32 round-off
+// floor of the algorithm, not bit-comparable with the strict oracle). Each variant lives in its own inner
+// namespace so that its kernels are distinct symbols; carlb_brax_set_arithmetic selects per handle.
+#ifdef CARLB_BRAX_FMA_BUILD
+#define CARLB_BRAX_VARIANT fma_variant
+#else
+#define CARLB_BRAX_VARIANT strict_variant
+#endif
+
 namespace carlb {
+namespace CARLB_BRAX_VARIANT {
 using namespace brax;
 
 // Warps (= env instances) per CTA. 4 x 128-thread CTAs per SM is the default; for batches of several
@@ -41,6 +54,8 @@ struct BraxSeg {
   int act_dim;
   long long global_offset;
   uint64_t seed;
+  int reset_rng;     // CARLB_RESET_PHILOX / CARLB_RESET_JAX
+  uint32_t batch;    // JAX reset stream: size of the (global) batch the reference's VmapWrapper would split the key over
   const float* sys;  // BraxSys::table in global memory
   float* state;      // [n][state_words]
   const float* ctx;  // [n][n_ctx]  (AoS per env: one coalesced load + shuffle broadcast)
@@ -562,21 +577,45 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
       const float noise = sys[H_RESET_NOISE], qd_noise = sys[H_QD_NOISE];
       const bool hopper = sys[H_QD_UNIFORM] > 0.0f;  // Hopper / Walker2d / pendulum / reacher: qd ~ U(+-noise), else noise * N(0,1)
       const bool reacher = (int)sys[H_ENV] == ENV_REACHER;
-      if (lane < nq) {
-        w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
-                                      : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
-      }
-      if (lane < nqd) {
-        w.qd[lane] = (qd_in != nullptr) ? qd_in[(size_t)env * nqd + lane]
-                     : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -qd_noise, qd_noise)
-                                        : qd_noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
-      }
-      if (reacher && q_in == nullptr && lane >= 2 && lane < 4) {
-        // brax.envs.reacher._random_target: dist = 0.2 U, ang = 2 pi U; q[2:] = target, qd[2:] = 0
-        const float dist = 0.2f * reset_uniform(seg.seed, gid, episode, 128u, 0.0f, 1.0f);
-        const float ang = 6.283185307179586f * reset_uniform(seg.seed, gid, episode, 129u, 0.0f, 1.0f);
-        w.q[lane] = lane == 2 ? dist * cosf(ang) : dist * sinf(ang);
-        w.qd[lane] = 0.0f;
+      if (seg.reset_rng == CARLB_RESET_JAX && (q_in == nullptr || qd_in == nullptr)) {
+        // the reference's own stream: `rng, rng1, rng2 = jax.random.split(rng, 3)` on the key this env receives at
+        // its `episode`-th reset, q = init_q + uniform(rng1, (nq,), -noise, noise), qd = noise * normal(rng2, (nqd,))
+        // (Ant, Halfcheetah, InvertedDoublePendulum) or uniform(rng2, (nqd,), -noise, noise) (Hopper, Walker2d,
+        // InvertedPendulum, Reacher) -- brax 0.12.1 envs/*.py `reset`
+        const JaxKey ek = jax_env_reset_key(seg.seed, episode, seg.batch, (uint32_t)gid);
+        const JaxKey rng0 = jax_split(ek, 3u, 0u), rng1 = jax_split(ek, 3u, 1u), rng2 = jax_split(ek, 3u, 2u);
+        if (lane < nq && q_in == nullptr)
+          w.q[lane] = sys[OFF_INIT_Q + lane] + jax_uniform(rng1, (uint32_t)nq, (uint32_t)lane, -noise, noise);
+        if (lane < nqd && qd_in == nullptr)
+          w.qd[lane] = hopper ? jax_uniform(rng2, (uint32_t)nqd, (uint32_t)lane, -qd_noise, qd_noise)
+                              : qd_noise * jax_normal(rng2, (uint32_t)nqd, (uint32_t)lane);
+        if (reacher && q_in == nullptr && lane >= 2 && lane < 4) {
+          // brax.envs.reacher._random_target(rng): rng, rng1, rng2 = split(rng, 3); dist = 0.2 U(rng1); ang = 2 pi U(rng2)
+          const JaxKey t1 = jax_split(rng0, 3u, 1u), t2 = jax_split(rng0, 3u, 2u);
+          const float dist = 0.2f * jax_uniform(t1, 1u, 0u, 0.0f, 1.0f);
+          const float ang = 6.283185307179586f * jax_uniform(t2, 1u, 0u, 0.0f, 1.0f);
+          w.q[lane] = lane == 2 ? dist * cosf(ang) : dist * sinf(ang);
+          w.qd[lane] = 0.0f;
+        }
+        if (lane < nq && q_in != nullptr) w.q[lane] = q_in[(size_t)env * nq + lane];
+        if (lane < nqd && qd_in != nullptr) w.qd[lane] = qd_in[(size_t)env * nqd + lane];
+      } else {
+        if (lane < nq) {
+          w.q[lane] = (q_in != nullptr) ? q_in[(size_t)env * nq + lane]
+                                        : sys[OFF_INIT_Q + lane] + reset_uniform(seg.seed, gid, episode, (uint32_t)lane, -noise, noise);
+        }
+        if (lane < nqd) {
+          w.qd[lane] = (qd_in != nullptr) ? qd_in[(size_t)env * nqd + lane]
+                       : hopper           ? reset_uniform(seg.seed, gid, episode, 64u + (uint32_t)lane, -qd_noise, qd_noise)
+                                          : qd_noise * reset_normal(seg.seed, gid, episode, (uint32_t)lane);
+        }
+        if (reacher && q_in == nullptr && lane >= 2 && lane < 4) {
+          // brax.envs.reacher._random_target: dist = 0.2 U, ang = 2 pi U; q[2:] = target, qd[2:] = 0
+          const float dist = 0.2f * reset_uniform(seg.seed, gid, episode, 128u, 0.0f, 1.0f);
+          const float ang = 6.283185307179586f * reset_uniform(seg.seed, gid, episode, 129u, 0.0f, 1.0f);
+          w.q[lane] = lane == 2 ? dist * cosf(ang) : dist * sinf(ang);
+          w.qd[lane] = 0.0f;
+        }
       }
       __syncwarp();
       // forward kinematics down the tree (parents have smaller indices)
@@ -619,6 +658,8 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
 
 // ---------------------------------------------------------------------------- host side
 struct BraxHandle {
+  int reset_rng = CARLB_RESET_PHILOX;
+  uint32_t batch = 1;
   BraxSys* dev_sys = nullptr;
   float host_table[TABLE_FLOATS] = {};
   bool have_table = false;
@@ -726,6 +767,8 @@ static int make_brax_seg(const carlb_env* env, BraxSeg& s, const char* what, int
   s.act_dim = info.act_dim;
   s.global_offset = env->global_offset;
   s.seed = h->seed;
+  s.reset_rng = h->reset_rng;
+  s.batch = h->batch;
   s.sys = h->dev_sys->table;
   s.state = static_cast<float*>(env->bufs.state);
   s.ctx = static_cast<const float*>(env->bufs.ctx);
@@ -844,6 +887,13 @@ int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) {
   return CARLB_OK;
 }
 
+int brax_set_reset_rng(carlb_env* env, int mode, long long n_global) {
+  BraxHandle* h = static_cast<BraxHandle*>(env->brax_sys);
+  h->reset_rng = mode;
+  h->batch = (uint32_t)(n_global > 0 ? n_global : 1);
+  return CARLB_OK;
+}
+
 int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st) {
   BraxSeg seg;
   int rc = make_brax_seg(env, seg, "carlb_env_reset", GL_RESET);
@@ -888,4 +938,40 @@ int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32
   return CARLB_OK;
 }
 
+}  // namespace CARLB_BRAX_VARIANT
+
+// the entry points engine.h declares
+#ifndef CARLB_BRAX_FMA_BUILD
+int brax_query(int kind, carlb_env_info_t* out) { return strict_variant::brax_query(kind, out); }
+int brax_create(carlb_env* env) { return strict_variant::brax_create(env); }
+void brax_destroy(carlb_env* env) { strict_variant::brax_destroy(env); }
+int brax_seed(const carlb_env* env, uint64_t seed, cudaStream_t st) { return strict_variant::brax_seed(env, seed, st); }
+int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st) { return strict_variant::brax_reset(env, mask, st); }
+int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm) {
+  return strict_variant::brax_step(env, actions, act_dtype, st, hm);
+}
+int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                 int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
+  return strict_variant::brax_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, st);
+}
+int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_contact) {
+  return strict_variant::brax_set_system(env, table, n_floats, stock_contact);
+}
+int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st) {
+  return strict_variant::brax_reset_from(env, mask, q, qd, st);
+}
+int brax_goal_step(const carlb_env* env, int idx0, int idx1, double dt, double* position, const double* goal,
+                   const double* radius, double* reward, uint8_t* success, cudaStream_t st) {
+  return strict_variant::brax_goal_step(env, idx0, idx1, dt, position, goal, radius, reward, success, st);
+}
+int brax_set_reset_rng(carlb_env* env, int mode, long long n_global) { return strict_variant::brax_set_reset_rng(env, mode, n_global); }
+#else
+int brax_step_fma(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm) {
+  return fma_variant::brax_step(env, actions, act_dtype, st, hm);
+}
+int brax_rollout_fma(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st) {
+  return fma_variant::brax_rollout(env, n_steps, policy_seed, step_base, actions, act_dtype, traj, st);
+}
+#endif
 }  // namespace carlb

@@ -114,7 +114,7 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
     StateIO<T, Tr::S>::store(chk.undo_state, i, s);
     chk.undo_elapsed[i] = el;
     if (KIND == KIND_CARTPOLE) chk.undo_sbt[i] = sb;
-    if (Tr::DISCRETE && (unsigned)a.i >= (unsigned)chk.n_actions) {
+    if (Tr::DISCRETE && chk.n_actions > 0 && (unsigned)a.i >= (unsigned)chk.n_actions) {
       *reinterpret_cast<volatile int*>(chk.bad_action) = i + 1;  // any one offender is enough
       chk.undo_rng_flag[i] = 0;
       return;  // this env does not step; the host rolls the others back after the sync
@@ -228,9 +228,25 @@ template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock) step_checked_kernel(const __grid_constant__ Segment seg, const void* actions,
                                                               const __grid_constant__ StepCheck chk) {
   const unsigned int gseq = gather_begin(seg.gth);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < seg.n) step_one<KIND, T, true>(seg, actions, i, chk, gseq);
+  const int i = chk.first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < chk.first + chk.count) step_one<KIND, T, true>(seg, actions, i, chk, gseq);
   gather_epilogue_immediate(seg.gth, gseq);
+  if (chk.done_word != nullptr) {
+    // completion word in mapped host memory: the host polls it instead of synchronising the stream. CTAs
+    // arrive with a device-scope release; the last one fences at system scope (its fence is cumulative over
+    // every CTA's posted PCIe writes) and stores the ticket.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned int prev = atomicAdd(chk.part_counter, 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence();
+        *chk.part_counter = 0;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned int*>(chk.done_word) = chk.done_ticket;
+      }
+    }
+  }
 }
 
 // Roll a checked step back: state / elapsed / steps-beyond flag of every env, PCG64 state where it moved.
@@ -238,8 +254,8 @@ template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock) step_undo_kernel(const __grid_constant__ Segment seg,
                                                            const __grid_constant__ StepCheck chk) {
   typedef Traits<KIND> Tr;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= seg.n) return;
+  const int i = chk.first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= chk.first + chk.count) return;
   T s[Tr::S];
   StateIO<T, Tr::S>::load(chk.undo_state, i, s);
   StateIO<T, Tr::S>::store(seg.state, i, s);
@@ -572,7 +588,7 @@ int classic_step_checked(const carlb_env* env, const void* actions, int act_dtyp
     seg.host_truncated = hm->truncated;
   }
   CARLB_DISPATCH_KIND_T(env->kind, env->precision,
-                        (step_checked_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, actions, chk)));
+                        (step_checked_kernel<K_, T_><<<grid_for(chk.count), kBlock, 0, st>>>(seg, actions, chk)));
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;
@@ -580,10 +596,38 @@ int classic_step_checked(const carlb_env* env, const void* actions, int act_dtyp
 
 int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk) {
   Segment seg = make_segment(env, CARLB_ACT_I32);
-  CARLB_DISPATCH_KIND_T(env->kind, env->precision, (step_undo_kernel<K_, T_><<<grid_for(env->n), kBlock, 0, st>>>(seg, chk)));
+  CARLB_DISPATCH_KIND_T(env->kind, env->precision, (step_undo_kernel<K_, T_><<<grid_for(chk.count), kBlock, 0, st>>>(seg, chk)));
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;
+}
+
+// Compute threads per CTA of a rollout launch: the preferred size unless the grid would then need more than ONE
+// wave of resident CTAs -- a rollout is a long per-thread loop, a second (partial) wave doubles the launch. The
+// publisher warp of the deferred gather push makes the CTAs bigger, which can cost a resident CTA per SM (r02e:
+// 96-thread CTAs at 94 registers -> 6 per SM = 888 slots < 1 024 CTAs, 11.4 -> 19.2 us); twice the compute threads per
+// CTA then halve the grid.
+template <int KIND, typename T, bool REC>
+static void launch_rollout(const carlb_env* env, const Segment& seg, int preferred, int extra, int n_steps, uint64_t policy_seed,
+                           uint32_t step_base, const void* actions, const carlb_traj_t& tj, int refill, cudaStream_t st) {
+  static int n_sms[64] = {};
+  static int occ[2][3] = {};  // [extra != 0][block 64 / 128 / 32]: resident CTAs per SM of this instantiation
+  const int dev = env->device & 63;
+  if (n_sms[dev] == 0) cudaDeviceGetAttribute(&n_sms[dev], cudaDevAttrMultiProcessorCount, env->device);
+  int block = preferred;
+  const int candidates[2] = {preferred, 128};
+  for (int c = 0; c < 2; ++c) {
+    block = candidates[c] > preferred ? candidates[c] : preferred;
+    const int slot = block == 64 ? 0 : (block == 128 ? 1 : 2);
+    int& o = occ[extra != 0][slot];
+    if (o == 0 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, rollout_kernel<KIND, T, REC>, block + extra, 0) != cudaSuccess) {
+      cudaGetLastError();
+      o = 1;
+    }
+    if ((long long)(env->n + block - 1) / block <= (long long)o * n_sms[dev]) break;
+  }
+  const int grid = (env->n + block - 1) / block;
+  rollout_kernel<KIND, T, REC><<<grid, block + extra, 0, st>>>(seg, n_steps, policy_seed, step_base, actions, tj, refill);
 }
 
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
@@ -606,16 +650,16 @@ int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uin
     const int v = e != nullptr ? atoi(e) : 16;  // sweep on B200 (profiles/r01j_sweep.txt): 4 -> 0.332, 8 -> 0.286, 16 -> 0.278 ms
     return (v >= 1 && v <= 32) ? v : 16;
   }();
-  const int grid = (env->n + kRolloutBlock - 1) / kRolloutBlock;
   const bool rec = actions == nullptr && tj.obs != nullptr && tj.actions != nullptr && tj.reward != nullptr && tj.done != nullptr;
+  const int extra = block_with_publisher(seg, 0);  // 32 when the push is deferred to a publisher warp
   if (rec) {
     CARLB_DISPATCH_KIND_T(env->kind, env->precision,
-                          (rollout_kernel<K_, T_, true><<<grid, block_with_publisher(seg, kRolloutBlock), 0, st>>>(seg, n_steps, policy_seed, step_base,
-                                                                                        actions, tj, kRefillThreshold)));
+                          (launch_rollout<K_, T_, true>(env, seg, kRolloutBlock, extra, n_steps, policy_seed, step_base, actions,
+                                                        tj, kRefillThreshold, st)));
   } else {
     CARLB_DISPATCH_KIND_T(env->kind, env->precision,
-                          (rollout_kernel<K_, T_, false><<<grid, block_with_publisher(seg, kRolloutBlock), 0, st>>>(seg, n_steps, policy_seed, step_base,
-                                                                                         actions, tj, kRefillThreshold)));
+                          (launch_rollout<K_, T_, false>(env, seg, kRolloutBlock, extra, n_steps, policy_seed, step_base, actions,
+                                                         tj, kRefillThreshold, st)));
   }
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());

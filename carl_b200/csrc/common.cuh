@@ -32,6 +32,7 @@ struct GatherDev {
   int n_peers;                                // world size (0: no gather attached)
   int mode;                                   // GATHER_IMMEDIATE / GATHER_DEFERRED
   int wait_lag;                               // < 0: no in-kernel wait
+  int debug;                                  // CARLB_GATHER_DEBUG bit mask (A/B measurements only; breaks correctness)
   unsigned long long slot_floats;             // floats per slot
   float* peer_base[CARLB_MAX_PEERS];          // slot 0 of rank r's buffer (mapped here)
   unsigned int* peer_flags[CARLB_MAX_PEERS];  // MY flag word in rank r's buffer
@@ -52,20 +53,20 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
   return v;
 }
 
-// Push sequence number of this launch, identical in every thread of the CTA. One aligned barrier:
-// every thread of the CTA must call it (before anything divergent).
+// Push sequence number of this launch: every thread reads the device-side counter itself, first thing in the
+// kernel (no barrier: the load overlaps the thread's other prologue loads). All threads of the grid see the same
+// value because the counter only moves when the LAST CTA publishes, i.e. after every CTA has arrived, and a CTA
+// arrives only after all of its threads have passed this read.
 __device__ __forceinline__ unsigned int gather_begin(const GatherDev& g) {
-  __shared__ unsigned int sh_seq;
   if (g.n_peers <= 0) return 0u;
-  if (threadIdx.x == 0) sh_seq = ld_volatile_u32(g.ctrl + GCTRL_SEQ);
-  __syncthreads();
-  return sh_seq;
+  return ld_volatile_u32(g.ctrl + GCTRL_SEQ);
 }
 
 // Store one obs row (D floats, 16-byte aligned when D % 4 == 0) into slot `seq` of every rank.
 template <int D>
 __device__ __forceinline__ void gather_store_row(const GatherDev& g, unsigned int seq, size_t global_row, const float* o) {
   const size_t off = (size_t)(seq % kGatherSlots) * g.slot_floats + global_row * D;
+  if (g.debug & 4) return;
   if (g.mc_base != nullptr) {
     float* dst = g.mc_base + off;
     if (D % 4 == 0) {
@@ -116,17 +117,19 @@ __device__ __forceinline__ void gather_store_elem(const GatherDev& g, unsigned i
 // per CTA matters: system-scope fences of different SMs serialise (r02b: 1 024 of them cost ~12 us per launch).
 // Returns true in the thread that published.
 __device__ __forceinline__ bool gather_publish(const GatherDev& g, unsigned int seq, unsigned int n_ctas) {
-  __threadfence();
+  if (!(g.debug & 1)) __threadfence();
   const unsigned int prev = atomicAdd(g.ctrl + GCTRL_PUSH_COUNTER, 1u);
   if (prev != n_ctas - 1) return false;
   __threadfence();  // acquire side of the CTA arrivals
   g.ctrl[GCTRL_PUSH_COUNTER] = 0;
-  __threadfence_system();
+  // release pattern: ONE system-scope fence, then relaxed flag stores (a st.release per peer would repeat the
+  // MEMBAR.SYS for every rank)
+  if (!(g.debug & 8)) __threadfence_system();
   if (g.mc_flag != nullptr) {
-    asm volatile("multimem.st.release.sys.global.u32 [%0], %1;" ::"l"(g.mc_flag), "r"(seq + 1u) : "memory");
+    asm volatile("multimem.st.relaxed.sys.global.u32 [%0], %1;" ::"l"(g.mc_flag), "r"(seq + 1u) : "memory");
   } else {
     for (int r = 0; r < g.n_peers; ++r)
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(g.peer_flags[r]), "r"(seq + 1u) : "memory");
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(g.peer_flags[r]), "r"(seq + 1u) : "memory");
   }
   asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(g.ctrl + GCTRL_SEQ), "r"(seq + 1u) : "memory");
   return true;
@@ -134,7 +137,7 @@ __device__ __forceinline__ bool gather_publish(const GatherDev& g, unsigned int 
 
 // Spin (one thread) until every rank has published push `seq - wait_lag`.
 __device__ __forceinline__ void gather_wait_all(const GatherDev& g, unsigned int seq) {
-  if (g.wait_lag < 0) return;
+  if (g.wait_lag < 0 || (g.debug & 2)) return;
   const int target = (int)(seq + 1u) - g.wait_lag;
   if (target <= 0) return;
   for (int r = 0; r < g.n_peers; ++r)
@@ -206,7 +209,12 @@ struct Segment {
 // logs what it overwrites so that a step with an invalid action can be rolled back (the reference's
 // env is untouched when the assert fires).
 struct StepCheck {
-  int n_actions;           // valid discrete actions are [0, n_actions)
+  int first;               // this launch steps the envs [first, first + count) of the handle (a "part")
+  int count;
+  int n_actions;           // valid discrete actions are [0, n_actions); <= 0: no check
+  unsigned int* done_word;     // mapped host word: the last CTA stores done_ticket after a system fence (or null)
+  unsigned int done_ticket;
+  unsigned int* part_counter;  // device: CTA arrival counter of this part
   int* bad_action;         // mapped host word: 1 + index of an env whose action is invalid (0: none)
   void* undo_state;        // T[n][S] state before this step
   int32_t* undo_elapsed;   // [n]

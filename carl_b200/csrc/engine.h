@@ -18,13 +18,21 @@ struct carlb_env {
   long long global_offset = 0;
   bool bound = false;
   carlb_buffers_t bufs{};
+  int brax_arithmetic = CARLB_BRAX_STRICT;  // which build of the Brax step / rollout kernels this handle runs
   void* brax_sys = nullptr;  // BraxHandle: device copy of the per-handle Brax system table
   carlb_gather* gather = nullptr;  // fused cross-GPU obs gather (gather.cu), or null
   // host-buffer step with in-kernel action validation (carlb_env_step_host_checked): undo log (one device
   // block, allocated on first use -- never per step) and the mapped host word the kernel reports into
   void* undo_block = nullptr;
-  int* bad_action_host = nullptr;
+  unsigned int* part_counters = nullptr;  // device: CTA arrival counters of the completion words
+  int* bad_action_host = nullptr;   // mapped host block: [CARLB_MAX_PARTS] bad-action words, then [CARLB_MAX_PARTS] completion words
   const void* zc_verified[4] = {};  // result pointers already verified as mapped page-locked memory
+  // split-batch host step (carlb_env_step_host_begin / _end): per part, the ticket the kernel will store and
+  // what is needed to roll the part back
+  unsigned int part_ticket[CARLB_MAX_PARTS] = {};
+  bool part_pending[CARLB_MAX_PARTS] = {};
+  int part_first[CARLB_MAX_PARTS] = {}, part_count[CARLB_MAX_PARTS] = {}, part_n_actions[CARLB_MAX_PARTS] = {};
+  cudaStream_t part_stream[CARLB_MAX_PARTS] = {};
 };
 
 namespace carlb {
@@ -68,8 +76,13 @@ int brax_reset(const carlb_env* env, const uint8_t* mask, cudaStream_t st);
 int brax_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm = nullptr);
 int brax_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                  int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
+// brax_fma.cu: the FMA-contracted build of the step / rollout kernels
+int brax_step_fma(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm = nullptr);
+int brax_rollout_fma(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
+                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
 int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_contact);
 int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, const float* qd, cudaStream_t st);
+int brax_set_reset_rng(carlb_env* env, int mode, long long n_global);
 int brax_goal_step(const carlb_env* env, int idx0, int idx1, double dt, double* position, const double* goal,
                    const double* radius, double* reward, uint8_t* success, cudaStream_t st);
 

@@ -25,6 +25,7 @@
 // started launch p-2 and therefore finished consuming push p-4 (its consumer of push j is stream-ordered
 // before its launch j+2). Four slots cover every mode.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -71,6 +72,11 @@ static void fill_dev(const carlb_gather* g, GatherDev* d, int mode, int wait_lag
   d->n_peers = g->world;
   d->mode = mode;
   d->wait_lag = wait_lag;
+  static const int debug = [] {
+    const char* e = getenv("CARLB_GATHER_DEBUG");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  d->debug = debug;
   d->slot_floats = g->slot_floats;
   for (int r = 0; r < g->world; ++r) {
     d->peer_base[r] = reinterpret_cast<float*>(g->base[r]);

@@ -13,6 +13,7 @@
 // itself (PCG64 / SeedSequence) and the Random123 known-answer vectors (Philox).
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define CARLB_HD __host__ __device__ __forceinline__
@@ -190,6 +191,113 @@ CARLB_HD float u32_to_unit_float(uint32_t x) { return (float)(x >> 8) * (1.0f / 
 CARLB_HD Philox4 policy_draw(uint64_t seed, uint64_t env_id, uint32_t step) {
   return philox4x32_10((uint32_t)env_id, (uint32_t)(env_id >> 32), step, 0x43415242u /*"CARB"*/,
                        (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// ------------------------------------------------------------- JAX threefry2x32 PRNG
+// The Brax envs the reference steps draw their reset noise from JAX's default PRNG
+// (carl/envs/brax/wrappers.py:41,54-59,69-72,80-81 -> brax `Env.reset(rng)`): Threefry-2x32 (20 rounds,
+// Random123) behind `jax.random.PRNGKey / split / uniform / normal` (jax/_src/prng.py, jax/_src/random.py; the
+// original, non-"partitionable" bit layout). Pinned by the Random123 known answers and by the outputs JAX's own
+// documentation prints (tests/golden/jax_prng_known_answers.json).
+struct JaxKey {
+  uint32_t k0, k1;
+};
+
+CARLB_HD uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+
+CARLB_HD void threefry2x32(JaxKey key, uint32_t x0, uint32_t x1, uint32_t* y0, uint32_t* y1) {
+  const uint32_t ks[3] = {key.k0, key.k1, key.k0 ^ key.k1 ^ 0x1BD11BDAu};
+  const int R[2][4] = {{13, 15, 26, 6}, {17, 29, 16, 24}};
+  x0 += ks[0];
+  x1 += ks[1];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int i = 0; i < 5; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) {
+      x0 += x1;
+      x1 = rotl32(x1, R[i & 1][j]);
+      x1 ^= x0;
+    }
+    x0 += ks[(i + 1) % 3];
+    x1 += ks[(i + 2) % 3] + (uint32_t)(i + 1);
+  }
+  *y0 = x0;
+  *y1 = x1;
+}
+
+// jax.random.PRNGKey(seed): (high word, low word)
+CARLB_HD JaxKey jax_prng_key(uint64_t seed) { return JaxKey{(uint32_t)(seed >> 32), (uint32_t)seed}; }
+
+// Element `idx` of `threefry_random_bits(key, 32, (n,))`: the counts 0..n-1 (padded with one 0 when n is odd) are
+// cut into two halves that go through the block cipher pairwise; the outputs are concatenated.
+CARLB_HD uint32_t jax_random_bits(JaxKey key, uint32_t n, uint32_t idx) {
+  const uint32_t h = (n + 1u) / 2u;            // half length of the (padded) count array
+  const uint32_t j = idx < h ? idx : idx - h;  // position inside its half
+  const uint32_t c1 = (h + j < n) ? h + j : 0u;  // second half: counts h.. (the pad element is 0)
+  uint32_t y0, y1;
+  threefry2x32(key, j, c1, &y0, &y1);
+  return idx < h ? y0 : y1;
+}
+
+// jax.random.split(key, num)[which]
+CARLB_HD JaxKey jax_split(JaxKey key, uint32_t num, uint32_t which) {
+  return JaxKey{jax_random_bits(key, 2u * num, 2u * which), jax_random_bits(key, 2u * num, 2u * which + 1u)};
+}
+
+// jax.random.uniform(key, (n,), float32, minval, maxval)[idx]  (bit-exact)
+CARLB_HD float jax_uniform(JaxKey key, uint32_t n, uint32_t idx, float minval, float maxval) {
+  const uint32_t bits = jax_random_bits(key, n, idx);
+  const uint32_t fb = (bits >> 9) | 0x3F800000u;
+  float f;
+#if defined(__CUDA_ARCH__)
+  f = __uint_as_float(fb);
+  f = __fsub_rn(f, 1.0f);
+  const float v = __fadd_rn(__fmul_rn(f, __fsub_rn(maxval, minval)), minval);  // XLA: multiply, then add (no contraction across ops)
+#else
+  memcpy(&f, &fb, sizeof(f));
+  f = f - 1.0f;
+  volatile float prod = f * (maxval - minval);
+  const float v = prod + minval;
+#endif
+  return v > minval ? v : minval;
+}
+
+// XLA's float32 erf_inv (Giles' single-precision polynomial, xla/client/lib/math.cc ErfInv32)
+CARLB_HD float xla_erf_inv_f32(float x) {
+  float w = -log1pf(-x * x);
+  const bool lt = w < 5.0f;
+  w = lt ? w - 2.5f : sqrtf(w) - 3.0f;
+  float p = lt ? 2.81022636e-08f : -0.000200214257f;
+  p = (lt ? 3.43273939e-07f : 0.000100950558f) + p * w;
+  p = (lt ? -3.5233877e-06f : 0.00134934322f) + p * w;
+  p = (lt ? -4.39150654e-06f : -0.00367342844f) + p * w;
+  p = (lt ? 0.00021858087f : 0.00573950773f) + p * w;
+  p = (lt ? -0.00125372503f : -0.0076224613f) + p * w;
+  p = (lt ? -0.00417768164f : 0.00943887047f) + p * w;
+  p = (lt ? 0.246640727f : 1.00167406f) + p * w;
+  p = (lt ? 1.50140941f : 2.83297682f) + p * w;
+  return p * x;
+}
+
+// jax.random.normal(key, (n,), float32)[idx] = sqrt(2) * erf_inv(uniform(key, (n,), minval=nextafter(-1, 0), maxval=1)).
+// The uniform draw is bit-exact; log1p / the polynomial may differ from XLA's in the last ulp.
+CARLB_HD float jax_normal(JaxKey key, uint32_t n, uint32_t idx) {
+  const float lo = -0.99999994f;  // nextafter(-1, 0) in float32
+  return 1.41421356f * xla_erf_inv_f32(jax_uniform(key, n, idx, lo, 1.0f));
+}
+
+// The key `Env.reset` receives for env `env_index` of a batch of `batch` envs at the `n_resets`-th reset (0-based)
+// of the gym shell: the shell keeps key1 of `key1, key2 = split(key)` and hands key2 on at every reset
+// (wrappers.py:54-59,121-128); VmapWrapper.reset splits that over the batch (batch == 1: the unbatched shell).
+CARLB_HD JaxKey jax_env_reset_key(uint64_t seed, uint32_t n_resets, uint32_t batch, uint32_t env_index) {
+  JaxKey key = jax_prng_key(seed);
+  for (uint32_t r = 0; r < n_resets; ++r) key = jax_split(key, 2u, 0u);
+  const JaxKey key2 = jax_split(key, 2u, 1u);
+  return batch > 1u ? jax_split(key2, batch, env_index) : key2;
 }
 
 }  // namespace carlb

@@ -76,10 +76,25 @@ class CARLBraxEnv(CARLEnv):
 
     def __init__(self, env=None, batch_size: int | None = None, contexts=None, obs_context_features=None,
                  obs_context_as_dict: bool = True, context_selector=None, context_selector_kwargs=None,
-                 use_language_goals: bool = False, brax_tunables: dict | None = None, **kwargs):
+                 use_language_goals: bool = False, brax_tunables: dict | None = None, arithmetic: str = "strict",
+                 reset_rng: str = "jax", **kwargs):
         """``carl_brax_env.py:119-236``. ``batch_size`` is the reference's name for the number of
         batched env instances (``brax.envs.create(batch_size=...)``, :163-167); here every instance
         may carry its own context."""
+        if arithmetic not in ("strict", "fma"):
+            raise ValueError(f"arithmetic must be 'strict' or 'fma', got {arithmetic!r}")
+        # "strict": products and sums rounded separately (reproduces the float32 restatement of the reference
+        # arithmetic to ~1e-6 per env-step: the parity mode). "fma": the same kernels built with FMA contraction,
+        # as XLA compiles the reference's own -- faster, results at the float32 round-off floor of the algorithm.
+        self.arithmetic = arithmetic
+        if reset_rng not in ("jax", "philox"):
+            raise ValueError(f"reset_rng must be 'jax' or 'philox', got {reset_rng!r}")
+        # "jax": the reference's own reset-noise stream (JAX threefry2x32 keys consumed as wrappers.py / brax do:
+        # PRNGKey(seed), `key1, key2 = split(key)` per reset, `split(key2, num_envs)[i]`, `split(rng, 3)`, uniform /
+        # normal). Like the reference, an unseeded env draws from PRNGKey(0) (wrappers.py:41 `self.seed(0)`); unlike
+        # it (SURVEY App. E B5: `reset(seed=...)` is ignored there), an explicit seed re-keys the stream.
+        # "philox": one Philox block per (seed, env, reset, index) -- the throughput-mode stream of round 1.
+        self.reset_rng = reset_rng
         if batch_size is not None and batch_size != 1 and "num_envs" not in kwargs:
             kwargs["num_envs"] = int(batch_size)
         self.use_language_goals = use_language_goals
@@ -114,6 +129,9 @@ class CARLBraxEnv(CARLEnv):
         self._sys_table_host = t
         _native.check(self._lib.carlb_brax_set_system(
             self._handle, t.ctypes.data_as(ctypes.c_void_p), int(t.size), 1 if self.context_mode == "reference" else 0))
+        _native.check(self._lib.carlb_brax_set_arithmetic(self._handle, 1 if self.arithmetic == "fma" else 0))
+        _native.check(self._lib.carlb_brax_set_reset_rng(self._handle, 1 if self.reset_rng == "jax" else 0,
+                                                         self.global_num_envs))
 
     # ------------------------------------------------------------------ goal wrappers
     def _goal_reset(self, device_like, mask=None):
@@ -160,6 +178,8 @@ class CARLBraxEnv(CARLEnv):
         return self._goal_strings
 
     def reset(self, *, seed=None, options=None, mask=None):
+        if seed is None and not self._seeded and self.reset_rng == "jax":
+            seed = 0  # the reference's shells are keyed with PRNGKey(0) at construction (wrappers.py:41,80-81)
         state, info = super().reset(seed=seed, options=options, mask=mask)
         if self._goal_active:
             mask_np = None

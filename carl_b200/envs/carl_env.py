@@ -24,7 +24,9 @@ from __future__ import annotations
 
 import abc
 import ctypes
+import functools
 import inspect
+import os
 from typing import Any
 
 import numpy as np
@@ -44,6 +46,27 @@ _NP_ACT = {
     np.dtype(np.float32): _native.ACT_F32,
 }
 _UNSIGNED = {1: np.uint8, 4: np.uint32, 8: np.uint64}
+
+
+# NVTX ranges around reset / step / rollout for nsys / ncu timelines (SURVEY §5 "tracing"): CARLB_NVTX=1.
+# Off by default: a range push / pop pair costs ~1 us of host time per call.
+_NVTX = os.environ.get("CARLB_NVTX", "0") == "1"
+
+
+def _nvtx(name):
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        @functools.wraps(fn)
+        def wrapped(self, *a, **k):
+            torch.cuda.nvtx.range_push(f"carlb.{self.kind}.{name}")
+            try:
+                return fn(self, *a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
 
 
 def _ptr(t: torch.Tensor | None) -> int | None:
@@ -207,6 +230,9 @@ class CARLEnv(abc.ABC):
         self._has_reset = False
         self._validate_actions = bool(validate_actions)
         self._host_io = None
+        self._async_parts = min(2, self.num_envs)
+        self._async_pending = [False] * 8
+        self._async_cache = None
 
     # ------------------------------------------------------------------ contexts
     @property
@@ -481,6 +507,7 @@ class CARLEnv(abc.ABC):
         return changed
 
     # ------------------------------------------------------------- reset / step
+    @_nvtx("reset")
     def reset(self, *, seed: int | None = None, options: dict[str, Any] | None = None,
               mask: np.ndarray | torch.Tensor | None = None):
         """``carl_env.py:245-274``: select contexts, re-inject those that changed, reset, dict obs.
@@ -536,6 +563,7 @@ class CARLEnv(abc.ABC):
         ok = shape in ((n_expected,), (n_expected, a)) if a == 1 else shape == (n_expected, a)
         assert ok, f"actions must have shape ({n_expected}, {a}), got {shape}"
 
+    @_nvtx("step")
     def step(self, action: Any):
         """``carl_env.py:321-342`` batched. torch CUDA actions -> device results;
         numpy / list actions -> host (numpy) results through pinned buffers."""
@@ -612,6 +640,111 @@ class CARLEnv(abc.ABC):
         state = {"obs": io["np_obs"], "context": self._context_obs_host()}
         return state, io["np_reward"], io["np_term"], io["np_trunc"], {"context_id": self.context_id}
 
+    # ------------------------------------------------- split-batch (EnvPool-style) host stepping
+    @property
+    def async_parts(self) -> int:
+        """Number of contiguous parts ``step_async`` / ``step_wait`` cut the batch into (default 2)."""
+        return self._async_parts
+
+    @async_parts.setter
+    def async_parts(self, k: int) -> None:
+        if any(self._async_pending):
+            raise RuntimeError("async_parts cannot change while a step is in flight")
+        k = int(k)
+        if not (1 <= k <= 8 and k <= self.num_envs):
+            raise ValueError("async_parts must lie in [1, min(8, num_envs)]")
+        self._async_parts = k
+        self._async_cache = None
+
+    def part_range(self, part: int) -> tuple[int, int]:
+        """``[lo, hi)`` of part ``part`` among this object's env instances."""
+        k = self._async_parts
+        return self.num_envs * part // k, self.num_envs * (part + 1) // k
+
+    def _async_state(self):
+        if self._async_cache is None:
+            io = self._ensure_host_io()
+            k = self._async_parts
+            bounds = [self.part_range(p) for p in range(k)]
+            self._async_cache = dict(
+                streams=[torch.cuda.Stream(self.device) for _ in range(k)], bounds=bounds,
+                views=[(io["np_obs"][lo:hi], io["np_reward"][lo:hi], io["np_term"][lo:hi], io["np_trunc"][lo:hi])
+                       for lo, hi in bounds],
+                ctx=[None] * k)
+        return self._async_cache
+
+    def step_async(self, action: Any, part: int | None = None) -> None:
+        """Split-batch stepping with host buffers (EnvPool ``send`` / SB3 ``VecEnv.step_async``): enqueue the step
+        of one part (``action`` = that part's actions) or, with ``part=None``, of every part (``action`` = the whole
+        batch) and return at once. ``step_wait(part)`` hands back the part's results; while the host consumes them
+        and computes the part's next actions, the other parts' results are crossing PCIe. Classic-control envs."""
+        if not self._has_reset:
+            raise RuntimeError("Cannot call env.step_async() before calling env.reset()")
+        st = self._async_state()
+        io = self._host_io
+        if part is None:
+            a = np.asarray(action)
+            self._check_actions(self.num_envs, tuple(a.shape))
+            flat = a.reshape(self.num_envs, -1)
+            for p_, (lo, hi) in enumerate(st["bounds"]):
+                self.step_async(flat[lo:hi].reshape((hi - lo,) + tuple(a.shape[1:])), part=p_)
+            return
+        lo, hi = st["bounds"][part]
+        a = np.asarray(action)
+        self._check_actions(hi - lo, tuple(a.shape))
+        if self._info.act_discrete:
+            if a.dtype not in _NP_ACT or a.dtype == np.float32:
+                a = a.astype(np.int64)
+        elif a.dtype != np.float32:
+            a = a.astype(np.float32)
+        flat = np.ascontiguousarray(a).reshape(-1)
+        n_act = self._info.n_actions if (self._validate_actions and self._info.act_discrete) else 0
+        src = flat.ctypes.data
+        if not hostmem.is_pinned(src, flat.nbytes):
+            # pageable actions: one native pass copies them into the part's slice of the page-locked staging block
+            # (and range-checks them; the kernel checks again, which costs nothing)
+            adim = max(1, self._info.act_dim)
+            dst = io["staged"][a.dtype][lo * adim:hi * adim]
+            if self._lib.carlb_stage_actions(dst.ctypes.data, src, flat.size, _NP_ACT[a.dtype], n_act) != 0:
+                raise AssertionError(_native.last_error())
+            src = dst.ctypes.data
+        p = io["ptrs"]
+        rc = self._lib.carlb_env_step_host_begin(self._handle, part, self._async_parts, src, _NP_ACT[a.dtype], n_act,
+                                                 p[1], p[2], p[3], p[4], st["streams"][part].cuda_stream)
+        _native.check(rc)
+        self._async_pending[part] = True
+
+    def step_wait(self, part: int | None = None):
+        """Results of the step ``step_async`` enqueued for ``part`` (views of the page-locked result arrays
+        restricted to the part's envs) -- or, with ``part=None``, of the whole batch once every part has landed."""
+        st = self._async_state()
+        parts = range(self._async_parts) if part is None else [part]
+        for p_ in parts:
+            if not self._async_pending[p_]:
+                raise RuntimeError(f"step_wait: part {p_} has no step in flight")
+            rc = self._lib.carlb_env_step_host_end(self._handle, p_)
+            self._async_pending[p_] = False
+            if rc != 0:
+                msg = _native.last_error()
+                if msg.startswith("invalid action"):
+                    raise AssertionError(msg)
+                _native.check(rc)
+        io = self._host_io
+        if part is None:
+            state = {"obs": io["np_obs"], "context": self._context_obs_host()}
+            return state, io["np_reward"], io["np_term"], io["np_trunc"], {"context_id": self.context_id}
+        lo, hi = st["bounds"][part]
+        if st["ctx"][part] is None:
+            full = self._context_obs_host()
+            if isinstance(full, dict):
+                st["ctx"][part] = full if self.num_envs == 1 else {k: v[lo:hi] for k, v in full.items()}
+            else:
+                st["ctx"][part] = full[lo:hi]
+        obs, rew, term, trunc = st["views"][part]
+        ids = self.context_id
+        return ({"obs": obs, "context": st["ctx"][part]}, rew, term, trunc,
+                {"context_id": ids if np.isscalar(ids) else ids[lo:hi]})
+
     def _context_obs_host(self):
         if self._ctx_obs_host_cache is None:  # contexts only change at reset / context_id assignment
             ids = self._context_ids
@@ -627,6 +760,7 @@ class CARLEnv(abc.ABC):
         return self._ctx_obs_host_cache
 
     # ----------------------------------------------------------- fused rollout
+    @_nvtx("rollout")
     def rollout(self, n_steps: int, policy_seed: int = 0, step_base: int = 0, actions: torch.Tensor | None = None,
                 record: bool = False):
         """Advance every env ``n_steps`` steps in ONE launch (state stays in registers).

@@ -26,6 +26,7 @@ extern "C" {
 #define CARLB_ABI_VERSION 1
 #define CARLB_MAX_PEERS 8
 #define CARLB_MAX_MIXED 8
+#define CARLB_MAX_PARTS 8
 
 /* error codes */
 #define CARLB_OK 0
@@ -161,6 +162,21 @@ int carlb_env_step_host(carlb_env_t* env, const void* actions_host, int act_dtyp
 int carlb_env_step_host_checked(carlb_env_t* env, const void* actions_host, int act_dtype, int n_actions, float* obs_host,
                                 float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host, void* stream);
 
+/* Split-batch stepping with HOST buffers (EnvPool-style send / recv; SB3's VecEnv step_async / step_wait):
+ * the handle's envs are cut into n_parts contiguous parts, part p = envs [p*n/n_parts, (p+1)*n/n_parts).
+ * _begin enqueues the step of ONE part on `stream` and returns at once. actions_host holds the PART's actions
+ * (element 0 belongs to the part's first env); the result pointers are the FULL page-locked arrays (obs[n][D],
+ * reward[n], ...), of which the kernel writes only the part's rows. The kernel reads the actions and writes the
+ * results over PCIe itself and finally stores a completion word the host can poll;
+ * _end waits for that word (no stream synchronisation) and, if an action of the part was invalid, rolls the
+ * part back and returns CARLB_ERR_INVALID ("invalid action ..."). While the host consumes part p and prepares
+ * its next actions, the other parts' results are crossing PCIe. Classic-control handles without a fused gather;
+ * one step per part in flight; use a different stream per part. n_actions as in carlb_env_step_host_checked. */
+int carlb_env_step_host_begin(carlb_env_t* env, int part, int n_parts, const void* actions_host, int act_dtype, int n_actions,
+                              float* obs_host, float* reward_host, uint8_t* terminated_host, uint8_t* truncated_host,
+                              void* stream);
+int carlb_env_step_host_end(carlb_env_t* env, int part);
+
 /* Host helper for the call above: copy a caller's (pageable) action array into the page-locked staging
  * block in one pass and, for discrete action dtypes with n_actions > 0, range-check it like the
  * `assert self.action_space.contains(action)` of the gymnasium envs the reference steps
@@ -184,6 +200,25 @@ int carlb_mixed_step(carlb_env_t* const* envs, const void* const* actions, const
  * carl_b200/csrc/physics_brax.h. stock_contact != 0 keeps the per-geom stock friction/elasticity
  * (context_mode="reference", where the reference's context never reaches the physics). */
 int carlb_brax_set_system(carlb_env_t* env, const float* table, int n_floats, int stock_contact);
+
+/* Brax arithmetic of the step / rollout kernels of a handle. CARLB_BRAX_STRICT (default): products and sums
+ * rounded separately, reproduces the float32 restatement of the reference arithmetic to ~1e-6 per env-step (the
+ * parity mode). CARLB_BRAX_FMA: a*b+c contracted into fused multiply-adds, as XLA does in the reference's own
+ * compiled kernels -- fewer issued instructions, results at the float32 round-off floor of the algorithm against
+ * a float64 evaluation (tests/test_brax_parity_gpu.py states the tolerance). */
+#define CARLB_BRAX_STRICT 0
+#define CARLB_BRAX_FMA 1
+int carlb_brax_set_arithmetic(carlb_env_t* env, int arithmetic);
+
+/* Brax reset-noise stream. CARLB_RESET_PHILOX (default): one Philox4x32-10 block per (seed, global env id, reset
+ * count, index) -- invariant to sharding, not the reference's stream. CARLB_RESET_JAX: the reference's own stream --
+ * JAX threefry2x32 keys exactly as carl/envs/brax/wrappers.py:41,54-59,69-72,80-81 and brax's VmapWrapper /
+ * `Env.reset` consume them (PRNGKey(seed); per reset `key1, key2 = split(key)`; `split(key2, n_global)[env]`;
+ * `rng, rng1, rng2 = split(rng, 3)`; uniform / normal draws): uniform draws bit-exact, normal draws to ~1e-6
+ * (erf_inv). n_global = size of the whole batch (the reference's `batch_size`; 1 = the unbatched shell). */
+#define CARLB_RESET_PHILOX 0
+#define CARLB_RESET_JAX 1
+int carlb_brax_set_reset_rng(carlb_env_t* env, int mode, int64_t n_global);
 
 /* Brax parity-mode reset: `pipeline_init(q, qd)` (forward kinematics) from caller-supplied
  * generalized coordinates q[n][n_q], qd[n][n_qd] (DEVICE) instead of the noise draws of

@@ -152,3 +152,26 @@ void hc_policy_sequence(uint64_t seed, uint64_t env_id, const uint32_t* steps, i
 }
 
 }  // extern "C"
+
+// ---- JAX threefry PRNG (rng.h) compiled by g++: checked against oracle/jax_prng.py and the published known answers
+extern "C" {
+void hc_threefry2x32(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t out[2]) {
+  carlb::threefry2x32(carlb::JaxKey{k0, k1}, x0, x1, &out[0], &out[1]);
+}
+void hc_jax_split(uint32_t k0, uint32_t k1, uint32_t num, uint32_t* out /* [num][2] */) {
+  for (uint32_t i = 0; i < num; ++i) {
+    const carlb::JaxKey k = carlb::jax_split(carlb::JaxKey{k0, k1}, num, i);
+    out[2 * i] = k.k0; out[2 * i + 1] = k.k1;
+  }
+}
+void hc_jax_uniform(uint32_t k0, uint32_t k1, uint32_t n, float lo, float hi, float* out) {
+  for (uint32_t i = 0; i < n; ++i) out[i] = carlb::jax_uniform(carlb::JaxKey{k0, k1}, n, i, lo, hi);
+}
+void hc_jax_normal(uint32_t k0, uint32_t k1, uint32_t n, float* out) {
+  for (uint32_t i = 0; i < n; ++i) out[i] = carlb::jax_normal(carlb::JaxKey{k0, k1}, n, i);
+}
+void hc_jax_env_reset_key(uint64_t seed, uint32_t n_resets, uint32_t batch, uint32_t env_index, uint32_t out[2]) {
+  const carlb::JaxKey k = carlb::jax_env_reset_key(seed, n_resets, batch, env_index);
+  out[0] = k.k0; out[1] = k.k1;
+}
+}  // extern "C"

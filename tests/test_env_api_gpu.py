@@ -153,6 +153,85 @@ def test_checkpoint_roundtrip():
     assert torch.equal(t1["obs"], t2["obs"]) and torch.equal(t1["done"], t2["done"])
 
 
+def test_checkpoint_resume_with_fewer_contexts_than_envs_and_selection_state():
+    """round-robin selection state (per-env reset counters, the selector's context_id / n_calls) is
+    part of the checkpoint -- with M contexts != N envs an uninterrupted run and a resumed one must keep selecting
+    the same contexts at the next resets."""
+    from carl_b200.envs import CARLCartPole
+
+    ctxs = {k: {"gravity": 5.0 + k, "length": 0.3 + 0.1 * k} for k in range(5)}   # M = 5 contexts
+    env = CARLCartPole(contexts=ctxs, num_envs=12, autoreset=False)               # N = 12 envs
+    env.reset(seed=4)
+    env.reset()
+    env.step(np.ones(12, dtype=np.int64))
+    sd = env.state_dict()
+    env.reset()
+    ids_a, n_calls_a = env.context_id.copy(), env.context_selector.n_calls
+    st_a = env.state.clone()
+    env2 = CARLCartPole(contexts=ctxs, num_envs=12, autoreset=False)
+    env2.load_state_dict(sd)
+    env2.reset()
+    np.testing.assert_array_equal(env2.context_id, ids_a)
+    assert env2.context_selector.n_calls == n_calls_a
+    assert torch.equal(env2.state, st_a)
+    with pytest.raises(AssertionError, match="different env"):
+        CARLCartPole(contexts=ctxs, num_envs=13).load_state_dict(sd)
+
+
+def test_checkpoint_resume_brax_reset_stream_and_goal_state():
+    """A resumed Brax env draws the same reset noise as the uninterrupted one (seed + per-env reset counters are
+    restored) and keeps the goal wrapper's dead-reckoned positions."""
+    from carl_b200.envs import CARLBraxAnt
+
+    ctxs = {k: {"target_direction": d, "target_distance": 5.0 + k} for k, d in enumerate([1, 12, 3, 34])}
+    env = CARLBraxAnt(contexts=ctxs, num_envs=4)
+    assert env._goal_active
+    env.reset(seed=3)
+    a = torch.rand(4, 8, device="cuda") * 2 - 1
+    for _ in range(3):
+        env.step(a)
+    sd = env.state_dict()
+    env.step(a)
+    pos_a = env._goal_state["position"].clone()
+    env.reset()
+    st_a = env.state.clone()
+    env2 = CARLBraxAnt(contexts=ctxs, num_envs=4)
+    env2.load_state_dict(sd)
+    env2.step(a)
+    assert torch.equal(env2._goal_state["position"], pos_a)
+    env2.reset()
+    assert torch.equal(env2.state, st_a)
+
+
+def test_masked_goal_reset_keeps_the_other_positions():
+    """reset(mask=...) re-zeroes the dead-reckoned position only of the envs being reset."""
+    from carl_b200.envs import CARLBraxAnt
+
+    ctxs = {k: {"target_direction": d, "target_distance": 5.0 + k} for k, d in enumerate([1, 12, 3, 34])}
+    env = CARLBraxAnt(contexts=ctxs, num_envs=4)
+    env.reset(seed=0)
+    a = torch.rand(4, 8, device="cuda") * 2 - 1
+    for _ in range(4):
+        env.step(a)
+    pos = env._goal_state["position"].clone()
+    assert (pos.abs().sum(dim=1) > 0).all()
+    mask = np.array([True, False, False, True])
+    env.reset(mask=mask)
+    now = env._goal_state["position"]
+    assert torch.equal(now[1:3], pos[1:3]) and (now[0] == 0).all() and (now[3] == 0).all()
+
+
+def test_discrete_env_accepts_float_cuda_actions_like_the_host_path():
+    from carl_b200.envs import CARLCartPole
+
+    a_env, b_env = CARLCartPole(num_envs=64), CARLCartPole(num_envs=64)
+    a_env.reset(seed=1); b_env.reset(seed=1)
+    acts = torch.randint(0, 2, (64,), device="cuda")
+    oa, *_ = a_env.step(acts.to(torch.float32))
+    ob, *_ = b_env.step(acts.to(torch.int32))
+    assert torch.equal(oa["obs"], ob["obs"])
+
+
 def test_page_locked_actions_are_read_in_place_and_match_staged_path():
     """`step(numpy)` with an array from carl_b200.hostmem.pinned_empty (no staging copy, the kernel reads
     it over PCIe) must give exactly what the same actions in an ordinary array give; the range check
@@ -222,4 +301,91 @@ def test_in_kernel_action_check_rolls_the_step_back(kind):
         np.testing.assert_array_equal(ta, tb)
         np.testing.assert_array_equal(tra, trb)
     assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env._rng, b_env._rng)
+    hostmem.release(pinned)
+
+
+@pytest.mark.parametrize("kind,parts", [("cartpole", 2), ("cartpole", 3), ("pendulum", 4), ("acrobot", 2)])
+def test_split_batch_step_async_equals_step(kind, parts):
+    """step_async / step_wait (split-batch host stepping: the parts' kernels run on their own streams, the host polls
+    a completion word per part) produces exactly what the synchronous env.step(numpy) produces -- whole-batch calls,
+    per-part calls in any order, pinned and pageable actions, auto-resets included."""
+    import carl_b200.envs as E
+    from carl_b200 import hostmem
+
+    cls = {"cartpole": E.CARLCartPole, "pendulum": E.CARLPendulum, "acrobot": E.CARLAcrobot}[kind]
+    n = 1000 + 7
+    a_env = cls(num_envs=n, autoreset=True, max_episode_steps=9)
+    b_env = cls(num_envs=n, autoreset=True, max_episode_steps=9)
+    a_env.async_parts = parts
+    a_env.reset(seed=11)
+    b_env.reset(seed=11)
+    rng = np.random.default_rng(5)
+    discrete = a_env._info.act_discrete
+    pinned = hostmem.pinned_empty((n,) if discrete else (n, 1), np.int32 if discrete else np.float32)
+    bounds = [a_env.part_range(p) for p in range(parts)]
+    assert bounds[0][0] == 0 and bounds[-1][1] == n
+    for t in range(24):
+        acts = rng.integers(0, a_env._info.n_actions, size=n).astype(np.int32) if discrete else \
+            rng.uniform(-2, 2, size=(n, 1)).astype(np.float32)
+        ob, rb, tb, trb, _ = b_env.step(acts)
+        if t % 3 == 0:      # whole batch, pageable actions
+            a_env.step_async(acts)
+            oa, ra, ta, tra, info = a_env.step_wait()
+            np.testing.assert_array_equal(oa["obs"], ob["obs"])
+            np.testing.assert_array_equal(ra, rb)
+            np.testing.assert_array_equal(ta, tb)
+            np.testing.assert_array_equal(tra, trb)
+        else:               # part by part, page-locked actions, waited for in reverse order
+            pinned[...] = acts
+            for p, (lo, hi) in enumerate(bounds):
+                a_env.step_async(pinned[lo:hi], part=p)
+            for p in reversed(range(parts)):
+                lo, hi = bounds[p]
+                oa, ra, ta, tra, info = a_env.step_wait(part=p)
+                np.testing.assert_array_equal(oa["obs"], ob["obs"][lo:hi])
+                np.testing.assert_array_equal(ra, rb[lo:hi])
+                np.testing.assert_array_equal(ta, tb[lo:hi])
+                np.testing.assert_array_equal(tra, trb[lo:hi])
+                assert len(info["context_id"]) == hi - lo
+    assert torch.equal(a_env.state, b_env.state) and torch.equal(a_env._rng, b_env._rng)
+    with pytest.raises(RuntimeError, match="no step in flight"):
+        a_env.step_wait(part=0)
+    hostmem.release(pinned)
+
+
+def test_split_batch_invalid_action_rolls_back_only_that_part():
+    import carl_b200.envs as E
+    from carl_b200 import hostmem
+
+    n = 2048
+    env = E.CARLCartPole(num_envs=n, autoreset=True, max_episode_steps=5)
+    ref = E.CARLCartPole(num_envs=n, autoreset=True, max_episode_steps=5)
+    env.async_parts = 2
+    env.reset(seed=3)
+    ref.reset(seed=3)
+    pinned = hostmem.pinned_empty((n,), np.int32)
+    rng = np.random.default_rng(0)
+    for t in range(8):
+        acts = rng.integers(0, 2, size=n).astype(np.int32)
+        pinned[...] = acts
+        if t == 4:  # every env truncates and resets in this step; part 1 carries an invalid action
+            before = (env.state.clone(), env._elapsed.clone(), env._rng.clone())
+            pinned[n - 3] = 7
+            env.step_async(pinned[:n // 2], part=0)
+            env.step_async(pinned[n // 2:], part=1)
+            env.step_wait(part=0)
+            with pytest.raises(AssertionError, match="invalid action"):
+                env.step_wait(part=1)
+            # part 0 stepped, part 1 is exactly where it was
+            assert torch.equal(env.state[n // 2:], before[0][n // 2:])
+            assert torch.equal(env._elapsed[n // 2:], before[1][n // 2:])
+            assert torch.equal(env._rng[:, n // 2:], before[2][:, n // 2:])
+            pinned[n - 3] = acts[n - 3]
+            env.step_async(pinned[n // 2:], part=1)  # retry the rejected part with valid actions
+            env.step_wait(part=1)
+        else:
+            env.step_async(pinned)
+            env.step_wait()
+        ref.step(acts)
+    assert torch.equal(env.state, ref.state) and torch.equal(env._rng, ref._rng) and torch.equal(env._elapsed, ref._elapsed)
     hostmem.release(pinned)

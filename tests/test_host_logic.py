@@ -36,6 +36,18 @@ def test_pendulum_gravity_feature_is_dead_in_reference_mode():
     assert CARLPendulum.kernel_params(t, names, "applied")[0, 0] == 3.0
 
 
+def test_pendulum_applied_mode_honours_a_deliberate_gravity_of_8():
+    """`gravity` = 8.0 is the feature's default; a context that names it explicitly must still win
+    over `g` in applied mode (the `explicit` mask says which features each context set itself)."""
+    t, names = _table(CARLPendulum, gravity=8.0)
+    j = names.index("gravity")
+    explicit = np.zeros((1, len(names)), dtype=bool)
+    assert CARLPendulum.kernel_params(t, names, "applied", explicit=explicit)[0, 0] == 10.0   # filled-in default: g stays
+    explicit[0, j] = True
+    assert CARLPendulum.kernel_params(t, names, "applied", explicit=explicit)[0, 0] == 8.0    # chosen on purpose
+    assert CARLPendulum.kernel_params(t, names, "reference", explicit=explicit)[0, 0] == 10.0  # dead in the reference
+
+
 def test_param_row_counts_match_kernel_tables(native_lib):
     from carl_b200 import _native
 
