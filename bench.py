@@ -40,6 +40,8 @@ import numpy as np  # noqa: E402
 
 N_ENVS_PER_GPU = 65536
 METRIC = "env-steps/sec at N contexts"
+WORKLOAD = (f"CARLCartPole, {N_ENVS_PER_GPU} sampled contexts (gravity/length/masscart) per GPU (BASELINE configs[1]), "
+            f"uniform random policy, autoreset, TimeLimit 500")
 UNIT = "env-steps/s"
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 L2_BYTES = 126 * 1024 * 1024
@@ -345,8 +347,8 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"CARLCartPole, {N_ENVS_PER_GPU} sampled contexts (gravity/length/masscart) per GPU",
-                   "n_envs": n, "policy": "uniform random (xorshift)", "autoreset": True, "time_limit": 500},
+        "config": {"workload": WORKLOAD, "n_envs": n, "policy": "uniform random", "autoreset": True, "time_limit": 500,
+                   "passes": reps, "policy_rng": "xorshift (CPU arm)"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": f"{n} contexts x {args.steps} steps x {reps} passes, C/OpenMP oracle port "
                                    f"(gymnasium/CARL not installable); thread calibration {cal}; cgroup cpu quota {quota}"},
@@ -704,9 +706,9 @@ def run_gpu_arm(args):
         "ms_per_step": train_ms / (passes * K), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {
-            "workload": f"CARLCartPole, {N_ENVS_PER_GPU} sampled contexts (gravity/length/masscart) per GPU "
-                        f"(BASELINE configs[1]), uniform random policy, autoreset, TimeLimit 500",
-            "n_envs": n_global, "fused_steps_per_launch": T, "launches_per_pass": len(plan),
+            "workload": WORKLOAD, "n_envs": n_global, "policy": "uniform random", "autoreset": True, "time_limit": 500,
+            "policy_rng": "Philox4x32-10 in-kernel (GPU arm)",
+            "fused_steps_per_launch": T, "launches_per_pass": len(plan),
             "timed_region": f"{passes} back-to-back passes of the {K}-step plan ({launches} rollout launches, "
                             f"{train_ms:.1f} ms of GPU time) between two CUDA events; "
                             + (f"replayed from a CUDA graph of {passes_per_chunk} passes" if graph is not None else "eager launches"),
@@ -746,7 +748,7 @@ def run_gpu_arm(args):
             # the kernel is instruction-issue bound, not HBM bound, at this batch size (ncu, same T):
             "issue_slot_utilisation_pct": prof.get("issue_active_pct"),
             "warps_active_pct": prof.get("warps_active_pct"),
-            "ncu_kernel_us": prof.get("duration_us"),
+            "ncu_kernel_us": prof.get("duration_us_under_ncu"),
         },
         "step_api": {
             "value": api_value, "unit": UNIT, "steps": K_api, "us_per_launch": api_ms_per_launch * 1e3,

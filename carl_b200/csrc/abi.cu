@@ -543,11 +543,15 @@ int carlb_env_step_host_begin(carlb_env_t* env, int part, int n_parts, const voi
   chk.done_ticket = ++env->part_ticket[part];
   if (chk.done_ticket == 0) chk.done_ticket = ++env->part_ticket[part];  // 0 is the initial value of the word
   chk.part_counter = env->part_counters + part;
+  const size_t esz = act_dtype == CARLB_ACT_I64 ? 8 : (act_dtype == CARLB_ACT_U8 ? 1 : 4);
+  const size_t arow = esz * (size_t)info.act_dim;
+  // (Moving the data with the copy engines instead -- actions host -> device staging, four result slices device ->
+  // host, a one-thread kernel storing the completion word behind them -- was measured and dropped: every small
+  // cudaMemcpyAsync costs microseconds of fixed latency, 70.9 vs 36.6 us per two-part step, profiles/r02j_e2e_async_probe.json.)
   HostMirrors hm{obs_host, reward_host, terminated_host, truncated_host};
   // the kernel indexes the action array with the env's index in the handle: shift the part's pointer back by
   // `first` elements (only the part's own rows are ever dereferenced)
-  const size_t esz = act_dtype == CARLB_ACT_I64 ? 8 : (act_dtype == CARLB_ACT_U8 ? 1 : 4);
-  const unsigned char* act_base = static_cast<const unsigned char*>(actions_host) - (size_t)chk.first * esz * (size_t)info.act_dim;
+  const unsigned char* act_base = static_cast<const unsigned char*>(actions_host) - (size_t)chk.first * arow;
   rc = classic_step_checked(env, act_base, act_dtype, st, &hm, chk);
   if (rc != CARLB_OK) return rc;
   env->part_pending[part] = true;

@@ -181,7 +181,10 @@ template <int D>
 __device__ __forceinline__ bool deferred_push_prologue(const Segment& seg, unsigned int gseq, int nct, int i) {
   if ((int)threadIdx.x >= nct) {
     named_bar_sync(kBarPushed, nct + 32);
-    if ((int)threadIdx.x == nct) gather_publish(seg.gth, gseq, gridDim.x);
+    // The thread that publishes (last CTA to arrive) also waits for every rank's flag of this push -- mid-kernel,
+    // with nothing else to do -- so the completion of the grid implies that the gathered tensor is complete here;
+    // the compute warps never see a barrier, a counter or a fence.
+    if ((int)threadIdx.x == nct && gather_publish(seg.gth, gseq, gridDim.x)) gather_wait_all(seg.gth, gseq);
     return false;
   }
   if (i < seg.n) {
@@ -209,6 +212,26 @@ __device__ __forceinline__ bool deferred_push_prologue(const Segment& seg, unsig
   return true;
 }
 
+// Ahead of the deferred push (whose row store waits an L2 round trip for the row load and the push counter): pull
+// the lines this thread's env reads first -- state row, context rows, counters -- towards L1, so that the two waits
+// overlap instead of adding up.
+template <int KIND, typename T>
+__device__ __forceinline__ void prefetch_ctx(const Segment& seg, int i) {
+  const T* ctx = static_cast<const T*>(seg.ctx);
+#pragma unroll
+  for (int r = 0; r < Traits<KIND>::P; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(ctx + (size_t)r * seg.n + i));
+}
+template <int KIND, typename T>
+__device__ __forceinline__ void prefetch_env(const Segment& seg, int i) {
+  typedef Traits<KIND> Tr;
+  const T* ctx = static_cast<const T*>(seg.ctx);
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(static_cast<const T*>(seg.state) + (size_t)i * Tr::S));
+#pragma unroll
+  for (int r = 0; r < Tr::P; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(ctx + (size_t)r * seg.n + i));
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(seg.elapsed + i));
+  if (KIND == KIND_CARTPOLE) asm volatile("prefetch.global.L1 [%0];" ::"l"(seg.sbt + i));
+}
+
 template <int KIND, typename T>
 __global__ void __launch_bounds__(kBlock + 32) step_kernel(const __grid_constant__ Segment seg, const void* actions) {
   pdl_launch_dependents();
@@ -219,8 +242,7 @@ __global__ void __launch_bounds__(kBlock + 32) step_kernel(const __grid_constant
   if (deferred && !deferred_push_prologue<Traits<KIND>::D>(seg, gseq, nct, i)) return;
   if (i < seg.n) step_one<KIND, T, false>(seg, actions, i, StepCheck{}, gseq);
   else pdl_wait();
-  if (deferred) gather_epilogue_deferred(seg.gth, gseq, nct);
-  else gather_epilogue_immediate(seg.gth, gseq);
+  if (!deferred) gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // The host-buffer step with in-kernel action validation and an undo log (StepCheck).
@@ -327,10 +349,13 @@ template <typename P> __device__ __forceinline__ P* pin_reg(P* v) {
 template <int KIND, typename T, bool REC, bool AR>
 __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
                                              uint32_t step_base, const void* actions, const carlb_traj_t& traj,
-                                             int refill_threshold, uint64_t* sv_slot, unsigned int gseq) {
+                                             int refill_threshold, uint64_t* sv_slot, unsigned int gseq, int pdl_lead) {
   typedef Traits<KIND> Tr;
   const int n = seg.n;
   const int max_steps = pin_reg(seg.max_steps);
+  // programmatic dependent launch: the step at which this thread lets the NEXT launch of the stream begin to
+  // schedule its CTAs (they block in griddepcontrol.wait until this grid has completed); < 0: never
+  const int pdl_step = pdl_lead > 0 ? pin_reg(n_steps > pdl_lead ? n_steps - pdl_lead : 0) : -1;
   const size_t row_stride = pin_reg((size_t)n);
   n_steps = pin_reg(n_steps);
   step_base = pin_reg(step_base);
@@ -388,6 +413,7 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   for (int k = 0; k < Tr::D; ++k) no[k] = 0.0f;
 #pragma unroll 1
   for (int t = 0; t < n_steps; ++t) {
+    if (t == pdl_step) pdl_launch_dependents();
     Action a;
     if (REC) a = policy_action<KIND>(ps, step_base + (uint32_t)t);
     else a = (a_in != nullptr) ? load_action(a_in, seg.act_dtype, 0) : policy_action<KIND>(ps, step_base + (uint32_t)t);
@@ -470,24 +496,31 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
 template <int KIND, typename T, bool REC>
 __global__ void __launch_bounds__(kBlock + 32) rollout_kernel(const __grid_constant__ Segment seg, int n_steps,
                                                               uint64_t policy_seed, uint32_t step_base, const void* actions,
-                                                              const carlb_traj_t traj, int refill_threshold) {
+                                                              const carlb_traj_t traj, int refill_threshold, int pdl_lead) {
   __shared__ uint64_t sv_sh[2 * kBlock];  // per-thread PCG64 state saved before a pre-generated reset
   const bool deferred = seg.gth.n_peers > 0 && seg.gth.mode == GATHER_DEFERRED;
   const int nct = deferred ? (int)blockDim.x - 32 : (int)blockDim.x;  // compute threads per CTA
-  const unsigned int gseq = gather_begin(seg.gth);
   const int i = blockIdx.x * nct + threadIdx.x;
+  if (pdl_lead > 0) {
+    // launched with the programmatic-serialization attribute: this CTA may have started while the previous launch
+    // of the stream was still in its last steps. What does not depend on that launch -- the read-only context rows
+    // -- is pulled towards L1 now; everything else waits for the previous grid to complete and flush.
+    if (i < seg.n && (int)threadIdx.x < nct) prefetch_ctx<KIND, T>(seg, i);
+    pdl_wait();
+  }
+  const unsigned int gseq = gather_begin(seg.gth);
+  if (deferred && i < seg.n && (int)threadIdx.x < nct) prefetch_env<KIND, T>(seg, i);
   if (deferred && !deferred_push_prologue<Traits<KIND>::D>(seg, gseq, nct, i)) return;
   if (i < seg.n) {
     bool clean = seg.autoreset != CARLB_AUTORESET_NONE;  // warp-uniform choice of the specialised loop
     if (KIND == KIND_CARTPOLE) clean = __all_sync(__activemask(), clean && seg.sbt[i] == 0);
     uint64_t* sv_slot = &sv_sh[threadIdx.x];
-    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq);
-    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq);
+    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq, pdl_lead);
+    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq, pdl_lead);
   }
   // ONE call site reached by every (compute) thread of the CTA: the epilogues contain an aligned barrier,
   // which must not be executed from divergent code (ragged tail warps)
-  if (deferred) gather_epilogue_deferred(seg.gth, gseq, nct);
-  else gather_epilogue_immediate(seg.gth, gseq);
+  if (!deferred) gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // --------------------------------------------------------------------------- launchers
@@ -627,7 +660,31 @@ static void launch_rollout(const carlb_env* env, const Segment& seg, int preferr
     if ((long long)(env->n + block - 1) / block <= (long long)o * n_sms[dev]) break;
   }
   const int grid = (env->n + block - 1) / block;
-  rollout_kernel<KIND, T, REC><<<grid, block + extra, 0, st>>>(seg, n_steps, policy_seed, step_base, actions, tj, refill);
+  // CARLB_ROLLOUT_PDL=L (opt-in, default 0 = plain launches): launch with the programmatic-serialization attribute and
+  // let every thread release the next launch of the stream L steps before its last one, so that launch latency, CTA
+  // scheduling and the context prefetch of launch k+1 could overlap the tail of launch k. Measured on B200 inside
+  // CUDA-graph trains of 20-step launches (profiles/r02j_pdl_sweep.txt): L = 1 gains 1 % (11.51 -> 11.36 us), larger
+  // leads lose (the early CTAs take resident slots from the running grid: L = 8 13.1 us) -- not worth a default.
+  static const int pdl_lead = [] {
+    const char* e = getenv("CARLB_ROLLOUT_PDL");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return v < 0 ? 0 : v;
+  }();
+  if (pdl_lead == 0) {
+    rollout_kernel<KIND, T, REC><<<grid, block + extra, 0, st>>>(seg, n_steps, policy_seed, step_base, actions, tj, refill, 0);
+    return;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)(block + extra));
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, rollout_kernel<KIND, T, REC>, seg, n_steps, policy_seed, step_base, actions, tj, refill, pdl_lead);
 }
 
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,

@@ -26,7 +26,7 @@ namespace carlb {
 //                     the end of the grid.
 constexpr int kGatherSlots = 4;
 enum { GATHER_IMMEDIATE = 0, GATHER_DEFERRED = 1 };
-enum { GCTRL_SEQ = 0, GCTRL_PUSH_COUNTER = 1, GCTRL_END_COUNTER = 2 };
+enum { GCTRL_SEQ = 0, GCTRL_PUSH_COUNTER = 1 };
 
 struct GatherDev {
   int n_peers;                                // world size (0: no gather attached)
@@ -57,9 +57,15 @@ __device__ __forceinline__ unsigned int ld_acquire_sys_u32(const unsigned int* p
 // kernel (no barrier: the load overlaps the thread's other prologue loads). All threads of the grid see the same
 // value because the counter only moves when the LAST CTA publishes, i.e. after every CTA has arrived, and a CTA
 // arrives only after all of its threads have passed this read.
+// (No "memory" clobber on this load, on the row stores or on the compute warps' barrier arrival: they are
+// `asm volatile`, so the compiler keeps them in order among themselves, but it stays free to hoist the thread's
+// own prologue loads -- state, context rows -- above them; otherwise every compute thread would first wait an L2
+// round trip for the counter and only then start loading its env.)
 __device__ __forceinline__ unsigned int gather_begin(const GatherDev& g) {
   if (g.n_peers <= 0) return 0u;
-  return ld_volatile_u32(g.ctrl + GCTRL_SEQ);
+  unsigned int v;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(g.ctrl + GCTRL_SEQ));
+  return v;
 }
 
 // Store one obs row (D floats, 16-byte aligned when D % 4 == 0) into slot `seq` of every rank.
@@ -73,14 +79,14 @@ __device__ __forceinline__ void gather_store_row(const GatherDev& g, unsigned in
 #pragma unroll
       for (int k = 0; k < D; k += 4)
         asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]),
-                     "f"(o[k + 2]), "f"(o[k + 3]) : "memory");
+                     "f"(o[k + 2]), "f"(o[k + 3]));
     } else if (D % 2 == 0) {
 #pragma unroll
       for (int k = 0; k < D; k += 2)
-        asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]) : "memory");
+        asm volatile("multimem.st.weak.global.v2.f32 [%0], {%1, %2};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]));
     } else {
 #pragma unroll
-      for (int k = 0; k < D; ++k) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(dst + k), "f"(o[k]) : "memory");
+      for (int k = 0; k < D; ++k) asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(dst + k), "f"(o[k]));
     }
     return;
   }
@@ -88,13 +94,15 @@ __device__ __forceinline__ void gather_store_row(const GatherDev& g, unsigned in
     float* dst = g.peer_base[r] + off;
     if (D % 4 == 0) {
 #pragma unroll
-      for (int k = 0; k < D; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(o[k], o[k + 1], o[k + 2], o[k + 3]);
+      for (int k = 0; k < D; k += 4)
+        asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]), "f"(o[k + 2]),
+                     "f"(o[k + 3]));
     } else if (D % 2 == 0) {
 #pragma unroll
-      for (int k = 0; k < D; k += 2) *reinterpret_cast<float2*>(dst + k) = make_float2(o[k], o[k + 1]);
+      for (int k = 0; k < D; k += 2) asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(dst + k), "f"(o[k]), "f"(o[k + 1]));
     } else {
 #pragma unroll
-      for (int k = 0; k < D; ++k) dst[k] = o[k];
+      for (int k = 0; k < D; ++k) asm volatile("st.global.f32 [%0], %1;" ::"l"(dst + k), "f"(o[k]));
     }
   }
 }
@@ -102,10 +110,10 @@ __device__ __forceinline__ void gather_store_row(const GatherDev& g, unsigned in
 __device__ __forceinline__ void gather_store_elem(const GatherDev& g, unsigned int seq, size_t global_elem, float v) {
   const size_t off = (size_t)(seq % kGatherSlots) * g.slot_floats + global_elem;
   if (g.mc_base != nullptr) {
-    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(g.mc_base + off), "f"(v) : "memory");
+    asm volatile("multimem.st.weak.global.f32 [%0], %1;" ::"l"(g.mc_base + off), "f"(v));
     return;
   }
-  for (int r = 0; r < g.n_peers; ++r) g.peer_base[r][off] = v;
+  for (int r = 0; r < g.n_peers; ++r) asm volatile("st.global.f32 [%0], %1;" ::"l"(g.peer_base[r] + off), "f"(v));
 }
 
 // Called by ONE thread per CTA after the CTA's pushed rows are ordered before it (barrier). The CTA
@@ -153,25 +161,12 @@ __device__ __forceinline__ void gather_epilogue_immediate(const GatherDev& g, un
   if (threadIdx.x == 0 && gather_publish(g, seq, gridDim.x)) gather_wait_all(g, seq);
 }
 
-// Named barriers of the DEFERRED push (barrier 0 is __syncthreads). `count` must be a multiple of 32 and
-// every thread of a participating warp must execute the instruction.
+// Named barrier of the DEFERRED push (barrier 0 is __syncthreads). `count` must be a multiple of 32 and every
+// thread of a participating warp must execute the instruction.
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// the compute warps' side: ordered after the thread's (asm volatile) row stores, no compiler memory barrier
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count)); }
 constexpr int kBarPushed = 1;   // compute warps arrive after storing their rows; the publisher warp syncs on it
-constexpr int kBarCompute = 2;  // compute warps only, at the end of the kernel
-
-// End of a DEFERRED-push kernel, called by every COMPUTE thread (n_compute of them per CTA) from
-// non-divergent code: the last CTA to finish checks that every rank's push has arrived.
-__device__ __forceinline__ void gather_epilogue_deferred(const GatherDev& g, unsigned int seq, int n_compute) {
-  named_bar_sync(kBarCompute, n_compute);
-  if (threadIdx.x == 0) {
-    const unsigned int prev = atomicAdd(g.ctrl + GCTRL_END_COUNTER, 1u);
-    if (prev == gridDim.x - 1) {
-      g.ctrl[GCTRL_END_COUNTER] = 0;
-      gather_wait_all(g, seq);
-    }
-  }
-}
 
 // One homogeneous shard of env instances resident on this GPU. All pointers are device
 // pointers into caller-owned buffers (torch tensors); the library never allocates per step.

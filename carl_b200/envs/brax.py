@@ -110,6 +110,18 @@ class CARLBraxEnv(CARLEnv):
         super().__init__(env=env, contexts=contexts, obs_context_features=obs_context_features,
                          obs_context_as_dict=obs_context_as_dict, context_selector=context_selector,
                          context_selector_kwargs=context_selector_kwargs, **kwargs)
+        if self.context_mode == "reference" and len(self._table) > 1:
+            vals, names_ = np.asarray(self._table.values), self._feature_names
+            varying = [n for j, n in enumerate(names_)
+                       if not n.startswith("target_") and np.ptp(vals[:, j]) > 0]
+            if varying:
+                import warnings
+
+                warnings.warn(
+                    f"{type(self).__name__}: the contexts vary {varying}, but context_mode='reference' reproduces the reference, "
+                    "whose Brax context injection never reaches the physics (carl_brax_env.py:292 assigns the modified `sys` to "
+                    "the gym shell, SURVEY §0.5): every env will step with the stock dynamics. Pass context_mode='applied' for "
+                    "what the reference intends.", stacklevel=2)
         if contexts is not None and not isinstance(contexts, dict):
             # a dense ContextTable that varies the target behaves like the equivalent dict of contexts
             self._goal_active = brax_goals.goal_wrapper_active_table(list(contexts.names), np.asarray(contexts.values))

@@ -21,14 +21,14 @@ def main():
     mode = sys.argv[1] if len(sys.argv) > 1 else "none"
     short = "--ncu" in sys.argv
     dev = torch.device("cuda", 0)
-    n, T = bench.N_ENVS_PER_GPU, 20
+    n, T = bench.N_ENVS_PER_GPU, int(os.environ.get("PROBE_T", "20"))
     names, table = bench.make_context_table(n)
     env = CARLCartPole(contexts=ContextTable(names, table), device=dev, autoreset=True)
     env.reset(seed=0)
     g = None
     if mode != "none":
         g = ObsGather(env, mode="fused", pipelined=(mode == "pipelined"), symmetric="ipc")
-    n_slots = 8
+    n_slots = max(2, int(np.ceil(1.5 * bench.L2_BYTES / (T * n * bench.TRAJ_BYTES))) + 1)
     ring = [dict(obs=torch.empty(T, n, 4, device=dev), actions=torch.empty(T, n, dtype=torch.int32, device=dev),
                  reward=torch.empty(T, n, device=dev), done=torch.empty(T, n, dtype=torch.uint8, device=dev)) for _ in range(n_slots)]
     trajs = [_native.Traj(obs=r["obs"].data_ptr(), actions=r["actions"].data_ptr(), reward=r["reward"].data_ptr(),
@@ -64,7 +64,7 @@ def main():
         graph.replay()
     e1.record(stream)
     torch.cuda.synchronize()
-    print(json.dumps({"mode": mode, "debug": os.environ.get("CARLB_GATHER_DEBUG"), "block": os.environ.get("CARLB_ROLLOUT_BLOCK"),
+    print(json.dumps({"mode": mode, "debug": os.environ.get("CARLB_GATHER_DEBUG"), "block": os.environ.get("CARLB_ROLLOUT_BLOCK"), "pdl": os.environ.get("CARLB_ROLLOUT_PDL"), "T": T,
                       "us_per_launch": e0.elapsed_time(e1) * 1e3 / (300 * 32)}))
 
 

@@ -1,11 +1,10 @@
 #!/bin/bash
-# r02f (NG GPUs): scaling lines of bench.py at N = 1, 2, .., NG (the driver's command) + the multi-GPU correctness worker.
+# Scaling lines of bench.py at N in NLIST (capped at NG) with the driver's command; prints per-N efficiency.
 set +e
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
 NG=${NG:-2}
 nvidia-smi topo -m > gpurun_out/topo.txt 2>&1
-CARLB_MGPU_TIMEOUT=500 timeout 560 python -m torch.distributed.run --nnodes=1 --nproc-per-node=$NG --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_worker.py > gpurun_out/mgpu_worker_${NG}gpu.log 2>&1; echo "mgpu worker ($NG ranks) exit $?"; grep -c "MGPU_OK" gpurun_out/mgpu_worker_${NG}gpu.log; tail -3 gpurun_out/mgpu_worker_${NG}gpu.log
-for n in 1 2 4 8; do
+for n in ${NLIST:-1 2 4 8}; do
   if [ $n -gt $NG ]; then break; fi
   if [ $n -eq 1 ]; then
     timeout 400 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/scale_n1.json 2> gpurun_out/scale_n1.err

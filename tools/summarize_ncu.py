@@ -51,7 +51,7 @@ def launch_list(tag):
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(PROF, f"{tag}_launch_list.txt"), "w") as f:
         f.write("# ncu --metrics gpu__time_duration.sum --clock-control none  (cold-cache, serialised: compare SHARES)\n")
-        f.write("# command: python bench.py --steps 2000 --warmup 200 --fused-only  = warm-up + the timed region of the default bench\n")
+        f.write("# command: python bench.py --steps 20 --warmup 5 --fused-only (the driver's command, fused-rollout leg only; first 600 launches)\n")
         f.write(f"# total kernel time {tot / 1e3:.1f} us over {sum(v[0] for v in agg.values())} launches\n")
         for k, v in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{v[1] / 1e3:12.1f} us  {v[0]:6d} launches  {100 * v[1] / tot:6.2f}%  avg {v[1] / v[0] / 1e3:9.2f} us  {k}\n")
