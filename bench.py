@@ -684,6 +684,7 @@ def run_gpu_arm(args):
     if not args.no_ant:
         extra["ant_8192"] = ant_leg(dev, peak, args, rank, world, barrier)
         extra["config5_halfcheetah_hopper"] = config5_leg(dev, args, rank, world, barrier)
+        extra["config3_pendulum_acrobot"] = config3_leg(dev, args, rank, world, barrier)
     if not args.no_f64:
         extra["value_f64"] = f64_leg(dev, names, table, rank, world, K, T, barrier, args, n_global)
     if rank != 0:
@@ -1013,6 +1014,72 @@ def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
                 "api": "CARLBraxAnt.step(numpy float32 actions in page-locked memory) -> numpy obs/reward/terminated/truncated "
                        "(the step kernel reads the actions and writes the results over PCIe itself)"},
     }
+
+
+def config3_leg(dev, args, rank, world, barrier):
+    """BASELINE configs[2]: CARLPendulum + CARLAcrobot, 32 768 contexts each PER GPU, advanced by ONE mixed launch
+    per step (`carlb_mixed_step`: block-uniform kind switch), replayed from a CUDA graph; plus the two shards as fused
+    rollouts (20 steps per launch)."""
+    import ctypes
+
+    import torch
+
+    from carl_b200 import _native
+    from carl_b200.context import ContextSampler, UniformFloatContextFeature
+    from carl_b200.envs import CARLAcrobot, CARLPendulum, ContextTable, MixedBatch
+
+    n = 32768
+
+    def table(cls, feats):
+        names = list(cls.get_context_space().get_default_context().keys())
+        smp = ContextSampler([UniformFloatContextFeature(k, lo, hi) for k, (lo, hi) in feats.items()],
+                             context_space=cls.get_context_space(), seed=0)
+        return ContextTable(names, smp.sample_context_table(n * world, names))
+
+    pen = CARLPendulum(contexts=table(CARLPendulum, {"g": (5, 15), "m": (0.5, 2), "l": (0.5, 2)}), device=dev, autoreset=True,
+                       shard=(rank, world))
+    acr = CARLAcrobot(contexts=table(CARLAcrobot, {"LINK_MASS_1": (0.5, 2), "LINK_MASS_2": (0.5, 2), "LINK_LENGTH_1": (0.5, 2)}),
+                      device=dev, autoreset=True, shard=(rank, world))
+    mixed = MixedBatch([pen, acr])
+    mixed.reset(seed=0)
+    G = 64
+    ap = torch.rand(G, n, device=dev) * 4 - 2
+    aa = torch.randint(0, 3, (G, n), dtype=torch.int32, device=dev)
+    dts = (ctypes.c_int * 2)(_native.ACT_F32, _native.ACT_I32)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(j, st):
+        ptrs = (ctypes.c_void_p * 2)(ap[j % G].data_ptr(), aa[j % G].data_ptr())
+        _native.check(mixed._lib.carlb_mixed_step(mixed._handles, ptrs, dts, 2, st))
+
+    for j in range(3):
+        step(j, stream.cuda_stream)
+    torch.cuda.synchronize(dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(stream)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        for j in range(G):
+            step(j, torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize(dev)
+    ms, _, reps = timed_train(graph.replay, G, stream, barrier, min(args.min_gpu_seconds, 0.05), min_replays=3)
+    ms = max_over_ranks(ms, dev, world > 1)
+    us = ms / (reps * G) * 1e3
+    out = {"workload": f"CARLPendulum {n} + CARLAcrobot {n} contexts per GPU, ONE mixed launch per step (CUDA-graph replay), "
+                       f"{world} GPU(s)",
+           "value": 2 * n * world / (us * 1e-6), "unit": UNIT, "us_per_step": us,
+           "algorithmic_GBps_62B_110B": (62 + 110) * n / (us * 1e-6) / 1e9}
+    T = 20
+    for env, name in ((pen, "pendulum"), (acr, "acrobot")):
+        fn = lambda: env.rollout(T, policy_seed=1, record=False)
+        for _ in range(2):
+            fn()
+        ms_r, _, reps_r = timed_train(fn, 1, stream, barrier, 0.03, min_replays=5)
+        ms_r = max_over_ranks(ms_r, dev, world > 1)
+        out[f"{name}_fused_{T}_steps"] = {"value": n * world * T * reps_r / (ms_r * 1e-3), "unit": UNIT}
+    pen.close()
+    acr.close()
+    return out
 
 
 def config5_leg(dev, args, rank, world, barrier):

@@ -394,9 +394,9 @@ static int ensure_step_check(carlb_env* env, int n_actions, StepCheck* chk) {
   const size_t n = (size_t)env->n;
   const size_t word = env->precision == CARLB_F64 ? 8 : 4;
   const size_t state_b = ((n * info.state_words * word + 15) / 16) * 16, el_b = ((n * 4 + 15) / 16) * 16,
-               flag_b = ((n + 15) / 16) * 16, rng_b = 2 * n * 8;
+               flag_b = ((n + 15) / 16) * 16, rng_b = 2 * n * 8, obs_b = ((n * info.obs_dim * 4 + 15) / 16) * 16;
   if (env->undo_block == nullptr) {
-    CARLB_CUDA_CHECK(cudaMalloc(&env->undo_block, state_b + el_b + 2 * flag_b + rng_b));
+    CARLB_CUDA_CHECK(cudaMalloc(&env->undo_block, state_b + el_b + 2 * flag_b + rng_b + obs_b + el_b + 2 * flag_b));
     CARLB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&env->bad_action_host), 2 * CARLB_MAX_PARTS * sizeof(int),
                                    cudaHostAllocMapped));
     memset(env->bad_action_host, 0, 2 * CARLB_MAX_PARTS * sizeof(int));
@@ -416,6 +416,10 @@ static int ensure_step_check(carlb_env* env, int n_actions, StepCheck* chk) {
   chk->undo_elapsed = reinterpret_cast<int32_t*>(p + state_b + rng_b);
   chk->undo_sbt = p + state_b + rng_b + el_b;
   chk->undo_rng_flag = p + state_b + rng_b + el_b + flag_b;
+  unsigned char* q = p + state_b + rng_b + el_b + 2 * flag_b;
+  chk->undo_obs = reinterpret_cast<float*>(q);
+  chk->undo_reward = reinterpret_cast<float*>(q + obs_b);
+  chk->undo_flags = q + obs_b + el_b;  // [2][n]: needs 2 * n bytes <= 2 * flag_b
   return CARLB_OK;
 }
 
@@ -478,7 +482,7 @@ int carlb_env_step_host_checked(carlb_env_t* env, const void* actions_host, int 
   const int bad = *reinterpret_cast<volatile int*>(env->bad_action_host);
   if (bad != 0) {  // roll every env back: the reference's env is untouched when `action_space.contains` fails
     *env->bad_action_host = 0;
-    rc = classic_step_undo(env, st, chk);
+    rc = classic_step_undo(env, st, chk, &hm);
     if (rc != CARLB_OK) return rc;
     CARLB_CUDA_CHECK(cudaStreamSynchronize(st));
     set_error("invalid action: values must lie in [0, %d) (env %d)", n_actions, bad - 1);
@@ -594,7 +598,11 @@ int carlb_env_step_host_end(carlb_env_t* env, int part) {
     chk.first = env->part_first[part];
     chk.count = env->part_count[part];
     CARLB_CUDA_CHECK(cudaSetDevice(env->device));
-    rc = classic_step_undo(env, env->part_stream[part], chk);
+    const HostMirrors hm{const_cast<float*>(static_cast<const float*>(env->zc_verified[0])),
+                         const_cast<float*>(static_cast<const float*>(env->zc_verified[1])),
+                         const_cast<uint8_t*>(static_cast<const uint8_t*>(env->zc_verified[2])),
+                         const_cast<uint8_t*>(static_cast<const uint8_t*>(env->zc_verified[3]))};
+    rc = classic_step_undo(env, env->part_stream[part], chk, &hm);
     if (rc != CARLB_OK) return rc;
     CARLB_CUDA_CHECK(cudaStreamSynchronize(env->part_stream[part]));
     set_error("invalid action: values must lie in [0, %d) (env %d)", env->part_n_actions[part], bad - 1);

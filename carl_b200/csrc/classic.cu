@@ -114,6 +114,11 @@ __device__ __forceinline__ void step_one(const Segment& seg, const void* actions
     StateIO<T, Tr::S>::store(chk.undo_state, i, s);
     chk.undo_elapsed[i] = el;
     if (KIND == KIND_CARTPOLE) chk.undo_sbt[i] = sb;
+#pragma unroll
+    for (int k = 0; k < Tr::D; ++k) chk.undo_obs[(size_t)i * Tr::D + k] = seg.obs[(size_t)i * Tr::D + k];
+    chk.undo_reward[i] = seg.reward[i];
+    chk.undo_flags[i] = seg.terminated[i];
+    chk.undo_flags[(size_t)seg.n + i] = seg.truncated[i];
     if (Tr::DISCRETE && chk.n_actions > 0 && (unsigned)a.i >= (unsigned)chk.n_actions) {
       *reinterpret_cast<volatile int*>(chk.bad_action) = i + 1;  // any one offender is enough
       chk.undo_rng_flag[i] = 0;
@@ -287,6 +292,18 @@ __global__ void __launch_bounds__(kBlock) step_undo_kernel(const __grid_constant
     seg.rng[i] = chk.undo_rng[i];
     seg.rng[(size_t)seg.n + i] = chk.undo_rng[(size_t)seg.n + i];
   }
+  // the returned quantities: device buffers and (zero-copy mirrors) the caller's host arrays
+  float o[Tr::D];
+#pragma unroll
+  for (int k = 0; k < Tr::D; ++k) o[k] = chk.undo_obs[(size_t)i * Tr::D + k];
+  const float rw = chk.undo_reward[i];
+  const uint8_t te = chk.undo_flags[i], tr = chk.undo_flags[(size_t)seg.n + i];
+  store_obs<Tr::D>(seg.obs, (size_t)i, o);
+  seg.reward[i] = rw; seg.terminated[i] = te; seg.truncated[i] = tr;
+  if (seg.host_obs != nullptr) {
+    store_obs<Tr::D>(seg.host_obs, (size_t)i, o);
+    seg.host_reward[i] = rw; seg.host_terminated[i] = te; seg.host_truncated[i] = tr;
+  }
 }
 
 // ----------------------------------------------------------------------- mixed batch
@@ -349,7 +366,8 @@ template <typename P> __device__ __forceinline__ P* pin_reg(P* v) {
 template <int KIND, typename T, bool REC, bool AR>
 __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_steps, uint64_t policy_seed,
                                              uint32_t step_base, const void* actions, const carlb_traj_t& traj,
-                                             int refill_threshold, uint64_t* sv_slot, unsigned int gseq, int pdl_lead) {
+                                             int refill_threshold, uint64_t* sv_slot, unsigned int gseq, int pdl_lead,
+                                             float* o_fin) {
   typedef Traits<KIND> Tr;
   const int n = seg.n;
   const int max_steps = pin_reg(seg.max_steps);
@@ -482,7 +500,12 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   }
   StateIO<T, Tr::S>::store(seg.state, i, s);
   if (n_steps > 0) {
-    store_obs<Tr::D>(seg.obs, (size_t)i, o);
+    if (o_fin != nullptr) {  // deferred gather push: the kernel stores the row once the publisher warp has read the old one
+#pragma unroll
+      for (int k = 0; k < Tr::D; ++k) o_fin[k] = o[k];
+    } else {
+      store_obs<Tr::D>(seg.obs, (size_t)i, o);
+    }
     if (seg.gth.n_peers > 0 && seg.gth.mode == GATHER_IMMEDIATE)
       gather_store_row<Tr::D>(seg.gth, gseq, (size_t)(seg.global_offset + i), o);
     seg.reward[i] = so.reward;
@@ -491,6 +514,51 @@ __device__ __forceinline__ void rollout_body(const Segment& seg, int i, int n_st
   }
   seg.elapsed[i] = el;
   if (KIND == KIND_CARTPOLE) seg.sbt[i] = sb;
+}
+
+// The publisher warp of a rollout launch in DEFERRED gather mode (warp specialisation): it alone reads the rows the
+// PREVIOUS launch left in seg.obs (this CTA's nct rows: 512 contiguous bytes per load instruction) and pushes them
+// into every rank's gathered buffer, then releases the compute warps' final obs store (named barrier), fences, counts
+// the CTA in and -- in the last CTA -- publishes the push and waits for the other ranks' flags. The compute warps run
+// the physics meanwhile; all they ever see of the gather is one barrier before their last store, passed long before.
+template <int D>
+__device__ __forceinline__ void rollout_publisher(const Segment& seg, unsigned int gseq, int nct) {
+  const int lane = (int)threadIdx.x - nct;
+  const int base = blockIdx.x * nct;
+  constexpr int kRows = kBlock / 32;
+  float rows[kRows][D];
+  bool valid[kRows];
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    const int j = lane + 32 * r;
+    valid[r] = j < nct && base + j < seg.n;
+    if (valid[r]) {
+      const float* src = seg.obs + (size_t)(base + j) * D;
+      if (D % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+          const float4 v = *reinterpret_cast<const float4*>(src + k);
+          rows[r][k] = v.x; rows[r][k + 1] = v.y; rows[r][k + 2] = v.z; rows[r][k + 3] = v.w;
+        }
+      } else if (D % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < D; k += 2) {
+          const float2 v = *reinterpret_cast<const float2*>(src + k);
+          rows[r][k] = v.x; rows[r][k + 1] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < D; ++k) rows[r][k] = src[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r)
+    if (valid[r]) gather_store_row<D>(seg.gth, gseq, (size_t)(seg.global_offset + base + lane + 32 * r), rows[r]);
+  // the stores above consumed the loaded values, so the old rows have been read: the compute warps may overwrite them
+  named_bar_arrive(kBarObsRead, nct + 32);
+  __syncwarp();  // the other lanes' row stores happen-before lane 0's fence
+  if (lane == 0 && gather_publish(seg.gth, gseq, gridDim.x)) gather_wait_all(seg.gth, gseq);
 }
 
 template <int KIND, typename T, bool REC>
@@ -509,18 +577,27 @@ __global__ void __launch_bounds__(kBlock + 32) rollout_kernel(const __grid_const
     pdl_wait();
   }
   const unsigned int gseq = gather_begin(seg.gth);
-  if (deferred && i < seg.n && (int)threadIdx.x < nct) prefetch_env<KIND, T>(seg, i);
-  if (deferred && !deferred_push_prologue<Traits<KIND>::D>(seg, gseq, nct, i)) return;
+  if (deferred && (int)threadIdx.x >= nct) {
+    rollout_publisher<Traits<KIND>::D>(seg, gseq, nct);
+    return;
+  }
+  float o_fin[Traits<KIND>::D];
   if (i < seg.n) {
     bool clean = seg.autoreset != CARLB_AUTORESET_NONE;  // warp-uniform choice of the specialised loop
     if (KIND == KIND_CARTPOLE) clean = __all_sync(__activemask(), clean && seg.sbt[i] == 0);
     uint64_t* sv_slot = &sv_sh[threadIdx.x];
-    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq, pdl_lead);
-    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq, pdl_lead);
+    float* of = deferred ? o_fin : nullptr;
+    if (clean) rollout_body<KIND, T, REC, true>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq, pdl_lead, of);
+    else rollout_body<KIND, T, REC, false>(seg, i, n_steps, policy_seed, step_base, actions, traj, refill_threshold, sv_slot, gseq, pdl_lead, of);
   }
-  // ONE call site reached by every (compute) thread of the CTA: the epilogues contain an aligned barrier,
-  // which must not be executed from divergent code (ragged tail warps)
-  if (!deferred) gather_epilogue_immediate(seg.gth, gseq);
+  // ONE call site reached by every (compute) thread of the CTA: the barriers below are aligned and must not be
+  // executed from divergent code (ragged tail warps)
+  if (deferred) {
+    named_bar_sync(kBarObsRead, nct + 32);  // the publisher warp arrived once its loads of the OLD rows had completed
+    if (i < seg.n && n_steps > 0) store_obs<Traits<KIND>::D>(seg.obs, (size_t)i, o_fin);
+  } else {
+    gather_epilogue_immediate(seg.gth, gseq);
+  }
 }
 
 // --------------------------------------------------------------------------- launchers
@@ -627,8 +704,12 @@ int classic_step_checked(const carlb_env* env, const void* actions, int act_dtyp
   return CARLB_OK;
 }
 
-int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk) {
+int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk, const HostMirrors* hm) {
   Segment seg = make_segment(env, CARLB_ACT_I32);
+  if (hm != nullptr) {
+    seg.host_obs = hm->obs; seg.host_reward = hm->reward; seg.host_terminated = hm->terminated;
+    seg.host_truncated = hm->truncated;
+  }
   CARLB_DISPATCH_KIND_T(env->kind, env->precision, (step_undo_kernel<K_, T_><<<grid_for(chk.count), kBlock, 0, st>>>(seg, chk)));
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());

@@ -166,7 +166,8 @@ __device__ __forceinline__ void gather_epilogue_immediate(const GatherDev& g, un
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 // the compute warps' side: ordered after the thread's (asm volatile) row stores, no compiler memory barrier
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count)); }
-constexpr int kBarPushed = 1;   // compute warps arrive after storing their rows; the publisher warp syncs on it
+constexpr int kBarPushed = 1;   // step kernel: compute warps arrive after storing their rows; the publisher warp syncs on it
+constexpr int kBarObsRead = 2;  // rollout kernel: the publisher warp arrives after reading the old rows; compute warps sync before overwriting them
 
 // One homogeneous shard of env instances resident on this GPU. All pointers are device
 // pointers into caller-owned buffers (torch tensors); the library never allocates per step.
@@ -216,6 +217,11 @@ struct StepCheck {
   uint8_t* undo_sbt;       // [n]
   uint64_t* undo_rng;      // [2][n] PCG64 state words before this step (valid where undo_rng_flag)
   uint8_t* undo_rng_flag;  // [n]
+  // what the step RETURNS is logged too, so that after a roll-back the device result buffers and the caller's host
+  // arrays show the previous step again (`state_dict()` right after a rejected step must be consistent)
+  float* undo_obs;         // [n][D]
+  float* undo_reward;      // [n]
+  uint8_t* undo_flags;     // [2][n] terminated, truncated
 };
 
 __device__ __forceinline__ Action load_action(const void* actions, int act_dtype, long long i) {

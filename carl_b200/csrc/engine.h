@@ -61,7 +61,7 @@ struct HostMirrors {  // mapped (page-locked) host result buffers of one zero-co
 int classic_step(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm = nullptr);
 int classic_step_checked(const carlb_env* env, const void* actions, int act_dtype, cudaStream_t st, const HostMirrors* hm,
                          const StepCheck& chk);
-int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk);
+int classic_step_undo(const carlb_env* env, cudaStream_t st, const StepCheck& chk, const HostMirrors* hm = nullptr);
 int classic_rollout(const carlb_env* env, int n_steps, uint64_t policy_seed, uint32_t step_base, const void* actions,
                     int act_dtype, const carlb_traj_t* traj, cudaStream_t st);
 int classic_mixed_step(carlb_env* const* envs, const void* const* actions, const int* act_dtypes, int n_handles,

@@ -286,14 +286,20 @@ def test_in_kernel_action_check_rolls_the_step_back(kind):
     for t in range(20):
         acts = rng.integers(0, n_act, size=n)
         if t in (6, 13):  # the truncation step (every env resets) and an ordinary one
-            before = (a_env.state.clone(), a_env._elapsed.clone(), a_env._rng.clone(), a_env._sbt.clone())
+            before = (a_env.state.clone(), a_env._elapsed.clone(), a_env._rng.clone(), a_env._sbt.clone(),
+                      a_env._obs.clone(), a_env._reward.clone(), a_env._terminated.clone(), a_env._truncated.clone())
+            host_before = [np.array(x) for x in (oa["obs"], ra, ta, tra)] if t > 0 else None
             pinned[...] = acts
             pinned[n // 2] = n_act if t == 6 else -1
             with pytest.raises(AssertionError, match="invalid action"):
                 a_env.step(pinned)
-            after = (a_env.state, a_env._elapsed, a_env._rng, a_env._sbt)
+            after = (a_env.state, a_env._elapsed, a_env._rng, a_env._sbt, a_env._obs, a_env._reward, a_env._terminated,
+                     a_env._truncated)
             for x, y in zip(before, after):
                 assert torch.equal(x, y)
+            if host_before is not None:  # the caller's arrays of the previous step show that step again
+                for x, y in zip(host_before, (oa["obs"], ra, ta, tra)):
+                    np.testing.assert_array_equal(x, y)
         pinned[...] = acts
         oa, ra, ta, tra, _ = a_env.step(pinned)
         ob, rb, tb, trb, _ = b_env.step(acts)  # pageable -> host check + staged copy

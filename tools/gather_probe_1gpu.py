@@ -64,7 +64,15 @@ def main():
         graph.replay()
     e1.record(stream)
     torch.cuda.synchronize()
-    print(json.dumps({"mode": mode, "debug": os.environ.get("CARLB_GATHER_DEBUG"), "block": os.environ.get("CARLB_ROLLOUT_BLOCK"), "pdl": os.environ.get("CARLB_ROLLOUT_PDL"), "T": T,
+    check = None
+    if g is not None:  # the gathered tensor must be the handle's observation (lag 1 in pipelined mode, lag 0 in sync mode)
+        g.resync()
+        prev = env._obs.clone()
+        launch(stream.cuda_stream)
+        torch.cuda.synchronize()
+        check = bool(torch.equal(g.gather(lag=1), prev)) and bool(torch.equal(g.gather(lag=0), env._obs))
+        assert check, "gathered tensor != observation"
+    print(json.dumps({"mode": mode, "gather_ok": check, "debug": os.environ.get("CARLB_GATHER_DEBUG"), "block": os.environ.get("CARLB_ROLLOUT_BLOCK"), "pdl": os.environ.get("CARLB_ROLLOUT_PDL"), "T": T,
                       "us_per_launch": e0.elapsed_time(e1) * 1e3 / (300 * 32)}))
 
 
