@@ -23,7 +23,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 # Brax: parity first -- without FMA contraction the float32 kernel reproduces the float32 restatement
 # of the reference arithmetic to ~1e-6 per env-step (with contraction the stiff joint springs amplify
 # the different rounding to a few 1e-5; tests/test_brax_parity_gpu.py measures both against a float64
-# yardstick). CARLB_BRAX_FMAD=1 builds the contracted variant for performance experiments.
+# yardstick). The FMA-contracted variant is built next to it (brax_fma.cu) and selected per handle
+# (carlb_brax_set_arithmetic / CARLBraxEnv(arithmetic="fma")).
 UNITS = [
     ("abi.cu", []),
     ("classic.cu", ["-fmad=false"]),

@@ -583,6 +583,12 @@ __global__ void __launch_bounds__(kBlock + 32) rollout_kernel(const __grid_const
   }
   float o_fin[Traits<KIND>::D];
   if (i < seg.n) {
+    // the env's PCG64 words are first needed a few steps into the loop (batched reset pre-generation: every warp
+    // refills once per launch); pulling them towards L1 now takes their L2 round trip off that pass
+    if (seg.autoreset != CARLB_AUTORESET_NONE) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) asm volatile("prefetch.global.L1 [%0];" ::"l"(seg.rng + (size_t)r * seg.n + i));
+    }
     bool clean = seg.autoreset != CARLB_AUTORESET_NONE;  // warp-uniform choice of the specialised loop
     if (KIND == KIND_CARTPOLE) clean = __all_sync(__activemask(), clean && seg.sbt[i] == 0);
     uint64_t* sv_slot = &sv_sh[threadIdx.x];
