@@ -776,6 +776,22 @@ def run_gpu_arm(args):
     if gather_check is not None:
         out["gather_check"] = gather_check
     out.update(extra)
+    # what the parity claims rest on; "unpinned" = no reference-run vector exists or can be generated here
+    out["parity"] = {
+        "pinned_by_published_known_answers": ["CARLCartPole step + reset (gymnasium known answers)", "ContextSampler stream "
+                                              "(reference notebooks)", "PCG64 / SeedSequence reset streams (numpy)",
+                                              "Philox4x32-10, threefry2x32 (Random123 KATs)",
+                                              "Brax reset stream: JAX PRNGKey / split / uniform / normal (JAX documentation outputs)"],
+        "anchored_to_independent_physics": ["CARLPendulum (uniform-rod period, torque response, O(dt) energy drift)",
+                                            "CARLAcrobot (one step == RK4 of the textbook manipulator equations, 1e-10)",
+                                            "CARLMountainCar / Continuous (valley period of the symplectic map)",
+                                            "Brax spring pipeline: free fall closed form (dt x n_frames, gravity), momentum "
+                                            "conservation, cart-pendulum frequency; geometry by CARL's own mass defaults"],
+        "unpinned": ["Pendulum / Acrobot / MountainCar conventions no textbook fixes (clip order, reward constants): from SURVEY App. A",
+                     "all seven Brax bodies against real brax 0.12.1 (not installable: profiles/r02a_pip_install_attempt.txt); "
+                     "kernel-vs-oracle parity is exact to the stated tolerances, oracle-vs-Brax is not verifiable offline"],
+        "gpu_tests": "tests -m gpu: CUDA through the C ABI vs the CPU oracle (profiles/r02i_pytest_gpu.txt)",
+    }
     done_counts = committed_done_mask_counts()
     if done_counts is not None:
         out["done_mask_mismatches_fp32"] = done_counts

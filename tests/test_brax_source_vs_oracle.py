@@ -259,3 +259,48 @@ def test_free_flight_conserves_momentum(hc, body):
     p1, l1 = momenta(st)
     np.testing.assert_allclose(p1 - p0, want_dp, rtol=0, atol=3e-3)
     np.testing.assert_allclose((l1 - l0)[:, 2], 0.0, atol=3e-3)
+
+
+@pytest.mark.parametrize("body", ["ant", "halfcheetah", "hopper", "walker2d"])
+def test_free_fall_follows_the_semi_implicit_euler_closed_form(hc, body):
+    """Independent anchor for the integrator, the env's substep schedule and the gravity context: a body released at
+    rest in its rest pose, far above the ground, with zero actions, falls rigidly -- after one env-step of n_frames
+    substeps of length dt every link has dropped by g dt^2 n (n + 1) / 2 and moves at g dt n (semi-implicit Euler:
+    v += g dt; x += v dt), with dt and n_frames the values brax documents for the spring backend (Ant 0.005 x 10,
+    Halfcheetah 0.003125 x 16, Hopper / Walker2d 0.002 x 4). Oracle (float64 and float32) and kernel source."""
+    sysd = bs.SYSTEMS[body]
+    dt_n = {"ant": (0.005, 10), "halfcheetah": (0.003125, 16), "hopper": (0.002, 4), "walker2d": (0.002, 4)}[body]
+    n = 4
+    rng = np.random.default_rng(3)
+    ctx = random_ctx(sysd, n, rng)          # per-env gravity in [-15, -5], random masses
+    ctx[:, 3] = 0.0                          # no angular damping
+    nq = sysd["n_q"]
+    q = np.tile(sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + nq].astype(np.float32), (n, 1))
+    zi = 2 if body == "ant" else 1           # free root: q = (x, y, z, quat...); planar root: (x, z, pitch)
+    q[:, zi] += 40.0
+    qd = np.zeros((n, sysd["n_qd"]), np.float32)
+    a = np.zeros((n, sysd["n_act"]), np.float32)
+    g = ctx[:, 0].astype(np.float64)
+    dt, nf = dt_n
+    drop = g * dt * dt * nf * (nf + 1) / 2
+    speed = g * dt * nf
+    L = sysd["n_links"]
+
+    def link_z(state):
+        rows = np.array(state, dtype=np.float64)[:, :13 * L].reshape(n, L, 13)  # a copy: the oracle steps in place
+        return rows[..., 2], rows[..., 9]   # COM z, COM vz of every link
+
+    for f64, tol in ((True, 1e-9), (False, 2e-5)):
+        ora = OracleBraxEnv(sysd, ctx, autoreset=False, f64=f64)
+        ora.init_from_q(q, qd)
+        z0, _ = link_z(ora.state)
+        ora.step(a)
+        z1, vz1 = link_z(ora.state)
+        np.testing.assert_allclose(z1 - z0, np.repeat(drop[:, None], L, 1), rtol=0, atol=max(tol, 1e-7 * 40))
+        np.testing.assert_allclose(vz1, np.repeat(speed[:, None], L, 1), rtol=0, atol=max(tol, 1e-7))
+    st, ob = hc.init(sysd, q, qd)
+    z0, _ = link_z(st)
+    hc.step(sysd, st, ctx, a, np.zeros(n, np.int32), 0, 0, st.copy(), ob.copy())
+    z1, vz1 = link_z(st)
+    np.testing.assert_allclose(z1 - z0, np.repeat(drop[:, None], L, 1), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(vz1, np.repeat(speed[:, None], L, 1), rtol=0, atol=2e-5)
