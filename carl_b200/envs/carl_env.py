@@ -333,6 +333,9 @@ class CARLEnv(abc.ABC):
         self._ctx_obs_cache = None
         self._ctx_obs_host_cache = None
         self._ids_view = None
+        if getattr(self, "_async_cache", None) is not None:  # per-part context views of the split-batch API
+            self._async_cache["ctx"] = [None] * len(self._async_cache["ctx"])
+            self._async_cache["ids"] = [None] * len(self._async_cache["ctx"])
 
     # -------------------------------------------------------------------- spaces
     def get_observation_space(self, obs_context_feature_names: list[str] | None = None):
@@ -666,11 +669,17 @@ class CARLEnv(abc.ABC):
             io = self._ensure_host_io()
             k = self._async_parts
             bounds = [self.part_range(p) for p in range(k)]
+            streams = [torch.cuda.Stream(self.device) for _ in range(k)]
+            p = io["ptrs"]
             self._async_cache = dict(
-                streams=[torch.cuda.Stream(self.device) for _ in range(k)], bounds=bounds,
+                streams=streams, bounds=bounds,
+                # everything the per-call path needs, resolved once
+                begin=self._lib.carlb_env_step_host_begin, end=self._lib.carlb_env_step_host_end,
+                tail=[(p[1], p[2], p[3], p[4], s_.cuda_stream) for s_ in streams],
+                n_act=self._info.n_actions if (self._validate_actions and self._info.act_discrete) else 0,
                 views=[(io["np_obs"][lo:hi], io["np_reward"][lo:hi], io["np_term"][lo:hi], io["np_trunc"][lo:hi])
                        for lo, hi in bounds],
-                ctx=[None] * k)
+                ctx=[None] * k, ids=[None] * k)
         return self._async_cache
 
     def step_async(self, action: Any, part: int | None = None) -> None:
@@ -690,39 +699,41 @@ class CARLEnv(abc.ABC):
                 self.step_async(flat[lo:hi].reshape((hi - lo,) + tuple(a.shape[1:])), part=p_)
             return
         lo, hi = st["bounds"][part]
-        a = np.asarray(action)
-        self._check_actions(hi - lo, tuple(a.shape))
+        a = action if type(action) is np.ndarray else np.asarray(action)
+        adim = self._info.act_dim
+        if not (a.shape == (hi - lo,) and adim == 1) and a.shape != (hi - lo, adim):
+            self._check_actions(hi - lo, tuple(a.shape))
         if self._info.act_discrete:
             if a.dtype not in _NP_ACT or a.dtype == np.float32:
                 a = a.astype(np.int64)
         elif a.dtype != np.float32:
             a = a.astype(np.float32)
-        flat = np.ascontiguousarray(a).reshape(-1)
-        n_act = self._info.n_actions if (self._validate_actions and self._info.act_discrete) else 0
-        src = flat.ctypes.data
-        if not hostmem.is_pinned(src, flat.nbytes):
+        if not a.flags.c_contiguous:
+            a = np.ascontiguousarray(a)
+        n_act = st["n_act"]
+        src = a.ctypes.data
+        if not hostmem.is_pinned(src, a.nbytes):
             # pageable actions: one native pass copies them into the part's slice of the page-locked staging block
             # (and range-checks them; the kernel checks again, which costs nothing)
-            adim = max(1, self._info.act_dim)
+            adim = max(1, adim)
             dst = io["staged"][a.dtype][lo * adim:hi * adim]
-            if self._lib.carlb_stage_actions(dst.ctypes.data, src, flat.size, _NP_ACT[a.dtype], n_act) != 0:
+            if self._lib.carlb_stage_actions(dst.ctypes.data, src, a.size, _NP_ACT[a.dtype], n_act) != 0:
                 raise AssertionError(_native.last_error())
             src = dst.ctypes.data
-        p = io["ptrs"]
-        rc = self._lib.carlb_env_step_host_begin(self._handle, part, self._async_parts, src, _NP_ACT[a.dtype], n_act,
-                                                 p[1], p[2], p[3], p[4], st["streams"][part].cuda_stream)
-        _native.check(rc)
+        rc = st["begin"](self._handle, part, self._async_parts, src, _NP_ACT[a.dtype], n_act, *st["tail"][part])
+        if rc != 0:
+            _native.check(rc)
         self._async_pending[part] = True
 
     def step_wait(self, part: int | None = None):
         """Results of the step ``step_async`` enqueued for ``part`` (views of the page-locked result arrays
         restricted to the part's envs) -- or, with ``part=None``, of the whole batch once every part has landed."""
         st = self._async_state()
-        parts = range(self._async_parts) if part is None else [part]
+        parts = range(self._async_parts) if part is None else (part,)
         for p_ in parts:
             if not self._async_pending[p_]:
                 raise RuntimeError(f"step_wait: part {p_} has no step in flight")
-            rc = self._lib.carlb_env_step_host_end(self._handle, p_)
+            rc = st["end"](self._handle, p_)
             self._async_pending[p_] = False
             if rc != 0:
                 msg = _native.last_error()
@@ -740,10 +751,11 @@ class CARLEnv(abc.ABC):
                 st["ctx"][part] = full if self.num_envs == 1 else {k: v[lo:hi] for k, v in full.items()}
             else:
                 st["ctx"][part] = full[lo:hi]
+        if st["ids"][part] is None:
+            ids = self.context_id
+            st["ids"][part] = ids if np.isscalar(ids) else ids[lo:hi]
         obs, rew, term, trunc = st["views"][part]
-        ids = self.context_id
-        return ({"obs": obs, "context": st["ctx"][part]}, rew, term, trunc,
-                {"context_id": ids if np.isscalar(ids) else ids[lo:hi]})
+        return {"obs": obs, "context": st["ctx"][part]}, rew, term, trunc, {"context_id": st["ids"][part]}
 
     def _context_obs_host(self):
         if self._ctx_obs_host_cache is None:  # contexts only change at reset / context_id assignment

@@ -62,3 +62,8 @@ def test_gpu_arm_prints_the_contract_line():
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
     assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(d["roofline"])
     assert 0 < d["roofline"]["frac"] < 1.5
+    # the timed region is a train of passes of the K-step plan, not one launch on an idle stream
+    assert d["config"]["passes"] >= 100 and d["gpu_launches"] == d["config"]["passes"] * d["config"]["launches_per_pass"]
+    # synchronous gym-style call beside the split-batch headline; float64 leg; what parity rests on
+    assert d["e2e_sync"]["value"] > 0 and d["e2e"]["parts"] == 2 and d["value_f64"]["value"] > 0
+    assert "unpinned" in d["parity"] and "pinned_by_published_known_answers" in d["parity"]

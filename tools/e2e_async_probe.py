@@ -65,10 +65,8 @@ if __name__ == "__main__":
     out = {}
     for label, mode, env in [("sync_poll", "sync", {"CARLB_HOST_POLL": "1"}), ("sync_streamsync", "sync", {"CARLB_HOST_POLL": "0"}),
                              ("async_1", "async_1", {}), ("async_2", "async_2", {}), ("async_3", "async_3", {}),
-                             ("async_4", "async_4", {}), ("async_8", "async_8", {}),
-                             ("sync_ce", "sync", {"CARLB_HOST_TRANSPORT": "ce"}), ("async_1_ce", "async_1", {"CARLB_HOST_TRANSPORT": "ce"}),
-                             ("async_2_ce", "async_2", {"CARLB_HOST_TRANSPORT": "ce"}), ("async_3_ce", "async_3", {"CARLB_HOST_TRANSPORT": "ce"}),
-                             ("async_4_ce", "async_4", {"CARLB_HOST_TRANSPORT": "ce"})]:
+                             ("async_4", "async_4", {}), ("async_8", "async_8", {})]:
+
         e = dict(os.environ)
         e.update(env)
         p = subprocess.run([sys.executable, os.path.abspath(__file__), mode], capture_output=True, text=True, env=e, timeout=120)
