@@ -790,7 +790,7 @@ def run_gpu_arm(args):
         "unpinned": ["Pendulum / Acrobot / MountainCar conventions no textbook fixes (clip order, reward constants): from SURVEY App. A",
                      "all seven Brax bodies against real brax 0.12.1 (not installable: profiles/r02a_pip_install_attempt.txt); "
                      "kernel-vs-oracle parity is exact to the stated tolerances, oracle-vs-Brax is not verifiable offline"],
-        "gpu_tests": "tests -m gpu: CUDA through the C ABI vs the CPU oracle (profiles/r02i_pytest_gpu.txt)",
+        "gpu_tests": "tests -m gpu: CUDA through the C ABI vs the CPU oracle (profiles/r02o_pytest_gpu.txt)",
     }
     done_counts = committed_done_mask_counts()
     if done_counts is not None:
