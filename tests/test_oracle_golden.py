@@ -16,6 +16,30 @@ def test_seeding_recipe_reproduces_published_reset_vectors():
         np.testing.assert_allclose(got, np.asarray(GOLD[key], dtype=np.float32), rtol=0, atol=1e-8)
 
 
+def test_published_pendulum_and_mountaincar_resets_pin_the_discarded_gymnasium_draws():
+    """Every CARL reset first lets gymnasium's own reset draw (and discards the result): Pendulum-v1 draws (theta,
+    thetadot) in ONE uniform call with high = (pi, 1), MountainCar-v0 one U(-0.6, -0.4). The published reset
+    observations pin those draw counts and ranges; the oracle's CARL state is what the SAME generator yields next."""
+    for seed, key in ((0, "pendulum_reset_seed0"), (42, "pendulum_reset_seed42")):
+        g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed)))
+        th, thd = g.uniform(low=[-np.pi, -1.0], high=[np.pi, 1.0])
+        np.testing.assert_allclose(np.array([np.cos(th), np.sin(th), thd], np.float32), np.asarray(GOLD[key], np.float32),
+                                   rtol=0, atol=1e-7)
+        assert KINDS["pendulum"]["gym_draws"] == 2
+        env = OracleClassicEnv("pendulum", np.array([DEFAULTS["pendulum"]]))
+        env.reset(seed=seed)
+        want = np.array([g.uniform(high=np.pi), g.uniform(high=1.0)], dtype=np.float32)  # CARL's own two draws follow
+        np.testing.assert_array_equal(env.state[0], want.astype(np.float64))
+    g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(42)))
+    pos = g.uniform(low=-0.6, high=-0.4)
+    np.testing.assert_allclose(np.array([pos, 0.0], np.float32), np.asarray(GOLD["mountaincar_reset_seed42"], np.float32),
+                               rtol=0, atol=1e-7)
+    assert KINDS["mountaincar"]["gym_draws"] == 1
+    env = OracleClassicEnv("mountaincar", np.array([DEFAULTS["mountaincar"]]))
+    env.reset(seed=42)
+    np.testing.assert_array_equal(env.state[0], [g.uniform(low=-0.6, high=-0.4), g.uniform(low=0.0, high=0.0)])
+
+
 def test_oracle_cartpole_step_known_answer():
     env = OracleClassicEnv("cartpole", np.array([DEFAULTS["cartpole"]]))
     g = np.random.Generator(np.random.PCG64(np.random.SeedSequence(0)))

@@ -21,8 +21,8 @@ for f in sorted(glob.glob('gpurun_out/scale_n*.json'), key=lambda s:int(re.finda
     except Exception as e: print(f,'unparsable',e); continue
     n=d['n_gpus']
     if n==1: v1=d
-    def eff(a,b): return a/(n*b) if b else None
-    print(f"N={n} value {d['value']:.4e} eff {eff(d['value'],v1['value']):.3f} pass_ms {d['config']['pass_ms_median']:.4f} | step_api {d['step_api']['us_per_launch']:.2f} us | e2e {d['e2e']['value']:.3e} ({d['e2e']['ms_per_step']*1e3:.1f} us) | gather_check {d.get('gather_check',{}).get('equal')}")
+    def eff(a,b): return a/(n*b) if b else float('nan')
+    print(f"N={n} value {d['value']:.4e} eff {eff(d['value'],v1 and v1['value']):.3f} pass_ms {d['config']['pass_ms_median']:.4f} | step_api {d['step_api']['us_per_launch']:.2f} us | e2e {d['e2e']['value']:.3e} ({d['e2e']['ms_per_step']*1e3:.1f} us) | gather_check {d.get('gather_check',{}).get('equal')}")
     a=d.get('ant_8192'); c=d.get('config5_halfcheetah_hopper')
-    if a: print(f"     ant {a['value']:.4e} (eff {eff(a['value'],v1['ant_8192']['value']):.3f}) fma {a['value_fma']:.4e} step {a['step_api']['us_per_launch']:.1f} us | config5 {c['value']:.4e} ({c['us_per_step']:.1f} us/step)")
+    if a: print(f"     ant {a['value']:.4e} (eff {eff(a['value'],v1 and v1['ant_8192']['value']):.3f}) fma {a['value_fma']:.4e} step {a['step_api']['us_per_launch']:.1f} us | config5 {c['value']:.4e} ({c['us_per_step']:.1f} us/step)")
 PY
