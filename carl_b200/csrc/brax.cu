@@ -17,6 +17,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "engine.h"
 #include "physics_brax.h"
 
@@ -90,6 +92,23 @@ struct EnvScratch {
   float obs[64];
   float ctx[24];                     // this env's context scalars (gravity, friction, ..., link masses)
 };
+// The humanoids' scratch (3.6 KB): room for the 244-entry observation and 17 actions, plus the effective link
+// masses that their observation and centre-of-mass reward read. Same leading fields as EnvScratch.
+struct EnvScratchH {
+  float ls[MAX_LINKS * LINK_WORDS];
+  float pw[MAX_LINKS * 6];
+  float org[MAX_LINKS * 3];
+  float co[MAX_POINTS * 7];
+  float lc[MAX_LINKS * 6];
+  float q[MAX_Q];
+  float qd[MAX_Q];
+  float act[MAX_ACT];
+  float obs[MAX_OBS_LARGE];
+  float ctx[24];
+  float meff[MAX_LINKS];             // mass^(1 - spring_mass_scale) per link
+};
+template <int M> struct ScratchOf { typedef EnvScratch type; };
+template <> struct ScratchOf<MODE_HUMANOID> { typedef EnvScratchH type; };
 
 // ---- TMA bulk copy + mbarrier (PTX) ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -178,11 +197,14 @@ struct LaneCtx {
   LinkConst lc;      // loop invariants of my link
   V3 anchor_p;       // my joint's anchor in the parent link frame (table-only)
   int jflags;        // JointFlags of my joint (table-only)
+  const float* dt;   // my link's dof row (stacked hinges: humanoid kernels only)
 };
 
 // n_frames spring substeps for the sub-envs of this warp. `s` is this lane's link.
-template <int E, bool SP>
-__device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, EnvScratch& w, LinkState& s, float tau) {
+template <int E, int M>
+__device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, typename ScratchOf<M>::type& w, LinkState& s,
+                                               float tau, float tau1 = 0.0f, float tau2 = 0.0f) {
+  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
   constexpr int LPE = Lanes<E>::LPE;
   const float dt = sys[H_DT];
   const int n_pass = (c.P + LPE - 1) / LPE;
@@ -195,7 +217,8 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
     if (c.is_link && c.type != TYPE_FREE) {
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve<SP>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags);
+      const JointOut jo = joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p,
+                                                c.jflags, c.dt, tau1, tau2);
       wr = jo.child;
       float* pw = w.pw + c.sl * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
@@ -265,10 +288,13 @@ struct RootFacts {
   V3 site;             // pendulum tip (world) / reacher: fingertip - target
 };
 
-// SP: the body may have slide joints / an env-specific observation or outcome (inverted pendulums, reacher)
-template <int E, bool SP>
-__device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, EnvScratch& w, const LinkState& s) {
+// M == MODE_SPECIAL: the body may have slide joints / an env-specific observation or outcome (inverted pendulums,
+// reacher); M == MODE_HUMANOID: stacked hinges and the humanoids' observation (brax.envs.humanoid._get_obs)
+template <int E, int M>
+__device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, typename ScratchOf<M>::type& w,
+                                                 const LinkState& s) {
   constexpr int LPE = Lanes<E>::LPE;
+  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
   if (c.is_link) write_link(w.ls, c.sl, s);
   __syncwarp();
   const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
@@ -283,8 +309,8 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
     } else {
       const bool world_parent = c.parent < 0;
       const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve<SP>(sys, c.lt, s, world_parent, c.plt, ps, 0.0f);
-      const int nd = SP ? type_ndof(c.type) : (c.type == TYPE_PLANAR ? 3 : 1);
+      const JointOut jo = joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, 0.0f, 1.0f, c.dt);
+      const int nd = (SP || HU) ? type_ndof(c.type) : (c.type == TYPE_PLANAR ? 3 : 1);
       for (int k = 0; k < nd; ++k) {
         w.q[qi + k] = jo.q[k];
         w.qd[qdi + k] = jo.qd[k];
@@ -300,7 +326,32 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   if (SP && kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
     r.site = site_position(sys, read_link(w.ls, (int)sys[H_SITE_LINK]), read_link(w.ls, kind == ENV_REACHER ? 2 : 0));
   }
-  if (SP && (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER)) {
+  float com_x = 0.0f;
+  if constexpr (HU) {
+    // q[2:] | qd | cinert (10 per link) | cvel (6 per link) | actuator torques in qd layout
+    const int n0 = (nq - 2) + nqd;
+    if (c.sl < LPE)
+      for (int i = c.sl; i < n0; i += LPE) w.obs[i] = i < nq - 2 ? w.q[2 + i] : w.qd[i - (nq - 2)];
+    V3 com;
+    const float msum = body_com(w.ls, w.meff, c.L, com);  // every lane: the same sums in the same order
+    com_x = com.x;
+    if (c.is_link) {
+      const float m = w.meff[c.sl];
+      link_cinert(sys, c.lt, s, m, com, w.obs + n0 + 10 * c.sl);
+      link_cvel(s, m, msum, w.obs + n0 + 10 * c.L + 6 * c.sl);
+      float* qf = w.obs + n0 + 16 * c.L;
+      const int qdi = (int)c.lt[L_QDIDX];
+      if (c.type == TYPE_FREE) {
+        for (int k = 0; k < 6; ++k) qf[qdi + k] = 0.0f;
+      } else {
+        const int a1 = (int)c.dt[D_ACT1], a2 = (int)c.dt[D_ACT2];
+        const float lo = c.lt[L_CTRL_LO], hi = c.lt[L_CTRL_HI];
+        qf[qdi] = c.act >= 0 ? c.lt[L_GEAR] * fminf(fmaxf(w.act[c.act], lo), hi) : 0.0f;
+        if (c.type == TYPE_HINGE2 || c.type == TYPE_HINGE3) qf[qdi + 1] = a1 >= 0 ? c.dt[D_GEAR1] * fminf(fmaxf(w.act[a1], lo), hi) : 0.0f;
+        if (c.type == TYPE_HINGE3) qf[qdi + 2] = a2 >= 0 ? c.dt[D_GEAR2] * fminf(fmaxf(w.act[a2], lo), hi) : 0.0f;
+      }
+    }
+  } else if (SP && (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER)) {
     const int D = kind == ENV_REACHER ? 11 : 8;
     if (c.sl < LPE)
       for (int i = c.sl; i < D; i += LPE) w.obs[i] = special_obs_entry(kind, i, w.q, w.qd, r.site);
@@ -332,21 +383,23 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   const LinkState s0 = read_link(w.ls, 0);
   const V3 o0 = link_origin(s0, lt0);
   r.x = o0.x;
+  if (HU && kind == ENV_HUMANOID) r.x = com_x;  // brax.envs.humanoid: velocity of the body's centre of mass
   r.z = o0.z;
   r.angle = ((int)lt0[L_TYPE] == TYPE_PLANAR) ? w.q[2] : 0.0f;
   return r;
 }
 
 // Env layer of brax.envs.{ant,half_cheetah,hopper}.step after the pipeline advanced.
-template <bool SP>
+template <int M>
 __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& before, const RootFacts& after,
                                             float act_sq_sum, float& reward, bool& done) {
   const float dt_env = sys[H_DT] * sys[H_N_FRAMES];
   const float x_velocity = (after.x - before.x) / dt_env;
   const float forward_reward = sys[H_FORWARD_WEIGHT] * x_velocity;
   const int kind = (int)sys[H_ENV];
+  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
   bool healthy = true;
-  if (kind == ENV_ANT) {
+  if (kind == ENV_ANT || (HU && kind == ENV_HUMANOID)) {
     healthy = !(after.z < sys[H_HEALTHY_Z_MIN]) && !(after.z > sys[H_HEALTHY_Z_MAX]);
   } else if (kind == ENV_HOPPER) {
     const bool hz = (sys[H_HEALTHY_Z_MIN] < after.z) && (after.z < sys[H_HEALTHY_Z_MAX]);
@@ -360,20 +413,24 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
   done = (sys[H_TERMINATE] > 0.0f) && !healthy;
   if (SP && kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
+  if (HU && kind == ENV_HUMANOIDSTANDUP) {  // brax.envs.humanoidstandup.step: uph_cost + 1 - quad_ctrl_cost, never done
+    reward = (after.z - 0.0f) / dt_env + sys[H_HEALTHY_REWARD] - ctrl_cost;
+    done = false;
+  }
 }
 
-template <int W, int E>
+template <int W, int E, int M = MODE_LOCO>
 struct SmemLayoutT {
   float sys[TABLE_FLOATS];
-  EnvScratch env[W * E];
+  typename ScratchOf<M>::type env[W * E];
   uint64_t bar;
 };
 
 // Per-lane setup shared by the step and reset kernels: lane mapping, context staging (one strided
 // coalesced load of the env's context row into its scratch, then shared-memory broadcast reads),
 // loop invariants.
-template <int E>
-__device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg& seg, EnvScratch& w, int env, bool active,
+template <int E, class SC>
+__device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg& seg, SC& w, int env, bool active,
                                                  int sub, int sl, bool stock_contact) {
   constexpr int LPE = Lanes<E>::LPE;
   LaneCtx c;
@@ -393,6 +450,7 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
   c.stock_contact = stock_contact;
   c.anchor_p = parent_anchor(c.lt);
   c.jflags = joint_flags(c.lt);
+  c.dt = dof_tab(sys, l);
   if (active && sl < LPE) {
     const float* row = seg.ctx + (size_t)env * seg.n_ctx;
     for (int i = sl; i < seg.n_ctx; i += LPE) w.ctx[i] = row[i];
@@ -405,6 +463,11 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
     float* p = w.lc + sl * 6;
     p[0] = c.lc.inv_mass; p[1] = c.lc.inv_idiag.x; p[2] = c.lc.inv_idiag.y; p[3] = c.lc.inv_idiag.z;
     p[4] = c.lc.vel_decay; p[5] = c.lc.ang_decay;
+    if constexpr (std::is_same<SC, EnvScratchH>::value) w.meff[sl] = eff_mass(w.ctx[C_MASS0 + l], sys);
+  }
+  if constexpr (std::is_same<SC, EnvScratchH>::value) {
+    if (active && sl < LPE)
+      for (int i = sl; i < MAX_ACT; i += LPE) w.act[i] = 0.0f;  // the observation reads the actuator torques: none yet
   }
   __syncwarp();
   return c;
@@ -414,8 +477,8 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
 // One env-step per sub-env: [AutoReset zeroing] -> n_frames substeps -> obs/reward/done ->
 // EpisodeWrapper truncation -> AutoReset (state/obs replaced by the stored first ones where done).
 // Every __syncwarp() is reached by all 32 lanes: per-env conditions only predicate memory traffic.
-template <int W, int E, bool SP>
-__device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W, E>& sm, const float* actions, int n_steps,
+template <int W, int E, int M>
+__device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W, E, M>& sm, const float* actions, int n_steps,
                                                uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& traj,
                                                int stock_contact, unsigned int gseq) {
   constexpr int LPE = Lanes<E>::LPE;
@@ -425,7 +488,8 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
   const int env = (blockIdx.x * W + warp) * E + sub;
   const bool active = lane_ok && env < seg.n;
   const float* sys = sm.sys;
-  EnvScratch& w = sm.env[warp * E + sub];
+  constexpr bool HU = M == MODE_HUMANOID;
+  typename ScratchOf<M>::type& w = sm.env[warp * E + sub];
   const LaneCtx c = make_lane_ctx<E>(sys, seg, w, env, active, sub, lane_ok ? sl : LPE, stock_contact != 0);
   const int words = seg.state_words, D = seg.obs_dim, A = seg.act_dim;
   float* state_row = seg.state + (size_t)(active ? env : 0) * words;
@@ -438,11 +502,28 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
   const uint64_t gid = (uint64_t)(seg.global_offset + env);
   float reward = 0.0f;
   bool done = false;
-  RootFacts before = compute_obs<E, SP>(sys, c, w, s);
+  RootFacts before = compute_obs<E, M>(sys, c, w, s);
   for (int t = 0; t < n_steps; ++t) {
     // actions of this step: given tensor [n][A] (single step) / [K][n][A] (rollout) or Philox policy
     float a = 0.0f;
-    if (active && c.sl < A) {
+    if constexpr (HU) {
+      // 17 actions for 16 (or 32) lanes: a strided loop; the trajectory copy is stored as they are read
+      if (active && c.sl < LPE) {
+        for (int k = c.sl; k < A; k += LPE) {
+          float ak;
+          if (actions != nullptr) {
+            ak = actions[((size_t)t * seg.n + env) * A + k];
+          } else {
+            const Philox4 r = philox4x32_10((uint32_t)gid, (uint32_t)(gid >> 32), step_base + (uint32_t)t,
+                                            0x42524158u + (uint32_t)k, (uint32_t)policy_seed, (uint32_t)(policy_seed >> 32));
+            ak = sys[H_ACT_SCALE] * (2.0f * u32_to_unit_float(r.v[0]) - 1.0f);
+          }
+          w.act[k] = ak;
+          if (traj.actions != nullptr && (n_steps > 1 || traj.obs != nullptr))
+            static_cast<float*>(traj.actions)[((size_t)t * seg.n + env) * A + k] = ak;
+        }
+      }
+    } else if (active && c.sl < A) {
       if (actions != nullptr) {
         a = actions[((size_t)t * seg.n + env) * A + c.sl];
       } else {
@@ -455,11 +536,16 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
     __syncwarp();
     float act_sq = 0.0f;
     for (int k = 0; k < A; ++k) act_sq += w.act[k] * w.act[k];  // jp.sum(jp.square(action)), in order
-    float tau = 0.0f;
+    float tau = 0.0f, tau1 = 0.0f, tau2 = 0.0f;
     if (c.is_link && c.act >= 0) tau = c.lt[L_GEAR] * fminf(fmaxf(w.act[c.act], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
-    pipeline_steps<E, SP>(sys, c, w, s, tau);
-    const RootFacts after = compute_obs<E, SP>(sys, c, w, s);
-    env_outcome<SP>(sys, before, after, act_sq, reward, done);
+    if constexpr (HU) {  // dofs 1 and 2 of a stacked hinge
+      const int a1 = (int)c.dt[D_ACT1], a2 = (int)c.dt[D_ACT2];
+      if (c.is_link && a1 >= 0) tau1 = c.dt[D_GEAR1] * fminf(fmaxf(w.act[a1], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
+      if (c.is_link && a2 >= 0) tau2 = c.dt[D_GEAR2] * fminf(fmaxf(w.act[a2], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
+    }
+    pipeline_steps<E, M>(sys, c, w, s, tau, tau1, tau2);
+    const RootFacts after = compute_obs<E, M>(sys, c, w, s);
+    env_outcome<M>(sys, before, after, act_sq, reward, done);
     // EpisodeWrapper: steps += 1; done = where(steps >= episode_length, 1, done)
     el += 1;
     if (seg.max_steps > 0 && el >= seg.max_steps) done = true;
@@ -478,7 +564,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
       if (do_reset) s = read_link(w.ls, c.is_link ? c.sl : 0);
       __syncwarp();
       // root facts of the restored state (also recomputes the unchanged obs of the other sub-envs)
-      const RootFacts fresh = compute_obs<E, SP>(sys, c, w, s);
+      const RootFacts fresh = compute_obs<E, M>(sys, c, w, s);
       if (do_reset) {
         before = fresh;
         el = 0;
@@ -491,7 +577,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
       const size_t row = (size_t)t * seg.n + env;
       if (traj.obs != nullptr && c.sl < LPE)
         for (int i = c.sl; i < D; i += LPE) traj.obs[row * D + i] = w.obs[i];
-      if (traj.actions != nullptr && c.sl < A) static_cast<float*>(traj.actions)[row * A + c.sl] = a;
+      if (!HU && traj.actions != nullptr && c.sl < A) static_cast<float*>(traj.actions)[row * A + c.sl] = a;
       if (c.sl == 0) {
         if (traj.reward != nullptr) traj.reward[row] = reward;
         if (traj.done != nullptr) traj.done[row] = done ? 1 : 0;
@@ -533,28 +619,29 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
   }
 }
 
-template <int W, int E, bool SP>
+template <int W, int E, int M>
 __global__ void __launch_bounds__(W * 32, W == 4 ? (E >= 3 ? 5 : 4) : 2) brax_step_kernel(const __grid_constant__ BraxSeg seg,
                                                                           const float* actions, int n_steps,
                                                                           uint64_t policy_seed, uint32_t step_base,
                                                                           const carlb_traj_t traj, int stock_contact) {
-  typedef SmemLayoutT<W, E> SmemLayout;
+  typedef SmemLayoutT<W, E, M> SmemLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
   const unsigned int gseq = gather_begin(seg.gth);
   const int warp = threadIdx.x >> 5;
   if ((blockIdx.x * W + warp) * E < seg.n)  // warp-uniform: at least one sub-env of this warp is real
-    brax_step_body<W, E, SP>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact, gseq);
+    brax_step_body<W, E, M>(seg, sm, actions, n_steps, policy_seed, step_base, traj, stock_contact, gseq);
   gather_epilogue_immediate(seg.gth, gseq);
 }
 
 // ------------------------------------------------------------------------------ reset
 // Env.reset: q = init_q + U(+-noise), qd = noise * N(0,1) (Hopper: both uniform), forward
 // kinematics (pipeline_init), obs; stores the first state/obs for AutoResetWrapper. One env per warp.
+template <int M>
 __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__ BraxSeg seg, const uint8_t* mask,
                                                          const float* q_in, const float* qd_in) {
-  typedef SmemLayoutT<4, 1> SmemLayout;
+  typedef SmemLayoutT<4, 1, M> SmemLayout;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
@@ -569,7 +656,7 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
           gather_store_elem(seg.gth, gseq, (size_t)(seg.global_offset + env) * seg.obs_dim + i, seg.obs[(size_t)env * seg.obs_dim + i]);
     } else {
       const float* sys = sm.sys;
-      EnvScratch& w = sm.env[warp];
+      typename ScratchOf<M>::type& w = sm.env[warp];
       const LaneCtx c = make_lane_ctx<1>(sys, seg, w, env, true, 0, lane, true);
       const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
       const uint64_t gid = (uint64_t)(seg.global_offset + env);
@@ -625,12 +712,12 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
         if (lane == l) {
           const bool world_parent = c.parent < 0;
           const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-          s = forward_link(sys, c.lt, w.q, w.qd, world_parent, c.plt, ps);
+          s = forward_link<M == MODE_HUMANOID>(sys, c.lt, w.q, w.qd, world_parent, c.plt, ps, c.dt);
           write_link(w.ls, lane, s);
         }
         __syncwarp();
       }
-      compute_obs<1, true>(sys, c, w, s);
+      compute_obs<1, M>(sys, c, w, s);
       const int D = seg.obs_dim;
       for (int i = c.L * LINK_WORDS + lane; i < seg.state_words; i += 32) w.ls[i] = 0.0f;  // padding words
       __syncwarp();
@@ -675,6 +762,8 @@ static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
     case KIND_BRAX_INVERTED_PENDULUM: L = 2; nq = 2; nqd = 2; A = 1; break;
     case KIND_BRAX_INVERTED_DOUBLE_PENDULUM: L = 3; nq = 3; nqd = 3; A = 1; break;
     case KIND_BRAX_REACHER: L = 3; nq = 4; nqd = 4; A = 2; break;
+    case KIND_BRAX_HUMANOID:
+    case KIND_BRAX_HUMANOIDSTANDUP: L = 11; nq = 24; nqd = 23; A = 17; break;
     default: L = 4; nq = 6; nqd = 6; A = 3; break;
   }
 }
@@ -682,12 +771,14 @@ static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
 int brax_query(int kind, carlb_env_info_t* o) {
   int L, nq, nqd, A;
   static_facts(kind, L, nq, nqd, A);
-  const int ex = kind == KIND_BRAX_ANT ? 2 : (kind == KIND_BRAX_INVERTED_PENDULUM ? 0 : 1);
+  const bool humanoid = kind == KIND_BRAX_HUMANOID || kind == KIND_BRAX_HUMANOIDSTANDUP;
+  const int ex = (kind == KIND_BRAX_ANT || humanoid) ? 2 : (kind == KIND_BRAX_INVERTED_PENDULUM ? 0 : 1);
   o->kind = kind;
   o->state_words = ((LINK_WORDS * L + 3) / 4) * 4;
   o->obs_dim = (nq - ex) + nqd;
   if (kind == KIND_BRAX_INVERTED_DOUBLE_PENDULUM) o->obs_dim = 8;  // q0, sin, cos, clipped qd
   if (kind == KIND_BRAX_REACHER) o->obs_dim = 11;                  // cos, sin, target, qd[:2], tip - target
+  if (humanoid) o->obs_dim = humanoid_obs_dim(nq, nqd, L);         // 244: q[2:], qd, cinert, cvel, actuator torques
   o->act_dim = A;
   o->act_discrete = 0;
   o->n_actions = 0;
@@ -695,7 +786,7 @@ int brax_query(int kind, carlb_env_info_t* o) {
   o->n_step_rows = 5 + L;
   o->default_max_steps = 1000;  // brax.envs.create(episode_length=1000)
   o->gym_reset_draws = 0;
-  o->act_low = kind == KIND_BRAX_INVERTED_PENDULUM ? -3.0f : -1.0f;  // BraxGymWrapper: Box(ctrl_range) (wrappers.py:48-50)
+  o->act_low = kind == KIND_BRAX_INVERTED_PENDULUM ? -3.0f : (humanoid ? -0.4f : -1.0f);  // BraxGymWrapper: Box(ctrl_range) (wrappers.py:48-50)
   o->act_high = -o->act_low;
   return CARLB_OK;
 }
@@ -797,7 +888,8 @@ static int brax_pack(const float* table, int n) {
     const char* e = getenv("CARLB_BRAX_PACK");
     return e != nullptr ? atoi(e) : 0;
   }();
-  const int need = max((int)table[H_N_LINKS], (int)table[H_N_ACT]);
+  int need = max((int)table[H_N_LINKS], (int)table[H_N_ACT]);
+  if ((int)table[H_ENV] == ENV_HUMANOID || (int)table[H_ENV] == ENV_HUMANOIDSTANDUP) need = (int)table[H_N_LINKS];  // actions are looped
   if (forced == 1) return 1;
   // Small batches of the larger bodies are latency bound (one warp walks its substeps in ~40 us whatever the
   // grid): one env per warp spreads the contact candidates over all 32 lanes (one pass instead of three) and
@@ -806,20 +898,21 @@ static int brax_pack(const float* table, int n) {
   if (forced == 0 && n <= 1024 && (int)table[H_N_LINKS] >= 7) return 1;
   if (need <= Lanes<4>::LPE && forced != 3) return 4;
   if (need <= Lanes<3>::LPE) return 3;
+  if (need <= Lanes<2>::LPE) return 2;
   return 1;
 }
 
-template <int W, int E, bool SP>
+template <int W, int E, int M>
 static cudaError_t launch_brax_step_we(const BraxSeg& seg, int n, const float* actions, int n_steps, uint64_t policy_seed,
                                        uint32_t step_base, const carlb_traj_t& tj, int stock_contact, cudaStream_t st) {
-  typedef SmemLayoutT<W, E> Smem;
+  typedef SmemLayoutT<W, E, M> Smem;
   static bool configured = false;
   if (!configured) {  // > 48 KB of dynamic shared memory needs the opt-in attribute
-    cudaError_t e = cudaFuncSetAttribute(brax_step_kernel<W, E, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    cudaError_t e = cudaFuncSetAttribute(brax_step_kernel<W, E, M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  brax_step_kernel<W, E, SP><<<brax_grid(n, W * E), W * 32, sizeof(Smem), st>>>(seg, actions, n_steps, policy_seed, step_base, tj,
+  brax_step_kernel<W, E, M><<<brax_grid(n, W * E), W * 32, sizeof(Smem), st>>>(seg, actions, n_steps, policy_seed, step_base, tj,
                                                                           stock_contact);
   return cudaGetLastError();
 }
@@ -828,19 +921,25 @@ static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, co
                                     uint64_t policy_seed, uint32_t step_base, const carlb_traj_t& tj, cudaStream_t st) {
   const BraxHandle* h = static_cast<const BraxHandle*>(env->brax_sys);
   const int n = env->n, sc = h->stock_contact;
-  if ((int)h->host_table[H_ENV] >= ENV_INVERTED_PENDULUM) {
+  const int env_kind = (int)h->host_table[H_ENV];
+  if (env_kind == ENV_HUMANOID || env_kind == ENV_HUMANOIDSTANDUP) {
+    // 11 links: two envs per warp (16 lanes each; the 17 actions and 29 contact candidates go in two passes)
+    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, MODE_HUMANOID>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    return launch_brax_step_we<4, 2, MODE_HUMANOID>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  }
+  if (env_kind >= ENV_INVERTED_PENDULUM) {
     // inverted pendulums / reacher (2-3 links): the instantiation with slide joints and their env layers
-    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
-    return launch_brax_step_we<4, 4, true>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, MODE_SPECIAL>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    return launch_brax_step_we<4, 4, MODE_SPECIAL>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
   }
   switch (brax_pack(h->host_table, n)) {
-    case 4: return launch_brax_step_we<4, 4, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
-    case 3: return launch_brax_step_we<4, 3, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    case 4: return launch_brax_step_we<4, 4, MODE_LOCO>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    case 3: return launch_brax_step_we<4, 3, MODE_LOCO>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
     default: break;
   }
   // one env per warp: 7-warp CTAs (2 per SM) keep large grids close to whole waves of 148 SMs
-  if (n >= 4096) return launch_brax_step_we<7, 1, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
-  return launch_brax_step_we<4, 1, false>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  if (n >= 4096) return launch_brax_step_we<7, 1, MODE_LOCO>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  return launch_brax_step_we<4, 1, MODE_LOCO>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
 }
 
 // ------------------------------------------------------------------------ goal epilogue
@@ -898,7 +997,11 @@ int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, c
   BraxSeg seg;
   int rc = make_brax_seg(env, seg, "carlb_env_reset", GL_RESET);
   if (rc != CARLB_OK) return rc;
-  brax_reset_kernel<<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1>), st>>>(seg, mask, q, qd);
+  const int env_kind = (int)static_cast<const BraxHandle*>(env->brax_sys)->host_table[H_ENV];
+  if (env_kind == ENV_HUMANOID || env_kind == ENV_HUMANOIDSTANDUP)
+    brax_reset_kernel<MODE_HUMANOID><<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1, MODE_HUMANOID>), st>>>(seg, mask, q, qd);
+  else
+    brax_reset_kernel<MODE_SPECIAL><<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1, MODE_SPECIAL>), st>>>(seg, mask, q, qd);
   g_launches++;
   CARLB_CUDA_CHECK(cudaGetLastError());
   return CARLB_OK;

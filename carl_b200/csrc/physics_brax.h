@@ -35,7 +35,12 @@ constexpr int P_SCHED = 7;  // point row slot 7: contact schedule (candidate han
 constexpr int OFF_LINKS = HEADER;
 constexpr int OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS;
 constexpr int OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS;
-constexpr int TABLE_FLOATS = OFF_INIT_Q + MAX_Q;
+constexpr int DOF_STRIDE = 16;  // per-link rows of the stacked (2- / 3-dof) revolute joints: what dofs 1 and 2 need
+constexpr int OFF_DOF = OFF_INIT_Q + MAX_Q;
+constexpr int TABLE_FLOATS = OFF_DOF + DOF_STRIDE * MAX_LINKS;
+constexpr int MAX_OBS_SMALL = 64;   // observation capacity of the per-env scratch: every body but the humanoids
+constexpr int MAX_OBS_LARGE = 244;  // humanoid / humanoidstandup (brax.envs.humanoid._get_obs)
+constexpr int MAX_ACT = 20;
 
 // H_SITE_LINK: link carrying the body-fixed point the env layer reads (pendulum tip / reacher fingertip, L_SITE);
 // H_QD_NOISE: scale of the reset noise on qd (H_RESET_NOISE is the one on q); H_ACT_SCALE: action-space half width
@@ -56,13 +61,24 @@ enum LinkSlot {
 };
 // TYPE_SLIDE: one prismatic dof along the joint x axis (the cart of the inverted pendulums);
 // TYPE_SLIDE2: two prismatic dofs along the joint x and y axes (the reacher's target body)
-enum LinkType { TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_SLIDE = 2, TYPE_PLANAR = 3, TYPE_SLIDE2 = 4 };
+// TYPE_HINGE2 / TYPE_HINGE3: two / three stacked revolute dofs (the humanoid's abdomen, shoulders / hips): the joint
+// rotation is Rx(a0) Ry(a1) Rz(a2) in the joint frame, whose x and y axes are the first two MJCF axes
+enum LinkType {
+  TYPE_FREE = 0, TYPE_HINGE = 1, TYPE_SLIDE = 2, TYPE_PLANAR = 3, TYPE_SLIDE2 = 4, TYPE_HINGE2 = 5, TYPE_HINGE3 = 6
+};
 enum EnvId {
   ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2, ENV_WALKER2D = 3, ENV_INVERTED_PENDULUM = 4,
-  ENV_INVERTED_DOUBLE_PENDULUM = 5, ENV_REACHER = 6
+  ENV_INVERTED_DOUBLE_PENDULUM = 5, ENV_REACHER = 6, ENV_HUMANOID = 7, ENV_HUMANOIDSTANDUP = 8
 };
+// dof rows (OFF_DOF + DOF_STRIDE * link): actuator index / gear / range of dofs 1 and 2 (dof 0 lives in the link row),
+// then the sign of each dof's coordinate against the right-handed joint frame (-1 where the MJCF axis is -z)
+enum DofSlot { D_ACT1 = 0, D_ACT2, D_GEAR1, D_GEAR2, D_LO1, D_HI1, D_LO2, D_HI2, D_SIGN0, D_SIGN1, D_SIGN2 };
+// Kernel flavours (template parameter of the step / reset kernels): which joint types and env layers are compiled in
+enum BodyMode { MODE_LOCO = 0, MODE_SPECIAL = 1, MODE_HUMANOID = 2 };
 // joint coordinates per link type (free roots are handled separately: 7 / 6)
-CARLB_HD int type_ndof(int type) { return type == TYPE_PLANAR ? 3 : (type == TYPE_SLIDE2 ? 2 : 1); }
+CARLB_HD int type_ndof(int type) {
+  return (type == TYPE_PLANAR || type == TYPE_HINGE3) ? 3 : ((type == TYPE_SLIDE2 || type == TYPE_HINGE2) ? 2 : 1);
+}
 // per-env context rows: gravity, friction, elasticity, ang_damping, joint-stiffness scale (the
 // legacy `joint_stiffness` feature of CARL's docs mapped onto the spring constraint stiffness,
 // 1 = stock), then one mass per link
@@ -111,6 +127,11 @@ CARLB_HD V3 rotate_ey(Q4 q) {
   const float s = q.w, c = s * s - dot(u, u), d = 2.0f * q.y, t = 2.0f * s;
   return v3(d * u.x + t * (0.0f - u.z), d * u.y + c, d * u.z + t * u.x);
 }
+CARLB_HD V3 rotate_ez(Q4 q) {
+  const V3 u = v3(q.x, q.y, q.z);
+  const float s = q.w, c = s * s - dot(u, u), d = 2.0f * q.z, t = 2.0f * s;
+  return v3(d * u.x + t * u.y, d * u.y + t * (0.0f - u.x), d * u.z + c);
+}
 CARLB_HD Q4 quat_axis_angle(V3 axis, float angle) {
   const float h = 0.5f * angle;
   const float s = sinf(h);
@@ -132,6 +153,7 @@ struct Wrench {
 
 CARLB_HD const float* link_tab(const float* sys, int l) { return sys + OFF_LINKS + LINK_STRIDE * l; }
 CARLB_HD const float* point_tab(const float* sys, int p) { return sys + OFF_POINTS + POINT_STRIDE * p; }
+CARLB_HD const float* dof_tab(const float* sys, int l) { return sys + OFF_DOF + DOF_STRIDE * l; }
 
 // link-frame origin in the world (Brax `x.pos`) from the COM state
 CARLB_HD V3 link_origin(const LinkState& s, const float* lt) { return s.pos - rotate(ld3(lt + L_COM), s.rot); }
@@ -199,10 +221,32 @@ CARLB_HD int joint_flags(const float* lt) {
   return f;
 }
 
-template <bool SLIDES = true>
+// Stacked hinges (kinematics.axis_angle_ang restated as intrinsic x-y'-z'' Euler angles of the joint rotation
+// R = Rx(a0) Ry(a1) Rz(a2)): the angles and the axes the limit / actuator torques and the rates refer to, in the
+// joint frame: e_x, the line of nodes Rx(a0) e_y, and the child's z axis R e_z.
+struct EulerAxes {
+  float ang[3];
+  V3 a1, a2;
+};
+CARLB_HD EulerAxes euler_axes(Q4 jrot) {
+  EulerAxes e;
+  const V3 xc = rotate_ex(jrot), yc = rotate_ey(jrot), zc = rotate_ez(jrot);
+  const float c1 = sqrtf(zc.y * zc.y + zc.z * zc.z);
+  const float inv = 1.0f / (1e-10f + c1);
+  e.ang[0] = atan2f(0.0f - zc.y, zc.z);
+  e.ang[1] = atan2f(zc.x, c1);
+  e.ang[2] = atan2f(0.0f - yc.x, xc.x);
+  e.a1 = v3(0.0f, zc.z * inv, (0.0f - zc.y) * inv);
+  e.a2 = zc;
+  return e;
+}
+
+// STACKED = true compiles the 2- / 3-dof revolute branches in (humanoid kernels only); `dt` is the link's dof row,
+// `tau1` / `tau2` the actuator torques of dofs 1 and 2.
+template <bool SLIDES = true, bool STACKED = false>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
                                 const float* plt, const LinkState& p, float tau, float stiffness_scale, V3 anchor_p,
-                                int flags) {
+                                int flags, const float* dt = nullptr, float tau1 = 0.0f, float tau2 = 0.0f) {
   JointOut o;
   const int type = (int)lt[L_TYPE];
   const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
@@ -242,7 +286,33 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
   // torque aligning the child's joint axis with the parent's
   const V3 axis_c_x = rotate_ex(jrot);
   fa = k * cross(axis_c_x, ex);
-  if (type == TYPE_PLANAR) {
+  EulerAxes ea;
+  const bool stacked = STACKED && (type == TYPE_HINGE2 || type == TYPE_HINGE3);
+  if (stacked) {
+    // universal / spherical joint: position spring on the anchor; no axis-alignment torque -- the universal joint
+    // instead keeps the child's y axis perpendicular to the parent's x axis (third Euler angle = 0); range limit and
+    // actuator torque per dof about its Euler axis; damping on the whole relative rate
+    ea = euler_axes(jrot);
+    fv = (-k) * jpos - cv * jvel;
+    fa = v3(0, 0, 0);
+    if (type == TYPE_HINGE2) {
+      const float inv = 1.0f / (1e-10f + sqrtf(yc.y * yc.y + yc.z * yc.z));
+      fa = fa + k * cross(yc, v3(0.0f, yc.y * inv, yc.z * inv));
+    }
+    const int nd = type == TYPE_HINGE3 ? 3 : 2;
+    for (int d = 0; d < nd; ++d) {
+      const float lo = d == 0 ? lt[L_LIM_LO] : (d == 1 ? dt[D_LO1] : dt[D_LO2]);
+      const float hi = d == 0 ? lt[L_LIM_HI] : (d == 1 ? dt[D_HI1] : dt[D_HI2]);
+      const float sg = dt[D_SIGN0 + d];
+      const float coord = sg * ea.ang[d];
+      float dang = 0.0f;
+      if (coord < lo) dang = lo - coord;
+      if (coord > hi) dang = hi - coord;
+      const float tq = sg * (kl * dang + (d == 0 ? tau : (d == 1 ? tau1 : tau2)));
+      fa = fa + tq * (d == 0 ? ex : (d == 1 ? ea.a1 : ea.a2));
+    }
+    fa = fa - ca * jang;
+  } else if (type == TYPE_PLANAR) {
     // slide-x / slide-z / hinge-y root: only the off-plane offset and off-axis rotation are constrained
     fv = v3(-k * jpos.x - cv * jvel.x, 0.0f, 0.0f);
     fa = fa - ca * v3(0.0f, jang.y, jang.z);
@@ -284,13 +354,20 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
     o.q[0] = jpos.x; o.q[1] = jpos.y;
     o.qd[0] = jvel.x; o.qd[1] = jvel.y;
   }
+  if (stacked) {
+    // kinematics.inverse: signed Euler angles; rates = projections of the relative rate on the Euler axes
+    o.q[0] = dt[D_SIGN0] * ea.ang[0]; o.q[1] = dt[D_SIGN1] * ea.ang[1]; o.q[2] = dt[D_SIGN2] * ea.ang[2];
+    o.qd[0] = dt[D_SIGN0] * jang.x; o.qd[1] = dt[D_SIGN1] * dot(ea.a1, jang); o.qd[2] = dt[D_SIGN2] * dot(ea.a2, jang);
+  }
   return o;
 }
 
-template <bool SLIDES = true>
+template <bool SLIDES = true, bool STACKED = false>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
-                                const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f) {
-  return joint_resolve<SLIDES>(sys, lt, c, world_parent, plt, p, tau, stiffness_scale, parent_anchor(lt), joint_flags(lt));
+                                const float* plt, const LinkState& p, float tau, float stiffness_scale = 1.0f,
+                                const float* dt = nullptr, float tau1 = 0.0f, float tau2 = 0.0f) {
+  return joint_resolve<SLIDES, STACKED>(sys, lt, c, world_parent, plt, p, tau, stiffness_scale, parent_anchor(lt),
+                                        joint_flags(lt), dt, tau1, tau2);
 }
 
 // ---- semi-implicit velocity update (brax.spring.integrator.integrate_xdd) ---------------------
@@ -376,8 +453,9 @@ CARLB_HD void integrate_pose(LinkState& s, float dt) {
 }
 
 // ---- forward kinematics of one link (kinematics.forward + com.from_world), parent first ------
+template <bool STACKED = false>
 CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* q, const float* qd, bool world_parent,
-                                const float* plt, const LinkState& p) {
+                                const float* plt, const LinkState& p, const float* dt = nullptr) {
   const int type = (int)lt[L_TYPE];
   const float* ql = q + (int)lt[L_QIDX];
   const float* qdl = qd + (int)lt[L_QDIDX];
@@ -402,7 +480,11 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
     }
     float angle, rate;
     V3 trans = v3(0, 0, 0), tvel = v3(0, 0, 0);
-    if (type == TYPE_PLANAR) {
+    const bool stacked = STACKED && (type == TYPE_HINGE2 || type == TYPE_HINGE3);
+    if (stacked) {
+      angle = 0.0f;
+      rate = 0.0f;
+    } else if (type == TYPE_PLANAR) {
       trans = v3(ql[0], 0.0f, ql[1]);
       tvel = v3(qdl[0], 0.0f, qdl[1]);
       angle = ql[2];
@@ -421,7 +503,22 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
       angle = ql[0];
       rate = qdl[0];
     }
-    const Q4 jrot = qnormalize(quat_axis_angle(axis, angle));
+    Q4 jrot = quat_axis_angle(axis, angle);
+    V3 wj = v3(0, 0, 0);  // stacked hinges: relative angular velocity in the joint frame
+    if (stacked) {
+      // joint rotation Rx(a0) Ry(a1) Rz(a2) in the joint frame, carried into the link frame by the joint
+      // orientation; rates about e_x, Rx(a0) e_y, Rx(a0) Ry(a1) e_z
+      Q4 acc = q4(1, 0, 0, 0);
+      const int nd = type == TYPE_HINGE3 ? 3 : 2;
+      for (int d = 0; d < nd; ++d) {
+        const float sg = dt[D_SIGN0 + d];
+        const V3 b = v3(d == 0 ? 1.0f : 0.0f, d == 1 ? 1.0f : 0.0f, d == 2 ? 1.0f : 0.0f);
+        wj = wj + (sg * qdl[d]) * rotate(b, acc);
+        acc = qmul(acc, quat_axis_angle(b, sg * ql[d]));
+      }
+      jrot = qmul(qmul(j_rot, acc), qconj(j_rot));
+    }
+    jrot = qnormalize(jrot);
     const V3 jpos = trans + (j_pos - rotate(j_pos, jrot));  // the joint position is the rotation pivot
     const V3 lpos = t_pos + rotate(jpos, t_rot);
     const Q4 lrot = qmul(t_rot, jrot);
@@ -429,6 +526,7 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
     xrot = qnormalize(qmul(xp_rot, lrot));
     xvel = vp + cross(wp, xpos - xp_pos) + rotate(tvel, xp_rot);
     xang = wp + rotate(axis * rate, xrot);
+    if (stacked) xang = wp + rotate(rotate(wj, j_rot), qmul(xp_rot, t_rot));
   }
   LinkState s;
   const V3 rc = rotate(ld3(lt + L_COM), xrot);
@@ -438,6 +536,47 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
   s.ang = xang;
   return s;
 }
+
+// ---- humanoid observation pieces (brax.envs.humanoid._get_obs / _com) -----------------------------------------
+// centre of mass of the whole body with the spring backend's effective link masses; `rows` = L link rows of
+// LINK_WORDS floats (COM position first), `meff` = effective mass per link. Returns the mass sum.
+CARLB_HD float body_com(const float* rows, const float* meff, int L, V3& com) {
+  float msum = 0.0f;
+  com = v3(0, 0, 0);
+  for (int l = 0; l < L; ++l) {
+    const float m = meff[l];
+    msum += m;
+    com = com + m * ld3(rows + l * LINK_WORDS);
+  }
+  com = v3(com.x / msum, com.y / msum, com.z / msum);
+  return msum;
+}
+// cinert row of one link: its inertia about the body COM in world axes (3x3 row-major) and its mass:
+// R diag(I_eff) R^T + m (|p|^2 E - p p^T), R = link rotation o principal frame, p = link COM - body COM
+CARLB_HD void link_cinert(const float* sys, const float* lt, const LinkState& s, float m, V3 com, float* out) {
+  const V3 p = s.pos - com;
+  const Q4 r = qmul(s.rot, ld4(lt + L_IROT));
+  const V3 c0 = rotate_ex(r), c1 = rotate_ey(r), c2 = rotate_ez(r);
+  const float R[3][3] = {{c0.x, c1.x, c2.x}, {c0.y, c1.y, c2.y}, {c0.z, c1.z, c2.z}};
+  const float e = 1.0f - sys[H_INERTIA_SCALE];
+  const float ie[3] = {powf(lt[L_IDIAG + 0], e), powf(lt[L_IDIAG + 1], e), powf(lt[L_IDIAG + 2], e)};
+  const float pv[3] = {p.x, p.y, p.z};
+  const float pp = dot(p, p);
+  for (int a = 0; a < 3; ++a)
+    for (int b = 0; b < 3; ++b) {
+      const float rot_i = (R[a][0] * ie[0] * R[b][0] + R[a][1] * ie[1] * R[b][1]) + R[a][2] * ie[2] * R[b][2];
+      const float par = (a == b ? pp : 0.0f) - pv[a] * pv[b];
+      out[3 * a + b] = rot_i + m * par;
+    }
+  out[9] = m;
+}
+// cvel row of one link: mass-weighted COM velocity and the angular velocity
+CARLB_HD void link_cvel(const LinkState& s, float m, float msum, float* out) {
+  out[0] = m * s.vel.x / msum; out[1] = m * s.vel.y / msum; out[2] = m * s.vel.z / msum;
+  out[3] = s.ang.x; out[4] = s.ang.y; out[5] = s.ang.z;
+}
+// humanoid observation layout: q[2:] (nq - 2) | qd | cinert 10 L | cvel 6 L | actuator torques (qd layout)
+CARLB_HD int humanoid_obs_dim(int nq, int nqd, int L) { return (nq - 2) + nqd + 16 * L + nqd; }
 
 // Observation entry i of the bodies whose obs is not q[exclude:] ++ qd
 // (brax.envs.inverted_double_pendulum._get_obs, brax.envs.reacher._get_obs)

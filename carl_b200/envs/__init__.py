@@ -13,6 +13,8 @@ from carl_b200.envs.brax import (  # noqa: F401,E402
     CARLBraxEnv,
     CARLBraxHalfcheetah,
     CARLBraxHopper,
+    CARLBraxHumanoid,
+    CARLBraxHumanoidStandup,
     CARLBraxInvertedDoublePendulum,
     CARLBraxInvertedPendulum,
     CARLBraxReacher,
@@ -22,12 +24,12 @@ from carl_b200.envs.mixed import MixedBatch  # noqa: F401,E402
 
 
 def __getattr__(name: str):
-    """The Brax bodies of ``carl/envs/brax/__init__.py`` that this engine does not build fail loudly
+    """The Brax body of ``carl/envs/brax/__init__.py`` that this engine does not build fails loudly
     (nothing is substituted): see DESIGN.md (f)."""
     from carl_b200.envs.brax import UNSUPPORTED_BODIES
 
     if name in UNSUPPORTED_BODIES:
         raise NotImplementedError(
-            f"{name} is not built by carl_b200: humanoid / humanoidstandup need multi-dof revolute joints and Brax's "
-            "cinert / cvel observation, pusher needs body-vs-body contacts (DESIGN.md (f)). No fallback is substituted.")
+            f"{name} is not built by carl_b200: the pusher needs body-vs-body contacts (DESIGN.md (f)). "
+            "No fallback is substituted.")
     raise AttributeError(f"module 'carl_b200.envs' has no attribute {name!r}")

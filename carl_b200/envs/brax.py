@@ -439,7 +439,49 @@ class CARLBraxReacher(CARLBraxEnv):
         return f
 
 
-# Bodies of carl/envs/brax/__init__.py that this engine does not build: humanoid /
-# humanoidstandup need multi-dof spherical joints and Brax's 244-dim cinert/cvel observation, pusher needs
-# capsule-vs-cylinder body/body contacts. Asking for them fails loudly instead of substituting anything.
-UNSUPPORTED_BODIES = ("CARLBraxHumanoid", "CARLBraxHumanoidStandup", "CARLBraxPusher")
+def _humanoid_features() -> dict[str, ContextFeature]:
+    """``carl/envs/brax/carl_humanoid.py:19-85`` (``carl_humanoidstandup.py:14-71`` lists the same physics and mass
+    features without the goal block)."""
+    f = _common_features()
+    f["viscosity"] = _uf("viscosity", 0, np.inf, 0)
+    for name, m in (("torso", 10), ("lwaist", 2.2619467), ("pelvis", 6.6161942), ("right_thigh", 4.751751),
+                    ("right_shin", 4.522842), ("left_thigh", 4.751751), ("left_shin", 4.522842),
+                    ("right_upper_arm", 1.6610805), ("right_lower_arm", 1.2295402), ("left_upper_arm", 1.6610805),
+                    ("left_lower_arm", 1.2295402)):
+        f[f"mass_{name}"] = _uf(f"mass_{name}", 1e-6, np.inf, m)
+    return f
+
+
+class CARLBraxHumanoid(CARLBraxEnv):
+    """``carl/envs/brax/carl_humanoid.py:14-85``: 11 links on stacked 2- / 3-dof hinges, 17 actuators, the 244-entry
+    observation of ``brax.envs.humanoid`` (q[2:], qd, cinert, cvel, actuator torques), centre-of-mass forward reward."""
+
+    env_name: str = "humanoid"
+    kind = "brax_humanoid"
+    asset_path: str = "envs/assets/humanoid.xml"
+    metadata = {"render_modes": []}
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        f = _humanoid_features()
+        f.update(_goal_features())
+        return f
+
+
+class CARLBraxHumanoidStandup(CARLBraxEnv):
+    """``carl/envs/brax/carl_humanoidstandup.py:9-71``: the humanoid lying on its back; reward = torso height / dt + 1
+    - 0.01 |a|^2, episodes end only by the time limit."""
+
+    env_name: str = "humanoidstandup"
+    kind = "brax_humanoidstandup"
+    asset_path: str = "envs/assets/humanoidstandup.xml"
+    metadata = {"render_modes": []}
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        return _humanoid_features()
+
+
+# The body of carl/envs/brax/__init__.py that this engine does not build (DESIGN.md (f)): pusher needs body-vs-body
+# contacts (sphere / capsule against the pushed cylinder). Asking for it fails loudly instead of substituting anything.
+UNSUPPORTED_BODIES = ("CARLBraxPusher",)

@@ -19,7 +19,7 @@ STATE_INDICES = {"ant": [13, 14], "humanoid": [22, 23], "halfcheetah": [14, 15],
 
 # the wrapper reads `sys.opt.timestep` of the freshly loaded MJCF (:107-109): the XML timestep,
 # not the spring-backend override
-MJCF_TIMESTEP = {"ant": 0.01, "halfcheetah": 0.01, "hopper": 0.002, "walker2d": 0.002}
+MJCF_TIMESTEP = {"ant": 0.01, "halfcheetah": 0.01, "hopper": 0.002, "walker2d": 0.002, "humanoid": 0.003}
 
 _c, _s = np.cos(22.5 * np.pi / 180), np.sin(22.5 * np.pi / 180)
 DIRECTION_VALUES = {  # brax_walker_goal_wrapper.py:70-105

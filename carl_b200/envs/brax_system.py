@@ -30,7 +30,13 @@ P_SCHED = 7  # point row slot 7: contact schedule (the candidate handled in this
 OFF_LINKS = HEADER
 OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS
 OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS
-TABLE_FLOATS = OFF_INIT_Q + MAX_Q  # 792 floats = 3168 B (a multiple of 16 B for the bulk copy)
+# per-link rows of the 2- and 3-dof revolute joints (humanoid): what dofs 1 and 2 need beyond the link row
+DOF_STRIDE = 16
+OFF_DOF = OFF_INIT_Q + MAX_Q
+TABLE_FLOATS = OFF_DOF + DOF_STRIDE * MAX_LINKS  # 984 floats = 3936 B (a multiple of 16 B for the bulk copy)
+# dof-row slots: actuator index / gear / range of dofs 1 and 2, then the sign of each dof's coordinate against the
+# right-handed joint frame (x = first axis, y = second axis, z = x cross y; -1 where the MJCF axis is -z)
+(D_ACT1, D_ACT2, D_GEAR1, D_GEAR2, D_LO1, D_HI1, D_LO2, D_HI2, D_SIGN0, D_SIGN1, D_SIGN2) = range(11)
 
 # header slots
 H_N_LINKS, H_N_Q, H_N_QD, H_N_POINTS, H_N_FRAMES, H_DT, H_ENV, H_N_ACT = range(8)
@@ -49,9 +55,12 @@ L_TPOS, L_TROT, L_JPOS, L_JROT, L_LIM_LO, L_LIM_HI = 4, 7, 11, 14, 18, 19
 L_COM, L_IROT, L_IDIAG, L_MASS, L_GEAR, L_ACT, L_CTRL_LO, L_CTRL_HI, L_FIRST_PT, L_N_PT = 20, 23, 27, 30, 31, 32, 33, 34, 35, 36
 L_SITE = 37  # body-fixed point read by the env layer (pendulum tip / reacher fingertip), on the H_SITE_LINK row
 # TYPE_SLIDE: one prismatic dof along the joint axis; TYPE_SLIDE2: two (joint x and y axes: the reacher's target)
-TYPE_FREE, TYPE_HINGE, TYPE_SLIDE, TYPE_PLANAR, TYPE_SLIDE2 = 0, 1, 2, 3, 4
-ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER, ENV_WALKER2D, ENV_INVERTED_PENDULUM, ENV_INVERTED_DOUBLE_PENDULUM, ENV_REACHER = range(7)
-TYPE_DOFS = {TYPE_FREE: (7, 6), TYPE_HINGE: (1, 1), TYPE_SLIDE: (1, 1), TYPE_PLANAR: (3, 3), TYPE_SLIDE2: (2, 2)}
+# TYPE_HINGE2 / TYPE_HINGE3: two / three stacked revolute dofs about the joint frame's x, y(, z) axes (humanoid)
+TYPE_FREE, TYPE_HINGE, TYPE_SLIDE, TYPE_PLANAR, TYPE_SLIDE2, TYPE_HINGE2, TYPE_HINGE3 = 0, 1, 2, 3, 4, 5, 6
+(ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER, ENV_WALKER2D, ENV_INVERTED_PENDULUM, ENV_INVERTED_DOUBLE_PENDULUM, ENV_REACHER,
+ ENV_HUMANOID, ENV_HUMANOIDSTANDUP) = range(9)
+TYPE_DOFS = {TYPE_FREE: (7, 6), TYPE_HINGE: (1, 1), TYPE_SLIDE: (1, 1), TYPE_PLANAR: (3, 3), TYPE_SLIDE2: (2, 2),
+             TYPE_HINGE2: (2, 2), TYPE_HINGE3: (3, 3)}
 UNLIMITED = 1e30  # joint range of an unlimited hinge
 
 
@@ -103,6 +112,16 @@ def frame_with_x(axis):
     y /= np.linalg.norm(y)
     z = np.cross(x, y)
     return mat_to_quat(np.stack([x, y, z], axis=1))
+
+
+def frame_with_axes(a0, a1):
+    """Right-handed joint frame of a 2- / 3-dof revolute joint: x = first axis, y = second axis, z = x cross y
+    (the MJCF axes of such a stack are mutually orthogonal; a third axis is +-z)."""
+    x = np.asarray(a0, dtype=np.float64)
+    y = np.asarray(a1, dtype=np.float64)
+    x, y = x / np.linalg.norm(x), y / np.linalg.norm(y)
+    assert abs(np.dot(x, y)) < 1e-12, "stacked hinge axes must be orthogonal"
+    return mat_to_quat(np.stack([x, y, np.cross(x, y)], axis=1))
 
 
 # ------------------------------------------------------------------------- geometry
@@ -170,7 +189,10 @@ def contact_points(geoms):
 # --------------------------------------------------------------------------- models
 def _link(name, parent, typ, pos, geoms, axis=None, joint_pos=(0, 0, 0), limit=(0, 0), gear=0.0, quat=(1, 0, 0, 0),
           ctrl_range=(-1.0, 1.0)):
-    return dict(name=name, parent=parent, type=typ, pos=np.asarray(pos, float), quat=np.asarray(quat, float),
+    """One link and the joint to its parent. For TYPE_HINGE2 / TYPE_HINGE3 ``axis``, ``limit`` and ``gear`` are
+    lists with one entry per dof (MJCF order of the stacked <joint> elements)."""
+    quat = np.asarray(quat, float)
+    return dict(name=name, parent=parent, type=typ, pos=np.asarray(pos, float), quat=quat / np.linalg.norm(quat),
                 geoms=geoms, axis=axis, joint_pos=np.asarray(joint_pos, float), limit=limit, gear=gear, ctrl_range=ctrl_range)
 
 
@@ -375,10 +397,9 @@ def reacher_model():
 
 
 def humanoid_geometry():
-    """Groundwork for ``CARLBraxHumanoid`` (NOT a buildable model yet: its 2- and 3-dof revolute joints and Brax's
-    cinert / cvel observation are not implemented). The collision geometry of Gym / Brax
-    ``humanoid.xml`` per link, pinned by CARL's own mass defaults (``carl/envs/brax/carl_humanoid.py:37-75``):
-    ``tests/test_brax_system.py::test_humanoid_geometry_matches_carl_masses`` reproduces all ten to 7 digits."""
+    """The collision geometry of Gym / Brax ``humanoid.xml`` per link, pinned by CARL's own mass defaults
+    (``carl/envs/brax/carl_humanoid.py:37-75``): ``tests/test_brax_system.py::test_humanoid_geometry_matches_carl_masses``
+    reproduces all ten to 7 digits."""
     arm_up = lambda sy: [capsule((0, 0, 0), (0.16, sy * 0.16, -0.16), 0.04)]
     arm_lo = lambda sy: [capsule((0.01, sy * 0.01, 0.01), (0.17, sy * 0.17, 0.17), 0.031), sphere((0.18, sy * 0.18, 0.18), 0.04)]
     thigh = lambda sy: [capsule((0, 0, 0), (0, sy * 0.01, -0.34), 0.06)]
@@ -391,6 +412,104 @@ def humanoid_geometry():
         "right_thigh": thigh(1), "right_shin": shin, "left_thigh": thigh(-1), "left_shin": shin,
         "right_upper_arm": arm_up(-1), "right_lower_arm": arm_lo(1), "left_upper_arm": arm_up(1), "left_lower_arm": arm_lo(-1),
     }
+
+
+def humanoid_model():
+    """Gym / Brax ``humanoid.xml`` (angles in degree, density 1000): torso on a free joint; abdomen (z, y) and
+    abdomen x; hips (x, z, y) and knees; shoulders (two oblique axes) and elbows -- 11 links, 17 actuated dofs,
+    ctrlrange +-0.4. Spring backend of brax 0.12.1 ``envs/humanoid.py``: dt 0.0015, 10 substeps, gears 350 (abdomen,
+    legs) / 100 (arms). The feet and hands are spheres fused into the shins / lower arms. Every geom is a
+    ground-contact candidate (29 end spheres), no body-vs-body contacts. The geometry is pinned by CARL's mass
+    defaults (``carl/envs/brax/carl_humanoid.py:37-75``, ``tests/test_brax_system.py``)."""
+    deg = np.pi / 180
+    g = humanoid_geometry()
+    x, y, z = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+    rng = lambda lo, hi: (lo * deg, hi * deg)
+    leg, arm = 350.0, 100.0
+    links = [
+        _link("torso", -1, TYPE_FREE, (0, 0, 1.4), g["torso"]),
+        _link("lwaist", 0, TYPE_HINGE2, (-0.01, 0, -0.26), g["lwaist"], axis=[z, y], joint_pos=(0, 0, 0.065),
+              limit=[rng(-45, 45), rng(-75, 30)], gear=[leg, leg], quat=(1, 0, -0.002, 0)),
+        _link("pelvis", 1, TYPE_HINGE, (0, 0, -0.165), g["pelvis"], axis=x, joint_pos=(0, 0, 0.1), limit=rng(-35, 35), gear=leg,
+              quat=(1, 0, -0.002, 0)),
+        _link("right_thigh", 2, TYPE_HINGE3, (0, -0.1, -0.04), g["right_thigh"], axis=[x, z, y],
+              limit=[rng(-25, 5), rng(-60, 35), rng(-110, 20)], gear=[leg] * 3),
+        _link("right_shin", 3, TYPE_HINGE, (0, 0.01, -0.403), g["right_shin"], axis=(0, -1, 0), joint_pos=(0, 0, 0.02),
+              limit=rng(-160, -2), gear=leg),
+        _link("left_thigh", 2, TYPE_HINGE3, (0, 0.1, -0.04), g["left_thigh"], axis=[(-1, 0, 0), (0, 0, -1), y],
+              limit=[rng(-25, 5), rng(-60, 35), rng(-120, 20)], gear=[leg] * 3),
+        _link("left_shin", 5, TYPE_HINGE, (0, -0.01, -0.403), g["left_shin"], axis=(0, -1, 0), joint_pos=(0, 0, 0.02),
+              limit=rng(-160, -2), gear=leg),
+        _link("right_upper_arm", 0, TYPE_HINGE2, (0, -0.17, 0.06), g["right_upper_arm"], axis=[(2, 1, 1), (0, -1, 1)],
+              limit=[rng(-85, 60), rng(-85, 60)], gear=[arm, arm]),
+        _link("right_lower_arm", 7, TYPE_HINGE, (0.18, -0.18, -0.18), g["right_lower_arm"], axis=(0, -1, 1), limit=rng(-90, 50),
+              gear=arm),
+        _link("left_upper_arm", 0, TYPE_HINGE2, (0, 0.17, 0.06), g["left_upper_arm"], axis=[(2, -1, 1), (0, 1, 1)],
+              limit=[rng(-60, 85), rng(-60, 85)], gear=[arm, arm]),
+        _link("left_lower_arm", 9, TYPE_HINGE, (0.18, 0.18, -0.18), g["left_lower_arm"], axis=(0, -1, -1), limit=rng(-90, 50),
+              gear=arm),
+    ]
+    for l in links[1:]:
+        l["ctrl_range"] = (-0.4, 0.4)
+    init_q = np.zeros(24)
+    init_q[:7] = (0, 0, 1.4, 1, 0, 0, 0)
+    return dict(
+        name="humanoid", env=ENV_HUMANOID, links=links, density=1000.0, total_mass=None, friction=1.0, init_q=init_q,
+        dt=0.0015, n_frames=10, obs_dim=244,
+        tunables=dict(constraint_stiffness=27000.0, constraint_vel_damping=80.0, constraint_limit_stiffness=2500.0,
+                      constraint_ang_damping=30.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.01, qd_noise=0.01, ctrl_cost=0.1, healthy_reward=5.0, z_min=1.0, z_max=2.0,
+                        forward_weight=1.25, angle_min=0.0, angle_max=0.0, exclude_pos=2, qd_clip=0.0, terminate=1.0,
+                        qd_uniform=1.0),
+        stock_gravity=-9.81, stock_ang_damping=-0.05, stock_elasticity=0.0,
+        # MJCF <actuator> order; "link:k" is dof k of a stacked joint
+        actuator_links=["lwaist:1", "lwaist:0", "pelvis", "right_thigh:0", "right_thigh:1", "right_thigh:2", "right_shin",
+                        "left_thigh:0", "left_thigh:1", "left_thigh:2", "left_shin", "right_upper_arm:0", "right_upper_arm:1",
+                        "right_lower_arm", "left_upper_arm:0", "left_upper_arm:1", "left_lower_arm"],
+    )
+
+
+def _rotate_model_frames(links, quat):
+    """Express every link-local vector of a model in link frames turned by ``quat`` (the body keeps its shape;
+    the pose that the identity root orientation describes changes)."""
+    r = quat_to_mat(np.asarray(quat, float))
+    rv = lambda v: r @ np.asarray(v, float)
+    out = []
+    for l in links:
+        l = dict(l)
+        l["pos"], l["joint_pos"] = rv(l["pos"]), rv(l["joint_pos"])
+        q = np.asarray(l["quat"], float)
+        l["quat"] = np.concatenate([[q[0]], rv(q[1:])])
+        if l["axis"] is not None:
+            l["axis"] = [tuple(rv(a)) for a in l["axis"]] if isinstance(l["axis"], list) else tuple(rv(l["axis"]))
+        geoms = []
+        for gm in l["geoms"]:
+            gm = dict(gm)
+            gm["p0"] = rv(gm["p0"])
+            if "p1" in gm:
+                gm["p1"] = rv(gm["p1"])
+            geoms.append(gm)
+        l["geoms"] = geoms
+        out.append(l)
+    return out
+
+
+def humanoidstandup_model():
+    """Gym / Brax ``humanoidstandup.xml``: the humanoid lying on its back, root at z = 0.105 with the identity
+    orientation (the XML defines the body along x: head towards -x, legs towards +x). Restated as the humanoid's
+    links expressed in frames turned by -90 deg about y; CARL's mass defaults are the humanoid's
+    (``carl/envs/brax/carl_humanoidstandup.py:32-69``). Env layer of brax 0.12.1 ``envs/humanoidstandup.py``:
+    reward = z_torso / dt + 1 - 0.01 |a|^2, never done."""
+    m = humanoid_model()
+    m["links"] = _rotate_model_frames(m["links"], quat_axis_angle((0, 1, 0), -np.pi / 2))
+    m["links"][0]["pos"] = np.array([0.0, 0.0, 0.105])
+    m["name"], m["env"] = "humanoidstandup", ENV_HUMANOIDSTANDUP
+    m["init_q"] = m["init_q"].copy()
+    m["init_q"][2] = 0.105
+    m["env_params"] = dict(m["env_params"], ctrl_cost=0.01, healthy_reward=1.0, z_min=-1e9, z_max=1e9, forward_weight=0.0,
+                           terminate=0.0)
+    return m
 
 
 def _initial_point_clearance(links, init_q, pts_all, q_idx):
@@ -411,7 +530,12 @@ def _initial_point_clearance(links, init_q, pts_all, q_idx):
                 angle = q[0]
             elif l["type"] in (TYPE_SLIDE, TYPE_SLIDE2):
                 trans = np.asarray(l["axis"], float) * q[0]
-            jrot = quat_axis_angle(l["axis"], angle) if l["axis"] is not None else np.array([1.0, 0, 0, 0])
+            if l["type"] in (TYPE_HINGE2, TYPE_HINGE3):  # stacked hinges: successive rotations about the given axes
+                jrot = np.array([1.0, 0, 0, 0])
+                for k, a in enumerate(l["axis"]):
+                    jrot = quat_mul(jrot, quat_axis_angle(a, q[k]))
+            else:
+                jrot = quat_axis_angle(l["axis"], angle) if l["axis"] is not None else np.array([1.0, 0, 0, 0])
             lrot = quat_mul(l["quat"], jrot)
             pos = ppos + quat_to_mat(prot) @ (l["pos"] + quat_to_mat(l["quat"]) @ trans)
             rot = quat_mul(prot, lrot)
@@ -457,14 +581,35 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
         t[o + L_TPOS:o + L_TPOS + 3] = l["pos"]
         t[o + L_TROT:o + L_TROT + 4] = l["quat"]
         t[o + L_JPOS:o + L_JPOS + 3] = l["joint_pos"]
-        t[o + L_JROT:o + L_JROT + 4] = frame_with_x(l["axis"]) if l["axis"] is not None else (1, 0, 0, 0)
-        t[o + L_LIM_LO], t[o + L_LIM_HI] = l["limit"]
+        d = OFF_DOF + DOF_STRIDE * i
+        t[d + D_ACT1], t[d + D_ACT2] = -1, -1
+        t[d + D_SIGN0:d + D_SIGN0 + 3] = 1.0
+        if l["type"] in (TYPE_HINGE2, TYPE_HINGE3):
+            axes, nd = l["axis"], TYPE_DOFS[l["type"]][0]
+            assert len(axes) == nd and len(l["limit"]) == nd and len(l["gear"]) == nd
+            jrot = frame_with_axes(axes[0], axes[1])
+            t[o + L_JROT:o + L_JROT + 4] = jrot
+            t[o + L_LIM_LO], t[o + L_LIM_HI] = l["limit"][0]
+            t[o + L_GEAR] = l["gear"][0]
+            t[o + L_ACT] = act_of.get(f"{l['name']}:0", -1)
+            t[d + D_ACT1], t[d + D_GEAR1] = act_of.get(f"{l['name']}:1", -1), l["gear"][1]
+            t[d + D_LO1], t[d + D_HI1] = l["limit"][1]
+            if nd == 3:
+                zf = quat_to_mat(jrot)[:, 2]
+                a2 = np.asarray(axes[2], float) / np.linalg.norm(axes[2])
+                assert abs(abs(np.dot(zf, a2)) - 1.0) < 1e-12, "third hinge axis must be +-(first x second)"
+                t[d + D_SIGN2] = np.sign(np.dot(zf, a2))
+                t[d + D_ACT2], t[d + D_GEAR2] = act_of.get(f"{l['name']}:2", -1), l["gear"][2]
+                t[d + D_LO2], t[d + D_HI2] = l["limit"][2]
+        else:
+            t[o + L_JROT:o + L_JROT + 4] = frame_with_x(l["axis"]) if l["axis"] is not None else (1, 0, 0, 0)
+            t[o + L_LIM_LO], t[o + L_LIM_HI] = l["limit"]
+            t[o + L_GEAR] = l["gear"]
+            t[o + L_ACT] = act_of.get(l["name"], -1)
         t[o + L_COM:o + L_COM + 3] = com
         t[o + L_IROT:o + L_IROT + 4] = irot
         t[o + L_IDIAG:o + L_IDIAG + 3] = idiag
         t[o + L_MASS] = m
-        t[o + L_GEAR] = l["gear"]
-        t[o + L_ACT] = act_of.get(l["name"], -1)
         t[o + L_CTRL_LO], t[o + L_CTRL_HI] = l["ctrl_range"]
         pts = contact_points(l["geoms"]) if model.get("contacts", True) else []
         t[o + L_FIRST_PT] = len(pts_all)
@@ -496,7 +641,8 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     t[H_TERMINATE], t[H_MAX_CHILD_POINTS] = ep["terminate"], max_pts
     t[H_QD_UNIFORM] = ep.get("qd_uniform", 0.0)  # Hopper / Walker2d draw qd uniformly, the others N(0,1)
     t[H_QD_NOISE] = ep.get("qd_noise", ep["reset_noise"])
-    ranges = {tuple(l["ctrl_range"]) for l in links if l["name"] in act_of}
+    actuated = {k.split(":")[0] for k in act_of}
+    ranges = {tuple(l["ctrl_range"]) for l in links if l["name"] in actuated}
     assert len(ranges) == 1 and next(iter(ranges))[0] == -next(iter(ranges))[1], "one symmetric ctrl_range per body"
     t[H_ACT_SCALE] = next(iter(ranges))[1]
     if model.get("site"):
@@ -512,12 +658,12 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
         stock_gravity=model["stock_gravity"], stock_friction=stock_friction,
         stock_elasticity=model["stock_elasticity"], stock_ang_damping=model["stock_ang_damping"],
         tunables=tun, obs_dim=model.get("obs_dim", (qi - int(ep["exclude_pos"])) + qdi), state_words=((13 * n + 3) // 4) * 4,
-        act_scale=float(t[H_ACT_SCALE]),
+        act_scale=float(np.float32(t[H_ACT_SCALE])),
         dt=model["dt"] * model["n_frames"],
     )
 
 
 MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model, "walker2d": walker2d_model,
           "inverted_pendulum": inverted_pendulum_model, "inverted_double_pendulum": inverted_double_pendulum_model,
-          "reacher": reacher_model}
+          "reacher": reacher_model, "humanoid": humanoid_model, "humanoidstandup": humanoidstandup_model}
 SYSTEMS = {k: build_system(f()) for k, f in MODELS.items()}

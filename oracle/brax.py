@@ -42,7 +42,8 @@ class OracleBraxEnv:
         q = np.ascontiguousarray(q, dtype=np.float32)
         qd = np.ascontiguousarray(qd, dtype=np.float32)
         obs = np.zeros((self.n, self.D), dtype=np.float32)
-        getattr(lib(), 'brax_oracle_init64' if self.f64 else 'brax_oracle_init')(_p(self.table), self.n, _p(q), _p(qd), _p(self.state), self.words, _p(obs), self.D)
+        getattr(lib(), 'brax_oracle_init64' if self.f64 else 'brax_oracle_init')(_p(self.table), self.n, _p(q), _p(qd), _p(self.state), self.words, _p(obs), self.D,
+            _p(self.ctx), self.ctx.shape[1])
         self.first_state[:] = self.state
         self.first_obs[:] = obs
         self.elapsed[:] = 0

@@ -30,8 +30,11 @@
 #endif
 
 /* ---- table layout (must match carl_b200/envs/brax_system.py) ---- */
-enum { MAXL = 12, MAXP = 32, MAXQ = 24, HDR = 32, LSTR = 40, PSTR = 8 };
-enum { OFF_L = HDR, OFF_P = HDR + LSTR * MAXL, OFF_Q = HDR + LSTR * MAXL + PSTR * MAXP, TABLE_N = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ };
+enum { MAXL = 12, MAXP = 32, MAXQ = 24, HDR = 32, LSTR = 40, PSTR = 8, DSTR = 16, MAXOBS = 256 };
+enum { OFF_L = HDR, OFF_P = HDR + LSTR * MAXL, OFF_Q = HDR + LSTR * MAXL + PSTR * MAXP, OFF_D = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ,
+       TABLE_N = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ + DSTR * MAXL };
+/* dof rows (stacked hinges): actuator / gear / range of dofs 1 and 2, sign of each coordinate against the joint frame */
+enum { dACT1 = 0, dACT2, dGEAR1, dGEAR2, dLO1, dHI1, dLO2, dHI2, dSIGN0, dSIGN1, dSIGN2 };
 enum { hN_LINKS = 0, hN_Q, hN_QD, hN_POINTS, hN_FRAMES, hDT, hENV, hN_ACT, hK, hCV, hKL, hCA, hERP, hVDAMP, hMSCALE,
        hISCALE, hNOISE, hCTRL, hHEALTHY, hZMIN, hZMAX, hFWD, hAMIN, hAMAX, hEXCL, hQDCLIP, hTERM, hMAXCP, hQDUNI,
        hSITE_LINK, hQDNOISE, hACTSCALE };
@@ -39,8 +42,11 @@ enum { lPARENT = 0, lTYPE, lQ, lQD, lTPOS = 4, lTROT = 7, lJPOS = 11, lJROT = 14
        lIROT = 23, lIDIAG = 27, lMASS = 30, lGEAR = 31, lACT = 32, lCLO = 33, lCHI = 34, lFIRSTP = 35, lNP = 36, lSITE = 37 };
 /* T_SLIDE: prismatic joint along the joint x axis (carts of brax.envs.inverted_pendulum /
  * inverted_double_pendulum); T_SLIDE2: two prismatic dofs, joint x and y (target of brax.envs.reacher) */
-enum { T_FREE = 0, T_HINGE = 1, T_SLIDE = 2, T_PLANAR = 3, T_SLIDE2 = 4 };
-enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2, E_WALKER2D = 3, E_IPENDULUM = 4, E_IDPENDULUM = 5, E_REACHER = 6 };
+/* T_HINGE2 / T_HINGE3: two / three stacked revolute dofs (universal / spherical joints of brax humanoid.xml):
+ * the joint rotation is Rx(a0) Ry(a1) Rz(a2) in the joint frame whose x, y are the first two MJCF axes */
+enum { T_FREE = 0, T_HINGE = 1, T_SLIDE = 2, T_PLANAR = 3, T_SLIDE2 = 4, T_HINGE2 = 5, T_HINGE3 = 6 };
+enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2, E_WALKER2D = 3, E_IPENDULUM = 4, E_IDPENDULUM = 5, E_REACHER = 6,
+       E_HUMANOID = 7, E_STANDUP = 8 };
 
 /* Arithmetic type of the restatement: float (the reference's JAX pipeline) by default; built a
  * second time with -DORACLE_F64 as the round-off-free yardstick that tells float32 noise (stiff
@@ -134,6 +140,33 @@ typedef struct {
   real psi;
 } jframe_t;
 
+/* Stacked hinges (kinematics.axis_angle_ang restated as intrinsic x-y'-z'' Euler angles): the joint rotation
+ * R = Rx(a0) Ry(a1) Rz(a2); torque / rate axes in the joint frame: e_x, the line of nodes Rx(a0) e_y, and the
+ * child's z axis R e_z. */
+static void euler_axes(const real *jrot, real *ang, real ax[3][3]) {
+  f3 ex = {1, 0, 0}, ey = {0, 1, 0}, ez = {0, 0, 1}, xc, yc, zc;
+  rot3(ex, jrot, xc);
+  rot3(ey, jrot, yc);
+  rot3(ez, jrot, zc);
+  real c1 = SQRT(zc[1] * zc[1] + zc[2] * zc[2]);
+  real inv = 1.0f / (1e-10f + c1);
+  ang[0] = ATAN2(-zc[1], zc[2]);
+  ang[1] = ATAN2(zc[0], c1);
+  ang[2] = ATAN2(-yc[0], xc[0]);
+  ax[0][0] = 1; ax[0][1] = 0; ax[0][2] = 0;
+  ax[1][0] = 0; ax[1][1] = zc[2] * inv; ax[1][2] = -zc[1] * inv;
+  for (int k = 0; k < 3; ++k) ax[2][k] = zc[k];
+}
+static int type_dofs(int type) { return type == T_HINGE3 || type == T_PLANAR ? 3 : (type == T_HINGE2 || type == T_SLIDE2 ? 2 : 1); }
+/* range and sign of dof k of a stacked hinge */
+static void dof_range(const real *sys, int l, int k, real *lo, real *hi, real *sign) {
+  const real *lt = sys + OFF_L + LSTR * l, *dt = sys + OFF_D + DSTR * l;
+  *sign = dt[dSIGN0 + k];
+  if (k == 0) { *lo = lt[lLO]; *hi = lt[lHI]; }
+  else if (k == 1) { *lo = dt[dLO1]; *hi = dt[dHI1]; }
+  else { *lo = dt[dLO2]; *hi = dt[dHI2]; }
+}
+
 static void joint_frame(const real *sys, const real *rows, int l, jframe_t *j) {
   const real *lt = sys + OFF_L + LSTR * l;
   const real *c = rows + 13 * l;
@@ -181,7 +214,7 @@ static void joint_frame(const real *sys, const real *rows, int l, jframe_t *j) {
 }
 
 /* one spring substep over all links of one env (brax.spring.pipeline.step) */
-static void substep(const real *sys, real *rows, const real *ctx, const real *tau) {
+static void substep(const real *sys, real *rows, const real *ctx, real (*tau)[3]) {
   const int L = (int)sys[hN_LINKS], P = (int)sys[hN_POINTS];
   const real dt = sys[hDT];
   const real gravity = ctx[0], friction = ctx[1], elasticity = ctx[2], ang_damping = ctx[3];
@@ -207,6 +240,33 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
       fv[0] = -k * j.jpos[0] - cv * j.jvel[0]; fv[1] = 0; fv[2] = 0;
       fa[1] -= ca * j.jang[1];
       fa[2] -= ca * j.jang[2];
+    } else if (type == T_HINGE2 || type == T_HINGE3) {
+      /* universal / spherical: position spring on the anchor, no axis-alignment torque; the universal joint keeps
+       * the child's y axis perpendicular to the parent's x axis (third Euler angle = 0) with a spring torque;
+       * range limit and actuator torque per dof about its Euler axis; damping on the whole relative rate */
+      real ang[3], ax[3][3];
+      euler_axes(j.jrot, ang, ax);
+      for (int q = 0; q < 3; ++q) fv[q] = -k * j.jpos[q] - cv * j.jvel[q];
+      fa[0] = fa[1] = fa[2] = 0.0f;
+      if (type == T_HINGE2) {
+        f3 ey = {0, 1, 0}, yc, proj, t2;
+        rot3(ey, j.jrot, yc);
+        real inv = 1.0f / (1e-10f + SQRT(yc[1] * yc[1] + yc[2] * yc[2]));
+        proj[0] = 0; proj[1] = yc[1] * inv; proj[2] = yc[2] * inv;
+        cross3(yc, proj, t2);
+        for (int q = 0; q < 3; ++q) fa[q] += k * t2[q];
+      }
+      int nd = type_dofs(type);
+      for (int d = 0; d < nd; ++d) {
+        real lo, hi, sg;
+        dof_range(sys, l, d, &lo, &hi, &sg);
+        real coord = sg * ang[d], dang = 0.0f;
+        if (coord < lo) dang = lo - coord;
+        if (coord > hi) dang = hi - coord;
+        real tq = sg * (kl * dang + tau[l][d]);
+        for (int q = 0; q < 3; ++q) fa[q] += tq * ax[d][q];
+      }
+      for (int q = 0; q < 3; ++q) fa[q] -= ca * j.jang[q];
     } else if (type == T_SLIDE || type == T_SLIDE2) {
       /* prismatic: no relative rotation at all (a second alignment torque on the y axes), springs on the
        * constrained offsets only, range limit and actuator force along the first sliding axis */
@@ -218,7 +278,7 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
       real dpos = 0.0f;
       if (j.jpos[0] < lt[lLO]) dpos = lt[lLO] - j.jpos[0];
       if (j.jpos[0] > lt[lHI]) dpos = lt[lHI] - j.jpos[0];
-      fv[0] = kl * dpos + tau[l];
+      fv[0] = kl * dpos + tau[l][0];
       fv[1] = (type == T_SLIDE) ? (-k * j.jpos[1] - cv * j.jvel[1]) : 0.0f;
       fv[2] = -k * j.jpos[2] - cv * j.jvel[2];
     } else {
@@ -228,7 +288,7 @@ static void substep(const real *sys, real *rows, const real *ctx, const real *ta
       if (j.psi > lt[lHI]) dang = lt[lHI] - j.psi;
       fa[0] += kl * dang;
       for (int q = 0; q < 3; ++q) fa[q] -= ca * j.jang[q];
-      fa[0] += tau[l];
+      fa[0] += tau[l][0];
     }
     f3 Fw, Tw, r, rxF;
     rot3(fv, j.ap_rot, Fw);
@@ -356,6 +416,14 @@ static void inverse_kinematics(const real *sys, const real *rows, real *q, real 
         q[qi] = j.jpos[0];
         qd[qdi] = j.jvel[0];
         if (type == T_SLIDE2) { q[qi + 1] = j.jpos[1]; qd[qdi + 1] = j.jvel[1]; }
+      } else if (type == T_HINGE2 || type == T_HINGE3) {
+        real ang[3], ax[3][3];
+        euler_axes(j.jrot, ang, ax);
+        for (int d = 0; d < type_dofs(type); ++d) {
+          real sg = sys[OFF_D + DSTR * l + dSIGN0 + d];
+          q[qi + d] = sg * ang[d];
+          qd[qdi + d] = sg * dot3(ax[d], j.jang);
+        }
       } else {
         q[qi] = j.psi;
         qd[qdi] = j.jang[0];
@@ -374,10 +442,94 @@ static void site_pos(const real *sys, const real *rows, real *o) {
   for (int k = 0; k < 3; ++k) o[k] = org[k] + r[k];
 }
 
-static void make_obs(const real *sys, const real *rows, const real *q, const real *qd, real *obs) {
+/* centre of mass of the whole body with the spring backend's effective link masses (brax humanoid._com) */
+static real body_com(const real *sys, const real *rows, const real *ctx, real *com) {
+  const int L = (int)sys[hN_LINKS];
+  real msum = 0.0f;
+  com[0] = com[1] = com[2] = 0.0f;
+  for (int l = 0; l < L; ++l) {
+    real m = eff_mass(ctx[5 + l], sys);
+    msum += m;
+    for (int k = 0; k < 3; ++k) com[k] += m * rows[13 * l + k];
+  }
+  for (int k = 0; k < 3; ++k) com[k] = com[k] / msum;
+  return msum;
+}
+
+/* actuator torque of every actuated dof: gear * clip(action) (brax.actuator.to_tau) */
+static void actuator_taus(const real *sys, const real *act, real (*tau)[3]) {
+  const int L = (int)sys[hN_LINKS];
+  for (int l = 0; l < L; ++l) {
+    const real *lt = sys + OFF_L + LSTR * l, *dt = sys + OFF_D + DSTR * l;
+    int ai[3] = {(int)lt[lACT], (int)dt[dACT1], (int)dt[dACT2]};
+    real gear[3] = {lt[lGEAR], dt[dGEAR1], dt[dGEAR2]};
+    int nd = (int)lt[lTYPE] == T_FREE ? 0 : type_dofs((int)lt[lTYPE]);
+    for (int d = 0; d < 3; ++d) {
+      tau[l][d] = 0.0f;
+      if (d < nd && ai[d] >= 0) tau[l][d] = gear[d] * FMIN(FMAX(act[ai[d]], lt[lCLO]), lt[lCHI]);
+    }
+  }
+}
+
+/* brax.envs.humanoid._get_obs: q[2:], qd, per link (inertia about the body COM in the world frame 3x3, mass),
+ * per link (mass-weighted COM velocity, angular velocity), actuator torques in qd layout */
+static void humanoid_obs(const real *sys, const real *rows, const real *q, const real *qd, const real *ctx,
+                         const real *act, real *obs) {
+  const int L = (int)sys[hN_LINKS], nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD];
+  int k = 0;
+  for (int i = 2; i < nq; ++i) obs[k++] = q[i];
+  for (int i = 0; i < nqd; ++i) obs[k++] = qd[i];
+  f3 com;
+  real msum = body_com(sys, rows, ctx, com);
+  real e = 1.0f - sys[hISCALE];
+  for (int l = 0; l < L; ++l) {
+    const real *lt = sys + OFF_L + LSTR * l, *s = rows + 13 * l;
+    real m = eff_mass(ctx[5 + l], sys);
+    f3 p = {s[0] - com[0], s[1] - com[1], s[2] - com[2]};
+    f4 r;
+    qmul(s + 3, lt + lIROT, r);
+    real R[3][3]; /* R[a][c]: component a of the rotated basis vector c */
+    for (int c = 0; c < 3; ++c) {
+      f3 b = {c == 0, c == 1, c == 2}, o;
+      rot3(b, r, o);
+      for (int a = 0; a < 3; ++a) R[a][c] = o[a];
+    }
+    real ie[3];
+    for (int c = 0; c < 3; ++c) ie[c] = POW(lt[lIDIAG + c], e);
+    real pp = dot3(p, p);
+    for (int a = 0; a < 3; ++a)
+      for (int b = 0; b < 3; ++b) {
+        real rot_i = (R[a][0] * ie[0] * R[b][0] + R[a][1] * ie[1] * R[b][1]) + R[a][2] * ie[2] * R[b][2];
+        real par = (a == b ? pp : 0.0f) - p[a] * p[b];
+        obs[k++] = rot_i + m * par;
+      }
+    obs[k++] = m;
+  }
+  for (int l = 0; l < L; ++l) {
+    const real *s = rows + 13 * l;
+    real m = eff_mass(ctx[5 + l], sys);
+    for (int c = 0; c < 3; ++c) obs[k++] = m * s[7 + c] / msum;
+    for (int c = 0; c < 3; ++c) obs[k++] = s[10 + c];
+  }
+  real tau[MAXL][3];
+  actuator_taus(sys, act, tau);
+  for (int i = 0; i < nqd; ++i) obs[k + i] = 0.0f;
+  for (int l = 0; l < L; ++l) {
+    const real *lt = sys + OFF_L + LSTR * l;
+    if ((int)lt[lTYPE] == T_FREE) continue;
+    for (int d = 0; d < type_dofs((int)lt[lTYPE]); ++d) obs[k + (int)lt[lQD] + d] = tau[l][d];
+  }
+}
+
+static void make_obs(const real *sys, const real *rows, const real *q, const real *qd, const real *ctx, const real *act,
+                     real *obs) {
   int nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD], ex = (int)sys[hEXCL], env = (int)sys[hENV];
   real clip = sys[hQDCLIP];
   int k = 0;
+  if (env == E_HUMANOID || env == E_STANDUP) {
+    humanoid_obs(sys, rows, q, qd, ctx, act, obs);
+    return;
+  }
   if (env == E_IDPENDULUM) { /* brax.envs.inverted_double_pendulum._get_obs */
     obs[k++] = q[0];
     obs[k++] = SIN(q[1]); obs[k++] = SIN(q[2]);
@@ -406,7 +558,7 @@ static void make_obs(const real *sys, const real *rows, const real *q, const rea
 
 /* pipeline_init: forward kinematics from (q, qd) into the COM rows */
 void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const float *qd_all, real *state, int state_words,
-                      float *obs, int obs_dim) {
+                      float *obs, int obs_dim, const float *ctx, int n_ctx) {
   real sys[TABLE_N];
   for (int i = 0; i < TABLE_N; ++i) sys[i] = sys_f[i];
   const int L = (int)sys[hN_LINKS], nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD];
@@ -441,7 +593,10 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
         }
         real angle, rate;
         f3 trans = {0, 0, 0}, tvel = {0, 0, 0};
-        if (type == T_PLANAR) {
+        int stacked = (type == T_HINGE2 || type == T_HINGE3);
+        if (stacked) {
+          angle = 0.0f; rate = 0.0f;
+        } else if (type == T_PLANAR) {
           trans[0] = ql[0]; trans[2] = ql[1];
           tvel[0] = qdl[0]; tvel[2] = qdl[1];
           angle = ql[2]; rate = qdl[2];
@@ -458,6 +613,26 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
         }
         real h = 0.5f * angle, sn = SIN(h);
         f4 jrot = {COS(h), axis[0] * sn, axis[1] * sn, axis[2] * sn};
+        f3 wj = {0, 0, 0}; /* stacked hinges: relative angular velocity in the joint frame */
+        if (stacked) {
+          /* joint rotation Rx(a0) Ry(a1) Rz(a2) in the joint frame, carried into the link frame by the joint
+           * orientation; rates about e_x, Rx(a0) e_y, Rx(a0) Ry(a1) e_z */
+          const real *dof = sys + OFF_D + DSTR * l;
+          f4 acc = {1, 0, 0, 0}, t, jc;
+          for (int d = 0; d < type_dofs(type); ++d) {
+            real a = dof[dSIGN0 + d] * ql[d], hh = 0.5f * a;
+            f4 e = {COS(hh), 0, 0, 0};
+            e[1 + d] = SIN(hh);
+            f3 b = {d == 0, d == 1, d == 2}, bw;
+            rot3(b, acc, bw);
+            for (int k = 0; k < 3; ++k) wj[k] += dof[dSIGN0 + d] * qdl[d] * bw[k];
+            qmul(acc, e, t);
+            memcpy(acc, t, sizeof(f4));
+          }
+          qmul(lt + lJROT, acc, t);
+          qconj(lt + lJROT, jc);
+          qmul(t, jc, jrot);
+        }
         qnorm(jrot);
         f3 rj, jpos, lpos, tmp, tmp2;
         rot3(lt + lJPOS, jrot, rj);
@@ -476,6 +651,12 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
         for (int k = 0; k < 3; ++k) xvel[k] = vp[k] + tmp2[k] + tmp[k];
         f3 ar = {axis[0] * rate, axis[1] * rate, axis[2] * rate};
         rot3(ar, xrot, tmp);
+        if (stacked) {
+          f4 xpt;
+          qmul(xprot, lt + lTROT, xpt);
+          rot3(wj, lt + lJROT, tmp2);
+          rot3(tmp2, xpt, tmp);
+        }
         for (int k = 0; k < 3; ++k) xang[k] = wp[k] + tmp[k];
       }
       real *s = rows + 13 * l;
@@ -485,9 +666,15 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
       for (int k = 0; k < 3; ++k) { s[k] = xpos[k] + rc[k]; s[7 + k] = xvel[k] + w[k]; s[10 + k] = xang[k]; }
       for (int k = 0; k < 4; ++k) s[3 + k] = xrot[k];
     }
-    real qq[MAXQ], qqd[MAXQ], ob[64];
+    real qq[MAXQ], qqd[MAXQ], ob[MAXOBS], c[5 + MAXL], zero_act[MAXQ];
+    /* context row of the env (link masses enter the humanoid's observation); stock masses without one */
+    for (int i = 0; i < 5; ++i) c[i] = 0.0f;
+    for (int l = 0; l < L; ++l) c[5 + l] = sys[OFF_L + LSTR * l + lMASS];
+    if (ctx != 0)
+      for (int i = 0; i < n_ctx; ++i) c[i] = ctx[(size_t)e * n_ctx + i];
+    memset(zero_act, 0, sizeof(zero_act));
     inverse_kinematics(sys, rows, qq, qqd);
-    make_obs(sys, rows, qq, qqd, ob);
+    make_obs(sys, rows, qq, qqd, c, zero_act, ob);
     for (int i = 0; i < obs_dim; ++i) obs[(size_t)e * obs_dim + i] = (float)ob[i];
   }
 }
@@ -501,38 +688,38 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
                       float *final_obs) {
   real sys[TABLE_N];
   for (int i = 0; i < TABLE_N; ++i) sys[i] = sys_f[i];
-  const int L = (int)sys[hN_LINKS], A = (int)sys[hN_ACT], NF = (int)sys[hN_FRAMES], env = (int)sys[hENV];
+  const int A = (int)sys[hN_ACT], NF = (int)sys[hN_FRAMES], env = (int)sys[hENV];
   const int nq = (int)sys[hN_Q], nqd = (int)sys[hN_QD];
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)
 #endif
   for (int e = 0; e < n; ++e) {
     real *rows = state + (size_t)e * state_words;
-    real c[5 + MAXL], act[MAXL];
+    real c[5 + MAXL], act[MAXQ];
     for (int i = 0; i < n_ctx; ++i) c[i] = ctx[(size_t)e * n_ctx + i];
     for (int i = 0; i < A; ++i) act[i] = actions[(size_t)e * A + i];
-    real tau[MAXL];
+    real tau[MAXL][3];
     real act_sq = 0.0f;
     for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
-    for (int l = 0; l < L; ++l) {
-      const real *lt = sys + OFF_L + LSTR * l;
-      int ai = (int)lt[lACT];
-      tau[l] = 0.0f;
-      if (ai >= 0) tau[l] = lt[lGEAR] * FMIN(FMAX(act[ai], lt[lCLO]), lt[lCHI]);
-    }
+    actuator_taus(sys, act, tau);
     f3 o0, o1;
     origin_of(rows, sys + OFF_L, o0);
+    if (env == E_HUMANOID) body_com(sys, rows, c, o0); /* humanoid: velocity of the body COM, not of the torso */
     for (int f = 0; f < NF; ++f) substep(sys, rows, c, tau);
     origin_of(rows, sys + OFF_L, o1);
+    real z_root = o1[2];
+    if (env == E_HUMANOID) body_com(sys, rows, c, o1);
     real q[MAXQ], qd[MAXQ];
     inverse_kinematics(sys, rows, q, qd);
-    real ob[64];
-    make_obs(sys, rows, q, qd, ob);
+    real ob[MAXOBS];
+    make_obs(sys, rows, q, qd, c, act, ob);
     real dt_env = sys[hDT] * sys[hN_FRAMES];
     real xvel = (o1[0] - o0[0]) / dt_env;
     int healthy = 1;
     if (env == E_ANT) {
       healthy = !(o1[2] < sys[hZMIN]) && !(o1[2] > sys[hZMAX]);
+    } else if (env == E_HUMANOID) { /* brax.envs.humanoid.step: torso z inside healthy_z_range */
+      healthy = !(z_root < sys[hZMIN]) && !(z_root > sys[hZMAX]);
     } else if (env == E_HOPPER) {
       int ok = 1;
       for (int i = 2; i < nq; ++i) ok = ok && (q[i] > -100.0f) && (q[i] < 100.0f);
@@ -553,6 +740,9 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
       real vel_penalty = 1e-3f * (qd[1] * qd[1]) + 5e-3f * (qd[2] * qd[2]);
       r = 10.0f - dist_penalty - vel_penalty;
       done = tip[2] <= 1.0f;
+    } else if (env == E_STANDUP) { /* brax.envs.humanoidstandup.step: uph_cost + 1 - quad_ctrl_cost, never done */
+      r = (z_root - 0.0f) / dt_env + sys[hHEALTHY] - sys[hCTRL] * act_sq;
+      done = 0;
     } else if (env == E_REACHER) { /* reward_dist + reward_ctrl = -|tip - target| - sum(a^2) */
       real d2 = ob[8] * ob[8] + ob[9] * ob[9] + ob[10] * ob[10];
       r = (0.0f - SQRT(d2)) + (0.0f - act_sq);

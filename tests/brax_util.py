@@ -47,13 +47,17 @@ class BraxHostCheck:
     def _p(a):
         return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
-    def init(self, sysd, q, qd):
+    def init(self, sysd, q, qd, ctx=None):
         n = q.shape[0]
+        if ctx is None:  # stock masses (they enter the humanoid's observation)
+            ctx = np.zeros((n, 5 + sysd["n_links"]), dtype=np.float32)
+            ctx[:, 5:] = np.asarray(sysd["stock_masses"], dtype=np.float32)[None]
+        ctx = np.ascontiguousarray(ctx, dtype=np.float32)
         state = np.zeros((n, sysd["state_words"]), dtype=np.float32)
         obs = np.zeros((n, sysd["obs_dim"]), dtype=np.float32)
         t = np.ascontiguousarray(sysd["table"], dtype=np.float32)
         self.lib.hc_brax_init(self._p(t), n, self._p(np.ascontiguousarray(q)), self._p(np.ascontiguousarray(qd)),
-                              self._p(state), sysd["state_words"], self._p(obs), sysd["obs_dim"])
+                              self._p(state), sysd["state_words"], self._p(obs), sysd["obs_dim"], self._p(ctx), ctx.shape[1])
         return state, obs
 
     def step(self, sysd, state, ctx, actions, elapsed, max_steps, autoreset, first_state, first_obs, stock_contact=0):

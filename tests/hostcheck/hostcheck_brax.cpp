@@ -19,7 +19,22 @@ static void wr(float* p, const LinkState& s) {
   p[7] = s.vel.x; p[8] = s.vel.y; p[9] = s.vel.z; p[10] = s.ang.x; p[11] = s.ang.y; p[12] = s.ang.z;
 }
 
-static void obs_of(const float* sys, const LinkState* st, float* obs, float* root /*x,z,angle,ok,q1,qd1,qd2,site xyz*/) {
+// actuator torques of the (up to three) dofs of link l: gear * clip(action)
+static void taus_of(const float* sys, int l, const float* act, float* tau) {
+  const float* lt = link_tab(sys, l);
+  const float* dt = dof_tab(sys, l);
+  const int ai[3] = {(int)lt[L_ACT], (int)dt[D_ACT1], (int)dt[D_ACT2]};
+  const float gear[3] = {lt[L_GEAR], dt[D_GEAR1], dt[D_GEAR2]};
+  const int type = (int)lt[L_TYPE];
+  const int nd = type == TYPE_FREE ? 0 : type_ndof(type);
+  for (int d = 0; d < 3; ++d) {
+    tau[d] = 0.0f;
+    if (d < nd && ai[d] >= 0) tau[d] = gear[d] * fminf(fmaxf(act[ai[d]], lt[L_CTRL_LO]), lt[L_CTRL_HI]);
+  }
+}
+
+static void obs_of(const float* sys, const LinkState* st, float* obs, float* root /*x,z,angle,ok,q1,qd1,qd2,site xyz*/,
+                   const float* masses, const float* act) {
   const int L = (int)sys[H_N_LINKS], nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
   float q[MAX_Q], qd[MAX_Q];
   for (int l = 0; l < L; ++l) {
@@ -30,7 +45,8 @@ static void obs_of(const float* sys, const LinkState* st, float* obs, float* roo
       q[qi] = o.x; q[qi + 1] = o.y; q[qi + 2] = o.z; q[qi + 3] = st[l].rot.w; q[qi + 4] = st[l].rot.x; q[qi + 5] = st[l].rot.y; q[qi + 6] = st[l].rot.z;
       qd[qdi] = vo.x; qd[qdi + 1] = vo.y; qd[qdi + 2] = vo.z; qd[qdi + 3] = al.x; qd[qdi + 4] = al.y; qd[qdi + 5] = al.z;
     } else {
-      const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], 0.0f);
+      const JointOut jo = joint_resolve<true, true>(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent),
+                                                    st[parent < 0 ? 0 : parent], 0.0f, 1.0f, dof_tab(sys, l));
       const int nd = type_ndof(type);
       for (int k = 0; k < nd; ++k) { q[qi + k] = jo.q[k]; qd[qdi + k] = jo.qd[k]; }
     }
@@ -40,8 +56,28 @@ static void obs_of(const float* sys, const LinkState* st, float* obs, float* roo
   int k = 0;
   const int kind = (int)sys[H_ENV];
   V3 site = v3(0, 0, 0);
-  if (kind >= ENV_INVERTED_PENDULUM) site = site_position(sys, st[(int)sys[H_SITE_LINK]], st[kind == ENV_REACHER ? 2 : 0]);
-  if (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER) {
+  if (kind >= ENV_INVERTED_PENDULUM && kind <= ENV_REACHER) site = site_position(sys, st[(int)sys[H_SITE_LINK]], st[kind == ENV_REACHER ? 2 : 0]);
+  float comx = 0.0f;
+  if (kind == ENV_HUMANOID || kind == ENV_HUMANOIDSTANDUP) {
+    // brax.envs.humanoid._get_obs, laid out as the kernel does: q[2:] | qd | cinert | cvel | actuator torques
+    float rows[MAX_LINKS * LINK_WORDS], meff[MAX_LINKS];
+    for (int l = 0; l < L; ++l) { wr(rows + l * LINK_WORDS, st[l]); meff[l] = eff_mass(masses[l], sys); }
+    V3 com;
+    const float msum = body_com(rows, meff, L, com);
+    comx = com.x;
+    for (int i = 2; i < nq; ++i) obs[k++] = q[i];
+    for (int i = 0; i < nqd; ++i) obs[k++] = qd[i];
+    for (int l = 0; l < L; ++l) { link_cinert(sys, link_tab(sys, l), st[l], meff[l], com, obs + k); k += 10; }
+    for (int l = 0; l < L; ++l) { link_cvel(st[l], meff[l], msum, obs + k); k += 6; }
+    for (int i = 0; i < nqd; ++i) obs[k + i] = 0.0f;
+    for (int l = 0; l < L; ++l) {
+      const float* lt = link_tab(sys, l);
+      if ((int)lt[L_TYPE] == TYPE_FREE) continue;
+      float tau[3];
+      taus_of(sys, l, act, tau);
+      for (int d = 0; d < type_ndof((int)lt[L_TYPE]); ++d) obs[k + (int)lt[L_QDIDX] + d] = tau[d];
+    }
+  } else if (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER) {
     const int D = kind == ENV_REACHER ? 11 : 8;
     for (int i = 0; i < D; ++i) obs[i] = special_obs_entry(kind, i, q, qd, site);
   } else {
@@ -53,26 +89,27 @@ static void obs_of(const float* sys, const LinkState* st, float* obs, float* roo
   for (int i = 2; i < nq; ++i) ok = ok && q[i] > -100.0f && q[i] < 100.0f;
   for (int i = 0; i < nqd; ++i) ok = ok && qd[i] > -100.0f && qd[i] < 100.0f;
   const V3 o0 = link_origin(st[0], link_tab(sys, 0));
-  root[0] = o0.x; root[1] = o0.z; root[2] = ((int)link_tab(sys, 0)[L_TYPE] == TYPE_PLANAR) ? q[2] : 0.0f; root[3] = ok ? 1.0f : 0.0f;
+  root[0] = kind == ENV_HUMANOID ? comx : o0.x; root[1] = o0.z; root[2] = ((int)link_tab(sys, 0)[L_TYPE] == TYPE_PLANAR) ? q[2] : 0.0f; root[3] = ok ? 1.0f : 0.0f;
 }
 
 extern "C" {
 
-void hc_brax_init(const float* sys, int n, const float* q_all, const float* qd_all, float* state, int words, float* obs, int D) {
+void hc_brax_init(const float* sys, int n, const float* q_all, const float* qd_all, float* state, int words, float* obs, int D,
+                  const float* ctx, int n_ctx) {
   const int L = (int)sys[H_N_LINKS], nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
   for (int e = 0; e < n; ++e) {
     LinkState st[MAX_LINKS];
     for (int l = 0; l < L; ++l) {
       const float* lt = link_tab(sys, l);
       const int parent = (int)lt[L_PARENT];
-      st[l] = forward_link(sys, lt, q_all + (size_t)e * nq, qd_all + (size_t)e * nqd, parent < 0,
-                           link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent]);
+      st[l] = forward_link<true>(sys, lt, q_all + (size_t)e * nq, qd_all + (size_t)e * nqd, parent < 0,
+                                 link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], dof_tab(sys, l));
     }
     float* rows = state + (size_t)e * words;
     memset(rows, 0, sizeof(float) * words);
     for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);
-    float root[10];
-    obs_of(sys, st, obs + (size_t)e * D, root);
+    float root[10], zero_act[MAX_ACT] = {0};
+    obs_of(sys, st, obs + (size_t)e * D, root, ctx + (size_t)e * n_ctx + C_MASS0, zero_act);
   }
 }
 
@@ -86,8 +123,8 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     const float* act = actions + (size_t)e * A;
     LinkState st[MAX_LINKS];
     for (int l = 0; l < L; ++l) st[l] = rd(rows + l * LINK_WORDS);
-    float before[10], after[10], ob[64];
-    obs_of(sys, st, ob, before);
+    float before[10], after[10], ob[MAX_OBS_LARGE];
+    obs_of(sys, st, ob, before, c + C_MASS0, act);
     float act_sq = 0.0f;
     for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
     LinkConst lcs[MAX_LINKS];
@@ -98,10 +135,12 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         w[l].f = v3(0, 0, 0); w[l].t = v3(0, 0, 0); pw[l] = w[l];
         const float* lt = link_tab(sys, l);
         if ((int)lt[L_TYPE] == TYPE_FREE) continue;
-        const int parent = (int)lt[L_PARENT], ai = (int)lt[L_ACT];
-        float tau = 0.0f;
-        if (ai >= 0) tau = lt[L_GEAR] * fminf(fmaxf(act[ai], lt[L_CTRL_LO]), lt[L_CTRL_HI]);
-        const JointOut jo = joint_resolve(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent), st[parent < 0 ? 0 : parent], tau, c[C_STIFFNESS_SCALE]);
+        const int parent = (int)lt[L_PARENT];
+        float tau[3];
+        taus_of(sys, l, act, tau);
+        const JointOut jo = joint_resolve<true, true>(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent),
+                                                      st[parent < 0 ? 0 : parent], tau[0], c[C_STIFFNESS_SCALE], dof_tab(sys, l),
+                                                      tau[1], tau[2]);
         w[l] = jo.child; pw[l] = jo.parent;
       }
       LinkState nx[MAX_LINKS];
@@ -130,12 +169,12 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         st[l] = nx[l];
       }
     }
-    obs_of(sys, st, ob, after);
+    obs_of(sys, st, ob, after, c + C_MASS0, act);
     const float dt_env = sys[H_DT] * sys[H_N_FRAMES];
     const float xvel = (after[0] - before[0]) / dt_env;
     const int kind = (int)sys[H_ENV];
     bool healthy = true;
-    if (kind == ENV_ANT) healthy = !(after[1] < sys[H_HEALTHY_Z_MIN]) && !(after[1] > sys[H_HEALTHY_Z_MAX]);
+    if (kind == ENV_ANT || kind == ENV_HUMANOID) healthy = !(after[1] < sys[H_HEALTHY_Z_MIN]) && !(after[1] > sys[H_HEALTHY_Z_MAX]);
     else if (kind == ENV_HOPPER)
       healthy = after[3] > 0.5f && sys[H_HEALTHY_Z_MIN] < after[1] && after[1] < sys[H_HEALTHY_Z_MAX] &&
                 sys[H_ANGLE_MIN] < after[2] && after[2] < sys[H_ANGLE_MAX];
@@ -144,7 +183,10 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
                 !(after[2] < sys[H_ANGLE_MIN]);
     float r = sys[H_FORWARD_WEIGHT] * xvel + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
     bool done = sys[H_TERMINATE] > 0.0f && !healthy;
-    if (kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after[4], after[5], after[6], v3(after[7], after[8], after[9]), act_sq, r, done);
+    if (kind == ENV_HUMANOIDSTANDUP) {  // uph_cost + 1 - quad_ctrl_cost, never done
+      r = (after[1] - 0.0f) / dt_env + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
+      done = false;
+    } else if (kind >= ENV_INVERTED_PENDULUM && kind <= ENV_REACHER) special_outcome(kind, after[4], after[5], after[6], v3(after[7], after[8], after[9]), act_sq, r, done);
     elapsed[e] += 1;
     if (max_steps > 0 && elapsed[e] >= max_steps) done = true;
     for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);

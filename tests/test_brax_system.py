@@ -8,8 +8,9 @@ import numpy as np
 import pytest
 
 from carl_b200.envs import brax_system as bs
-from carl_b200.envs.brax import (CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxInvertedDoublePendulum,
-                                 CARLBraxInvertedPendulum, CARLBraxReacher, CARLBraxWalker2d)
+from carl_b200.envs.brax import (CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxHumanoid,
+                                 CARLBraxHumanoidStandup, CARLBraxInvertedDoublePendulum, CARLBraxInvertedPendulum,
+                                 CARLBraxReacher, CARLBraxWalker2d)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -53,7 +54,8 @@ def test_shapes_match_reference_observation_sizes():
 def test_every_mass_feature_names_a_link():
     for cls, key in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
                      (CARLBraxWalker2d, "walker2d"), (CARLBraxInvertedPendulum, "inverted_pendulum"),
-                     (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher")):
+                     (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher"),
+                     (CARLBraxHumanoid, "humanoid"), (CARLBraxHumanoidStandup, "humanoidstandup")):
         links = bs.SYSTEMS[key]["link_names"]
         for f in cls.get_context_features():
             if f.startswith("mass_"):
@@ -109,7 +111,7 @@ def _enum_values(text, enum_name):
 
 def test_table_layout_identical_in_python_and_cuda_header():
     text = open(os.path.join(ROOT, "carl_b200", "csrc", "physics_brax.h")).read()
-    for name in ("MAX_LINKS", "MAX_POINTS", "MAX_Q", "HEADER", "LINK_STRIDE", "POINT_STRIDE"):
+    for name in ("MAX_LINKS", "MAX_POINTS", "MAX_Q", "HEADER", "LINK_STRIDE", "POINT_STRIDE", "DOF_STRIDE"):
         assert int(re.search(rf"constexpr int {name} = (\d+);", text).group(1)) == getattr(bs, name)
     hdr = _enum_values(text, "Hdr")
     for k, v in hdr.items():
@@ -117,6 +119,10 @@ def test_table_layout_identical_in_python_and_cuda_header():
     ls = _enum_values(text, "LinkSlot")
     for k, v in ls.items():
         assert getattr(bs, k) == v, k
+    for enum in ("DofSlot", "LinkType", "EnvId"):
+        for k, v in _enum_values(text, enum).items():
+            assert getattr(bs, k) == v, k
+    assert bs.OFF_DOF == bs.OFF_INIT_Q + bs.MAX_Q and bs.TABLE_FLOATS == bs.OFF_DOF + bs.DOF_STRIDE * bs.MAX_LINKS
     assert bs.TABLE_FLOATS * 4 % 16 == 0  # TMA bulk copies move multiples of 16 bytes
 
 
@@ -158,7 +164,7 @@ def test_contact_schedule_is_a_permutation_with_the_feet_first():
 
 
 def test_humanoid_geometry_matches_carl_masses():
-    """Groundwork for the humanoid (not buildable yet): the per-link geoms reproduce every MJCF-derived mass default of
+    """The humanoid's per-link geoms reproduce every MJCF-derived mass default of
     carl/envs/brax/carl_humanoid.py:41-75 to 7 digits (``mass_torso = 10`` there is a placeholder, like the Ant's)."""
     want = {"lwaist": 2.2619467, "pelvis": 6.6161942, "right_thigh": 4.751751, "right_shin": 4.522842,
             "left_thigh": 4.751751, "left_shin": 4.522842, "right_upper_arm": 1.6610805, "right_lower_arm": 1.2295402,
@@ -168,3 +174,36 @@ def test_humanoid_geometry_matches_carl_masses():
     for name, m in want.items():
         assert bs.body_inertia(geo[name], 1000.0)[0] == pytest.approx(m, rel=2e-7), name
     assert bs.body_inertia(geo["torso"], 1000.0)[0] == pytest.approx(8.907463, rel=1e-6)  # the MJCF's own torso mass
+
+
+def test_humanoid_tables():
+    """carl/envs/brax/carl_humanoid.py / carl_humanoidstandup.py: 11 links, q 24 / qd 23, 17 actuators in the MJCF
+    order, the 244-entry observation of brax.envs.humanoid; the masses of both systems are CARL's defaults; the
+    stacked-hinge rows carry orthogonal right-handed joint frames, and the hips' third coordinate runs against z."""
+    for key, cls in (("humanoid", CARLBraxHumanoid), ("humanoidstandup", CARLBraxHumanoidStandup)):
+        s = bs.SYSTEMS[key]
+        assert (s["n_links"], s["n_q"], s["n_qd"], s["obs_dim"], s["n_act"], s["n_points"]) == (11, 24, 23, 244, 17, 29)
+        assert s["act_scale"] == pytest.approx(0.4) and s["dt"] == pytest.approx(0.015)
+        d = cls.get_context_space().get_default_context()
+        for name, m in zip(s["link_names"][1:], s["stock_masses"][1:]):
+            assert m == pytest.approx(d[f"mass_{name}"], rel=2e-7), name
+        t = s["table"]
+        acts = []
+        for l, name in enumerate(s["link_names"]):
+            o, dr = bs.OFF_LINKS + bs.LINK_STRIDE * l, bs.OFF_DOF + bs.DOF_STRIDE * l
+            typ = int(t[o + bs.L_TYPE])
+            nd = 0 if typ == bs.TYPE_FREE else bs.TYPE_DOFS[typ][1]
+            acts += [int(v) for v in (t[o + bs.L_ACT], t[dr + bs.D_ACT1], t[dr + bs.D_ACT2])[:nd]]
+            q = t[o + bs.L_JROT:o + bs.L_JROT + 4].astype(np.float64)
+            assert abs(np.linalg.norm(q) - 1.0) < 1e-6
+            assert np.linalg.det(bs.quat_to_mat(q)) == pytest.approx(1.0, abs=1e-6)
+            if name.endswith("thigh"):
+                assert typ == bs.TYPE_HINGE3 and t[dr + bs.D_SIGN2] == -1.0
+        assert sorted(acts) == list(range(17))
+    # standing vs lying: the standup system is the same body expressed in frames turned by -90 deg about y
+    up, lying = bs.SYSTEMS["humanoid"]["table"], bs.SYSTEMS["humanoidstandup"]["table"]
+    head_up = up[bs.OFF_POINTS + bs.POINT_STRIDE * 2 + 1:bs.OFF_POINTS + bs.POINT_STRIDE * 2 + 4]
+    head_ly = lying[bs.OFF_POINTS + bs.POINT_STRIDE * 2 + 1:bs.OFF_POINTS + bs.POINT_STRIDE * 2 + 4]
+    np.testing.assert_allclose(head_up, (0, 0, 0.19), atol=1e-7)
+    np.testing.assert_allclose(head_ly, (-0.19, 0, 0), atol=1e-7)
+    assert lying[bs.OFF_INIT_Q + 2] == pytest.approx(0.105)

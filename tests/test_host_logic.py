@@ -203,7 +203,7 @@ def test_brax_param_rows_and_shapes_match_native_query(native_lib):
     from carl_b200.envs import brax_system as bs
 
     for name in ("CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d", "CARLBraxInvertedPendulum",
-                 "CARLBraxInvertedDoublePendulum", "CARLBraxReacher"):
+                 "CARLBraxInvertedDoublePendulum", "CARLBraxReacher", "CARLBraxHumanoid", "CARLBraxHumanoidStandup"):
         cls = getattr(E, name)
         info = _native.query_env(_native.KIND[cls.kind])
         sysd = bs.SYSTEMS[cls.env_name]
@@ -218,7 +218,7 @@ def test_brax_param_rows_and_shapes_match_native_query(native_lib):
         for j, ln in enumerate(sysd["link_names"]):
             want = d.get(f"mass_{ln}", sysd["stock_masses"][j])
             assert applied[0, 5 + j] == pytest.approx(want)
-    assert E.brax.UNSUPPORTED_BODIES == ("CARLBraxHumanoid", "CARLBraxHumanoidStandup", "CARLBraxPusher")
+    assert E.brax.UNSUPPORTED_BODIES == ("CARLBraxPusher",)
     for name in E.brax.UNSUPPORTED_BODIES:  # asking for them fails loudly, nothing is substituted
         with pytest.raises(NotImplementedError, match="not built"):
             getattr(E, name)
