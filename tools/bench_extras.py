@@ -9,8 +9,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from carl_b200.context import ContextSampler, UniformFloatContextFeature
-from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxInvertedDoublePendulum,
-                            CARLBraxInvertedPendulum, CARLBraxReacher, CARLBraxWalker2d, CARLPendulum, ContextTable, MixedBatch)
+from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxHumanoid, CARLBraxHumanoidStandup,
+                            CARLBraxInvertedDoublePendulum, CARLBraxInvertedPendulum, CARLBraxReacher, CARLBraxWalker2d,
+                            CARLPendulum, ContextTable, MixedBatch)
 
 
 def table(cls, feats, n):
@@ -33,8 +34,31 @@ def timed(fn, iters, warm=5):
     return e0.elapsed_time(e1) / iters
 
 
+def brax_bodies(out, bodies):
+    nb = 8192
+    for cls, feats, name in bodies:
+        for arithmetic in ("strict", "fma"):
+            env = cls(contexts=table(cls, feats, nb), context_mode="applied", arithmetic=arithmetic)
+            env.reset(seed=0)
+            T = 20
+            ms = timed(lambda: env.rollout(T, policy_seed=1, record=False), 10, warm=2)
+            a = (torch.rand(nb, env._info.act_dim, device="cuda") * 2 - 1) * env._sysd["act_scale"]
+            ms1 = timed(lambda: env.step(a), 50)
+            key = f"config5_{name}" + ("" if arithmetic == "strict" else "_fma")
+            out[key] = {"workload": f"{cls.__name__} {nb} contexts", "fused_env_steps_per_s": nb * T / (ms * 1e-3),
+                        "step_api_env_steps_per_s": nb / (ms1 * 1e-3), "step_us": ms1 * 1e3}
+
+
+HUMANOIDS = ((CARLBraxHumanoid, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "humanoid"),
+             (CARLBraxHumanoidStandup, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "humanoidstandup"))
+
+
 def main():
     out = {}
+    if "--only-humanoid" in sys.argv:
+        brax_bodies(out, HUMANOIDS)
+        print(json.dumps(out))
+        return
     n = 32768
     pen = CARLPendulum(contexts=table(CARLPendulum, {"g": (5, 15), "m": (0.5, 2), "l": (0.5, 2)}, n), autoreset=True)
     acr = CARLAcrobot(contexts=table(CARLAcrobot, {"LINK_MASS_1": (0.5, 2), "LINK_MASS_2": (0.5, 2), "LINK_LENGTH_1": (0.5, 2)}, n),
@@ -62,22 +86,14 @@ def main():
         T = 100
         ms = timed(lambda: env.rollout(T, policy_seed=1, record=False), 10, warm=2)
         out[f"config3_{name}_fused"] = {"env_steps_per_s": n * T / (ms * 1e-3), "ms_per_100_steps": ms}
-    nb = 8192
-    for cls, feats, name in ((CARLBraxHalfcheetah, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "halfcheetah"),
-                             (CARLBraxHopper, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "hopper"),
-                             (CARLBraxWalker2d, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "walker2d"),
-                             (CARLBraxInvertedPendulum, {"gravity": (-15, -5), "mass_cart": (5, 20), "mass_pole": (2, 8)}, "inverted_pendulum"),
-                             (CARLBraxInvertedDoublePendulum, {"gravity": (-15, -5), "mass_cart": (5, 20), "mass_pole": (2, 8)},
-                              "inverted_double_pendulum"),
-                             (CARLBraxReacher, {"gravity": (-15, -5), "mass_body0": (0.02, 0.06), "mass_body1": (0.02, 0.06)}, "reacher")):
-        env = cls(contexts=table(cls, feats, nb), context_mode="applied")
-        env.reset(seed=0)
-        T = 20
-        ms = timed(lambda: env.rollout(T, policy_seed=1, record=False), 10, warm=2)
-        a = torch.rand(nb, env._info.act_dim, device="cuda") * 2 - 1
-        ms1 = timed(lambda: env.step(a), 50)
-        out[f"config5_{name}"] = {"workload": f"{cls.__name__} {nb} contexts", "fused_env_steps_per_s": nb * T / (ms * 1e-3),
-                                  "step_api_env_steps_per_s": nb / (ms1 * 1e-3), "step_us": ms1 * 1e3}
+    brax_bodies(out, ((CARLBraxHalfcheetah, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "halfcheetah"),
+                      (CARLBraxHopper, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "hopper"),
+                      (CARLBraxWalker2d, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "walker2d"),
+                      (CARLBraxInvertedPendulum, {"gravity": (-15, -5), "mass_cart": (5, 20), "mass_pole": (2, 8)}, "inverted_pendulum"),
+                      (CARLBraxInvertedDoublePendulum, {"gravity": (-15, -5), "mass_cart": (5, 20), "mass_pole": (2, 8)},
+                       "inverted_double_pendulum"),
+                      (CARLBraxReacher, {"gravity": (-15, -5), "mass_body0": (0.02, 0.06), "mass_body1": (0.02, 0.06)}, "reacher"))
+                + HUMANOIDS)
     print(json.dumps(out))
 
 
