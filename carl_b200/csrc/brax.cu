@@ -38,6 +38,14 @@ namespace carlb {
 namespace CARLB_BRAX_VARIANT {
 using namespace brax;
 
+// FAST arithmetic of the FMA build: the world-frame hinge and the unit-inertia shortcut (physics_brax.h) -- identical
+// mathematics, different rounding; the strict build keeps the restated reference order everywhere.
+#ifdef CARLB_BRAX_FMA_BUILD
+constexpr bool FAST = true;
+#else
+constexpr bool FAST = false;
+#endif
+
 // Warps (= env instances) per CTA. 4 x 128-thread CTAs per SM is the default; for batches of several
 // thousand envs a 7-warp CTA (2 resident per SM = 14 warps) makes the grid an almost exact multiple
 // of the machine: 8 192 envs = 3.96 waves of 148 SMs x 14 warps instead of 3.46 waves of 16.
@@ -198,49 +206,64 @@ struct LaneCtx {
   V3 anchor_p;       // my joint's anchor in the parent link frame (table-only)
   int jflags;        // JointFlags of my joint (table-only)
   const float* dt;   // my link's dof row (stacked hinges: humanoid kernels only)
+  unsigned children; // bit k set: link k is a child of my link (table-only)
+  V3 anchor_pc;      // anchor_p relative to the parent's centre of mass (FAST hinge; table-only)
 };
 
 // n_frames spring substeps for the sub-envs of this warp. `s` is this lane's link.
+// `reach`: per contact candidate, the COM height above which it cannot touch the ground (contact_reach; per CTA).
 template <int E, int M>
 __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, typename ScratchOf<M>::type& w, LinkState& s,
-                                               float tau, float tau1 = 0.0f, float tau2 = 0.0f) {
+                                               const float* reach, float tau, float tau1 = 0.0f, float tau2 = 0.0f) {
   constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
   constexpr int LPE = Lanes<E>::LPE;
   const float dt = sys[H_DT];
   const int n_pass = (c.P + LPE - 1) / LPE;
+  // Every link publishes its state and (strict arithmetic) its link-frame origin once per substep, right after the
+  // pose integration: the joint phase of the next substep reads the parent's origin instead of re-deriving it, and the
+  // contact phase reads the candidate's. The FAST arithmetic works from the centres of mass and needs no origins.
+  if (c.is_link) {
+    write_link(w.ls, c.sl, s);
+    if (!FAST) {
+      const V3 o0 = link_origin(s, c.lt);
+      float* og = w.org + c.sl * 3;
+      og[0] = o0.x; og[1] = o0.y; og[2] = o0.z;
+    }
+  }
   for (int f = 0; f < c.n_frames; ++f) {
-    if (c.is_link) write_link(w.ls, c.sl, s);
     __syncwarp();
     // joints: sub-lane l resolves the joint between link l and its parent
     Wrench wr;
     wr.f = v3(0, 0, 0); wr.t = v3(0, 0, 0);
     if (c.is_link && c.type != TYPE_FREE) {
       const bool world_parent = c.parent < 0;
-      const LinkState ps = read_link(w.ls, world_parent ? 0 : c.parent);
-      const JointOut jo = joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p,
-                                                c.jflags, c.dt, tau1, tau2);
+      const int pi = world_parent ? 0 : c.parent;
+      const LinkState ps = read_link(w.ls, pi);
+      JointOut jo;
+      if (FAST) {
+        jo = (c.type == TYPE_HINGE)
+                 ? joint_resolve_world(sys, c.lt, s, world_parent, ps, tau, c.stiffness_scale, c.anchor_pc, c.jflags)
+                 : joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags,
+                                         c.dt, tau1, tau2);
+      } else {
+        const V3 origins[2] = {ld3(w.org + c.sl * 3), ld3(w.org + pi * 3)};
+        jo = joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags, c.dt,
+                                   tau1, tau2, origins);
+      }
       wr = jo.child;
       float* pw = w.pw + c.sl * 6;
       pw[0] = jo.parent.f.x; pw[1] = jo.parent.f.y; pw[2] = jo.parent.f.z;
       pw[3] = jo.parent.t.x; pw[4] = jo.parent.t.y; pw[5] = jo.parent.t.z;
-      float* og = w.org + c.sl * 3;
-      og[0] = jo.origin.x; og[1] = jo.origin.y; og[2] = jo.origin.z;
-    } else if (c.is_link && c.P > 0) {  // free root: no joint, but its contact points need the origin too
-      const V3 o0 = link_origin(s, c.lt);
-      float* og = w.org + c.sl * 3;
-      og[0] = o0.x; og[1] = o0.y; og[2] = o0.z;
     }
     __syncwarp();
     if (c.is_link) {
-      // add the reactions of my children (fixed order: deterministic sums)
-      for (int k = c.sl + 1; k < c.L; ++k) {
-        if ((int)link_tab(sys, k)[L_PARENT] == c.sl) {
-          const float* pw = w.pw + k * 6;
-          wr.f = wr.f + v3(pw[0], pw[1], pw[2]);
-          wr.t = wr.t + v3(pw[3], pw[4], pw[5]);
-        }
+      // add the reactions of my children (ascending link order: deterministic sums)
+      for (unsigned m = c.children; m != 0u; m &= m - 1u) {
+        const float* pw = w.pw + (__ffs((int)m) - 1) * 6;
+        wr.f = wr.f + v3(pw[0], pw[1], pw[2]);
+        wr.t = wr.t + v3(pw[3], pw[4], pw[5]);
       }
-      integrate_xdd(s, wr, sys, c.lt, c.lc, c.gravity);
+      integrate_xdd<FAST>(s, wr, sys, c.lt, c.lc, c.gravity);
       write_link(w.ls, c.sl, s);
     }
     __syncwarp();
@@ -253,12 +276,17 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
         const int p = (int)point_tab(sys, slot)[P_SCHED];
         const float* pt = point_tab(sys, p);
         const int pl = (int)pt[0];
-        const LinkState ps = read_link(w.ls, pl);
-        const float fr = (c.stock_contact || w.ctx[C_FRICTION] < 0.0f) ? pt[5] : w.ctx[C_FRICTION];
-        const float el = (c.stock_contact || w.ctx[C_ELASTICITY] < 0.0f) ? pt[6] : w.ctx[C_ELASTICITY];
-        const ContactOut co = contact_resolve(sys, pt, link_tab(sys, pl), ps, read_lc(w.lc, pl), fr, el, ld3(w.org + pl * 3));
         float* o = w.co + p * 7;
-        o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
+        if (w.ls[pl * LINK_WORDS + 2] > reach[p]) {
+          o[6] = 0.0f;  // the link's COM is higher than the candidate can reach down: inactive (only the flag is read)
+        } else {
+          const LinkState ps = read_link(w.ls, pl);
+          const float fr = (c.stock_contact || w.ctx[C_FRICTION] < 0.0f) ? pt[5] : w.ctx[C_FRICTION];
+          const float el = (c.stock_contact || w.ctx[C_ELASTICITY] < 0.0f) ? pt[6] : w.ctx[C_ELASTICITY];
+          const ContactOut co = contact_resolve<FAST>(sys, pt, link_tab(sys, pl), ps, read_lc(w.lc, pl), fr, el,
+                                                      FAST ? v3(0, 0, 0) : ld3(w.org + pl * 3));
+          o[0] = co.p.x; o[1] = co.p.y; o[2] = co.p.z; o[3] = co.t.x; o[4] = co.t.y; o[5] = co.t.z; o[6] = co.active;
+        }
       }
     }
     __syncwarp();
@@ -268,15 +296,24 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
       const int p0 = (int)c.lt[L_FIRST_PT], np = (int)c.lt[L_N_PT];
       for (int k = p0; k < p0 + np; ++k) {
         const float* o = w.co + k * 7;
-        ps = ps + v3(o[0], o[1], o[2]);
-        ts = ts + v3(o[3], o[4], o[5]);
-        na += o[6];
+        const float on = o[6];
+        if (on != 0.0f) {  // an inactive candidate holds exact zeros: skipping it leaves the sums bit-identical
+          ps = ps + v3(o[0], o[1], o[2]);
+          ts = ts + v3(o[3], o[4], o[5]);
+          na += on;
+        }
       }
-      integrate_xdv(s, ps, ts, na, c.lt, c.lc);
+      integrate_xdv<FAST>(s, ps, ts, na, c.lt, c.lc);
       integrate_pose(s, dt);
+      write_link(w.ls, c.sl, s);
+      if (!FAST) {
+        const V3 o0 = link_origin(s, c.lt);
+        float* og = w.org + c.sl * 3;
+        og[0] = o0.x; og[1] = o0.y; og[2] = o0.z;
+      }
     }
-    __syncwarp();
   }
+  __syncwarp();
 }
 
 // kinematics.inverse + env observation: fills w.obs[0..D) and returns the root facts of the sub-env
@@ -424,6 +461,7 @@ struct SmemLayoutT {
   float sys[TABLE_FLOATS];
   typename ScratchOf<M>::type env[W * E];
   uint64_t bar;
+  float reach[MAX_POINTS];  // contact_reach of every candidate (table-only)
 };
 
 // Per-lane setup shared by the step and reset kernels: lane mapping, context staging (one strided
@@ -450,7 +488,12 @@ __device__ __forceinline__ LaneCtx make_lane_ctx(const float* sys, const BraxSeg
   c.stock_contact = stock_contact;
   c.anchor_p = parent_anchor(c.lt);
   c.jflags = joint_flags(c.lt);
+  c.anchor_pc = parent_anchor_from_com(c.lt, c.plt, c.parent < 0);
   c.dt = dof_tab(sys, l);
+  c.children = 0u;
+  if (c.is_link)
+    for (int k = l + 1; k < c.L; ++k)
+      if ((int)link_tab(sys, k)[L_PARENT] == l) c.children |= 1u << k;
   if (active && sl < LPE) {
     const float* row = seg.ctx + (size_t)env * seg.n_ctx;
     for (int i = sl; i < seg.n_ctx; i += LPE) w.ctx[i] = row[i];
@@ -543,7 +586,7 @@ __device__ __forceinline__ void brax_step_body(const BraxSeg& seg, SmemLayoutT<W
       if (c.is_link && a1 >= 0) tau1 = c.dt[D_GEAR1] * fminf(fmaxf(w.act[a1], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
       if (c.is_link && a2 >= 0) tau2 = c.dt[D_GEAR2] * fminf(fmaxf(w.act[a2], c.lt[L_CTRL_LO]), c.lt[L_CTRL_HI]);
     }
-    pipeline_steps<E, M>(sys, c, w, s, tau, tau1, tau2);
+    pipeline_steps<E, M>(sys, c, w, s, sm.reach, tau, tau1, tau2);
     const RootFacts after = compute_obs<E, M>(sys, c, w, s);
     env_outcome<M>(sys, before, after, act_sq, reward, done);
     // EpisodeWrapper: steps += 1; done = where(steps >= episode_length, 1, done)
@@ -628,6 +671,11 @@ __global__ void __launch_bounds__(W * 32, W == 4 ? (E >= 3 ? 5 : 4) : 2) brax_st
   extern __shared__ __align__(128) unsigned char smem_raw[];
   SmemLayout& sm = *reinterpret_cast<SmemLayout*>(smem_raw);
   stage_system(sm.sys, seg.sys, &sm.bar);
+  if (threadIdx.x < (int)sm.sys[H_N_POINTS]) {
+    const float* pt = point_tab(sm.sys, threadIdx.x);
+    sm.reach[threadIdx.x] = contact_reach(pt, link_tab(sm.sys, (int)pt[0]));
+  }
+  __syncthreads();
   const unsigned int gseq = gather_begin(seg.gth);
   const int warp = threadIdx.x >> 5;
   if ((blockIdx.x * W + warp) * E < seg.n)  // warp-uniform: at least one sub-env of this warp is real

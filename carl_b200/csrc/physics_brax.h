@@ -192,6 +192,15 @@ CARLB_HD V3 apply_inv_inertia(V3 v, Q4 rot, const float* lt, V3 inv_idiag) {
   return rotate(w, r);
 }
 
+// FAST arithmetic (the FMA-contracted build, `arithmetic="fma"`): mathematically identical reformulations that round
+// differently from the restated reference order -- with unit effective inertia (spring_inertia_scale = 1, every
+// shipped body) I_eff^-1 v is v itself, so the two rotations through the principal frame are skipped.
+template <bool FAST>
+CARLB_HD V3 apply_inv_inertia_sel(V3 v, Q4 rot, const float* lt, V3 inv_idiag) {
+  if (FAST && inv_idiag.x == 1.0f && inv_idiag.y == 1.0f && inv_idiag.z == 1.0f) return v;
+  return apply_inv_inertia(v, rot, lt, inv_idiag);
+}
+
 // ---- joints (brax.spring.joints.resolve, one joint) ------------------------------------------
 // Output of one joint: force/torque in the WORLD frame acting on the child at its anchor `a_c`
 // and the opposite reaction on the parent at its anchor `a_p`; plus the joint coordinate (q, qd)
@@ -243,16 +252,20 @@ CARLB_HD EulerAxes euler_axes(Q4 jrot) {
 
 // STACKED = true compiles the 2- / 3-dof revolute branches in (humanoid kernels only); `dt` is the link's dof row,
 // `tau1` / `tau2` the actuator torques of dofs 1 and 2.
+// `origins` (optional): the link-frame origins of the child and of the parent, already evaluated by their owners with
+// link_origin() on these very states (the kernel shares them through its scratch: one rotation per link and substep
+// instead of three); nullptr = evaluate them here. Same function of the same inputs: identical values.
 template <bool SLIDES = true, bool STACKED = false>
 CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkState& c, bool world_parent,
                                 const float* plt, const LinkState& p, float tau, float stiffness_scale, V3 anchor_p,
-                                int flags, const float* dt = nullptr, float tau1 = 0.0f, float tau2 = 0.0f) {
+                                int flags, const float* dt = nullptr, float tau1 = 0.0f, float tau2 = 0.0f,
+                                const V3* origins = nullptr) {
   JointOut o;
   const int type = (int)lt[L_TYPE];
   const Q4 t_rot = ld4(lt + L_TROT), j_rot = ld4(lt + L_JROT);
   const V3 t_pos = ld3(lt + L_TPOS), j_pos = ld3(lt + L_JPOS);
   // anchors (kinematics.world_to_joint): a_c = x_c o joint ; a_p = x_p o link.transform o joint
-  const V3 xc_pos = link_origin(c, lt);
+  const V3 xc_pos = origins != nullptr ? origins[0] : link_origin(c, lt);
   o.origin = xc_pos;
   V3 ac_pos = xc_pos;
   if (!(flags & JF_JPOS_ZERO)) ac_pos = xc_pos + rotate(j_pos, c.rot);
@@ -260,7 +273,7 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
   V3 ap_pos, xp_pos = v3(0, 0, 0), vp = v3(0, 0, 0), wp = v3(0, 0, 0), pcom = v3(0, 0, 0);
   Q4 xp_rot = q4(1, 0, 0, 0);
   if (!world_parent) {
-    xp_pos = link_origin(p, plt);
+    xp_pos = origins != nullptr ? origins[1] : link_origin(p, plt);
     xp_rot = p.rot;
     wp = p.ang;
     pcom = p.pos;
@@ -370,12 +383,70 @@ CARLB_HD JointOut joint_resolve(const float* sys, const float* lt, const LinkSta
                                         joint_flags(lt), dt, tau1, tau2);
 }
 
+// anchor of the joint in the parent link frame relative to the PARENT'S CENTRE OF MASS (table-only): with it the
+// world anchor is p.pos + rotate(., p.rot) -- one rotation instead of link_origin + rotate(anchor)
+CARLB_HD V3 parent_anchor_from_com(const float* lt, const float* plt, bool world_parent) {
+  const V3 a = parent_anchor(lt);
+  return world_parent ? a : a - ld3(plt + L_COM);
+}
+
+// FAST arithmetic, revolute joints (TYPE_HINGE) only: the same spring / damper / limit / actuator wrench as
+// joint_resolve, evaluated in the WORLD frame. The positional spring and damper of a hinge are isotropic, so
+// rotating the anchor offset and rate into the joint frame and the force back out is the identity; the axis torques
+// use the world images of the two joint x axes. 2 rotations + 3 quaternion products instead of 8 + 3. Mathematically
+// identical, rounded differently: not comparable bit for bit with the float32 oracle, held to the float64 yardstick
+// like every result of the FMA build (tests/test_brax_parity_gpu.py).
+CARLB_HD JointOut joint_resolve_world(const float* sys, const float* lt, const LinkState& c, bool world_parent,
+                                      const LinkState& p, float tau, float stiffness_scale, V3 anchor_pc, int flags) {
+  JointOut o;
+  const Q4 j_rot = ld4(lt + L_JROT);
+  V3 rc = v3(0, 0, 0) - ld3(lt + L_COM);
+  if (!(flags & JF_JPOS_ZERO)) rc = ld3(lt + L_JPOS) + rc;
+  const V3 lc = rotate(rc, c.rot);  // child anchor relative to the child's COM, world axes
+  const V3 ac_pos = c.pos + lc;
+  o.origin = (flags & JF_JPOS_ZERO) ? ac_pos : link_origin(c, lt);
+  V3 lp = anchor_pc, wp = v3(0, 0, 0), vp = v3(0, 0, 0), ap_pos = anchor_pc;
+  Q4 tj = j_rot;
+  if (!(flags & JF_TROT_IDENTITY)) tj = qmul(ld4(lt + L_TROT), j_rot);
+  Q4 ap_rot = tj;
+  if (!world_parent) {
+    lp = rotate(anchor_pc, p.rot);
+    ap_pos = p.pos + lp;
+    wp = p.ang;
+    vp = p.vel + cross(p.ang, lp);
+    ap_rot = qmul(p.rot, tj);
+  }
+  const V3 vc = c.vel + cross(c.ang, lc);
+  const Q4 ac_rot = qmul(c.rot, j_rot);
+  const Q4 jrot = qmul(qconj(ap_rot), ac_rot);
+  const V3 yc = rotate_ey(jrot);
+  const float psi = atan2f(yc.z, yc.y);
+  const V3 xp_w = rotate_ex(ap_rot), xc_w = rotate_ex(ac_rot);
+  const float k = sys[H_STIFFNESS] * stiffness_scale, cv = sys[H_VEL_DAMPING_C], kl = sys[H_LIMIT_STIFFNESS],
+              ca = sys[H_ANG_DAMPING_C];
+  const V3 F = (-k) * (ac_pos - ap_pos) - cv * (vc - vp);
+  const float lo = lt[L_LIM_LO], hi = lt[L_LIM_HI];
+  float dang = 0.0f;
+  if (psi < lo) dang = lo - psi;
+  if (psi > hi) dang = hi - psi;
+  const V3 wrel = c.ang - wp;
+  const V3 T = k * cross(xc_w, xp_w) + (kl * dang + tau) * xp_w - ca * wrel;
+  o.child.f = F;
+  o.child.t = T + cross(lc, F);
+  o.parent.f = v3(0, 0, 0) - F;
+  o.parent.t = (v3(0, 0, 0) - T) - cross(lp, F);
+  o.q[0] = psi; o.q[1] = 0; o.q[2] = 0;
+  o.qd[0] = dot(wrel, xp_w); o.qd[1] = 0; o.qd[2] = 0;
+  return o;
+}
+
 // ---- semi-implicit velocity update (brax.spring.integrator.integrate_xdd) ---------------------
+template <bool FAST = false>
 CARLB_HD void integrate_xdd(LinkState& s, const Wrench& w, const float* sys, const float* lt, const LinkConst& lc,
                             float gravity) {
   const float dt = sys[H_DT];
   const V3 acc = v3(0, 0, gravity) + w.f * lc.inv_mass;
-  const V3 alpha = apply_inv_inertia(w.t, s.rot, lt, lc.inv_idiag);
+  const V3 alpha = apply_inv_inertia_sel<FAST>(w.t, s.rot, lt, lc.inv_idiag);
   s.vel = s.vel + acc * dt;
   s.ang = s.ang + alpha * dt;
   s.vel = s.vel * lc.vel_decay;
@@ -391,12 +462,23 @@ struct ContactOut {
 
 // `origin` is link_origin(s, lt): pose integration is the last phase of a substep, so the value the joint phase
 // computed for the link is still exact here and is passed in instead of being recomputed per contact point.
+// Height of a link's centre of mass above which contact candidate `pt` cannot touch the ground whatever the link's
+// orientation: |candidate - COM| + radius, plus a margin far above float32 rounding. A pure early-out: a candidate
+// skipped by this bound would have failed the penetration test.
+CARLB_HD float contact_reach(const float* pt, const float* lt) {
+  return norm(v3(pt[1], pt[2], pt[3]) - ld3(lt + L_COM)) + pt[4] + 1e-3f;
+}
+
+// FAST: the sphere centre is taken from the centre of mass (pos + rotate(candidate - COM)) instead of the link
+// origin, which the FAST substeps never evaluate; `origin` is then unused.
+template <bool FAST = false>
 CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const float* lt, const LinkState& s,
                                     const LinkConst& lc, float friction, float elasticity, V3 origin) {
   ContactOut o;
   o.p = v3(0, 0, 0); o.t = v3(0, 0, 0); o.active = 0.0f;
   const float radius = pt[4];
-  const V3 c = origin + rotate(v3(pt[1], pt[2], pt[3]), s.rot);  // sphere centre in the world
+  const V3 c = FAST ? s.pos + rotate(v3(pt[1], pt[2], pt[3]) - ld3(lt + L_COM), s.rot)
+                    : origin + rotate(v3(pt[1], pt[2], pt[3]), s.rot);  // sphere centre in the world
   const float dist = c.z - radius;                               // signed distance to the plane
   const float penetration = -dist;
   if (!(penetration > 0.0f)) return o;
@@ -409,7 +491,7 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
   const V3 rel_vel = s.vel + cross(s.ang, rel_pos);
   const float normal_vel = rel_vel.z;                                       // dot(n, rel_vel)
   const float inv_m = lc.inv_mass;
-  const V3 temp1 = apply_inv_inertia(v3(rel_pos.y, 0.0f - rel_pos.x, 0.0f), s.rot, lt, lc.inv_idiag);  // cross(rel_pos, n)
+  const V3 temp1 = apply_inv_inertia_sel<FAST>(v3(rel_pos.y, 0.0f - rel_pos.x, 0.0f), s.rot, lt, lc.inv_idiag);  // cross(rel_pos, n)
   const float ang = temp1.x * rel_pos.y - temp1.y * rel_pos.x;              // dot(n, cross(temp1, rel_pos))
   const float dt = sys[H_DT];
   const float baumgarte_vel = sys[H_BAUMGARTE] * penetration / dt;
@@ -434,11 +516,12 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
 }
 
 // delta-velocity from the link's summed contact impulses, averaged over its active contacts
+template <bool FAST = false>
 CARLB_HD void integrate_xdv(LinkState& s, V3 p_sum, V3 t_sum, float n_active, const float* lt, const LinkConst& lc) {
   if (!(n_active > 0.0f)) return;
   const float inv_n = 1.0f / n_active;
   s.vel = s.vel + p_sum * (inv_n * lc.inv_mass);
-  s.ang = s.ang + apply_inv_inertia(t_sum * inv_n, s.rot, lt, lc.inv_idiag);
+  s.ang = s.ang + apply_inv_inertia_sel<FAST>(t_sum * inv_n, s.rot, lt, lc.inv_idiag);
 }
 
 // ---- pose integration (brax.spring.integrator.integrate) --------------------------------------

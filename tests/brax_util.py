@@ -60,8 +60,10 @@ class BraxHostCheck:
                               self._p(state), sysd["state_words"], self._p(obs), sysd["obs_dim"], self._p(ctx), ctx.shape[1])
         return state, obs
 
-    def step(self, sysd, state, ctx, actions, elapsed, max_steps, autoreset, first_state, first_obs, stock_contact=0):
+    def step(self, sysd, state, ctx, actions, elapsed, max_steps, autoreset, first_state, first_obs, stock_contact=0, fast=False):
+        """fast=True: the reformulated arithmetic of the FMA build (world-frame hinge, unit-inertia shortcut)."""
         n = state.shape[0]
+        self.lib.hc_brax_set_fast(1 if fast else 0)
         obs = np.zeros((n, sysd["obs_dim"]), dtype=np.float32)
         reward = np.zeros(n, dtype=np.float32)
         done = np.zeros(n, dtype=np.uint8)

@@ -92,7 +92,25 @@ static void obs_of(const float* sys, const LinkState* st, float* obs, float* roo
   root[0] = kind == ENV_HUMANOID ? comx : o0.x; root[1] = o0.z; root[2] = ((int)link_tab(sys, 0)[L_TYPE] == TYPE_PLANAR) ? q[2] : 0.0f; root[3] = ok ? 1.0f : 0.0f;
 }
 
+static JointOut joint_resolve_shared_origins(const float* sys, const float* lt, const LinkState& c, bool world_parent,
+                                             const float* plt, const LinkState& p, const float* tau, float stiffness_scale,
+                                             const float* dt, V3 org_c, V3 org_p) {
+  const V3 origins[2] = {org_c, org_p};
+  return joint_resolve<true, true>(sys, lt, c, world_parent, plt, p, tau[0], stiffness_scale, parent_anchor(lt), joint_flags(lt),
+                                   dt, tau[1], tau[2], origins);
+}
+
+// one env-step of all envs; FAST selects the reformulations of the FMA build (world-frame hinge, unit-inertia shortcut)
+template <bool FAST>
+static void step_all(const float* sys, int n, float* state, int words, const float* ctx, int n_ctx, const float* actions,
+                     int* elapsed, int max_steps, int autoreset, const float* first_state, const float* first_obs, float* obs,
+                     int D, float* reward, uint8_t* done_out, int stock_contact);
+
+static int g_fast = 0;
+
 extern "C" {
+
+void hc_brax_set_fast(int fast) { g_fast = fast; }
 
 void hc_brax_init(const float* sys, int n, const float* q_all, const float* qd_all, float* state, int words, float* obs, int D,
                   const float* ctx, int n_ctx) {
@@ -116,6 +134,20 @@ void hc_brax_init(const float* sys, int n, const float* q_all, const float* qd_a
 void hc_brax_step(const float* sys, int n, float* state, int words, const float* ctx, int n_ctx, const float* actions,
                   int* elapsed, int max_steps, int autoreset, const float* first_state, const float* first_obs, float* obs,
                   int D, float* reward, uint8_t* done_out, int stock_contact) {
+  if (g_fast)
+    step_all<true>(sys, n, state, words, ctx, n_ctx, actions, elapsed, max_steps, autoreset, first_state, first_obs, obs, D, reward,
+                   done_out, stock_contact);
+  else
+    step_all<false>(sys, n, state, words, ctx, n_ctx, actions, elapsed, max_steps, autoreset, first_state, first_obs, obs, D, reward,
+                    done_out, stock_contact);
+}
+
+}  // extern "C"
+
+template <bool FAST>
+static void step_all(const float* sys, int n, float* state, int words, const float* ctx, int n_ctx, const float* actions,
+                     int* elapsed, int max_steps, int autoreset, const float* first_state, const float* first_obs, float* obs,
+                     int D, float* reward, uint8_t* done_out, int stock_contact) {
   const int L = (int)sys[H_N_LINKS], P = (int)sys[H_N_POINTS], A = (int)sys[H_N_ACT], NF = (int)sys[H_N_FRAMES];
   for (int e = 0; e < n; ++e) {
     float* rows = state + (size_t)e * words;
@@ -129,8 +161,12 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     for (int a = 0; a < A; ++a) act_sq += act[a] * act[a];
     LinkConst lcs[MAX_LINKS];
     for (int l = 0; l < L; ++l) lcs[l] = make_link_const(sys, link_tab(sys, l), c[C_MASS0 + l], c[C_ANG_DAMPING]);
+    float reach[MAX_POINTS];
+    for (int p = 0; p < P; ++p) reach[p] = contact_reach(point_tab(sys, p), link_tab(sys, (int)point_tab(sys, p)[0]));
     for (int f = 0; f < NF; ++f) {
       Wrench w[MAX_LINKS], pw[MAX_LINKS];
+      V3 org[MAX_LINKS];  // link-frame origins, evaluated once per link by its owner (as the kernel shares them)
+      for (int l = 0; l < L; ++l) org[l] = link_origin(st[l], link_tab(sys, l));
       for (int l = 0; l < L; ++l) {
         w[l].f = v3(0, 0, 0); w[l].t = v3(0, 0, 0); pw[l] = w[l];
         const float* lt = link_tab(sys, l);
@@ -138,9 +174,15 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         const int parent = (int)lt[L_PARENT];
         float tau[3];
         taus_of(sys, l, act, tau);
-        const JointOut jo = joint_resolve<true, true>(sys, lt, st[l], parent < 0, link_tab(sys, parent < 0 ? 0 : parent),
-                                                      st[parent < 0 ? 0 : parent], tau[0], c[C_STIFFNESS_SCALE], dof_tab(sys, l),
-                                                      tau[1], tau[2]);
+        const float* plt = link_tab(sys, parent < 0 ? 0 : parent);
+        const LinkState& pst = st[parent < 0 ? 0 : parent];
+        const JointOut jo = (FAST && (int)lt[L_TYPE] == TYPE_HINGE)
+                                ? joint_resolve_world(sys, lt, st[l], parent < 0, pst, tau[0], c[C_STIFFNESS_SCALE],
+                                                      parent_anchor_from_com(lt, plt, parent < 0), joint_flags(lt))
+                                : (FAST ? joint_resolve<true, true>(sys, lt, st[l], parent < 0, plt, pst, tau[0], c[C_STIFFNESS_SCALE],
+                                                                    dof_tab(sys, l), tau[1], tau[2])
+                                        : joint_resolve_shared_origins(sys, lt, st[l], parent < 0, plt, pst, tau, c[C_STIFFNESS_SCALE],
+                                                                       dof_tab(sys, l), org[l], org[parent < 0 ? 0 : parent]));
         w[l] = jo.child; pw[l] = jo.parent;
       }
       LinkState nx[MAX_LINKS];
@@ -149,7 +191,7 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         for (int k = l + 1; k < L; ++k)
           if ((int)link_tab(sys, k)[L_PARENT] == l) { tot.f = tot.f + pw[k].f; tot.t = tot.t + pw[k].t; }
         nx[l] = st[l];
-        integrate_xdd(nx[l], tot, sys, link_tab(sys, l), lcs[l], c[C_GRAVITY]);
+        integrate_xdd<FAST>(nx[l], tot, sys, link_tab(sys, l), lcs[l], c[C_GRAVITY]);
       }
       ContactOut co[MAX_POINTS];
       for (int p = 0; p < P; ++p) {
@@ -157,14 +199,18 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
         const int l = (int)pt[0];
         const float fr = (c[C_FRICTION] < 0.0f || stock_contact) ? pt[5] : c[C_FRICTION];
         const float el = (c[C_ELASTICITY] < 0.0f || stock_contact) ? pt[6] : c[C_ELASTICITY];
-        co[p] = contact_resolve(sys, pt, link_tab(sys, l), nx[l], lcs[l], fr, el, link_origin(nx[l], link_tab(sys, l)));
+        if (nx[l].pos.z > reach[p]) {  // the kernel's early-out: out of reach of the ground
+          co[p].p = v3(0, 0, 0); co[p].t = v3(0, 0, 0); co[p].active = 0.0f;
+          continue;
+        }
+        co[p] = contact_resolve<FAST>(sys, pt, link_tab(sys, l), nx[l], lcs[l], fr, el, org[l]);
       }
       for (int l = 0; l < L; ++l) {
         const float* lt = link_tab(sys, l);
         V3 ps = v3(0, 0, 0), ts = v3(0, 0, 0);
         float na = 0.0f;
         for (int k = (int)lt[L_FIRST_PT]; k < (int)lt[L_FIRST_PT] + (int)lt[L_N_PT]; ++k) { ps = ps + co[k].p; ts = ts + co[k].t; na += co[k].active; }
-        integrate_xdv(nx[l], ps, ts, na, lt, lcs[l]);
+        integrate_xdv<FAST>(nx[l], ps, ts, na, lt, lcs[l]);
         integrate_pose(nx[l], sys[H_DT]);
         st[l] = nx[l];
       }
@@ -200,5 +246,3 @@ void hc_brax_step(const float* sys, int n, float* state, int words, const float*
     done_out[e] = done ? 1 : 0;
   }
 }
-
-}  // extern "C"
