@@ -240,11 +240,12 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
       const int pi = world_parent ? 0 : c.parent;
       const LinkState ps = read_link(w.ls, pi);
       JointOut jo;
-      if (FAST) {
-        jo = (c.type == TYPE_HINGE)
-                 ? joint_resolve_world(sys, c.lt, s, world_parent, ps, tau, c.stiffness_scale, c.anchor_pc, c.jflags)
-                 : joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags,
-                                         c.dt, tau1, tau2);
+      if (FAST && !SP) {
+        // every joint of the locomotion bodies and the humanoids is revolute: one world-frame path for all lanes
+        jo = joint_resolve_world<HU>(sys, c.lt, s, world_parent, ps, tau, c.stiffness_scale, c.anchor_pc, c.jflags, c.dt, tau1, tau2);
+      } else if (FAST) {
+        jo = joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags, c.dt,
+                                   tau1, tau2);
       } else {
         const V3 origins[2] = {ld3(w.org + c.sl * 3), ld3(w.org + pi * 3)};
         jo = joint_resolve<SP, HU>(sys, c.lt, s, world_parent, c.plt, ps, tau, c.stiffness_scale, c.anchor_p, c.jflags, c.dt,

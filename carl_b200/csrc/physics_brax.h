@@ -390,21 +390,25 @@ CARLB_HD V3 parent_anchor_from_com(const float* lt, const float* plt, bool world
   return world_parent ? a : a - ld3(plt + L_COM);
 }
 
-// FAST arithmetic, revolute joints (TYPE_HINGE) only: the same spring / damper / limit / actuator wrench as
-// joint_resolve, evaluated in the WORLD frame. The positional spring and damper of a hinge are isotropic, so
-// rotating the anchor offset and rate into the joint frame and the force back out is the identity; the axis torques
-// use the world images of the two joint x axes. 2 rotations + 3 quaternion products instead of 8 + 3. Mathematically
-// identical, rounded differently: not comparable bit for bit with the float32 oracle, held to the float64 yardstick
-// like every result of the FMA build (tests/test_brax_parity_gpu.py).
+// FAST arithmetic, revolute joints (hinge, planar root, and -- STACKED -- the 2- / 3-dof hinges): the same spring /
+// damper / limit / actuator wrench as joint_resolve, evaluated in the WORLD frame. The positional spring and damper of
+// a revolute joint are isotropic, so rotating the anchor offset and rate into the joint frame and the force back out is
+// the identity (the planar root keeps only the component along its joint x axis); the axis torques use the world
+// images of the two joint x axes. 2 rotations + 3 quaternion products instead of 8 + 3. Mathematically identical,
+// rounded differently: not comparable bit for bit with the float32 oracle, held to the float64 yardstick like every
+// result of the FMA build (tests/test_brax_parity_gpu.py). Every joint lane of a warp takes this one path.
+template <bool STACKED = false>
 CARLB_HD JointOut joint_resolve_world(const float* sys, const float* lt, const LinkState& c, bool world_parent,
-                                      const LinkState& p, float tau, float stiffness_scale, V3 anchor_pc, int flags) {
+                                      const LinkState& p, float tau, float stiffness_scale, V3 anchor_pc, int flags,
+                                      const float* dt = nullptr, float tau1 = 0.0f, float tau2 = 0.0f) {
   JointOut o;
+  const int type = (int)lt[L_TYPE];
   const Q4 j_rot = ld4(lt + L_JROT);
   V3 rc = v3(0, 0, 0) - ld3(lt + L_COM);
   if (!(flags & JF_JPOS_ZERO)) rc = ld3(lt + L_JPOS) + rc;
   const V3 lc = rotate(rc, c.rot);  // child anchor relative to the child's COM, world axes
   const V3 ac_pos = c.pos + lc;
-  o.origin = (flags & JF_JPOS_ZERO) ? ac_pos : link_origin(c, lt);
+  o.origin = ac_pos;  // (the FAST substeps do not use link origins)
   V3 lp = anchor_pc, wp = v3(0, 0, 0), vp = v3(0, 0, 0), ap_pos = anchor_pc;
   Q4 tj = j_rot;
   if (!(flags & JF_TROT_IDENTITY)) tj = qmul(ld4(lt + L_TROT), j_rot);
@@ -424,17 +428,47 @@ CARLB_HD JointOut joint_resolve_world(const float* sys, const float* lt, const L
   const V3 xp_w = rotate_ex(ap_rot), xc_w = rotate_ex(ac_rot);
   const float k = sys[H_STIFFNESS] * stiffness_scale, cv = sys[H_VEL_DAMPING_C], kl = sys[H_LIMIT_STIFFNESS],
               ca = sys[H_ANG_DAMPING_C];
-  const V3 F = (-k) * (ac_pos - ap_pos) - cv * (vc - vp);
-  const float lo = lt[L_LIM_LO], hi = lt[L_LIM_HI];
-  float dang = 0.0f;
-  if (psi < lo) dang = lo - psi;
-  if (psi > hi) dang = hi - psi;
-  const V3 wrel = c.ang - wp;
-  const V3 T = k * cross(xc_w, xp_w) + (kl * dang + tau) * xp_w - ca * wrel;
+  const V3 d = ac_pos - ap_pos, vrel = vc - vp, wrel = c.ang - wp;
+  V3 F = (-k) * d - cv * vrel;
+  V3 T;
+  if (STACKED && (type == TYPE_HINGE2 || type == TYPE_HINGE3)) {
+    // limit / actuator torques about the Euler axes and the universal joint's constraint torque are assembled in the
+    // joint frame (as joint_resolve does) and carried out with ONE rotation
+    const EulerAxes ea = euler_axes(jrot);
+    V3 fa = v3(0, 0, 0);
+    if (type == TYPE_HINGE2) {
+      const float inv = 1.0f / (1e-10f + sqrtf(yc.y * yc.y + yc.z * yc.z));
+      fa = k * cross(yc, v3(0.0f, yc.y * inv, yc.z * inv));
+    }
+    const int nd = type == TYPE_HINGE3 ? 3 : 2;
+    for (int a = 0; a < nd; ++a) {
+      const float lo = a == 0 ? lt[L_LIM_LO] : (a == 1 ? dt[D_LO1] : dt[D_LO2]);
+      const float hi = a == 0 ? lt[L_LIM_HI] : (a == 1 ? dt[D_HI1] : dt[D_HI2]);
+      const float sg = dt[D_SIGN0 + a];
+      const float coord = sg * ea.ang[a];
+      float dang = 0.0f;
+      if (coord < lo) dang = lo - coord;
+      if (coord > hi) dang = hi - coord;
+      const float tq = sg * (kl * dang + (a == 0 ? tau : (a == 1 ? tau1 : tau2)));
+      fa = fa + tq * (a == 0 ? v3(1, 0, 0) : (a == 1 ? ea.a1 : ea.a2));
+    }
+    T = rotate(fa, ap_rot) - ca * wrel;
+  } else if (type == TYPE_PLANAR) {
+    // slide-x / slide-z / hinge-y root: only the off-plane offset and the off-axis rotation are constrained
+    F = ((-k) * dot(d, xp_w) - cv * dot(vrel, xp_w)) * xp_w;
+    T = k * cross(xc_w, xp_w) - ca * (wrel - dot(wrel, xp_w) * xp_w);
+  } else {
+    const float lo = lt[L_LIM_LO], hi = lt[L_LIM_HI];
+    float dang = 0.0f;
+    if (psi < lo) dang = lo - psi;
+    if (psi > hi) dang = hi - psi;
+    T = k * cross(xc_w, xp_w) + (kl * dang + tau) * xp_w - ca * wrel;
+  }
   o.child.f = F;
   o.child.t = T + cross(lc, F);
   o.parent.f = v3(0, 0, 0) - F;
   o.parent.t = (v3(0, 0, 0) - T) - cross(lp, F);
+  // (the generalized coordinates of the observation always come from joint_resolve)
   o.q[0] = psi; o.q[1] = 0; o.q[2] = 0;
   o.qd[0] = dot(wrel, xp_w); o.qd[1] = 0; o.qd[2] = 0;
   return o;

@@ -176,9 +176,13 @@ static void step_all(const float* sys, int n, float* state, int words, const flo
         taus_of(sys, l, act, tau);
         const float* plt = link_tab(sys, parent < 0 ? 0 : parent);
         const LinkState& pst = st[parent < 0 ? 0 : parent];
-        const JointOut jo = (FAST && (int)lt[L_TYPE] == TYPE_HINGE)
-                                ? joint_resolve_world(sys, lt, st[l], parent < 0, pst, tau[0], c[C_STIFFNESS_SCALE],
-                                                      parent_anchor_from_com(lt, plt, parent < 0), joint_flags(lt))
+        const int jt = (int)lt[L_TYPE];
+        const bool revolute = jt == TYPE_HINGE || jt == TYPE_PLANAR || jt == TYPE_HINGE2 || jt == TYPE_HINGE3;
+        const bool special = (int)sys[H_ENV] >= ENV_INVERTED_PENDULUM && (int)sys[H_ENV] <= ENV_REACHER;  // kernels: MODE_SPECIAL
+        const JointOut jo = (FAST && revolute && !special)
+                                ? joint_resolve_world<true>(sys, lt, st[l], parent < 0, pst, tau[0], c[C_STIFFNESS_SCALE],
+                                                            parent_anchor_from_com(lt, plt, parent < 0), joint_flags(lt),
+                                                            dof_tab(sys, l), tau[1], tau[2])
                                 : (FAST ? joint_resolve<true, true>(sys, lt, st[l], parent < 0, plt, pst, tau[0], c[C_STIFFNESS_SCALE],
                                                                     dof_tab(sys, l), tau[1], tau[2])
                                         : joint_resolve_shared_origins(sys, lt, st[l], parent < 0, plt, pst, tau, c[C_STIFFNESS_SCALE],
