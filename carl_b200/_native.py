@@ -21,7 +21,7 @@ MAX_PEERS, MAX_MIXED = 8, 8
 KIND = {
     "cartpole": 0, "pendulum": 1, "acrobot": 2, "mountaincar": 3, "mountaincar_cont": 4,
     "brax_ant": 16, "brax_halfcheetah": 17, "brax_hopper": 18, "brax_walker2d": 19,
-    "brax_inverted_pendulum": 20, "brax_inverted_double_pendulum": 21, "brax_reacher": 22, "brax_humanoid": 23, "brax_humanoidstandup": 24,
+    "brax_inverted_pendulum": 20, "brax_inverted_double_pendulum": 21, "brax_reacher": 22, "brax_humanoid": 23, "brax_humanoidstandup": 24, "brax_pusher": 25,
 }
 
 EXPORTS = [

@@ -75,7 +75,7 @@ template <int KIND> static void fill_info(carlb_env_info_t* o) {
 }
 
 static bool is_classic(int kind) { return kind >= 0 && kind < KIND_CLASSIC_COUNT; }
-static bool is_brax(int kind) { return kind >= KIND_BRAX_ANT && kind <= KIND_BRAX_HUMANOIDSTANDUP; }
+static bool is_brax(int kind) { return kind >= KIND_BRAX_ANT && kind <= KIND_BRAX_PUSHER; }
 
 static bool valid_act_dtype(const carlb_env* env, int act_dtype) {
   carlb_env_info_t info;

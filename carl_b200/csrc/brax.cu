@@ -290,6 +290,27 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
         }
       }
     }
+    if constexpr (SP) {
+      // body-vs-body pairs (pusher): sub-lane k resolves pair k and writes the two candidate rows reserved for it
+      const int n_pairs = (int)sys[OFF_PAIR + X_N_PAIRS];
+      if (n_pairs > 0) {  // block-uniform
+        __syncwarp();  // the ground passes initialised those rows
+        if (c.active && c.sl < n_pairs) {
+          const float* pr = pair_tab(sys, c.sl);
+          const int la = (int)pr[R_LINK_A], lb = (int)pr[R_LINK_B], row_a = (int)pr[R_ROW_A], row_b = (int)pr[R_ROW_B];
+          const float* pta = point_tab(sys, row_a);
+          const float fr = (c.stock_contact || w.ctx[C_FRICTION] < 0.0f) ? pta[5] : w.ctx[C_FRICTION];
+          const float el = (c.stock_contact || w.ctx[C_ELASTICITY] < 0.0f) ? pta[6] : w.ctx[C_ELASTICITY];
+          const PairOut po = pair_resolve(sys, pr, link_tab(sys, la), link_tab(sys, lb), read_link(w.ls, la), read_link(w.ls, lb),
+                                          read_lc(w.lc, la), read_lc(w.lc, lb), fr, el);
+          float* oa = w.co + row_a * 7;
+          float* ob = w.co + row_b * 7;
+          oa[0] = po.p.x; oa[1] = po.p.y; oa[2] = po.p.z; oa[3] = po.ta.x; oa[4] = po.ta.y; oa[5] = po.ta.z; oa[6] = po.active;
+          ob[0] = 0.0f - po.p.x; ob[1] = 0.0f - po.p.y; ob[2] = 0.0f - po.p.z; ob[3] = po.tb.x; ob[4] = po.tb.y; ob[5] = po.tb.z;
+          ob[6] = po.active;
+        }
+      }
+    }
     __syncwarp();
     if (c.is_link) {
       V3 ps = v3(0, 0, 0), ts = v3(0, 0, 0);
@@ -361,7 +382,9 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   const int kind = (int)sys[H_ENV];
   RootFacts r;
   r.site = v3(0, 0, 0);
-  if (SP && kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
+  if (SP && kind == ENV_PUSHER) {
+    r.site = pusher_distances(sys, w.ls);
+  } else if (SP && kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
     r.site = site_position(sys, read_link(w.ls, (int)sys[H_SITE_LINK]), read_link(w.ls, kind == ENV_REACHER ? 2 : 0));
   }
   float com_x = 0.0f;
@@ -389,6 +412,9 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
         if (c.type == TYPE_HINGE3) qf[qdi + 2] = a2 >= 0 ? c.dt[D_GEAR2] * fminf(fmaxf(w.act[a2], lo), hi) : 0.0f;
       }
     }
+  } else if (SP && kind == ENV_PUSHER) {
+    if (c.sl < LPE)
+      for (int i = c.sl; i < 23; i += LPE) w.obs[i] = pusher_obs_entry(sys, i, w.q, w.qd, w.ls);
   } else if (SP && (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER)) {
     const int D = kind == ENV_REACHER ? 11 : 8;
     if (c.sl < LPE)
@@ -450,7 +476,8 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   const float ctrl_cost = sys[H_CTRL_COST] * act_sq_sum;
   reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
   done = (sys[H_TERMINATE] > 0.0f) && !healthy;
-  if (SP && kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
+  if (SP && kind == ENV_PUSHER) pusher_outcome(sys, before.site, act_sq_sum, reward, done);
+  else if (SP && kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
   if (HU && kind == ENV_HUMANOIDSTANDUP) {  // brax.envs.humanoidstandup.step: uph_cost + 1 - quad_ctrl_cost, never done
     reward = (after.z - 0.0f) / dt_env + sys[H_HEALTHY_REWARD] - ctrl_cost;
     done = false;
@@ -713,6 +740,7 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
       const float noise = sys[H_RESET_NOISE], qd_noise = sys[H_QD_NOISE];
       const bool hopper = sys[H_QD_UNIFORM] > 0.0f;  // Hopper / Walker2d / pendulum / reacher: qd ~ U(+-noise), else noise * N(0,1)
       const bool reacher = (int)sys[H_ENV] == ENV_REACHER;
+      const bool pusher = (int)sys[H_ENV] == ENV_PUSHER;
       if (seg.reset_rng == CARLB_RESET_JAX && (q_in == nullptr || qd_in == nullptr)) {
         // the reference's own stream: `rng, rng1, rng2 = jax.random.split(rng, 3)` on the key this env receives at
         // its `episode`-th reset, q = init_q + uniform(rng1, (nq,), -noise, noise), qd = noise * normal(rng2, (nqd,))
@@ -733,6 +761,15 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
           w.q[lane] = lane == 2 ? dist * cosf(ang) : dist * sinf(ang);
           w.qd[lane] = 0.0f;
         }
+        if (pusher && q_in == nullptr && lane >= 7 && lane < 11) {
+          // brax.envs.pusher.reset: the object starts at (U(rng, -0.3, -1e-6), U(rng1, -0.2, 0.2)) on its two slides, pushed
+          // out to 0.17 from the goal if closer; the goal offsets and the last four rates are zero
+          const float c0 = jax_uniform(rng0, 1u, 0u, -0.3f, -1e-6f), c1 = jax_uniform(rng1, 1u, 0u, -0.2f, 0.2f);
+          const float nrm = sqrtf(c0 * c0 + c1 * c1);
+          const float scale = nrm < 0.17f ? 0.17f / nrm : 1.0f;
+          w.q[lane] = lane == 7 ? c0 * scale : (lane == 8 ? c1 * scale : 0.0f);
+          w.qd[lane] = 0.0f;
+        }
         if (lane < nq && q_in != nullptr) w.q[lane] = q_in[(size_t)env * nq + lane];
         if (lane < nqd && qd_in != nullptr) w.qd[lane] = qd_in[(size_t)env * nqd + lane];
       } else {
@@ -750,6 +787,14 @@ __global__ void __launch_bounds__(128) brax_reset_kernel(const __grid_constant__
           const float dist = 0.2f * reset_uniform(seg.seed, gid, episode, 128u, 0.0f, 1.0f);
           const float ang = 6.283185307179586f * reset_uniform(seg.seed, gid, episode, 129u, 0.0f, 1.0f);
           w.q[lane] = lane == 2 ? dist * cosf(ang) : dist * sinf(ang);
+          w.qd[lane] = 0.0f;
+        }
+        if (pusher && q_in == nullptr && lane >= 7 && lane < 11) {
+          const float c0 = reset_uniform(seg.seed, gid, episode, 128u, -0.3f, -1e-6f);
+          const float c1 = reset_uniform(seg.seed, gid, episode, 129u, -0.2f, 0.2f);
+          const float nrm = sqrtf(c0 * c0 + c1 * c1);
+          const float scale = nrm < 0.17f ? 0.17f / nrm : 1.0f;
+          w.q[lane] = lane == 7 ? c0 * scale : (lane == 8 ? c1 * scale : 0.0f);
           w.qd[lane] = 0.0f;
         }
       }
@@ -813,6 +858,7 @@ static void static_facts(int kind, int& L, int& nq, int& nqd, int& A) {
     case KIND_BRAX_REACHER: L = 3; nq = 4; nqd = 4; A = 2; break;
     case KIND_BRAX_HUMANOID:
     case KIND_BRAX_HUMANOIDSTANDUP: L = 11; nq = 24; nqd = 23; A = 17; break;
+    case KIND_BRAX_PUSHER: L = 9; nq = 11; nqd = 11; A = 7; break;
     default: L = 4; nq = 6; nqd = 6; A = 3; break;
   }
 }
@@ -821,13 +867,14 @@ int brax_query(int kind, carlb_env_info_t* o) {
   int L, nq, nqd, A;
   static_facts(kind, L, nq, nqd, A);
   const bool humanoid = kind == KIND_BRAX_HUMANOID || kind == KIND_BRAX_HUMANOIDSTANDUP;
-  const int ex = (kind == KIND_BRAX_ANT || humanoid) ? 2 : (kind == KIND_BRAX_INVERTED_PENDULUM ? 0 : 1);
+  const int ex = (kind == KIND_BRAX_ANT || humanoid) ? 2 : ((kind == KIND_BRAX_INVERTED_PENDULUM || kind == KIND_BRAX_PUSHER) ? 0 : 1);
   o->kind = kind;
   o->state_words = ((LINK_WORDS * L + 3) / 4) * 4;
   o->obs_dim = (nq - ex) + nqd;
   if (kind == KIND_BRAX_INVERTED_DOUBLE_PENDULUM) o->obs_dim = 8;  // q0, sin, cos, clipped qd
   if (kind == KIND_BRAX_REACHER) o->obs_dim = 11;                  // cos, sin, target, qd[:2], tip - target
   if (humanoid) o->obs_dim = humanoid_obs_dim(nq, nqd, L);         // 244: q[2:], qd, cinert, cvel, actuator torques
+  if (kind == KIND_BRAX_PUSHER) o->obs_dim = 23;                   // q[:7], qd[:7], three centres of mass
   o->act_dim = A;
   o->act_discrete = 0;
   o->n_actions = 0;
@@ -835,7 +882,7 @@ int brax_query(int kind, carlb_env_info_t* o) {
   o->n_step_rows = 5 + L;
   o->default_max_steps = 1000;  // brax.envs.create(episode_length=1000)
   o->gym_reset_draws = 0;
-  o->act_low = kind == KIND_BRAX_INVERTED_PENDULUM ? -3.0f : (humanoid ? -0.4f : -1.0f);  // BraxGymWrapper: Box(ctrl_range) (wrappers.py:48-50)
+  o->act_low = kind == KIND_BRAX_INVERTED_PENDULUM ? -3.0f : (humanoid ? -0.4f : (kind == KIND_BRAX_PUSHER ? -2.0f : -1.0f));  // BraxGymWrapper: Box(ctrl_range) (wrappers.py:48-50)
   o->act_high = -o->act_low;
   return CARLB_OK;
 }
@@ -975,6 +1022,10 @@ static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, co
     // 11 links: two envs per warp (16 lanes each; the 17 actions and 29 contact candidates go in two passes)
     if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, MODE_HUMANOID>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
     return launch_brax_step_we<4, 2, MODE_HUMANOID>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+  }
+  if (env_kind == ENV_PUSHER) {  // 9 links, slide joints, body-vs-body pairs: three envs per warp
+    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, MODE_SPECIAL>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    return launch_brax_step_we<4, 3, MODE_SPECIAL>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
   }
   if (env_kind >= ENV_INVERTED_PENDULUM) {
     // inverted pendulums / reacher (2-3 links): the instantiation with slide joints and their env layers

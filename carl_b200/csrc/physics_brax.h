@@ -37,7 +37,12 @@ constexpr int OFF_POINTS = OFF_LINKS + LINK_STRIDE * MAX_LINKS;
 constexpr int OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS;
 constexpr int DOF_STRIDE = 16;  // per-link rows of the stacked (2- / 3-dof) revolute joints: what dofs 1 and 2 need
 constexpr int OFF_DOF = OFF_INIT_Q + MAX_Q;
-constexpr int TABLE_FLOATS = OFF_DOF + DOF_STRIDE * MAX_LINKS;
+// body-vs-body contact pairs (pusher) + what the pusher's env layer reads: header, then MAX_PAIRS rows
+constexpr int MAX_PAIRS = 4;
+constexpr int PAIR_STRIDE = 16;
+constexpr int PAIR_HEADER = 8;
+constexpr int OFF_PAIR = OFF_DOF + DOF_STRIDE * MAX_LINKS;
+constexpr int TABLE_FLOATS = OFF_PAIR + PAIR_HEADER + PAIR_STRIDE * MAX_PAIRS;
 constexpr int MAX_OBS_SMALL = 64;   // observation capacity of the per-env scratch: every body but the humanoids
 constexpr int MAX_OBS_LARGE = 244;  // humanoid / humanoidstandup (brax.envs.humanoid._get_obs)
 constexpr int MAX_ACT = 20;
@@ -68,8 +73,15 @@ enum LinkType {
 };
 enum EnvId {
   ENV_ANT = 0, ENV_HALFCHEETAH = 1, ENV_HOPPER = 2, ENV_WALKER2D = 3, ENV_INVERTED_PENDULUM = 4,
-  ENV_INVERTED_DOUBLE_PENDULUM = 5, ENV_REACHER = 6, ENV_HUMANOID = 7, ENV_HUMANOIDSTANDUP = 8
+  ENV_INVERTED_DOUBLE_PENDULUM = 5, ENV_REACHER = 6, ENV_HUMANOID = 7, ENV_HUMANOIDSTANDUP = 8, ENV_PUSHER = 9
 };
+// pair-region header: pair count, height of the contact plane in the MJCF's world (the engine's plane is z = 0), the
+// three links whose centres of mass the pusher observes (wrist-flex link, object, goal)
+enum PairHdr { X_N_PAIRS = 0, X_PLANE_Z, X_OBS_LINK0, X_OBS_LINK1, X_OBS_LINK2 };
+// pair row: capsule side A (link, candidate row that receives its impulse, segment end points, radius), sphere side B
+enum PairSlot { R_LINK_A = 0, R_ROW_A = 1, R_A0 = 2, R_A1 = 5, R_RADIUS_A = 8, R_LINK_B = 9, R_ROW_B = 10, R_B0 = 11, R_RADIUS_B = 14 };
+// the bodies of the MODE_SPECIAL kernels (slide joints, their own observation / outcome layers)
+CARLB_HD bool is_special_env(int kind) { return (kind >= ENV_INVERTED_PENDULUM && kind <= ENV_REACHER) || kind == ENV_PUSHER; }
 // dof rows (OFF_DOF + DOF_STRIDE * link): actuator index / gear / range of dofs 1 and 2 (dof 0 lives in the link row),
 // then the sign of each dof's coordinate against the right-handed joint frame (-1 where the MJCF axis is -z)
 enum DofSlot { D_ACT1 = 0, D_ACT2, D_GEAR1, D_GEAR2, D_LO1, D_HI1, D_LO2, D_HI2, D_SIGN0, D_SIGN1, D_SIGN2 };
@@ -154,6 +166,7 @@ struct Wrench {
 CARLB_HD const float* link_tab(const float* sys, int l) { return sys + OFF_LINKS + LINK_STRIDE * l; }
 CARLB_HD const float* point_tab(const float* sys, int p) { return sys + OFF_POINTS + POINT_STRIDE * p; }
 CARLB_HD const float* dof_tab(const float* sys, int l) { return sys + OFF_DOF + DOF_STRIDE * l; }
+CARLB_HD const float* pair_tab(const float* sys, int k) { return sys + OFF_PAIR + PAIR_HEADER + PAIR_STRIDE * k; }
 
 // link-frame origin in the world (Brax `x.pos`) from the COM state
 CARLB_HD V3 link_origin(const LinkState& s, const float* lt) { return s.pos - rotate(ld3(lt + L_COM), s.rot); }
@@ -511,6 +524,7 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
   ContactOut o;
   o.p = v3(0, 0, 0); o.t = v3(0, 0, 0); o.active = 0.0f;
   const float radius = pt[4];
+  if (radius < 0.0f) return o;  // a row that only receives the impulse of a body-vs-body pair
   const V3 c = FAST ? s.pos + rotate(v3(pt[1], pt[2], pt[3]) - ld3(lt + L_COM), s.rot)
                     : origin + rotate(v3(pt[1], pt[2], pt[3]), s.rot);  // sphere centre in the world
   const float dist = c.z - radius;                               // signed distance to the plane
@@ -545,6 +559,59 @@ CARLB_HD ContactOut contact_resolve(const float* sys, const float* pt, const flo
   if (apply_d) total = total + impulse_d_vec;
   o.p = total;
   o.t = cross(rel_pos, total);
+  o.active = 1.0f;
+  return o;
+}
+
+// ---- body-vs-body contact of one pair (spring/collisions.py with two dynamic bodies): capsule A vs sphere B --------
+// The normal points from B's centre to the closest point of A's segment (it pushes A away from B), the contact point
+// lies midway between the two surfaces; the impulse divides by both inverse masses and both angular terms and acts
+// with opposite signs on the two links.
+struct PairOut {
+  V3 p;       // linear impulse on A (B receives -p)
+  V3 ta, tb;  // angular impulses about the two centres of mass (tb already carries its sign)
+  float active;
+};
+CARLB_HD PairOut pair_resolve(const float* sys, const float* pr, const float* lta, const float* ltb, const LinkState& sa,
+                              const LinkState& sb, const LinkConst& lca, const LinkConst& lcb, float friction, float elasticity) {
+  PairOut o;
+  o.p = v3(0, 0, 0); o.ta = v3(0, 0, 0); o.tb = v3(0, 0, 0); o.active = 0.0f;
+  const V3 oa = link_origin(sa, lta), ob = link_origin(sb, ltb);
+  const V3 a0 = oa + rotate(ld3(pr + R_A0), sa.rot), a1 = oa + rotate(ld3(pr + R_A1), sa.rot);
+  const V3 cb = ob + rotate(ld3(pr + R_B0), sb.rot);
+  const V3 ab = a1 - a0, ac = cb - a0;
+  float tt = dot(ac, ab) / dot(ab, ab);
+  tt = fminf(fmaxf(tt, 0.0f), 1.0f);
+  const V3 cp = a0 + tt * ab;  // closest point of the segment to the sphere's centre
+  const V3 dvec = cp - cb;
+  const float dist = norm(dvec);
+  const float ra_ = pr[R_RADIUS_A], rb_ = pr[R_RADIUS_B];
+  const float penetration = ra_ + rb_ - dist;
+  if (!(penetration > 0.0f)) return o;
+  const V3 n = dvec * (1.0f / (1e-6f + dist));
+  const V3 cpos = 0.5f * ((cb + rb_ * n) + (cp - ra_ * n));
+  const V3 ra = cpos - sa.pos, rb = cpos - sb.pos;
+  const V3 contact_vel = (sa.vel + cross(sa.ang, ra)) - (sb.vel + cross(sb.ang, rb));
+  const float normal_vel = dot(n, contact_vel);
+  const V3 t1a = apply_inv_inertia(cross(ra, n), sa.rot, lta, lca.inv_idiag);
+  const V3 t1b = apply_inv_inertia(cross(rb, n), sb.rot, ltb, lcb.inv_idiag);
+  const float ang = dot(n, cross(t1a, ra)) + dot(n, cross(t1b, rb));
+  const float denom = lca.inv_mass + lcb.inv_mass + ang;
+  const float baumgarte_vel = sys[H_BAUMGARTE] * penetration / sys[H_DT];
+  const float impulse = (-1.0f * (1.0f + elasticity) * normal_vel + baumgarte_vel) / denom;
+  const V3 vel_d = contact_vel - normal_vel * n;
+  const float speed_d = norm(vel_d);
+  float impulse_d = speed_d / denom;
+  const V3 dir_d = vel_d * (1.0f / (1e-6f + speed_d));
+  impulse_d = fminf(impulse_d, friction * impulse);
+  const bool apply_n = (normal_vel < 0.0f) && (impulse > 0.0f);
+  const bool apply_d = apply_n && (speed_d > 0.01f);
+  if (!apply_n) return o;
+  V3 total = impulse * n;
+  if (apply_d) total = total + (-impulse_d) * dir_d;
+  o.p = total;
+  o.ta = cross(ra, total);
+  o.tb = v3(0, 0, 0) - cross(rb, total);
   o.active = 1.0f;
   return o;
 }
@@ -728,6 +795,27 @@ CARLB_HD void special_outcome(int kind, float q1, float qd1, float qd2, V3 site,
     reward = (0.0f - norm(site)) + (0.0f - act_sq_sum);
     done = false;
   }
+}
+
+// brax.envs.pusher: entry i of the observation (q[:7], qd[:7], centre of mass of the wrist-flex link, the object and
+// the goal, heights relative to the MJCF's world) from the env's link rows; and what its reward reads: the distances
+// object - fingertip link (x) and object - goal (y) of the state BEFORE the pipeline advances
+CARLB_HD float pusher_obs_entry(const float* sys, int i, const float* q, const float* qd, const float* rows) {
+  if (i < 7) return q[i];
+  if (i < 14) return qd[i - 7];
+  const int j = (i - 14) / 3, k = (i - 14) % 3;
+  const float v = rows[(int)sys[OFF_PAIR + X_OBS_LINK0 + j] * LINK_WORDS + k];
+  return k == 2 ? v - sys[OFF_PAIR + X_PLANE_Z] : v;
+}
+CARLB_HD V3 pusher_distances(const float* sys, const float* rows) {
+  const V3 tip = ld3(rows + (int)sys[OFF_PAIR + X_OBS_LINK0] * LINK_WORDS), obj = ld3(rows + (int)sys[OFF_PAIR + X_OBS_LINK1] * LINK_WORDS),
+           goal = ld3(rows + (int)sys[OFF_PAIR + X_OBS_LINK2] * LINK_WORDS);
+  return v3(norm(obj - tip), norm(obj - goal), 0.0f);
+}
+// reward_dist + 0.1 reward_ctrl + 0.5 reward_near, never done (`before` = pusher_distances of the pre-step state)
+CARLB_HD void pusher_outcome(const float* sys, V3 before, float act_sq_sum, float& reward, bool& done) {
+  reward = ((0.0f - before.y) + sys[H_CTRL_COST] * (0.0f - act_sq_sum)) + 0.5f * (0.0f - before.x);
+  done = false;
 }
 
 // world position of the env's site: x.take(link).do(Transform(pos=site)); for the reacher minus the target origin

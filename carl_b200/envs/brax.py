@@ -482,6 +482,39 @@ class CARLBraxHumanoidStandup(CARLBraxEnv):
         return _humanoid_features()
 
 
-# The body of carl/envs/brax/__init__.py that this engine does not build: pusher needs body-vs-body
-# contacts (sphere / capsule against the pushed cylinder). Asking for it fails loudly instead of substituting anything.
-UNSUPPORTED_BODIES = ("CARLBraxPusher",)
+class CARLBraxPusher(CARLBraxEnv):
+    """``carl/envs/brax/carl_pusher.py:11-103``: a 7-dof arm pushes a ball towards a goal marker; gripper-vs-ball
+    contacts are body-vs-body pairs of the kernel's contact phase. Like the reference, the ``goal_position_*``
+    features are part of the context (and of the observed context) but do not move the goal: the reference stores
+    them in ``env._goal_pos``, an attribute nothing reads (:93-103; its own notebook prints the default goal for a
+    changed context)."""
+
+    env_name: str = "pusher"
+    kind = "brax_pusher"
+    asset_path: str = "envs/assets/pusher.xml"
+    metadata = {"render_modes": []}
+    GOAL_FEATURES = ("goal_position_x", "goal_position_y", "goal_position_z")
+
+    @staticmethod
+    def get_context_features() -> dict[str, ContextFeature]:
+        f = _common_features()
+        f["viscosity"] = _uf("viscosity", 0, np.inf, 0)
+        for name, m in (("r_shoulder_pan_link", 7.2935214), ("r_shoulder_lift_link", np.pi), ("r_upper_arm_roll_link", 1.7140529),
+                        ("r_elbow_flex_link", 4.0715042e-01), ("r_forearm_roll_link", 9.2818356e-01),
+                        ("r_wrist_flex_link", 5.0265482e-03), ("r_wrist_roll_link", 1.8346901e-01), ("object", 1.8325957e-03)):
+            f[f"mass_{name}"] = _uf(f"mass_{name}", 1e-6, np.inf, m)
+        f["goal_position_x"] = _uf("goal_position_x", 0, np.inf, 0.45)
+        f["goal_position_y"] = _uf("goal_position_y", 0, np.inf, 0.05)
+        f["goal_position_z"] = _uf("goal_position_z", 0, np.inf, 0.05)
+        return f
+
+    @classmethod
+    def kernel_params(cls, table, names, context_mode="reference", explicit=None):
+        """``carl_pusher.py:93-103``: the goal features are taken out of the context before the family's
+        ``_update_context`` runs (they never reach ``check_context`` nor the physics)."""
+        keep = [j for j, n in enumerate(names) if n not in cls.GOAL_FEATURES]
+        return super().kernel_params(np.asarray(table)[:, keep], [names[j] for j in keep], context_mode, explicit)
+
+
+# Every body of carl/envs/brax/__init__.py is built.
+UNSUPPORTED_BODIES = ()

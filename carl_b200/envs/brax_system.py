@@ -33,7 +33,17 @@ OFF_INIT_Q = OFF_POINTS + POINT_STRIDE * MAX_POINTS
 # per-link rows of the 2- and 3-dof revolute joints (humanoid): what dofs 1 and 2 need beyond the link row
 DOF_STRIDE = 16
 OFF_DOF = OFF_INIT_Q + MAX_Q
-TABLE_FLOATS = OFF_DOF + DOF_STRIDE * MAX_LINKS  # 984 floats = 3936 B (a multiple of 16 B for the bulk copy)
+# body-vs-body contact pairs (pusher: the gripper's capsules against the pushed ball) and what the pusher's env layer
+# reads: a small header (pair count, height of the contact plane, the three links of the observation) + pair rows
+MAX_PAIRS = 4
+PAIR_STRIDE = 16
+PAIR_HEADER = 8
+OFF_PAIR = OFF_DOF + DOF_STRIDE * MAX_LINKS
+TABLE_FLOATS = OFF_PAIR + PAIR_HEADER + PAIR_STRIDE * MAX_PAIRS  # 1056 floats = 4224 B (a multiple of 16 B for the bulk copy)
+(X_N_PAIRS, X_PLANE_Z, X_OBS_LINK0, X_OBS_LINK1, X_OBS_LINK2) = range(5)
+# pair row: capsule side (link, candidate row receiving its impulse, segment end points, radius), sphere side (link,
+# candidate row, centre, radius)
+(R_LINK_A, R_ROW_A, R_A0, R_A1, R_RADIUS_A, R_LINK_B, R_ROW_B, R_B0, R_RADIUS_B) = (0, 1, 2, 5, 8, 9, 10, 11, 14)
 # dof-row slots: actuator index / gear / range of dofs 1 and 2, then the sign of each dof's coordinate against the
 # right-handed joint frame (x = first axis, y = second axis, z = x cross y; -1 where the MJCF axis is -z)
 (D_ACT1, D_ACT2, D_GEAR1, D_GEAR2, D_LO1, D_HI1, D_LO2, D_HI2, D_SIGN0, D_SIGN1, D_SIGN2) = range(11)
@@ -58,7 +68,7 @@ L_SITE = 37  # body-fixed point read by the env layer (pendulum tip / reacher fi
 # TYPE_HINGE2 / TYPE_HINGE3: two / three stacked revolute dofs about the joint frame's x, y(, z) axes (humanoid)
 TYPE_FREE, TYPE_HINGE, TYPE_SLIDE, TYPE_PLANAR, TYPE_SLIDE2, TYPE_HINGE2, TYPE_HINGE3 = 0, 1, 2, 3, 4, 5, 6
 (ENV_ANT, ENV_HALFCHEETAH, ENV_HOPPER, ENV_WALKER2D, ENV_INVERTED_PENDULUM, ENV_INVERTED_DOUBLE_PENDULUM, ENV_REACHER,
- ENV_HUMANOID, ENV_HUMANOIDSTANDUP) = range(9)
+ ENV_HUMANOID, ENV_HUMANOIDSTANDUP, ENV_PUSHER) = range(10)
 TYPE_DOFS = {TYPE_FREE: (7, 6), TYPE_HINGE: (1, 1), TYPE_SLIDE: (1, 1), TYPE_PLANAR: (3, 3), TYPE_SLIDE2: (2, 2),
              TYPE_HINGE2: (2, 2), TYPE_HINGE3: (3, 3)}
 UNLIMITED = 1e30  # joint range of an unlimited hinge
@@ -160,7 +170,7 @@ def geom_mass_inertia(g, density):
 
 
 def body_inertia(geoms, density):
-    parts = [geom_mass_inertia(g, density) for g in geoms]
+    parts = [geom_mass_inertia(g, g.get("density", density)) for g in geoms]
     m = sum(p[0] for p in parts)
     com = sum(p[0] * p[1] for p in parts) / m
     inertia = np.zeros((3, 3))
@@ -178,6 +188,8 @@ def body_inertia(geoms, density):
 def contact_points(geoms):
     pts = []
     for g in geoms:
+        if not g.get("collide", True):  # contype = conaffinity = 0
+            continue
         if g["type"] == "sphere":
             pts.append((g["p0"], g["r"], g.get("friction")))
         else:  # capsule vs plane: both end spheres are contact candidates
@@ -512,6 +524,65 @@ def humanoidstandup_model():
     return m
 
 
+def pusher_model():
+    """Gym / Brax ``pusher.xml`` (``arm3d``, density 300, zero gravity): a 7-dof arm (seven single hinges; the
+    jointless ``r_upper_arm_link`` / ``r_forearm_link`` / ``tips_arm`` bodies are fused into their parents), the pushed
+    object and the goal marker on two slide joints each (MJCF order: y, then x). Collisions as the MJCF's contype /
+    conaffinity bits allow: the gripper's three capsules and the object against the table plane, and the three capsules
+    against the object. The object is a ball of radius 0.05 whose mass is CARL's ``mass_object`` default (1.8326e-3 kg =
+    density 3.5: the Brax asset replaces Gym's cylinder, which the spring backend cannot collide); the arm geometry is
+    pinned by CARL's seven link-mass defaults (``carl/envs/brax/carl_pusher.py:36-84``, ``tests/test_brax_system.py``).
+    Spring backend of brax 0.12.1 ``envs/pusher.py``: dt 0.001, 50 substeps, gears 20. The world is shifted up by 0.325 so
+    that the table is the engine's contact plane z = 0; the observation subtracts the shift again (``X_PLANE_Z``)."""
+    zt = 0.325  # the table plane sits at z = -0.325 in the MJCF
+    x, y, z = (1, 0, 0), (0, 1, 0), (0, 0, 1)
+    no = dict(collide=False)
+    nc = lambda g: dict(g, **no)
+    grip = [capsule((0, -0.1, 0), (0, 0.1, 0), 0.02), capsule((0, -0.1, 0), (0.1, -0.1, 0), 0.02), capsule((0, 0.1, 0), (0.1, 0.1, 0), 0.02)]
+    ball = sphere((0, 0, 0), 0.05)
+    ball["density"] = 3.5
+    marker = nc(sphere((0, 0, 0), 0.001))   # the goal marker: no collisions, negligible mass
+    marker["density"] = 1e-5
+    links = [
+        _link("r_shoulder_pan_link", -1, TYPE_HINGE, (0, -0.6, zt),
+              [nc(sphere((-0.06, 0.05, 0.2), 0.05)), nc(sphere((0.06, 0.05, 0.2), 0.05)), nc(sphere((-0.06, 0.09, 0.2), 0.03)),
+               nc(sphere((0.06, 0.09, 0.2), 0.03)), nc(capsule((0, 0, -0.4), (0, 0, 0.2), 0.1))], axis=z, limit=(-2.2854, 1.714602)),
+        _link("r_shoulder_lift_link", 0, TYPE_HINGE, (0.1, 0, 0), [nc(capsule((0, -0.1, 0), (0, 0.1, 0), 0.1))], axis=y,
+              limit=(-0.5236, 1.3963)),
+        _link("r_upper_arm_roll_link", 1, TYPE_HINGE, (0, 0, 0),
+              [nc(capsule((-0.1, 0, 0), (0.1, 0, 0), 0.02)), nc(capsule((0, 0, 0), (0.4, 0, 0), 0.06))], axis=x, limit=(-1.5, 1.7)),
+        _link("r_elbow_flex_link", 2, TYPE_HINGE, (0.4, 0, 0), [nc(capsule((0, -0.02, 0), (0, 0.02, 0), 0.06))], axis=y,
+              limit=(-2.3213, 0.0)),
+        _link("r_forearm_roll_link", 3, TYPE_HINGE, (0, 0, 0),
+              [nc(capsule((-0.1, 0, 0), (0.1, 0, 0), 0.02)), nc(capsule((0, 0, 0), (0.291, 0, 0), 0.05))], axis=x, limit=(-1.5, 1.5)),
+        _link("r_wrist_flex_link", 4, TYPE_HINGE, (0.321, 0, 0), [nc(capsule((0, -0.02, 0), (0, 0.02, 0), 0.01))], axis=y,
+              limit=(-1.094, 0.0)),
+        _link("r_wrist_roll_link", 5, TYPE_HINGE, (0, 0, 0),
+              [nc(sphere((0.1, -0.1, 0), 0.01)), nc(sphere((0.1, 0.1, 0), 0.01))] + grip, axis=x, limit=(-1.5, 1.5)),
+        _link("object", -1, TYPE_SLIDE2, (0.45, -0.05, -0.275 + zt), [ball], axis=y, limit=(-10.3213, 10.3)),
+        _link("goal", -1, TYPE_SLIDE2, (0.45, -0.05, -0.323 + zt), [marker], axis=y, limit=(-10.3213, 10.3)),
+    ]
+    for l in links[:7]:
+        l["gear"], l["ctrl_range"] = 20.0, (-2.0, 2.0)
+    links[7]["axis2"] = links[8]["axis2"] = x  # slide order of the MJCF: y, then x
+    return dict(
+        name="pusher", env=ENV_PUSHER, links=links, density=300.0, total_mass=None, friction=0.8, init_q=np.zeros(11),
+        dt=0.001, n_frames=50, obs_dim=23, plane_z=zt, obs_links=("r_wrist_flex_link", "object", "goal"),
+        pairs=[("r_wrist_roll_link", k, "object", 0) for k in (2, 3, 4)],  # (capsule link, geom index, sphere link, geom index)
+        # unit effective masses / inertias (scale 1), like the Ant and the reacher: the 2-gram ball and 5-gram wrist
+        # link would need a far smaller step otherwise
+        tunables=dict(constraint_stiffness=5000.0, constraint_vel_damping=50.0, constraint_limit_stiffness=1000.0,
+                      constraint_ang_damping=5.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=1.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.0, qd_noise=0.005, ctrl_cost=0.1, healthy_reward=0.0, z_min=-1e9, z_max=1e9,
+                        forward_weight=0.0, angle_min=0.0, angle_max=0.0, exclude_pos=0, qd_clip=0.0, terminate=0.0,
+                        qd_uniform=1.0),
+        stock_gravity=0.0, stock_ang_damping=-0.05, stock_elasticity=0.0,
+        actuator_links=["r_shoulder_pan_link", "r_shoulder_lift_link", "r_upper_arm_roll_link", "r_elbow_flex_link",
+                        "r_forearm_roll_link", "r_wrist_flex_link", "r_wrist_roll_link"],
+    )
+
+
 def _initial_point_clearance(links, init_q, pts_all, q_idx):
     """Height above the ground (sphere centre z - radius) of every contact candidate in the initial pose:
     a plain forward-kinematics pass (joints at the link origin, as in every model here). Only used to ORDER
@@ -571,6 +642,7 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
         qdi += nqd
     act_of = {name: i for i, name in enumerate(model["actuator_links"])}
     pts_all = []
+    pair_rows = {}
     max_pts = 0
     for i, (l, (m, com, irot, idiag)) in enumerate(zip(links, props)):
         o = OFF_LINKS + LINK_STRIDE * i
@@ -603,6 +675,8 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
                 t[d + D_LO2], t[d + D_HI2] = l["limit"][2]
         else:
             t[o + L_JROT:o + L_JROT + 4] = frame_with_x(l["axis"]) if l["axis"] is not None else (1, 0, 0, 0)
+            if l["type"] == TYPE_SLIDE2 and l.get("axis2") is not None:
+                t[o + L_JROT:o + L_JROT + 4] = frame_with_axes(l["axis"], l["axis2"])
             t[o + L_LIM_LO], t[o + L_LIM_HI] = l["limit"]
             t[o + L_GEAR] = l["gear"]
             t[o + L_ACT] = act_of.get(l["name"], -1)
@@ -612,6 +686,13 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
         t[o + L_MASS] = m
         t[o + L_CTRL_LO], t[o + L_CTRL_HI] = l["ctrl_range"]
         pts = contact_points(l["geoms"]) if model.get("contacts", True) else []
+        # body-vs-body pairs: one extra candidate row per pair on either link receives that pair's impulse (radius -1:
+        # the ground pass leaves such a row inactive)
+        for k, (la, _ga, lb, _gb) in enumerate(model.get("pairs", [])):
+            for side, name in ((0, la), (1, lb)):
+                if name == l["name"]:
+                    pair_rows[(k, side)] = len(pts_all) + len(pts)
+                    pts.append((np.zeros(3), -1.0, None))
         t[o + L_FIRST_PT] = len(pts_all)
         t[o + L_N_PT] = len(pts)
         max_pts = max(max_pts, len(pts))
@@ -643,6 +724,8 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
     t[H_QD_NOISE] = ep.get("qd_noise", ep["reset_noise"])
     actuated = {k.split(":")[0] for k in act_of}
     ranges = {tuple(l["ctrl_range"]) for l in links if l["name"] in actuated}
+    if not ranges:  # a body without actuators (test bodies)
+        ranges = {(-1.0, 1.0)}
     assert len(ranges) == 1 and next(iter(ranges))[0] == -next(iter(ranges))[1], "one symmetric ctrl_range per body"
     t[H_ACT_SCALE] = next(iter(ranges))[1]
     if model.get("site"):
@@ -651,6 +734,19 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
         o = OFF_LINKS + LINK_STRIDE * names.index(site_link)
         t[o + L_SITE:o + L_SITE + 3] = site_pos
     t[OFF_INIT_Q:OFF_INIT_Q + qi] = model["init_q"]
+    pairs = model.get("pairs", [])
+    assert len(pairs) <= MAX_PAIRS
+    t[OFF_PAIR + X_N_PAIRS], t[OFF_PAIR + X_PLANE_Z] = len(pairs), model.get("plane_z", 0.0)
+    for k, name in enumerate(model.get("obs_links", ())):
+        t[OFF_PAIR + X_OBS_LINK0 + k] = names.index(name)
+    for k, (la, ga, lb, gb) in enumerate(pairs):
+        o = OFF_PAIR + PAIR_HEADER + PAIR_STRIDE * k
+        cap, ball = links[names.index(la)]["geoms"][ga], links[names.index(lb)]["geoms"][gb]
+        assert cap["type"] == "capsule" and ball["type"] == "sphere"
+        t[o + R_LINK_A], t[o + R_ROW_A] = names.index(la), pair_rows[(k, 0)]
+        t[o + R_A0:o + R_A0 + 3], t[o + R_A1:o + R_A1 + 3], t[o + R_RADIUS_A] = cap["p0"], cap["p1"], cap["r"]
+        t[o + R_LINK_B], t[o + R_ROW_B] = names.index(lb), pair_rows[(k, 1)]
+        t[o + R_B0:o + R_B0 + 3], t[o + R_RADIUS_B] = ball["p0"], ball["r"]
     stock_friction = float(np.max([p[3] for p in pts_all])) if pts_all else float(model["friction"])
     return dict(
         name=model["name"], table=t.astype(np.float32), link_names=names, n_links=n, n_q=qi, n_qd=qdi,
@@ -665,5 +761,6 @@ def build_system(model: dict, tunables: dict | None = None) -> dict:
 
 MODELS = {"ant": ant_model, "halfcheetah": halfcheetah_model, "hopper": hopper_model, "walker2d": walker2d_model,
           "inverted_pendulum": inverted_pendulum_model, "inverted_double_pendulum": inverted_double_pendulum_model,
-          "reacher": reacher_model, "humanoid": humanoid_model, "humanoidstandup": humanoidstandup_model}
+          "reacher": reacher_model, "humanoid": humanoid_model, "humanoidstandup": humanoidstandup_model,
+          "pusher": pusher_model}
 SYSTEMS = {k: build_system(f()) for k, f in MODELS.items()}

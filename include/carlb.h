@@ -49,6 +49,7 @@ extern "C" {
 #define CARLB_BRAX_REACHER 22                  /* carl/envs/brax/carl_reacher.py:9 (two-slide target body) */
 #define CARLB_BRAX_HUMANOID 23                 /* carl/envs/brax/carl_humanoid.py:14 (stacked 2- / 3-dof hinges, 244-entry obs) */
 #define CARLB_BRAX_HUMANOIDSTANDUP 24          /* carl/envs/brax/carl_humanoidstandup.py:9 */
+#define CARLB_BRAX_PUSHER 25                   /* carl/envs/brax/carl_pusher.py:11 (capsule-vs-ball contact pairs) */
 
 /* state / context precision of a handle */
 #define CARLB_F32 0 /* throughput mode: fp32 state and context in HBM */

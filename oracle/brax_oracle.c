@@ -30,9 +30,14 @@
 #endif
 
 /* ---- table layout (must match carl_b200/envs/brax_system.py) ---- */
-enum { MAXL = 12, MAXP = 32, MAXQ = 24, HDR = 32, LSTR = 40, PSTR = 8, DSTR = 16, MAXOBS = 256 };
+enum { MAXL = 12, MAXP = 32, MAXQ = 24, HDR = 32, LSTR = 40, PSTR = 8, DSTR = 16, MAXOBS = 256, MAXPAIR = 4, RSTR = 16, RHDR = 8 };
 enum { OFF_L = HDR, OFF_P = HDR + LSTR * MAXL, OFF_Q = HDR + LSTR * MAXL + PSTR * MAXP, OFF_D = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ,
-       TABLE_N = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ + DSTR * MAXL };
+       OFF_R = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ + DSTR * MAXL,
+       TABLE_N = HDR + LSTR * MAXL + PSTR * MAXP + MAXQ + DSTR * MAXL + RHDR + RSTR * MAXPAIR };
+/* pair region (body-vs-body contacts, pusher): header, then rows: capsule side (link, candidate row, segment ends,
+ * radius), sphere side (link, candidate row, centre, radius) */
+enum { xN_PAIRS = 0, xPLANE_Z, xOBS_LINK0, xOBS_LINK1, xOBS_LINK2 };
+enum { rLINK_A = 0, rROW_A = 1, rA0 = 2, rA1 = 5, rRAD_A = 8, rLINK_B = 9, rROW_B = 10, rB0 = 11, rRAD_B = 14 };
 /* dof rows (stacked hinges): actuator / gear / range of dofs 1 and 2, sign of each coordinate against the joint frame */
 enum { dACT1 = 0, dACT2, dGEAR1, dGEAR2, dLO1, dHI1, dLO2, dHI2, dSIGN0, dSIGN1, dSIGN2 };
 enum { hN_LINKS = 0, hN_Q, hN_QD, hN_POINTS, hN_FRAMES, hDT, hENV, hN_ACT, hK, hCV, hKL, hCA, hERP, hVDAMP, hMSCALE,
@@ -46,7 +51,7 @@ enum { lPARENT = 0, lTYPE, lQ, lQD, lTPOS = 4, lTROT = 7, lJPOS = 11, lJROT = 14
  * the joint rotation is Rx(a0) Ry(a1) Rz(a2) in the joint frame whose x, y are the first two MJCF axes */
 enum { T_FREE = 0, T_HINGE = 1, T_SLIDE = 2, T_PLANAR = 3, T_SLIDE2 = 4, T_HINGE2 = 5, T_HINGE3 = 6 };
 enum { E_ANT = 0, E_CHEETAH = 1, E_HOPPER = 2, E_WALKER2D = 3, E_IPENDULUM = 4, E_IDPENDULUM = 5, E_REACHER = 6,
-       E_HUMANOID = 7, E_STANDUP = 8 };
+       E_HUMANOID = 7, E_STANDUP = 8, E_PUSHER = 9 };
 
 /* Arithmetic type of the restatement: float (the reference's JAX pipeline) by default; built a
  * second time with -DORACLE_F64 as the round-off-free yardstick that tells float32 noise (stiff
@@ -339,6 +344,7 @@ static void substep(const real *sys, real *rows, const real *ctx, real (*tau)[3]
     origin_of(s, lt, org);
     rot3(pt + 1, s + 3, loc);
     for (int q = 0; q < 3; ++q) c[q] = org[q] + loc[q];
+    if (pt[4] < 0.0f) continue; /* a row that only receives the impulse of a body-vs-body pair */
     real dist = c[2] - pt[4], pen = -dist;
     if (!(pen > 0.0f)) continue;
     f3 n = {0, 0, 1}, cpos = {c[0], c[1], 0.5f * dist}, rel, rv, tmp;
@@ -369,6 +375,81 @@ static void substep(const real *sys, real *rows, const real *ctx, real (*tau)[3]
     cross3(rel, tot, tmp);
     for (int q = 0; q < 3; ++q) { ps[l][q] += tot[q]; ts[l][q] += tmp[q]; }
     na[l] += 1.0f;
+  }
+  /* 3b. body-vs-body contacts (spring/collisions.py with two dynamic bodies): capsule A against sphere B. The contact
+   * normal points from B's centre to the closest point of A's segment (it pushes A away from B), the contact point
+   * lies midway between the two surfaces; the impulse divides by both inverse masses and both angular terms and acts
+   * with opposite signs on the two links; each side counts as one active contact of its link */
+  const int NPAIR = (int)sys[OFF_R + xN_PAIRS];
+  for (int k = 0; k < NPAIR; ++k) {
+    const real *pr = sys + OFF_R + RHDR + RSTR * k;
+    int la = (int)pr[rLINK_A], lb = (int)pr[rLINK_B];
+    const real *lta = sys + OFF_L + LSTR * la, *ltb = sys + OFF_L + LSTR * lb;
+    const real *sa = rows + 13 * la, *sb = rows + 13 * lb;
+    const real *pta = sys + OFF_P + PSTR * (int)pr[rROW_A];
+    real fr = friction < 0.0f ? pta[5] : friction;
+    real el = elasticity < 0.0f ? pta[6] : elasticity;
+    f3 oa, ob, a0, a1, cb, t0;
+    origin_of(sa, lta, oa);
+    origin_of(sb, ltb, ob);
+    rot3(pr + rA0, sa + 3, t0);
+    for (int q = 0; q < 3; ++q) a0[q] = oa[q] + t0[q];
+    rot3(pr + rA1, sa + 3, t0);
+    for (int q = 0; q < 3; ++q) a1[q] = oa[q] + t0[q];
+    rot3(pr + rB0, sb + 3, t0);
+    for (int q = 0; q < 3; ++q) cb[q] = ob[q] + t0[q];
+    /* closest point of the segment a0-a1 to the sphere centre */
+    f3 ab, ac, cp, dvec;
+    for (int q = 0; q < 3; ++q) { ab[q] = a1[q] - a0[q]; ac[q] = cb[q] - a0[q]; }
+    real tt = dot3(ac, ab) / dot3(ab, ab);
+    tt = FMIN(FMAX(tt, 0.0f), 1.0f);
+    for (int q = 0; q < 3; ++q) { cp[q] = a0[q] + tt * ab[q]; dvec[q] = cp[q] - cb[q]; }
+    real dist = SQRT(dot3(dvec, dvec));
+    real pen = pr[rRAD_A] + pr[rRAD_B] - dist;
+    if (!(pen > 0.0f)) continue;
+    f3 n, cpos, ra, rb, va, vb, cv_, tmp;
+    real inv_d = 1.0f / (1e-6f + dist);
+    for (int q = 0; q < 3; ++q) n[q] = dvec[q] * inv_d;
+    /* midway between the sphere's surface point and the capsule's surface point */
+    for (int q = 0; q < 3; ++q) cpos[q] = 0.5f * ((cb[q] + pr[rRAD_B] * n[q]) + (cp[q] - pr[rRAD_A] * n[q]));
+    for (int q = 0; q < 3; ++q) { ra[q] = cpos[q] - sa[q]; rb[q] = cpos[q] - sb[q]; }
+    cross3(sa + 10, ra, tmp);
+    for (int q = 0; q < 3; ++q) va[q] = sa[7 + q] + tmp[q];
+    cross3(sb + 10, rb, tmp);
+    for (int q = 0; q < 3; ++q) vb[q] = sb[7 + q] + tmp[q];
+    for (int q = 0; q < 3; ++q) cv_[q] = va[q] - vb[q];
+    real nv = dot3(n, cv_);
+    real inv_ma = 1.0f / eff_mass(ctx[5 + la], sys), inv_mb = 1.0f / eff_mass(ctx[5 + lb], sys);
+    f3 rxn, t1, t2a, t2b;
+    cross3(ra, n, rxn);
+    apply_inv_inertia(rxn, sa + 3, lta, sys, t1);
+    cross3(t1, ra, t2a);
+    cross3(rb, n, rxn);
+    apply_inv_inertia(rxn, sb + 3, ltb, sys, t1);
+    cross3(t1, rb, t2b);
+    real ang = dot3(n, t2a) + dot3(n, t2b);
+    real denom = inv_ma + inv_mb + ang;
+    real bvel = sys[hERP] * pen / sys[hDT];
+    real imp = (-1.0f * (1.0f + el) * nv + bvel) / denom;
+    f3 vd;
+    for (int q = 0; q < 3; ++q) vd[q] = cv_[q] - nv * n[q];
+    real sd = SQRT(dot3(vd, vd));
+    real impd = sd / denom;
+    real inv_sd = 1.0f / (1e-6f + sd);
+    impd = FMIN(impd, fr * imp);
+    int apply_n = (nv < 0.0f) && (imp > 0.0f);
+    int apply_d = apply_n && (sd > 0.01f);
+    if (!apply_n) continue;
+    f3 tot;
+    for (int q = 0; q < 3; ++q) tot[q] = imp * n[q];
+    if (apply_d)
+      for (int q = 0; q < 3; ++q) tot[q] += -impd * (vd[q] * inv_sd);
+    cross3(ra, tot, tmp);
+    for (int q = 0; q < 3; ++q) { ps[la][q] += tot[q]; ts[la][q] += tmp[q]; }
+    na[la] += 1.0f;
+    cross3(rb, tot, tmp);
+    for (int q = 0; q < 3; ++q) { ps[lb][q] -= tot[q]; ts[lb][q] -= tmp[q]; }
+    na[lb] += 1.0f;
   }
   /* 4. delta-velocity + pose integration */
   for (int l = 0; l < L; ++l) {
@@ -528,6 +609,15 @@ static void make_obs(const real *sys, const real *rows, const real *q, const rea
   int k = 0;
   if (env == E_HUMANOID || env == E_STANDUP) {
     humanoid_obs(sys, rows, q, qd, ctx, act, obs);
+    return;
+  }
+  if (env == E_PUSHER) { /* brax.envs.pusher._get_obs: q[:7], qd[:7], COM of the wrist-flex link, the object, the goal */
+    for (int i = 0; i < 7; ++i) obs[k++] = q[i];
+    for (int i = 0; i < 7; ++i) obs[k++] = qd[i];
+    for (int j = 0; j < 3; ++j) {
+      const real *s = rows + 13 * (int)sys[OFF_R + xOBS_LINK0 + j];
+      obs[k++] = s[0]; obs[k++] = s[1]; obs[k++] = s[2] - sys[OFF_R + xPLANE_Z];
+    }
     return;
   }
   if (env == E_IDPENDULUM) { /* brax.envs.inverted_double_pendulum._get_obs */
@@ -705,6 +795,14 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
     f3 o0, o1;
     origin_of(rows, sys + OFF_L, o0);
     if (env == E_HUMANOID) body_com(sys, rows, c, o0); /* humanoid: velocity of the body COM, not of the torso */
+    real near0 = 0.0f, dist0 = 0.0f;
+    if (env == E_PUSHER) { /* brax.envs.pusher.step: the reward reads the positions BEFORE the pipeline advances */
+      const real *tip = rows + 13 * (int)sys[OFF_R + xOBS_LINK0], *ob_ = rows + 13 * (int)sys[OFF_R + xOBS_LINK1],
+                 *gl = rows + 13 * (int)sys[OFF_R + xOBS_LINK2];
+      f3 v1 = {ob_[0] - tip[0], ob_[1] - tip[1], ob_[2] - tip[2]}, v2 = {ob_[0] - gl[0], ob_[1] - gl[1], ob_[2] - gl[2]};
+      near0 = SQRT(dot3(v1, v1));
+      dist0 = SQRT(dot3(v2, v2));
+    }
     for (int f = 0; f < NF; ++f) substep(sys, rows, c, tau);
     origin_of(rows, sys + OFF_L, o1);
     real z_root = o1[2];
@@ -740,6 +838,9 @@ void NAME(brax_oracle_step)(const float *sys_f, int n, real *state, int state_wo
       real vel_penalty = 1e-3f * (qd[1] * qd[1]) + 5e-3f * (qd[2] * qd[2]);
       r = 10.0f - dist_penalty - vel_penalty;
       done = tip[2] <= 1.0f;
+    } else if (env == E_PUSHER) { /* reward_dist + 0.1 reward_ctrl + 0.5 reward_near, never done */
+      r = ((0.0f - dist0) + sys[hCTRL] * (0.0f - act_sq)) + 0.5f * (0.0f - near0);
+      done = 0;
     } else if (env == E_STANDUP) { /* brax.envs.humanoidstandup.step: uph_cost + 1 - quad_ctrl_cost, never done */
       r = (z_root - 0.0f) / dt_env + sys[hHEALTHY] - sys[hCTRL] * act_sq;
       done = 0;

@@ -37,6 +37,30 @@ def random_q(sysd, n, rng, scale=1.0):
     return q.astype(np.float32), qd
 
 
+def pusher_contact_states(sysd, n, rng):
+    """Pusher states in which the gripper is down at the table next to the ball (the arm lowered by the shoulder-lift
+    joint, the ball placed within 0.12 of the wrist-roll link's centre of mass): roughly a quarter of them have an
+    active capsule-vs-ball contact pair, which generic random states around the initial pose never reach."""
+    from oracle.brax import OracleBraxEnv
+
+    nq = sysd["n_q"]
+    q = np.zeros((n, nq), np.float32)
+    qd = np.zeros((n, sysd["n_qd"]), np.float32)
+    q[:, 0] = rng.uniform(-0.5, 0.8, n)
+    q[:, 1] = rng.uniform(0.30, 0.42, n)
+    q[:, 2:7] = rng.uniform(-0.1, 0.1, (n, 5))
+    q[:, 3] -= 0.15
+    q[:, 5] -= 0.1
+    qd[:, :7] = rng.uniform(-1, 1, (n, 7))
+    ora = OracleBraxEnv(sysd, np.ones((n, 5 + sysd["n_links"]), np.float32), autoreset=False)
+    ora.init_from_q(q, qd)
+    wrist = ora.state[:, :13 * sysd["n_links"]].reshape(n, sysd["n_links"], 13)[:, 6, :3]
+    ang, dist = rng.uniform(0, 2 * np.pi, n), rng.uniform(0.0, 0.12, n)
+    q[:, 8] = wrist[:, 0] + dist * np.cos(ang) - 0.45   # slide along x (second coordinate of the object)
+    q[:, 7] = wrist[:, 1] + dist * np.sin(ang) + 0.05   # slide along y
+    return q, qd
+
+
 class BraxHostCheck:
     def __init__(self):
         from tests.hostcheck.build_hostcheck import build

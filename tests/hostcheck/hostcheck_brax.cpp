@@ -77,6 +77,11 @@ static void obs_of(const float* sys, const LinkState* st, float* obs, float* roo
       taus_of(sys, l, act, tau);
       for (int d = 0; d < type_ndof((int)lt[L_TYPE]); ++d) obs[k + (int)lt[L_QDIDX] + d] = tau[d];
     }
+  } else if (kind == ENV_PUSHER) {
+    float rows[MAX_LINKS * LINK_WORDS];
+    for (int l = 0; l < L; ++l) wr(rows + l * LINK_WORDS, st[l]);
+    for (int i = 0; i < 23; ++i) obs[i] = pusher_obs_entry(sys, i, q, qd, rows);
+    site = pusher_distances(sys, rows);
   } else if (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER) {
     const int D = kind == ENV_REACHER ? 11 : 8;
     for (int i = 0; i < D; ++i) obs[i] = special_obs_entry(kind, i, q, qd, site);
@@ -178,7 +183,7 @@ static void step_all(const float* sys, int n, float* state, int words, const flo
         const LinkState& pst = st[parent < 0 ? 0 : parent];
         const int jt = (int)lt[L_TYPE];
         const bool revolute = jt == TYPE_HINGE || jt == TYPE_PLANAR || jt == TYPE_HINGE2 || jt == TYPE_HINGE3;
-        const bool special = (int)sys[H_ENV] >= ENV_INVERTED_PENDULUM && (int)sys[H_ENV] <= ENV_REACHER;  // kernels: MODE_SPECIAL
+        const bool special = is_special_env((int)sys[H_ENV]);  // kernels: MODE_SPECIAL
         const JointOut jo = (FAST && revolute && !special)
                                 ? joint_resolve_world<true>(sys, lt, st[l], parent < 0, pst, tau[0], c[C_STIFFNESS_SCALE],
                                                             parent_anchor_from_com(lt, plt, parent < 0), joint_flags(lt),
@@ -209,6 +214,17 @@ static void step_all(const float* sys, int n, float* state, int words, const flo
         }
         co[p] = contact_resolve<FAST>(sys, pt, link_tab(sys, l), nx[l], lcs[l], fr, el, org[l]);
       }
+      // body-vs-body pairs (pusher): each writes the two candidate rows reserved for it
+      for (int k = 0; k < (int)sys[OFF_PAIR + X_N_PAIRS]; ++k) {
+        const float* pr = pair_tab(sys, k);
+        const int la = (int)pr[R_LINK_A], lb = (int)pr[R_LINK_B], ra = (int)pr[R_ROW_A], rb = (int)pr[R_ROW_B];
+        const float* pta = point_tab(sys, ra);
+        const float fr = (c[C_FRICTION] < 0.0f || stock_contact) ? pta[5] : c[C_FRICTION];
+        const float el = (c[C_ELASTICITY] < 0.0f || stock_contact) ? pta[6] : c[C_ELASTICITY];
+        const PairOut po = pair_resolve(sys, pr, link_tab(sys, la), link_tab(sys, lb), nx[la], nx[lb], lcs[la], lcs[lb], fr, el);
+        co[ra].p = po.p; co[ra].t = po.ta; co[ra].active = po.active;
+        co[rb].p = v3(0, 0, 0) - po.p; co[rb].t = po.tb; co[rb].active = po.active;
+      }
       for (int l = 0; l < L; ++l) {
         const float* lt = link_tab(sys, l);
         V3 ps = v3(0, 0, 0), ts = v3(0, 0, 0);
@@ -233,7 +249,9 @@ static void step_all(const float* sys, int n, float* state, int words, const flo
                 !(after[2] < sys[H_ANGLE_MIN]);
     float r = sys[H_FORWARD_WEIGHT] * xvel + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
     bool done = sys[H_TERMINATE] > 0.0f && !healthy;
-    if (kind == ENV_HUMANOIDSTANDUP) {  // uph_cost + 1 - quad_ctrl_cost, never done
+    if (kind == ENV_PUSHER) {
+      pusher_outcome(sys, v3(before[7], before[8], before[9]), act_sq, r, done);
+    } else if (kind == ENV_HUMANOIDSTANDUP) {  // uph_cost + 1 - quad_ctrl_cost, never done
       r = (after[1] - 0.0f) / dt_env + sys[H_HEALTHY_REWARD] - sys[H_CTRL_COST] * act_sq;
       done = false;
     } else if (kind >= ENV_INVERTED_PENDULUM && kind <= ENV_REACHER) special_outcome(kind, after[4], after[5], after[6], v3(after[7], after[8], after[9]), act_sq, r, done);

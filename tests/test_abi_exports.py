@@ -90,6 +90,6 @@ def test_new_entry_points_reject_null_handles_without_touching_the_gpu(native_li
     rc = native_lib.carlb_brax_goal_step(None, 0, 1, ctypes.c_double(0.01), None, None, None, None, None, None)
     assert rc in (_native.ERR_INVALID, _native.ERR_STATE) and native_lib.carlb_last_error()
     for kind, (D, A) in {"brax_inverted_pendulum": (4, 1), "brax_inverted_double_pendulum": (8, 1), "brax_reacher": (11, 2),
-                         "brax_humanoid": (244, 17), "brax_humanoidstandup": (244, 17)}.items():
+                         "brax_humanoid": (244, 17), "brax_humanoidstandup": (244, 17), "brax_pusher": (23, 7)}.items():
         q = _native.query_env(_native.KIND[kind])
         assert (q.obs_dim, q.act_dim, q.default_max_steps) == (D, A, 1000)

@@ -7,13 +7,13 @@ import torch
 
 from carl_b200.envs import brax_system as bs
 from oracle.brax import OracleBraxEnv
-from tests.brax_util import assert_close_scaled, random_q
+from tests.brax_util import assert_close_scaled, pusher_contact_states, random_q
 
 pytestmark = pytest.mark.gpu
 BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper",
           "walker2d": "CARLBraxWalker2d", "inverted_pendulum": "CARLBraxInvertedPendulum",
           "inverted_double_pendulum": "CARLBraxInvertedDoublePendulum", "reacher": "CARLBraxReacher",
-          "humanoid": "CARLBraxHumanoid", "humanoidstandup": "CARLBraxHumanoidStandup"}
+          "humanoid": "CARLBraxHumanoid", "humanoidstandup": "CARLBraxHumanoidStandup", "pusher": "CARLBraxPusher"}
 HUMANOIDS = ("humanoid", "humanoidstandup")
 # blocks of brax.envs.humanoid._get_obs: q[2:] ++ qd | cinert | cvel | actuator torques. The torques reach 140
 # (gear 350 x 0.4), so an error relative to the whole vector's magnitude would not see the joint coordinates: each
@@ -24,11 +24,16 @@ HUM_BLOCK_F64_TOL = 6e-5  # against the float64 yardstick (the float32 restateme
 
 
 OBS_TOL = 1e-5
+# pusher: 50 substeps per env-step (the Ant has 10); its float32 restatement sits 1.2-1.6e-5 (obs) / 1.3e-5 (state) from
+# float64 on contact-free states, hence its own float64-yardstick numbers. States with live gripper-vs-ball contacts are
+# compared over a 2-substep horizon instead (test_pusher_contact_pairs_match): hard contacts amplify a last-bit
+# difference by ~1e6 over 50 substeps in ANY arithmetic (float32 vs float64 oracle: up to 0.3 on those states).
+F64_OBS_TOL_BODY = {"pusher": 4e-5}
 STATE_TOL = {"ant": 1.5e-5, "halfcheetah": 4e-5, "hopper": 1e-5, "walker2d": 1e-5, "inverted_pendulum": 1e-5,
-             "inverted_double_pendulum": 1.5e-5, "reacher": 1.5e-5, "humanoid": 2e-5, "humanoidstandup": 2e-5}
+             "inverted_double_pendulum": 1.5e-5, "reacher": 1.5e-5, "humanoid": 2e-5, "humanoidstandup": 2e-5, "pusher": 2e-5}
 F64_OBS_TOL = 1.5e-5
 F64_STATE_TOL = {"ant": 1.5e-5, "halfcheetah": 6e-5, "hopper": 2e-5, "walker2d": 2e-5, "inverted_pendulum": 2e-5,
-                 "inverted_double_pendulum": 2.5e-5, "reacher": 2e-5, "humanoid": 6e-5, "humanoidstandup": 6e-5}
+                 "inverted_double_pendulum": 2.5e-5, "reacher": 2e-5, "humanoid": 6e-5, "humanoidstandup": 6e-5, "pusher": 4e-5}
 
 
 # arithmetic="fma" (FMA contraction + the FAST world-frame reformulations): same tolerances against the float64
@@ -51,6 +56,10 @@ def make_env(body, n, rng, mode="applied", **kw):
     d = cls.get_default_context()
     table = np.tile(np.array([float(d[k]) for k in names]), (n, 1))
     table[:, names.index("gravity")] = rng.uniform(-15, -5, n)
+    if body == "pusher":
+        # (almost) the MJCF's zero gravity: under gravity the ball, which rests exactly tangent to the table, chatters
+        # between contact and no contact -- differently in float32 and float64, whatever the implementation
+        table[:, names.index("gravity")] = rng.uniform(-1e-3, -1e-6, n)
     table[:, names.index("friction")] = rng.uniform(0.5, 1.5, n)
     table[:, names.index("elasticity")] = rng.uniform(0.0, 0.3, n)
     table[:, names.index("viscosity")] = rng.uniform(-0.1, 0.0, n)  # overwrites ang_damping (reference quirk B2)
@@ -126,7 +135,7 @@ def test_single_env_step_matches(body, mode):
     #    sits 0.5 .. 3.6e-5 from float64 (`floor` above), no float32 implementation can be closer.
     assert scaled_err(got, o_ref) <= OBS_TOL, (body, mode, scaled_err(got, o_ref))
     assert scaled_err(env.state.cpu().numpy(), ora.state) <= STATE_TOL[body], (body, mode)
-    assert e_obs <= F64_OBS_TOL and e_state <= F64_STATE_TOL[body], (body, mode, e_obs, e_state)
+    assert e_obs <= F64_OBS_TOL_BODY.get(body, F64_OBS_TOL) and e_state <= F64_STATE_TOL[body], (body, mode, e_obs, e_state)
     if body in HUMANOIDS:
         b32, b64 = humanoid_block_errs(got, o_ref), humanoid_block_errs(got, o64)
         print(f"[{body}/{mode}] obs blocks vs fp32 oracle {b32}; vs f64 {b64}")
@@ -169,8 +178,8 @@ def test_fma_arithmetic_within_the_float64_yardstick_tolerance(body):
     if os.path.isdir(out):
         with open(os.path.join(out, "brax_parity_floor.txt"), "a") as f:
             f.write(line + "\n")
-    assert e_obs <= F64_OBS_TOL and e_state <= FMA_F64_STATE_TOL[body], (body, e_obs, e_state)
-    assert scaled_err(got, o_ref) <= 1.5e-5
+    assert e_obs <= F64_OBS_TOL_BODY.get(body, F64_OBS_TOL) and e_state <= FMA_F64_STATE_TOL[body], (body, e_obs, e_state)
+    assert scaled_err(got, o_ref) <= F64_OBS_TOL_BODY.get(body, 1.5e-5)
     if body in HUMANOIDS:
         b64 = humanoid_block_errs(got, o64)
         assert max(b64.values()) <= HUM_BLOCK_F64_TOL, b64
@@ -195,6 +204,9 @@ def test_rollout_with_autoreset_matches(body):
     whatever the implementation, so the per-step transition is what can be compared."""
     rng = np.random.default_rng(2)
     n, T, max_steps = 64, 60, 25
+    # pusher: gentle actions keep the gripper off the table and the ball for the 25-step episodes (live hard contacts
+    # are compared over a short horizon in test_pusher_contact_pairs_match, see the tolerance notes at the top)
+    act_gain = 0.15 if body == "pusher" else 1.0
     env = make_env(body, n, rng, max_episode_steps=max_steps)
     q, qd = random_q(env._sysd, n, rng)
     env.reset_from_q(q, qd)
@@ -202,7 +214,7 @@ def test_rollout_with_autoreset_matches(body):
     ora.init_from_q(q, qd)
     n_done = 0
     for t in range(T):
-        a = (rng.uniform(-1, 1, (n, env._sysd["n_act"])) * env._sysd["act_scale"]).astype(np.float32)
+        a = (rng.uniform(-1, 1, (n, env._sysd["n_act"])) * env._sysd["act_scale"] * act_gain).astype(np.float32)
         ora.state[:] = env.state.cpu().numpy()
         ora.elapsed[:] = env._elapsed.cpu().numpy()
         o_ref, r_ref, d_ref, fin_ref = ora.step(a)
@@ -376,15 +388,17 @@ PACK_SCRIPT = r"""
 import sys, numpy as np, torch
 sys.path.insert(0, {root!r})
 from carl_b200.envs import (CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxWalker2d, CARLBraxInvertedPendulum,
-                            CARLBraxInvertedDoublePendulum, CARLBraxReacher)
+                            CARLBraxInvertedDoublePendulum, CARLBraxReacher, CARLBraxHumanoid, CARLBraxHumanoidStandup,
+                            CARLBraxPusher)
 out = {{}}
 for cls, name in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
                   (CARLBraxWalker2d, "walker2d"), (CARLBraxInvertedPendulum, "inverted_pendulum"),
-                  (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher")):
+                  (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher"),
+                  (CARLBraxHumanoid, "humanoid"), (CARLBraxHumanoidStandup, "humanoidstandup"), (CARLBraxPusher, "pusher")):
     env = cls(num_envs=301, max_episode_steps=7)   # ragged vs both 12- and 4-env CTAs, short episodes
     env.reset(seed=3)
     t = env.rollout(24, policy_seed=5, record=True)
-    acts = (torch.rand(301, env._info.act_dim, generator=torch.Generator().manual_seed(1)) * 2 - 1).cuda()
+    acts = ((torch.rand(301, env._info.act_dim, generator=torch.Generator().manual_seed(1)) * 2 - 1) * env._sysd["act_scale"]).cuda()
     o, r, te, tr, _ = env.step(acts)
     out[name + "_obs"] = t["obs"].cpu().numpy(); out[name + "_rew"] = t["reward"].cpu().numpy()
     out[name + "_done"] = t["done"].cpu().numpy(); out[name + "_step"] = o["obs"].cpu().numpy()
@@ -394,8 +408,8 @@ np.savez(sys.argv[1], **out)
 
 
 def test_packed_lanes_equal_one_env_per_warp(tmp_path):
-    """Three / four envs per warp (Ant E = 3, Halfcheetah and Hopper E = 4) must be BIT-identical to
-    one env per warp (E = 1): the lane mapping changes, the per-link arithmetic does not."""
+    """Two / three / four envs per warp (humanoids E = 2, Ant and pusher E = 3, Halfcheetah and Hopper E = 4) must be
+    BIT-identical to one env per warp (E = 1): the lane mapping changes, the per-link arithmetic does not."""
     import os
     import subprocess
     import sys
@@ -478,6 +492,16 @@ def test_reset_draws_follow_the_jax_threefry_stream(body, n):
                 ang = np.float32(6.283185307179586) * jp.uniform(r2, 1)[0]
                 q[i, 2:4] = [dist * np.cos(ang, dtype=np.float32), dist * np.sin(ang, dtype=np.float32)]
                 qd[i, 2:4] = 0.0
+            if body == "pusher":  # brax.envs.pusher.reset: object at (U(rng), U(rng1)), pushed out to 0.17 from the goal
+                _, k1, _ = jp.split(jp.env_reset_key(0, k, n, i), 3)  # (rng0 above is the env's new `rng`, k1 its `rng1`)
+                c = np.array([jp.uniform(rng0, 1, np.float32(-0.3), np.float32(-1e-6))[0],
+                              jp.uniform(k1, 1, np.float32(-0.2), np.float32(0.2))[0]], np.float32)
+                nrm = np.sqrt(c[0] * c[0] + c[1] * c[1], dtype=np.float32)
+                if nrm < np.float32(0.17):
+                    c = c * (np.float32(0.17) / nrm)
+                q[i] = init_q
+                q[i, 7:9] = c
+                qd[i, 7:] = 0.0
         twin.reset_from_q(q, qd)
         np.testing.assert_allclose(env.state.cpu().numpy(), twin.state.cpu().numpy(), rtol=2e-6, atol=2e-7,
                                    err_msg=f"{body} n={n} reset {k}")
@@ -485,8 +509,43 @@ def test_reset_draws_follow_the_jax_threefry_stream(body, n):
     # an explicit seed re-keys the stream: PRNGKey(5), reset count 0 again
     env.reset(seed=5)
     dq, v, _ = jp.brax_reset_draws(5, 0, n, n - 1, nq, nqd, q_noise, qd_noise, qd_uniform)
-    if body != "reacher":
+    if body not in ("reacher", "pusher"):
         q1 = (init_q + dq)[None]
         twin1 = make_env(body, 1, np.random.default_rng(0))
         twin1.reset_from_q(q1.astype(np.float32), v[None].astype(np.float32))
         np.testing.assert_allclose(env.state.cpu().numpy()[n - 1], twin1.state.cpu().numpy()[0], rtol=2e-6, atol=2e-7)
+
+
+def test_pusher_contact_pairs_match(monkeypatch):
+    """The body-vs-body pairs of the pusher (gripper capsules against the pushed ball) through the CUDA kernels, on
+    states built to have them, over a TWO-substep env-step (the table's n_frames patched from 50 to 2: hard contacts
+    amplify a last-bit libm difference ~1e6-fold over 50 substeps in any arithmetic, so the long horizon says nothing
+    about an implementation): observations, link state and reward against the float32 oracle, the ball really struck
+    in a good share of the envs. (Packed lanes vs one env per warp: test_packed_lanes_equal_one_env_per_warp.)"""
+    import carl_b200.envs as E
+    from carl_b200.envs import ContextTable
+
+    short = dict(bs.SYSTEMS["pusher"])
+    short["table"] = short["table"].copy()
+    short["table"][bs.H_N_FRAMES] = 2
+    monkeypatch.setitem(bs.SYSTEMS, "pusher", short)
+    n = 2048
+    rng = np.random.default_rng(4)
+    env = make_env("pusher", n, rng, autoreset=False)
+    assert int(env._sysd["table"][bs.H_N_FRAMES]) == 2
+    q, qd = pusher_contact_states(env._sysd, n, rng)
+    env.reset_from_q(q, qd)
+    ora = oracle_for(env, autoreset=False)
+    ora.init_from_q(q, qd)
+    struck = np.zeros(n, bool)
+    for _ in range(6):
+        a = rng.uniform(-2, 2, (n, 7)).astype(np.float32)
+        ora.state[:] = env.state.cpu().numpy()
+        o_ref, r_ref, d_ref, _ = ora.step(a)
+        obs, r, te, tr, _ = env.step(torch.from_numpy(a).cuda())
+        assert scaled_err(obs["obs"].cpu().numpy(), o_ref) <= OBS_TOL
+        assert scaled_err(env.state.cpu().numpy(), ora.state) <= STATE_TOL["pusher"]
+        np.testing.assert_allclose(r.cpu().numpy(), r_ref, rtol=1e-5, atol=1e-5)
+        assert not te.any()
+        struck |= np.abs(ora.state[:, 13 * 7 + 7:13 * 7 + 9]).max(axis=1) > 1e-3
+    assert struck.mean() > 0.1

@@ -7,10 +7,10 @@ import pytest
 
 from carl_b200.envs import brax_system as bs
 from oracle.brax import OracleBraxEnv
-from tests.brax_util import BraxHostCheck, assert_close_scaled, random_ctx, random_q
+from tests.brax_util import BraxHostCheck, assert_close_scaled, pusher_contact_states, random_ctx, random_q
 
 BODIES = ["ant", "halfcheetah", "hopper", "walker2d", "inverted_pendulum", "inverted_double_pendulum", "reacher",
-          "humanoid", "humanoidstandup"]
+          "humanoid", "humanoidstandup", "pusher"]
 HUMANOIDS = ("humanoid", "humanoidstandup")
 
 
@@ -85,6 +85,15 @@ def test_pipeline_init_matches(hc, body):
         tip = np.stack([0.1 * np.cos(th1) + 0.11 * np.cos(th12), 0.1 * np.sin(th1) + 0.11 * np.sin(th12), 0.01 + 0 * th1], axis=1)
         tgt = np.concatenate([q[:, 2:4], np.full((q.shape[0], 1), 0.01)], axis=1)
         want = np.concatenate([np.cos(q[:, :2]), np.sin(q[:, :2]), q[:, 2:4], qd[:, :2], tip - tgt], axis=1)
+    if body == "pusher":  # q[:7], qd[:7], centres of mass of the wrist-flex link, the object and the goal
+        L = sysd["n_links"]
+        rows = ora.state[:, :13 * L].reshape(-1, L, 13)
+        com = rows[:, [5, 7, 8], :3].copy()
+        com[..., 2] -= 0.325  # heights are reported in the MJCF's world (table at z = -0.325)
+        want = np.concatenate([q[:, :7], qd[:, :7], com.reshape(-1, 9)], axis=1)
+        # the object and the goal ride on their slides: x = 0.45 + second coordinate, y = -0.05 + first coordinate
+        np.testing.assert_allclose(com[:, 1, :2], np.stack([0.45 + q[:, 8], -0.05 + q[:, 7]], axis=1), atol=2e-6)
+        np.testing.assert_allclose(com[:, 2, :2], np.stack([0.45 + q[:, 10], -0.05 + q[:, 9]], axis=1), atol=2e-6)
     if body == "ant":  # the free root's quaternion is normalised by forward()
         want[:, 1:5] /= np.linalg.norm(want[:, 1:5], axis=1, keepdims=True)
         want[:, 13 + 3:13 + 6] = o_ref[:, 13 + 3:13 + 6]  # angular velocity is reported in the local frame
@@ -127,6 +136,10 @@ def test_fast_arithmetic_is_the_same_mathematics(hc, body):
     n = 512
     rng = np.random.default_rng(1)
     ctx = random_ctx(sysd, n, rng)
+    if body == "pusher":
+        # the MJCF's zero gravity: under gravity the ball, which rests exactly tangent to the table, chatters between
+        # contact and no contact -- in float32 and float64 differently, whatever the implementation
+        ctx[:, 0] = 0.0
     q, qd = random_q(sysd, n, rng, scale=2.0)
     ora64 = OracleBraxEnv(sysd, ctx, autoreset=False, f64=True)
     ora64.init_from_q(q, qd)
@@ -135,8 +148,9 @@ def test_fast_arithmetic_is_the_same_mathematics(hc, body):
     st, o0 = hc.init(sysd, q, qd, ctx)
     el = np.zeros(n, dtype=np.int32)
     o, r, d = hc.step(sysd, st, ctx, a, el, 1000, 0, st.copy(), o0.copy(), fast=True)
-    assert_close_scaled(o, o64, rel=2e-5)
-    assert_close_scaled(st, ora64.state, rel=6e-5, what="state")
+    # (the pusher integrates 50 substeps per env-step, five times the Ant's: its round-off floor is accordingly higher)
+    assert_close_scaled(o, o64, rel=1e-4 if body == "pusher" else 2e-5)
+    assert_close_scaled(st, ora64.state, rel=1e-4 if body == "pusher" else 6e-5, what="state")
     assert (d == d64).all()
 
 
@@ -190,6 +204,10 @@ def test_physical_sanity(body):
         return
     if body == "reacher":
         assert np.isfinite(obs).all() and np.abs(obs[0, 6:8]).max() < 0.5
+        return
+    if body == "pusher":  # zero gravity, no control: the arm stays where it is, ball and goal do not move
+        assert np.isfinite(obs).all() and np.abs(obs[0, :14]).max() < 1e-3
+        np.testing.assert_allclose(obs[0, 14:], [0.821, -0.6, 0.0, 0.45, -0.05, -0.275, 0.45, -0.05, -0.323], atol=1e-4)
         return
     if body.startswith("inverted"):  # an unstable equilibrium: the pole may fall, the cart stays on its rail
         assert np.isfinite(obs).all() and abs(obs[0, 0]) < 1.1
@@ -321,6 +339,128 @@ def test_stacked_hinge_pendulum_period_and_torque_response_are_analytic(hc, stac
     for o in (o_o, o_k):
         assert o[0, ydof] == pytest.approx(want, rel=0.01)
         assert abs(o[0, 0]) < 1e-3
+
+
+def test_pusher_gripper_ball_contacts_match(hc):
+    """The body-vs-body pairs of the pusher (gripper capsules against the pushed ball) on states built to have them:
+    kernel source vs oracle, teacher-forced over several env-steps; the ball must really be struck in a good share of
+    the envs (it has no actuator and no gravity: only a contact can set it in motion)."""
+    sysd = bs.SYSTEMS["pusher"]
+    n = 512
+    rng = np.random.default_rng(4)
+    ctx = random_ctx(sysd, n, rng)
+    ctx[:, 0] = 0.0  # the MJCF's zero gravity
+    q, qd = pusher_contact_states(sysd, n, rng)
+    ora = OracleBraxEnv(sysd, ctx, autoreset=False, max_steps=0)
+    o0 = ora.init_from_q(q, qd)
+    st, o = hc.init(sysd, q, qd, ctx)
+    np.testing.assert_allclose(st, ora.state, rtol=1e-6, atol=1e-6)
+    el = np.zeros(n, dtype=np.int32)
+    struck = np.zeros(n, bool)
+    for _ in range(4):
+        a = rng.uniform(-2, 2, (n, 7)).astype(np.float32)
+        o_ref, r_ref, d_ref, _ = ora.step(a)
+        o, r, d = hc.step(sysd, st, ctx, a, el, 0, 0, st.copy(), o0.copy())
+        assert_close_scaled(o, o_ref, rel=1e-5)
+        assert_close_scaled(st, ora.state, rel=1e-5, what="state")
+        np.testing.assert_allclose(r, r_ref, rtol=1e-5, atol=1e-5)
+        assert not d.any() and not d_ref.any()
+        struck |= np.abs(ora.state[:, 13 * 7 + 7:13 * 7 + 9]).max(axis=1) > 1e-3
+        st[:] = ora.state
+    assert struck.mean() > 0.15
+    # reward of brax.envs.pusher.step: positions BEFORE the step: -|object - goal| - 0.1 |a|^2 - 0.5 |object - wrist-flex link|
+    rows = ora.state[:, :13 * 9].reshape(n, 9, 13).copy()
+    a = rng.uniform(-2, 2, (n, 7)).astype(np.float32)
+    _, r_ref, _, _ = ora.step(a)
+    want = (-np.linalg.norm(rows[:, 7, :3] - rows[:, 8, :3], axis=1) - 0.1 * (a.astype(np.float64) ** 2).sum(1)
+            - 0.5 * np.linalg.norm(rows[:, 7, :3] - rows[:, 5, :3], axis=1))
+    np.testing.assert_allclose(r_ref, want, rtol=1e-5, atol=1e-5)
+
+
+def _bar_and_ball():
+    """A synthetic two-body system no shipped env has: a free-floating capsule and a free-floating ball (real masses,
+    unit effective inertias), paired for body-vs-body contact, far above the ground, no gravity."""
+    bar = bs._link("bar", -1, bs.TYPE_FREE, (0, 0, 5.0), [bs.capsule((-0.3, 0, 0), (0.3, 0, 0), 0.05)])
+    ball = bs._link("ball", -1, bs.TYPE_FREE, (0, 0.5, 5.0), [bs.sphere((0, 0, 0), 0.08)])
+    init_q = np.array([0, 0, 5, 1, 0, 0, 0, 0, 0.5, 5, 1, 0, 0, 0], dtype=np.float64)
+    return dict(
+        name="bar_and_ball", env=bs.ENV_HALFCHEETAH, links=[bar, ball], density=1000.0, total_mass=None, friction=0.0,
+        init_q=init_q, dt=0.001, n_frames=1, pairs=[("bar", 0, "ball", 0)],
+        tunables=dict(constraint_stiffness=1000.0, constraint_vel_damping=10.0, constraint_limit_stiffness=0.0,
+                      constraint_ang_damping=0.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.0, ctrl_cost=0.0, healthy_reward=0.0, z_min=-1e9, z_max=1e9, forward_weight=0.0,
+                        angle_min=0.0, angle_max=0.0, exclude_pos=0, qd_clip=0.0, terminate=0.0),
+        stock_gravity=0.0, stock_ang_damping=0.0, stock_elasticity=0.0, actuator_links=[],
+    )
+
+
+def test_two_body_collision_conserves_momentum_and_restitutes(hc):
+    """Independent anchor of the body-vs-body impulse (nothing in the code encodes it): a ball thrown at a free bar.
+    The impulse is equal and opposite and acts at ONE point, so the total linear momentum and the total angular
+    momentum about the world origin (orbital + spin, unit effective inertias) are conserved through the collision;
+    and along the contact normal the separation speed after one substep is e times the approach speed plus the
+    Baumgarte term erp * penetration / dt. Oracle (float64, float32) and kernel source."""
+    model = _bar_and_ball()
+    model["env_params"] = dict(model["env_params"])
+    sysd = bs.build_system(model)
+    assert sysd["n_act"] == 0 and sysd["n_q"] == 14
+    n = 64
+    rng = np.random.default_rng(11)
+    ctx = random_ctx(sysd, n, rng)
+    ctx[:, 0] = 0.0       # no gravity
+    ctx[:, 1] = 0.0       # frictionless: the impulse is purely normal
+    ctx[:, 3] = 0.0       # no angular damping
+    el_ = ctx[:, 2].astype(np.float64)
+    m = ctx[:, 5:7].astype(np.float64)
+    q = np.tile(np.asarray(model["init_q"], np.float32), (n, 1))
+    # ball centre 0.12 from the bar's axis (radii 0.05 + 0.08: penetration 0.01), somewhere along the bar
+    q[:, 7] = rng.uniform(-0.25, 0.25, n)
+    q[:, 8] = 0.12
+    qd = np.zeros((n, 12), np.float32)
+    qd[:, 7] = -rng.uniform(0.5, 2.0, n)      # ball flies towards the bar (-y)
+    qd[:, 6] = rng.uniform(-1, 1, n)          # and sideways
+    qd[:, 0:3] = rng.uniform(-0.2, 0.2, (n, 3))
+    qd[:, 5] = rng.uniform(-1, 1, n)          # the bar spins about z
+    a = np.zeros((n, 0), np.float32)
+
+    def momenta(state):
+        rows = np.array(state, dtype=np.float64)[:, :26].reshape(n, 2, 13)  # a copy: the oracle steps in place
+        pos, vel, ang = rows[..., 0:3], rows[..., 7:10], rows[..., 10:13]
+        mv = m[..., None] * vel
+        return mv.sum(1), (np.cross(pos, mv) + ang).sum(1), rows
+
+    def normal_speed(rows):  # contact normal = +y here (ball above the bar's axis in y), approach speed of the contact points
+        contact = np.stack([rows[:, 1, 0], 0.5 * (0.05 + (0.12 - 0.08)) + 0 * rows[:, 1, 0], rows[:, 1, 2]], axis=1)
+        va = rows[:, 0, 7:10] + np.cross(rows[:, 0, 10:13], contact - rows[:, 0, 0:3])
+        vb = rows[:, 1, 7:10] + np.cross(rows[:, 1, 10:13], contact - rows[:, 1, 0:3])
+        return (vb - va)[:, 1]
+
+    for f64, tol in ((True, 1e-6), (False, 2e-5)):
+        ora = OracleBraxEnv(sysd, ctx, autoreset=False, f64=f64, max_steps=0)
+        ora.init_from_q(q, qd)
+        # the spinning, translating bar: make the geometry exact at the instant of contact (bar along x at y = 0)
+        p0, l0, r0 = momenta(ora.state)
+        v0 = normal_speed(r0)
+        assert (v0 < 0).all()
+        ora.step(a)
+        p1, l1, r1 = momenta(ora.state)
+        np.testing.assert_allclose(p1, p0, atol=tol)
+        np.testing.assert_allclose(l1, l0, atol=tol * 10)
+        # the velocities changed (a collision happened) ...
+        assert (np.abs(r1[:, 1, 8] - r0[:, 1, 8]) > 1e-3).all()
+        # ... and the normal separation speed is -e v0 + erp * penetration / dt
+        rows_after = r1.copy()
+        rows_after[..., 0:7] = r0[..., 0:7]  # evaluate at the contact geometry of the impulse
+        v1 = normal_speed(rows_after)
+        np.testing.assert_allclose(v1, -el_ * v0 + 0.1 * 0.01 / 0.001, rtol=2e-4 if f64 else 2e-3, atol=1e-4)
+    st, ob = hc.init(sysd, q, qd, ctx)
+    p0, l0, r0 = momenta(st)
+    hc.step(sysd, st, ctx, a, np.zeros(n, np.int32), 0, 0, st.copy(), ob.copy())
+    p1, l1, r1 = momenta(st)
+    np.testing.assert_allclose(p1, p0, atol=2e-5)
+    np.testing.assert_allclose(l1, l0, atol=2e-4)
+    np.testing.assert_allclose(st, ora.state, rtol=1e-5, atol=1e-5)
 
 
 def _crooked_hopper():

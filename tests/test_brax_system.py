@@ -10,7 +10,7 @@ import pytest
 from carl_b200.envs import brax_system as bs
 from carl_b200.envs.brax import (CARLBraxAnt, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxHumanoid,
                                  CARLBraxHumanoidStandup, CARLBraxInvertedDoublePendulum, CARLBraxInvertedPendulum,
-                                 CARLBraxReacher, CARLBraxWalker2d)
+                                 CARLBraxPusher, CARLBraxReacher, CARLBraxWalker2d)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -55,7 +55,7 @@ def test_every_mass_feature_names_a_link():
     for cls, key in ((CARLBraxAnt, "ant"), (CARLBraxHalfcheetah, "halfcheetah"), (CARLBraxHopper, "hopper"),
                      (CARLBraxWalker2d, "walker2d"), (CARLBraxInvertedPendulum, "inverted_pendulum"),
                      (CARLBraxInvertedDoublePendulum, "inverted_double_pendulum"), (CARLBraxReacher, "reacher"),
-                     (CARLBraxHumanoid, "humanoid"), (CARLBraxHumanoidStandup, "humanoidstandup")):
+                     (CARLBraxHumanoid, "humanoid"), (CARLBraxHumanoidStandup, "humanoidstandup"), (CARLBraxPusher, "pusher")):
         links = bs.SYSTEMS[key]["link_names"]
         for f in cls.get_context_features():
             if f.startswith("mass_"):
@@ -111,7 +111,8 @@ def _enum_values(text, enum_name):
 
 def test_table_layout_identical_in_python_and_cuda_header():
     text = open(os.path.join(ROOT, "carl_b200", "csrc", "physics_brax.h")).read()
-    for name in ("MAX_LINKS", "MAX_POINTS", "MAX_Q", "HEADER", "LINK_STRIDE", "POINT_STRIDE", "DOF_STRIDE"):
+    for name in ("MAX_LINKS", "MAX_POINTS", "MAX_Q", "HEADER", "LINK_STRIDE", "POINT_STRIDE", "DOF_STRIDE", "MAX_PAIRS",
+                 "PAIR_STRIDE", "PAIR_HEADER"):
         assert int(re.search(rf"constexpr int {name} = (\d+);", text).group(1)) == getattr(bs, name)
     hdr = _enum_values(text, "Hdr")
     for k, v in hdr.items():
@@ -119,10 +120,11 @@ def test_table_layout_identical_in_python_and_cuda_header():
     ls = _enum_values(text, "LinkSlot")
     for k, v in ls.items():
         assert getattr(bs, k) == v, k
-    for enum in ("DofSlot", "LinkType", "EnvId"):
+    for enum in ("DofSlot", "LinkType", "EnvId", "PairHdr", "PairSlot"):
         for k, v in _enum_values(text, enum).items():
             assert getattr(bs, k) == v, k
-    assert bs.OFF_DOF == bs.OFF_INIT_Q + bs.MAX_Q and bs.TABLE_FLOATS == bs.OFF_DOF + bs.DOF_STRIDE * bs.MAX_LINKS
+    assert bs.OFF_DOF == bs.OFF_INIT_Q + bs.MAX_Q and bs.OFF_PAIR == bs.OFF_DOF + bs.DOF_STRIDE * bs.MAX_LINKS
+    assert bs.TABLE_FLOATS == bs.OFF_PAIR + bs.PAIR_HEADER + bs.PAIR_STRIDE * bs.MAX_PAIRS
     assert bs.TABLE_FLOATS * 4 % 16 == 0  # TMA bulk copies move multiples of 16 bytes
 
 
@@ -207,3 +209,37 @@ def test_humanoid_tables():
     np.testing.assert_allclose(head_up, (0, 0, 0.19), atol=1e-7)
     np.testing.assert_allclose(head_ly, (-0.19, 0, 0), atol=1e-7)
     assert lying[bs.OFF_INIT_Q + 2] == pytest.approx(0.105)
+
+
+def test_pusher_table():
+    """carl/envs/brax/carl_pusher.py:36-84: all eight mass defaults (seven arm links + the pushed object) pin the
+    restated pusher.xml geometry to 7 digits -- the object's 1.8325957e-3 kg is a ball of radius 0.05 at density 3.5;
+    shapes of brax.envs.pusher (obs 23 = q[:7], qd[:7], three centres of mass; 7 actuators with ctrl range +-2); the
+    gripper's three capsules are paired with the ball, and every pair owns one candidate row on either link."""
+    s = bs.SYSTEMS["pusher"]
+    d = CARLBraxPusher.get_context_space().get_default_context()
+    for name, m in zip(s["link_names"][:8], s["stock_masses"][:8]):
+        assert m == pytest.approx(d[f"mass_{name}"], rel=2e-7), name
+    assert (s["n_links"], s["n_q"], s["n_qd"], s["obs_dim"], s["n_act"]) == (9, 11, 11, 23, 7)
+    assert s["act_scale"] == 2.0 and s["dt"] == pytest.approx(0.05)
+    t = s["table"]
+    assert int(t[bs.OFF_PAIR + bs.X_N_PAIRS]) == 3 and t[bs.OFF_PAIR + bs.X_PLANE_Z] == pytest.approx(0.325)
+    assert [s["link_names"][int(t[bs.OFF_PAIR + bs.X_OBS_LINK0 + k])] for k in range(3)] == ["r_wrist_flex_link", "object", "goal"]
+    rows = set()
+    for k in range(3):
+        o = bs.OFF_PAIR + bs.PAIR_HEADER + bs.PAIR_STRIDE * k
+        la, lb = int(t[o + bs.R_LINK_A]), int(t[o + bs.R_LINK_B])
+        assert (s["link_names"][la], s["link_names"][lb]) == ("r_wrist_roll_link", "object")
+        for link, row in ((la, int(t[o + bs.R_ROW_A])), (lb, int(t[o + bs.R_ROW_B]))):
+            lo = int(t[bs.OFF_LINKS + bs.LINK_STRIDE * link + bs.L_FIRST_PT])
+            assert lo <= row < lo + int(t[bs.OFF_LINKS + bs.LINK_STRIDE * link + bs.L_N_PT])
+            assert t[bs.OFF_POINTS + bs.POINT_STRIDE * row + 4] == -1.0  # an impulse-only row: no ground candidate
+            rows.add(row)
+        assert t[o + bs.R_RADIUS_A] == pytest.approx(0.02) and t[o + bs.R_RADIUS_B] == pytest.approx(0.05)
+    assert len(rows) == 6
+    # slides of the object and the goal: first coordinate along y, second along x (MJCF order obj_slidey, obj_slidex)
+    for name in ("object", "goal"):
+        o = bs.OFF_LINKS + bs.LINK_STRIDE * s["link_names"].index(name)
+        m = bs.quat_to_mat(t[o + bs.L_JROT:o + bs.L_JROT + 4].astype(np.float64))
+        np.testing.assert_allclose(m[:, 0], (0, 1, 0), atol=1e-6)
+        np.testing.assert_allclose(m[:, 1], (1, 0, 0), atol=1e-6)

@@ -203,7 +203,8 @@ def test_brax_param_rows_and_shapes_match_native_query(native_lib):
     from carl_b200.envs import brax_system as bs
 
     for name in ("CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d", "CARLBraxInvertedPendulum",
-                 "CARLBraxInvertedDoublePendulum", "CARLBraxReacher", "CARLBraxHumanoid", "CARLBraxHumanoidStandup"):
+                 "CARLBraxInvertedDoublePendulum", "CARLBraxReacher", "CARLBraxHumanoid", "CARLBraxHumanoidStandup",
+                 "CARLBraxPusher"):
         cls = getattr(E, name)
         info = _native.query_env(_native.KIND[cls.kind])
         sysd = bs.SYSTEMS[cls.env_name]
@@ -218,7 +219,7 @@ def test_brax_param_rows_and_shapes_match_native_query(native_lib):
         for j, ln in enumerate(sysd["link_names"]):
             want = d.get(f"mass_{ln}", sysd["stock_masses"][j])
             assert applied[0, 5 + j] == pytest.approx(want)
-    assert E.brax.UNSUPPORTED_BODIES == ("CARLBraxPusher",)
-    for name in E.brax.UNSUPPORTED_BODIES:  # asking for them fails loudly, nothing is substituted
-        with pytest.raises(NotImplementedError, match="not built"):
-            getattr(E, name)
+    assert E.brax.UNSUPPORTED_BODIES == ()  # every body of carl/envs/brax/__init__.py is built
+    # the pusher's goal features stay in the context but never reach the family's check_context / the physics
+    d = E.CARLBraxPusher.get_context_space().get_default_context()
+    assert [d[k] for k in E.CARLBraxPusher.GOAL_FEATURES] == [0.45, 0.05, 0.05]
