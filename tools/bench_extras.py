@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 from carl_b200.context import ContextSampler, UniformFloatContextFeature
-from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxHumanoid, CARLBraxHumanoidStandup,
+from carl_b200.envs import (CARLAcrobot, CARLBraxHalfcheetah, CARLBraxHopper, CARLBraxHumanoid, CARLBraxHumanoidStandup, CARLBraxPusher,
                             CARLBraxInvertedDoublePendulum, CARLBraxInvertedPendulum, CARLBraxReacher, CARLBraxWalker2d,
                             CARLPendulum, ContextTable, MixedBatch)
 
@@ -50,7 +50,8 @@ def brax_bodies(out, bodies):
 
 
 HUMANOIDS = ((CARLBraxHumanoid, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "humanoid"),
-             (CARLBraxHumanoidStandup, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "humanoidstandup"))
+             (CARLBraxHumanoidStandup, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)}, "humanoidstandup"),
+             (CARLBraxPusher, {"gravity": (-1e-3, -1e-6), "mass_object": (1e-3, 3e-3), "friction": (0.5, 1.5)}, "pusher"))
 
 
 def main():
