@@ -1,11 +1,11 @@
-// Brax-locomotion kernels (sm_100a): ONE WARP PER 1 OR 3 ENV INSTANCES.
+// Brax-locomotion kernels (sm_100a): ONE WARP PER 1, 2, 3 OR 4 ENV INSTANCES.
 //
-// Each env owns LPE = 32/E consecutive lanes of a warp (E = 3 for bodies of at most 10 links: Ant,
-// Halfcheetah, Hopper). Sub-lanes 0..L-1 own the links of the body (13-float centre-of-mass state in
+// Each env owns LPE = 32/E consecutive lanes of a warp (E = 4: Halfcheetah, Hopper, Walker2d, pendulums, reacher;
+// E = 3: Ant, pusher; E = 2: humanoids). Sub-lanes 0..L-1 own the links of the body (13-float centre-of-mass state in
 // registers) and, in ceil(P/LPE) passes, the ground-contact candidate points of the collision phase;
 // the exchange between the lanes of an env (parent/child states, joint reactions, contact
 // impulses, loop invariants) goes through a 2.7 KB shared-memory scratch guarded by __syncwarp.
-// The system table (3.1 KB: link frames, inertias, joint limits, contact points, tunables) is
+// The system table (4.1 KB: link frames, inertias, joint limits, contact points, dof rows, contact pairs, tunables) is
 // staged once per CTA into shared memory with a TMA bulk copy (cp.async.bulk + mbarrier); each
 // env's context scalars (gravity, friction, elasticity, ang_damping, stiffness scale, link masses)
 // are staged with one coalesced load and then read as shared-memory broadcasts.

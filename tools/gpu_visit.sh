@@ -6,6 +6,7 @@
 #   tools/gpu_visit.sh sanitizer        compute-sanitizer memcheck / racecheck / synccheck over the fused-gather and host-step paths
 #   tools/gpu_visit.sh mgpu             multi-GPU correctness worker on NG ranks (gpurun --gpus NG)
 #   tools/gpu_visit.sh scale            bench.py at N in NLIST (default "1 2 4 8", capped at NG)
+#   tools/gpu_visit.sh extras           secondary configs and every Brax body on one GPU (tools/bench_extras.py)
 # Several stages may be given; outputs go to gpurun_out/ (copy what should be kept into profiles/).
 set +e
 mkdir -p gpurun_out; cd "$(dirname "$0")/.."
@@ -39,6 +40,8 @@ ncu)
     python bench.py --steps $K --warmup $W --fused-only > gpurun_out/ncu_rollout.log 2>&1; echo "ncu rollout exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:brax_step_kernel -s 4 -c 2 -f -o gpurun_out/prof_brax \
     python tools/ncu_targets.py brax > gpurun_out/ncu_brax.log 2>&1; echo "ncu brax exit $?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:brax_step_kernel -s 4 -c 2 -f -o gpurun_out/prof_brax_fma \
+    python tools/ncu_targets.py brax_fma > gpurun_out/ncu_brax_fma.log 2>&1; echo "ncu brax_fma exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 10 -c 2 -f -o gpurun_out/prof_step \
     python tools/ncu_targets.py step > gpurun_out/ncu_step.log 2>&1; echo "ncu step exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_checked_kernel -s 10 -c 2 -f -o gpurun_out/prof_step_checked \
@@ -63,6 +66,9 @@ mgpu)
   ;;
 scale)
   NLIST="${NLIST:-1 2 4 8}" NG=$NG bash tools/gpu_scale.sh
+  ;;
+extras)
+  timeout 400 python tools/bench_extras.py > gpurun_out/extras.json 2> gpurun_out/extras.err; echo "extras exit $?"; tail -2 gpurun_out/extras.err
   ;;
 *) echo "unknown stage $stage";;
 esac

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Short workloads for `ncu -k` captures (tools/gpu_visit.sh ncu): brax | step | step_host."""
+"""Short workloads for `ncu -k` captures (tools/gpu_visit.sh ncu): brax | brax_fma | step | step_host."""
 import ctypes
 import os
 import sys
@@ -15,12 +15,12 @@ from carl_b200 import _native, hostmem
 def main():
     what = sys.argv[1]
     dev = torch.device("cuda", 0)
-    if what == "brax":
+    if what in ("brax", "brax_fma"):
         from carl_b200.envs import CARLBraxAnt
 
         n, T = 8192, 20
         ctxs = bench._brax_contexts(CARLBraxAnt, n, {"gravity": (-15, -5), "mass_torso": (5, 20), "friction": (0.5, 1.5)})
-        env = CARLBraxAnt(contexts=ctxs, device=dev, context_mode="applied")
+        env = CARLBraxAnt(contexts=ctxs, device=dev, context_mode="applied", arithmetic="fma" if what == "brax_fma" else "strict")
         env.reset(seed=0)
         tr = dict(obs=torch.empty(T, n, 27, device=dev), actions=torch.empty(T, n, 8, device=dev), reward=torch.empty(T, n, device=dev),
                   done=torch.empty(T, n, dtype=torch.uint8, device=dev))
