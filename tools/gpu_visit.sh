@@ -47,6 +47,9 @@ ncu)
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_checked_kernel -s 10 -c 2 -f -o gpurun_out/prof_step_checked \
     python tools/ncu_targets.py step_host > gpurun_out/ncu_step_checked.log 2>&1; echo "ncu step_checked exit $?"
   ls -la gpurun_out/*.ncu-rep
+  # gpurun copies back at most 64 MiB: summarise every report here, keep only the two that are read at source level
+  CARLB_PROF_DIR=gpurun_out/summary python tools/summarize_ncu.py ${TAG:-visit}; echo "summaries exit $?"
+  rm -f gpurun_out/prof_step.ncu-rep gpurun_out/prof_step_checked.ncu-rep gpurun_out/prof_brax.ncu-rep
   ;;
 sanitizer)
   for tool in memcheck racecheck synccheck; do

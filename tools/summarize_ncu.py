@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
-PROF = os.path.join(ROOT, "profiles")
+PROF = os.environ.get("CARLB_PROF_DIR") or os.path.join(ROOT, "profiles")  # (on the GPU box: a directory under gpurun_out/)
 
 WANT = [
     "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
