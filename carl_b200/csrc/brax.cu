@@ -215,7 +215,7 @@ struct LaneCtx {
 template <int E, int M>
 __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& c, typename ScratchOf<M>::type& w, LinkState& s,
                                                const float* reach, float tau, float tau1 = 0.0f, float tau2 = 0.0f) {
-  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
+  constexpr bool SP = M == MODE_SPECIAL || M == MODE_PUSHER, HU = M == MODE_HUMANOID, PU = M == MODE_PUSHER;
   constexpr int LPE = Lanes<E>::LPE;
   const float dt = sys[H_DT];
   const int n_pass = (c.P + LPE - 1) / LPE;
@@ -290,7 +290,7 @@ __device__ __forceinline__ void pipeline_steps(const float* sys, const LaneCtx& 
         }
       }
     }
-    if constexpr (SP) {
+    if constexpr (PU) {
       // body-vs-body pairs (pusher): sub-lane k resolves pair k and writes the two candidate rows reserved for it
       const int n_pairs = (int)sys[OFF_PAIR + X_N_PAIRS];
       if (n_pairs > 0) {  // block-uniform
@@ -353,7 +353,7 @@ template <int E, int M>
 __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx& c, typename ScratchOf<M>::type& w,
                                                  const LinkState& s) {
   constexpr int LPE = Lanes<E>::LPE;
-  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
+  constexpr bool SP = M == MODE_SPECIAL || M == MODE_PUSHER, HU = M == MODE_HUMANOID, PU = M == MODE_PUSHER;
   if (c.is_link) write_link(w.ls, c.sl, s);
   __syncwarp();
   const int nq = (int)sys[H_N_Q], nqd = (int)sys[H_N_QD];
@@ -382,7 +382,7 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
   const int kind = (int)sys[H_ENV];
   RootFacts r;
   r.site = v3(0, 0, 0);
-  if (SP && kind == ENV_PUSHER) {
+  if (PU) {
     r.site = pusher_distances(sys, w.ls);
   } else if (SP && kind >= ENV_INVERTED_PENDULUM) {  // block-uniform: the locomotion bodies never enter
     r.site = site_position(sys, read_link(w.ls, (int)sys[H_SITE_LINK]), read_link(w.ls, kind == ENV_REACHER ? 2 : 0));
@@ -412,7 +412,7 @@ __device__ __forceinline__ RootFacts compute_obs(const float* sys, const LaneCtx
         if (c.type == TYPE_HINGE3) qf[qdi + 2] = a2 >= 0 ? c.dt[D_GEAR2] * fminf(fmaxf(w.act[a2], lo), hi) : 0.0f;
       }
     }
-  } else if (SP && kind == ENV_PUSHER) {
+  } else if (PU) {
     if (c.sl < LPE)
       for (int i = c.sl; i < 23; i += LPE) w.obs[i] = pusher_obs_entry(sys, i, w.q, w.qd, w.ls);
   } else if (SP && (kind == ENV_INVERTED_DOUBLE_PENDULUM || kind == ENV_REACHER)) {
@@ -461,7 +461,7 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   const float x_velocity = (after.x - before.x) / dt_env;
   const float forward_reward = sys[H_FORWARD_WEIGHT] * x_velocity;
   const int kind = (int)sys[H_ENV];
-  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID;
+  constexpr bool SP = M == MODE_SPECIAL, HU = M == MODE_HUMANOID, PU = M == MODE_PUSHER;
   bool healthy = true;
   if (kind == ENV_ANT || (HU && kind == ENV_HUMANOID)) {
     healthy = !(after.z < sys[H_HEALTHY_Z_MIN]) && !(after.z > sys[H_HEALTHY_Z_MAX]);
@@ -476,7 +476,7 @@ __device__ __forceinline__ void env_outcome(const float* sys, const RootFacts& b
   const float ctrl_cost = sys[H_CTRL_COST] * act_sq_sum;
   reward = forward_reward + sys[H_HEALTHY_REWARD] - ctrl_cost;
   done = (sys[H_TERMINATE] > 0.0f) && !healthy;
-  if (SP && kind == ENV_PUSHER) pusher_outcome(sys, before.site, act_sq_sum, reward, done);
+  if (PU) pusher_outcome(sys, before.site, act_sq_sum, reward, done);
   else if (SP && kind >= ENV_INVERTED_PENDULUM) special_outcome(kind, after.q1, after.qd1, after.qd2, after.site, act_sq_sum, reward, done);
   if (HU && kind == ENV_HUMANOIDSTANDUP) {  // brax.envs.humanoidstandup.step: uph_cost + 1 - quad_ctrl_cost, never done
     reward = (after.z - 0.0f) / dt_env + sys[H_HEALTHY_REWARD] - ctrl_cost;
@@ -1024,8 +1024,8 @@ static cudaError_t launch_brax_step(const carlb_env* env, const BraxSeg& seg, co
     return launch_brax_step_we<4, 2, MODE_HUMANOID>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
   }
   if (env_kind == ENV_PUSHER) {  // 9 links, slide joints, body-vs-body pairs: three envs per warp
-    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, MODE_SPECIAL>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
-    return launch_brax_step_we<4, 3, MODE_SPECIAL>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    if (brax_pack(h->host_table, n) == 1) return launch_brax_step_we<4, 1, MODE_PUSHER>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
+    return launch_brax_step_we<4, 3, MODE_PUSHER>(seg, n, actions, n_steps, policy_seed, step_base, tj, sc, st);
   }
   if (env_kind >= ENV_INVERTED_PENDULUM) {
     // inverted pendulums / reacher (2-3 links): the instantiation with slide joints and their env layers
@@ -1100,6 +1100,8 @@ int brax_reset_from(const carlb_env* env, const uint8_t* mask, const float* q, c
   const int env_kind = (int)static_cast<const BraxHandle*>(env->brax_sys)->host_table[H_ENV];
   if (env_kind == ENV_HUMANOID || env_kind == ENV_HUMANOIDSTANDUP)
     brax_reset_kernel<MODE_HUMANOID><<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1, MODE_HUMANOID>), st>>>(seg, mask, q, qd);
+  else if (env_kind == ENV_PUSHER)
+    brax_reset_kernel<MODE_PUSHER><<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1, MODE_PUSHER>), st>>>(seg, mask, q, qd);
   else
     brax_reset_kernel<MODE_SPECIAL><<<brax_grid(env->n, 4), 128, sizeof(SmemLayoutT<4, 1, MODE_SPECIAL>), st>>>(seg, mask, q, qd);
   g_launches++;

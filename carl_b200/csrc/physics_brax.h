@@ -86,7 +86,7 @@ CARLB_HD bool is_special_env(int kind) { return (kind >= ENV_INVERTED_PENDULUM &
 // then the sign of each dof's coordinate against the right-handed joint frame (-1 where the MJCF axis is -z)
 enum DofSlot { D_ACT1 = 0, D_ACT2, D_GEAR1, D_GEAR2, D_LO1, D_HI1, D_LO2, D_HI2, D_SIGN0, D_SIGN1, D_SIGN2 };
 // Kernel flavours (template parameter of the step / reset kernels): which joint types and env layers are compiled in
-enum BodyMode { MODE_LOCO = 0, MODE_SPECIAL = 1, MODE_HUMANOID = 2 };
+enum BodyMode { MODE_LOCO = 0, MODE_SPECIAL = 1, MODE_HUMANOID = 2, MODE_PUSHER = 3 };  // PUSHER: SPECIAL + contact pairs
 // joint coordinates per link type (free roots are handled separately: 7 / 6)
 CARLB_HD int type_ndof(int type) {
   return (type == TYPE_PLANAR || type == TYPE_HINGE3) ? 3 : ((type == TYPE_SLIDE2 || type == TYPE_HINGE2) ? 2 : 1);
