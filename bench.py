@@ -997,6 +997,18 @@ def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
         acc += float(r_h[0])
     torch.cuda.synchronize(dev)
     e2e_ms = max_over_ranks(time.perf_counter() - t0, dev, distributed) / n_e2e * 1e3
+    # the same host-buffer loop with the FMA build (arithmetic="fma"): the shorter kernel shortens the serial part
+    _native.check(env._lib.carlb_brax_set_arithmetic(env._handle, 1))
+    for j in range(5):
+        env.step(host_acts[j % 4])
+    barrier()
+    t0 = time.perf_counter()
+    for j in range(n_e2e):
+        o_h, r_h, te_h, tr_h, _ = env.step(host_acts[j % 4])
+        acc += float(r_h[0])
+    torch.cuda.synchronize(dev)
+    e2e_fma_ms = max_over_ranks(time.perf_counter() - t0, dev, distributed) / n_e2e * 1e3
+    _native.check(env._lib.carlb_brax_set_arithmetic(env._handle, 0))
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         try:  # reported next to the GPU number; never allowed to break the bench line
@@ -1026,6 +1038,7 @@ def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
                      "gather": "fused, sync (push + wait inside every step launch)" if distributed else None,
                      "hbm_frac_1114B": step_bytes * n / (api_ms * 1e-3) / 1e9 / peak},
         "e2e": {"value": n_global / (e2e_ms * 1e-3), "unit": UNIT, "us_per_step": e2e_ms * 1e3,
+                "value_fma": n_global / (e2e_fma_ms * 1e-3), "us_per_step_fma": e2e_fma_ms * 1e3,
                 "h2d_bytes_per_step": n * info.act_dim * 4, "d2h_bytes_per_step": n * (info.obs_dim * 4 + 4 + 1 + 1),
                 "api": "CARLBraxAnt.step(numpy float32 actions in page-locked memory) -> numpy obs/reward/terminated/truncated "
                        "(the step kernel reads the actions and writes the results over PCIe itself)"},

@@ -4,7 +4,8 @@ from __future__ import annotations
 
 ENV_NAMES = ["CARLCartPole", "CARLPendulum", "CARLAcrobot", "CARLMountainCar", "CARLMountainCarContinuous",
              "CARLBraxAnt", "CARLBraxHalfcheetah", "CARLBraxHopper", "CARLBraxWalker2d",
-             "CARLBraxInvertedPendulum", "CARLBraxInvertedDoublePendulum", "CARLBraxReacher"]
+             "CARLBraxHumanoid", "CARLBraxHumanoidStandup", "CARLBraxInvertedPendulum", "CARLBraxInvertedDoublePendulum",
+             "CARLBraxReacher", "CARLBraxPusher"]
 
 
 def register_envs(namespace: str = "carl_b200") -> list[str]:

@@ -107,7 +107,7 @@ def test_goal_wrapper_on_device_rewards_nonnegative():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("cls_name,body", [("CARLBraxAnt", "ant"), ("CARLBraxHopper", "hopper")])
+@pytest.mark.parametrize("cls_name,body", [("CARLBraxAnt", "ant"), ("CARLBraxHopper", "hopper"), ("CARLBraxHumanoid", "humanoid")])
 def test_goal_kernel_epilogue_matches_reference_wrapper(cls_name, body):
     """carlb_brax_goal_step (one launch after the step, float64) against the reference wrapper's own per-env
     statements driven by the SAME observations: reward to 1e-12, terminated / success identical; the goal
@@ -131,7 +131,7 @@ def test_goal_kernel_epilogue_matches_reference_wrapper(cls_name, body):
     goal = [np.array(bg.DIRECTION_VALUES[int(dirs[i])]) * ctxs[i]["target_distance"] for i in range(n)]
     n_reached = 0
     for t in range(T):
-        a = torch.from_numpy(rng.uniform(-1, 1, (n, env._info.act_dim)).astype(np.float32)).cuda()
+        a = torch.from_numpy((rng.uniform(-1, 1, (n, env._info.act_dim)) * env._sysd["act_scale"]).astype(np.float32)).cuda()
         obs, r, te, tr, info = env.step(a)
         o = obs["obs"].cpu().numpy()
         brax_done = env._elapsed.cpu().numpy() == 0  # auto-reset this step (time limit / unhealthy)

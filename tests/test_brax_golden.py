@@ -9,7 +9,8 @@ import pytest
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "brax")
 BODIES = {"ant": "CARLBraxAnt", "halfcheetah": "CARLBraxHalfcheetah", "hopper": "CARLBraxHopper",
           "walker2d": "CARLBraxWalker2d", "inverted_pendulum": "CARLBraxInvertedPendulum",
-          "inverted_double_pendulum": "CARLBraxInvertedDoublePendulum", "reacher": "CARLBraxReacher"}
+          "inverted_double_pendulum": "CARLBraxInvertedDoublePendulum", "reacher": "CARLBraxReacher",
+          "humanoid": "CARLBraxHumanoid", "humanoidstandup": "CARLBraxHumanoidStandup", "pusher": "CARLBraxPusher"}
 
 
 def _load(body):

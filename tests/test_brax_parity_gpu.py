@@ -549,3 +549,28 @@ def test_pusher_contact_pairs_match(monkeypatch):
         assert not te.any()
         struck |= np.abs(ora.state[:, 13 * 7 + 7:13 * 7 + 9]).max(axis=1) > 1e-3
     assert struck.mean() > 0.1
+
+
+@pytest.mark.parametrize("reset_rng", ["jax", "philox"])
+def test_pusher_reset_places_the_object_like_brax(reset_rng):
+    """brax.envs.pusher.reset through both reset streams: arm at the initial pose with rates in +-0.005, the object at
+    (U(-0.3, 0), U(-0.2, 0.2)) on its slides but never closer than 0.17 to the goal, goal offsets and the last four
+    rates zero; the observation reports the three centres of mass in the MJCF's world (table at z = -0.325)."""
+    import carl_b200.envs as E
+
+    n = 4096
+    env = E.CARLBraxPusher(num_envs=n, reset_rng=reset_rng)
+    obs, _ = env.reset(seed=3)
+    o = obs["obs"].cpu().numpy()
+    assert o.shape == (n, 23)
+    np.testing.assert_allclose(o[:, :7], 0.0, atol=1e-6)
+    assert np.abs(o[:, 7:14]).max() <= 0.005 + 1e-7 and o[:, 7:14].std() > 0.002
+    obj, goal = o[:, 17:20], o[:, 20:23]
+    np.testing.assert_allclose(goal, np.tile([0.45, -0.05, -0.323], (n, 1)), atol=1e-6)
+    np.testing.assert_allclose(obj[:, 2], -0.275, atol=1e-6)
+    dy, dx = obj[:, 1] + 0.05, obj[:, 0] - 0.45     # first slide coordinate along y, second along x
+    assert dy.min() >= -0.3 - 1e-6 and dy.max() <= 1e-6 and np.abs(dx).max() <= 0.2 + 1e-6
+    assert np.hypot(dx, dy).min() >= 0.17 - 1e-6
+    assert dy.std() > 0.05 and dx.std() > 0.08
+    state = env.state.cpu().numpy().reshape(n, -1)[:, :13 * 9].reshape(n, 9, 13)
+    np.testing.assert_allclose(state[:, 7:, 7:], 0.0, atol=1e-7)   # object and goal at rest

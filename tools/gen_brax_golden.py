@@ -26,7 +26,8 @@ def main():
     from brax import envs
 
     os.makedirs(args.out, exist_ok=True)
-    for name in ("ant", "halfcheetah", "hopper", "walker2d", "inverted_pendulum", "inverted_double_pendulum", "reacher"):
+    for name in ("ant", "halfcheetah", "hopper", "walker2d", "inverted_pendulum", "inverted_double_pendulum", "reacher",
+                 "humanoid", "humanoidstandup", "pusher"):
         env = envs.create(env_name=name, backend="spring", auto_reset=False, episode_length=1000)
         sys = env.sys
         state = jax.jit(env.reset)(jax.random.PRNGKey(0))
