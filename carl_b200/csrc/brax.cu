@@ -921,10 +921,45 @@ int brax_set_system(carlb_env* env, const float* table, int n_floats, int stock_
               (int)table[H_N_LINKS], (int)table[H_N_Q], (int)table[H_N_QD], (int)table[H_N_ACT]);
     return CARLB_ERR_INVALID;
   }
+  // the kernels are picked by the table's env id: it has to be the one of the handle's kind
+  const int env_id = (int)table[H_ENV];
+  const int want_env = env->kind - KIND_BRAX_ANT;  // CARLB_BRAX_* and EnvId enumerate the bodies in the same order
+  if (env_id != want_env) {
+    set_error("carlb_brax_set_system: table is for env id %d, the handle's kind %d needs %d", env_id, env->kind, want_env);
+    return CARLB_ERR_INVALID;
+  }
+  const bool humanoid = env_id == ENV_HUMANOID || env_id == ENV_HUMANOIDSTANDUP;
   for (int l = 0; l < L; ++l) {
     const int parent = (int)table[OFF_LINKS + LINK_STRIDE * l + L_PARENT];
+    const int type = (int)table[OFF_LINKS + LINK_STRIDE * l + L_TYPE];
     if (parent >= l) {
       set_error("carlb_brax_set_system: link %d has parent %d (parents must precede children)", l, parent);
+      return CARLB_ERR_INVALID;
+    }
+    // joint types a kernel flavour does not compile in would silently be treated as plain hinges
+    const bool slide = type == TYPE_SLIDE || type == TYPE_SLIDE2, stacked = type == TYPE_HINGE2 || type == TYPE_HINGE3;
+    if (type < TYPE_FREE || type > TYPE_HINGE3 || (slide && !is_special_env(env_id)) || (stacked && !humanoid)) {
+      set_error("carlb_brax_set_system: link %d has joint type %d, which the kernels of env id %d do not build", l, type, env_id);
+      return CARLB_ERR_INVALID;
+    }
+  }
+  const int P = (int)table[H_N_POINTS], n_pairs = (int)table[OFF_PAIR + X_N_PAIRS];
+  for (int p = 0; p < P; ++p) {
+    const int pl = (int)table[OFF_POINTS + POINT_STRIDE * p], slot = (int)table[OFF_POINTS + POINT_STRIDE * p + P_SCHED];
+    if (pl < 0 || pl >= L || slot < 0 || slot >= P) {
+      set_error("carlb_brax_set_system: contact candidate %d names link %d / schedule slot %d", p, pl, slot);
+      return CARLB_ERR_INVALID;
+    }
+  }
+  if (n_pairs < 0 || n_pairs > MAX_PAIRS || (n_pairs > 0 && env_id != ENV_PUSHER)) {
+    set_error("carlb_brax_set_system: %d body-vs-body pairs (at most %d, pusher only)", n_pairs, MAX_PAIRS);
+    return CARLB_ERR_INVALID;
+  }
+  for (int k = 0; k < n_pairs; ++k) {
+    const float* pr = table + OFF_PAIR + PAIR_HEADER + PAIR_STRIDE * k;
+    const int la = (int)pr[R_LINK_A], lb = (int)pr[R_LINK_B], ra = (int)pr[R_ROW_A], rb = (int)pr[R_ROW_B];
+    if (la < 0 || la >= L || lb < 0 || lb >= L || ra < 0 || ra >= P || rb < 0 || rb >= P || ra == rb) {
+      set_error("carlb_brax_set_system: pair %d names links %d / %d and candidate rows %d / %d", k, la, lb, ra, rb);
       return CARLB_ERR_INVALID;
     }
   }

@@ -574,3 +574,45 @@ def test_pusher_reset_places_the_object_like_brax(reset_rng):
     assert dy.std() > 0.05 and dx.std() > 0.08
     state = env.state.cpu().numpy().reshape(n, -1)[:, :13 * 9].reshape(n, 9, 13)
     np.testing.assert_allclose(state[:, 7:, 7:], 0.0, atol=1e-7)   # object and goal at rest
+
+
+def test_system_table_validation_rejects_what_the_kernels_would_misread():
+    """carlb_brax_set_system: the kernels are picked by the table's env id and compile only the joint types of their
+    flavour in -- a table for another body, a joint type the flavour lacks, contact candidates / pairs that point
+    outside the table are refused with CARLB_ERR_INVALID and a message (the handle keeps its previous table)."""
+    import ctypes
+
+    import carl_b200.envs as E
+    from carl_b200 import _native
+
+    def upload(env, table):
+        t = np.ascontiguousarray(table, dtype=np.float32)
+        return env._lib.carlb_brax_set_system(env._handle, t.ctypes.data_as(ctypes.c_void_p), int(t.size), 0)
+
+    ant = E.CARLBraxAnt(num_envs=4)
+    good = bs.SYSTEMS["ant"]["table"]
+    assert upload(ant, good) == _native.CARLB_OK
+    assert upload(ant, bs.SYSTEMS["humanoid"]["table"]) == _native.ERR_INVALID      # another body
+    wrong_env = good.copy()
+    wrong_env[bs.H_ENV] = bs.ENV_HOPPER
+    assert upload(ant, wrong_env) == _native.ERR_INVALID and b"env id" in ant._lib.carlb_last_error()
+    stacked = good.copy()
+    stacked[bs.OFF_LINKS + bs.LINK_STRIDE * 2 + bs.L_TYPE] = bs.TYPE_HINGE2         # the Ant kernels build no stacked hinges
+    assert upload(ant, stacked) == _native.ERR_INVALID and b"joint type" in ant._lib.carlb_last_error()
+    slide = good.copy()
+    slide[bs.OFF_LINKS + bs.LINK_STRIDE * 2 + bs.L_TYPE] = bs.TYPE_SLIDE
+    assert upload(ant, slide) == _native.ERR_INVALID
+    cand = good.copy()
+    cand[bs.OFF_POINTS] = 11                                                          # candidate on a link the body lacks
+    assert upload(ant, cand) == _native.ERR_INVALID
+    pairs = good.copy()
+    pairs[bs.OFF_PAIR + bs.X_N_PAIRS] = 1                                              # pairs are the pusher's
+    assert upload(ant, pairs) == _native.ERR_INVALID
+    # still stepping with the table it accepted
+    ant.reset(seed=0)
+    obs, *_ = ant.step(torch.zeros(4, 8, device="cuda"))
+    assert torch.isfinite(obs["obs"]).all()
+    pusher = E.CARLBraxPusher(num_envs=4)
+    bad = bs.SYSTEMS["pusher"]["table"].copy()
+    bad[bs.OFF_PAIR + bs.PAIR_HEADER + bs.R_ROW_B] = 40
+    assert upload(pusher, bad) == _native.ERR_INVALID and b"pair" in pusher._lib.carlb_last_error()
