@@ -463,6 +463,73 @@ def test_two_body_collision_conserves_momentum_and_restitutes(hc):
     np.testing.assert_allclose(st, ora.state, rtol=1e-5, atol=1e-5)
 
 
+def _lone_ball(dt, n_frames):
+    """A synthetic one-link body: a free ball of radius 0.1 above the ground plane."""
+    ball = bs._link("ball", -1, bs.TYPE_FREE, (0, 0, 0.5), [bs.sphere((0, 0, 0), 0.1)])
+    return dict(
+        name="lone_ball", env=bs.ENV_HALFCHEETAH, links=[ball], density=1000.0, total_mass=None, friction=1.0,
+        init_q=np.array([0, 0, 0.5, 1, 0, 0, 0], dtype=np.float64), dt=dt, n_frames=n_frames,
+        tunables=dict(constraint_stiffness=1000.0, constraint_vel_damping=10.0, constraint_limit_stiffness=0.0,
+                      constraint_ang_damping=0.0, baumgarte_erp=0.1, vel_damping=0.0, spring_mass_scale=0.0,
+                      spring_inertia_scale=1.0),
+        env_params=dict(reset_noise=0.0, ctrl_cost=0.0, healthy_reward=0.0, z_min=-1e9, z_max=1e9, forward_weight=0.0,
+                        angle_min=0.0, angle_max=0.0, exclude_pos=0, qd_clip=0.0, terminate=0.0),
+        stock_gravity=-9.81, stock_ang_damping=0.0, stock_elasticity=0.0, actuator_links=[],
+    )
+
+
+@pytest.mark.parametrize("dt", [0.005, 0.002])
+def test_ball_in_the_ground_is_pushed_out_at_the_baumgarte_rate(hc, dt):
+    """Independent anchor of the ground-contact impulse (brax.spring.collisions with Baumgarte stabilisation): a ball
+    at rest 5 mm inside the plane, zero restitution. In the first substep the semi-implicit update makes the normal
+    velocity -g dt, the contact impulse replaces it by erp * penetration / dt WHATEVER the mass and the gravity, and the
+    pose moves by that times dt: penetration (1 - erp) * 5 mm, velocity erp * 5 mm / dt. Afterwards the ball only
+    feels the contact while it approaches the plane: replaying that scalar rule (free flight under gravity while moving
+    out, the Baumgarte velocity when moving in) reproduces height and velocity over 40 substeps. Oracle (float64,
+    float32) and kernel source, two step sizes, random per-env gravity and mass."""
+    sysd = bs.build_system(_lone_ball(dt, 1))
+    n = 16
+    rng = np.random.default_rng(5)
+    ctx = random_ctx(sysd, n, rng)
+    ctx[:, 1], ctx[:, 2], ctx[:, 3] = 1.0, 0.0, 0.0   # friction 1, no restitution, no angular damping
+    g = -ctx[:, 0].astype(np.float64)
+    q = np.tile(np.asarray(sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + 7], np.float32), (n, 1))
+    q[:, 2] = 0.095
+    qd = np.zeros((n, 6), np.float32)
+    a = np.zeros((n, 0), np.float32)
+    pen0 = 0.1 - np.float64(np.float32(0.095))
+    erp, dtf = 0.1, np.float64(np.float32(dt))
+
+    def replay(steps):  # the scalar rule of the docstring
+        pen, v, out = np.full(n, pen0), np.zeros(n), []
+        for _ in range(steps):
+            v = v - g * dtf
+            hit = (pen > 0) & (v < 0)
+            v = np.where(hit, erp * pen / dtf, v)
+            pen = pen - v * dtf
+            out.append((pen.copy(), v.copy()))
+        return out
+
+    ref = replay(40)
+    for f64, tol in ((True, 1e-7), (False, 2e-6)):
+        ora = OracleBraxEnv(sysd, ctx, autoreset=False, f64=f64, max_steps=0)
+        ora.init_from_q(q, qd)
+        for k in range(40):
+            ora.step(a)
+            row = np.array(ora.state, dtype=np.float64)
+            if k == 0:  # the closed form of the first substep
+                np.testing.assert_allclose(0.1 - row[:, 2], (1 - erp) * pen0, rtol=1e-5)
+                np.testing.assert_allclose(row[:, 9], erp * pen0 / dtf, rtol=1e-5)
+            np.testing.assert_allclose(0.1 - row[:, 2], ref[k][0], atol=tol * (k + 1))
+            np.testing.assert_allclose(row[:, 9], ref[k][1], atol=tol * (k + 1) / dt)
+        assert (np.abs(0.1 - row[:, 2]) < pen0).all()   # closer to the surface than it started
+    st, ob = hc.init(sysd, q, qd, ctx)
+    el = np.zeros(n, np.int32)
+    for k in range(40):
+        hc.step(sysd, st, ctx, a, el, 0, 0, st.copy(), ob.copy())
+        np.testing.assert_allclose(0.1 - st[:, 2].astype(np.float64), ref[k][0], atol=2e-6 * (k + 1))
+
+
 def _crooked_hopper():
     """A table no shipped body has: rotated link transforms (L_TROT != identity) and joints away from the link
     origin (L_JPOS != 0) -- the general branches of joint_resolve / forward_link that the table-derived
