@@ -103,6 +103,15 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    only = os.environ.get("CARLB_MGPU_ONLY", "")  # "brax": just the Brax part (a quick check of the Brax kernels' pushes)
+    if only != "brax":
+        classic_part(rank, world, dev)
+    brax_part(rank, world, dev)
+    dist.destroy_process_group()
+    print(f"MGPU_OK rank {rank}")
+
+
+def classic_part(rank, world, dev):
     n = 4096 + 3  # ragged over the ranks
     classic_variant(rank, world, dev, n, "nccl", "nccl", False, "ipc")
     for symmetric in ("ipc", "auto"):
@@ -133,6 +142,9 @@ def main():
         dist.barrier()
         gp.close()
     say(rank, "pendulum ok")
+
+
+def brax_part(rank, world, dev):
     # Brax Ant, fused gather (immediate pushes; pipelined = one push behind)
     nb = 512
     for pipelined in (False, True):
@@ -157,8 +169,6 @@ def main():
         dist.barrier()
         gb.close()
     say(rank, "brax ok")
-    dist.destroy_process_group()
-    print(f"MGPU_OK rank {rank}")
 
 
 if __name__ == "__main__":
