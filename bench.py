@@ -89,6 +89,24 @@ def measured_profile(rep: str, fused_steps: int | None = None):
     return {}, None
 
 
+def issue_roof(rep: str, env_steps_per_launch: int, env_steps_per_s: float, sm_mhz: float | None, n_sms: int = 148):
+    """Instruction-issue roofline of an issue-bound kernel (the Brax steps): warp instructions per env-step from the
+    newest committed ncu capture of `rep` (profiles/<tag>_traffic.json: smsp__inst_executed.sum per launch) against the
+    chip's issue rate, 4 schedulers per SM x one warp instruction per cycle at the SM clock sampled during the run.
+    None when no capture is committed. Never raises (the bench line must not depend on it)."""
+    try:
+        prof, f = measured_profile(rep)
+        wi = float(prof["warp_instructions_per_launch"]) / float(env_steps_per_launch)
+        mhz = float(sm_mhz) if sm_mhz else 1965.0
+        peak = n_sms * 4 * mhz * 1e6 / wi  # env-steps/s at one issued warp instruction per scheduler and cycle
+        return {"bound": "instruction issue", "warp_instructions_per_env_step": wi, "peak_env_steps_per_s": peak,
+                "frac": env_steps_per_s / peak, "sm_mhz": mhz,
+                "source": f"profiles/{f} [{rep}]: smsp__inst_executed.sum of one launch of {env_steps_per_launch} env-steps; "
+                          f"peak = {n_sms} SMs x 4 schedulers x SM clock / instructions per env-step"}
+    except Exception:
+        return None
+
+
 def measured_traffic(rep: str):
     p, f = measured_profile(rep)
     return (float(p["dram_bytes_per_launch"]) if "dram_bytes_per_launch" in p else None), f
@@ -1034,6 +1052,9 @@ def ant_leg(dev, peak, args, rank=0, world=1, barrier=None):
                      "achieved": (traj_bytes * T + step_bytes) * n / (launch_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                      "frac": (traj_bytes * T + step_bytes) * n / (launch_ms * 1e-3) / 1e9 / peak,
                      "frac_vs_step_contract_1114B": step_bytes * n * T / (launch_ms * 1e-3) / 1e9 / peak},
+        # the bound that matters for this kernel: instruction issue (per GPU; ncu instruction counts of the same launch)
+        "issue_roofline": issue_roof("prof_brax", n * T, fused / world, None),
+        "issue_roofline_fma": issue_roof("prof_brax_fma", n * T, fused_fma / world, None),
         "step_api": {"value": n_global / (api_ms * 1e-3), "us_per_launch": api_ms * 1e3,
                      "gather": "fused, sync (push + wait inside every step launch)" if distributed else None,
                      "hbm_frac_1114B": step_bytes * n / (api_ms * 1e-3) / 1e9 / peak},

@@ -67,3 +67,15 @@ def test_gpu_arm_prints_the_contract_line():
     # synchronous gym-style call beside the split-batch headline; float64 leg; what parity rests on
     assert d["e2e_sync"]["value"] > 0 and d["e2e"]["parts"] == 2 and d["value_f64"]["value"] > 0
     assert "unpinned" in d["parity"] and "pinned_by_published_known_answers" in d["parity"]
+
+
+def test_issue_roofline_helper_reads_the_committed_capture():
+    """bench.issue_roof: the Brax kernels are issue bound, so `ant_8192` reports warp instructions per env-step (ncu
+    capture committed under profiles/) against 148 SMs x 4 schedulers x the SM clock; it never raises."""
+    import bench
+
+    r = bench.issue_roof("prof_brax_fma", 8192 * 20, 1.6e8, 1965.0)
+    assert r is not None and 2000 < r["warp_instructions_per_env_step"] < 10000
+    assert r["peak_env_steps_per_s"] == pytest.approx(148 * 4 * 1965e6 / r["warp_instructions_per_env_step"])
+    assert 0.3 < r["frac"] < 1.0 and "profiles/" in r["source"]
+    assert bench.issue_roof("no_such_capture", 1, 1.0, None) is None
