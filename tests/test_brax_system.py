@@ -243,3 +243,117 @@ def test_pusher_table():
         m = bs.quat_to_mat(t[o + bs.L_JROT:o + bs.L_JROT + 4].astype(np.float64))
         np.testing.assert_allclose(m[:, 0], (0, 1, 0), atol=1e-6)
         np.testing.assert_allclose(m[:, 1], (1, 0, 0), atol=1e-6)
+
+
+def _axis_rot(axis, angle):
+    """Rodrigues rotation matrix about a (not necessarily unit) axis."""
+    a = np.asarray(axis, np.float64)
+    a = a / np.linalg.norm(a)
+    k = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    return np.eye(3) + np.sin(angle) * k + (1 - np.cos(angle)) * (k @ k)
+
+
+def _model_forward_kinematics(model, q):
+    """Link frames (origin, rotation matrix) straight from the MODEL description -- MJCF body positions / quats, joint
+    positions and the RAW joint axes, rotations composed in the order the MJCF stacks them -- in float64 numpy. It shares
+    nothing with the packed table (joint-frame quaternions, per-dof signs, Euler decomposition) nor with the C / CUDA
+    kinematics that consume it."""
+    frames, qi = [], 0
+    for l in model["links"]:
+        typ = l["type"]
+        if typ == bs.TYPE_FREE:
+            quat = q[qi + 3:qi + 7] / np.linalg.norm(q[qi + 3:qi + 7])
+            frames.append((q[qi:qi + 3].astype(np.float64), bs.quat_to_mat(quat)))
+            qi += 7
+            continue
+        ppos, prot = (np.zeros(3), np.eye(3)) if l["parent"] < 0 else frames[l["parent"]]
+        body_rot = bs.quat_to_mat(l["quat"])
+        trans, rot = np.zeros(3), np.eye(3)
+        if typ == bs.TYPE_HINGE:
+            rot = _axis_rot(l["axis"], q[qi]); nd = 1
+        elif typ == bs.TYPE_PLANAR:    # slide x, slide z, hinge about the given axis
+            trans = np.array([q[qi], 0.0, q[qi + 1]]); rot = _axis_rot(l["axis"], q[qi + 2]); nd = 3
+        elif typ == bs.TYPE_SLIDE:
+            trans = np.asarray(l["axis"], np.float64) * q[qi]; nd = 1
+        elif typ == bs.TYPE_SLIDE2:
+            second = l.get("axis2")
+            if second is None:
+                second = bs.quat_to_mat(bs.frame_with_x(l["axis"]))[:, 1]
+            trans = np.asarray(l["axis"], np.float64) * q[qi] + np.asarray(second, np.float64) * q[qi + 1]; nd = 2
+        else:                          # stacked hinges: successive rotations about the raw MJCF axes
+            nd = len(l["axis"])
+            for k in range(nd):
+                rot = rot @ _axis_rot(l["axis"][k], q[qi + k])
+        jp = np.asarray(l["joint_pos"], np.float64)
+        local = trans + (jp - rot @ jp)          # the joint position is the pivot of the rotation
+        pos = ppos + prot @ (np.asarray(l["pos"], np.float64) + body_rot @ local)
+        frames.append((pos, prot @ body_rot @ rot))
+        qi += nd
+    return frames
+
+
+@pytest.mark.parametrize("body", list(bs.MODELS))
+def test_table_kinematics_match_the_model_description(body):
+    """Independent check of everything the packed table encodes about kinematics (link transforms, joint frames built
+    from the MJCF axes, the sign of the hips' third coordinate, slide axes, centres of mass): the oracle's
+    pipeline_init on the TABLE against a float64 numpy forward kinematics on the MODEL, for random generalized
+    coordinates -- link rotation matrices to 2e-6, centre-of-mass positions to 2e-6."""
+    from oracle.brax import OracleBraxEnv
+    from tests.brax_util import random_q
+
+    model, sysd = bs.MODELS[body](), bs.SYSTEMS[body]
+    n, L = 32, sysd["n_links"]
+    rng = np.random.default_rng(7)
+    q, qd = random_q(sysd, n, rng, scale=4.0)
+    ctx = np.zeros((n, 5 + L), np.float32)
+    ctx[:, 5:] = np.asarray(sysd["stock_masses"], np.float32)
+    ora = OracleBraxEnv(sysd, ctx, f64=True)
+    ora.init_from_q(q, 0 * qd)
+    rows = ora.state[:, :13 * L].reshape(n, L, 13)
+    coms = [bs.body_inertia(l["geoms"], model["density"])[1] for l in model["links"]]
+    for e in range(n):
+        frames = _model_forward_kinematics(model, q[e].astype(np.float64))
+        for l in range(L):
+            pos, rot = frames[l]
+            np.testing.assert_allclose(bs.quat_to_mat(rows[e, l, 3:7]), rot, atol=2e-6, err_msg=f"{body} link {l} rotation")
+            np.testing.assert_allclose(rows[e, l, :3], pos + rot @ coms[l], atol=2e-6, err_msg=f"{body} link {l} COM")
+
+
+def _geom_quadrature(g, density, h=0.002):
+    """Mass, first and second moments of one geom by brute-force voxel integration (float64)."""
+    r = g["r"]
+    p0 = np.asarray(g["p0"], np.float64)
+    p1 = np.asarray(g.get("p1", g["p0"]), np.float64)
+    lo, hi = np.minimum(p0, p1) - r, np.maximum(p0, p1) + r
+    axes = [np.arange(lo[k] + h / 2, hi[k], h) for k in range(3)]
+    x, y, z = np.meshgrid(*axes, indexing="ij")
+    pts = np.stack([x.ravel(), y.ravel(), z.ravel()], axis=1)
+    ab = p1 - p0
+    t = np.zeros(len(pts)) if not ab.any() else np.clip(((pts - p0) @ ab) / (ab @ ab), 0, 1)
+    inside = np.linalg.norm(pts - (p0 + t[:, None] * ab), axis=1) <= r
+    pts = pts[inside]
+    dm = density * h ** 3
+    return dm * len(pts), dm * pts.sum(0), dm * (pts[:, :, None] * pts[:, None, :]).sum(0)
+
+
+@pytest.mark.parametrize("link", ["torso", "right_lower_arm", "left_thigh"])
+def test_inertia_from_geom_matches_brute_force_integration(link):
+    """MuJoCo's inertiafromgeom as restated in brax_system.body_inertia (capsule = cylinder + two half spheres, geoms
+    of a body add up, overlaps counted twice) against voxel integration of the same solids: mass and centre of mass
+    (which place every joint anchor and contact candidate relative to the link's COM state) and the principal
+    moments -- independent of the closed forms in the code. Composite and oblique geoms of the humanoid."""
+    geoms = bs.humanoid_geometry()[link]
+    m, com, irot, idiag = bs.body_inertia(geoms, 1000.0)
+    mass, first, second = 0.0, np.zeros(3), np.zeros((3, 3))
+    for g in geoms:
+        a, b, c = _geom_quadrature(g, 1000.0)
+        mass, first, second = mass + a, first + b, second + c
+    com_q = first / mass
+    # (2 mm voxels: the thin arm capsules, r = 31 mm, integrate to ~1 %; a missing hemisphere would be 10 %)
+    assert m == pytest.approx(mass, rel=2e-2)
+    np.testing.assert_allclose(com, com_q, atol=1e-3)
+    inertia_q = (np.trace(second) * np.eye(3) - second) - mass * (com_q @ com_q * np.eye(3) - np.outer(com_q, com_q))
+    np.testing.assert_allclose(np.sort(idiag), np.sort(np.linalg.eigvalsh(inertia_q)), rtol=4e-2)
+    # and the principal frame really diagonalises it
+    rot = bs.quat_to_mat(irot)
+    np.testing.assert_allclose(rot.T @ inertia_q @ rot, np.diag(idiag), atol=4e-2 * idiag.max())
