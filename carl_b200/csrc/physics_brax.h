@@ -711,6 +711,14 @@ CARLB_HD LinkState forward_link(const float* sys, const float* lt, const float* 
     xvel = vp + cross(wp, xpos - xp_pos) + rotate(tvel, xp_rot);
     xang = wp + rotate(axis * rate, xrot);
     if (stacked) xang = wp + rotate(rotate(wj, j_rot), qmul(xp_rot, t_rot));
+    if (j_pos.x != 0.0f || j_pos.y != 0.0f || j_pos.z != 0.0f) {
+      // a joint away from the link origin is the PIVOT of the rotation: the origin sits at pivot - R j_pos and is
+      // carried around the pivot at -w x (R j_pos), w = the joint's own angular rate in the link-transform frame
+      // (bodies whose joints sit at their link origins -- all but the humanoids' waist and knees -- never get here)
+      const V3 wl = stacked ? rotate(wj, j_rot) : axis * rate;
+      const V3 swing = v3(0, 0, 0) - cross(wl, rotate(j_pos, jrot));
+      xvel = xvel + rotate(rotate(swing, t_rot), xp_rot);
+    }
   }
   LinkState s;
   const V3 rc = rotate(ld3(lt + L_COM), xrot);

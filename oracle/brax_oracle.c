@@ -748,6 +748,17 @@ void NAME(brax_oracle_init)(const float *sys_f, int n, const float *q_all, const
           rot3(tmp2, xpt, tmp);
         }
         for (int k = 0; k < 3; ++k) xang[k] = wp[k] + tmp[k];
+        if (lt[lJPOS] != 0.0f || lt[lJPOS + 1] != 0.0f || lt[lJPOS + 2] != 0.0f) {
+          /* the joint position is the pivot of the rotation: the link origin (pivot - R j_pos) swings around it at
+           * -w x (R j_pos), w = the joint's own angular rate in the link-transform frame */
+          f3 wl = {axis[0] * rate, axis[1] * rate, axis[2] * rate}, sw, t3;
+          if (stacked) rot3(wj, lt + lJROT, wl);
+          cross3(wl, rj, sw);
+          for (int k = 0; k < 3; ++k) sw[k] = 0.0f - sw[k];
+          rot3(sw, lt + lTROT, t3);
+          rot3(t3, xprot, sw);
+          for (int k = 0; k < 3; ++k) xvel[k] += sw[k];
+        }
       }
       real *s = rows + 13 * l;
       f3 rc, w;

@@ -357,3 +357,57 @@ def test_inertia_from_geom_matches_brute_force_integration(link):
     # and the principal frame really diagonalises it
     rot = bs.quat_to_mat(irot)
     np.testing.assert_allclose(rot.T @ inertia_q @ rot, np.diag(idiag), atol=4e-2 * idiag.max())
+
+
+def _advance_q(model, q, qd, h):
+    """q moved by h along the generalized velocity qd (free roots: position by the linear velocity, orientation by the
+    LOCAL angular velocity, as brax's free joint defines its rates)."""
+    out, qi, di = q.astype(np.float64).copy(), 0, 0
+    for l in model["links"]:
+        if l["type"] == bs.TYPE_FREE:
+            out[qi:qi + 3] += h * qd[di:di + 3]
+            quat = out[qi + 3:qi + 7] / np.linalg.norm(out[qi + 3:qi + 7])
+            w = qd[di + 3:di + 6].astype(np.float64)
+            ang = np.linalg.norm(w) * h  # signed: h < 0 turns backwards
+            dq = np.array([1.0, 0, 0, 0]) if ang == 0 else np.concatenate([[np.cos(ang / 2)], np.sin(ang / 2) * w / np.linalg.norm(w)])
+            out[qi + 3:qi + 7] = bs.quat_mul(quat, dq)
+            qi, di = qi + 7, di + 6
+        else:
+            nd = bs.TYPE_DOFS[l["type"]][0]
+            out[qi:qi + nd] += h * qd[di:di + nd]
+            qi, di = qi + nd, di + nd
+    return out
+
+
+@pytest.mark.parametrize("body", list(bs.MODELS))
+def test_table_velocity_kinematics_match_finite_differences(body):
+    """The velocity half of pipeline_init (link COM velocities and angular velocities from qd: parent chains, joint
+    pivots, the stacked hinges' rate composition e_x, Rx e_y, Rx Ry e_z) against central finite differences of the
+    model-level forward kinematics above -- independent of the table and of the C / CUDA code."""
+    from oracle.brax import OracleBraxEnv
+    from tests.brax_util import random_q
+
+    model, sysd = bs.MODELS[body](), bs.SYSTEMS[body]
+    n, L = 8, sysd["n_links"]
+    rng = np.random.default_rng(8)
+    q, qd = random_q(sysd, n, rng, scale=4.0)
+    qd = (qd * 5).astype(np.float32)
+    ctx = np.zeros((n, 5 + L), np.float32)
+    ctx[:, 5:] = np.asarray(sysd["stock_masses"], np.float32)
+    ora = OracleBraxEnv(sysd, ctx, f64=True)
+    ora.init_from_q(q, qd)
+    rows = ora.state[:, :13 * L].reshape(n, L, 13)
+    coms = [bs.body_inertia(l["geoms"], model["density"])[1] for l in model["links"]]
+    h = 1e-5
+    for e in range(n):
+        qe = q[e].astype(np.float64)
+        if model["links"][0]["type"] == bs.TYPE_FREE:  # pipeline_init normalises the root quaternion
+            qe[3:7] /= np.linalg.norm(qe[3:7])
+        fp = _model_forward_kinematics(model, _advance_q(model, qe, qd[e], +h))
+        fm = _model_forward_kinematics(model, _advance_q(model, qe, qd[e], -h))
+        for l in range(L):
+            v = ((fp[l][0] + fp[l][1] @ coms[l]) - (fm[l][0] + fm[l][1] @ coms[l])) / (2 * h)
+            wx = (fp[l][1] @ fm[l][1].T - fm[l][1] @ fp[l][1].T) / (4 * h)
+            w = np.array([wx[2, 1], wx[0, 2], wx[1, 0]])
+            np.testing.assert_allclose(rows[e, l, 7:10], v, atol=2e-5, err_msg=f"{body} link {l} COM velocity")
+            np.testing.assert_allclose(rows[e, l, 10:13], w, atol=2e-5, err_msg=f"{body} link {l} angular velocity")
