@@ -377,6 +377,67 @@ def test_pusher_gripper_ball_contacts_match(hc):
     np.testing.assert_allclose(r_ref, want, rtol=1e-5, atol=1e-5)
 
 
+def test_pusher_matches_the_reference_notebooks_printed_step(hc):
+    """The one Brax step whose output the reference tree holds (examples/brax_with_goals.ipynb, cell 5: CARLBraxPusher,
+    spring backend, default context, `reset()` then ONE `step` with an unrecorded random action; extracted into
+    tests/golden/notebook_goldens.json by tools/extract_notebook_goldens.py). The action is unknown, so the joint part
+    cannot be replayed, but everything else the printout fixes must hold for the restatement:
+    * the layout f32[23] = q[:7], qd[:7], three positions; the goal at (0.45, -0.05, -0.323) and the object's height
+      -0.275 in the MJCF's world (the engine's shifted plane is subtracted again), exactly;
+    * the observed "tip" is the centre of mass of the wrist-flex link of the seven-link chain: (0.821, -0.6, 0) at the
+      initial pose -- the printout, one 0.05 s step later, is within 3e-4 of it;
+    * the object sits where brax.envs.pusher.reset can put it with OUR reading of the two slide coordinates (first
+      coordinate along y from U(-0.3, 0), second along x from U(-0.2, 0.2), at least 0.17 from the goal);
+    * the printed reward minus the two distance terms (taken before the step) leaves -0.1 |a|^2 with |a|^2 = 2.28,
+      inside what seven actions of the env's action space can give."""
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_goldens.json")))
+    ref = np.array(gold["pusher_obs_after_one_random_step"], np.float64)
+    reward = gold["pusher_reward_after_one_random_step"]
+    sysd = bs.SYSTEMS["pusher"]
+    assert ref.shape == (sysd["obs_dim"],)
+    dy, dx = ref[18] + 0.05, ref[17] - 0.45
+    assert -0.3 <= dy <= 0.0 and -0.2 <= dx <= 0.2 and np.hypot(dx, dy) >= 0.17
+    q = np.zeros((1, 11), np.float32)
+    q[0, 7], q[0, 8] = dy, dx
+    qd = np.zeros((1, 11), np.float32)
+    ctx = random_ctx(sysd, 1, np.random.default_rng(0), applied=False)
+    ora = OracleBraxEnv(sysd, ctx, autoreset=False, max_steps=0)
+    o_ora = ora.init_from_q(q, qd)[0]
+    _, o_hc = hc.init(sysd, q, qd, ctx)
+    for o in (o_ora, o_hc[0]):
+        np.testing.assert_allclose(o[17:23], ref[17:23], atol=2e-7)          # object and goal: exact
+        np.testing.assert_allclose(o[14:17], ref[14:17], atol=3e-4)          # tip: the printout is one step later
+        np.testing.assert_allclose(o[14:17], [0.821, -0.6, 0.0], atol=2e-6)
+    # the reward of brax.envs.pusher.step reads the positions before the step
+    dist = np.linalg.norm(ref[17:20] - ref[20:23])
+    near = np.linalg.norm(ref[17:20] - np.array([0.821, -0.6, 0.0]))
+    a_sq = (-reward - dist - 0.5 * near) / 0.1
+    assert a_sq == pytest.approx(2.278, abs=0.01) and 0.0 < a_sq < 7 * sysd["act_scale"] ** 2
+    # the same through our own step: zero action from this state gives exactly the two distance terms
+    _, r0, d0, _ = ora.step(np.zeros((1, 7), np.float32))
+    assert r0[0] == pytest.approx(-(dist + 0.5 * near), abs=2e-6) and not d0[0]
+
+
+def test_ant_initial_pose_matches_the_reference_notebooks_printed_observation():
+    """examples/brax_with_goals.ipynb, cell 3: CARLBraxAnt's observation f32[27] after reset() and one random step.
+    The reset noise is +-0.1 on q, so the printout pins the initial pose's PATTERN: torso height about 0.55, a
+    near-identity root quaternion first, then the eight joint angles around (0, 1, 0, -1, 0, -1, 0, 1) in this order."""
+    import json
+    import os
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "notebook_goldens.json")))
+    ref = np.array(gold["ant_obs_after_one_random_step"], np.float64)
+    sysd = bs.SYSTEMS["ant"]
+    assert ref.shape == (sysd["obs_dim"],)
+    init_q = sysd["table"][bs.OFF_INIT_Q:bs.OFF_INIT_Q + 15].astype(np.float64)
+    assert abs(ref[0] - init_q[2]) < 0.12                                    # z (x, y are excluded from the observation)
+    assert abs(np.linalg.norm(ref[1:5]) - 1.0) < 1e-5 and ref[1] > 0.98      # unit quaternion, w first
+    np.testing.assert_allclose(ref[5:13], init_q[7:15], atol=0.2)            # +-0.1 reset noise + one step of motion
+
+
 def _bar_and_ball():
     """A synthetic two-body system no shipped env has: a free-floating capsule and a free-floating ball (real masses,
     unit effective inertias), paired for body-vs-body contact, far above the ground, no gravity."""

@@ -58,6 +58,13 @@ def main():
     _, out = cell_text(nb, 3)
     arr = re.search(r"Array\(\[(.*?)\], dtype=float32\)", out, re.S).group(1)
     g["ant_obs_after_one_random_step"] = [float(x) for x in arr.replace("\n", " ").split(",")]
+    # cell 5: CARLBraxPusher (spring backend, default context) after reset() and ONE step with an unrecorded random
+    # action: the printed observation f32[23] and reward -- the only output of a Brax body's step in the reference tree
+    src, out = cell_text(nb, 5)
+    assert "env.step(action)" in src
+    arr = re.search(r"Array\(\[(.*?)\], dtype=float32\)", out, re.S).group(1)
+    g["pusher_obs_after_one_random_step"] = [float(x) for x in arr.replace("\n", " ").split(",")]
+    g["pusher_reward_after_one_random_step"] = float(re.search(r"\}\}\n(-?\d+\.\d+)", out).group(1))
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1)
     print("wrote", os.path.abspath(OUT), "keys:", list(g))
