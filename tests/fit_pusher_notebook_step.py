@@ -6,7 +6,7 @@ fixes |a|^2 = 2.278). This script fits the seven unknown actions (inner Gauss-Ne
 tunables (gear, constraint stiffness / velocity damping / limit stiffness / angular damping; outer differential
 evolution) of the oracle's pusher to the 14 printed joint numbers, for a given (spring_mass_scale, spring_inertia_scale):
 
-    python tools/fit_pusher_notebook_step.py 1 1        # unit effective masses and inertias (the shipped table)
+    python tests/fit_pusher_notebook_step.py 1 1        # unit effective masses and inertias (the shipped table)
 
 Result of the runs recorded in DESIGN.md (c): no hypothesis closes -- chi^2 = 183 (scales 1 / 1) and 153 (0 / 1) for 15
 data and 12 parameters at the noise scale of the reset (qd0 = U(+-0.005)), residuals up to 4e-3 rad on q and 0.06 rad/s
